@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — the Decoder hot path on B200: log lines/s and GB/s parsed, with roofline + CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W [--format rfc5424|ltsv|gelf] [--lines L] [--impl reference]
+
+A "step" is one pass of the parse kernel over one synthetic batch that is already resident in HBM
+(BASELINE.json configs[1]: 10 M RFC5424 lines, mean 180 B, per GPU).  `e2e` is the same metric through
+the reference-facing C-ABI call fg_decode_batch() with HOST buffers (pinned H2D + kernels + D2H inside
+the timed region).  For N>1 every rank owns one GPU and an independent shard of lines (weak scaling,
+no collective on the parse path); time is the max over ranks.  `--impl reference` times the CPU
+restatement of the reference decoders (oracle/) on the host cores for the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+FORMATS = {"rfc5424": 0, "ltsv": 1, "gelf": 2}
+SEEDS = {"rfc5424": 5424, "ltsv": 1757, "gelf": 0x6E1F}
+# generator parameter that lands the ACTUAL mean line length on the BASELINE.json shape
+GEN_MEAN = {"rfc5424": 171.0, "ltsv": 420.0, "gelf": 512.0}
+TARGET_MEAN = {"rfc5424": 180, "ltsv": 420, "gelf": 512}
+DEFAULT_LINES = {"rfc5424": 10_000_000, "ltsv": 4_000_000, "gelf": 3_500_000}  # int32 offsets cap a batch at 2 GiB
+
+
+def env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = REPO / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(fb, fmt_name: str, lines: int, rank: int):
+    fmt = FORMATS[fmt_name]
+    nthreads = min(os.cpu_count() or 8, 32)
+    data, offs = fb.generate(fmt, SEEDS[fmt_name], lines, first_index=rank * lines, mean_len=GEN_MEAN[fmt_name],
+                             bad_frac=0.005, nthreads=nthreads)
+    return data, offs
+
+
+def ltsv_kwargs(fmt_name: str) -> dict:
+    return {}
+
+
+def run_reference(args) -> None:
+    """CPU arm: the restated reference decoders (oracle/) on the host cores, same workload shape."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import flowgger_b200 as fb
+    sys.path.insert(0, str(REPO / "oracle"))
+    import pyoracle
+    fmt_name = args.format
+    fmt = FORMATS[fmt_name]
+    cores = os.cpu_count() or 1
+    sample = min(args.lines, 2_000_000)
+    data, offs = make_batch(fb, fmt_name, sample, 0)
+    nbytes = int(offs[-1])
+    for _ in range(max(args.warmup, 1)):
+        pyoracle.decode_bench(fmt, data, offs, None, nthreads=cores)
+    t = 0.0
+    for _ in range(args.steps):
+        s, _ok = pyoracle.decode_bench(fmt, data, offs, None, nthreads=cores)
+        t += s
+    ms = 1e3 * t / args.steps
+    value = sample / (t / args.steps)
+    line = {
+        "impl": "reference", "metric": "log lines/sec parsed (%s)" % fmt_name.upper(), "value": value, "unit": "lines/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "gb_per_s": nbytes / (t / args.steps) / 1e9,
+        "config": {"workload": workload_name(fmt_name, args.lines), "sample_lines": sample,
+                   "mean_line_bytes": round(nbytes / sample, 2)},
+        "cpu_baseline": {"value": value, "unit": "lines/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} lines of the same generator/seed, all {cores} host threads over contiguous line shards; "
+                                   "restated reference decoder (Rust toolchain unavailable), owned Record per line"},
+        "e2e": {"value": value, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(fmt_name: str, lines: int) -> str:
+    return f"{fmt_name.upper()} batch: {lines} synthetic lines per GPU, mean {TARGET_MEAN[fmt_name]} B (BASELINE.json configs[{ {'rfc5424': 1, 'gelf': 2, 'ltsv': 3}[fmt_name] }])"
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--format", default="rfc5424", choices=list(FORMATS))
+    ap.add_argument("--lines", type=int, default=0, help="lines per GPU (default: the BASELINE.json config)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.lines <= 0:
+        args.lines = DEFAULT_LINES[args.format]
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import flowgger_b200 as fb
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: flowgger_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    fmt_name = args.format
+    fmt = FORMATS[fmt_name]
+    data, offs = make_batch(fb, fmt_name, args.lines, rank)
+    n = args.lines
+    nbytes = int(offs[-1])
+    b_read = nbytes + 4 * (n + 1)  # algorithmic bytes per launch: every input byte + offset read once
+
+    dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nbytes + (1 << 20), max_batch_lines=n,
+                          chunk_lines=1 << 18, **ltsv_kwargs(fmt_name))
+    # pinned host arenas, as a batching splitter would fill them
+    h_bytes = dec.host_alloc(nbytes)
+    h_offs = dec.host_alloc(offs.nbytes, dtype=np.int32)
+    h_bytes[:] = data
+    h_offs[:] = offs
+    del data
+
+    # ---- device-resident: the kernel against the HBM roofline -------------------------------------
+    dec.upload(h_bytes, h_offs)
+    for _ in range(max(args.warmup, 3)):
+        dec.parse_resident()
+    launches0 = dec.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms = []
+    for _ in range(args.steps):
+        kernel_ms.append(dec.parse_resident())  # CUDA events around the launch on the launching stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = dec.kernel_launches() - launches0
+    wall = max_over_ranks(wall)
+    k_avg_ms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    total_lines = sum_over_ranks(float(n))
+    total_bytes = sum_over_ranks(float(nbytes))
+    ms_per_step = 1e3 * wall / args.steps
+    value = total_lines / (wall / args.steps)
+
+    res = dec.download()
+    n_err = int((res.status != 0).sum())
+    n_entries = res.n_entries
+    used_cols = 9 if fmt == 0 else 6
+    b_write = n * (12 + 8 * (used_cols - 2)) + n_entries * 17
+    d2h_bytes = b_write
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------
+    dec.decode(h_bytes, h_offs)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_kernel_ms = 0.0
+    for _ in range(args.e2e_steps):
+        r = dec.decode(h_bytes, h_offs)
+        e2e_kernel_ms += r.kernel_ms
+    barrier()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_lines / (e2e_wall / args.e2e_steps)
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, str(REPO / "oracle"))
+        import pyoracle
+        cores = os.cpu_count() or 1
+        sample = min(n, 2_000_000)
+        so = np.ascontiguousarray(h_offs[: sample + 1])
+        sb = h_bytes[: int(so[-1])]
+        pyoracle.decode_bench(fmt, sb, so, None, nthreads=cores)
+        s_all, _ = pyoracle.decode_bench(fmt, sb, so, None, nthreads=cores)
+        s_one, _ = pyoracle.decode_bench(fmt, sb[: int(so[sample // 8])], np.ascontiguousarray(so[: sample // 8 + 1]), None, nthreads=1)
+        cpu = {"value": sample / s_all, "unit": "lines/s", "cores": cores, "kind": "port",
+               "single_thread_lines_per_s": (sample // 8) / s_one,
+               "sample": f"first {sample} lines of the GPU batch, {cores} host threads over contiguous line shards "
+                         f"(+ {sample // 8} lines on 1 thread); restated reference decoder (oracle/, Rust toolchain unavailable)"}
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        achieved = (b_read / 1e9) / (k_avg_ms / 1e3)
+        traffic = None
+        tp = REPO / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(fmt_name)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "log lines/sec parsed (%s)" % fmt_name.upper(), "value": value, "unit": "lines/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "gb_per_s": total_bytes / (wall / args.steps) / 1e9,
+            "config": {"workload": workload_name(fmt_name, n), "lines_per_gpu": n, "bytes_per_gpu": nbytes,
+                       "mean_line_bytes": round(nbytes / n, 2), "error_rows": n_err, "sd_entries": n_entries,
+                       "parallelism": f"line shards x{world}, no collective",
+                       "l2": "input per step (%.2f GB) >> 126 MB L2, no flush needed" % (nbytes / 1e9)},
+            "kernel_ms": k_avg_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "of": peak_kind, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": b_read, "written_bytes_per_launch": b_write},
+            "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": b_read, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": args.e2e_steps, "gb_per_s": total_bytes / (e2e_wall / args.e2e_steps) / 1e9,
+                    "kernel_ms_per_step": e2e_kernel_ms / args.e2e_steps, "api": "fg_decode_batch (pinned host buffers)"},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    dec.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

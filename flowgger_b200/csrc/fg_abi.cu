@@ -1,0 +1,598 @@
+// fg_abi.cu — the C ABI declared in include/flowgger_cuda.h.
+//
+// Host side of the drop-in boundary: owns the device buffers, pinned host
+// result arrays and streams of one context, pipelines host<->device copies
+// with the parse kernels chunk by chunk, and exposes the device-resident
+// variant used for roofline measurement.  There is no CPU parsing anywhere in
+// this file: if CUDA is unavailable every entry point returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/flowgger_cuda.h"
+#include "fg_kernels.cuh"
+#include "fg_status.h"
+
+namespace {
+
+// The reference's `&'static str` for every status (file:line in /root/reference/src/flowgger/decoder/)
+const char* kErrorStrings[FG_ST_COUNT] = {};
+struct ErrorTableInit {
+    ErrorTableInit() {
+        auto& t = kErrorStrings;
+        t[FG_E5_BOM] = "Unsupported BOM";                                        // rfc5424_decoder.rs:69
+        t[FG_E5_PRI_BRACKETS] = "The priority should be inside brackets";         // :76
+        t[FG_E5_INVALID_PRI] = "Invalid priority";                                // :83
+        t[FG_E5_MISSING_VERSION] = "Missing version";                             // :84
+        t[FG_E5_UNSUPPORTED_VERSION] = "Unsupported version";                     // :86
+        t[FG_E5_MISSING_TS] = "Missing timestamp";                                // :25
+        t[FG_E5_BAD_TS] = "Unable to parse the date from RFC3339 to Unix time in RFC5424 decoder";  // :97
+        t[FG_E5_MISSING_HOST] = "Missing hostname";                               // :26
+        t[FG_E5_MISSING_APP] = "Missing application name";                        // :27
+        t[FG_E5_MISSING_PROCID] = "Missing process id";                           // :28
+        t[FG_E5_MISSING_MSGID] = "Missing message id";                            // :29
+        t[FG_E5_MISSING_DATA] = "Missing message data";                           // :30
+        t[FG_E5_MISSING_MSG] = "Missing log message";                             // :129,:148
+        t[FG_E5_MALFORMED] = "Malformated RFC5424 message";                       // :154,:159
+        t[FG_E5_MISSING_SD] = "Missing structured data";                          // :177
+        t[FG_E5_SD_FORMAT] = "Format error in the structured data";               // :235
+        t[FG_E5_SD_NO_END] = "Missing ] after structured data";                   // :239
+        t[FG_E5_MISSING_PRI_VERSION] = "Missing priority and version";            // :24 (unreachable)
+        t[FG_E5_EMPTY_PRI] = "Empty priority";                                    // :81 (unreachable)
+        t[FG_E5_MISSING_SD_ID] = "Missing structured data id";                    // :176 (unreachable)
+        t[FG_EL_TS] = "Unable to parse the English to Unix timestamp in LTSV decoder";  // ltsv_decoder.rs:252
+        t[FG_EL_SEV] = "Invalid severity level";                                  // :116
+        t[FG_EL_SEV_HIGH] = "Severity level should be <= 7";                      // :118
+        t[FG_EL_BOOL] = "Type error; boolean was expected";                       // :143
+        t[FG_EL_F64] = "Type error; f64 was expected";                            // :159
+        t[FG_EL_I64] = "Type error; i64 was expected";                            // :175
+        t[FG_EL_U64] = "Type error; u64 was expected";                            // :191
+        t[FG_EL_MISSING_TS] = "Missing timestamp";                                // :205
+        t[FG_EL_MISSING_HOST] = "Missing hostname";                               // :206
+        t[FG_EG_JSON] = "Invalid GELF input, unable to parse as a JSON object";   // gelf_decoder.rs:49
+        t[FG_EG_EMPTY] = "Empty GELF input";                                      // :50
+        t[FG_EG_TS] = "Invalid GELF timestamp";                                   // :53
+        t[FG_EG_HOST] = "GELF host name must be a string";                        // :58
+        t[FG_EG_SHORT] = "GELF short message must be a string";                   // :66
+        t[FG_EG_FULL] = "GELF full message must be a string";                     // :74
+        t[FG_EG_VERSION_T] = "GELF version must be a string";                     // :78
+        t[FG_EG_VERSION] = "Unsupported GELF version";                            // :80
+        t[FG_EG_SEV] = "Invalid severity level";                                  // :83
+        t[FG_EG_SEV_HIGH] = "Invalid severity level (too high)";                  // :85
+        t[FG_EG_SD_TYPE] = "Invalid value type in structured data";               // :97
+        t[FG_EG_MISSING_HOST] = "Missing hostname";                               // :110
+    }
+} g_error_table_init;
+
+constexpr size_t kPad = 256;            // slack after the device byte buffer (16-byte bulk-copy granules)
+constexpr size_t kBounceBytes = 32u << 20;  // pinned bounce buffers for pageable caller memory
+constexpr size_t kL2FlushBytes = 256u << 20;
+
+}  // namespace
+
+struct fg_ctx {
+    int device = 0;
+    size_t max_bytes = 0;
+    int max_lines = 0;
+    int chunk_lines = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // device
+    uint8_t* d_bytes = nullptr;
+    int32_t* d_offsets = nullptr;
+    uint8_t* d_rows = nullptr;  // 9 columns, each sized for max_lines
+    int2* d_entry_name = nullptr;
+    unsigned long long* d_entry_val = nullptr;
+    uint8_t* d_entry_meta = nullptr;
+    uint32_t* d_counter = nullptr;
+    uint8_t* d_flush = nullptr;
+    size_t entry_cap = 0;
+    // LTSV config blobs
+    uint8_t* d_ltsv_blob = nullptr;
+    fg::LtsvDeviceConfig ltsv{};
+    // pinned host
+    uint8_t* h_rows = nullptr;
+    fg_span* h_entry_name = nullptr;
+    uint64_t* h_entry_val = nullptr;
+    uint8_t* h_entry_meta = nullptr;
+    uint32_t* h_counts = nullptr;  // per-chunk running entry totals
+    int h_counts_cap = 0;
+    uint8_t* h_bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_h2d, ev_k0, ev_k1;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // resident batch
+    int res_n = 0;
+    size_t res_bytes = 0;
+    int res_tile = 0;
+    int res_fmt = -1;
+    uint32_t res_entries = 0;
+    std::string last_error;
+    int64_t launches = 0;
+    int max_tile = 0;
+};
+
+namespace {
+
+size_t col_off(const fg_ctx* c, int col) {
+    // ts(8) meta(4) host app proc msgid msg full sd (8 each)
+    const size_t n = (size_t)c->max_lines;
+    static const int w[9] = {8, 4, 8, 8, 8, 8, 8, 8, 8};
+    size_t o = 0;
+    for (int k = 0; k < col; ++k) o += (size_t)w[k] * n;
+    return o;
+}
+constexpr int kColW[9] = {8, 4, 8, 8, 8, 8, 8, 8, 8};
+enum { C_TS = 0, C_META, C_HOST, C_APP, C_PROC, C_MSGID, C_MSG, C_FULL, C_SD, C_COUNT };
+
+int fail(fg_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->last_error = what;
+        if (e != cudaSuccess) {
+            c->last_error += ": ";
+            c->last_error += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define FG_CUDA(ctx, call)                                         \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return fail(ctx, FG_E_CUDA, #call, _e); \
+    } while (0)
+
+void free_entries(fg_ctx* c) {
+    if (c->d_entry_name) cudaFree(c->d_entry_name);
+    if (c->d_entry_val) cudaFree(c->d_entry_val);
+    if (c->d_entry_meta) cudaFree(c->d_entry_meta);
+    if (c->h_entry_name) cudaFreeHost(c->h_entry_name);
+    if (c->h_entry_val) cudaFreeHost(c->h_entry_val);
+    if (c->h_entry_meta) cudaFreeHost(c->h_entry_meta);
+    c->d_entry_name = nullptr;
+    c->d_entry_val = nullptr;
+    c->d_entry_meta = nullptr;
+    c->h_entry_name = nullptr;
+    c->h_entry_val = nullptr;
+    c->h_entry_meta = nullptr;
+}
+
+int alloc_entries(fg_ctx* c, size_t cap) {
+    free_entries(c);
+    cap = (cap + 255) & ~(size_t)255;
+    FG_CUDA(c, cudaMalloc(&c->d_entry_name, cap * sizeof(int2)));
+    FG_CUDA(c, cudaMalloc(&c->d_entry_val, cap * sizeof(unsigned long long)));
+    FG_CUDA(c, cudaMalloc(&c->d_entry_meta, cap));
+    FG_CUDA(c, cudaHostAlloc(&c->h_entry_name, cap * sizeof(fg_span), cudaHostAllocDefault));
+    FG_CUDA(c, cudaHostAlloc(&c->h_entry_val, cap * sizeof(uint64_t), cudaHostAllocDefault));
+    FG_CUDA(c, cudaHostAlloc(&c->h_entry_meta, cap, cudaHostAllocDefault));
+    c->entry_cap = cap;
+    return FG_OK;
+}
+
+// shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles
+// whatever does not fit in extra rounds
+int pick_tile(const fg_ctx* c, size_t total_bytes, int n) {
+    double mean = n > 0 ? (double)total_bytes / n : 0.0;
+    long t = (long)(mean * fg::kLinesPerCta * 1.20) + 2048;
+    t = (t + 1023) & ~1023L;
+    t = std::max(t, 8L * 1024);
+    t = std::min(t, (long)c->max_tile);
+    return (int)t;
+}
+
+void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
+    P.bytes = c->d_bytes;
+    P.offsets = c->d_offsets + line0;
+    P.n = n;
+    P.tile_bytes = tile;
+    uint8_t* r = c->d_rows;
+    P.ts = (double*)(r + col_off(c, C_TS)) + line0;
+    P.meta = (uint32_t*)(r + col_off(c, C_META)) + line0;
+    P.host = (int2*)(r + col_off(c, C_HOST)) + line0;
+    P.app = (int2*)(r + col_off(c, C_APP)) + line0;
+    P.proc = (int2*)(r + col_off(c, C_PROC)) + line0;
+    P.msgid = (int2*)(r + col_off(c, C_MSGID)) + line0;
+    P.msg = (int2*)(r + col_off(c, C_MSG)) + line0;
+    P.full = (int2*)(r + col_off(c, C_FULL)) + line0;
+    P.sd = (int2*)(r + col_off(c, C_SD)) + line0;
+    P.entry_name = c->d_entry_name;
+    P.entry_val = c->d_entry_val;
+    P.entry_meta = c->d_entry_meta;
+    P.entry_counter = c->d_counter;
+    P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
+    P.ltsv = c->ltsv;
+}
+
+bool col_used(int fmt, int col) {
+    if (fmt == FG_FMT_RFC5424) return true;
+    return !(col == C_APP || col == C_PROC || col == C_MSGID);
+}
+
+void fill_out(fg_ctx* c, int fmt, int n, uint32_t n_entries, fg_batch_out* out) {
+    uint8_t* r = c->h_rows;
+    out->n = n;
+    out->n_entries = (int32_t)n_entries;
+    out->ts = (const double*)(r + col_off(c, C_TS));
+    out->meta = (const uint32_t*)(r + col_off(c, C_META));
+    out->hostname = (const fg_span*)(r + col_off(c, C_HOST));
+    const bool r5 = fmt == FG_FMT_RFC5424;
+    out->appname = r5 ? (const fg_span*)(r + col_off(c, C_APP)) : nullptr;
+    out->procid = r5 ? (const fg_span*)(r + col_off(c, C_PROC)) : nullptr;
+    out->msgid = r5 ? (const fg_span*)(r + col_off(c, C_MSGID)) : nullptr;
+    out->msg = (const fg_span*)(r + col_off(c, C_MSG));
+    out->full_msg = (const fg_span*)(r + col_off(c, C_FULL));
+    out->sd = (const fg_span*)(r + col_off(c, C_SD));
+    out->entry_name = c->h_entry_name;
+    out->entry_val = c->h_entry_val;
+    out->entry_meta = c->h_entry_meta;
+}
+
+int copy_rows_d2h(fg_ctx* c, int fmt, int line0, int n, cudaStream_t s) {
+    for (int col = 0; col < C_COUNT; ++col) {
+        if (!col_used(fmt, col)) continue;
+        const size_t o = col_off(c, col) + (size_t)line0 * kColW[col];
+        FG_CUDA(c, cudaMemcpyAsync(c->h_rows + o, c->d_rows + o, (size_t)n * kColW[col], cudaMemcpyDeviceToHost, s));
+    }
+    return FG_OK;
+}
+
+int copy_entries_d2h(fg_ctx* c, size_t from, size_t to, cudaStream_t s) {
+    if (to <= from) return FG_OK;
+    const size_t k = to - from;
+    FG_CUDA(c, cudaMemcpyAsync(c->h_entry_name + from, c->d_entry_name + from, k * sizeof(int2), cudaMemcpyDeviceToHost, s));
+    FG_CUDA(c, cudaMemcpyAsync(c->h_entry_val + from, c->d_entry_val + from, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    FG_CUDA(c, cudaMemcpyAsync(c->h_entry_meta + from, c->d_entry_meta + from, k, cudaMemcpyDeviceToHost, s));
+    return FG_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// H2D of an arbitrary host range: direct DMA when pinned, else through two pinned bounce buffers
+int h2d(fg_ctx* c, void* dst, const void* src, size_t bytes, bool pinned, int& bounce_ix) {
+    if (!bytes) return FG_OK;
+    if (pinned) {
+        FG_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+        return FG_OK;
+    }
+    size_t done = 0;
+    while (done < bytes) {
+        const size_t k = std::min(kBounceBytes, bytes - done);
+        const int b = bounce_ix & 1;
+        FG_CUDA(c, cudaEventSynchronize(c->bounce_ev[b]));
+        memcpy(c->h_bounce[b], (const uint8_t*)src + done, k);
+        FG_CUDA(c, cudaMemcpyAsync((uint8_t*)dst + done, c->h_bounce[b], k, cudaMemcpyHostToDevice, c->s_h2d));
+        FG_CUDA(c, cudaEventRecord(c->bounce_ev[b], c->s_h2d));
+        done += k;
+        ++bounce_ix;
+    }
+    return FG_OK;
+}
+
+int ensure_events(fg_ctx* c, int chunks) {
+    while ((int)c->ev_h2d.size() < chunks) {
+        cudaEvent_t a, b, d;
+        FG_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FG_CUDA(c, cudaEventCreate(&b));
+        FG_CUDA(c, cudaEventCreate(&d));
+        c->ev_h2d.push_back(a);
+        c->ev_k0.push_back(b);
+        c->ev_k1.push_back(d);
+    }
+    if (c->h_counts_cap < chunks) {
+        if (c->h_counts) cudaFreeHost(c->h_counts);
+        FG_CUDA(c, cudaHostAlloc(&c->h_counts, sizeof(uint32_t) * (size_t)chunks, cudaHostAllocDefault));
+        c->h_counts_cap = chunks;
+    }
+    return FG_OK;
+}
+
+int check_batch(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {
+    if (!c) return FG_E_ARG;
+    if (n < 0 || (n > 0 && (!bytes || !offsets))) return fail(c, FG_E_ARG, "null input");
+    if (n > c->max_lines) return fail(c, FG_E_CAPACITY, "batch has more lines than max_batch_lines");
+    if (n > 0) {
+        if (offsets[0] < 0 || offsets[n] < offsets[0]) return fail(c, FG_E_ARG, "offsets must be non-negative and monotone");
+        if ((size_t)offsets[n] > c->max_bytes) return fail(c, FG_E_CAPACITY, "batch has more bytes than max_batch_bytes");
+    }
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fg_create(const fg_config* cfg, fg_ctx** out) {
+    if (!out) return FG_E_ARG;
+    *out = nullptr;
+    fg_config def{};
+    if (!cfg) cfg = &def;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return FG_E_NO_DEVICE;  // no CPU fallback: the decoder does not exist without a GPU
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return FG_E_ARG;
+    fg_ctx* c = new (std::nothrow) fg_ctx();
+    if (!c) return FG_E_ARG;
+    c->device = cfg->device;
+    c->max_bytes = cfg->max_batch_bytes > 0 ? (size_t)cfg->max_batch_bytes : ((size_t)256 << 20);
+    if (c->max_bytes > 0x7FFFFFC0ull) c->max_bytes = 0x7FFFFFC0ull;  // int32 offsets
+    c->max_lines = cfg->max_batch_lines > 0 ? cfg->max_batch_lines : (2 << 20);
+    c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (256 << 10);
+    c->chunk_lines = (c->chunk_lines + fg::kLinesPerCta - 1) / fg::kLinesPerCta * fg::kLinesPerCta;
+#define FG_CREATE_CUDA(call)                                  \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) {                              \
+            fprintf(stderr, "flowgger_cuda: %s failed: %s\n", #call, cudaGetErrorString(_e)); \
+            fg_destroy(c);                                    \
+            return FG_E_CUDA;                                 \
+        }                                                     \
+    } while (0)
+    FG_CREATE_CUDA(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    FG_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    c->max_tile = (int)std::min<size_t>(prop.sharedMemPerBlockOptin - 1024, 200 * 1024);
+    c->max_tile &= ~1023;
+    FG_CREATE_CUDA(fg::configure_kernels(c->max_tile));
+    FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    FG_CREATE_CUDA(cudaEventCreate(&c->ev_a));
+    FG_CREATE_CUDA(cudaEventCreate(&c->ev_b));
+    FG_CREATE_CUDA(cudaMalloc(&c->d_bytes, c->max_bytes + kPad));
+    FG_CREATE_CUDA(cudaMemset(c->d_bytes + c->max_bytes, 0, kPad));
+    FG_CREATE_CUDA(cudaMalloc(&c->d_offsets, sizeof(int32_t) * ((size_t)c->max_lines + 1)));
+    const size_t rows_bytes = col_off(c, C_COUNT);
+    FG_CREATE_CUDA(cudaMalloc(&c->d_rows, rows_bytes));
+    FG_CREATE_CUDA(cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
+    FG_CREATE_CUDA(cudaMalloc(&c->d_counter, 256));
+    FG_CREATE_CUDA(cudaMemset(c->d_counter, 0, 256));
+    for (int b = 0; b < 2; ++b) {
+        FG_CREATE_CUDA(cudaHostAlloc(&c->h_bounce[b], kBounceBytes, cudaHostAllocDefault));
+        FG_CREATE_CUDA(cudaEventCreateWithFlags(&c->bounce_ev[b], cudaEventDisableTiming));
+    }
+    if (alloc_entries(c, std::max<size_t>(c->max_bytes / 24, 4096)) != FG_OK) {
+        fprintf(stderr, "flowgger_cuda: %s\n", c->last_error.c_str());
+        fg_destroy(c);
+        return FG_E_CUDA;
+    }
+    // LTSV schema / suffixes -> one device blob
+    {
+        std::vector<uint8_t> names, suffix;
+        std::vector<int32_t> name_off{0}, types;
+        const int ns = (cfg->ltsv_schema_names && cfg->ltsv_schema_types) ? cfg->ltsv_schema_len : 0;
+        for (int k = 0; k < ns; ++k) {
+            const char* s = cfg->ltsv_schema_names[k];
+            names.insert(names.end(), (const uint8_t*)s, (const uint8_t*)s + strlen(s));
+            name_off.push_back((int32_t)names.size());
+            types.push_back(cfg->ltsv_schema_types[k]);
+        }
+        fg::LtsvDeviceConfig& L = c->ltsv;
+        L.has_schema = (cfg->ltsv_has_schema || ns > 0) ? 1 : 0;
+        L.n_schema = ns;
+        L.suffix_present = 0;
+        L.suffix_off[0] = 0;
+        for (int t = 0; t < 5; ++t) {
+            const char* s = cfg->ltsv_suffix[t];
+            if (t > 0 && s) {
+                L.suffix_present |= 1u << t;
+                suffix.insert(suffix.end(), (const uint8_t*)s, (const uint8_t*)s + strlen(s));
+            }
+            L.suffix_off[t + 1] = (int32_t)suffix.size();
+        }
+        const size_t o_names = 0, o_off = (names.size() + 15) & ~(size_t)15;
+        const size_t o_types = o_off + ((name_off.size() * 4 + 15) & ~(size_t)15);
+        const size_t o_suf = o_types + ((types.size() * 4 + 15) & ~(size_t)15);
+        const size_t total = o_suf + suffix.size() + 16;
+        std::vector<uint8_t> blob(total, 0);
+        if (!names.empty()) memcpy(blob.data() + o_names, names.data(), names.size());
+        memcpy(blob.data() + o_off, name_off.data(), name_off.size() * 4);
+        if (!types.empty()) memcpy(blob.data() + o_types, types.data(), types.size() * 4);
+        if (!suffix.empty()) memcpy(blob.data() + o_suf, suffix.data(), suffix.size());
+        FG_CREATE_CUDA(cudaMalloc(&c->d_ltsv_blob, total));
+        FG_CREATE_CUDA(cudaMemcpy(c->d_ltsv_blob, blob.data(), total, cudaMemcpyHostToDevice));
+        L.names = c->d_ltsv_blob + o_names;
+        L.name_off = (const int32_t*)(c->d_ltsv_blob + o_off);
+        L.types = (const int32_t*)(c->d_ltsv_blob + o_types);
+        L.suffix = c->d_ltsv_blob + o_suf;
+    }
+#undef FG_CREATE_CUDA
+    *out = c;
+    return FG_OK;
+}
+
+void fg_destroy(fg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_entries(c);
+    if (c->d_bytes) cudaFree(c->d_bytes);
+    if (c->d_offsets) cudaFree(c->d_offsets);
+    if (c->d_rows) cudaFree(c->d_rows);
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_flush) cudaFree(c->d_flush);
+    if (c->d_ltsv_blob) cudaFree(c->d_ltsv_blob);
+    if (c->h_rows) cudaFreeHost(c->h_rows);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    for (int b = 0; b < 2; ++b) {
+        if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
+        if (c->bounce_ev[b]) cudaEventDestroy(c->bounce_ev[b]);
+    }
+    for (auto e : c->ev_h2d) cudaEventDestroy(e);
+    for (auto e : c->ev_k0) cudaEventDestroy(e);
+    for (auto e : c->ev_k1) cudaEventDestroy(e);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+const char* fg_last_error(const fg_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+
+int fg_host_alloc(fg_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return FG_E_ARG;
+    FG_CUDA(c, cudaSetDevice(c->device));
+    FG_CUDA(c, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FG_OK;
+}
+void fg_host_free(fg_ctx* c, void* p) {
+    if (c && p) cudaFreeHost(p);
+}
+
+int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                    fg_batch_out* out) {
+    if (!c || !out) return FG_E_ARG;
+    if (int rc = check_batch(c, bytes, offsets, n)) return rc;
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    if (n == 0) {
+        fill_out(c, fmt, 0, 0, out);
+        return FG_OK;
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    const bool pin_b = is_pinned(bytes), pin_o = is_pinned(offsets);
+    const int C = c->chunk_lines;
+    const int chunks = (n + C - 1) / C;
+    if (int rc = ensure_events(c, chunks)) return rc;
+    const int tile = pick_tile(c, (size_t)(offsets[n] - offsets[0]), n);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        int bounce_ix = 0;
+        for (int k = 0; k < chunks; ++k) {
+            const int l0 = k * C, l1 = std::min(n, l0 + C);
+            const size_t b0 = (size_t)offsets[l0], b1 = (size_t)offsets[l1];
+            if (int rc = h2d(c, c->d_bytes + b0, bytes + b0, b1 - b0, pin_b, bounce_ix)) return rc;
+            if (int rc = h2d(c, c->d_offsets + l0, offsets + l0, sizeof(int32_t) * (size_t)(l1 - l0 + 1), pin_o, bounce_ix))
+                return rc;
+            FG_CUDA(c, cudaEventRecord(c->ev_h2d[k], c->s_h2d));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[k], 0));
+            fg::ParseParams P;
+            fill_params(c, P, l0, l1 - l0, tile);
+            FG_CUDA(c, cudaEventRecord(c->ev_k0[k], c->s_comp));
+            FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
+            ++c->launches;
+            FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_counts + k, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+            FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_a, 0));
+            if (int rc = copy_rows_d2h(c, fmt, l0, l1 - l0, c->s_d2h)) return rc;
+        }
+        // side table: every chunk's rows are a contiguous range of the bump allocator
+        FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+        const uint32_t total = c->h_counts[chunks - 1];
+        if ((size_t)total > c->entry_cap) {
+            // the allocator kept counting past the capacity: grow once to the exact need and redo
+            FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+            continue;
+        }
+        if (int rc = copy_entries_d2h(c, 0, total, c->s_d2h)) return rc;
+        FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+        float kms = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            float ms = 0.f;
+            FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_k0[k], c->ev_k1[k]));
+            kms += ms;
+        }
+        fill_out(c, fmt, n, total, out);
+        out->kernel_ms = kms;
+        out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        return FG_OK;
+    }
+    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+}
+
+int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {
+    if (int rc = check_batch(c, bytes, offsets, n)) return rc;
+    FG_CUDA(c, cudaSetDevice(c->device));
+    if (n > 0) {
+        const size_t b0 = (size_t)offsets[0], b1 = (size_t)offsets[n];
+        FG_CUDA(c, cudaMemcpy(c->d_bytes + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice));
+        FG_CUDA(c, cudaMemcpy(c->d_offsets, offsets, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+        c->res_bytes = b1 - b0;
+    } else {
+        c->res_bytes = 0;
+    }
+    c->res_n = n;
+    c->res_tile = pick_tile(c, c->res_bytes, n);
+    c->res_fmt = -1;
+    return FG_OK;
+}
+
+int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
+    if (!c) return FG_E_ARG;
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        fg::ParseParams P;
+        fill_params(c, P, 0, c->res_n, c->res_tile);
+        FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
+        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
+        ++c->launches;
+        FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
+        uint32_t total = 0;
+        FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+        FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+        if ((size_t)total > c->entry_cap) {
+            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+            continue;
+        }
+        float ms = 0.f;
+        FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+        if (kernel_ms) *kernel_ms = ms;
+        c->res_fmt = (int)fmt;
+        c->res_entries = total;
+        return FG_OK;
+    }
+    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+}
+
+int fg_download(fg_ctx* c, fg_format fmt, fg_batch_out* out) {
+    if (!c || !out) return FG_E_ARG;
+    if (c->res_fmt != (int)fmt) return fail(c, FG_E_ARG, "no resident parse of this format to download");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    if (int rc = copy_rows_d2h(c, fmt, 0, c->res_n, c->s_d2h)) return rc;
+    if (int rc = copy_entries_d2h(c, 0, c->res_entries, c->s_d2h)) return rc;
+    FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+    fill_out(c, fmt, c->res_n, c->res_entries, out);
+    return FG_OK;
+}
+
+int fg_flush_l2(fg_ctx* c) {
+    if (!c) return FG_E_ARG;
+    FG_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_flush) FG_CUDA(c, cudaMalloc(&c->d_flush, kL2FlushBytes));
+    FG_CUDA(c, cudaMemsetAsync(c->d_flush, 0x5A, kL2FlushBytes, c->s_comp));
+    FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+    return FG_OK;
+}
+
+const char* fg_error_string(fg_format, uint32_t status) {
+    if (status == 0 || status >= FG_ST_COUNT) return nullptr;
+    return kErrorStrings[status];
+}
+uint32_t fg_error_count(void) { return FG_ST_COUNT; }
+
+const char* fg_build_info(void) { return fg::kernel_build_info(); }
+int64_t fg_kernel_launches(const fg_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

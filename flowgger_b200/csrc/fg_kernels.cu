@@ -1,0 +1,181 @@
+// fg_kernels.cu — the batched parse kernels (sm_100a).
+//
+// Execution model:
+//   * one CTA = kLinesPerCta consecutive lines; the CTA's contiguous byte span
+//     [offsets[first] & ~15, offsets[first+r]) is staged into shared memory with
+//     ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier,
+//     so HBM is read once, fully coalesced, with no per-thread load instructions;
+//   * one thread = one line: it walks its bytes in shared memory with the
+//     format's sequential state machine and produces the Record fields;
+//   * the variable-length structured-data rows are placed by a CTA-wide scan of
+//     per-line counts plus ONE global atomic per CTA, then emitted by a second
+//     walk over the (still resident) shared-memory bytes;
+//   * the fixed-width row columns are written SoA, i.e. fully coalesced.
+// Spans whose bytes do not fit the tile are handled in several rounds; a single
+// line longer than the tile is parsed straight from global memory.
+#include "fg_kernels.cuh"
+
+#include "fg_common.cuh"
+#include "fg_rfc5424.cuh"
+#include "fg_status.h"
+
+namespace fg {
+
+FG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+FG_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+FG_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FG_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy through the TMA unit (1-D, 16-byte granules)
+FG_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+FG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int FMT>
+struct Format;
+
+template <>
+struct Format<0> {  // RFC5424
+    static FG_DEV void parse(bytes_t p, int len, LineResult& r, const ParseParams&) { rfc5424_parse_line(p, len, r); }
+    static FG_DEV void emit(bytes_t p, int len, int line_off, const LineResult& r, const EntrySink& s, uint32_t ebase,
+                            const ParseParams&) {
+        rfc5424_emit(p, len, line_off, r, s, ebase);
+    }
+};
+
+// out-of-line copies for the rare "line longer than the tile" path (generic loads from global)
+template <int FMT>
+__device__ __noinline__ void parse_from_global(const uint8_t* p, int len, LineResult& r, const ParseParams& P) {
+    Format<FMT>::parse(p, len, r, P);
+}
+template <int FMT>
+__device__ __noinline__ void emit_from_global(const uint8_t* p, int len, int line_off, const LineResult& r,
+                                              const EntrySink& s, uint32_t ebase, const ParseParams& P) {
+    Format<FMT>::emit(p, len, line_off, r, s, ebase, P);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_constant__ ParseParams P) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t scan_ws[33];
+    __shared__ uint32_t s_ebase;
+
+    const int tid = threadIdx.x;
+    const int first = blockIdx.x * kLinesPerCta;
+    const int last = min(P.n, first + kLinesPerCta);
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+
+    const EntrySink sink = {P.entry_name, P.entry_val, P.entry_meta};
+    uint32_t parity = 0;
+    int cur = first;
+    while (cur < last) {
+        const int i = cur + tid;
+        const int o0 = __ldg(P.offsets + min(i, last));
+        const int o1 = __ldg(P.offsets + min(i + 1, last));
+        const int ocur = __ldg(P.offsets + cur);
+        const int base = ocur & ~15;
+        const bool fits = (i < last) && (o1 - base <= P.tile_bytes);
+        int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
+        const bool direct = (r == 0);       // first pending line alone exceeds the tile
+        if (direct) {
+            r = 1;
+        } else {
+            if (tid == 0) {
+                const int oend = __ldg(P.offsets + cur + r);
+                const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
+                fence_proxy_async();  // generic-proxy reads of the previous round happen-before this async write
+                mbar_expect_tx(&mbar, nbytes);
+                bulk_g2s(tile, P.bytes + base, nbytes, &mbar);
+            }
+            mbar_wait(&mbar, parity);
+            parity ^= 1u;
+        }
+        const bool active = tid < r;
+        const int len = o1 - o0;
+        LineResult res;
+        res.n_entries = 0;
+        if (active) {
+            if (!direct) Format<FMT>::parse(tile + (o0 - base), len, res, P);
+            else parse_from_global<FMT>(P.bytes + o0, len, res, P);
+        }
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(active ? res.n_entries : 0u, scan_ws, total);
+        uint32_t my_begin = 0;
+        if (total) {  // CTA-uniform
+            if (tid == 0) s_ebase = atomicAdd(P.entry_counter, total);
+            __syncthreads();
+            const uint32_t ebase = s_ebase;
+            const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
+            if (active && res.n_entries && !ovf) {
+                my_begin = ebase + excl;
+                if (!direct) Format<FMT>::emit(tile + (o0 - base), len, o0, res, sink, my_begin, P);
+                else emit_from_global<FMT>(P.bytes + o0, len, o0, res, sink, my_begin, P);
+            }
+        }
+        if (active) {
+            const bool ok = res.status == FG_ST_OK;
+            P.ts[i] = res.ts;
+            P.meta[i] = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);
+            P.host[i] = make_int2(res.host_o >= 0 ? o0 + res.host_o : -1, res.host_l);
+            if (FMT == 0) {
+                P.app[i] = make_int2(res.app_o >= 0 ? o0 + res.app_o : -1, res.app_l);
+                P.proc[i] = make_int2(res.proc_o >= 0 ? o0 + res.proc_o : -1, res.proc_l);
+                P.msgid[i] = make_int2(res.mid_o >= 0 ? o0 + res.mid_o : -1, res.mid_l);
+            }
+            P.msg[i] = make_int2(res.msg_o >= 0 ? o0 + res.msg_o : -1, res.msg_l);
+            // error rows: full.off = absolute byte offset of the failing part (LTSV side effects), len 0
+            P.full[i] = ok ? make_int2(res.full_o >= 0 ? o0 + res.full_o : -1, res.full_l)
+                           : make_int2(o0 + max(res.full_o, 0), 0);
+            P.sd[i] = make_int2((int)my_begin, (int)(ok ? res.n_entries : 0u));
+        }
+        __syncthreads();  // tile and scan scratch are reused by the next round
+        cur += r;
+    }
+}
+
+static int g_max_tile = 48 * 1024;
+
+cudaError_t configure_kernels(int max_tile_bytes) {
+    g_max_tile = max_tile_bytes;
+    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    return e;
+}
+
+cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
+    switch (fmt) {
+        case 0: parse_kernel<0><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+const char* kernel_build_info() {
+    return "flowgger_b200 parse kernels: sm_100a, thread-per-line over TMA-bulk-staged CTA tiles, "
+           "kernels=[parse_kernel<rfc5424>]";
+}
+
+}  // namespace fg

@@ -1,0 +1,50 @@
+// fg_kernels.cuh — launch parameters shared by fg_kernels.cu and fg_abi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fg {
+
+// LTSV decoder configuration in device memory (ltsv_decoder.rs:19-22)
+struct LtsvDeviceConfig {
+    int32_t has_schema;
+    int32_t n_schema;
+    const uint8_t* names;       // concatenated schema key bytes
+    const int32_t* name_off;    // [n_schema+1]
+    const int32_t* types;       // [n_schema] fg_ltsv_type
+    const uint8_t* suffix;      // concatenated suffix bytes
+    int32_t suffix_off[6];      // per fg_ltsv_type: [t]..[t+1]; empty span + present bit
+    uint32_t suffix_present;    // bit t set if a suffix is configured for type t
+};
+
+struct ParseParams {
+    const uint8_t* bytes;     // device copy of the caller's byte buffer (base of all spans)
+    const int32_t* offsets;   // [n+1] line offsets into bytes
+    int32_t n;                // lines in this launch
+    int32_t tile_bytes;       // dynamic shared memory staging tile, multiple of 16
+    // row columns, element 0 = first line of this launch
+    double* ts;
+    uint32_t* meta;
+    int2* host;
+    int2* app;
+    int2* proc;
+    int2* msgid;
+    int2* msg;
+    int2* full;
+    int2* sd;
+    // structured-data side table
+    int2* entry_name;
+    unsigned long long* entry_val;
+    uint8_t* entry_meta;
+    uint32_t* entry_counter;  // running total (atomic bump, one add per CTA round)
+    uint32_t entry_cap;
+    LtsvDeviceConfig ltsv;
+};
+
+constexpr int kLinesPerCta = 128;
+
+cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
+cudaError_t configure_kernels(int max_tile_bytes);
+const char* kernel_build_info();
+
+}  // namespace fg

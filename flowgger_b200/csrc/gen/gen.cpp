@@ -1,0 +1,245 @@
+// gen.cpp — synthetic log generators for tests and bench (NOT product code, NOT the oracle).
+// Workload shapes follow SURVEY.md §8(d): C2 RFC5424 (mean 180 B), C3 GELF (mean 512 B),
+// C4 LTSV (20 key:value fields).  Every line is a pure function of (seed, line index), so shards can
+// be generated in parallel and any sub-range can be regenerated on its own.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed, uint64_t idx) {
+        s = seed * 0x9E3779B97F4A7C15ull ^ (idx + 0x632BE59BD9B4E019ull) * 0xD1B54A32D192ED03ull;
+        next();
+        next();
+    }
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    uint32_t below(uint32_t n) { return (uint32_t)((next() >> 32) * (uint64_t)n >> 32); }
+    int range(int lo, int hi) { return lo + (int)below((uint32_t)(hi - lo + 1)); }  // inclusive
+    bool chance(double p) { return (double)(next() >> 11) * (1.0 / 9007199254740992.0) < p; }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    double normal() {
+        double u1 = uniform(), u2 = uniform();
+        if (u1 < 1e-300) u1 = 1e-300;
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    }
+};
+
+const char kHostChars[] = "abcdefghijklmnopqrstuvwxyz0123456789.-";
+const char kAlnum[] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789";
+const char kWords[][16] = {"error", "warning", "request", "user", "failed", "connection", "timeout", "from", "to",
+                           "session", "opened", "closed", "for", "id", "status", "GET", "POST", "/api/v1/items",
+                           "200", "404", "500", "ms", "bytes", "cache", "miss", "hit", "retry", "queue", "worker",
+                           "started", "stopped", "invalid", "token", "auth", "ok", "disk", "usage", "memory"};
+const char* kUtf8Bits[] = {"caf\xC3\xA9", "na\xC3\xAFve", "\xE6\x97\xA5\xE6\x9C\xAC\xE8\xAA\x9E", "\xE2\x82\xAC" "42",
+                           "\xF0\x9F\x9A\x80", "\xC3\x9Cml\xC3\xA4ut", "\xD0\xBB\xD0\xBE\xD0\xB3"};
+
+void rand_chars(Rng& r, std::string& o, int n, const char* alphabet, int alen) {
+    for (int i = 0; i < n; ++i) o.push_back(alphabet[r.below((uint32_t)alen)]);
+}
+
+void put2(std::string& o, int v) {
+    o.push_back((char)('0' + v / 10));
+    o.push_back((char)('0' + v % 10));
+}
+
+int dim(int y, int m) {
+    static const int d[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+    return (m == 2 && leap) ? 29 : d[m - 1];
+}
+
+// RFC3339 timestamp: 2015-2035, fractional digits {0,3,6,9}, Z 70% / +-HH:MM 30%
+void rfc3339(Rng& r, std::string& o) {
+    int y = r.range(2015, 2035), m = r.range(1, 12), d = r.range(1, dim(y, m));
+    char b[8];
+    snprintf(b, sizeof b, "%04d", y);
+    o += b;
+    o.push_back('-');
+    put2(o, m);
+    o.push_back('-');
+    put2(o, d);
+    o.push_back('T');
+    put2(o, r.range(0, 23));
+    o.push_back(':');
+    put2(o, r.range(0, 59));
+    o.push_back(':');
+    put2(o, r.range(0, 59));
+    int fd = r.below(4) * 3;
+    if (fd) {
+        o.push_back('.');
+        for (int i = 0; i < fd; ++i) o.push_back((char)('0' + r.below(10)));
+    }
+    if (r.chance(0.7)) o.push_back('Z');
+    else {
+        o.push_back(r.chance(0.5) ? '+' : '-');
+        put2(o, r.range(0, 14));
+        o.push_back(':');
+        put2(o, r.below(4) * 15);
+    }
+}
+
+void message_text(Rng& r, std::string& o, int target, bool utf8) {
+    const size_t start = o.size();
+    const int nw = (int)(sizeof kWords / sizeof kWords[0]);
+    while ((int)(o.size() - start) < target) {
+        if (o.size() > start) o.push_back(' ');
+        if (utf8 && r.chance(0.25)) o += kUtf8Bits[r.below(7)];
+        else if (r.chance(0.15)) rand_chars(r, o, r.range(2, 10), kAlnum, 62);
+        else o += kWords[r.below((uint32_t)nw)];
+    }
+    if ((int)(o.size() - start) > target && !utf8) o.resize(start + (size_t)std::max(target, 1));
+    while (o.size() > start && o.back() == ' ') o.pop_back();  // message must not end in a space here
+    if (o.size() == start) o.push_back('x');
+}
+
+void sd_element(Rng& r, std::string& o) {
+    o.push_back('[');
+    rand_chars(r, o, r.range(3, 8), kAlnum, 26);
+    o.push_back('@');
+    rand_chars(r, o, r.range(1, 5), "0123456789", 10);
+    int np = r.range(1, 4);
+    for (int k = 0; k < np; ++k) {
+        o.push_back(' ');
+        rand_chars(r, o, r.range(2, 10), kAlnum, 52);
+        o += "=\"";
+        int vl = r.range(1, 24);
+        bool esc = r.chance(0.05);
+        for (int i = 0; i < vl; ++i) {
+            if (esc && r.chance(0.2)) {
+                static const char* e[4] = {"\\\"", "\\\\", "\\]", "\\x"};
+                o += e[r.below(4)];
+                ++i;
+            } else {
+                char c = (char)r.range(32, 126);
+                if (c == '"' || c == '\\') c = '_';
+                o.push_back(c);
+            }
+        }
+        o.push_back('"');
+    }
+    o.push_back(']');
+}
+
+// C2: `<PRI>1 TS HOST APP PROCID MSGID SD MSG`
+void gen_rfc5424(uint64_t seed, uint64_t idx, double mean_len, double bad_frac, std::string& o) {
+    Rng r(seed, idx);
+    const size_t start = o.size();
+    int target = (int)std::lround(mean_len + 40.0 * r.normal());
+    if (target < 60) target = 60;
+    if (target > 1024) target = 1024;
+    const bool bad = r.chance(bad_frac);
+    const int bad_kind = bad ? (int)r.below(24) : -1;
+    if (bad_kind == 0) { o += "\xEF\xBB\xBF"; }               // BOM (valid)
+    if (bad_kind == 1) { /* no '<' */ } else o.push_back('<');
+    if (bad_kind == 2) o += "256";
+    else if (bad_kind == 3) { /* empty pri */ }
+    else if (bad_kind == 4) o += "1x";
+    else { char b[8]; snprintf(b, sizeof b, "%d", r.range(0, 191)); o += b; }
+    if (bad_kind != 5) o.push_back('>');
+    o += bad_kind == 6 ? "2" : (bad_kind == 7 ? "" : "1");
+    if (bad_kind == 8) return;  // only "<PRI>1"
+    o.push_back(' ');
+    if (bad_kind == 9) o.push_back('-');                        // NILVALUE timestamp
+    else if (bad_kind == 10) o += "2015-13-05T15:53:45Z";       // month 13
+    else if (bad_kind == 11) o += "2015-02-30 15:53:45Z";       // no 'T' (adds a space -> shifts fields)
+    else if (bad_kind == 12) o += "2017-02-29T00:00:00Z";       // not a leap year
+    else rfc3339(r, o);
+    int fields = 4;
+    if (bad_kind == 13) fields = (int)r.below(4);               // truncated header
+    for (int f = 0; f < fields; ++f) {
+        o.push_back(' ');
+        switch (f) {
+            case 0: rand_chars(r, o, r.range(8, 24), kHostChars, 38); break;
+            case 1: rand_chars(r, o, r.range(3, 16), kAlnum, 52); break;
+            case 2: if (r.chance(0.2)) o.push_back('-'); else rand_chars(r, o, r.range(1, 6), "0123456789", 10); break;
+            default: if (r.chance(0.3)) o.push_back('-'); else rand_chars(r, o, r.range(2, 8), kAlnum, 62); break;
+        }
+    }
+    if (bad_kind == 13) return;
+    if (bad_kind == 14) return;  // "Missing message data"
+    o.push_back(' ');
+    if (bad_kind == 15) return;  // "Missing log message"
+    const double u = r.uniform();
+    const int nsd = u < 0.40 ? 0 : (u < 0.85 ? 1 : 2);
+    if (bad_kind == 16) { o += "[id]"; if (r.chance(0.5)) return; }
+    else if (bad_kind == 17) o += "[id a=b]";
+    else if (bad_kind == 18) { o += "[id a=\"1\""; if (r.chance(0.5)) return; }  // missing ]
+    else if (bad_kind == 19) o += "[id =\"v\"]";
+    else if (bad_kind == 20) o += "x";                           // Malformated
+    else if (nsd == 0) o.push_back('-');
+    else for (int k = 0; k < nsd; ++k) sd_element(r, o);
+    if (bad_kind == 21) return;                                  // nothing after SD
+    if (bad_kind == 22) { o += "junk"; }                         // junk right after ']' (or after '-')
+    o.push_back(' ');
+    if (bad_kind == 23) { o += "  "; return; }                   // whitespace-only message -> msg None
+    const bool utf8 = r.chance(0.02);
+    int room = target - (int)(o.size() - start);
+    message_text(r, o, room < 1 ? 1 : room, utf8);
+    if (r.chance(0.01)) o.append((size_t)r.range(1, 3), ' ');
+}
+
+}  // namespace
+
+extern "C" {
+
+void fgen_free(void* p) { free(p); }
+
+// kind 0 = RFC5424 (C2).  Returns malloc'd bytes + int32 offsets[n+1]; fails (-1) past 2 GiB.
+int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, double mean_len, double bad_frac,
+                  int nthreads, uint8_t** out_bytes, int32_t** out_offsets, int64_t* out_total) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::string> parts((size_t)nthreads);
+    std::vector<std::vector<int32_t>> lens((size_t)nthreads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            std::string& o = parts[(size_t)t];
+            o.reserve((size_t)((hi - lo) * (int64_t)(mean_len + 16)));
+            lens[(size_t)t].reserve((size_t)(hi - lo));
+            for (int64_t i = lo; i < hi; ++i) {
+                const size_t before = o.size();
+                switch (kind) {
+                    default: gen_rfc5424(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
+                }
+                lens[(size_t)t].push_back((int32_t)(o.size() - before));
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    if (total > 0x7FFFFFC0ull) return -1;
+    uint8_t* buf = (uint8_t*)malloc(total + 64);
+    int32_t* offs = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n + 1));
+    size_t pos = 0;
+    int64_t li = 0;
+    offs[0] = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        memcpy(buf + pos, parts[(size_t)t].data(), parts[(size_t)t].size());
+        for (int32_t l : lens[(size_t)t]) {
+            offs[li + 1] = offs[li] + l;
+            ++li;
+        }
+        pos += parts[(size_t)t].size();
+    }
+    *out_bytes = buf;
+    *out_offsets = offs;
+    *out_total = (int64_t)total;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,578 @@
+// flowgger.cpp — host-side mirror of the reference's decoder-facing interface (see flowgger.hpp).
+// No parsing happens here: spans and scalars come from the CUDA kernels through the C ABI; this
+// file only copies them into owned Records (applying the deferred unescapes) and frames batches.
+#include "flowgger.hpp"
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <istream>
+#include <ostream>
+#include <stdexcept>
+#include <thread>
+
+namespace flowgger {
+
+// ---------------------------------------------------------------------------
+// small string helpers
+// ---------------------------------------------------------------------------
+static std::string lower(std::string s) {
+    for (auto& c : s)
+        if (c >= 'A' && c <= 'Z') c = (char)(c + 32);
+    return s;
+}
+
+static int ltsv_type_of(const std::string& t) {
+    const std::string l = lower(t);
+    if (l == "string") return FG_LTSV_STRING;
+    if (l == "bool") return FG_LTSV_BOOL;
+    if (l == "f64") return FG_LTSV_F64;
+    if (l == "i64") return FG_LTSV_I64;
+    if (l == "u64") return FG_LTSV_U64;
+    return -1;
+}
+
+// Unicode White_Space (str::trim), same table as the kernels use
+static size_t ws_front(std::string_view s) {
+    if (s.empty()) return 0;
+    const unsigned char c0 = (unsigned char)s[0];
+    if ((c0 >= 9 && c0 <= 13) || c0 == 32) return 1;
+    if (s.size() >= 2 && c0 == 0xC2) {
+        const unsigned char c1 = (unsigned char)s[1];
+        return (c1 == 0x85 || c1 == 0xA0) ? 2 : 0;
+    }
+    if (s.size() >= 3) {
+        const unsigned char c1 = (unsigned char)s[1], c2 = (unsigned char)s[2];
+        if (c0 == 0xE1) return (c1 == 0x9A && c2 == 0x80) ? 3 : 0;
+        if (c0 == 0xE2) {
+            if (c1 == 0x80) return ((c2 >= 0x80 && c2 <= 0x8A) || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF) ? 3 : 0;
+            return (c1 == 0x81 && c2 == 0x9F) ? 3 : 0;
+        }
+        if (c0 == 0xE3) return (c1 == 0x80 && c2 == 0x80) ? 3 : 0;
+    }
+    return 0;
+}
+static size_t ws_back(std::string_view s) {
+    const size_t n = s.size();
+    if (!n) return 0;
+    for (size_t k = 1; k <= 3 && k <= n; ++k) {
+        const unsigned char lead = (unsigned char)s[n - k];
+        if ((lead & 0xC0) == 0x80) continue;  // continuation byte: keep walking back
+        return ws_front(s.substr(n - k)) == k ? k : 0;
+    }
+    return 0;
+}
+std::string_view rust_trim(std::string_view s) {
+    for (size_t w; (w = ws_back(s)) != 0;) s.remove_suffix(w);
+    for (size_t w; (w = ws_front(s)) != 0;) s.remove_prefix(w);
+    return s;
+}
+
+// core::str::from_utf8 acceptance
+bool is_valid_utf8(const uint8_t* p, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        const uint8_t c = p[i];
+        if (c < 0x80) { ++i; continue; }
+        size_t need;
+        uint32_t cp;
+        if (c >= 0xC2 && c <= 0xDF) { need = 1; cp = c & 0x1F; }
+        else if (c >= 0xE0 && c <= 0xEF) { need = 2; cp = c & 0x0F; }
+        else if (c >= 0xF0 && c <= 0xF4) { need = 3; cp = c & 0x07; }
+        else return false;
+        if (i + need >= n) return false;  // truncated sequence
+        for (size_t k = 1; k <= need; ++k) {
+            const uint8_t d = p[i + k];
+            if ((d & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (d & 0x3F);
+        }
+        if (need == 2 && (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF))) return false;
+        if (need == 3 && (cp < 0x10000 || cp > 0x10FFFF)) return false;
+        i += need + 1;
+    }
+    return true;
+}
+
+// rfc5424_decoder.rs:105-125 (deferred from the kernel: the table carries the raw span + FG_EM_UNESCAPE)
+static std::string unescape_sd_value(std::string_view v) {
+    std::string res;
+    res.reserve(v.size());
+    bool esc = false;
+    for (const char c : v) {
+        if (!esc) {
+            if (c == '\\') esc = true;
+            else res.push_back(c);
+        } else {
+            if (c != '"' && c != '\\' && c != ']') res.push_back('\\');
+            res.push_back(c);
+            esc = false;
+        }
+    }
+    return res;
+}
+
+static void push_utf8(std::string& s, uint32_t cp) {
+    if (cp < 0x80) s.push_back((char)cp);
+    else if (cp < 0x800) {
+        s.push_back((char)(0xC0 | (cp >> 6)));
+        s.push_back((char)(0x80 | (cp & 0x3F)));
+    } else if (cp < 0x10000) {
+        s.push_back((char)(0xE0 | (cp >> 12)));
+        s.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+        s.push_back((char)(0x80 | (cp & 0x3F)));
+    } else {
+        s.push_back((char)(0xF0 | (cp >> 18)));
+        s.push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+        s.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+        s.push_back((char)(0x80 | (cp & 0x3F)));
+    }
+}
+static uint32_t hex4(std::string_view v, size_t i) {
+    uint32_t n = 0;
+    for (size_t k = 0; k < 4; ++k) {
+        const unsigned char c = (unsigned char)v[i + k];
+        n = n * 16 + (c <= '9' ? c - '0' : (c | 0x20) - 'a' + 10);
+    }
+    return n;
+}
+// JSON string body (already validated by the kernel) -> String.  `nl_retry`: the line went through
+// gelf_decoder.rs:44-46, where a raw LF is read as the escape `\n` and `\`+LF as `\\` followed by 'n'.
+static std::string json_unescape(std::string_view v, bool nl_retry) {
+    std::string res;
+    res.reserve(v.size());
+    for (size_t i = 0; i < v.size();) {
+        const char c = v[i];
+        if (c != '\\') {
+            res.push_back(c);
+            ++i;
+            continue;
+        }
+        const char e = v[i + 1];
+        i += 2;
+        switch (e) {
+            case '"': res.push_back('"'); break;
+            case '\\': res.push_back('\\'); break;
+            case '/': res.push_back('/'); break;
+            case 'b': res.push_back('\x08'); break;
+            case 'f': res.push_back('\x0c'); break;
+            case 'n': res.push_back('\n'); break;
+            case 'r': res.push_back('\r'); break;
+            case 't': res.push_back('\t'); break;
+            case 'u': {
+                uint32_t n1 = hex4(v, i);
+                i += 4;
+                if (n1 >= 0xD800 && n1 <= 0xDBFF) {
+                    const uint32_t n2 = hex4(v, i + 2);
+                    i += 6;
+                    n1 = (((n1 - 0xD800) << 10) | (n2 - 0xDC00)) + 0x10000;
+                }
+                push_utf8(res, n1);
+                break;
+            }
+            case '\n':
+                if (nl_retry) {
+                    res.push_back('\\');
+                    res.push_back('n');
+                }
+                break;
+            default: break;
+        }
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------
+// CudaBatchDecoder
+// ---------------------------------------------------------------------------
+CudaBatchDecoder::CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv, const DeviceOptions& opt) : fmt_(fmt) {
+    fg_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = opt.device;
+    cfg.max_batch_bytes = opt.max_batch_bytes;
+    cfg.max_batch_lines = opt.max_batch_lines;
+    cfg.chunk_lines = opt.chunk_lines;
+    std::vector<const char*> names;
+    std::vector<int32_t> types;
+    for (const auto& kv : ltsv.schema) {
+        const int t = ltsv_type_of(kv.second);
+        if (t < 0) throw std::invalid_argument("Unsupported type in input.ltsv_schema for name [" + kv.first + "]");  // ltsv_decoder.rs:44
+        names.push_back(kv.first.c_str());
+        types.push_back(t);
+    }
+    for (const auto& kv : ltsv.suffixes) {
+        const int t = ltsv_type_of(kv.first);
+        if (t == FG_LTSV_STRING) throw std::invalid_argument("Strings cannot be suffixed");  // :69
+        if (t < 0) throw std::invalid_argument("Unsupported type in input.ltsv_suffixes for type [" + kv.first + "]");  // :74
+        suffix_[t] = kv.second;
+        has_suffix_[t] = true;
+    }
+    cfg.ltsv_has_schema = ltsv.has_schema || !ltsv.schema.empty();
+    cfg.ltsv_schema_len = (int32_t)names.size();
+    cfg.ltsv_schema_names = names.data();
+    cfg.ltsv_schema_types = types.data();
+    for (int t = 0; t < 5; ++t) cfg.ltsv_suffix[t] = has_suffix_[t] ? suffix_[t].c_str() : nullptr;
+    const int rc = fg_create(&cfg, &ctx_);
+    if (rc != FG_OK) {
+        // No CPU fallback exists: without the CUDA library + a GPU the decoder cannot be constructed.
+        throw std::runtime_error(rc == FG_E_NO_DEVICE ? "flowgger_cuda: no CUDA device (the GPU decoder has no CPU fallback)"
+                                                      : "flowgger_cuda: fg_create failed");
+    }
+}
+CudaBatchDecoder::~CudaBatchDecoder() { fg_destroy(ctx_); }
+
+void CudaBatchDecoder::decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_batch_out* out) {
+    const int rc = fg_decode_batch(ctx_, fmt_, bytes, offsets, n, out);
+    if (rc != FG_OK) throw std::runtime_error(std::string("fg_decode_batch: ") + fg_last_error(ctx_));
+}
+
+static std::string_view span_sv(const uint8_t* bytes, fg_span s) {
+    return std::string_view((const char*)bytes + s.off, (size_t)s.len);
+}
+
+DecodeResult CudaBatchDecoder::materialize(const fg_batch_out& out, const uint8_t* bytes, const int32_t* offsets,
+                                           int32_t i, std::vector<std::string>* side_effects) const {
+    DecodeResult r;
+    const uint32_t meta = out.meta[i];
+    const uint32_t status = FG_META_STATUS(meta), flags = FG_META_FLAGS(meta);
+    if (side_effects && (flags & FG_FLAG_MISSING_VALUE)) {
+        // println! at ltsv_decoder.rs:99 for every tab-separated part without ':' that the decode loop
+        // reached: all parts when Ok / post-loop error, else the parts before the failing one.
+        const int32_t lo = offsets[i], hi = offsets[i + 1];
+        const int32_t stop = status ? out.full_msg[i].off : hi + 1;
+        int32_t a = lo;
+        for (;;) {
+            int32_t b = a;
+            while (b < hi && bytes[b] != '\t') ++b;
+            if (a >= stop) break;
+            std::string_view part((const char*)bytes + a, (size_t)(b - a));
+            if (part.find(':') == std::string_view::npos)
+                side_effects->push_back("Missing value for name '" + std::string(part) + "'");
+            if (b >= hi) break;
+            a = b + 1;
+        }
+    }
+    if (status) {
+        r.err = fg_error_string(fmt_, status);
+        return r;
+    }
+    const bool nl_retry = (flags & FG_FLAG_NL_RETRY) != 0;
+    Record& rec = r.record;
+    rec.ts = out.ts[i];
+    {
+        std::string_view h = span_sv(bytes, out.hostname[i]);
+        rec.hostname = (flags & FG_FLAG_HOST_ESC) ? json_unescape(h, nl_retry) : std::string(h);
+    }
+    if (FG_META_FACILITY(meta) != 0xFF) rec.facility = (uint8_t)FG_META_FACILITY(meta);
+    if (FG_META_SEVERITY(meta) != 0xFF) rec.severity = (uint8_t)FG_META_SEVERITY(meta);
+    if (out.appname && out.appname[i].off >= 0) rec.appname = std::string(span_sv(bytes, out.appname[i]));
+    if (out.procid && out.procid[i].off >= 0) rec.procid = std::string(span_sv(bytes, out.procid[i]));
+    if (out.msgid && out.msgid[i].off >= 0) rec.msgid = std::string(span_sv(bytes, out.msgid[i]));
+    if (out.msg[i].off >= 0) {
+        std::string_view m = span_sv(bytes, out.msg[i]);
+        rec.msg = (flags & FG_FLAG_MSG_ESC) ? json_unescape(m, nl_retry) : std::string(m);
+    }
+    if (out.full_msg[i].off >= 0) {
+        std::string_view m = span_sv(bytes, out.full_msg[i]);
+        rec.full_msg = (flags & FG_FLAG_FULL_ESC) ? json_unescape(m, nl_retry) : std::string(m);
+    }
+    const fg_span sd = out.sd[i];
+    if (sd.len > 0) {
+        std::vector<StructuredData> vec;
+        const bool r5 = fmt_ == FG_FMT_RFC5424;
+        if (!r5) vec.emplace_back();  // one element with sd_id None (ltsv_decoder.rs:88, gelf_decoder.rs:35)
+        for (int32_t e = sd.off; e < sd.off + sd.len; ++e) {
+            const uint8_t em = out.entry_meta[e];
+            const uint32_t tag = em & FG_EM_TAG_MASK;
+            const fg_span nm = out.entry_name[e];
+            if (tag == FG_TAG_SD_HEADER) {
+                vec.emplace_back();
+                if (nm.off >= 0) vec.back().sd_id = std::string(span_sv(bytes, nm));
+                vec.back().pairs.reserve((size_t)out.entry_val[e]);
+                continue;
+            }
+            std::string name;
+            std::string_view raw = span_sv(bytes, nm);
+            if (!(em & FG_EM_NO_PREFIX)) name.push_back('_');
+            if (em & FG_EM_NAME_ESC) name += json_unescape(raw, nl_retry);
+            else name.append(raw);
+            if ((em & FG_EM_SUFFIX) && tag >= 1 && tag <= 4) name += suffix_[tag];
+            SDValue v;
+            v.kind = (SDValue::Kind)tag;
+            const uint64_t val = out.entry_val[e];
+            switch (tag) {
+                case FG_TAG_STRING: {
+                    std::string_view sv((const char*)bytes + (uint32_t)(val & 0xFFFFFFFFu), (size_t)(val >> 32));
+                    if (em & FG_EM_UNESCAPE) v.s = r5 ? unescape_sd_value(sv) : json_unescape(sv, nl_retry);
+                    else v.s = std::string(sv);
+                    break;
+                }
+                case FG_TAG_BOOL: v.b = val != 0; break;
+                case FG_TAG_F64: memcpy(&v.f, &val, 8); break;
+                case FG_TAG_I64: v.i = (int64_t)val; break;
+                case FG_TAG_U64: v.u = val; break;
+                default: break;
+            }
+            vec.back().pairs.emplace_back(std::move(name), std::move(v));
+        }
+        rec.sd = std::move(vec);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// Decoder trait objects
+// ---------------------------------------------------------------------------
+CudaDecoder::CudaDecoder(fg_format fmt, const LtsvConfig& ltsv, const DeviceOptions& opt)
+    : impl_(std::make_shared<CudaBatchDecoder>(fmt, ltsv, opt)) {}
+
+DecodeResult CudaDecoder::decode(std::string_view line) const {
+    const int32_t offsets[2] = {0, (int32_t)line.size()};
+    fg_batch_out out;
+    const uint8_t dummy = 0;
+    const uint8_t* bytes = line.empty() ? &dummy : (const uint8_t*)line.data();
+    impl_->decode_batch(bytes, offsets, 1, &out);
+    std::vector<std::string> fx;
+    DecodeResult r = impl_->materialize(out, bytes, offsets, 0, &fx);
+    for (const auto& s : fx) fprintf(stdout, "%s\n", s.c_str());
+    if (r.ok() && (FG_META_FLAGS(out.meta[0]) & FG_FLAG_TS_MISSING)) {
+        // gelf_decoder.rs:109 -> utils/mod.rs:16-21
+        timespec tsn;
+        clock_gettime(CLOCK_REALTIME, &tsn);
+        r.record.ts = (double)tsn.tv_sec + (double)tsn.tv_nsec / 1e9;
+    }
+    return r;
+}
+std::unique_ptr<Decoder> CudaDecoder::clone_boxed() const { return std::unique_ptr<Decoder>(new CudaDecoder(impl_)); }
+
+// ---------------------------------------------------------------------------
+// BatchingLineSplitter
+// ---------------------------------------------------------------------------
+void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx,
+                               const Decoder& decoder, const Encoder& encoder, std::ostream& err_out,
+                               std::ostream& std_out) const {
+    std::shared_ptr<CudaBatchDecoder> gpu = decoder.batch();
+    std::vector<uint8_t> arena;
+    std::vector<int32_t> offsets{0};
+    arena.reserve((size_t)lim_.max_bytes);
+    auto flush = [&]() {
+        const int32_t n = (int32_t)offsets.size() - 1;
+        if (n == 0) return;
+        fg_batch_out out;
+        const uint8_t dummy = 0;
+        const uint8_t* bytes = arena.empty() ? &dummy : arena.data();
+        gpu->decode_batch(bytes, offsets.data(), n, &out);
+        for (int32_t i = 0; i < n; ++i) {
+            std::vector<std::string> fx;
+            DecodeResult r = gpu->materialize(out, bytes, offsets.data(), i, &fx);
+            for (const auto& s : fx) std_out << s << "\n";
+            const char* e = r.err;
+            if (!e) {
+                if (FG_META_FLAGS(out.meta[i]) & FG_FLAG_TS_MISSING) {
+                    timespec tsn;
+                    clock_gettime(CLOCK_REALTIME, &tsn);
+                    r.record.ts = (double)tsn.tv_sec + (double)tsn.tv_nsec / 1e9;
+                }
+                std::vector<uint8_t> enc;
+                if (encoder.encode(std::move(r.record), enc, &e)) {
+                    tx(std::move(enc));
+                    continue;
+                }
+            }
+            std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+            err_out << e << ": [" << rust_trim(line) << "]\n";  // line_splitter.rs:37-39
+        }
+        arena.clear();
+        offsets.assign(1, 0);
+    };
+    std::string line;
+    while (std::getline(in, line)) {
+        // BufRead::lines: the '\n' is gone; a '\r' is stripped only when it preceded a '\n'
+        if (!in.eof() && !line.empty() && line.back() == '\r') line.pop_back();
+        if (!is_valid_utf8((const uint8_t*)line.data(), line.size())) {
+            err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
+            continue;
+        }
+        if ((int64_t)(arena.size() + line.size()) > lim_.max_bytes || (int32_t)offsets.size() - 1 >= lim_.max_lines)
+            flush();
+        arena.insert(arena.end(), line.begin(), line.end());
+        offsets.push_back((int32_t)arena.size());
+    }
+    flush();
+}
+
+// ---------------------------------------------------------------------------
+// canonical dump (format documented in oracle/oracle.cpp: both sides implement it independently)
+// ---------------------------------------------------------------------------
+static void put_s(std::string& o, std::string_view s) {
+    char b[24];
+    o.append(b, (size_t)snprintf(b, sizeof b, "%zu:", s.size()));
+    o.append(s);
+}
+static void put_o(std::string& o, const std::optional<std::string>& s) {
+    if (s) put_s(o, *s);
+    else o.push_back('~');
+}
+static void put_hex(std::string& o, double f) {
+    uint64_t bits;
+    memcpy(&bits, &f, 8);
+    char b[24];
+    o.append(b, (size_t)snprintf(b, sizeof b, "%016" PRIx64, bits));
+}
+
+void dump_result(const DecodeResult& r, bool ts_is_now, const std::vector<std::string>& fx, std::string& o) {
+    char b[48];
+    if (r.err) {
+        o.append("E:");
+        o.append(r.err);
+    } else {
+        const Record& rec = r.record;
+        o.append("R:ts=");
+        if (ts_is_now) o.append("now");
+        else put_hex(o, rec.ts);
+        o.append(";fac=");
+        if (rec.facility) o.append(b, (size_t)snprintf(b, sizeof b, "%u", *rec.facility)); else o.push_back('~');
+        o.append(";sev=");
+        if (rec.severity) o.append(b, (size_t)snprintf(b, sizeof b, "%u", *rec.severity)); else o.push_back('~');
+        o.append(";host="); put_s(o, rec.hostname);
+        o.append(";app="); put_o(o, rec.appname);
+        o.append(";proc="); put_o(o, rec.procid);
+        o.append(";msgid="); put_o(o, rec.msgid);
+        o.append(";msg="); put_o(o, rec.msg);
+        o.append(";full="); put_o(o, rec.full_msg);
+        o.append(";sd=");
+        if (!rec.sd) o.push_back('~');
+        else {
+            o.append(b, (size_t)snprintf(b, sizeof b, "%zu", rec.sd->size()));
+            for (const auto& sd : *rec.sd) {
+                o.append("[id="); put_o(o, sd.sd_id);
+                o.append(b, (size_t)snprintf(b, sizeof b, ";n=%zu", sd.pairs.size()));
+                for (const auto& kv : sd.pairs) {
+                    o.append(";k="); put_s(o, kv.first);
+                    o.append(";v=");
+                    const SDValue& v = kv.second;
+                    switch (v.kind) {
+                        case SDValue::String: o.push_back('s'); put_s(o, v.s); break;
+                        case SDValue::Bool: o.append(v.b ? "b1" : "b0"); break;
+                        case SDValue::F64: o.push_back('f'); put_hex(o, v.f); break;
+                        case SDValue::I64: o.append(b, (size_t)snprintf(b, sizeof b, "i%" PRId64, v.i)); break;
+                        case SDValue::U64: o.append(b, (size_t)snprintf(b, sizeof b, "u%" PRIu64, v.u)); break;
+                        case SDValue::Null: o.push_back('n'); break;
+                    }
+                }
+                o.push_back(']');
+            }
+        }
+    }
+    o.append(b, (size_t)snprintf(b, sizeof b, ";out=%zu", fx.size()));
+    for (const auto& s : fx) { o.push_back(';'); put_s(o, s); }
+}
+
+}  // namespace flowgger
+
+// ---------------------------------------------------------------------------
+// C entry points for the Python tests / bench (ctypes)
+// ---------------------------------------------------------------------------
+using namespace flowgger;
+
+extern "C" {
+
+void* fgh_decoder_new(int fmt, int device, int64_t max_bytes, int32_t max_lines, int32_t chunk_lines, int has_schema,
+                      int n_schema, const char* const* names, const char* const* types, int n_suffix,
+                      const char* const* suffix_types, const char* const* suffix_vals, char* errbuf, int errlen) {
+    try {
+        LtsvConfig lc;
+        lc.has_schema = has_schema != 0;
+        for (int k = 0; k < n_schema; ++k) lc.schema.emplace_back(names[k], types[k]);
+        for (int k = 0; k < n_suffix; ++k) lc.suffixes.emplace_back(suffix_types[k], suffix_vals[k]);
+        DeviceOptions opt;
+        opt.device = device;
+        opt.max_batch_bytes = max_bytes;
+        opt.max_batch_lines = max_lines;
+        opt.chunk_lines = chunk_lines;
+        return new CudaBatchDecoder((fg_format)fmt, lc, opt);
+    } catch (const std::exception& e) {
+        if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());
+        return nullptr;
+    }
+}
+void fgh_decoder_free(void* d) { delete (CudaBatchDecoder*)d; }
+fg_ctx* fgh_decoder_ctx(void* d) { return ((CudaBatchDecoder*)d)->ctx(); }
+void fgh_free(void* p) { free(p); }
+
+// materialise + canonical dump of every line of a decoded batch (multi-threaded over line shards)
+int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, int nthreads,
+                 uint8_t** out_buf, int64_t** out_offsets) {
+    auto* dec = (CudaBatchDecoder*)d;
+    const int64_t n = out->n;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::string> parts((size_t)nthreads);
+    std::vector<std::vector<int64_t>> lens((size_t)nthreads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            std::string& o = parts[(size_t)t];
+            lens[(size_t)t].reserve((size_t)(hi - lo));
+            std::vector<std::string> fx;
+            for (int64_t i = lo; i < hi; ++i) {
+                const size_t before = o.size();
+                fx.clear();
+                DecodeResult r = dec->materialize(*out, bytes, offsets, (int32_t)i, &fx);
+                const bool now = r.ok() && (FG_META_FLAGS(out->meta[i]) & FG_FLAG_TS_MISSING);
+                dump_result(r, now, fx, o);
+                lens[(size_t)t].push_back((int64_t)(o.size() - before));
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    uint8_t* buf = (uint8_t*)malloc(total ? total : 1);
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    size_t pos = 0;
+    int64_t li = 0;
+    offs[0] = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        memcpy(buf + pos, parts[(size_t)t].data(), parts[(size_t)t].size());
+        for (const int64_t l : lens[(size_t)t]) {
+            offs[li + 1] = offs[li] + l;
+            ++li;
+        }
+        pos += parts[(size_t)t].size();
+    }
+    *out_buf = buf;
+    *out_offsets = offs;
+    return 0;
+}
+
+// materialisation rate (owned Records, like the reference builds them), for the e2e report
+double fgh_materialize_bench(void* d, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets,
+                             int nthreads) {
+    auto* dec = (CudaBatchDecoder*)d;
+    const int64_t n = out->n;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    std::vector<uint64_t> sink((size_t)nthreads, 0);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            uint64_t s = 0;
+            for (int64_t i = lo; i < hi; ++i) {
+                DecodeResult r = dec->materialize(*out, bytes, offsets, (int32_t)i, nullptr);
+                s += r.record.hostname.size();
+            }
+            sink[(size_t)t] = s;
+        });
+    }
+    for (auto& x : th) x.join();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
+}
+
+int fgh_is_valid_utf8(const uint8_t* p, int64_t n) { return is_valid_utf8(p, (size_t)n) ? 1 : 0; }
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// flowgger.hpp — C++ host-side mirror of the reference's decoder-facing interface,
+// layered on the C ABI (include/flowgger_cuda.h).
+//
+// The reference is Rust; no Rust toolchain exists in the build environment, so
+// the code a flowgger maintainer would write in `cuda_decoder` (rust/cuda_decoder,
+// shipped as source) is mirrored here 1:1 in C++ and is what the tests drive:
+//   Record / StructuredData / SDValue      <- src/flowgger/record.rs:4-82
+//   Decoder::decode / clone_boxed          <- src/flowgger/decoder/mod.rs:23-46
+//   RFC5424Decoder / LTSVDecoder / GelfDecoder::new(&Config)
+//                                          <- decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16
+//   BatchingLineSplitter::run              <- splitter/line_splitter.rs:10-54 (batched)
+// All parsing happens in the CUDA kernels; this layer only packs lines, calls
+// fg_decode_batch and materialises owned Records from the columnar spans.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <iosfwd>
+#include <map>
+#include <memory>
+#include <optional>
+#include <string>
+#include <string_view>
+#include <utility>
+#include <vector>
+
+#include "flowgger_cuda.h"
+
+namespace flowgger {
+
+// record.rs:4-11
+struct SDValue {
+    enum Kind : uint8_t { String = 0, Bool = 1, F64 = 2, I64 = 3, U64 = 4, Null = 5 } kind = Null;
+    std::string s;
+    union {
+        bool b;
+        double f;
+        int64_t i;
+        uint64_t u;
+    };
+    SDValue() : u(0) {}
+};
+
+// record.rs:24-27
+struct StructuredData {
+    std::optional<std::string> sd_id;
+    std::vector<std::pair<std::string, SDValue>> pairs;
+};
+
+// record.rs:71-82
+struct Record {
+    double ts = 0.0;
+    std::string hostname;
+    std::optional<uint8_t> facility;
+    std::optional<uint8_t> severity;
+    std::optional<std::string> appname;
+    std::optional<std::string> procid;
+    std::optional<std::string> msgid;
+    std::optional<std::string> msg;
+    std::optional<std::string> full_msg;
+    std::optional<std::vector<StructuredData>> sd;
+};
+
+// Result<Record, &'static str>
+struct DecodeResult {
+    const char* err = nullptr;  // nullptr = Ok
+    Record record;
+    bool ok() const { return err == nullptr; }
+};
+
+// input.ltsv_schema / input.ltsv_suffixes (ltsv_decoder.rs:24-83); type names are case-insensitive
+struct LtsvConfig {
+    bool has_schema = false;
+    std::vector<std::pair<std::string, std::string>> schema;    // key -> "string"|"bool"|"f64"|"i64"|"u64"
+    std::vector<std::pair<std::string, std::string>> suffixes;  // type -> suffix
+};
+
+struct DeviceOptions {
+    int device = 0;
+    int64_t max_batch_bytes = 0;
+    int32_t max_batch_lines = 0;
+    int32_t chunk_lines = 0;
+};
+
+// One GPU decoding context of a fixed format.  Single caller at a time.
+class CudaBatchDecoder {
+   public:
+    CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv = {}, const DeviceOptions& opt = {});
+    ~CudaBatchDecoder();
+    CudaBatchDecoder(const CudaBatchDecoder&) = delete;
+    CudaBatchDecoder& operator=(const CudaBatchDecoder&) = delete;
+
+    fg_format format() const { return fmt_; }
+    fg_ctx* ctx() const { return ctx_; }
+    // packs nothing: bytes/offsets as in fg_decode_batch.  Throws std::runtime_error on a CUDA/argument failure.
+    void decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_batch_out* out);
+    // Owned Record (or the reference's error string) of line i of a decoded batch.
+    // `side_effects`, if given, receives the println! lines of ltsv_decoder.rs:99.
+    DecodeResult materialize(const fg_batch_out& out, const uint8_t* bytes, const int32_t* offsets, int32_t i,
+                             std::vector<std::string>* side_effects = nullptr) const;
+
+   private:
+    fg_format fmt_;
+    fg_ctx* ctx_ = nullptr;
+    std::string suffix_[5];
+    bool has_suffix_[5] = {false, false, false, false, false};
+};
+
+// decoder/mod.rs:44-46 + :23-36
+class Decoder {
+   public:
+    virtual ~Decoder() = default;
+    virtual DecodeResult decode(std::string_view line) const = 0;
+    virtual std::unique_ptr<Decoder> clone_boxed() const = 0;
+    virtual std::shared_ptr<CudaBatchDecoder> batch() const = 0;
+};
+
+// Drop-in decoders: `decode(line)` is a batch of one through the same kernels.
+class CudaDecoder : public Decoder {
+   public:
+    CudaDecoder(fg_format fmt, const LtsvConfig& ltsv = {}, const DeviceOptions& opt = {});
+    DecodeResult decode(std::string_view line) const override;
+    std::unique_ptr<Decoder> clone_boxed() const override;
+    std::shared_ptr<CudaBatchDecoder> batch() const override { return impl_; }
+
+   private:
+    explicit CudaDecoder(std::shared_ptr<CudaBatchDecoder> impl) : impl_(std::move(impl)) {}
+    std::shared_ptr<CudaBatchDecoder> impl_;
+};
+struct RFC5424Decoder : CudaDecoder {
+    explicit RFC5424Decoder(const DeviceOptions& opt = {}) : CudaDecoder(FG_FMT_RFC5424, {}, opt) {}
+};
+struct LTSVDecoder : CudaDecoder {
+    explicit LTSVDecoder(const LtsvConfig& cfg = {}, const DeviceOptions& opt = {}) : CudaDecoder(FG_FMT_LTSV, cfg, opt) {}
+};
+struct GelfDecoder : CudaDecoder {
+    explicit GelfDecoder(const DeviceOptions& opt = {}) : CudaDecoder(FG_FMT_GELF, {}, opt) {}
+};
+
+// encoder/mod.rs:54-56 (interface only: encoders are out of scope)
+class Encoder {
+   public:
+    virtual ~Encoder() = default;
+    virtual bool encode(Record&& record, std::vector<uint8_t>& out, const char** err) const = 0;
+};
+
+// Batched twin of LineSplitter::run (splitter/line_splitter.rs:10-54): reads lines like
+// BufRead::lines (strip "\n" and one "\r"; invalid UTF-8 => "Invalid UTF-8 input" on stderr,
+// line skipped), accumulates up to max_lines/max_bytes, decodes the batch on the GPU, then in
+// the original order encodes + sends each Record, or prints "{err}: [{line.trim()}]" to stderr.
+class BatchingLineSplitter {
+   public:
+    struct Limits {
+        int32_t max_lines = 1 << 16;
+        int64_t max_bytes = 16 << 20;
+    };
+    BatchingLineSplitter() = default;
+    explicit BatchingLineSplitter(Limits l) : lim_(l) {}
+    // tx: receives each encoded record; err_out/std_out: the reference's stderr/stdout text
+    void run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx, const Decoder& decoder,
+             const Encoder& encoder, std::ostream& err_out, std::ostream& std_out) const;
+
+   private:
+    Limits lim_;
+};
+
+// helpers shared with tests
+bool is_valid_utf8(const uint8_t* p, size_t n);
+std::string_view rust_trim(std::string_view s);
+void dump_result(const DecodeResult& r, bool ts_is_now, const std::vector<std::string>& side_effects, std::string& out);
+
+}  // namespace flowgger

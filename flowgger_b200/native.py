@@ -1,0 +1,275 @@
+"""ctypes binding of include/flowgger_cuda.h (+ the C++ host mirror and the synthetic generators)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_DIR = Path(__file__).resolve().parent / "lib"
+
+FMT_RFC5424, FMT_LTSV, FMT_GELF = 0, 1, 2
+FMT_NAMES = {FMT_RFC5424: "rfc5424", FMT_LTSV: "ltsv", FMT_GELF: "gelf"}
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class FgSpan(C.Structure):
+    _fields_ = [("off", C.c_int32), ("len", C.c_int32)]
+
+
+class FgBatchOut(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("n_entries", C.c_int32),
+        ("ts", C.POINTER(C.c_double)), ("meta", C.POINTER(C.c_uint32)),
+        ("hostname", C.POINTER(FgSpan)), ("appname", C.POINTER(FgSpan)), ("procid", C.POINTER(FgSpan)),
+        ("msgid", C.POINTER(FgSpan)), ("msg", C.POINTER(FgSpan)), ("full_msg", C.POINTER(FgSpan)),
+        ("sd", C.POINTER(FgSpan)),
+        ("entry_name", C.POINTER(FgSpan)), ("entry_val", C.POINTER(C.c_uint64)), ("entry_meta", C.POINTER(C.c_uint8)),
+        ("kernel_ms", C.c_float), ("total_ms", C.c_float),
+    ]
+
+
+_cuda = None
+_host = None
+_gen = None
+
+
+def cuda_lib_path() -> Path:
+    return LIB_DIR / "libflowgger_cuda.so"
+
+
+def _load(name: str) -> C.CDLL:
+    p = LIB_DIR / name
+    if not p.exists():
+        raise NativeLibraryMissing(
+            f"{p} is missing: run `python -m flowgger_b200.build` (nvcc, sm_100a). "
+            "flowgger_b200 has no CPU fallback.")
+    return C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+
+
+def load_cuda() -> C.CDLL:
+    global _cuda
+    if _cuda is None:
+        L = _load("libflowgger_cuda.so")
+        L.fg_error_string.restype = C.c_char_p
+        L.fg_error_string.argtypes = [C.c_int, C.c_uint32]
+        L.fg_build_info.restype = C.c_char_p
+        L.fg_last_error.restype = C.c_char_p
+        L.fg_last_error.argtypes = [C.c_void_p]
+        L.fg_kernel_launches.restype = C.c_int64
+        L.fg_kernel_launches.argtypes = [C.c_void_p]
+        L.fg_decode_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FgBatchOut)]
+        L.fg_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.fg_parse_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.fg_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(FgBatchOut)]
+        L.fg_flush_l2.argtypes = [C.c_void_p]
+        L.fg_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.fg_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.fg_error_count.restype = C.c_uint32
+        _cuda = L
+    return _cuda
+
+
+def load_host() -> C.CDLL:
+    global _host
+    if _host is None:
+        load_cuda()
+        L = _load("libflowgger_host.so")
+        L.fgh_decoder_new.restype = C.c_void_p
+        L.fgh_decoder_new.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int, C.c_int,
+                                      C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int,
+                                      C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int]
+        L.fgh_decoder_free.argtypes = [C.c_void_p]
+        L.fgh_decoder_ctx.restype = C.c_void_p
+        L.fgh_decoder_ctx.argtypes = [C.c_void_p]
+        L.fgh_free.argtypes = [C.c_void_p]
+        L.fgh_dump_out.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.fgh_materialize_bench.restype = C.c_double
+        L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
+        L.fgh_is_valid_utf8.argtypes = [C.c_void_p, C.c_int64]
+        _host = L
+    return _host
+
+
+def load_gen() -> C.CDLL:
+    global _gen
+    if _gen is None:
+        L = _load("libfg_gen.so")
+        L.fgen_generate.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int,
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.fgen_free.argtypes = [C.c_void_p]
+        _gen = L
+    return _gen
+
+
+def build_info() -> str:
+    return load_cuda().fg_build_info().decode()
+
+
+def error_string(fmt: int, status: int) -> str | None:
+    s = load_cuda().fg_error_string(fmt, status)
+    return None if s is None else s.decode()
+
+
+def generate(fmt: int, seed: int, n: int, *, first_index: int = 0, mean_len: float = 0.0, bad_frac: float = 0.005,
+             nthreads: int = 8) -> tuple[np.ndarray, np.ndarray]:
+    """Synthetic batch (SURVEY.md §8(d) shapes): returns (bytes uint8[total], offsets int32[n+1])."""
+    L = load_gen()
+    if mean_len <= 0:
+        mean_len = {FMT_RFC5424: 180.0, FMT_GELF: 512.0, FMT_LTSV: 420.0}[fmt]
+    pb, po, tot = C.c_void_p(), C.c_void_p(), C.c_int64()
+    rc = L.fgen_generate(fmt, seed, first_index, n, mean_len, bad_frac, nthreads, C.byref(pb), C.byref(po), C.byref(tot))
+    if rc != 0:
+        raise ValueError("generated batch exceeds the int32 offset range; generate fewer lines per batch")
+    try:
+        b = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint8)), shape=(max(tot.value, 1),))[: tot.value].copy()
+        o = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int32)), shape=(n + 1,)).copy()
+    finally:
+        L.fgen_free(pb)
+        L.fgen_free(po)
+    return b, o
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class BatchResult:
+    """numpy views over one fg_batch_out (valid until the next decode on the same decoder)."""
+
+    def __init__(self, out: FgBatchOut, fmt: int):
+        self.raw = out
+        self.fmt = fmt
+        self.n = out.n
+        self.n_entries = out.n_entries
+        self.kernel_ms = out.kernel_ms
+        self.total_ms = out.total_ms
+        n, ne = out.n, out.n_entries
+
+        def arr(p, dtype, count, cols=None):
+            if not p or count == 0:
+                return np.zeros((0,) if cols is None else (0, cols), dtype=dtype)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize * (cols or 1),))
+            a = a.view(dtype)
+            return a if cols is None else a.reshape(count, cols)
+
+        self.ts = arr(out.ts, np.float64, n)
+        self.meta = arr(out.meta, np.uint32, n)
+        self.hostname = arr(out.hostname, np.int32, n, 2)
+        self.appname = arr(out.appname, np.int32, n, 2)
+        self.procid = arr(out.procid, np.int32, n, 2)
+        self.msgid = arr(out.msgid, np.int32, n, 2)
+        self.msg = arr(out.msg, np.int32, n, 2)
+        self.full_msg = arr(out.full_msg, np.int32, n, 2)
+        self.sd = arr(out.sd, np.int32, n, 2)
+        self.entry_name = arr(out.entry_name, np.int32, ne, 2)
+        self.entry_val = arr(out.entry_val, np.uint64, ne)
+        self.entry_meta = arr(out.entry_meta, np.uint8, ne)
+
+    @property
+    def status(self) -> np.ndarray:
+        return self.meta & 0xFF
+
+
+class BatchDecoder:
+    """One GPU decoding context of a fixed format (wraps flowgger::CudaBatchDecoder / fg_ctx)."""
+
+    def __init__(self, fmt: int, *, device: int = 0, max_batch_bytes: int = 0, max_batch_lines: int = 0,
+                 chunk_lines: int = 0, ltsv_schema: dict[str, str] | None = None,
+                 ltsv_suffixes: dict[str, str] | None = None):
+        self._h = None
+        self.L = load_cuda()
+        self.H = load_host()
+        self.fmt = fmt
+        schema = list((ltsv_schema or {}).items())
+        suff = list((ltsv_suffixes or {}).items())
+
+        def carr(xs):
+            a = (C.c_char_p * max(len(xs), 1))()
+            for i, x in enumerate(xs):
+                a[i] = x.encode()
+            return a
+
+        err = C.create_string_buffer(512)
+        h = self.H.fgh_decoder_new(fmt, device, max_batch_bytes, max_batch_lines, chunk_lines,
+                                   1 if ltsv_schema is not None else 0, len(schema),
+                                   carr([k for k, _ in schema]), carr([v for _, v in schema]), len(suff),
+                                   carr([k for k, _ in suff]), carr([v for _, v in suff]), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode() or "fgh_decoder_new failed")
+        self._h = C.c_void_p(h)
+        self.ctx = C.c_void_p(self.H.fgh_decoder_ctx(self._h))
+        self._pinned: list[C.c_void_p] = []
+
+    def close(self) -> None:
+        if self._h:
+            for p in self._pinned:
+                self.L.fg_host_free(self.ctx, p)
+            self._pinned.clear()
+            self.H.fgh_decoder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.L.fg_last_error(self.ctx).decode()}")
+
+    def host_alloc(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """Pinned host array (what a batching splitter fills directly)."""
+        p = C.c_void_p()
+        self._check(self.L.fg_host_alloc(self.ctx, max(nbytes, 1), C.byref(p)), "fg_host_alloc")
+        self._pinned.append(p)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(nbytes, 1),))[:nbytes]
+        return a.view(dtype)
+
+    def decode(self, data: np.ndarray, offsets: np.ndarray) -> BatchResult:
+        assert data.dtype == np.uint8 and offsets.dtype == np.int32
+        out = FgBatchOut()
+        n = len(offsets) - 1
+        self._keep = (data, offsets)
+        self._check(self.L.fg_decode_batch(self.ctx, self.fmt, _ptr(data), _ptr(offsets), n, C.byref(out)), "fg_decode_batch")
+        return BatchResult(out, self.fmt)
+
+    def upload(self, data: np.ndarray, offsets: np.ndarray) -> None:
+        assert data.dtype == np.uint8 and offsets.dtype == np.int32
+        self._check(self.L.fg_upload(self.ctx, _ptr(data), _ptr(offsets), len(offsets) - 1), "fg_upload")
+
+    def parse_resident(self) -> float:
+        ms = C.c_float()
+        self._check(self.L.fg_parse_resident(self.ctx, self.fmt, C.byref(ms)), "fg_parse_resident")
+        return ms.value
+
+    def download(self) -> BatchResult:
+        out = FgBatchOut()
+        self._check(self.L.fg_download(self.ctx, self.fmt, C.byref(out)), "fg_download")
+        return BatchResult(out, self.fmt)
+
+    def flush_l2(self) -> None:
+        self._check(self.L.fg_flush_l2(self.ctx), "fg_flush_l2")
+
+    def kernel_launches(self) -> int:
+        return int(self.L.fg_kernel_launches(self.ctx))
+
+    def dump(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 8) -> tuple[bytes, np.ndarray]:
+        """Materialise every Record of a decoded batch and render the canonical parity dump."""
+        pb, po = C.c_void_p(), C.c_void_p()
+        self.H.fgh_dump_out(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads, C.byref(pb), C.byref(po))
+        try:
+            offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(res.n + 1,)).copy()
+            buf = C.string_at(pb, int(offs[-1]))
+        finally:
+            self.H.fgh_free(pb)
+            self.H.fgh_free(po)
+        return buf, offs
+
+    def materialize_seconds(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 1) -> float:
+        return float(self.H.fgh_materialize_bench(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads))

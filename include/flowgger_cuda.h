@@ -1,0 +1,151 @@
+/* flowgger_cuda.h — C ABI of the B200 batched log-line decoder.
+ *
+ * Drop-in boundary for flowgger's Decoder stage.  The reference interface this
+ * replaces is
+ *     trait Decoder { fn decode(&self, line: &str) -> Result<Record, &'static str>; }
+ *         (/root/reference/src/flowgger/decoder/mod.rs:44-46)
+ * constructed by RFC5424Decoder::new / LTSVDecoder::new / GelfDecoder::new
+ *         (decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16)
+ * and called once per record by the splitters
+ *         (splitter/line_splitter.rs:50, nul_splitter.rs:57, syslen_splitter.rs:65).
+ * The batched form is: N lines packed into one contiguous byte buffer plus an
+ * int32 offsets array -> one fg_decode_batch() call -> N columnar results
+ * (status code == the reference's Err(&'static str), or the Record fields as
+ * zero-copy spans into the caller's byte buffer plus normalised scalars).
+ *
+ * Plain C: pointers and sizes only.  No CPU fallback exists behind this ABI:
+ * every entry point that parses runs the sm_100a CUDA kernels or fails.
+ */
+#ifndef FLOWGGER_CUDA_H
+#define FLOWGGER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* input.format (mod.rs:413-422) */
+typedef enum fg_format { FG_FMT_RFC5424 = 0, FG_FMT_LTSV = 1, FG_FMT_GELF = 2 } fg_format;
+
+/* SDValue discriminant (record.rs:4-11) + table-internal marker */
+typedef enum fg_tag {
+    FG_TAG_STRING = 0,
+    FG_TAG_BOOL = 1,
+    FG_TAG_F64 = 2,
+    FG_TAG_I64 = 3,
+    FG_TAG_U64 = 4,
+    FG_TAG_NULL = 5,
+    FG_TAG_SD_HEADER = 7 /* entry opens a StructuredData element: name = sd_id, val = #pairs */
+} fg_tag;
+
+/* entry_meta bits */
+#define FG_EM_TAG_MASK 0x07u
+#define FG_EM_UNESCAPE 0x08u  /* string value holds escapes: RFC5424 (rfc5424_decoder.rs:105-125) or JSON */
+#define FG_EM_NO_PREFIX 0x10u /* GELF: name already starts with '_' (gelf_decoder.rs:99-103); else host prepends "_" */
+#define FG_EM_SUFFIX 0x20u    /* LTSV: append the configured type suffix (ltsv_decoder.rs:131-136) */
+#define FG_EM_NAME_ESC 0x40u  /* GELF: name span holds JSON escapes */
+
+/* row meta word: status | facility<<8 | severity<<16 | flags<<24 */
+#define FG_META_STATUS(m) ((uint32_t)(m)&0xFFu)
+#define FG_META_FACILITY(m) (((uint32_t)(m) >> 8) & 0xFFu) /* 0xFF = None */
+#define FG_META_SEVERITY(m) (((uint32_t)(m) >> 16) & 0xFFu) /* 0xFF = None */
+#define FG_META_FLAGS(m) (((uint32_t)(m) >> 24) & 0xFFu)
+#define FG_FLAG_TS_MISSING 0x01u   /* GELF without "timestamp": host fills wall clock (gelf_decoder.rs:109) */
+#define FG_FLAG_MISSING_VALUE 0x02u /* LTSV part without ':' seen (println! at ltsv_decoder.rs:99) */
+#define FG_FLAG_HOST_ESC 0x04u     /* GELF: hostname span holds JSON escapes */
+#define FG_FLAG_MSG_ESC 0x08u      /* GELF: short_message span holds JSON escapes */
+#define FG_FLAG_FULL_ESC 0x10u     /* GELF: full_message span holds JSON escapes */
+#define FG_FLAG_NL_RETRY 0x20u     /* GELF: parsed through the raw-newline retry (gelf_decoder.rs:44-46) */
+
+/* (offset,len) into the `bytes` buffer given to the call; off < 0 => None */
+typedef struct fg_span {
+    int32_t off;
+    int32_t len;
+} fg_span;
+
+/* LTSV schema value types (ltsv_decoder.rs:36-43) */
+typedef enum fg_ltsv_type { FG_LTSV_STRING = 0, FG_LTSV_BOOL = 1, FG_LTSV_F64 = 2, FG_LTSV_I64 = 3, FG_LTSV_U64 = 4 } fg_ltsv_type;
+
+typedef struct fg_config {
+    int32_t device;           /* CUDA device ordinal */
+    int64_t max_batch_bytes;  /* capacity of one fg_decode_batch call (<= 2^31-64) ; 0 = default 1 GiB */
+    int32_t max_batch_lines;  /* 0 = default 8 Mi */
+    int32_t chunk_lines;      /* host<->device pipeline granularity; 0 = default 256 Ki */
+    /* input.ltsv_schema / input.ltsv_suffixes (ltsv_decoder.rs:25-81); ignored by other formats */
+    int32_t ltsv_has_schema;
+    int32_t ltsv_schema_len;
+    const char* const* ltsv_schema_names; /* NUL-terminated UTF-8 */
+    const int32_t* ltsv_schema_types;     /* fg_ltsv_type */
+    const char* ltsv_suffix[5];           /* indexed by fg_ltsv_type; NULL = none ([0] unused) */
+} fg_config;
+
+/* Columnar result of one batch.  All pointers are host pointers owned by the
+ * context, valid until the next fg_decode_batch / fg_destroy on it. */
+typedef struct fg_batch_out {
+    int32_t n;         /* lines */
+    int32_t n_entries; /* rows of the structured-data side table */
+    const double* ts;        /* Record.ts (record.rs:72); utils/mod.rs:24-28 arithmetic, bit-exact */
+    const uint32_t* meta;    /* FG_META_* */
+    const fg_span* hostname; /* Record.hostname */
+    const fg_span* appname;  /* RFC5424 only, else NULL */
+    const fg_span* procid;   /* RFC5424 only, else NULL */
+    const fg_span* msgid;    /* RFC5424 only, else NULL */
+    const fg_span* msg;
+    const fg_span* full_msg; /* on error rows of LTSV: off = byte offset of the failing part */
+    const fg_span* sd;       /* {first entry, entry count} ; count 0 => Record.sd = None */
+    const fg_span* entry_name;  /* [n_entries] */
+    const uint64_t* entry_val;  /* string: off | len<<32 ; bool/i64/u64/f64: the 8 value bytes ; header: #pairs */
+    const uint8_t* entry_meta;  /* FG_EM_* */
+    /* timings of the call, milliseconds */
+    float kernel_ms; /* sum of parse-kernel time (CUDA events on the launch stream) */
+    float total_ms;  /* H2D + kernels + D2H wall time */
+} fg_batch_out;
+
+typedef struct fg_ctx fg_ctx;
+
+/* 0 on success; negative FG_E_* otherwise.  Never throws, never aborts. */
+#define FG_OK 0
+#define FG_E_ARG (-1)
+#define FG_E_CUDA (-2)
+#define FG_E_CAPACITY (-3)
+#define FG_E_NO_DEVICE (-4)
+
+/* XDecoder::new(&Config) */
+int fg_create(const fg_config* cfg, fg_ctx** out);
+void fg_destroy(fg_ctx* ctx);
+const char* fg_last_error(const fg_ctx* ctx); /* human-readable detail of the last negative return */
+
+/* Pinned host arenas a batching splitter fills directly (no staging copy).
+ * Any host pointer is accepted by fg_decode_batch; pinned ones go at PCIe rate. */
+int fg_host_alloc(fg_ctx* ctx, size_t bytes, void** out);
+void fg_host_free(fg_ctx* ctx, void* p);
+
+/* Decoder::decode for n lines.  offsets has n+1 monotone entries, offsets[0] >= 0;
+ * line i is bytes[offsets[i] .. offsets[i+1]) and must be valid UTF-8 without the
+ * line terminator (what LineSplitter hands to decode, line_splitter.rs:17-50). */
+int fg_decode_batch(fg_ctx* ctx, fg_format fmt, const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                    fg_batch_out* out);
+
+/* Device-resident variant used for roofline measurement: fg_upload stages a
+ * batch in HBM once; fg_parse_resident runs only the parse kernel(s) over it
+ * and reports the CUDA-event time; fg_download fetches the result of the last
+ * resident parse. */
+int fg_upload(fg_ctx* ctx, const uint8_t* bytes, const int32_t* offsets, int32_t n);
+int fg_parse_resident(fg_ctx* ctx, fg_format fmt, float* kernel_ms);
+int fg_download(fg_ctx* ctx, fg_format fmt, fg_batch_out* out);
+int fg_flush_l2(fg_ctx* ctx); /* writes a >L2-sized scratch buffer */
+
+/* the reference's Err(&'static str) for a row status (0 -> NULL) */
+const char* fg_error_string(fg_format fmt, uint32_t status);
+uint32_t fg_error_count(void);
+
+/* build/launch facts for tests and bench */
+const char* fg_build_info(void);          /* arch, compiler, kernel list */
+int64_t fg_kernel_launches(const fg_ctx* ctx); /* parse kernels launched by this ctx so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWGGER_CUDA_H */

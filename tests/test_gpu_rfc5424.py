@@ -1,0 +1,127 @@
+"""Parity of the CUDA RFC5424 path (through the C ABI) against the oracle. GPU only."""
+import numpy as np
+import pytest
+
+import vectors as V
+from conftest import assert_parity
+
+pytestmark = pytest.mark.gpu
+R5 = 0
+
+
+@pytest.fixture(scope="module")
+def dec(native):
+    d = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=600 << 20, max_batch_lines=3 << 20, chunk_lines=1 << 18)
+    yield d
+    d.close()
+
+
+def test_golden_g1_g2(dec, oracle, native):
+    data, offs = oracle.pack([V.G1_LINE.encode(), V.G2_LINE.encode()])
+    res = assert_parity(dec, oracle, R5, data, offs)
+    assert res.status.tolist() == [0, 0]
+    assert res.ts.view(np.uint64).tolist() == [0x41D5708C6268D21C] * 2  # 1438790025.637824, bit-exact
+    assert (res.meta >> 8 & 0xFF).tolist() == [2, 2] and (res.meta >> 16 & 0xFF).tolist() == [7, 7]
+    span = lambda a, i: bytes(data[a[i, 0]:a[i, 0] + a[i, 1]])
+    assert span(res.hostname, 0) == b"testhostname" and span(res.appname, 0) == b"appname"
+    assert span(res.procid, 0) == b"69" and span(res.msgid, 0) == b"42" and span(res.msg, 1) == b"test message"
+    assert res.sd[:, 1].tolist() == [3, 6]  # header + 2 pairs ; 2 headers + 4 pairs
+
+
+def test_appendix_vectors(dec, oracle, native):
+    lines = [l.encode() for l, _ in V.RFC5424_CASES]
+    data, offs = oracle.pack(lines)
+    res = assert_parity(dec, oracle, R5, data, offs)
+    for i, (line, err) in enumerate(V.RFC5424_CASES):
+        got = native.error_string(R5, int(res.status[i]))
+        assert got == err, (line, got, err)
+
+
+def test_empty_batch_and_empty_lines(dec, oracle):
+    data, offs = oracle.pack([])
+    res = dec.decode(data, offs)
+    assert res.n == 0
+    data, offs = oracle.pack([b"", b"", V.G1_LINE.encode(), b""])
+    assert_parity(dec, oracle, R5, data, offs)
+
+
+def test_ragged_and_long_lines(dec, oracle):
+    """lines longer than the shared-memory tile take the direct-from-global path; mixed with short ones."""
+    big_msg = b"x" * 300_000
+    lines = [V.G1_LINE.encode(), b"<13>1 " + V.TS.encode() + b" h a p m - " + big_msg,
+             b"<13>1 " + V.TS.encode() + b" h a p m [id k=\"" + b"v" * 250_000 + b"\\\"\"] tail  ",
+             V.G2_LINE.encode(), b"<13>1 " + V.TS.encode() + b" " + b"h" * 70_000 + b" a p m - z"] + [V.G2_LINE.encode()] * 300
+    data, offs = oracle.pack(lines)
+    assert_parity(dec, oracle, R5, data, offs)
+    assert_parity(dec, oracle, R5, data, offs, resident=True)
+
+
+def test_generated_1m_lines(dec, oracle, native):
+    data, offs = native.generate(native.FMT_RFC5424, 5424, 1_000_000, bad_frac=0.005)
+    res = assert_parity(dec, oracle, R5, data, offs)
+    bad = int((res.status != 0).sum())
+    assert 2000 < bad < 9000
+    assert dec.kernel_launches() > 0
+
+
+def test_generated_all_bad_and_resident(dec, oracle, native):
+    data, offs = native.generate(native.FMT_RFC5424, 99, 200_000, bad_frac=1.0)
+    assert_parity(dec, oracle, R5, data, offs, resident=True)
+
+
+def test_mutation_fuzz(dec, oracle, native):
+    """Random byte edits of valid lines (kept valid UTF-8 by using ASCII edits on ASCII lines)."""
+    rng = np.random.default_rng(1234)
+    data, offs = native.generate(native.FMT_RFC5424, 7, 100_000, bad_frac=0.0)
+    lines = [bytearray(data[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+    alphabet = b' []"\\=<>-1:TZ+.\t'
+    out = []
+    for ln in lines:
+        if any(b >= 0x80 for b in ln):
+            out.append(bytes(ln))
+            continue
+        k = int(rng.integers(1, 4))
+        for _ in range(k):
+            op = int(rng.integers(0, 3))
+            pos = int(rng.integers(0, max(len(ln), 1)))
+            ch = alphabet[int(rng.integers(0, len(alphabet)))]
+            if op == 0 and ln:
+                ln[pos] = ch
+            elif op == 1:
+                ln.insert(pos, ch)
+            elif ln:
+                del ln[pos]
+        out.append(bytes(ln))
+    d2, o2 = oracle.pack(out)
+    res = assert_parity(dec, oracle, R5, d2, o2)
+    assert int((res.status != 0).sum()) > 10_000
+
+
+def test_pageable_and_pinned_inputs_agree(dec, oracle, native):
+    data, offs = native.generate(native.FMT_RFC5424, 11, 300_000)
+    r1 = dec.decode(data, offs)
+    ts1, meta1 = r1.ts.copy(), r1.meta.copy()
+    pb = dec.host_alloc(len(data))
+    po = dec.host_alloc(offs.nbytes, dtype=np.int32)
+    pb[:] = data
+    po[:] = offs
+    r2 = dec.decode(pb, po)
+    assert np.array_equal(ts1.view(np.uint64), r2.ts.view(np.uint64)) and np.array_equal(meta1, r2.meta)
+
+
+def test_roundtrip_property_full_msg(dec, native):
+    """Size-independent property: for Ok rows, full_msg is the (BOM-stripped, right-trimmed) line and every
+    span lies inside its own line; holds at any batch size without the oracle."""
+    data, offs = native.generate(native.FMT_RFC5424, 3, 2_000_000, bad_frac=0.005)
+    res = dec.decode(data, offs)
+    ok = res.status == 0
+    lo, hi = offs[:-1][ok], offs[1:][ok]
+    for col in (res.hostname, res.appname, res.procid, res.msgid, res.full_msg):
+        o, l = col[ok, 0], col[ok, 1]
+        assert (o >= lo).all() and (o + l <= hi).all()
+    fo, fl = res.full_msg[ok, 0], res.full_msg[ok, 1]
+    assert ((fo == lo) | (fo == lo + 3)).all()
+    m = res.msg[ok]
+    has = m[:, 0] >= 0
+    assert (m[has, 0] + m[has, 1] <= fo[has] + fl[has]).all()
+    assert np.isfinite(res.ts[ok]).all() and (res.ts[ok] > 1.4e9).all() and (res.ts[ok] < 2.1e9).all()

@@ -1,0 +1,157 @@
+"""Pin the CPU oracle against every known-answer test the reference holds for the Decoder path
+ and against the derived behaviour vectors of Appendix A."""
+import struct
+
+import pytest
+
+import vectors as V
+
+R5, LT, GE = 0, 1, 2
+
+
+def f64_hex(x):
+    return struct.pack(">d", x).hex()
+
+
+def test_g1_rfc5424(oracle):  # rfc5424_decoder.rs:245-278
+    s = oracle.decode_debug(R5, V.G1_LINE)
+    assert s.startswith("Ok(Record { ts: 1438790025.637824, hostname: \"testhostname\", facility: Some(2), severity: Some(7), "
+                        "appname: Some(\"appname\"), procid: Some(\"69\"), msgid: Some(\"42\"), msg: Some(\"test message\")")
+    assert 'sd: Some([StructuredData { sd_id: Some("origin@123"), pairs: [("_software", String("te\\\\st sc\\"ript")), ("_swVersion", String("0.0.1"))] }])' in s
+    data, offs = oracle.pack([V.G1_LINE.encode()])
+    buf, _ = oracle.decode_dump(R5, data, offs)
+    assert b"ts=41d5708c6268d21c;" in buf  # exact f64 bits of 1438790025.637824 (two-rounding recipe)
+    assert f64_hex(1438790025.637824) == "41d5708c6268d21c"
+
+
+def test_g2_rfc5424_multiple_sd(oracle):  # rfc5424_decoder.rs:281-314
+    s = oracle.decode_debug(R5, V.G2_LINE)
+    assert s.count("StructuredData {") == 2
+    assert 'StructuredData { sd_id: Some("master@456"), pairs: [("_key", String("value")), ("_key2", String("value2"))] }' in s
+    assert 'msg: Some("test message")' in s
+
+
+def test_g3_gelf(oracle):  # gelf_decoder.rs:134-170
+    s = oracle.decode_debug(GE, V.G3_LINE)
+    assert s.startswith('Ok(Record { ts: 1385053862.3072, hostname: "example.org", facility: None, severity: Some(1), ')
+    assert 'msg: Some("A short message that helps you identify what is going on")' in s
+    assert 'full_msg: Some("Backtrace here\\n\\nmore stuff")' in s
+    assert 'pairs: [("_some_env_var", String("bar")), ("_some_info", String("foo")), ("_user_id", U64(9001))]' in s
+
+
+@pytest.mark.parametrize("line,err", V.GELF_ERRORS)
+def test_g4_g8_gelf_errors(oracle, line, err):  # gelf_decoder.rs:173-205
+    assert oracle.decode_debug(GE, line) == f'Err("{err}")'
+
+
+def test_g9_g12_ltsv_timestamps(oracle):  # ltsv_decoder.rs:369-393,475-487
+    cfg = oracle.LtsvConfig(V.LTSV_SCHEMA)
+    for line, ts in [(V.G9_LINE, 1438790025.99), (V.G10_LINE, 1438790025.637824), (V.G12_LINE, 1438790025.637824)]:
+        data, offs = oracle.pack([line.encode()])
+        buf, _ = oracle.decode_dump(LT, data, offs, cfg)
+        assert f"ts={f64_hex(ts)};".encode() in buf, (line, buf)
+
+
+def test_g11_ltsv_typed(oracle):  # ltsv_decoder.rs:396-472
+    cfg = oracle.LtsvConfig(V.LTSV_SCHEMA)
+    s = oracle.decode_debug(LT, V.G11_LINE, cfg)
+    assert s.startswith('Ok(Record { ts: 971211336.3, hostname: "testhostname", facility: None, severity: Some(3), ')
+    assert 'msg: Some("this is a test")' in s
+    for frag in ['("_name1", String("value1"))', '("_name 2", String(" value 2"))', '("_n3", String("v3"))',
+                 '("_counter", U64(42))', '("_score", I64(-1))', '("_mean", F64(0.42))', '("_done", Bool(true))']:
+        assert frag in s
+    data, offs = oracle.pack([V.G11_LINE.encode()])
+    buf, _ = oracle.decode_dump(LT, data, offs, cfg)
+    assert b"ts=41ccf1c124266666;" in buf
+
+
+def test_g13_g14_ltsv_suffixes(oracle):  # ltsv_decoder.rs:270-366
+    s = oracle.decode_debug(LT, V.G13_LINE, oracle.LtsvConfig(V.LTSV_SCHEMA_G13, V.LTSV_SUFFIX_G13))
+    for frag in ['("_counter_u64", U64(42))', '("_score_i64", I64(-1))', '("_mean_f64", F64(0.42))', '("_done_bool", Bool(true))']:
+        assert frag in s
+    s = oracle.decode_debug(LT, V.G14_LINE, oracle.LtsvConfig(V.LTSV_SCHEMA_G14, V.LTSV_SUFFIX_G14))
+    for frag in ['("_counter_u64", U64(42))', '("_score_i64", I64(-1))', '("_mean_f64", F64(0.42))', '("_done_bool", Bool(true))']:
+        assert frag in s
+    assert "_u64_u64" not in s
+
+
+def test_g15_record_display(oracle):  # record.rs:94-132
+    assert oracle.g15(0) == '[someid a="a string" b="123456" c="true" d="123.456" e="-123456" f]'
+    assert oracle.g15(1) == ('StructuredData { sd_id: Some("someid"), pairs: [("a", String("a string")), ("b", U64(123456)), '
+                             '("c", Bool(true)), ("d", F64(123.456)), ("e", I64(-123456)), ("_f", Null)] }')
+    assert oracle.g15(2) == ('Record { ts: 123.456, hostname: "hostname", facility: Some(3), severity: Some(8), appname: Some("app"), '
+                             'procid: Some("123"), msgid: None, msg: Some("msg"), full_msg: None, sd: None }')
+
+
+def _check(oracle, fmt, cases, cfg=None):
+    for line, err in cases:
+        s = oracle.decode_debug(fmt, line, cfg)
+        if err is None:
+            assert s.startswith("Ok("), (line, s)
+        else:
+            assert s == f'Err("{err}")', (line, s)
+
+
+def test_appendix_rfc5424(oracle):
+    _check(oracle, R5, V.RFC5424_CASES)
+    s = oracle.decode_debug(R5, V.RFC5424_CASES[0][0])  # E1: "-" stays Some("-")
+    assert 'facility: Some(4), severity: Some(2), appname: Some("su"), procid: Some("-"), msgid: Some("ID47"), msg: Some("\'su root\' failed")' in s
+    assert s.endswith("sd: None })")
+    s = oracle.decode_debug(R5, V.H + '[id a="\\\\"] m')  # E26
+    assert '("_a", String("\\\\"))' in s
+    s = oracle.decode_debug(R5, V.H + "- 　hello ")  # E27
+    assert 'msg: Some("hello")' in s
+    s = oracle.decode_debug(R5, "﻿<13>1 " + V.TS + " h a p m - x")  # E12: BOM not part of full_msg
+    assert 'full_msg: Some("<13>1 ' in s
+
+
+def test_appendix_ltsv(oracle):
+    _check(oracle, LT, V.LTSV_CASES)
+    _check(oracle, LT, V.LTSV_SCHEMA_CASES, oracle.LtsvConfig(V.LTSV_SCHEMA))
+    data, offs = oracle.pack([b"time:1\thost:h\tfoo", b"foo\tlevel:9\tbar", b""])
+    buf, o = oracle.decode_dump(LT, data, offs)
+    assert buf[o[0]:o[1]].endswith(b";out=1;28:Missing value for name 'foo'")
+    assert buf[o[1]:o[2]] == b"E:Severity level should be <= 7;out=1;28:Missing value for name 'foo'"
+    assert buf[o[2]:o[3]] == b"E:Missing timestamp;out=1;25:Missing value for name ''"
+    s = oracle.decode_debug(LT, "time:1\thost:a\thost:b")
+    assert 'hostname: "b"' in s
+
+
+def test_appendix_gelf(oracle):
+    _check(oracle, GE, V.GELF_CASES)
+    s = oracle.decode_debug(GE, '{"host":"h","x":null,"y":true,"z":-3,"w":2.5,"timestamp":0}')  # J7 sorted-key order
+    assert 'pairs: [("_w", F64(2.5)), ("_x", Null), ("_y", Bool(true)), ("_z", I64(-3))]' in s
+    s = oracle.decode_debug(GE, '{"host":"h","_x":1,"x":2,"timestamp":0}')  # J8
+    assert 'pairs: [("_x", U64(1)), ("_x", U64(2))]' in s
+    s = oracle.decode_debug(GE, '{"host":"h","timestamp":0,"k":"a\nb\\\nc"}')
+    assert '("_k", String("a\\nb\\\\nc"))' in s
+
+
+def test_timestamp_two_roundings_differ_from_decimal_parse(oracle):
+    """SURVEY.md §7 hard part 1: fl(fl(nanos)/1e9) != correctly rounded decimal in ~27% of stamps."""
+    import random
+    from datetime import datetime, timezone
+    rnd = random.Random(7)
+    differ = 0
+    n = 2000
+    for _ in range(n):
+        secs = rnd.randrange(1420070400, 2051222400)
+        us = rnd.randrange(1_000_000)
+        dt = datetime.fromtimestamp(secs, tz=timezone.utc)
+        s = dt.strftime("%Y-%m-%dT%H:%M:%S") + f".{us:06d}Z"
+        got = oracle.rfc3339(s.encode())
+        want = float(secs * 1_000_000_000 + us * 1000) / 1e9  # Python int->float is RNE like Rust's `as f64`
+        assert got == want, s
+        differ += got != float(f"{secs}.{us:06d}")
+    assert 0.15 < differ / n < 0.40
+
+
+def test_rust_f64_grammar(oracle):
+    ok = {"1": 1.0, "+1.5": 1.5, "-.5": -0.5, "5.": 5.0, "1e3": 1000.0, "1E-2": 0.01, "inf": float("inf"),
+          "-Infinity": float("-inf"), "1438790025.99": 1438790025.99, "9007199254740993": 9007199254740992.0,
+          "0.000000000000000000000000000000000000000000000001": 1e-48, "1e400": float("inf"), "4.9e-324": 5e-324}
+    for s, v in ok.items():
+        assert oracle.parse_f64(s.encode()) == v, s
+    for s in ["", "+", "-", ".", "e5", "1e", "1e+", "0x10", "1_0", " 1", "1 ", "infinit", "nane", "1.5.2", "--1"]:
+        assert oracle.parse_f64(s.encode()) is None, s
+    assert oracle.parse_f64(b"NaN") != oracle.parse_f64(b"NaN")
