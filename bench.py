@@ -27,7 +27,7 @@ sys.path.insert(0, str(REPO))
 FORMATS = {"rfc5424": 0, "ltsv": 1, "gelf": 2}
 SEEDS = {"rfc5424": 5424, "ltsv": 1757, "gelf": 0x6E1F}
 # generator parameter that lands the ACTUAL mean line length on the BASELINE.json shape
-GEN_MEAN = {"rfc5424": 171.0, "ltsv": 420.0, "gelf": 512.0}
+GEN_MEAN = {"rfc5424": 169.2, "ltsv": 420.0, "gelf": 512.0}
 TARGET_MEAN = {"rfc5424": 180, "ltsv": 420, "gelf": 512}
 DEFAULT_LINES = {"rfc5424": 10_000_000, "ltsv": 4_000_000, "gelf": 3_500_000}  # int32 offsets cap a batch at 2 GiB
 

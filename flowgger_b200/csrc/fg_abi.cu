@@ -91,6 +91,9 @@ struct fg_ctx {
     uint8_t* d_entry_meta = nullptr;
     uint32_t* d_counter = nullptr;
     uint8_t* d_flush = nullptr;
+    int2* d_tmp_name = nullptr;  // provisional side-table rows, indexed by byte offset / scratch_div
+    unsigned long long* d_tmp_val = nullptr;
+    uint8_t* d_tmp_meta = nullptr;
     size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
@@ -204,6 +207,9 @@ void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
     P.entry_name = c->d_entry_name;
     P.entry_val = c->d_entry_val;
     P.entry_meta = c->d_entry_meta;
+    P.tmp_name = c->d_tmp_name;
+    P.tmp_val = c->d_tmp_val;
+    P.tmp_meta = c->d_tmp_meta;
     P.entry_counter = c->d_counter;
     P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
     P.ltsv = c->ltsv;
@@ -359,6 +365,13 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     const size_t rows_bytes = col_off(c, C_COUNT);
     FG_CREATE_CUDA(cudaMalloc(&c->d_rows, rows_bytes));
     FG_CREATE_CUDA(cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
+    {
+        // a side-table row needs >= 2 input bytes in every format (LTSV ":\t"), >= 3 in RFC5424
+        const size_t tmp_cap = c->max_bytes / 2 + 64;
+        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_name, tmp_cap * sizeof(int2)));
+        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_val, tmp_cap * sizeof(unsigned long long)));
+        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_meta, tmp_cap));
+    }
     FG_CREATE_CUDA(cudaMalloc(&c->d_counter, 256));
     FG_CREATE_CUDA(cudaMemset(c->d_counter, 0, 256));
     for (int b = 0; b < 2; ++b) {
@@ -425,6 +438,9 @@ void fg_destroy(fg_ctx* c) {
     if (c->d_rows) cudaFree(c->d_rows);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_flush) cudaFree(c->d_flush);
+    if (c->d_tmp_name) cudaFree(c->d_tmp_name);
+    if (c->d_tmp_val) cudaFree(c->d_tmp_val);
+    if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
     if (c->d_ltsv_blob) cudaFree(c->d_ltsv_blob);
     if (c->h_rows) cudaFreeHost(c->h_rows);
     if (c->h_counts) cudaFreeHost(c->h_counts);

@@ -51,28 +51,26 @@ FG_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
 }
 FG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__constant__ SdTables c_sd_tables;
+
 template <int FMT>
 struct Format;
 
 template <>
 struct Format<0> {  // RFC5424
-    static FG_DEV void parse(bytes_t p, int len, LineResult& r, const ParseParams&) { rfc5424_parse_line(p, len, r); }
-    static FG_DEV void emit(bytes_t p, int len, int line_off, const LineResult& r, const EntrySink& s, uint32_t ebase,
-                            const ParseParams&) {
-        rfc5424_emit(p, len, line_off, r, s, ebase);
+    typedef R5Shared Shared;
+    static FG_DEV void init_shared(Shared& sh) {
+        // 320 bytes of DFA tables: constant memory -> shared (divergent indexing would serialise in the constant cache)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_sd_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.tab);
+        for (int k = threadIdx.x; k < (int)(sizeof(SdTables) / 4); k += blockDim.x) dst[k] = src[k];
     }
+    static FG_DEV void parse(bytes_t p, int len, int line_off, Shared& sh, LineResult& r, const EntrySink& tmp,
+                             const ParseParams&) {
+        rfc5424_parse_line(p, len, line_off, sh.tab, &sh.marks[0][threadIdx.x], r, tmp);
+    }
+    static FG_DEV uint32_t scratch_index(int line_off) { return (uint32_t)line_off / 3u; }
 };
-
-// out-of-line copies for the rare "line longer than the tile" path (generic loads from global)
-template <int FMT>
-__device__ __noinline__ void parse_from_global(const uint8_t* p, int len, LineResult& r, const ParseParams& P) {
-    Format<FMT>::parse(p, len, r, P);
-}
-template <int FMT>
-__device__ __noinline__ void emit_from_global(const uint8_t* p, int len, int line_off, const LineResult& r,
-                                              const EntrySink& s, uint32_t ebase, const ParseParams& P) {
-    Format<FMT>::emit(p, len, line_off, r, s, ebase, P);
-}
 
 template <int FMT>
 __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_constant__ ParseParams P) {
@@ -80,14 +78,17 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
     __shared__ uint32_t s_ebase;
+    __shared__ typename Format<FMT>::Shared fsh;
 
     const int tid = threadIdx.x;
     const int first = blockIdx.x * kLinesPerCta;
     const int last = min(P.n, first + kLinesPerCta);
     if (tid == 0) mbar_init(&mbar, 1);
+    Format<FMT>::init_shared(fsh);
     __syncthreads();
 
     const EntrySink sink = {P.entry_name, P.entry_val, P.entry_meta};
+    const EntrySink tmp = {P.tmp_name, P.tmp_val, P.tmp_meta};
     uint32_t parity = 0;
     int cur = first;
     while (cur < last) {
@@ -113,25 +114,28 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
             parity ^= 1u;
         }
         const bool active = tid < r;
-        const int len = o1 - o0;
+        const int len = active ? o1 - o0 : 0;  // idle lanes run the lock-step phases on an empty line
         LineResult res;
-        res.n_entries = 0;
-        if (active) {
-            if (!direct) Format<FMT>::parse(tile + (o0 - base), len, res, P);
-            else parse_from_global<FMT>(P.bytes + o0, len, res, P);
-        }
+        if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, fsh, res, tmp, P);
+        else Format<FMT>::parse(P.bytes + o0, len, o0, fsh, res, tmp, P);
+        const uint32_t my_n = (active && res.status == FG_ST_OK) ? res.n_entries : 0u;
         uint32_t total;
-        const uint32_t excl = block_exclusive_scan(active ? res.n_entries : 0u, scan_ws, total);
+        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
         uint32_t my_begin = 0;
         if (total) {  // CTA-uniform
             if (tid == 0) s_ebase = atomicAdd(P.entry_counter, total);
             __syncthreads();
             const uint32_t ebase = s_ebase;
             const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
-            if (active && res.n_entries && !ovf) {
+            if (my_n && !ovf) {
+                // compact this line's staged rows from the scratch table into the side table
                 my_begin = ebase + excl;
-                if (!direct) Format<FMT>::emit(tile + (o0 - base), len, o0, res, sink, my_begin, P);
-                else emit_from_global<FMT>(P.bytes + o0, len, o0, res, sink, my_begin, P);
+                const uint32_t src = Format<FMT>::scratch_index(o0);
+                for (uint32_t k = 0; k < my_n; ++k) {
+                    sink.name[my_begin + k] = tmp.name[src + k];
+                    sink.val[my_begin + k] = tmp.val[src + k];
+                    sink.meta[my_begin + k] = tmp.meta[src + k];
+                }
             }
         }
         if (active) {
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
             // error rows: full.off = absolute byte offset of the failing part (LTSV side effects), len 0
             P.full[i] = ok ? make_int2(res.full_o >= 0 ? o0 + res.full_o : -1, res.full_l)
                            : make_int2(o0 + max(res.full_o, 0), 0);
-            P.sd[i] = make_int2((int)my_begin, (int)(ok ? res.n_entries : 0u));
+            P.sd[i] = make_int2((int)my_begin, (int)my_n);
         }
         __syncthreads();  // tile and scan scratch are reused by the next round
         cur += r;
@@ -159,6 +163,12 @@ static int g_max_tile = 48 * 1024;
 
 cudaError_t configure_kernels(int max_tile_bytes) {
     g_max_tile = max_tile_bytes;
+    {
+        SdTables t;
+        sd_tables_fill(t);
+        cudaError_t e0 = cudaMemcpyToSymbol(c_sd_tables, &t, sizeof t);
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = cudaFuncSetAttribute(parse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     return e;
 }

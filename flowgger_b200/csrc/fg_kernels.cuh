@@ -36,6 +36,10 @@ struct ParseParams {
     int2* entry_name;
     unsigned long long* entry_val;
     uint8_t* entry_meta;
+    // provisional rows of a line, indexed by its byte offset (see Format<>::scratch_index)
+    int2* tmp_name;
+    unsigned long long* tmp_val;
+    uint8_t* tmp_meta;
     uint32_t* entry_counter;  // running total (atomic bump, one add per CTA round)
     uint32_t entry_cap;
     LtsvDeviceConfig ltsv;

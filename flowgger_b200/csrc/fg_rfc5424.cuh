@@ -8,13 +8,19 @@
 // the table carries the raw value span plus FG_EM_UNESCAPE.
 //
 // One thread owns one line whose bytes are already staged in shared memory by
-// the CTA-wide bulk copy (fg_kernels.cu); all positions are relative to the
-// line start.
+// the CTA-wide bulk copy (fg_kernels.cu).  SIMT discipline: the 32 lines of a
+// warp advance in LOCK STEP through the same phases; every data-dependent loop
+// is a warp-uniform `while (__any_sync(..))` whose body is predicated per lane,
+// so lanes never skew into different code (the first version of this kernel
+// averaged 1.95 active lanes per instruction, see profiles/r1_notes.md).
+// All 32 lanes of a warp MUST call rfc5424_parse_line (idle lanes with len = 0).
 #pragma once
 #include "fg_common.cuh"
 #include "fg_status.h"
 
 namespace fg {
+
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
 struct LineResult {
     double ts;
@@ -22,105 +28,97 @@ struct LineResult {
     uint32_t facility, severity, flags;
     // spans relative to the line start; off < 0 => None
     int host_o, host_l, app_o, app_l, proc_o, proc_l, mid_o, mid_l, msg_o, msg_l, full_o, full_l;
-    uint32_t n_entries;  // SD headers + pairs
-    int sd_pos;          // where the SD text starts (position of the first '['), for the emit pass
+    uint32_t n_entries;  // SD headers + pairs staged in the scratch table
 };
 
+// provisional side-table rows of one line live at scratch index line_off/3 + k
+// (an SD header needs >= 3 input bytes, a pair >= 4, so ranges of different lines never overlap)
 struct EntrySink {
     int2* name;
     unsigned long long* val;
     uint8_t* meta;
 };
 
-// The structured-data walk (parse_data :134-158 + parse_sd_data :174-242) as
-// an explicit 5-state machine.  The reference's 6-tuple match collapses to:
-//   OUT  : !in_name, name None, !in_value        NAME : in_name
-//   EQ   : name Some, !in_value (only '"' legal) VAL  : in_value, !esc
-//   VESC : in_value, esc
-// EMIT=false counts entries and finds the message; EMIT=true re-walks an
-// already validated SD text and writes the side-table rows.
-template <bool EMIT>
-FG_DEV uint32_t rfc5424_sd_walk(bytes_t p, int len, int pos, int line_off, uint32_t& n_entries, int& msg_from,
-                                const EntrySink& sink, uint32_t ebase) {
-    uint32_t n = 0;
-    for (;;) {
-        // parse_sd_data(line, pos + 1): sd_id = up to the first ' '
-        int s = pos + 1;
-        while (s < len && p[s] != ' ') ++s;
-        if (s >= len) return FG_E5_MISSING_SD;  // :177
-        const uint32_t header = n++;
-        uint32_t pairs = 0;
-        int i = s + 1;
-        int state = 0;  // 0 OUT, 1 NAME, 2 EQ, 3 VAL, 4 VESC
-        int name_start = 0, name_end = 0, value_start = 0;
-        bool has_bs = false;
-        int after = -1;
-        for (; i < len; ++i) {
-            const uint32_t c = p[i];
-            if (state == 3) {
-                if (c == '\\') {
-                    state = 4;
-                    has_bs = true;
-                } else if (c == '"') {
-                    if (EMIT) {
-                        const uint32_t e = ebase + n;
-                        sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
-                        sink.val[e] = (unsigned long long)(uint32_t)(line_off + value_start) |
-                                      ((unsigned long long)(uint32_t)(i - value_start) << 32);
-                        sink.meta[e] = (uint8_t)(0u /*FG_TAG_STRING*/ | (has_bs ? 0x08u : 0u));
-                    }
-                    ++n;
-                    ++pairs;
-                    state = 0;
-                }
-            } else if (state == 4) {
-                state = 3;
-            } else if (state == 0) {
-                if (c == ' ' || c == '"') {
-                } else if (c == ']') {
-                    after = i + 1;
-                    break;
-                } else if (c >= 33u && c <= 126u && c != '=') {  // is_sd_name :188-192 ('"' and ']' handled above)
-                    state = 1;
-                    name_start = i;
-                } else {
-                    return FG_E5_SD_FORMAT;  // :235
-                }
-            } else if (state == 1) {
-                if (c == '=') {
-                    name_end = i;
-                    state = 2;
-                } else if (!(c >= 33u && c <= 126u && c != '"' && c != ']')) {
-                    return FG_E5_SD_FORMAT;
-                }
-            } else {  // state 2: only '"' opens the value (:212)
-                if (c != '"') return FG_E5_SD_FORMAT;
-                state = 3;
-                value_start = i + 1;
-                has_bs = false;
-            }
-        }
-        if (after < 0) return FG_E5_SD_NO_END;  // :239
-        if (EMIT) {
-            const uint32_t e = ebase + header;
-            sink.name[e] = make_int2(line_off + pos + 1, s - (pos + 1));
-            sink.val[e] = pairs;
-            sink.meta[e] = 7u;  // FG_TAG_SD_HEADER
-        }
-        if (after >= len) return FG_E5_MISSING_MSG;  // :148
-        const uint32_t c = p[after];
-        if (c == '[') {
-            pos = after;
-            continue;
-        }
-        if (c != ' ') return FG_E5_MALFORMED;  // :154
-        msg_from = after;
-        n_entries = n;
-        return FG_ST_OK;
+// --- structured-data DFA (parse_data :134-158 + parse_sd_data :174-242) ------------------------
+// The reference's 6-tuple match collapses to these states:
+//   ID    scanning sd_id up to the first ' ' (:175-177)
+//   OUT   !in_name, name None, !in_value        NAME  in_name
+//   EQ    name Some, !in_value (only '"' legal) VAL   in_value, !esc      VESC  in_value, esc
+//   AFTER the byte right after the closing ']' (:145-155)
+enum : uint32_t { SD_ID = 0, SD_OUT = 1, SD_NAME = 2, SD_EQ = 3, SD_VAL = 4, SD_VESC = 5, SD_AFTER = 6, SD_DONE = 7 };
+// byte classes
+enum : uint32_t { CL_SP = 0, CL_QUOTE = 1, CL_BS = 2, CL_EQ = 3, CL_RB = 4, CL_LB = 5, CL_NAME = 6, CL_OTHER = 7 };
+// actions
+enum : uint32_t {
+    AC_NONE = 0, AC_ID_END = 1, AC_NAME_START = 2, AC_NAME_END = 3, AC_BS = 4, AC_PAIR = 5, AC_CLOSE = 6, AC_OPEN = 7,
+    AC_MSG = 8, AC_ERR_FORMAT = 9, AC_ERR_MALFORMED = 10
+};
+
+struct SdTables {
+    uint8_t cls[256];   // byte -> class
+    uint8_t tr[8 * 8];  // state*8 + class -> next | action << 3
+};
+
+__host__ __device__ constexpr uint8_t sd_tr(uint32_t next, uint32_t act) { return (uint8_t)(next | (act << 3)); }
+
+__host__ __device__ inline void sd_tables_fill(SdTables& t) {
+    for (int c = 0; c < 256; ++c) {
+        uint8_t k;
+        if (c == ' ') k = CL_SP;
+        else if (c == '"') k = CL_QUOTE;
+        else if (c == '\\') k = CL_BS;
+        else if (c == '=') k = CL_EQ;
+        else if (c == ']') k = CL_RB;
+        else if (c == '[') k = CL_LB;
+        else if (c >= 33 && c <= 126) k = CL_NAME;  // is_sd_name :188-192
+        else k = CL_OTHER;
+        t.cls[c] = k;
     }
+    for (int s = 0; s < 8; ++s)
+        for (int c = 0; c < 8; ++c) {
+            uint8_t e = sd_tr(SD_DONE, AC_ERR_FORMAT);  // :235
+            const bool namech = (c == CL_NAME || c == CL_LB || c == CL_BS);
+            switch (s) {
+                case SD_ID: e = (c == CL_SP) ? sd_tr(SD_OUT, AC_ID_END) : sd_tr(SD_ID, AC_NONE); break;
+                case SD_OUT:
+                    if (c == CL_SP || c == CL_QUOTE) e = sd_tr(SD_OUT, AC_NONE);        // :194, :232
+                    else if (c == CL_RB) e = sd_tr(SD_AFTER, AC_CLOSE);                  // :197
+                    else if (namech) e = sd_tr(SD_NAME, AC_NAME_START);                  // :201
+                    break;
+                case SD_NAME:
+                    if (namech) e = sd_tr(SD_NAME, AC_NONE);                             // :205
+                    else if (c == CL_EQ) e = sd_tr(SD_EQ, AC_NAME_END);                  // :208
+                    break;
+                case SD_EQ:
+                    if (c == CL_QUOTE) e = sd_tr(SD_VAL, AC_NONE);                       // :212
+                    break;
+                case SD_VAL:
+                    if (c == CL_BS) e = sd_tr(SD_VESC, AC_BS);                           // :216
+                    else if (c == CL_QUOTE) e = sd_tr(SD_OUT, AC_PAIR);                  // :217
+                    else e = sd_tr(SD_VAL, AC_NONE);                                     // :231
+                    break;
+                case SD_VESC: e = sd_tr(SD_VAL, AC_NONE); break;                         // :231
+                case SD_AFTER:
+                    if (c == CL_LB) e = sd_tr(SD_ID, AC_OPEN);                           // :145
+                    else if (c == CL_SP) e = sd_tr(SD_DONE, AC_MSG);                     // :153
+                    else e = sd_tr(SD_DONE, AC_ERR_MALFORMED);                           // :154
+                    break;
+                default: e = sd_tr(SD_DONE, AC_NONE); break;
+            }
+            t.tr[s * 8 + c] = e;
+        }
 }
 
-FG_DEV void rfc5424_parse_line(bytes_t p, int len, LineResult& r) {
+// Per-CTA scratch in shared memory used by the RFC5424 parser
+struct R5Shared {
+    SdTables tab;
+    int marks[6][128];  // [space index][thread]: positions of the first six spaces
+};
+
+// p: line bytes (shared memory, or global for oversized lines); len may be 0 for idle lanes.
+// marks: &sh.marks[0][threadIdx.x] (stride 128 ints between slots).
+FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables& tab, int* marks, LineResult& r,
+                               const EntrySink& sink) {
     r.ts = 0.0;
     r.facility = 0xFFu;
     r.severity = 0xFFu;
@@ -128,120 +126,169 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, LineResult& r) {
     r.host_o = r.app_o = r.proc_o = r.mid_o = r.msg_o = r.full_o = -1;
     r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
     r.n_entries = 0;
-    r.sd_pos = -1;
+    uint32_t status = FG_ST_OK;
 
-    // BOM::parse :63-71
+    // ---- BOM::parse :63-71 ---------------------------------------------------------------------
     int b = 0;
-    if (len >= 3 && p[0] == 0xEFu && p[1] == 0xBBu && p[2] == 0xBFu) {
-        b = 3;
-    } else if (!(len > 0 && p[0] == '<')) {
-        r.status = FG_E5_BOM;
-        return;
-    }
-    // splitn(7, ' ') :23 — positions of the first six spaces
-    int sp[6];
+    if (len >= 3 && p[0] == 0xEFu && p[1] == 0xBBu && p[2] == 0xBFu) b = 3;
+    else if (!(len > 0 && p[0] == '<')) status = FG_E5_BOM;
+
+    // ---- splitn(7, ' ') :23 — first six spaces, scanned a 32-bit word at a time ----------------------
     int nsp = 0;
     {
-        int i = b;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            sp[k] = len;
-            if (nsp == k) {
-                while (i < len && p[i] != ' ') ++i;
-                if (i < len) {
-                    sp[k] = i;
+        const uint8_t* q = p + b;
+        const uint32_t s0 = (uint32_t)(size_t)q & 3u;
+        const uint32_t* wq = (const uint32_t*)(q - s0);
+        const int nwords = (status == FG_ST_OK) ? (int)((s0 + (uint32_t)(len - b) + 3u) >> 2) : 0;
+        int k = 0;
+        bool active = nwords > 0;
+        while (__any_sync(kFullMask, active)) {
+            if (active) {
+                const uint32_t x = wq[k] ^ 0x20202020u;
+                uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every byte == ' '
+                if (k == 0) z &= 0xFFFFFFFFu << (8u * s0);
+                while (z != 0 && nsp < 6) {
+                    const int j = (__ffs((int)z) - 1) >> 3;
+                    marks[nsp * 128] = b + 4 * k + j - (int)s0;
                     ++nsp;
-                    ++i;
+                    z &= z - 1;
                 }
+                ++k;
+                active = (k < nwords) && (nsp < 6);
             }
         }
     }
-    // parse_pri_version :74-92 on part0 = [b, sp[0])
+    int sp0, sp1, sp2, sp3, sp4, sp5;
     {
-        const int e0 = sp[0];
+        // marks past the end of the line come from the bytes after it in the last word: drop them
+        int v;
+        v = nsp > 0 ? marks[0 * 128] : len; sp0 = v < len ? v : len;
+        v = nsp > 1 ? marks[1 * 128] : len; sp1 = v < len ? v : len;
+        v = nsp > 2 ? marks[2 * 128] : len; sp2 = v < len ? v : len;
+        v = nsp > 3 ? marks[3 * 128] : len; sp3 = v < len ? v : len;
+        v = nsp > 4 ? marks[4 * 128] : len; sp4 = v < len ? v : len;
+        v = nsp > 5 ? marks[5 * 128] : len; sp5 = v < len ? v : len;
+        nsp = (sp0 < len) + (sp1 < len) + (sp2 < len) + (sp3 < len) + (sp4 < len) + (sp5 < len);
+    }
+    __syncwarp();
+
+    // ---- parse_pri_version :74-92 on part0 = [b, sp0) --------------------------------------------
+    if (status == FG_ST_OK) {
+        const int e0 = sp0;
         if (!(b < e0 && p[b] == '<')) {
-            r.status = FG_E5_PRI_BRACKETS;
-            return;
+            status = FG_E5_PRI_BRACKETS;
+        } else {
+            int gt = b + 1;
+            while (gt < e0 && p[gt] != '>') ++gt;
+            uint32_t pri = 0;
+            if (!parse_u8(p, b + 1, gt, pri)) status = FG_E5_INVALID_PRI;
+            else if (gt >= e0) status = FG_E5_MISSING_VERSION;
+            else if (!(e0 - gt == 2 && p[gt + 1] == '1')) status = FG_E5_UNSUPPORTED_VERSION;
+            else {
+                r.facility = pri >> 3;
+                r.severity = pri & 7u;
+            }
         }
-        int gt = b + 1;
-        while (gt < e0 && p[gt] != '>') ++gt;
-        uint32_t pri;
-        if (!parse_u8(p, b + 1, gt, pri)) {
-            r.status = FG_E5_INVALID_PRI;
-            return;
+    }
+    __syncwarp();
+    // ---- timestamp :25, :94-103 ---------------------------------------------------------------
+    if (status == FG_ST_OK) {
+        if (nsp < 1) status = FG_E5_MISSING_TS;
+        else if (!parse_rfc3339(p, sp0 + 1, sp1, r.ts)) status = FG_E5_BAD_TS;
+        else if (nsp < 6) status = FG_E5_MISSING_HOST + (uint32_t)(nsp - 1);  // :26-30 in order
+    }
+    __syncwarp();
+
+    // ---- parse_data :127-161 on part6 = [sp5+1, len) -----------------------------------------------
+    const int d = sp5 + 1;
+    int msg_from = len;
+    bool walk = false;
+    if (status == FG_ST_OK) {
+        if (d >= len) status = FG_E5_MISSING_MSG;  // :129
+        else {
+            const uint32_t c0 = p[d];
+            if (c0 == '-') msg_from = d + 1;
+            else if (c0 == '[') walk = true;
+            else status = FG_E5_MALFORMED;  // :159
         }
-        if (gt >= e0) {
-            r.status = FG_E5_MISSING_VERSION;
-            return;
-        }
-        if (!(e0 - gt == 2 && p[gt + 1] == '1')) {
-            r.status = FG_E5_UNSUPPORTED_VERSION;
-            return;
-        }
-        r.facility = pri >> 3;
-        r.severity = pri & 7u;
     }
-    if (nsp < 1) {
-        r.status = FG_E5_MISSING_TS;
-        return;
-    }
-    if (!parse_rfc3339(p, sp[0] + 1, sp[1], r.ts)) {
-        r.status = FG_E5_BAD_TS;
-        return;
-    }
-    if (nsp < 6) {
-        r.status = FG_E5_MISSING_HOST + (uint32_t)(nsp - 1);  // :26-30 in order
-        return;
-    }
-    // parse_data :127-161 on part6 = [sp[5]+1, len)
-    const int d = sp[5] + 1;
-    if (d >= len) {
-        r.status = FG_E5_MISSING_MSG;  // :129
-        return;
-    }
-    const uint32_t c0 = p[d];
-    int msg_from;
-    if (c0 == '-') {
-        msg_from = d + 1;
-    } else if (c0 == '[') {
-        EntrySink none = {nullptr, nullptr, nullptr};
-        uint32_t st = rfc5424_sd_walk<false>(p, len, d, 0, r.n_entries, msg_from, none, 0);
-        if (st != FG_ST_OK) {
-            r.status = st;
-            r.n_entries = 0;
-            return;
-        }
-        r.sd_pos = d;
-    } else {
-        r.status = FG_E5_MALFORMED;  // :159
-        return;
-    }
-    // parse_msg :163-172
     {
-        int hi = trim_end(p, msg_from, len);
-        int lo = trim_start(p, msg_from, hi);
+        // structured data: table-driven DFA, one byte per lane per iteration, warp in lock step
+        uint32_t state = SD_ID, n = 1, pairs = 0, hdr = 0, has_bs = 0;
+        int i = d + 1, elem_start = d + 1, name_start = 0, name_end = 0;
+        const uint32_t sbase = (uint32_t)line_off / 3u;
+        bool active = walk && i < len;
+        if (walk && !active) status = FG_E5_MISSING_SD;  // "[" is the last byte: no ' ' after the id
+        while (__any_sync(kFullMask, active)) {
+            if (active) {
+                const uint32_t c = p[i];
+                const uint32_t t = tab.tr[state * 8u + tab.cls[c]];
+                state = t & 7u;
+                const uint32_t act = t >> 3;
+                if (act != AC_NONE) {
+                    switch (act) {
+                        case AC_NAME_START: name_start = i; break;
+                        case AC_NAME_END: name_end = i; break;
+                        case AC_BS: has_bs = 0x08u; break;
+                        case AC_PAIR: {
+                            const uint32_t e = sbase + n;
+                            sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
+                            sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
+                                          ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
+                            sink.meta[e] = (uint8_t)has_bs;  // FG_TAG_STRING | FG_EM_UNESCAPE?
+                            ++n;
+                            ++pairs;
+                            has_bs = 0;
+                            break;
+                        }
+                        case AC_ID_END: sink.name[sbase + hdr] = make_int2(line_off + elem_start, i - elem_start); break;
+                        case AC_CLOSE:
+                            sink.val[sbase + hdr] = pairs;
+                            sink.meta[sbase + hdr] = 7u;  // FG_TAG_SD_HEADER
+                            break;
+                        case AC_OPEN:
+                            elem_start = i + 1;
+                            hdr = n++;
+                            pairs = 0;
+                            break;
+                        case AC_MSG: msg_from = i; break;
+                        case AC_ERR_FORMAT: status = FG_E5_SD_FORMAT; break;
+                        default: status = FG_E5_MALFORMED; break;
+                    }
+                }
+                ++i;
+                if (state == SD_DONE) {
+                    active = false;
+                } else if (i >= len) {
+                    active = false;
+                    status = state == SD_ID ? FG_E5_MISSING_SD : (state == SD_AFTER ? FG_E5_MISSING_MSG : FG_E5_SD_NO_END);
+                }
+            }
+        }
+        if (walk && status == FG_ST_OK) r.n_entries = n;
+    }
+
+    // ---- parse_msg :163-172, Record assembly :32-47 ------------------------------------------------
+    if (status == FG_ST_OK) {
+        const int hi = trim_end(p, msg_from, len);
+        const int lo = trim_start(p, msg_from, hi);
         if (hi > lo) {
             r.msg_o = lo;
             r.msg_l = hi - lo;
         }
+        r.host_o = sp1 + 1;
+        r.host_l = sp2 - sp1 - 1;
+        r.app_o = sp2 + 1;
+        r.app_l = sp3 - sp2 - 1;
+        r.proc_o = sp3 + 1;
+        r.proc_l = sp4 - sp3 - 1;
+        r.mid_o = sp4 + 1;
+        r.mid_l = sp5 - sp4 - 1;
+        r.full_o = b;  // line.trim_end() of the BOM-stripped line :46
+        r.full_l = trim_end(p, b, len) - b;
     }
-    r.host_o = sp[1] + 1;
-    r.host_l = sp[2] - sp[1] - 1;
-    r.app_o = sp[2] + 1;
-    r.app_l = sp[3] - sp[2] - 1;
-    r.proc_o = sp[3] + 1;
-    r.proc_l = sp[4] - sp[3] - 1;
-    r.mid_o = sp[4] + 1;
-    r.mid_l = sp[5] - sp[4] - 1;
-    r.full_o = b;  // line.trim_end() of the BOM-stripped line :46
-    r.full_l = trim_end(p, b, len) - b;
-    r.status = FG_ST_OK;
-}
-
-FG_DEV void rfc5424_emit(bytes_t p, int len, int line_off, const LineResult& r, const EntrySink& sink, uint32_t ebase) {
-    uint32_t n;
-    int mf;
-    rfc5424_sd_walk<true>(p, len, r.sd_pos, line_off, n, mf, sink, ebase);
+    r.status = status;
+    __syncwarp();
 }
 
 }  // namespace fg
