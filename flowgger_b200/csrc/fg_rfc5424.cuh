@@ -213,56 +213,118 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
         }
     }
     {
-        // structured data: table-driven DFA, one byte per lane per iteration, warp in lock step
-        uint32_t state = SD_ID, n = 1, pairs = 0, hdr = 0, has_bs = 0;
-        int i = d + 1, elem_start = d + 1, name_start = 0, name_end = 0;
+        // Structured data, token-nested and in lock step: one outer iteration handles (per lane) either an
+        // sd_id or one name="value" pair; the byte scans inside are tiny warp-uniform loops, so a warp pays
+        // max-over-lanes of TOKEN lengths per step instead of a fat per-byte state machine.
+        //   st_id : at the first byte of an sd_id (state ID of the reference walk, :175-177)
+        //   !st_id: between params (state OUT: !in_name, name None, !in_value)
+        uint32_t n = 1, pairs = 0, hdr = 0;
+        int i = d + 1, elem_start = d + 1, id_end = 0;
+        bool st_id = true;
         const uint32_t sbase = (uint32_t)line_off / 3u;
-        bool active = walk && i < len;
-        if (walk && !active) status = FG_E5_MISSING_SD;  // "[" is the last byte: no ' ' after the id
+        bool active = walk;
         while (__any_sync(kFullMask, active)) {
-            if (active) {
-                const uint32_t c = p[i];
-                const uint32_t t = tab.tr[state * 8u + tab.cls[c]];
-                state = t & 7u;
-                const uint32_t act = t >> 3;
-                if (act != AC_NONE) {
-                    switch (act) {
-                        case AC_NAME_START: name_start = i; break;
-                        case AC_NAME_END: name_end = i; break;
-                        case AC_BS: has_bs = 0x08u; break;
-                        case AC_PAIR: {
-                            const uint32_t e = sbase + n;
-                            sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
-                            sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
-                                          ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
-                            sink.meta[e] = (uint8_t)has_bs;  // FG_TAG_STRING | FG_EM_UNESCAPE?
-                            ++n;
-                            ++pairs;
-                            has_bs = 0;
-                            break;
-                        }
-                        case AC_ID_END: sink.name[sbase + hdr] = make_int2(line_off + elem_start, i - elem_start); break;
-                        case AC_CLOSE:
-                            sink.val[sbase + hdr] = pairs;
-                            sink.meta[sbase + hdr] = 7u;  // FG_TAG_SD_HEADER
-                            break;
-                        case AC_OPEN:
-                            elem_start = i + 1;
-                            hdr = n++;
-                            pairs = 0;
-                            break;
-                        case AC_MSG: msg_from = i; break;
-                        case AC_ERR_FORMAT: status = FG_E5_SD_FORMAT; break;
-                        default: status = FG_E5_MALFORMED; break;
+            // (A) sd_id: up to the first ' '
+            {
+                bool run = active && st_id;
+                while (__any_sync(kFullMask, run)) {
+                    if (run) {
+                        if (i >= len) { run = false; active = false; status = FG_E5_MISSING_SD; }  // :177
+                        else if (p[i] == ' ') { run = false; id_end = i; ++i; st_id = false; }
+                        else ++i;
                     }
                 }
-                ++i;
-                if (state == SD_DONE) {
-                    active = false;
-                } else if (i >= len) {
-                    active = false;
-                    status = state == SD_ID ? FG_E5_MISSING_SD : (state == SD_AFTER ? FG_E5_MISSING_MSG : FG_E5_SD_NO_END);
+            }
+            // (B) OUT: skip ' ' and stray '"' (:194, :232)
+            {
+                bool run = active;
+                while (__any_sync(kFullMask, run)) {
+                    if (run) {
+                        if (i >= len) { run = false; active = false; status = FG_E5_SD_NO_END; }  // :239
+                        else {
+                            const uint32_t c = p[i];
+                            if (c == ' ' || c == '"') ++i;
+                            else run = false;
+                        }
+                    }
                 }
+            }
+            // classify the byte that ended (B)
+            bool do_name = false;
+            int name_start = 0, name_end = 0;
+            if (active) {
+                const uint32_t c = p[i];
+                if (c == ']') {  // :197 end of this element, then :145-155
+                    const uint32_t e = sbase + hdr;
+                    sink.name[e] = make_int2(line_off + elem_start, id_end - elem_start);
+                    sink.val[e] = pairs;
+                    sink.meta[e] = 7u;  // FG_TAG_SD_HEADER
+                    if (i + 1 >= len) { active = false; status = FG_E5_MISSING_MSG; }  // :148
+                    else {
+                        const uint32_t c2 = p[i + 1];
+                        if (c2 == '[') { elem_start = i + 2; i += 2; hdr = n++; pairs = 0; st_id = true; }
+                        else if (c2 == ' ') { msg_from = i + 1; active = false; }
+                        else { active = false; status = FG_E5_MALFORMED; }  // :154
+                    }
+                } else if (c >= 33u && c <= 126u && c != '=') {  // is_sd_name :188-192 ('"' and ']' excluded above)
+                    do_name = true;
+                    name_start = i;
+                    ++i;
+                } else {
+                    active = false;
+                    status = FG_E5_SD_FORMAT;  // :235
+                }
+            }
+            // (C) NAME: name chars up to '=' (:205, :208)
+            {
+                bool run = do_name;
+                while (__any_sync(kFullMask, run)) {
+                    if (run) {
+                        if (i >= len) { run = false; do_name = false; active = false; status = FG_E5_SD_NO_END; }
+                        else {
+                            const uint32_t c = p[i];
+                            if (c >= 33u && c <= 126u && c != '"' && c != '=' && c != ']') ++i;
+                            else run = false;
+                        }
+                    }
+                }
+            }
+            bool do_val = false;
+            bool has_bs = false;
+            if (do_name) {
+                if (p[i] != '=') { active = false; status = FG_E5_SD_FORMAT; }
+                else {
+                    name_end = i;
+                    ++i;
+                    if (i >= len) { active = false; status = FG_E5_SD_NO_END; }
+                    else if (p[i] != '"') { active = false; status = FG_E5_SD_FORMAT; }  // :212 is the only arm
+                    else { ++i; do_val = true; }
+                }
+            }
+            // (D) VAL: up to the first unescaped '"' (:216, :217, :231)
+            {
+                bool run = do_val;
+                while (__any_sync(kFullMask, run)) {
+                    if (run) {
+                        if (i >= len) { run = false; do_val = false; active = false; status = FG_E5_SD_NO_END; }
+                        else {
+                            const uint32_t c = p[i];
+                            if (c == '"') run = false;
+                            else if (c == '\\') { has_bs = true; i += 2; }
+                            else ++i;
+                        }
+                    }
+                }
+            }
+            if (do_val) {
+                const uint32_t e = sbase + n;
+                sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
+                sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
+                              ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
+                sink.meta[e] = (uint8_t)(has_bs ? 0x08u : 0u);  // FG_TAG_STRING | FG_EM_UNESCAPE
+                ++n;
+                ++pairs;
+                ++i;
             }
         }
         if (walk && status == FG_ST_OK) r.n_entries = n;
