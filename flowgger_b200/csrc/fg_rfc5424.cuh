@@ -223,31 +223,34 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
         bool st_id = true;
         const uint32_t sbase = (uint32_t)line_off / 3u;
         bool active = walk;
+        // Inner scans are written as `lim`-bounded loops whose only loop-carried value is the cursor:
+        // a lane that is not scanning has lim == i and falls through; nothing else is updated inside.
         while (__any_sync(kFullMask, active)) {
             // (A) sd_id: up to the first ' '
             {
-                bool run = active && st_id;
-                while (__any_sync(kFullMask, run)) {
-                    if (run) {
-                        if (i >= len) { run = false; active = false; status = FG_E5_MISSING_SD; }  // :177
-                        else if (p[i] == ' ') { run = false; id_end = i; ++i; st_id = false; }
-                        else ++i;
-                    }
+                const bool scan = active && st_id;
+                const int lim = scan ? len : i;
+                for (;;) {
+                    const bool more = (i < lim) && (p[i] != ' ');
+                    if (!__any_sync(kFullMask, more)) break;
+                    i += more ? 1 : 0;
+                }
+                if (scan) {
+                    if (i >= len) { active = false; status = FG_E5_MISSING_SD; }  // :177
+                    else { id_end = i; ++i; st_id = false; }
                 }
             }
             // (B) OUT: skip ' ' and stray '"' (:194, :232)
             {
-                bool run = active;
-                while (__any_sync(kFullMask, run)) {
-                    if (run) {
-                        if (i >= len) { run = false; active = false; status = FG_E5_SD_NO_END; }  // :239
-                        else {
-                            const uint32_t c = p[i];
-                            if (c == ' ' || c == '"') ++i;
-                            else run = false;
-                        }
-                    }
+                const int lim = active ? len : i;
+                for (;;) {
+                    uint32_t c = 0;
+                    if (i < lim) c = p[i];
+                    const bool more = (c == ' ') || (c == '"');
+                    if (!__any_sync(kFullMask, more)) break;
+                    i += more ? 1 : 0;
                 }
+                if (active && i >= len) { active = false; status = FG_E5_SD_NO_END; }  // :239
             }
             // classify the byte that ended (B)
             bool do_name = false;
@@ -277,22 +280,19 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
             }
             // (C) NAME: name chars up to '=' (:205, :208)
             {
-                bool run = do_name;
-                while (__any_sync(kFullMask, run)) {
-                    if (run) {
-                        if (i >= len) { run = false; do_name = false; active = false; status = FG_E5_SD_NO_END; }
-                        else {
-                            const uint32_t c = p[i];
-                            if (c >= 33u && c <= 126u && c != '"' && c != '=' && c != ']') ++i;
-                            else run = false;
-                        }
-                    }
+                const int lim = do_name ? len : i;
+                for (;;) {
+                    uint32_t c = 0;
+                    if (i < lim) c = p[i];
+                    const bool more = (c - 33u <= 93u) && c != '"' && c != '=' && c != ']';
+                    if (!__any_sync(kFullMask, more)) break;
+                    i += more ? 1 : 0;
                 }
             }
             bool do_val = false;
-            bool has_bs = false;
             if (do_name) {
-                if (p[i] != '=') { active = false; status = FG_E5_SD_FORMAT; }
+                if (i >= len) { active = false; status = FG_E5_SD_NO_END; }
+                else if (p[i] != '=') { active = false; status = FG_E5_SD_FORMAT; }
                 else {
                     name_end = i;
                     ++i;
@@ -302,29 +302,31 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
                 }
             }
             // (D) VAL: up to the first unescaped '"' (:216, :217, :231)
+            uint32_t has_bs = 0;
             {
-                bool run = do_val;
-                while (__any_sync(kFullMask, run)) {
-                    if (run) {
-                        if (i >= len) { run = false; do_val = false; active = false; status = FG_E5_SD_NO_END; }
-                        else {
-                            const uint32_t c = p[i];
-                            if (c == '"') run = false;
-                            else if (c == '\\') { has_bs = true; i += 2; }
-                            else ++i;
-                        }
-                    }
+                const int lim = do_val ? len : i;
+                for (;;) {
+                    uint32_t c = '"';
+                    if (i < lim) c = p[i];
+                    const bool more = c != '"';
+                    if (!__any_sync(kFullMask, more)) break;
+                    const uint32_t esc = (c == '\\') ? 1u : 0u;
+                    has_bs |= esc;
+                    i += more ? (int)(1u + esc) : 0;
                 }
             }
             if (do_val) {
-                const uint32_t e = sbase + n;
-                sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
-                sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
-                              ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
-                sink.meta[e] = (uint8_t)(has_bs ? 0x08u : 0u);  // FG_TAG_STRING | FG_EM_UNESCAPE
-                ++n;
-                ++pairs;
-                ++i;
+                if (i >= len) { active = false; status = FG_E5_SD_NO_END; }
+                else {
+                    const uint32_t e = sbase + n;
+                    sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
+                    sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
+                                  ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
+                    sink.meta[e] = (uint8_t)(has_bs ? 0x08u : 0u);  // FG_TAG_STRING | FG_EM_UNESCAPE
+                    ++n;
+                    ++pairs;
+                    ++i;
+                }
             }
         }
         if (walk && status == FG_ST_OK) r.n_entries = n;
