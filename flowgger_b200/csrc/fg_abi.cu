@@ -193,6 +193,7 @@ void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
     P.bytes = c->d_bytes;
     P.offsets = c->d_offsets + line0;
     P.n = n;
+    P.line0 = line0;
     P.tile_bytes = tile;
     uint8_t* r = c->d_rows;
     P.ts = (double*)(r + col_off(c, C_TS)) + line0;
@@ -367,7 +368,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
     {
         // a side-table row needs >= 2 input bytes in every format (LTSV ":\t"), >= 3 in RFC5424
-        const size_t tmp_cap = c->max_bytes / 2 + 64;
+        const size_t tmp_cap = c->max_bytes / 2 + (size_t)c->max_lines + 64;
         FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_name, tmp_cap * sizeof(int2)));
         FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_val, tmp_cap * sizeof(unsigned long long)));
         FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_meta, tmp_cap));

@@ -17,7 +17,11 @@
 
 #include "fg_common.cuh"
 #include "fg_rfc5424.cuh"
+#include "fg_ltsv.cuh"
 #include "fg_status.h"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace fg {
 
@@ -65,11 +69,26 @@ struct Format<0> {  // RFC5424
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.tab);
         for (int k = threadIdx.x; k < (int)(sizeof(SdTables) / 4); k += blockDim.x) dst[k] = src[k];
     }
-    static FG_DEV void parse(bytes_t p, int len, int line_off, Shared& sh, LineResult& r, const EntrySink& tmp,
-                             const ParseParams&) {
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int /*line_idx*/, bool /*active*/, Shared& sh,
+                             LineResult& r, const EntrySink& tmp, const ParseParams&) {
         rfc5424_parse_line(p, len, line_off, sh.tab, &sh.marks[0][threadIdx.x], r, tmp);
     }
-    static FG_DEV uint32_t scratch_index(int line_off) { return (uint32_t)line_off / 3u; }
+    // an SD header needs >= 3 input bytes and a pair >= 4: rows of different lines never overlap
+    static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
+};
+
+struct NoShared {};
+
+template <>
+struct Format<1> {  // LTSV
+    typedef NoShared Shared;
+    static FG_DEV void init_shared(Shared&) {}
+    // a pair needs >= 1 input byte plus its tab: at most len/2 + 1 rows per line
+    static FG_DEV uint32_t scratch_index(int line_off, int line_idx) { return (uint32_t)line_off / 2u + (uint32_t)line_idx; }
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, Shared&, LineResult& r,
+                             const EntrySink& tmp, const ParseParams& P) {
+        ltsv_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, P.ltsv, r, tmp);
+    }
 };
 
 template <int FMT>
@@ -116,8 +135,9 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
         const bool active = tid < r;
         const int len = active ? o1 - o0 : 0;  // idle lanes run the lock-step phases on an empty line
         LineResult res;
-        if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, fsh, res, tmp, P);
-        else Format<FMT>::parse(P.bytes + o0, len, o0, fsh, res, tmp, P);
+        const int lidx = P.line0 + i;  // index of the line inside the batch (unique scratch slot)
+        if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, lidx, active, fsh, res, tmp, P);
+        else Format<FMT>::parse(P.bytes + o0, len, o0, lidx, active, fsh, res, tmp, P);
         const uint32_t my_n = (active && res.status == FG_ST_OK) ? res.n_entries : 0u;
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
@@ -130,7 +150,7 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
             if (my_n && !ovf) {
                 // compact this line's staged rows from the scratch table into the side table
                 my_begin = ebase + excl;
-                const uint32_t src = Format<FMT>::scratch_index(o0);
+                const uint32_t src = Format<FMT>::scratch_index(o0, lidx);
                 for (uint32_t k = 0; k < my_n; ++k) {
                     sink.name[my_begin + k] = tmp.name[src + k];
                     sink.val[my_begin + k] = tmp.val[src + k];
@@ -169,7 +189,19 @@ cudaError_t configure_kernels(int max_tile_bytes) {
         cudaError_t e0 = cudaMemcpyToSymbol(c_sd_tables, &t, sizeof t);
         if (e0 != cudaSuccess) return e0;
     }
+    {
+        static Pow10Table t;
+        for (int k = 0; k <= 308; ++k) {
+            char buf[16];
+            snprintf(buf, sizeof buf, "1e%d", k);
+            t.v[k] = strtod(buf, nullptr);  // correctly rounded decimal literals, like rustc's POW10 table
+        }
+        cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);
+        if (e1 != cudaSuccess) return e1;
+    }
     cudaError_t e = cudaFuncSetAttribute(parse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(parse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     return e;
 }
 
@@ -178,6 +210,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
     switch (fmt) {
         case 0: parse_kernel<0><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        case 1: parse_kernel<1><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -185,7 +218,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
 
 const char* kernel_build_info() {
     return "flowgger_b200 parse kernels: sm_100a, thread-per-line over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse_kernel<rfc5424>]";
+           "kernels=[parse_kernel<rfc5424>, parse_kernel<ltsv>]";
 }
 
 }  // namespace fg

@@ -21,6 +21,7 @@ struct ParseParams {
     const uint8_t* bytes;     // device copy of the caller's byte buffer (base of all spans)
     const int32_t* offsets;   // [n+1] line offsets into bytes
     int32_t n;                // lines in this launch
+    int32_t line0;            // batch index of the first line of this launch
     int32_t tile_bytes;       // dynamic shared memory staging tile, multiple of 16
     // row columns, element 0 = first line of this launch
     double* ts;

@@ -1,0 +1,246 @@
+// fg_ltsv.cuh — one LTSV line -> Record fields, on device.
+//
+// B200-native replacement for LTSVDecoder::decode
+// (/root/reference/src/flowgger/decoder/ltsv_decoder.rs:87-221) and its helpers
+// rfc3339_to_unix :224-229, english_time_to_unix[_with_subsecond] :231-254,
+// unix_strtime_to_unix :256-261, parse_ts :263-267.  Schema / suffix configuration
+// (LTSVDecoder::new :24-83) arrives as flat device arrays (LtsvDeviceConfig).
+//
+// Lock-step discipline as in fg_rfc5424.cuh: one outer iteration = one tab-separated part per
+// lane; the byte scans inside are warp-uniform `lim`-bounded loops.
+#pragma once
+#include "fg_common.cuh"
+#include "fg_float.cuh"
+#include "fg_kernels.cuh"
+#include "fg_rfc5424.cuh"
+#include "fg_status.h"
+
+namespace fg {
+
+// "[day padding:none]/[month repr:short]/[year]:[hour]:[minute]:[second](.[subsecond]) [offset_hour sign:mandatory][offset_minute]"
+// (ltsv_decoder.rs:239-247), `time` 0.3 format-description semantics.
+__device__ __noinline__ bool parse_english_time(bytes_t p, int a, int b, bool with_subsecond, double& ts) {
+    int i = a;
+    DateTime t;
+    t.nanos = 0;
+    if (i >= b || !is_digit(p[i])) return false;
+    t.day = (int)(p[i++] - '0');
+    if (i < b && is_digit(p[i])) t.day = t.day * 10 + (int)(p[i++] - '0');
+    if (t.day == 0) return false;  // NonZeroU8
+    if (i >= b || p[i] != '/') return false;
+    ++i;
+    if (i + 3 > b) return false;
+    {
+        const uint32_t m3 = ((uint32_t)p[i] << 16) | ((uint32_t)p[i + 1] << 8) | (uint32_t)p[i + 2];
+        int m = 0;
+        switch (m3) {  // case-sensitive short month names
+            case 0x4A616E: m = 1; break;   // Jan
+            case 0x466562: m = 2; break;   // Feb
+            case 0x4D6172: m = 3; break;   // Mar
+            case 0x417072: m = 4; break;   // Apr
+            case 0x4D6179: m = 5; break;   // May
+            case 0x4A756E: m = 6; break;   // Jun
+            case 0x4A756C: m = 7; break;   // Jul
+            case 0x417567: m = 8; break;   // Aug
+            case 0x536570: m = 9; break;   // Sep
+            case 0x4F6374: m = 10; break;  // Oct
+            case 0x4E6F76: m = 11; break;  // Nov
+            case 0x446563: m = 12; break;  // Dec
+            default: return false;
+        }
+        t.month = m;
+        i += 3;
+    }
+    if (i >= b || p[i] != '/') return false;
+    ++i;
+    bool yneg = false;
+    if (i < b && (p[i] == '+' || p[i] == '-')) { yneg = p[i] == '-'; ++i; }
+    if (!four_digits(p, i, b, t.year)) return false;
+    if (yneg) t.year = -t.year;
+    if (i >= b || p[i] != ':') return false;
+    ++i;
+    if (!two_digits(p, i, b, t.hour)) return false;
+    if (i >= b || p[i] != ':') return false;
+    ++i;
+    if (!two_digits(p, i, b, t.minute)) return false;
+    if (i >= b || p[i] != ':') return false;
+    ++i;
+    if (!two_digits(p, i, b, t.second)) return false;
+    if (with_subsecond) {
+        if (i >= b || p[i] != '.') return false;
+        ++i;
+        if (!subsecond(p, i, b, t.nanos)) return false;
+    }
+    if (i >= b || p[i] != ' ') return false;
+    ++i;
+    if (i >= b || (p[i] != '+' && p[i] != '-')) return false;  // sign:mandatory
+    const bool oneg = p[i] == '-';
+    ++i;
+    int oh, om;
+    if (!two_digits(p, i, b, oh) || !two_digits(p, i, b, om)) return false;
+    if (oh > 25 || om > 59) return false;
+    t.offset_seconds = (oh * 3600 + om * 60) * (oneg ? -1 : 1);
+    if (i != b) return false;
+    return finish_datetime(t, false, ts);  // second == 60 is out of range for custom formats
+}
+
+// parse_ts :263-267: f64::from_str, then RFC3339, then the two English forms
+__device__ __noinline__ bool ltsv_parse_ts(bytes_t p, int a, int b, double& ts) {
+    if (parse_f64_rust(p, a, b, ts)) return true;
+    if (parse_rfc3339(p, a, b, ts)) return true;
+    if (parse_english_time(p, a, b, false, ts)) return true;
+    return parse_english_time(p, a, b, true, ts);
+}
+
+FG_DEV bool key_is(bytes_t p, int a, int n, const char* lit, int litn) {
+    if (n != litn) return false;
+    for (int k = 0; k < litn; ++k)
+        if (p[a + k] != (uint8_t)lit[k]) return false;
+    return true;
+}
+
+// schema.get(name) :129 — linear scan of the (small) configured key set; returns the fg_ltsv_type or 0 (string)
+__device__ __noinline__ int ltsv_schema_type(bytes_t p, int a, int n, const LtsvDeviceConfig& cfg) {
+    for (int k = 0; k < cfg.n_schema; ++k) {
+        const int o = cfg.name_off[k], l = cfg.name_off[k + 1] - o;
+        if (l != n) continue;
+        bool eq = true;
+        for (int j = 0; j < n && eq; ++j) eq = cfg.names[o + j] == p[a + j];
+        if (eq) return cfg.types[k];
+    }
+    return 0;
+}
+// !name.ends_with(suffix) :131 etc.
+__device__ __noinline__ bool ltsv_needs_suffix(bytes_t p, int a, int n, int type, const LtsvDeviceConfig& cfg) {
+    if (!((cfg.suffix_present >> type) & 1u)) return false;
+    const int o = cfg.suffix_off[type], l = cfg.suffix_off[type + 1] - o;
+    if (l > n) return true;
+    for (int j = 0; j < l; ++j)
+        if (cfg.suffix[o + j] != p[a + n - l + j]) return true;
+    return false;
+}
+
+// All 32 lanes of a warp must call this (idle lanes with len = 0, active_line = false).
+FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bool active_line,
+                            const LtsvDeviceConfig& cfg, LineResult& r, const EntrySink& sink) {
+    r.ts = 0.0;
+    r.facility = 0xFFu;
+    r.severity = 0xFFu;
+    r.flags = 0;
+    r.host_o = r.app_o = r.proc_o = r.mid_o = r.msg_o = r.full_o = -1;
+    r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
+    r.n_entries = 0;
+    uint32_t status = FG_ST_OK, n = 0, flags = 0;
+    bool have_ts = false;
+    int err_pos = 0;
+    int part = 0;  // start of the current part
+    bool active = active_line;
+    while (__any_sync(kFullMask, active)) {  // line.split('\t') :94
+        // scan the part: first ':' (splitn(2, ':') :95) and the terminating tab
+        int i = part;
+        {
+            const int lim = active ? len : i;
+            for (;;) {
+                uint32_t c = '\t';
+                if (i < lim) c = p[i];
+                const bool more = c != '\t' && c != ':';
+                if (!__any_sync(kFullMask, more)) break;
+                i += more ? 1 : 0;
+            }
+        }
+        const bool has_colon = active && i < len && p[i] == ':';
+        const int colon = i;
+        {
+            const int lim = has_colon ? len : i;
+            for (;;) {
+                uint32_t c = '\t';
+                if (i < lim) c = p[i];
+                const bool more = c != '\t';
+                if (!__any_sync(kFullMask, more)) break;
+                i += more ? 1 : 0;
+            }
+        }
+        const int part_end = i;
+        if (active) {
+            if (!has_colon) {
+                flags |= 0x02u;  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
+            } else {
+                const int ka = part, kn = colon - part, va = colon + 1, vb = part_end;
+                if (key_is(p, ka, kn, "time", 4)) {  // :104-111
+                    int ta = va, tb = vb;
+                    if (tb - ta >= 2 && p[ta] == '[' && p[tb - 1] == ']') { ++ta; --tb; }
+                    if (ltsv_parse_ts(p, ta, tb, r.ts)) have_ts = true;
+                    else status = FG_EL_TS;
+                } else if (key_is(p, ka, kn, "host", 4)) {
+                    r.host_o = va;
+                    r.host_l = vb - va;
+                } else if (key_is(p, ka, kn, "message", 7)) {
+                    r.msg_o = va;
+                    r.msg_l = vb - va;
+                } else if (key_is(p, ka, kn, "level", 5)) {  // :114-121
+                    uint32_t sev;
+                    if (!parse_u8(p, va, vb, sev)) status = FG_EL_SEV;
+                    else if (sev > 7u) status = FG_EL_SEV_HIGH;
+                    else r.severity = sev;
+                } else {  // :122-199
+                    const int type = cfg.has_schema ? ltsv_schema_type(p, ka, kn, cfg) : 0;
+                    unsigned long long val = (unsigned long long)(uint32_t)(line_off + va) | ((unsigned long long)(uint32_t)(vb - va) << 32);
+                    uint32_t meta = 0;  // FG_TAG_STRING
+                    if (type == 1) {  // bool::from_str: exactly "true" / "false"
+                        if (key_is(p, va, vb - va, "true", 4)) val = 1;
+                        else if (key_is(p, va, vb - va, "false", 5)) val = 0;
+                        else status = FG_EL_BOOL;
+                        meta = 1;
+                    } else if (type == 2) {
+                        double f;
+                        if (!parse_f64_rust(p, va, vb, f)) status = FG_EL_F64;
+                        else val = (unsigned long long)__double_as_longlong(f);
+                        meta = 2;
+                    } else if (type == 3) {
+                        int64_t v;
+                        if (!parse_i64(p, va, vb, v)) status = FG_EL_I64;
+                        else val = (unsigned long long)v;
+                        meta = 3;
+                    } else if (type == 4) {
+                        uint64_t v;
+                        if (!parse_u64(p, va, vb, v)) status = FG_EL_U64;
+                        else val = v;
+                        meta = 4;
+                    }
+                    if (status == FG_ST_OK) {
+                        if (type != 0 && ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
+                        const uint32_t e = sbase + n;
+                        sink.name[e] = make_int2(line_off + ka, kn);
+                        sink.val[e] = val;
+                        sink.meta[e] = (uint8_t)meta;
+                        ++n;
+                    }
+                }
+            }
+            if (status != FG_ST_OK) {
+                err_pos = part;
+                active = false;
+            } else if (part_end >= len) {
+                active = false;
+            } else {
+                part = part_end + 1;
+            }
+        }
+    }
+    if (active_line && status == FG_ST_OK) {
+        if (!have_ts) { status = FG_EL_MISSING_TS; err_pos = len + 1; }             // :205
+        else if (r.host_o < 0) { status = FG_EL_MISSING_HOST; err_pos = len + 1; }  // :206
+    }
+    if (status == FG_ST_OK) {
+        r.full_o = 0;  // full_msg = the whole line, untrimmed :219
+        r.full_l = len;
+        r.n_entries = n;
+    } else {
+        r.full_o = err_pos;
+    }
+    r.flags = flags;
+    r.status = status;
+    __syncwarp();
+}
+
+}  // namespace fg

@@ -191,6 +191,98 @@ void gen_rfc5424(uint64_t seed, uint64_t idx, double mean_len, double bad_frac, 
     if (r.chance(0.01)) o.append((size_t)r.range(1, 3), ' ');
 }
 
+
+// C4: 20 tab-separated key:value fields — time (1/3 decimal unix, 1/3 [RFC3339], 1/3 [D/Mon/YYYY:HH:MM:SS(.f) +-HHMM]),
+// host, message, level and 16 free pairs (4 of them are the typed keys counter/score/mean/done so that the same
+// lines exercise a u64/i64/f64/bool schema); keys 2-12 B, values 0-24 B and may contain ':'.
+void gen_ltsv(uint64_t seed, uint64_t idx, double /*mean_len*/, double bad_frac, std::string& o) {
+    static const char* MON[12] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
+    Rng r(seed, idx);
+    const size_t line_start = o.size();
+    const bool bad = r.chance(bad_frac);
+    const int bad_kind = bad ? (int)r.below(12) : -1;
+    // field order is shuffled: position of the 4 special keys among 20 slots
+    int order[20];
+    for (int k = 0; k < 20; ++k) order[k] = k;
+    for (int k = 19; k > 0; --k) { int j = (int)r.below((uint32_t)k + 1); int t = order[k]; order[k] = order[j]; order[j] = t; }
+    char buf[64];
+    for (int slot = 0; slot < 20; ++slot) {
+        if (slot) o.push_back('\t');
+        const int f = order[slot];
+        if (f == 0) {  // time
+            if (bad_kind == 0) { o += "tim:1"; continue; }
+            o += "time:";
+            if (bad_kind == 1) { o += "yesterday"; continue; }
+            const int form = (int)r.below(3);
+            if (form == 0) {
+                snprintf(buf, sizeof buf, "%u", (unsigned)r.range(1420070400, 2051222400));
+                o += buf;
+                int fd = (int)r.below(4) * 3;
+                if (fd) { o.push_back('.'); for (int i = 0; i < fd; ++i) o.push_back((char)('0' + r.below(10))); }
+            } else if (form == 1) {
+                o.push_back('[');
+                rfc3339(r, o);
+                o.push_back(']');
+            } else {
+                int y = r.range(2015, 2035), m = r.range(1, 12), d = r.range(1, dim(y, m));
+                snprintf(buf, sizeof buf, "[%d/%s/%04d:%02d:%02d:%02d", d, MON[m - 1], y, r.range(0, 23), r.range(0, 59), r.range(0, 59));
+                o += buf;
+                if (r.chance(0.5)) { o.push_back('.'); int fd = r.range(1, 9); for (int i = 0; i < fd; ++i) o.push_back((char)('0' + r.below(10))); }
+                snprintf(buf, sizeof buf, " %c%02d%02d]", r.chance(0.5) ? '+' : '-', r.range(0, 14), (int)r.below(4) * 15);
+                o += buf;
+            }
+        } else if (f == 1) {  // host
+            if (bad_kind == 2) { o += "hostname:x"; continue; }
+            o += "host:";
+            rand_chars(r, o, r.range(8, 24), kHostChars, 38);
+        } else if (f == 2) {  // message
+            o += "message:";
+            message_text(r, o, r.range(10, 60), r.chance(0.02));
+        } else if (f == 3) {  // level
+            o += "level:";
+            if (bad_kind == 3) o += "9";
+            else if (bad_kind == 4) o += "high";
+            else o.push_back((char)('0' + r.below(8)));
+        } else if (f == 4) {
+            o += "counter:";
+            if (bad_kind == 5) o += "-5";
+            else { snprintf(buf, sizeof buf, "%llu", (unsigned long long)(r.next() >> (r.below(60)))); o += buf; }
+        } else if (f == 5) {
+            o += "score:";
+            if (bad_kind == 6) o += "1.5";
+            else { snprintf(buf, sizeof buf, "%lld", (long long)(r.next() >> (1 + r.below(60))) * (r.chance(0.5) ? -1 : 1)); o += buf; }
+        } else if (f == 6) {
+            o += "mean:";
+            if (bad_kind == 7) o += "n/a";
+            else {
+                const int form = (int)r.below(4);
+                if (form == 0) snprintf(buf, sizeof buf, "%.*f", r.range(0, 9), r.uniform() * 1000.0);
+                else if (form == 1) snprintf(buf, sizeof buf, "%.17g", (r.uniform() - 0.5) * std::pow(10.0, r.range(-30, 30)));
+                else if (form == 2) snprintf(buf, sizeof buf, "%ue%d", (unsigned)r.below(100000), r.range(-40, 40));
+                else snprintf(buf, sizeof buf, "%llu.%llu", (unsigned long long)(r.next() >> 10), (unsigned long long)(r.next() >> 20));
+                o += buf;
+            }
+        } else if (f == 7) {
+            o += "done:";
+            if (bad_kind == 8) o += "TRUE";
+            else o += r.chance(0.5) ? "true" : "false";
+        } else {
+            if (bad_kind == 9 && f == 8) { rand_chars(r, o, r.range(2, 12), kAlnum, 52); continue; }  // no ':' -> println!
+            rand_chars(r, o, r.range(2, 12), kAlnum, 52);
+            o.push_back(':');
+            if (bad_kind == 10 && f == 9) continue;  // empty value
+            const int vl = r.range(0, 24);
+            const bool utf8 = r.chance(0.01);
+            for (int i = 0; i < vl; ++i) {
+                if (utf8 && r.chance(0.2)) { o += kUtf8Bits[r.below(7)]; continue; }
+                char c = (char)r.range(32, 126);
+                o.push_back(c);
+            }
+        }
+    }
+    if (bad_kind == 11) o.resize(line_start);  // empty line
+}
+
 }  // namespace
 
 extern "C" {
@@ -213,6 +305,7 @@ int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, doubl
             for (int64_t i = lo; i < hi; ++i) {
                 const size_t before = o.size();
                 switch (kind) {
+                    case 1: gen_ltsv(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     default: gen_rfc5424(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                 }
                 lens[(size_t)t].push_back((int32_t)(o.size() - before));
