@@ -18,6 +18,7 @@
 #include "fg_common.cuh"
 #include "fg_rfc5424.cuh"
 #include "fg_ltsv.cuh"
+#include "fg_gelf.cuh"
 #include "fg_status.h"
 
 #include <cstdio>
@@ -88,6 +89,18 @@ struct Format<1> {  // LTSV
     static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, Shared&, LineResult& r,
                              const EntrySink& tmp, const ParseParams& P) {
         ltsv_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, P.ltsv, r, tmp);
+    }
+};
+
+template <>
+struct Format<2> {  // GELF
+    typedef NoShared Shared;
+    static FG_DEV void init_shared(Shared&) {}
+    // a top-level member needs >= 5 input bytes (`"":0,`)
+    static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, Shared&, LineResult& r,
+                             const EntrySink& tmp, const ParseParams&) {
+        gelf_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, r, tmp);
     }
 };
 
@@ -202,6 +215,8 @@ cudaError_t configure_kernels(int max_tile_bytes) {
     cudaError_t e = cudaFuncSetAttribute(parse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(parse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     return e;
 }
 
@@ -211,6 +226,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     switch (fmt) {
         case 0: parse_kernel<0><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
         case 1: parse_kernel<1><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        case 2: parse_kernel<2><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -218,7 +234,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
 
 const char* kernel_build_info() {
     return "flowgger_b200 parse kernels: sm_100a, thread-per-line over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse_kernel<rfc5424>, parse_kernel<ltsv>]";
+           "kernels=[parse_kernel<rfc5424>, parse_kernel<ltsv>, parse_kernel<gelf>]";
 }
 
 }  // namespace fg

@@ -283,6 +283,114 @@ void gen_ltsv(uint64_t seed, uint64_t idx, double /*mean_len*/, double bad_frac,
     if (bad_kind == 11) o.resize(line_start);  // empty line
 }
 
+
+void json_text(Rng& r, std::string& o, int target, bool rich) {
+    // message text with JSON escapes: \n \t \" \\ and (1% of strings) \uXXXX incl. surrogate pairs
+    const size_t start = o.size();
+    const int nw = (int)(sizeof kWords / sizeof kWords[0]);
+    const bool uni = r.chance(0.01);
+    while ((int)(o.size() - start) < target) {
+        if (o.size() > start) {
+            const double u = r.uniform();
+            if (rich && u < 0.06) o += "\\n";
+            else if (rich && u < 0.09) o += "\\t";
+            else if (rich && u < 0.11) o += "\\\"";
+            else if (rich && u < 0.12) o += "\\\\";
+            else if (uni && u < 0.20) o += r.chance(0.5) ? "\\u00e9" : "\\ud83d\\ude80";
+            else o.push_back(' ');
+        }
+        if (r.chance(0.03)) o += kUtf8Bits[r.below(7)];
+        else if (r.chance(0.15)) rand_chars(r, o, r.range(2, 10), kAlnum, 62);
+        else o += kWords[r.below((uint32_t)nw)];
+    }
+}
+
+// C3: GELF objects — version, host, short_message (40-120 B), full_message (150-300 B, escape rich), timestamp,
+// level, 3-8 `_extra` members (strings 60 %, ints 25 %, floats <= 15 significant digits 10 %, bool/null 5 %),
+// member order shuffled, random inter-token spaces; 0.5 % malformed.
+void gen_gelf(uint64_t seed, uint64_t idx, double /*mean_len*/, double bad_frac, std::string& o) {
+    Rng r(seed, idx);
+    const size_t line_start = o.size();
+    const bool bad = r.chance(bad_frac);
+    const int bad_kind = bad ? (int)r.below(16) : -1;
+    const int nextra = r.range(3, 8);
+    const int nmem = 6 + nextra;
+    int order[16];
+    for (int k = 0; k < nmem; ++k) order[k] = k;
+    for (int k = nmem - 1; k > 0; --k) { int j = (int)r.below((uint32_t)k + 1); int t = order[k]; order[k] = order[j]; order[j] = t; }
+    auto sp = [&]() { if (r.chance(0.3)) o.append((size_t)r.range(1, 2), ' '); };
+    char buf[64];
+    o.push_back('{');
+    bool first = true;
+    for (int slot = 0; slot < nmem; ++slot) {
+        const int f = order[slot];
+        if (f == 4 && bad_kind == 0) continue;  // no timestamp (valid: wall clock)
+        if (f == 1 && bad_kind == 1) continue;  // Missing hostname
+        if (!first) { o.push_back(','); }
+        first = false;
+        sp();
+        if (f == 0) {
+            o += "\"version\":"; sp();
+            o += bad_kind == 2 ? "\"2.0\"" : (bad_kind == 3 ? "1.1" : (r.chance(0.5) ? "\"1.1\"" : "\"1.0\""));
+        } else if (f == 1) {
+            o += "\"host\":"; sp();
+            if (bad_kind == 4) o += "42";
+            else { o.push_back('"'); rand_chars(r, o, r.range(8, 24), kHostChars, 38); o.push_back('"'); }
+        } else if (f == 2) {
+            o += "\"short_message\":"; sp();
+            if (bad_kind == 5) o += "null";
+            else { o.push_back('"'); json_text(r, o, r.range(40, 120), true); o.push_back('"'); }
+        } else if (f == 3) {
+            o += "\"full_message\":"; sp();
+            if (bad_kind == 6) o += "[\"nested\",{\"a\":1}]";
+            else {
+                o.push_back('"');
+                json_text(r, o, r.range(150, 300), true);
+                if (bad_kind == 7) o.push_back('\n');       // raw LF inside a string: newline retry path
+                if (bad_kind == 8) o.push_back('\t');       // raw TAB inside a string: error
+                o.push_back('"');
+            }
+        } else if (f == 4) {
+            o += "\"timestamp\":"; sp();
+            if (bad_kind == 9) o += "\"yesterday\"";
+            else {
+                snprintf(buf, sizeof buf, "%u", (unsigned)r.range(1420070400, 2051222400));
+                o += buf;
+                const int fd = r.range(0, 6);
+                if (fd) { o.push_back('.'); for (int i = 0; i < fd; ++i) o.push_back((char)('0' + r.below(10))); }
+            }
+        } else if (f == 5) {
+            o += "\"level\":"; sp();
+            if (bad_kind == 10) o += "8";
+            else if (bad_kind == 11) o += "-1";
+            else o.push_back((char)('0' + r.below(8)));
+        } else {
+            o += "\"_";
+            rand_chars(r, o, r.range(3, 12), kAlnum, 52);
+            o += "\":"; sp();
+            const double u = r.uniform();
+            if (bad_kind == 12 && f == 6) o += "{\"nested\":{\"deep\":[1,2,3]}}";
+            else if (u < 0.60) { o.push_back('"'); json_text(r, o, r.range(2, 14), r.chance(0.2)); o.push_back('"'); }
+            else if (u < 0.85) { snprintf(buf, sizeof buf, "%lld", (long long)(r.next() >> (4 + r.below(56))) * (r.chance(0.2) ? -1 : 1)); o += buf; }
+            else if (u < 0.95) {
+                const int form = (int)r.below(3);
+                if (form == 0) snprintf(buf, sizeof buf, "%.*f", r.range(1, 6), r.uniform() * 10000.0);
+                else if (form == 1) snprintf(buf, sizeof buf, "%.15g", (r.uniform() - 0.5) * std::pow(10.0, r.range(-20, 20)));
+                else snprintf(buf, sizeof buf, "%ue%d", (unsigned)r.below(100000), r.range(-22, 22));
+                std::string t = buf;
+                if (t.find_first_of(".e") == std::string::npos) t += ".0";
+                if (t.find("inf") != std::string::npos || t.find("nan") != std::string::npos) t = "1.5";
+                o += t;
+            } else { o += r.chance(0.4) ? "true" : (r.chance(0.5) ? "false" : "null"); }
+        }
+        sp();
+    }
+    if (bad_kind == 13) o += ",";          // trailing comma
+    o.push_back('}');
+    if (bad_kind == 14) o += " x";         // trailing characters
+    if (bad_kind == 15) { o.resize(line_start); o += "[1,2,3]"; }  // not an object
+}
+
 }  // namespace
 
 extern "C" {
@@ -305,6 +413,7 @@ int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, doubl
             for (int64_t i = lo; i < hi; ++i) {
                 const size_t before = o.size();
                 switch (kind) {
+                    case 2: gen_gelf(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     case 1: gen_ltsv(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     default: gen_rfc5424(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                 }
