@@ -27,7 +27,7 @@ sys.path.insert(0, str(REPO))
 FORMATS = {"rfc5424": 0, "ltsv": 1, "gelf": 2}
 SEEDS = {"rfc5424": 5424, "ltsv": 1757, "gelf": 0x6E1F}
 # generator parameter that lands the ACTUAL mean line length on the BASELINE.json shape
-GEN_MEAN = {"rfc5424": 169.2, "ltsv": 420.0, "gelf": 512.0}
+GEN_MEAN = {"rfc5424": 169.2, "ltsv": 420.0, "gelf": 466.0}
 TARGET_MEAN = {"rfc5424": 180, "ltsv": 420, "gelf": 512}
 DEFAULT_LINES = {"rfc5424": 10_000_000, "ltsv": 4_000_000, "gelf": 3_500_000}  # int32 offsets cap a batch at 2 GiB
 
@@ -102,7 +102,13 @@ def make_batch(fb, fmt_name: str, lines: int, rank: int):
     return data, offs
 
 
-def ltsv_kwargs(fmt_name: str) -> dict:
+LTSV_SCHEMA = {"counter": "u64", "score": "i64", "mean": "f64", "done": "bool"}
+LTSV_SUFFIXES = {"u64": "_u64", "i64": "_i64", "f64": "_f64", "bool": "_bool"}
+
+
+def ltsv_kwargs(fmt_name: str, typed: bool = False) -> dict:
+    if fmt_name == "ltsv" and typed:
+        return {"ltsv_schema": LTSV_SCHEMA, "ltsv_suffixes": LTSV_SUFFIXES}
     return {}
 
 
@@ -120,11 +126,12 @@ def run_reference(args) -> None:
     sample = min(args.lines, 2_000_000)
     data, offs = make_batch(fb, fmt_name, sample, 0)
     nbytes = int(offs[-1])
+    ocfg = pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES) if (fmt_name == "ltsv" and args.ltsv_typed) else None
     for _ in range(max(args.warmup, 1)):
-        pyoracle.decode_bench(fmt, data, offs, None, nthreads=cores)
+        pyoracle.decode_bench(fmt, data, offs, ocfg, nthreads=cores)
     t = 0.0
     for _ in range(args.steps):
-        s, _ok = pyoracle.decode_bench(fmt, data, offs, None, nthreads=cores)
+        s, _ok = pyoracle.decode_bench(fmt, data, offs, ocfg, nthreads=cores)
         t += s
     ms = 1e3 * t / args.steps
     value = sample / (t / args.steps)
@@ -144,6 +151,9 @@ def run_reference(args) -> None:
 
 
 def workload_name(fmt_name: str, lines: int) -> str:
+    if fmt_name != "rfc5424":
+        return (f"{fmt_name.upper()} batch: {lines}-line int32-offset sub-batch per GPU of the 10 M-line workload, mean "
+                f"{TARGET_MEAN[fmt_name]} B (BASELINE.json configs[{ {'gelf': 2, 'ltsv': 3}[fmt_name] }])")
     return f"{fmt_name.upper()} batch: {lines} synthetic lines per GPU, mean {TARGET_MEAN[fmt_name]} B (BASELINE.json configs[{ {'rfc5424': 1, 'gelf': 2, 'ltsv': 3}[fmt_name] }])"
 
 
@@ -157,6 +167,7 @@ def main() -> None:
     ap.add_argument("--lines", type=int, default=0, help="lines per GPU (default: the BASELINE.json config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ltsv-typed", action="store_true", help="LTSV with the 4-entry typed schema + suffixes (C4, second run)")
     args = ap.parse_args()
     if args.lines <= 0:
         args.lines = DEFAULT_LINES[args.format]
@@ -207,7 +218,7 @@ def main() -> None:
     b_read = nbytes + 4 * (n + 1)  # algorithmic bytes per launch: every input byte + offset read once
 
     dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nbytes + (1 << 20), max_batch_lines=n,
-                          chunk_lines=1 << 18, **ltsv_kwargs(fmt_name))
+                          chunk_lines=1 << 18, **ltsv_kwargs(fmt_name, args.ltsv_typed))
     # pinned host arenas, as a batching splitter would fill them
     h_bytes = dec.host_alloc(nbytes)
     h_offs = dec.host_alloc(offs.nbytes, dtype=np.int32)
@@ -267,9 +278,10 @@ def main() -> None:
         sample = min(n, 2_000_000)
         so = np.ascontiguousarray(h_offs[: sample + 1])
         sb = h_bytes[: int(so[-1])]
-        pyoracle.decode_bench(fmt, sb, so, None, nthreads=cores)
-        s_all, _ = pyoracle.decode_bench(fmt, sb, so, None, nthreads=cores)
-        s_one, _ = pyoracle.decode_bench(fmt, sb[: int(so[sample // 8])], np.ascontiguousarray(so[: sample // 8 + 1]), None, nthreads=1)
+        ocfg = pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES) if (fmt_name == "ltsv" and args.ltsv_typed) else None
+        pyoracle.decode_bench(fmt, sb, so, ocfg, nthreads=cores)
+        s_all, _ = pyoracle.decode_bench(fmt, sb, so, ocfg, nthreads=cores)
+        s_one, _ = pyoracle.decode_bench(fmt, sb[: int(so[sample // 8])], np.ascontiguousarray(so[: sample // 8 + 1]), ocfg, nthreads=1)
         cpu = {"value": sample / s_all, "unit": "lines/s", "cores": cores, "kind": "port",
                "single_thread_lines_per_s": (sample // 8) / s_one,
                "sample": f"first {sample} lines of the GPU batch, {cores} host threads over contiguous line shards "

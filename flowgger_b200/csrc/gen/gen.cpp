@@ -308,8 +308,9 @@ void json_text(Rng& r, std::string& o, int target, bool rich) {
 // C3: GELF objects — version, host, short_message (40-120 B), full_message (150-300 B, escape rich), timestamp,
 // level, 3-8 `_extra` members (strings 60 %, ints 25 %, floats <= 15 significant digits 10 %, bool/null 5 %),
 // member order shuffled, random inter-token spaces; 0.5 % malformed.
-void gen_gelf(uint64_t seed, uint64_t idx, double /*mean_len*/, double bad_frac, std::string& o) {
+void gen_gelf(uint64_t seed, uint64_t idx, double mean_len, double bad_frac, std::string& o) {
     Rng r(seed, idx);
+    const double k = mean_len > 0 ? mean_len / 577.0 : 1.0;  // scales the message lengths (577 B = unscaled mean)
     const size_t line_start = o.size();
     const bool bad = r.chance(bad_frac);
     const int bad_kind = bad ? (int)r.below(16) : -1;
@@ -339,13 +340,13 @@ void gen_gelf(uint64_t seed, uint64_t idx, double /*mean_len*/, double bad_frac,
         } else if (f == 2) {
             o += "\"short_message\":"; sp();
             if (bad_kind == 5) o += "null";
-            else { o.push_back('"'); json_text(r, o, r.range(40, 120), true); o.push_back('"'); }
+            else { o.push_back('"'); json_text(r, o, (int)(k * r.range(40, 120)), true); o.push_back('"'); }
         } else if (f == 3) {
             o += "\"full_message\":"; sp();
             if (bad_kind == 6) o += "[\"nested\",{\"a\":1}]";
             else {
                 o.push_back('"');
-                json_text(r, o, r.range(150, 300), true);
+                json_text(r, o, (int)(k * r.range(150, 300)), true);
                 if (bad_kind == 7) o.push_back('\n');       // raw LF inside a string: newline retry path
                 if (bad_kind == 8) o.push_back('\t');       // raw TAB inside a string: error
                 o.push_back('"');
