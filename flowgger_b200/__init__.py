@@ -19,6 +19,9 @@ from .native import (  # noqa: F401
     load_cuda,
     load_gen,
     load_host,
+    multi_gpu_decode_dump,
+    shard_by_bytes,
+    splitter_run,
 )
 
 __all__ = [

@@ -338,6 +338,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     c->max_bytes = cfg->max_batch_bytes > 0 ? (size_t)cfg->max_batch_bytes : ((size_t)256 << 20);
     if (c->max_bytes > 0x7FFFFFC0ull) c->max_bytes = 0x7FFFFFC0ull;  // int32 offsets
     c->max_lines = cfg->max_batch_lines > 0 ? cfg->max_batch_lines : (2 << 20);
+    c->max_lines = (c->max_lines + 63) & ~63;  // keeps every row column 256-byte aligned
     c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (256 << 10);
     c->chunk_lines = (c->chunk_lines + fg::kLinesPerCta - 1) / fg::kLinesPerCta * fg::kLinesPerCta;
 #define FG_CREATE_CUDA(call)                                  \

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <istream>
 #include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <thread>
 
@@ -355,15 +356,21 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
     std::shared_ptr<CudaBatchDecoder> gpu = decoder.batch();
     std::vector<uint8_t> arena;
     std::vector<int32_t> offsets{0};
+    std::vector<int32_t> invalid_before{0};  // "Invalid UTF-8 input" events, kept in stream order relative to the lines
     arena.reserve((size_t)lim_.max_bytes);
     auto flush = [&]() {
         const int32_t n = (int32_t)offsets.size() - 1;
-        if (n == 0) return;
+        if (n == 0) {
+            for (int32_t k = 0; k < invalid_before[0]; ++k) err_out << "Invalid UTF-8 input\n";
+            invalid_before.assign(1, 0);
+            return;
+        }
         fg_batch_out out;
         const uint8_t dummy = 0;
         const uint8_t* bytes = arena.empty() ? &dummy : arena.data();
         gpu->decode_batch(bytes, offsets.data(), n, &out);
         for (int32_t i = 0; i < n; ++i) {
+            for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
             std::vector<std::string> fx;
             DecodeResult r = gpu->materialize(out, bytes, offsets.data(), i, &fx);
             for (const auto& s : fx) std_out << s << "\n";
@@ -383,23 +390,97 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
             std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
             err_out << e << ": [" << rust_trim(line) << "]\n";  // line_splitter.rs:37-39
         }
+        for (int32_t k = 0; k < invalid_before[(size_t)n]; ++k) err_out << "Invalid UTF-8 input\n";
         arena.clear();
         offsets.assign(1, 0);
+        invalid_before.assign(1, 0);
     };
     std::string line;
     while (std::getline(in, line)) {
         // BufRead::lines: the '\n' is gone; a '\r' is stripped only when it preceded a '\n'
         if (!in.eof() && !line.empty() && line.back() == '\r') line.pop_back();
         if (!is_valid_utf8((const uint8_t*)line.data(), line.size())) {
-            err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
+            ++invalid_before.back();  // printed in stream order when the batch is flushed
             continue;
         }
         if ((int64_t)(arena.size() + line.size()) > lim_.max_bytes || (int32_t)offsets.size() - 1 >= lim_.max_lines)
             flush();
         arena.insert(arena.end(), line.begin(), line.end());
         offsets.push_back((int32_t)arena.size());
+        invalid_before.push_back(0);
     }
     flush();
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU sharding: host-side split / gather only
+// ---------------------------------------------------------------------------
+void shard_by_bytes(const int32_t* offsets, int32_t n, int G, int32_t* bounds) {
+    if (G < 1) G = 1;
+    bounds[0] = 0;
+    const int64_t b0 = n > 0 ? offsets[0] : 0, total = n > 0 ? (int64_t)offsets[n] - b0 : 0;
+    for (int g = 1; g < G; ++g) {
+        const int64_t target = b0 + total * g / G;
+        // first line whose start offset is >= target
+        const int32_t* it = std::lower_bound(offsets, offsets + n, (int32_t)target);
+        int32_t k = (int32_t)(it - offsets);
+        if (k < bounds[g - 1]) k = bounds[g - 1];
+        if (k > n) k = n;
+        bounds[g] = k;
+    }
+    bounds[G] = n;
+}
+
+MultiGpuBatchDecoder::MultiGpuBatchDecoder(fg_format fmt, const std::vector<int>& devices, const LtsvConfig& ltsv,
+                                           const DeviceOptions& per_device) {
+    for (int d : devices) {
+        DeviceOptions o = per_device;
+        o.device = d;
+        dec_.emplace_back(new CudaBatchDecoder(fmt, ltsv, o));
+    }
+    shards_.resize(dec_.size());
+}
+
+const std::vector<MultiGpuBatchDecoder::Shard>& MultiGpuBatchDecoder::decode_batch(const uint8_t* bytes,
+                                                                                  const int32_t* offsets, int32_t n) {
+    const int G = (int)dec_.size();
+    std::vector<int32_t> bounds((size_t)G + 1);
+    shard_by_bytes(offsets, n, G, bounds.data());
+    std::vector<std::thread> th;
+    std::vector<std::string> errs((size_t)G);
+    for (int g = 0; g < G; ++g) {
+        Shard& s = shards_[(size_t)g];
+        s.line0 = bounds[(size_t)g];
+        s.n = bounds[(size_t)g + 1] - s.line0;
+        s.byte_base = s.n > 0 ? offsets[s.line0] : 0;
+        s.offsets.resize((size_t)s.n + 1);
+        for (int32_t k = 0; k <= s.n; ++k) s.offsets[(size_t)k] = (int32_t)(offsets[s.line0 + k] - s.byte_base);
+        if (s.n == 0) s.offsets[0] = 0;
+        th.emplace_back([&, g] {
+            Shard& sh = shards_[(size_t)g];
+            try {
+                const uint8_t dummy = 0;
+                dec_[(size_t)g]->decode_batch(sh.n ? bytes + sh.byte_base : &dummy, sh.offsets.data(), sh.n, &sh.out);
+            } catch (const std::exception& e) {
+                errs[(size_t)g] = e.what();
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (const auto& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    return shards_;
+}
+
+DecodeResult MultiGpuBatchDecoder::materialize(int32_t line, const uint8_t* bytes, std::vector<std::string>* fx) const {
+    for (size_t g = 0; g < shards_.size(); ++g) {
+        const Shard& s = shards_[g];
+        if (line >= s.line0 && line < s.line0 + s.n)
+            return dec_[g]->materialize(s.out, bytes + s.byte_base, s.offsets.data(), line - s.line0, fx);
+    }
+    DecodeResult r;
+    r.err = "line out of range";
+    return r;
 }
 
 // ---------------------------------------------------------------------------
@@ -574,5 +655,85 @@ double fgh_materialize_bench(void* d, const fg_batch_out* out, const uint8_t* by
 }
 
 int fgh_is_valid_utf8(const uint8_t* p, int64_t n) { return is_valid_utf8(p, (size_t)n) ? 1 : 0; }
+
+void fgh_shard_by_bytes(const int32_t* offsets, int32_t n, int G, int32_t* bounds) { shard_by_bytes(offsets, n, G, bounds); }
+
+// multi-GPU fan-out: decode on `ndev` devices and return the canonical dumps in batch order
+int fgh_multi_decode_dump(int fmt, const int* devices, int ndev, int64_t max_bytes, int32_t max_lines,
+                          const uint8_t* bytes, const int32_t* offsets, int32_t n, uint8_t** out_buf,
+                          int64_t** out_offsets, char* errbuf, int errlen) {
+    try {
+        DeviceOptions opt;
+        opt.max_batch_bytes = max_bytes;
+        opt.max_batch_lines = max_lines;
+        MultiGpuBatchDecoder dec((fg_format)fmt, std::vector<int>(devices, devices + ndev), {}, opt);
+        dec.decode_batch(bytes, offsets, n);
+        std::string all;
+        int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
+        offs[0] = 0;
+        std::vector<std::string> fx;
+        for (int32_t i = 0; i < n; ++i) {
+            fx.clear();
+            DecodeResult r = dec.materialize(i, bytes, &fx);
+            dump_result(r, false, fx, all);
+            offs[i + 1] = (int64_t)all.size();
+        }
+        uint8_t* buf = (uint8_t*)malloc(all.size() ? all.size() : 1);
+        memcpy(buf, all.data(), all.size());
+        *out_buf = buf;
+        *out_offsets = offs;
+        return 0;
+    } catch (const std::exception& e) {
+        if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());
+        return -1;
+    }
+}
+
+// BatchingLineSplitter twin of LineSplitter::run for tests: text in, one canonical dump line per record out
+// (encoder = the parity dump), stderr/stdout text of the reference captured.
+int fgh_splitter_run(void* d, const uint8_t* text, int64_t len, int32_t max_lines, int64_t max_bytes, uint8_t** out_records,
+                     int64_t* out_records_len, uint8_t** out_stderr, int64_t* out_stderr_len, uint8_t** out_stdout,
+                     int64_t* out_stdout_len) {
+    struct DumpEncoder : Encoder {
+        bool encode(Record&& rec, std::vector<uint8_t>& out, const char**) const override {
+            DecodeResult r;
+            r.record = std::move(rec);
+            std::string s;
+            dump_result(r, false, {}, s);
+            out.assign(s.begin(), s.end());
+            return true;
+        }
+    };
+    struct Shared : Decoder {
+        std::shared_ptr<CudaBatchDecoder> b;
+        DecodeResult decode(std::string_view) const override { return {}; }
+        std::unique_ptr<Decoder> clone_boxed() const override { return nullptr; }
+        std::shared_ptr<CudaBatchDecoder> batch() const override { return b; }
+    } dec;
+    dec.b = std::shared_ptr<CudaBatchDecoder>((CudaBatchDecoder*)d, [](CudaBatchDecoder*) {});
+    BatchingLineSplitter::Limits lim;
+    lim.max_lines = max_lines;
+    lim.max_bytes = max_bytes;
+    BatchingLineSplitter sp(lim);
+    std::string in((const char*)text, (size_t)len);
+    std::istringstream is(in);
+    std::ostringstream es, os;
+    std::string records;
+    DumpEncoder enc;
+    try {
+        sp.run(is, [&](std::vector<uint8_t>&& v) { records.append(v.begin(), v.end()); records.push_back('\n'); }, dec, enc, es, os);
+    } catch (const std::exception&) {
+        return -1;
+    }
+    auto give = [](const std::string& s, uint8_t** p, int64_t* n) {
+        *p = (uint8_t*)malloc(s.size() ? s.size() : 1);
+        memcpy(*p, s.data(), s.size());
+        *n = (int64_t)s.size();
+    };
+    give(records, out_records, out_records_len);
+    give(es.str(), out_stderr, out_stderr_len);
+    give(os.str(), out_stdout, out_stdout_len);
+    return 0;
+}
 
 }  // extern "C"

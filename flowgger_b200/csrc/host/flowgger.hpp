@@ -163,6 +163,33 @@ class BatchingLineSplitter {
     Limits lim_;
 };
 
+// §8(e): lines are independent, so a batch shards across GPUs by contiguous line ranges balanced by BYTES
+// (binary search on the offsets prefix); no collective, results concatenate in shard order.
+// bounds has G+1 entries: shard g covers lines [bounds[g], bounds[g+1]).
+void shard_by_bytes(const int32_t* offsets, int32_t n, int G, int32_t* bounds);
+
+// One CudaBatchDecoder per device + one host thread per device.
+class MultiGpuBatchDecoder {
+   public:
+    MultiGpuBatchDecoder(fg_format fmt, const std::vector<int>& devices, const LtsvConfig& ltsv = {},
+                         const DeviceOptions& per_device = {});
+    int shards() const { return (int)dec_.size(); }
+    struct Shard {
+        int32_t line0 = 0, n = 0;     // lines [line0, line0+n) of the batch
+        int64_t byte_base = 0;        // spans of this shard are relative to bytes + byte_base
+        fg_batch_out out{};
+        std::vector<int32_t> offsets; // rebased offsets handed to the device
+    };
+    // decodes the batch on all devices concurrently; shard g's result stays valid until the next call
+    const std::vector<Shard>& decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n);
+    DecodeResult materialize(int32_t line, const uint8_t* bytes, std::vector<std::string>* side_effects = nullptr) const;
+    CudaBatchDecoder& device(int g) { return *dec_[(size_t)g]; }
+
+   private:
+    std::vector<std::unique_ptr<CudaBatchDecoder>> dec_;
+    std::vector<Shard> shards_;
+};
+
 // helpers shared with tests
 bool is_valid_utf8(const uint8_t* p, size_t n);
 std::string_view rust_trim(std::string_view s);

@@ -91,6 +91,10 @@ def load_host() -> C.CDLL:
         L.fgh_materialize_bench.restype = C.c_double
         L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
         L.fgh_is_valid_utf8.argtypes = [C.c_void_p, C.c_int64]
+        L.fgh_shard_by_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
+        L.fgh_multi_decode_dump.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.fgh_splitter_run.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 3
         _host = L
     return _host
 
@@ -273,3 +277,49 @@ class BatchDecoder:
 
     def materialize_seconds(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 1) -> float:
         return float(self.H.fgh_materialize_bench(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads))
+
+
+def shard_by_bytes(offsets: np.ndarray, G: int) -> np.ndarray:
+    """contiguous line ranges balanced by bytes; returns bounds int32[G+1]."""
+    assert offsets.dtype == np.int32
+    bounds = np.zeros(G + 1, dtype=np.int32)
+    load_host().fgh_shard_by_bytes(_ptr(offsets), len(offsets) - 1, G, _ptr(bounds))
+    return bounds
+
+
+def multi_gpu_decode_dump(fmt: int, devices: list[int], data: np.ndarray, offsets: np.ndarray) -> tuple[bytes, np.ndarray]:
+    """Decode one batch on several GPUs (one host thread + context per device) and return the canonical dumps."""
+    H = load_host()
+    dev = np.asarray(devices, dtype=np.int32)
+    pb, po = C.c_void_p(), C.c_void_p()
+    err = C.create_string_buffer(512)
+    n = len(offsets) - 1
+    rc = H.fgh_multi_decode_dump(fmt, _ptr(dev), len(devices), int(offsets[-1]) + (1 << 20), n + 1024, _ptr(data), _ptr(offsets), n,
+                                 C.byref(pb), C.byref(po), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    try:
+        offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+        buf = C.string_at(pb, int(offs[-1]))
+    finally:
+        H.fgh_free(pb)
+        H.fgh_free(po)
+    return buf, offs
+
+
+def splitter_run(dec: "BatchDecoder", text: bytes, max_lines: int = 1 << 16, max_bytes: int = 16 << 20) -> tuple[bytes, bytes, bytes]:
+    """BatchingLineSplitter over `text` (the stdin of config #1): returns (records, stderr, stdout)."""
+    H = load_host()
+    ps = [C.c_void_p() for _ in range(3)]
+    ns = [C.c_int64() for _ in range(3)]
+    args = []
+    for p, n in zip(ps, ns):
+        args += [C.byref(p), C.byref(n)]
+    rc = H.fgh_splitter_run(dec._h, text, len(text), max_lines, max_bytes, *args)
+    if rc != 0:
+        raise RuntimeError("splitter failed")
+    out = []
+    for p, n in zip(ps, ns):
+        out.append(C.string_at(p, n.value))
+        H.fgh_free(p)
+    return tuple(out)

@@ -1,0 +1,100 @@
+"""Config #1 plumbing (stdin + line framing + RFC5424) through the batching splitter, and the
+multi-context fan-out. GPU only."""
+import numpy as np
+import pytest
+
+import vectors as V
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_stdin_10k_lines(native, oracle):
+    """10 000-line RFC5424 'file': BatchingLineSplitter (GPU decode) must emit exactly what LineSplitter +
+    the reference decoder would: same records in order, same stderr text for bad lines (line_splitter.rs:37-39)."""
+    data, offs = native.generate(native.FMT_RFC5424, 1, 10_000, bad_frac=0.01)
+    lines = [bytes(data[offs[i]:offs[i + 1]]) for i in range(10_000)]
+    lines[17] = lines[17] + b"\r"            # CRLF line: BufRead::lines strips the '\r'
+    lines[4000] = b"<13>1 \xff\xfe broken utf8"  # InvalidData -> "Invalid UTF-8 input", skipped
+    lines[5000] = b""                         # empty line -> "Unsupported BOM: []"
+    text = b"\n".join(lines) + b"\n"
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=64 << 20, max_batch_lines=1 << 16)
+    try:
+        records, err, out = native.splitter_run(dec, text, max_lines=3000, max_bytes=1 << 20)
+    finally:
+        dec.close()
+    # expected, from the oracle applied line by line to what LineSplitter would hand to decode()
+    fed = [l[:-1] if (i == 17) else l for i, l in enumerate(lines) if i != 4000]
+    d, o = oracle.pack(fed)
+    buf, bo = oracle.decode_dump(0, d, o)
+    exp_records, exp_err = [], []
+    k = 0
+    for i, l in enumerate(lines):
+        if i == 4000:
+            exp_err.append(b"Invalid UTF-8 input")
+            continue
+        dump = buf[bo[k]:bo[k + 1]]
+        line = fed[k]
+        k += 1
+        if dump.startswith(b"E:"):
+            msg = dump[2:dump.index(b";out=")]
+            exp_err.append(msg + b": [" + line.decode().strip().encode() + b"]")
+        else:
+            exp_records.append(dump[:dump.rindex(b";out=")] + b";out=0")
+    assert records.split(b"\n")[:-1] == exp_records
+    assert err.split(b"\n")[:-1] == exp_err
+    assert out == b""
+
+
+def test_single_line_decoder_trait(native, oracle):
+    """Decoder::decode(line) drop-in: a batch of one through the same kernels."""
+    dec = native.BatchDecoder(native.FMT_RFC5424)
+    try:
+        for line in (V.G1_LINE, V.G2_LINE, "abc", ""):
+            data, offs = oracle.pack([line.encode()])
+            res = dec.decode(data, offs)
+            g, _ = dec.dump(res, data, offs, nthreads=1)
+            r, _ = oracle.decode_dump(0, data, offs, nthreads=1)
+            assert g == r
+    finally:
+        dec.close()
+
+
+def test_multi_context_fanout(native, oracle):
+    """MultiGpuBatchDecoder: byte-balanced shards, one context + host thread per device, gathered in order.
+    Uses every visible GPU (falls back to two contexts on GPU 0 when only one is visible)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0]
+    data, offs = native.generate(native.FMT_RFC5424, 77, 400_000)
+    gbuf, goffs = native.multi_gpu_decode_dump(native.FMT_RFC5424, devices, data, offs)
+    obuf, ooffs = oracle.decode_dump(0, data, offs)
+    assert gbuf == obuf and np.array_equal(goffs, ooffs)
+    # fewer lines than shards
+    d2, o2 = oracle.pack([V.G1_LINE.encode()])
+    gbuf, _ = native.multi_gpu_decode_dump(native.FMT_RFC5424, devices + devices, d2, o2)
+    obuf, _ = oracle.decode_dump(0, d2, o2)
+    assert gbuf == obuf
+
+
+def test_capacity_and_argument_errors(native, oracle):
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=8 << 20, max_batch_lines=1000)
+    try:
+        data, offs = native.generate(native.FMT_RFC5424, 3, 5000)
+        with pytest.raises(RuntimeError, match="max_batch_lines|more lines"):
+            dec.decode(data, offs)
+        bad = offs[:10].copy()
+        bad[5] = bad[9] + 5
+        # non-monotone offsets inside the batch are the caller's contract; first/last are checked
+        bad2 = np.array([10, 5], dtype=np.int32)
+        with pytest.raises(RuntimeError, match="monotone"):
+            dec.decode(data, bad2)
+        # structured-data table overflow triggers a regrow, not a failure
+        lines = [(V.H + "".join('[i k="v"]' for _ in range(400)) + " m").encode()] * 900
+        d2, o2 = oracle.pack(lines)
+        res = dec.decode(d2, o2)
+        assert res.n_entries == 900 * 800
+        g, _ = dec.dump(res, d2, o2)
+        r, _ = oracle.decode_dump(0, d2, o2)
+        assert g == r
+    finally:
+        dec.close()
