@@ -1,0 +1,326 @@
+//! cuda_decoder — `flowgger::decoder::Decoder` implementations backed by the B200 batched parser.
+//!
+//! Mirrors flowgger_b200/csrc/host/flowgger.{hpp,cpp} (the C++ twin that the test-suite drives, because the
+//! build environment has no Rust toolchain).  Reference interfaces implemented here:
+//!   * `Decoder::decode(&self, line: &str) -> Result<Record, &'static str>`  (src/flowgger/decoder/mod.rs:44-46)
+//!   * `CloneBoxedDecoder` via `#[derive(Clone)]`                            (decoder/mod.rs:23-42)
+//!   * `Splitter<T>::run`                                                    (src/flowgger/splitter/mod.rs:18-26)
+//! All parsing happens on the GPU; this crate packs lines, calls `fg_decode_batch` and materialises Records.
+#![allow(non_camel_case_types, non_upper_case_globals, dead_code)]
+
+use flowgger::flowgger::config::Config;
+use flowgger::flowgger::decoder::Decoder;
+use flowgger::flowgger::encoder::Encoder;
+use flowgger::flowgger::record::{Record, SDValue, StructuredData};
+use flowgger::flowgger::splitter::Splitter;
+use std::ffi::{CStr, CString};
+use std::io::{stderr, BufRead, BufReader, ErrorKind, Read, Write};
+use std::os::raw::c_char;
+use std::ptr;
+use std::sync::mpsc::SyncSender;
+use std::sync::{Arc, Mutex};
+
+mod ffi {
+    include!(concat!(env!("OUT_DIR"), "/ffi.rs"));
+}
+use ffi::*;
+
+/// One GPU context of a fixed format (`fg_ctx`); shared by the clones handed to input threads.
+struct Ctx {
+    raw: *mut fg_ctx,
+    fmt: fg_format,
+    suffix: [Option<String>; 5],
+}
+unsafe impl Send for Ctx {}
+impl Drop for Ctx {
+    fn drop(&mut self) {
+        unsafe { fg_destroy(self.raw) }
+    }
+}
+
+#[derive(Clone)]
+pub struct CudaDecoder {
+    ctx: Arc<Mutex<Ctx>>,
+}
+
+fn ltsv_type(t: &str) -> Option<i32> {
+    match t.to_lowercase().as_ref() {
+        "string" => Some(0),
+        "bool" => Some(1),
+        "f64" => Some(2),
+        "i64" => Some(3),
+        "u64" => Some(4),
+        _ => None,
+    }
+}
+
+impl CudaDecoder {
+    /// `RFC5424Decoder::new(&Config)` / `LTSVDecoder::new` / `GelfDecoder::new` replacement, selected in
+    /// `flowgger::start` (src/flowgger/mod.rs:413-422) by `input.format`.
+    pub fn new(config: &Config, fmt: fg_format) -> CudaDecoder {
+        let mut names: Vec<CString> = Vec::new();
+        let mut types: Vec<i32> = Vec::new();
+        let mut suffix: [Option<String>; 5] = Default::default();
+        let has_schema = config.lookup("input.ltsv_schema").is_some();
+        if let Some(pairs) = config.lookup("input.ltsv_schema") {
+            // same panics as ltsv_decoder.rs:31-44
+            for (name, sdtype) in pairs.as_table().expect("input.ltsv_schema must be a list of key/type pairs") {
+                let t = sdtype.as_str().expect("input.ltsv_schema types must be strings");
+                let t = ltsv_type(t).unwrap_or_else(|| panic!("Unsupported type in input.ltsv_schema for name [{}]", name));
+                names.push(CString::new(name.as_str()).unwrap());
+                types.push(t);
+            }
+        }
+        if let Some(pairs) = config.lookup("input.ltsv_suffixes") {
+            for (sdtype, sfx) in pairs.as_table().expect("input.ltsv_suffixes must be a list of type/suffixes pairs") {
+                let sfx = sfx.as_str().expect("input.ltsv_suffixes suffixes must be strings").to_owned();
+                match ltsv_type(sdtype) {
+                    Some(0) => panic!("Strings cannot be suffixed"),
+                    Some(t) => suffix[t as usize] = Some(sfx),
+                    None => panic!("Unsupported type in input.ltsv_suffixes for type [{}]", sdtype),
+                }
+            }
+        }
+        let name_ptrs: Vec<*const c_char> = names.iter().map(|s| s.as_ptr()).collect();
+        let sfx_c: Vec<Option<CString>> = suffix.iter().map(|s| s.as_ref().map(|x| CString::new(x.as_str()).unwrap())).collect();
+        let mut cfg: fg_config = unsafe { std::mem::zeroed() };
+        cfg.device = config.lookup("input.cuda_device").and_then(|v| v.as_integer()).unwrap_or(0) as i32;
+        cfg.max_batch_bytes = config.lookup("input.cuda_max_batch_bytes").and_then(|v| v.as_integer()).unwrap_or(0);
+        cfg.max_batch_lines = config.lookup("input.cuda_max_batch_lines").and_then(|v| v.as_integer()).unwrap_or(0) as i32;
+        cfg.ltsv_has_schema = has_schema as i32;
+        cfg.ltsv_schema_len = names.len() as i32;
+        cfg.ltsv_schema_names = name_ptrs.as_ptr();
+        cfg.ltsv_schema_types = types.as_ptr();
+        for t in 1..5 {
+            cfg.ltsv_suffix[t] = sfx_c[t].as_ref().map_or(ptr::null(), |s| s.as_ptr());
+        }
+        let mut raw: *mut fg_ctx = ptr::null_mut();
+        let rc = unsafe { fg_create(&cfg, &mut raw) };
+        if rc != 0 {
+            // There is no CPU fallback: without the library + a GPU the decoder cannot exist.
+            panic!("flowgger_cuda: fg_create failed ({})", rc);
+        }
+        CudaDecoder { ctx: Arc::new(Mutex::new(Ctx { raw, fmt, suffix })) }
+    }
+
+    /// Decode `n` lines packed as bytes + offsets; calls `f(i, result)` in input order.
+    pub fn decode_batch<F: FnMut(usize, Result<Record, &'static str>, &[String])>(&self, bytes: &[u8], offsets: &[i32], mut f: F) {
+        let ctx = self.ctx.lock().unwrap();
+        let n = offsets.len() - 1;
+        let mut out: fg_batch_out = unsafe { std::mem::zeroed() };
+        let rc = unsafe { fg_decode_batch(ctx.raw, ctx.fmt, bytes.as_ptr(), offsets.as_ptr(), n as i32, &mut out) };
+        if rc != 0 {
+            let e = unsafe { CStr::from_ptr(fg_last_error(ctx.raw)) }.to_string_lossy().into_owned();
+            panic!("fg_decode_batch: {}", e);
+        }
+        for i in 0..n {
+            let mut side = Vec::new();
+            let r = materialize(&ctx, &out, bytes, offsets, i, &mut side);
+            f(i, r, &side);
+        }
+    }
+}
+
+fn span<'a>(bytes: &'a [u8], s: fg_span) -> &'a str {
+    // spans delimit whole UTF-8 sequences of a line that was validated before the call
+    unsafe { std::str::from_utf8_unchecked(&bytes[s.off as usize..(s.off + s.len) as usize]) }
+}
+
+/// rfc5424_decoder.rs:105-125, deferred from the kernel (FG_EM_UNESCAPE)
+fn unescape_sd_value(value: &str) -> String {
+    let mut res = String::with_capacity(value.len());
+    let mut esc = false;
+    for c in value.chars() {
+        match (c, esc) {
+            ('\\', false) => esc = true,
+            (_, false) => res.push(c),
+            ('"', true) | ('\\', true) | (']', true) => { res.push(c); esc = false; }
+            (_, true) => { res.push('\\'); res.push(c); esc = false; }
+        }
+    }
+    res
+}
+
+/// JSON string body already validated on the device -> String; `nl_retry` = gelf_decoder.rs:44-46 semantics.
+fn json_unescape(v: &str, nl_retry: bool) -> String {
+    let b = v.as_bytes();
+    let mut out = String::with_capacity(b.len());
+    let hex = |s: &[u8]| s.iter().fold(0u32, |n, &c| n * 16 + (c as char).to_digit(16).unwrap());
+    let mut i = 0;
+    let mut raw_from = 0;
+    while i < b.len() {
+        if b[i] != b'\\' { i += 1; continue; }
+        out.push_str(&v[raw_from..i]);
+        let e = b[i + 1];
+        i += 2;
+        match e {
+            b'"' => out.push('"'), b'\\' => out.push('\\'), b'/' => out.push('/'),
+            b'b' => out.push('\x08'), b'f' => out.push('\x0c'), b'n' => out.push('\n'),
+            b'r' => out.push('\r'), b't' => out.push('\t'),
+            b'u' => {
+                let mut n = hex(&b[i..i + 4]);
+                i += 4;
+                if (0xD800..=0xDBFF).contains(&n) {
+                    let n2 = hex(&b[i + 2..i + 6]);
+                    i += 6;
+                    n = (((n - 0xD800) << 10) | (n2 - 0xDC00)) + 0x1_0000;
+                }
+                out.push(std::char::from_u32(n).unwrap());
+            }
+            b'\n' if nl_retry => out.push_str("\\n"),
+            _ => {}
+        }
+        raw_from = i;
+    }
+    out.push_str(&v[raw_from..]);
+    out
+}
+
+fn materialize(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], offsets: &[i32], i: usize, side: &mut Vec<String>) -> Result<Record, &'static str> {
+    unsafe {
+        let meta = *out.meta.add(i);
+        let status = meta & 0xFF;
+        let flags = (meta >> 24) & 0xFF;
+        if flags & FG_FLAG_MISSING_VALUE != 0 {
+            // println! at ltsv_decoder.rs:99 for every part without ':' that the decode loop reached
+            let (lo, hi) = (offsets[i] as usize, offsets[i + 1] as usize);
+            let stop = if status != 0 { (*out.full_msg.add(i)).off as usize } else { hi + 1 };
+            let mut a = lo;
+            for part in span(bytes, fg_span { off: lo as i32, len: (hi - lo) as i32 }).split('\t') {
+                if a >= stop { break; }
+                if !part.contains(':') { side.push(format!("Missing value for name '{}'", part)); }
+                a += part.len() + 1;
+            }
+        }
+        if status != 0 {
+            let s = CStr::from_ptr(fg_error_string(ctx.fmt, status));
+            return Err(std::str::from_utf8_unchecked(std::slice::from_raw_parts(s.as_ptr() as *const u8, s.to_bytes().len())));
+        }
+        let nl = flags & FG_FLAG_NL_RETRY != 0;
+        let opt = |col: *const fg_span| if col.is_null() || (*col.add(i)).off < 0 { None } else { Some(span(bytes, *col.add(i)).to_owned()) };
+        let esc = |s: Option<String>, bit: u32| s.map(|x| if flags & bit != 0 { json_unescape(&x, nl) } else { x });
+        let fac = (meta >> 8) & 0xFF;
+        let sev = (meta >> 16) & 0xFF;
+        let sd_span = *out.sd.add(i);
+        let mut sd: Vec<StructuredData> = Vec::new();
+        if sd_span.len > 0 {
+            let r5 = ctx.fmt == fg_format_FG_FMT_RFC5424;
+            if !r5 { sd.push(StructuredData::new(None)); }
+            for e in sd_span.off..sd_span.off + sd_span.len {
+                let e = e as usize;
+                let em = *out.entry_meta.add(e) as u32;
+                let tag = em & FG_EM_TAG_MASK;
+                let nm = *out.entry_name.add(e);
+                if tag == fg_tag_FG_TAG_SD_HEADER as u32 {
+                    sd.push(StructuredData::new(if nm.off >= 0 { Some(span(bytes, nm)) } else { None }));
+                    continue;
+                }
+                let mut name = String::new();
+                if em & FG_EM_NO_PREFIX == 0 { name.push('_'); }
+                if em & FG_EM_NAME_ESC != 0 { name.push_str(&json_unescape(span(bytes, nm), nl)); } else { name.push_str(span(bytes, nm)); }
+                if em & FG_EM_SUFFIX != 0 { if let Some(ref s) = ctx.suffix[tag as usize] { name.push_str(s); } }
+                let val = *out.entry_val.add(e);
+                let v = match tag {
+                    0 => {
+                        let raw = span(bytes, fg_span { off: (val & 0xFFFF_FFFF) as i32, len: (val >> 32) as i32 });
+                        SDValue::String(if em & FG_EM_UNESCAPE == 0 { raw.to_owned() } else if r5 { unescape_sd_value(raw) } else { json_unescape(raw, nl) })
+                    }
+                    1 => SDValue::Bool(val != 0),
+                    2 => SDValue::F64(f64::from_bits(val)),
+                    3 => SDValue::I64(val as i64),
+                    4 => SDValue::U64(val),
+                    _ => SDValue::Null,
+                };
+                sd.last_mut().unwrap().pairs.push((name, v));
+            }
+        }
+        let ts = if flags & FG_FLAG_TS_MISSING != 0 {
+            flowgger::flowgger::utils::PreciseTimestamp::now().as_f64() // gelf_decoder.rs:109
+        } else {
+            *out.ts.add(i)
+        };
+        Ok(Record {
+            ts,
+            hostname: esc(opt(out.hostname), FG_FLAG_HOST_ESC).unwrap_or_default(),
+            facility: if fac != 0xFF { Some(fac as u8) } else { None },
+            severity: if sev != 0xFF { Some(sev as u8) } else { None },
+            appname: opt(out.appname),
+            procid: opt(out.procid),
+            msgid: opt(out.msgid),
+            msg: esc(opt(out.msg), FG_FLAG_MSG_ESC),
+            full_msg: esc(opt(out.full_msg), FG_FLAG_FULL_ESC),
+            sd: if sd.is_empty() { None } else { Some(sd) },
+        })
+    }
+}
+
+impl Decoder for CudaDecoder {
+    /// Drop-in single-line form: a batch of one through the same kernels.
+    fn decode(&self, line: &str) -> Result<Record, &'static str> {
+        let offsets = [0i32, line.len() as i32];
+        let mut res = Err("unreachable");
+        self.decode_batch(line.as_bytes(), &offsets, |_, r, side| {
+            for s in side { println!("{}", s); }
+            res = r;
+        });
+        res
+    }
+}
+
+/// Batched twin of `LineSplitter` (src/flowgger/splitter/line_splitter.rs:10-54): inserted between `input` and
+/// `decoder`; same line reading rules, same stderr text, Records sent in the original order.
+pub struct BatchingLineSplitter {
+    pub gpu: CudaDecoder,
+    pub max_lines: usize,
+    pub max_bytes: usize,
+}
+
+impl<T: Read> Splitter<T> for BatchingLineSplitter {
+    fn run(&self, buf_reader: BufReader<T>, tx: SyncSender<Vec<u8>>, _decoder: Box<dyn Decoder>, encoder: Box<dyn Encoder>) {
+        let mut arena: Vec<u8> = Vec::with_capacity(self.max_bytes);
+        let mut offsets: Vec<i32> = vec![0];
+        let mut invalid_before: Vec<u32> = vec![0];
+        let mut flush = |arena: &mut Vec<u8>, offsets: &mut Vec<i32>, invalid_before: &mut Vec<u32>| {
+            if offsets.len() > 1 {
+                let inv = invalid_before.clone();
+                self.gpu.decode_batch(arena, offsets, |i, r, side| {
+                    for _ in 0..inv[i] { let _ = writeln!(stderr(), "Invalid UTF-8 input"); }
+                    for s in side { println!("{}", s); }
+                    let line = unsafe { std::str::from_utf8_unchecked(&arena[offsets[i] as usize..offsets[i + 1] as usize]) };
+                    match r.and_then(|rec| encoder.encode(rec)) {
+                        Ok(bytes) => tx.send(bytes).unwrap(),
+                        Err(e) => { let _ = writeln!(stderr(), "{}: [{}]", e, line.trim()); }
+                    }
+                });
+            }
+            for _ in 0..*invalid_before.last().unwrap() { let _ = writeln!(stderr(), "Invalid UTF-8 input"); }
+            arena.clear();
+            offsets.clear();
+            offsets.push(0);
+            invalid_before.clear();
+            invalid_before.push(0);
+        };
+        for line in buf_reader.lines() {
+            let line = match line {
+                Ok(line) => line,
+                Err(e) => match e.kind() {
+                    ErrorKind::Interrupted => continue,
+                    ErrorKind::InvalidInput | ErrorKind::InvalidData => { *invalid_before.last_mut().unwrap() += 1; continue; }
+                    ErrorKind::WouldBlock => {
+                        flush(&mut arena, &mut offsets, &mut invalid_before);
+                        let _ = writeln!(stderr(), "Client hasn't sent any data for a while - Closing idle connection");
+                        return;
+                    }
+                    _ => { flush(&mut arena, &mut offsets, &mut invalid_before); return; }
+                },
+            };
+            if arena.len() + line.len() > self.max_bytes || offsets.len() > self.max_lines {
+                flush(&mut arena, &mut offsets, &mut invalid_before);
+            }
+            arena.extend_from_slice(line.as_bytes());
+            offsets.push(arena.len() as i32);
+            invalid_before.push(0);
+        }
+        flush(&mut arena, &mut offsets, &mut invalid_before);
+    }
+}
