@@ -164,7 +164,17 @@ __global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_consta
                 // compact this line's staged rows from the scratch table into the side table
                 my_begin = ebase + excl;
                 const uint32_t src = Format<FMT>::scratch_index(o0, lidx);
-                for (uint32_t k = 0; k < my_n; ++k) {
+                uint32_t k = 0;
+                for (; k + 4 <= my_n; k += 4) {  // loads first, then stores: 12 independent L2 round trips in flight
+                    int2 a[4];
+                    unsigned long long b[4];
+                    uint8_t c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a[u] = tmp.name[src + k + u]; b[u] = tmp.val[src + k + u]; c[u] = tmp.meta[src + k + u]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { sink.name[my_begin + k + u] = a[u]; sink.val[my_begin + k + u] = b[u]; sink.meta[my_begin + k + u] = c[u]; }
+                }
+                for (; k < my_n; ++k) {
                     sink.name[my_begin + k] = tmp.name[src + k];
                     sink.val[my_begin + k] = tmp.val[src + k];
                     sink.meta[my_begin + k] = tmp.meta[src + k];

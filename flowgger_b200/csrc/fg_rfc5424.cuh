@@ -226,14 +226,21 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
         // Inner scans are written as `lim`-bounded loops whose only loop-carried value is the cursor:
         // a lane that is not scanning has lim == i and falls through; nothing else is updated inside.
         while (__any_sync(kFullMask, active)) {
-            // (A) sd_id: up to the first ' '
+            // (A) sd_id: up to the first ' ' — 4 bytes per step (aligned word, bytes before the cursor masked off)
             {
                 const bool scan = active && st_id;
                 const int lim = scan ? len : i;
                 for (;;) {
-                    const bool more = (i < lim) && (p[i] != ' ');
+                    bool more = false;
+                    if (i < lim) {
+                        const uint32_t addr = (uint32_t)(size_t)(p + i);
+                        const uint32_t sh = (addr & 3u) * 8u;
+                        const uint32_t x = *(const uint32_t*)(p + i - (addr & 3u)) ^ 0x20202020u;
+                        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu) & (0xFFFFFFFFu << sh);
+                        if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);  // stop on the space (may lie past len: checked below)
+                        else { i += 4 - (int)(addr & 3u); more = true; }
+                    }
                     if (!__any_sync(kFullMask, more)) break;
-                    i += more ? 1 : 0;
                 }
                 if (scan) {
                     if (i >= len) { active = false; status = FG_E5_MISSING_SD; }  // :177
@@ -301,18 +308,30 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables&
                     else { ++i; do_val = true; }
                 }
             }
-            // (D) VAL: up to the first unescaped '"' (:216, :217, :231)
+            // (D) VAL: up to the first unescaped '"' (:216, :217, :231) — 4 bytes per step
             uint32_t has_bs = 0;
             {
                 const int lim = do_val ? len : i;
                 for (;;) {
-                    uint32_t c = '"';
-                    if (i < lim) c = p[i];
-                    const bool more = c != '"';
+                    bool more = false;
+                    if (i < lim) {
+                        const uint32_t addr = (uint32_t)(size_t)(p + i);
+                        const uint32_t sh = (addr & 3u) * 8u;
+                        const uint32_t w = *(const uint32_t*)(p + i - (addr & 3u));
+                        const uint32_t xq = w ^ 0x22222222u, xb = w ^ 0x5C5C5C5Cu;
+                        const uint32_t zq = ~(((xq & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | xq | 0x7F7F7F7Fu);
+                        const uint32_t zb = ~(((xb & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | xb | 0x7F7F7F7Fu);
+                        const uint32_t z = (zq | zb) & (0xFFFFFFFFu << sh);
+                        if (z) {
+                            const uint32_t bit = (uint32_t)__ffs((int)z) - 1u;  // 7, 15, 23 or 31
+                            i += (int)((bit - sh) >> 3);
+                            if ((zb >> bit) & 1u) { has_bs = 1u; i += 2; more = true; }  // escaped byte skipped
+                        } else {
+                            i += 4 - (int)(addr & 3u);
+                            more = true;
+                        }
+                    }
                     if (!__any_sync(kFullMask, more)) break;
-                    const uint32_t esc = (c == '\\') ? 1u : 0u;
-                    has_bs |= esc;
-                    i += more ? (int)(1u + esc) : 0;
                 }
             }
             if (do_val) {
