@@ -182,7 +182,7 @@ int alloc_entries(fg_ctx* c, size_t cap) {
 // whatever does not fit in extra rounds
 int pick_tile(const fg_ctx* c, size_t total_bytes, int n) {
     double mean = n > 0 ? (double)total_bytes / n : 0.0;
-    long t = (long)(mean * fg::kLinesPerCta * 1.20) + 2048;
+    long t = (long)(mean * fg::kLinesPerCta * 1.10) + 1024;
     t = (t + 1023) & ~1023L;
     t = std::max(t, 8L * 1024);
     t = std::min(t, (long)c->max_tile);

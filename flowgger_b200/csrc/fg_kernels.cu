@@ -56,23 +56,16 @@ FG_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
 }
 FG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__constant__ SdTables c_sd_tables;
-
 template <int FMT>
 struct Format;
 
 template <>
 struct Format<0> {  // RFC5424
     typedef R5Shared Shared;
-    static FG_DEV void init_shared(Shared& sh) {
-        // 320 bytes of DFA tables: constant memory -> shared (divergent indexing would serialise in the constant cache)
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_sd_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.tab);
-        for (int k = threadIdx.x; k < (int)(sizeof(SdTables) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    static FG_DEV void init_shared(Shared&) {}
     static FG_DEV void parse(bytes_t p, int len, int line_off, int /*line_idx*/, bool /*active*/, Shared& sh,
                              LineResult& r, const EntrySink& tmp, const ParseParams&) {
-        rfc5424_parse_line(p, len, line_off, sh.tab, &sh.marks[0][threadIdx.x], r, tmp);
+        rfc5424_parse_line(p, len, line_off, &sh.marks[0][threadIdx.x], r, tmp);
     }
     // an SD header needs >= 3 input bytes and a pair >= 4: rows of different lines never overlap
     static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
@@ -105,7 +98,7 @@ struct Format<2> {  // GELF
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(kLinesPerCta) parse_kernel(const __grid_constant__ ParseParams P) {
+__global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
@@ -206,12 +199,7 @@ static int g_max_tile = 48 * 1024;
 
 cudaError_t configure_kernels(int max_tile_bytes) {
     g_max_tile = max_tile_bytes;
-    {
-        SdTables t;
-        sd_tables_fill(t);
-        cudaError_t e0 = cudaMemcpyToSymbol(c_sd_tables, &t, sizeof t);
-        if (e0 != cudaSuccess) return e0;
-    }
+
     {
         static Pow10Table t;
         for (int k = 0; k <= 308; ++k) {

@@ -46,7 +46,8 @@ struct ParseParams {
     LtsvDeviceConfig ltsv;
 };
 
-constexpr int kLinesPerCta = 128;
+constexpr int kLinesPerCta = 128;   // lines (= threads) per CTA (256 was measured slower: bigger barriers, same warps/SM)
+constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (tile ~26 KB at 180 B/line) allows 7 CTAs
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes);

@@ -39,85 +39,14 @@ struct EntrySink {
     uint8_t* meta;
 };
 
-// --- structured-data DFA (parse_data :134-158 + parse_sd_data :174-242) ------------------------
-// The reference's 6-tuple match collapses to these states:
-//   ID    scanning sd_id up to the first ' ' (:175-177)
-//   OUT   !in_name, name None, !in_value        NAME  in_name
-//   EQ    name Some, !in_value (only '"' legal) VAL   in_value, !esc      VESC  in_value, esc
-//   AFTER the byte right after the closing ']' (:145-155)
-enum : uint32_t { SD_ID = 0, SD_OUT = 1, SD_NAME = 2, SD_EQ = 3, SD_VAL = 4, SD_VESC = 5, SD_AFTER = 6, SD_DONE = 7 };
-// byte classes
-enum : uint32_t { CL_SP = 0, CL_QUOTE = 1, CL_BS = 2, CL_EQ = 3, CL_RB = 4, CL_LB = 5, CL_NAME = 6, CL_OTHER = 7 };
-// actions
-enum : uint32_t {
-    AC_NONE = 0, AC_ID_END = 1, AC_NAME_START = 2, AC_NAME_END = 3, AC_BS = 4, AC_PAIR = 5, AC_CLOSE = 6, AC_OPEN = 7,
-    AC_MSG = 8, AC_ERR_FORMAT = 9, AC_ERR_MALFORMED = 10
-};
-
-struct SdTables {
-    uint8_t cls[256];   // byte -> class
-    uint8_t tr[8 * 8];  // state*8 + class -> next | action << 3
-};
-
-__host__ __device__ constexpr uint8_t sd_tr(uint32_t next, uint32_t act) { return (uint8_t)(next | (act << 3)); }
-
-__host__ __device__ inline void sd_tables_fill(SdTables& t) {
-    for (int c = 0; c < 256; ++c) {
-        uint8_t k;
-        if (c == ' ') k = CL_SP;
-        else if (c == '"') k = CL_QUOTE;
-        else if (c == '\\') k = CL_BS;
-        else if (c == '=') k = CL_EQ;
-        else if (c == ']') k = CL_RB;
-        else if (c == '[') k = CL_LB;
-        else if (c >= 33 && c <= 126) k = CL_NAME;  // is_sd_name :188-192
-        else k = CL_OTHER;
-        t.cls[c] = k;
-    }
-    for (int s = 0; s < 8; ++s)
-        for (int c = 0; c < 8; ++c) {
-            uint8_t e = sd_tr(SD_DONE, AC_ERR_FORMAT);  // :235
-            const bool namech = (c == CL_NAME || c == CL_LB || c == CL_BS);
-            switch (s) {
-                case SD_ID: e = (c == CL_SP) ? sd_tr(SD_OUT, AC_ID_END) : sd_tr(SD_ID, AC_NONE); break;
-                case SD_OUT:
-                    if (c == CL_SP || c == CL_QUOTE) e = sd_tr(SD_OUT, AC_NONE);        // :194, :232
-                    else if (c == CL_RB) e = sd_tr(SD_AFTER, AC_CLOSE);                  // :197
-                    else if (namech) e = sd_tr(SD_NAME, AC_NAME_START);                  // :201
-                    break;
-                case SD_NAME:
-                    if (namech) e = sd_tr(SD_NAME, AC_NONE);                             // :205
-                    else if (c == CL_EQ) e = sd_tr(SD_EQ, AC_NAME_END);                  // :208
-                    break;
-                case SD_EQ:
-                    if (c == CL_QUOTE) e = sd_tr(SD_VAL, AC_NONE);                       // :212
-                    break;
-                case SD_VAL:
-                    if (c == CL_BS) e = sd_tr(SD_VESC, AC_BS);                           // :216
-                    else if (c == CL_QUOTE) e = sd_tr(SD_OUT, AC_PAIR);                  // :217
-                    else e = sd_tr(SD_VAL, AC_NONE);                                     // :231
-                    break;
-                case SD_VESC: e = sd_tr(SD_VAL, AC_NONE); break;                         // :231
-                case SD_AFTER:
-                    if (c == CL_LB) e = sd_tr(SD_ID, AC_OPEN);                           // :145
-                    else if (c == CL_SP) e = sd_tr(SD_DONE, AC_MSG);                     // :153
-                    else e = sd_tr(SD_DONE, AC_ERR_MALFORMED);                           // :154
-                    break;
-                default: e = sd_tr(SD_DONE, AC_NONE); break;
-            }
-            t.tr[s * 8 + c] = e;
-        }
-}
-
 // Per-CTA scratch in shared memory used by the RFC5424 parser
 struct R5Shared {
-    SdTables tab;
     int marks[6][128];  // [space index][thread]: positions of the first six spaces
 };
 
 // p: line bytes (shared memory, or global for oversized lines); len may be 0 for idle lanes.
 // marks: &sh.marks[0][threadIdx.x] (stride 128 ints between slots).
-FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, const SdTables& tab, int* marks, LineResult& r,
+FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, LineResult& r,
                                const EntrySink& sink) {
     r.ts = 0.0;
     r.facility = 0xFFu;
