@@ -39,6 +39,19 @@ struct EntrySink {
     uint8_t* meta;
 };
 
+
+// --- 4-bytes-per-step scans over a line cursor ------------------------------------------------------
+// `wp` = the line's bytes viewed as aligned 32-bit words (wp = p - a0, a0 = address of p & 3).  The word that
+// holds byte i is wp[(a0 + i) >> 2]; bytes below the cursor are overwritten with 'A' (never a stop byte) so
+// that the cheap zero-byte test (false positives only ABOVE a true positive) stays exact for the FIRST hit.
+FG_DEV uint32_t swar_zero(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }  // 0x80 where byte == 0 (first hit exact)
+FG_DEV uint32_t scan_word(const uint32_t* wp, uint32_t a0, int i, uint32_t& sh) {
+    const uint32_t o = a0 + (uint32_t)i;
+    sh = (o & 3u) * 8u;
+    const uint32_t keep = 0xFFFFFFFFu << sh;
+    return (wp[o >> 2] & keep) | (0x41414141u & ~keep);
+}
+
 // Per-CTA scratch in shared memory used by the RFC5424 parser
 struct R5Shared {
     int marks[6][128];  // [space index][thread]: positions of the first six spaces
@@ -148,6 +161,8 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
         //   st_id : at the first byte of an sd_id (state ID of the reference walk, :175-177)
         //   !st_id: between params (state OUT: !in_name, name None, !in_value)
         uint32_t n = 1, pairs = 0, hdr = 0;
+        const uint32_t a0 = (uint32_t)(size_t)p & 3u;
+        const uint32_t* wp = (const uint32_t*)(p - a0);
         int i = d + 1, elem_start = d + 1, id_end = 0;
         bool st_id = true;
         const uint32_t sbase = (uint32_t)line_off / 3u;
@@ -162,12 +177,10 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
                 for (;;) {
                     bool more = false;
                     if (i < lim) {
-                        const uint32_t addr = (uint32_t)(size_t)(p + i);
-                        const uint32_t sh = (addr & 3u) * 8u;
-                        const uint32_t x = *(const uint32_t*)(p + i - (addr & 3u)) ^ 0x20202020u;
-                        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu) & (0xFFFFFFFFu << sh);
+                        uint32_t sh;
+                        const uint32_t z = swar_zero(scan_word(wp, a0, i, sh) ^ 0x20202020u);
                         if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);  // stop on the space (may lie past len: checked below)
-                        else { i += 4 - (int)(addr & 3u); more = true; }
+                        else { i += 4 - (int)(sh >> 3); more = true; }
                     }
                     if (!__any_sync(kFullMask, more)) break;
                 }
@@ -214,15 +227,21 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
                     status = FG_E5_SD_FORMAT;  // :235
                 }
             }
-            // (C) NAME: name chars up to '=' (:205, :208)
+            // (C) NAME: name chars up to '=' (:205, :208) — 4 bytes per step; stop bytes: < 33, > 126, '"', '=', ']'
             {
                 const int lim = do_name ? len : i;
                 for (;;) {
-                    uint32_t c = 0;
-                    if (i < lim) c = p[i];
-                    const bool more = (c - 33u <= 93u) && c != '"' && c != '=' && c != ']';
+                    bool more = false;
+                    if (i < lim) {
+                        uint32_t sh;
+                        const uint32_t w = scan_word(wp, a0, i, sh);
+                        const uint32_t z = ((w - 0x21212121u) & ~w & 0x80808080u)       // byte < 33
+                                         | (((w + 0x01010101u) | w) & 0x80808080u)       // byte > 126
+                                         | swar_zero(w ^ 0x22222222u) | swar_zero(w ^ 0x3D3D3D3Du) | swar_zero(w ^ 0x5D5D5D5Du);
+                        if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
+                        else { i += 4 - (int)(sh >> 3); more = true; }
+                    }
                     if (!__any_sync(kFullMask, more)) break;
-                    i += more ? 1 : 0;
                 }
             }
             bool do_val = false;
@@ -244,19 +263,16 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
                 for (;;) {
                     bool more = false;
                     if (i < lim) {
-                        const uint32_t addr = (uint32_t)(size_t)(p + i);
-                        const uint32_t sh = (addr & 3u) * 8u;
-                        const uint32_t w = *(const uint32_t*)(p + i - (addr & 3u));
-                        const uint32_t xq = w ^ 0x22222222u, xb = w ^ 0x5C5C5C5Cu;
-                        const uint32_t zq = ~(((xq & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | xq | 0x7F7F7F7Fu);
-                        const uint32_t zb = ~(((xb & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | xb | 0x7F7F7F7Fu);
-                        const uint32_t z = (zq | zb) & (0xFFFFFFFFu << sh);
+                        uint32_t sh;
+                        const uint32_t w = scan_word(wp, a0, i, sh);
+                        const uint32_t zb = swar_zero(w ^ 0x5C5C5C5Cu);
+                        const uint32_t z = swar_zero(w ^ 0x22222222u) | zb;
                         if (z) {
-                            const uint32_t bit = (uint32_t)__ffs((int)z) - 1u;  // 7, 15, 23 or 31
+                            const uint32_t bit = (uint32_t)__ffs((int)z) - 1u;  // 7, 15, 23 or 31: the first hit is exact
                             i += (int)((bit - sh) >> 3);
                             if ((zb >> bit) & 1u) { has_bs = 1u; i += 2; more = true; }  // escaped byte skipped
                         } else {
-                            i += 4 - (int)(addr & 3u);
+                            i += 4 - (int)(sh >> 3);
                             more = true;
                         }
                     }
