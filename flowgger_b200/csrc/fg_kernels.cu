@@ -56,6 +56,25 @@ FG_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
 }
 FG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// scratch table -> side table (loads first, then stores: independent L2 round trips in flight)
+FG_DEV void copy_rows(uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
+    uint32_t k = 0;
+    for (; k + 4 <= n; k += 4) {
+        int2 a[4];
+        unsigned long long b[4];
+        uint8_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = tmp.name[src + k + u]; b[u] = tmp.val[src + k + u]; c[u] = tmp.meta[src + k + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sink.name[dst + k + u] = a[u]; sink.val[dst + k + u] = b[u]; sink.meta[dst + k + u] = c[u]; }
+    }
+    for (; k < n; ++k) {
+        sink.name[dst + k] = tmp.name[src + k];
+        sink.val[dst + k] = tmp.val[src + k];
+        sink.meta[dst + k] = tmp.meta[src + k];
+    }
+}
+
 template <int FMT>
 struct Format;
 
@@ -63,9 +82,24 @@ template <>
 struct Format<0> {  // RFC5424
     typedef R5Shared Shared;
     static FG_DEV void init_shared(Shared&) {}
-    static FG_DEV void parse(bytes_t p, int len, int line_off, int /*line_idx*/, bool /*active*/, Shared& sh,
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int /*line_idx*/, bool /*active*/, bool in_smem, Shared& sh,
                              LineResult& r, const EntrySink& tmp, const ParseParams&) {
-        rfc5424_parse_line(p, len, line_off, &sh.marks[0][threadIdx.x], r, tmp);
+        rfc5424_parse_line(p, len, line_off, &sh.marks[0][threadIdx.x], in_smem, r, tmp);
+    }
+    // rows [0, stage_cap) were staged compactly in shared memory, the rest in the scratch table
+    static FG_DEV void expand(const LineResult& r, int line_off, uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink,
+                              const EntrySink& tmp) {
+        const uint32_t ns = n < r.stage_cap ? n : r.stage_cap;
+        for (uint32_t k = 0; k < ns; ++k) {
+            int2 nm;
+            unsigned long long v;
+            uint8_t m;
+            r5_unpack(r.stage[k], line_off, nm, v, m);
+            sink.name[dst + k] = nm;
+            sink.val[dst + k] = v;
+            sink.meta[dst + k] = m;
+        }
+        copy_rows(src + ns, dst + ns, n - ns, sink, tmp);
     }
     // an SD header needs >= 3 input bytes and a pair >= 4: rows of different lines never overlap
     static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
@@ -79,9 +113,12 @@ struct Format<1> {  // LTSV
     static FG_DEV void init_shared(Shared&) {}
     // a pair needs >= 1 input byte plus its tab: at most len/2 + 1 rows per line
     static FG_DEV uint32_t scratch_index(int line_off, int line_idx) { return (uint32_t)line_off / 2u + (uint32_t)line_idx; }
-    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, Shared&, LineResult& r,
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, bool /*in_smem*/, Shared&, LineResult& r,
                              const EntrySink& tmp, const ParseParams& P) {
         ltsv_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, P.ltsv, r, tmp);
+    }
+    static FG_DEV void expand(const LineResult&, int, uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
+        copy_rows(src, dst, n, sink, tmp);
     }
 };
 
@@ -91,9 +128,12 @@ struct Format<2> {  // GELF
     static FG_DEV void init_shared(Shared&) {}
     // a top-level member needs >= 5 input bytes (`"":0,`)
     static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
-    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, Shared&, LineResult& r,
+    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, bool /*in_smem*/, Shared&, LineResult& r,
                              const EntrySink& tmp, const ParseParams&) {
         gelf_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, r, tmp);
+    }
+    static FG_DEV void expand(const LineResult&, int, uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
+        copy_rows(src, dst, n, sink, tmp);
     }
 };
 
@@ -142,8 +182,8 @@ __global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(cons
         const int len = active ? o1 - o0 : 0;  // idle lanes run the lock-step phases on an empty line
         LineResult res;
         const int lidx = P.line0 + i;  // index of the line inside the batch (unique scratch slot)
-        if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, lidx, active, fsh, res, tmp, P);
-        else Format<FMT>::parse(P.bytes + o0, len, o0, lidx, active, fsh, res, tmp, P);
+        if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, lidx, active, true, fsh, res, tmp, P);
+        else Format<FMT>::parse(P.bytes + o0, len, o0, lidx, active, false, fsh, res, tmp, P);
         const uint32_t my_n = (active && res.status == FG_ST_OK) ? res.n_entries : 0u;
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
@@ -156,22 +196,7 @@ __global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(cons
             if (my_n && !ovf) {
                 // compact this line's staged rows from the scratch table into the side table
                 my_begin = ebase + excl;
-                const uint32_t src = Format<FMT>::scratch_index(o0, lidx);
-                uint32_t k = 0;
-                for (; k + 4 <= my_n; k += 4) {  // loads first, then stores: 12 independent L2 round trips in flight
-                    int2 a[4];
-                    unsigned long long b[4];
-                    uint8_t c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { a[u] = tmp.name[src + k + u]; b[u] = tmp.val[src + k + u]; c[u] = tmp.meta[src + k + u]; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { sink.name[my_begin + k + u] = a[u]; sink.val[my_begin + k + u] = b[u]; sink.meta[my_begin + k + u] = c[u]; }
-                }
-                for (; k < my_n; ++k) {
-                    sink.name[my_begin + k] = tmp.name[src + k];
-                    sink.val[my_begin + k] = tmp.val[src + k];
-                    sink.meta[my_begin + k] = tmp.meta[src + k];
-                }
+                Format<FMT>::expand(res, o0, Format<FMT>::scratch_index(o0, lidx), my_begin, my_n, sink, tmp);
             }
         }
         if (active) {

@@ -28,7 +28,9 @@ struct LineResult {
     uint32_t facility, severity, flags;
     // spans relative to the line start; off < 0 => None
     int host_o, host_l, app_o, app_l, proc_o, proc_l, mid_o, mid_l, msg_o, msg_l, full_o, full_l;
-    uint32_t n_entries;  // SD headers + pairs staged in the scratch table
+    uint32_t n_entries;  // SD headers + pairs staged for this line
+    unsigned long long* stage;  // RFC5424: compact rows staged in the line's own (already consumed) header bytes
+    uint32_t stage_cap;         // rows [0, stage_cap) are in `stage`, the rest in the scratch table
 };
 
 // provisional side-table rows of one line live at scratch index line_off/3 + k
@@ -52,6 +54,33 @@ FG_DEV uint32_t scan_word(const uint32_t* wp, uint32_t a0, int i, uint32_t& sh) 
     return (wp[o >> 2] & keep) | (0x41414141u & ~keep);
 }
 
+
+// --- side-table staging for RFC5424 ------------------------------------------------------------------------
+// After phase 1 the bytes [0, sp5) of a line (PRI, timestamp, hostname ... msgid) are never read again: every
+// Record field that points there is a span.  A thread therefore stages the compact (u16 positions) rows of its
+// structured data in its OWN header bytes of the shared-memory tile; rows that do not fit (or lines >= 64 KiB,
+// or lines parsed straight from global memory) go to the scratch table.  This removes the L2/DRAM round trip of
+// the provisional rows for ~97 % of C2 lines (profiles/r1_notes.md).
+FG_DEV unsigned long long r5_pack_pair(int ns, int ne, int ve, uint32_t esc) {
+    return (unsigned long long)(uint32_t)ns | ((unsigned long long)(uint32_t)ne << 16) | ((unsigned long long)(uint32_t)ve << 32) |
+           ((unsigned long long)(esc ? 1u : 0u) << 48);
+}
+FG_DEV unsigned long long r5_pack_header(int es, int id_end, uint32_t pairs) {
+    return (unsigned long long)(uint32_t)es | ((unsigned long long)(uint32_t)id_end << 16) | ((unsigned long long)pairs << 32) | (0x8000ull << 48);
+}
+FG_DEV void r5_unpack(unsigned long long v, int line_off, int2& name, unsigned long long& val, uint8_t& meta) {
+    const int a = (int)(v & 0xFFFFu), b = (int)((v >> 16) & 0xFFFFu), c = (int)((v >> 32) & 0xFFFFu);
+    if ((v >> 63) & 1ull) {  // SD element header: name = sd_id, val = #pairs
+        name = make_int2(line_off + a, b - a);
+        val = (unsigned long long)c;
+        meta = 7u;
+    } else {
+        name = make_int2(line_off + a, b - a);
+        val = (unsigned long long)(uint32_t)(line_off + b + 2) | ((unsigned long long)(uint32_t)(c - (b + 2)) << 32);
+        meta = (uint8_t)(((v >> 48) & 1ull) ? 0x08u : 0u);
+    }
+}
+
 // Per-CTA scratch in shared memory used by the RFC5424 parser
 struct R5Shared {
     int marks[6][128];  // [space index][thread]: positions of the first six spaces
@@ -59,7 +88,7 @@ struct R5Shared {
 
 // p: line bytes (shared memory, or global for oversized lines); len may be 0 for idle lanes.
 // marks: &sh.marks[0][threadIdx.x] (stride 128 ints between slots).
-FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, LineResult& r,
+FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, bool in_smem, LineResult& r,
                                const EntrySink& sink) {
     r.ts = 0.0;
     r.facility = 0xFFu;
@@ -68,6 +97,8 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
     r.host_o = r.app_o = r.proc_o = r.mid_o = r.msg_o = r.full_o = -1;
     r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
     r.n_entries = 0;
+    r.stage = nullptr;
+    r.stage_cap = 0;
     uint32_t status = FG_ST_OK;
 
     // ---- BOM::parse :63-71 ---------------------------------------------------------------------
@@ -166,6 +197,18 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
         int i = d + 1, elem_start = d + 1, id_end = 0;
         bool st_id = true;
         const uint32_t sbase = (uint32_t)line_off / 3u;
+        // staging area: the 8-byte aligned part of this line's header bytes [0, sp5)
+        unsigned long long* stg = nullptr;
+        uint32_t cap = 0;
+        if (walk && in_smem && len < 65536) {
+            const uint32_t pad = (8u - ((uint32_t)(size_t)p & 7u)) & 7u;
+            if ((uint32_t)sp5 > pad + 8u) {
+                stg = (unsigned long long*)(const_cast<uint8_t*>(p) + pad);
+                cap = ((uint32_t)sp5 - pad) >> 3;
+            }
+        }
+        r.stage = stg;
+        r.stage_cap = cap;
         bool active = walk;
         // Inner scans are written as `lim`-bounded loops whose only loop-carried value is the cursor:
         // a lane that is not scanning has lim == i and falls through; nothing else is updated inside.
@@ -207,10 +250,14 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
             if (active) {
                 const uint32_t c = p[i];
                 if (c == ']') {  // :197 end of this element, then :145-155
-                    const uint32_t e = sbase + hdr;
-                    sink.name[e] = make_int2(line_off + elem_start, id_end - elem_start);
-                    sink.val[e] = pairs;
-                    sink.meta[e] = 7u;  // FG_TAG_SD_HEADER
+                    if (hdr < cap) {
+                        stg[hdr] = r5_pack_header(elem_start, id_end, pairs);
+                    } else {
+                        const uint32_t e = sbase + hdr;
+                        sink.name[e] = make_int2(line_off + elem_start, id_end - elem_start);
+                        sink.val[e] = pairs;
+                        sink.meta[e] = 7u;  // FG_TAG_SD_HEADER
+                    }
                     if (i + 1 >= len) { active = false; status = FG_E5_MISSING_MSG; }  // :148
                     else {
                         const uint32_t c2 = p[i + 1];
@@ -282,11 +329,15 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, Lin
             if (do_val) {
                 if (i >= len) { active = false; status = FG_E5_SD_NO_END; }
                 else {
-                    const uint32_t e = sbase + n;
-                    sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
-                    sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
-                                  ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
-                    sink.meta[e] = (uint8_t)(has_bs ? 0x08u : 0u);  // FG_TAG_STRING | FG_EM_UNESCAPE
+                    if (n < cap) {
+                        stg[n] = r5_pack_pair(name_start, name_end, i, has_bs);
+                    } else {
+                        const uint32_t e = sbase + n;
+                        sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
+                        sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |
+                                      ((unsigned long long)(uint32_t)(i - (name_end + 2)) << 32);
+                        sink.meta[e] = (uint8_t)(has_bs ? 0x08u : 0u);  // FG_TAG_STRING | FG_EM_UNESCAPE
+                    }
                     ++n;
                     ++pairs;
                     ++i;
