@@ -94,6 +94,7 @@ struct fg_ctx {
     int2* d_tmp_name = nullptr;  // provisional side-table rows, indexed by byte offset / scratch_div
     unsigned long long* d_tmp_val = nullptr;
     uint8_t* d_tmp_meta = nullptr;
+    size_t tmp_cap = 0;
     size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
@@ -175,6 +176,25 @@ int alloc_entries(fg_ctx* c, size_t cap) {
     FG_CUDA(c, cudaHostAlloc(&c->h_entry_val, cap * sizeof(uint64_t), cudaHostAllocDefault));
     FG_CUDA(c, cudaHostAlloc(&c->h_entry_meta, cap, cudaHostAllocDefault));
     c->entry_cap = cap;
+    return FG_OK;
+}
+
+// Scratch table for provisional side-table rows, indexed by byte offset (see Format<>::scratch_index):
+// a row needs >= 3 input bytes in RFC5424 / GELF, >= 1 byte + its TAB in LTSV.  Allocated on first use of a format.
+int ensure_scratch(fg_ctx* c, int fmt) {
+    const size_t need = (fmt == FG_FMT_LTSV ? c->max_bytes / 2 + (size_t)c->max_lines : c->max_bytes / 3) + 64;
+    if (c->tmp_cap >= need) return FG_OK;
+    if (c->d_tmp_name) cudaFree(c->d_tmp_name);
+    if (c->d_tmp_val) cudaFree(c->d_tmp_val);
+    if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
+    c->d_tmp_name = nullptr;
+    c->d_tmp_val = nullptr;
+    c->d_tmp_meta = nullptr;
+    c->tmp_cap = 0;
+    FG_CUDA(c, cudaMalloc(&c->d_tmp_name, need * sizeof(int2)));
+    FG_CUDA(c, cudaMalloc(&c->d_tmp_val, need * sizeof(unsigned long long)));
+    FG_CUDA(c, cudaMalloc(&c->d_tmp_meta, need));
+    c->tmp_cap = need;
     return FG_OK;
 }
 
@@ -367,13 +387,6 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     const size_t rows_bytes = col_off(c, C_COUNT);
     FG_CREATE_CUDA(cudaMalloc(&c->d_rows, rows_bytes));
     FG_CREATE_CUDA(cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
-    {
-        // a side-table row needs >= 2 input bytes in every format (LTSV ":\t"), >= 3 in RFC5424
-        const size_t tmp_cap = c->max_bytes / 2 + (size_t)c->max_lines + 64;
-        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_name, tmp_cap * sizeof(int2)));
-        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_val, tmp_cap * sizeof(unsigned long long)));
-        FG_CREATE_CUDA(cudaMalloc(&c->d_tmp_meta, tmp_cap));
-    }
     FG_CREATE_CUDA(cudaMalloc(&c->d_counter, 256));
     FG_CREATE_CUDA(cudaMemset(c->d_counter, 0, 256));
     for (int b = 0; b < 2; ++b) {
@@ -479,6 +492,7 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
     if (int rc = check_batch(c, bytes, offsets, n)) return rc;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
     memset(out, 0, sizeof *out);
     if (n == 0) {
         fill_out(c, fmt, 0, 0, out);
@@ -558,6 +572,7 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     if (!c) return FG_E_ARG;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
     for (int attempt = 0; attempt < 2; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
         fg::ParseParams P;

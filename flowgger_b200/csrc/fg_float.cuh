@@ -163,6 +163,60 @@ __device__ __noinline__ double big_decimal_to_f64(bytes_t p, int a, int b, int q
     return __longlong_as_double((long long)M);
 }
 
+
+// ---- Eisel-Lemire (core::num::dec2flt::lemire::compute_float) ----------------------------------------------
+// Decides almost every <= 19-digit input in ~60 instructions; returns false when it cannot (the caller then takes
+// the exact big-integer path, like dec2flt's slow path).  Table: 128-bit truncated 5^q, q = -342 .. 308.
+struct Pow5 {
+    unsigned long long hi, lo;
+};
+__device__ const Pow5 kPow5[651] = {
+#include "fg_pow5_table.inc"
+};
+
+FG_DEV bool eisel_lemire(long long q, uint64_t w, uint64_t& bits) {
+    if (w == 0 || q < -342) { bits = 0; return true; }
+    if (q > 308) { bits = 0x7FF0000000000000ull; return true; }
+    const int lz = __clzll((long long)w);
+    w <<= lz;
+    // compute_product_approx(q, w, 52 + 3)
+    const Pow5 t = kPow5[q + 342];
+    uint64_t first_lo = w * t.hi, first_hi = __umul64hi(w, t.hi);
+    const uint64_t mask = 0xFFFFFFFFFFFFFFFFull >> 55;
+    if ((first_hi & mask) == mask) {
+        const uint64_t second_hi = __umul64hi(w, t.lo);
+        first_lo += second_hi;
+        if (second_hi > first_lo) ++first_hi;
+    }
+    const uint64_t lo = first_lo, hi = first_hi;
+    if (lo == 0xFFFFFFFFFFFFFFFFull && !(q >= -27 && q <= 55)) return false;
+    const int upperbit = (int)(hi >> 63);
+    uint64_t mantissa = hi >> (upperbit + 64 - 52 - 3);
+    int power2 = (int)((((int)q * (152170 + 65536)) >> 16) + 63) + upperbit - lz + 1023;
+    if (power2 <= 0) {
+        if (-power2 + 1 >= 64) { bits = 0; return true; }
+        mantissa >>= -power2 + 1;
+        mantissa += mantissa & 1ull;
+        mantissa >>= 1;
+        power2 = (mantissa >= (1ull << 52)) ? 1 : 0;
+        bits = mantissa + ((uint64_t)power2 << 52) - ((power2 ? (1ull << 52) : 0ull));
+        // BiasedFp{f: mantissa, e: power2}: when the subnormal rounds up to 2^52 the hidden bit IS the exponent field
+        bits = power2 ? (1ull << 52) | (mantissa & ((1ull << 52) - 1ull)) : mantissa;
+        return true;
+    }
+    if (lo <= 1 && q >= -4 && q <= 23 && (mantissa & 3ull) == 1ull && (mantissa << (upperbit + 64 - 52 - 3)) == hi) mantissa &= ~1ull;
+    mantissa += mantissa & 1ull;
+    mantissa >>= 1;
+    if (mantissa >= (2ull << 52)) {
+        mantissa = 1ull << 52;
+        ++power2;
+    }
+    mantissa &= ~(1ull << 52);
+    if (power2 >= 0x7FF) { bits = 0x7FF0000000000000ull; return true; }
+    bits = mantissa | ((uint64_t)power2 << 52);
+    return true;
+}
+
 FG_DEV bool ieq3(bytes_t p, int i, char a, char b, char c) {
     return (p[i] | 0x20u) == (uint32_t)a && (p[i + 1] | 0x20u) == (uint32_t)b && (p[i + 2] | 0x20u) == (uint32_t)c;
 }
@@ -232,8 +286,18 @@ __device__ __noinline__ bool parse_f64_rust(bytes_t p, int a, int b, double& out
             const double dw = (double)(long long)w;
             v = q < 0 ? __ddiv_rn(dw, kPow10Exact[-q]) : __dmul_rn(dw, kPow10Exact[q]);
         } else {
-            int qq = q > 100000 ? 100000 : (q < -100000 ? -100000 : (int)q);
-            v = big_decimal_to_f64(p, mant_start, mant_end, qq);
+            // Eisel-Lemire on the (at most) 19 leading digits; with more digits the truncated and the bumped
+            // significand must agree (dec2flt::dec2flt), otherwise — or when the approximation is undecided — exact path
+            const long long q19 = q + (nd > 19 ? nd - 19 : 0);
+            uint64_t b1 = 0, b2 = 0;
+            bool ok = eisel_lemire(q19, w, b1);
+            if (ok && nd > 19) ok = eisel_lemire(q19, w + 1, b2) && b1 == b2;
+            if (ok) {
+                v = __longlong_as_double((long long)b1);
+            } else {
+                int qq = q > 100000 ? 100000 : (q < -100000 ? -100000 : (int)q);
+                v = big_decimal_to_f64(p, mant_start, mant_end, qq);
+            }
         }
     }
     out = neg ? -v : v;
