@@ -59,8 +59,22 @@ FG_DEV bool json_hex4(Json& j, uint32_t& n) {
 __device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
     s = j.i;
     has_bs = false;
+    const uint32_t a0 = (uint32_t)(size_t)j.p & 3u;
+    const uint32_t* wp = (const uint32_t*)(j.p - a0);
     for (;;) {
         if (j.i >= j.len) return JS_SYNTAX;  // EOFWhileParsingString
+        {
+            // 4 bytes per step up to the next '"', '\\' or control byte (read.rs ESCAPE table)
+            uint32_t sh;
+            const uint32_t w = scan_word(wp, a0, j.i, sh);
+            const uint32_t z = swar_zero(w ^ 0x22222222u) | swar_zero(w ^ 0x5C5C5C5Cu) | ((w - 0x20202020u) & ~w & 0x80808080u);
+            if (!z) {
+                j.i += 4 - (int)(sh >> 3);
+                continue;
+            }
+            j.i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
+            if (j.i >= j.len) return JS_SYNTAX;  // the hit lies past the end of the line
+        }
         const uint32_t c = j.p[j.i];
         if (c == '"') {
             e = j.i;
@@ -96,10 +110,9 @@ __device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
             }
             continue;
         }
-        if (c < 0x20u) {
-            if (!j.mode2) return JS_CONTROL;  // first parse: InvalidUnicodeCodePoint -> the caller retries
-            if (c != '\n') return JS_SYNTAX;  // retry text still holds this control byte
-        }
+        // control byte (< 0x20)
+        if (!j.mode2) return JS_CONTROL;  // first parse: InvalidUnicodeCodePoint -> the caller retries
+        if (c != '\n') return JS_SYNTAX;  // retry text still holds this control byte
         ++j.i;
     }
 }
@@ -300,15 +313,48 @@ __device__ __noinline__ bool json_str_is(bytes_t p, int a0, int a1, bool mode2, 
     return key_iter_next(x) < 0;
 }
 
+
+// Top-level members of one line while it is being parsed: the first kMaxLocalMembers live in per-thread local
+// memory (L1-resident); an object with more members spills everything to the scratch table (rare).
+constexpr int kMaxLocalMembers = 24;
+struct Members {
+    int2 name[kMaxLocalMembers];
+    unsigned long long val[kMaxLocalMembers];
+    uint8_t meta[kMaxLocalMembers];
+    uint32_t m;
+    bool spilled;
+};
+FG_DEV void members_put(Members& M, const EntrySink& sink, uint32_t sbase, int2 name, unsigned long long val, uint32_t meta) {
+    if (!M.spilled && M.m < (uint32_t)kMaxLocalMembers) {
+        M.name[M.m] = name;
+        M.val[M.m] = val;
+        M.meta[M.m] = (uint8_t)meta;
+    } else {
+        if (!M.spilled) {
+            for (uint32_t k = 0; k < M.m; ++k) {
+                sink.name[sbase + k] = M.name[k];
+                sink.val[sbase + k] = M.val[k];
+                sink.meta[sbase + k] = M.meta[k];
+            }
+            M.spilled = true;
+        }
+        sink.name[sbase + M.m] = name;
+        sink.val[sbase + M.m] = val;
+        sink.meta[sbase + M.m] = (uint8_t)meta;
+    }
+    ++M.m;
+}
+
 // One full parse of the document in the given mode.  Returns JS_*; on JS_OK `is_object` tells whether the
 // top-level value is an object and `m` members were staged at sink[sbase ..) in document order.
 __device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off, uint32_t sbase, bool mode2,
-                                                const EntrySink& sink, bool& is_object, uint32_t& m) {
+                                                const EntrySink& sink, bool& is_object, Members& M) {
     Json j;
     j.p = p; j.len = len; j.i = 0; j.mode2 = mode2;
     uint32_t stack[4] = {0u, 0u, 0u, 0u};  // bit d-1: container at depth d is an object
     int depth = 0;                          // open containers (serde: remaining_depth = 128 - depth)
-    m = 0;
+    M.m = 0;
+    M.spilled = false;
     is_object = false;
     // member being built (only meaningful at depth 1 of a top-level object)
     int key_s = 0, key_e = 0;
@@ -358,11 +404,7 @@ __device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off
                 const bool obj = c == '{';
                 if (depth == 0) is_object = obj;
                 if (depth == 1 && is_object) {  // a container as a top-level member value
-                    const uint32_t e = sbase + m;
-                    sink.name[e] = make_int2(line_off + key_s, key_e - key_s);
-                    sink.val[e] = 0;
-                    sink.meta[e] = (uint8_t)(JT_CONTAINER | (key_bs ? 0x40u : 0u));
-                    ++m;
+                    members_put(M, sink, sbase, make_int2(line_off + key_s, key_e - key_s), 0ull, JT_CONTAINER | (key_bs ? 0x40u : 0u));
                 }
                 if (obj) stack[depth >> 5] |= 1u << (depth & 31);
                 else stack[depth >> 5] &= ~(1u << (depth & 31));
@@ -382,11 +424,7 @@ __device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off
             }
             if (scalar) {
                 if (depth == 1 && is_object) {
-                    const uint32_t e = sbase + m;
-                    sink.name[e] = make_int2(line_off + key_s, key_e - key_s);
-                    sink.val[e] = bits;
-                    sink.meta[e] = (uint8_t)(tag | vflags | (key_bs ? 0x40u : 0u));
-                    ++m;
+                    members_put(M, sink, sbase, make_int2(line_off + key_s, key_e - key_s), bits, tag | vflags | (key_bs ? 0x40u : 0u));
                 }
                 st = ST_AFTER;
             }
@@ -427,6 +465,56 @@ __device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off
     return JS_OK;
 }
 
+// Per-key rules of gelf_decoder.rs:51-107 applied to one (deduplicated) member, in sorted-key order.
+struct GelfAcc {
+    uint32_t status, flags, kept;
+    bool have_ts;
+};
+__device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta,
+                                               LineResult& r, GelfAcc& g, const EntrySink& sink, uint32_t sbase) {
+    const int ks = name.x - line_off, ke = ks + name.y;
+    const uint32_t tag = meta & 7u;
+    const int vs = (int)(uint32_t)(val & 0xFFFFFFFFull) - line_off, vl = (int)(val >> 32);
+    // reserved keys contain no '_' and differ in their first byte: skip the literal compares for ordinary `_extra` keys
+    const uint32_t k0 = (ke > ks) ? p[ks] : 0u;
+    const bool maybe = k0 == 't' || k0 == 'h' || k0 == 's' || k0 == 'f' || k0 == 'v' || k0 == 'l' || k0 == '\\';
+    if (maybe && json_str_is(p, ks, ke, mode2, "timestamp", 9)) {  // as_f64 :53
+        if (tag == JT_F64) r.ts = __longlong_as_double((long long)val);
+        else if (tag == JT_U64) r.ts = __ull2double_rn(val);
+        else if (tag == JT_I64) r.ts = __ll2double_rn((long long)val);
+        else g.status = FG_EG_TS;
+        g.have_ts = true;
+    } else if (maybe && json_str_is(p, ks, ke, mode2, "host", 4)) {
+        if (tag != JT_STRING) g.status = FG_EG_HOST;
+        else { r.host_o = vs; r.host_l = vl; if (meta & 0x08u) g.flags |= 0x04u; }
+    } else if (maybe && json_str_is(p, ks, ke, mode2, "short_message", 13)) {
+        if (tag != JT_STRING) g.status = FG_EG_SHORT;
+        else { r.msg_o = vs; r.msg_l = vl; if (meta & 0x08u) g.flags |= 0x08u; }
+    } else if (maybe && json_str_is(p, ks, ke, mode2, "full_message", 12)) {
+        if (tag != JT_STRING) g.status = FG_EG_FULL;
+        else { r.full_o = vs; r.full_l = vl; if (meta & 0x08u) g.flags |= 0x10u; }
+    } else if (maybe && json_str_is(p, ks, ke, mode2, "version", 7)) {
+        if (tag != JT_STRING) g.status = FG_EG_VERSION_T;
+        else if (!json_str_is(p, vs, vs + vl, mode2, "1.0", 3) && !json_str_is(p, vs, vs + vl, mode2, "1.1", 3)) g.status = FG_EG_VERSION;
+    } else if (maybe && json_str_is(p, ks, ke, mode2, "level", 5)) {  // as_u64 :83
+        if (tag != JT_U64) g.status = FG_EG_SEV;
+        else if (val > 7ull) g.status = FG_EG_SEV_HIGH;
+        else r.severity = (uint32_t)val;
+    } else {
+        if (tag == JT_CONTAINER) g.status = FG_EG_SD_TYPE;  // :97
+        else {
+            KeyIter it;
+            key_iter_init(it, p, ks, ke, mode2);
+            const bool under = key_iter_next(it) == '_';
+            const uint32_t e = sbase + g.kept;
+            sink.name[e] = name;
+            sink.val[e] = val;
+            sink.meta[e] = (uint8_t)((meta & 0x4Fu) | (under ? 0x10u : 0u));  // tag | UNESCAPE | NAME_ESC | NO_PREFIX
+            ++g.kept;
+        }
+    }
+}
+
 // All 32 lanes call this; idle lanes pass active_line = false.
 FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bool active_line, LineResult& r,
                             const EntrySink& sink) {
@@ -439,19 +527,52 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     r.n_entries = 0;
     r.status = FG_EG_JSON;
     if (active_line) {
-        uint32_t status = FG_ST_OK, flags = 0, m = 0;
+        GelfAcc g;
+        g.status = FG_ST_OK;
+        g.flags = 0;
+        g.kept = 0;
+        g.have_ts = false;
+        Members M;
         bool is_object = false, mode2 = false;
-        int rc = gelf_parse_document(p, len, line_off, sbase, false, sink, is_object, m);
+        int rc = gelf_parse_document(p, len, line_off, sbase, false, sink, is_object, M);
         if (rc == JS_CONTROL) {  // gelf_decoder.rs:44-46
             mode2 = true;
-            flags |= 0x20u;  // FG_FLAG_NL_RETRY
-            rc = gelf_parse_document(p, len, line_off, sbase, true, sink, is_object, m);
+            g.flags |= 0x20u;  // FG_FLAG_NL_RETRY
+            rc = gelf_parse_document(p, len, line_off, sbase, true, sink, is_object, M);
         }
-        if (rc != JS_OK) status = FG_EG_JSON;            // :49
-        else if (!is_object) status = FG_EG_EMPTY;       // :50
-        uint32_t kept = 0;
-        if (status == FG_ST_OK) {
-            // BTreeMap order: stable insertion sort of the staged members by unescaped key
+        if (rc != JS_OK) g.status = FG_EG_JSON;        // :49
+        else if (!is_object) g.status = FG_EG_EMPTY;   // :50
+        const uint32_t m = M.m;
+        if (g.status == FG_ST_OK && !M.spilled) {
+            // BTreeMap order: stable insertion sort of an index permutation by unescaped key (members stay in local memory)
+            uint8_t ord[kMaxLocalMembers];
+            for (uint32_t a = 0; a < m; ++a) {
+                const int2 kn = M.name[a];
+                int b = (int)a - 1;
+                while (b >= 0) {
+                    const int2 on = M.name[ord[b]];
+                    if (json_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y, mode2) <= 0) break;
+                    ord[b + 1] = ord[b];
+                    --b;
+                }
+                ord[b + 1] = (uint8_t)a;
+            }
+            uint32_t gi = 0;
+            while (gi < m && g.status == FG_ST_OK) {
+                uint32_t ge = gi + 1;  // group of equal keys [gi, ge): the last inserted value wins
+                const int2 gn = M.name[ord[gi]];
+                const int ks = gn.x - line_off, ke = ks + gn.y;
+                while (ge < m) {
+                    const int2 nn = M.name[ord[ge]];
+                    if (json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2) != 0) break;
+                    ++ge;
+                }
+                const uint32_t w = ord[ge - 1];
+                gelf_apply_member(p, line_off, mode2, M.name[w], M.val[w], M.meta[w], r, g, sink, sbase);
+                gi = ge;
+            }
+        } else if (g.status == FG_ST_OK) {
+            // > kMaxLocalMembers members: same algorithm in place on the scratch table
             for (uint32_t a = 1; a < m; ++a) {
                 const int2 kn = sink.name[sbase + a];
                 const unsigned long long kv = sink.val[sbase + a];
@@ -471,69 +592,30 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                     sink.meta[sbase + b + 1] = km;
                 }
             }
-            bool have_ts = false;
-            uint32_t g = 0;
-            while (g < m && status == FG_ST_OK) {
-                // group of equal keys [g, ge): the last inserted value wins
-                uint32_t ge = g + 1;
-                const int2 gn = sink.name[sbase + g];
+            uint32_t gi = 0;
+            while (gi < m && g.status == FG_ST_OK) {
+                uint32_t ge = gi + 1;
+                const int2 gn = sink.name[sbase + gi];
                 const int ks = gn.x - line_off, ke = ks + gn.y;
                 while (ge < m) {
                     const int2 nn = sink.name[sbase + ge];
                     if (json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2) != 0) break;
                     ++ge;
                 }
-                const unsigned long long val = sink.val[sbase + ge - 1];
-                const uint32_t meta = sink.meta[sbase + ge - 1];
-                const uint32_t tag = meta & 7u;
-                const int vs = (int)(uint32_t)(val & 0xFFFFFFFFull) - line_off, vl = (int)(val >> 32);
-                if (json_str_is(p, ks, ke, mode2, "timestamp", 9)) {  // as_f64 :53
-                    if (tag == JT_F64) r.ts = __longlong_as_double((long long)val);
-                    else if (tag == JT_U64) r.ts = __ull2double_rn(val);
-                    else if (tag == JT_I64) r.ts = __ll2double_rn((long long)val);
-                    else status = FG_EG_TS;
-                    have_ts = true;
-                } else if (json_str_is(p, ks, ke, mode2, "host", 4)) {
-                    if (tag != JT_STRING) status = FG_EG_HOST;
-                    else { r.host_o = vs; r.host_l = vl; if (meta & 0x08u) flags |= 0x04u; else flags &= ~0x04u; }
-                } else if (json_str_is(p, ks, ke, mode2, "short_message", 13)) {
-                    if (tag != JT_STRING) status = FG_EG_SHORT;
-                    else { r.msg_o = vs; r.msg_l = vl; if (meta & 0x08u) flags |= 0x08u; }
-                } else if (json_str_is(p, ks, ke, mode2, "full_message", 12)) {
-                    if (tag != JT_STRING) status = FG_EG_FULL;
-                    else { r.full_o = vs; r.full_l = vl; if (meta & 0x08u) flags |= 0x10u; }
-                } else if (json_str_is(p, ks, ke, mode2, "version", 7)) {
-                    if (tag != JT_STRING) status = FG_EG_VERSION_T;
-                    else if (!json_str_is(p, vs, vs + vl, mode2, "1.0", 3) && !json_str_is(p, vs, vs + vl, mode2, "1.1", 3))
-                        status = FG_EG_VERSION;
-                } else if (json_str_is(p, ks, ke, mode2, "level", 5)) {  // as_u64 :83
-                    if (tag != JT_U64) status = FG_EG_SEV;
-                    else if (val > 7ull) status = FG_EG_SEV_HIGH;
-                    else r.severity = (uint32_t)val;
-                } else {
-                    if (tag == JT_CONTAINER) status = FG_EG_SD_TYPE;  // :97
-                    else {
-                        KeyIter it;
-                        key_iter_init(it, p, ks, ke, mode2);
-                        const bool under = key_iter_next(it) == '_';
-                        const uint32_t e = sbase + kept;
-                        sink.name[e] = sink.name[sbase + ge - 1];  // same member as `meta` (its NAME_ESC flag)
-                        sink.val[e] = val;
-                        sink.meta[e] = (uint8_t)((meta & 0x4Fu) | (under ? 0x10u : 0u));  // tag | UNESCAPE | NAME_ESC | NO_PREFIX
-                        ++kept;
-                    }
-                }
-                g = ge;
-            }
-            if (status == FG_ST_OK) {
-                if (r.host_o < 0) status = FG_EG_MISSING_HOST;  // :110
-                else if (!have_ts) flags |= 0x01u;              // FG_FLAG_TS_MISSING :109
+                // rows [0, kept) are rewritten in place: kept <= gi, so nothing unread is clobbered
+                gelf_apply_member(p, line_off, mode2, sink.name[sbase + ge - 1], sink.val[sbase + ge - 1], sink.meta[sbase + ge - 1], r, g,
+                                  sink, sbase);
+                gi = ge;
             }
         }
-        if (status == FG_ST_OK) r.n_entries = kept;
+        if (g.status == FG_ST_OK) {
+            if (r.host_o < 0) g.status = FG_EG_MISSING_HOST;  // :110
+            else if (!g.have_ts) g.flags |= 0x01u;            // FG_FLAG_TS_MISSING :109
+        }
+        if (g.status == FG_ST_OK) r.n_entries = g.kept;
         else { r.host_o = r.msg_o = r.full_o = -1; r.severity = 0xFFu; r.ts = 0.0; }
-        r.flags = flags;
-        r.status = status;
+        r.flags = g.flags;
+        r.status = g.status;
     }
     __syncwarp();
 }

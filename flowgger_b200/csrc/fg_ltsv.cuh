@@ -135,30 +135,46 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     int err_pos = 0;
     int part = 0;  // start of the current part
     bool active = active_line;
+    const uint32_t a0 = (uint32_t)(size_t)p & 3u;
+    const uint32_t* wp = (const uint32_t*)(p - a0);
+    // The `time` value is parsed AFTER the part loop, in lock step for the whole warp (its position among the 20
+    // fields differs per line, so parsing it inline would run one lane at a time).  Evaluation order is preserved:
+    // a second `time`, or any error found later in the line, first settles the pending one.
+    int ts_a = -1, ts_b = -1, ts_part = 0;
+    bool err_set = false;
     while (__any_sync(kFullMask, active)) {  // line.split('\t') :94
-        // scan the part: first ':' (splitn(2, ':') :95) and the terminating tab
+        // scan the part 4 bytes per step: first ':' (splitn(2, ':') :95), then the terminating TAB
         int i = part;
         {
             const int lim = active ? len : i;
             for (;;) {
-                uint32_t c = '\t';
-                if (i < lim) c = p[i];
-                const bool more = c != '\t' && c != ':';
+                bool more = false;
+                if (i < lim) {
+                    uint32_t sh;
+                    const uint32_t w = scan_word(wp, a0, i, sh);
+                    const uint32_t z = swar_zero(w ^ 0x09090909u) | swar_zero(w ^ 0x3A3A3A3Au);
+                    if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
+                    else { i += 4 - (int)(sh >> 3); more = true; }
+                }
                 if (!__any_sync(kFullMask, more)) break;
-                i += more ? 1 : 0;
             }
+            if (i > len) i = len;  // a hit past the end of the line belongs to the next one
         }
         const bool has_colon = active && i < len && p[i] == ':';
         const int colon = i;
         {
             const int lim = has_colon ? len : i;
             for (;;) {
-                uint32_t c = '\t';
-                if (i < lim) c = p[i];
-                const bool more = c != '\t';
+                bool more = false;
+                if (i < lim) {
+                    uint32_t sh;
+                    const uint32_t z = swar_zero(scan_word(wp, a0, i, sh) ^ 0x09090909u);
+                    if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
+                    else { i += 4 - (int)(sh >> 3); more = true; }
+                }
                 if (!__any_sync(kFullMask, more)) break;
-                i += more ? 1 : 0;
             }
+            if (i > len) i = len;
         }
         const int part_end = i;
         if (active) {
@@ -166,18 +182,29 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                 flags |= 0x02u;  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
             } else {
                 const int ka = part, kn = colon - part, va = colon + 1, vb = part_end;
-                if (key_is(p, ka, kn, "time", 4)) {  // :104-111
-                    int ta = va, tb = vb;
-                    if (tb - ta >= 2 && p[ta] == '[' && p[tb - 1] == ']') { ++ta; --tb; }
-                    if (ltsv_parse_ts(p, ta, tb, r.ts)) have_ts = true;
-                    else status = FG_EL_TS;
-                } else if (key_is(p, ka, kn, "host", 4)) {
+                // the four reserved keys differ in (length, first byte): one cheap test rejects ordinary keys
+                const uint32_t k0 = kn > 0 ? p[ka] : 0u;
+                const bool maybe = (kn == 4 && (k0 == 't' || k0 == 'h')) || (kn == 7 && k0 == 'm') || (kn == 5 && k0 == 'l');
+                if (maybe && key_is(p, ka, kn, "time", 4)) {  // :104-111
+                    if (ts_a >= 0) {  // an earlier `time` is still pending: it is evaluated first (a failure returns there)
+                        if (ltsv_parse_ts(p, ts_a, ts_b, r.ts)) have_ts = true;
+                        else { status = FG_EL_TS; err_pos = ts_part; err_set = true; }
+                    }
+                    if (status == FG_ST_OK) {
+                        ts_a = va;
+                        ts_b = vb;
+                        ts_part = part;
+                        if (ts_b - ts_a >= 2 && p[ts_a] == '[' && p[ts_b - 1] == ']') { ++ts_a; --ts_b; }
+                    } else {
+                        ts_a = -1;
+                    }
+                } else if (maybe && key_is(p, ka, kn, "host", 4)) {
                     r.host_o = va;
                     r.host_l = vb - va;
-                } else if (key_is(p, ka, kn, "message", 7)) {
+                } else if (maybe && key_is(p, ka, kn, "message", 7)) {
                     r.msg_o = va;
                     r.msg_l = vb - va;
-                } else if (key_is(p, ka, kn, "level", 5)) {  // :114-121
+                } else if (maybe && key_is(p, ka, kn, "level", 5)) {  // :114-121
                     uint32_t sev;
                     if (!parse_u8(p, va, vb, sev)) status = FG_EL_SEV;
                     else if (sev > 7u) status = FG_EL_SEV_HIGH;
@@ -218,12 +245,28 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                 }
             }
             if (status != FG_ST_OK) {
-                err_pos = part;
+                if (!err_set) err_pos = part;  // the error belongs to the current part
+                if (ts_a >= 0) {
+                    // an error in a LATER part: the pending `time` (earlier in the line) is evaluated first
+                    double t;
+                    if (!ltsv_parse_ts(p, ts_a, ts_b, t)) { status = FG_EL_TS; err_pos = ts_part; }
+                    ts_a = -1;
+                }
                 active = false;
             } else if (part_end >= len) {
                 active = false;
             } else {
                 part = part_end + 1;
+            }
+        }
+    }
+    // the pending `time` of every lane, in lock step
+    {
+        const bool pend = active_line && status == FG_ST_OK && ts_a >= 0;
+        if (__any_sync(kFullMask, pend)) {
+            if (pend) {
+                if (ltsv_parse_ts(p, ts_a, ts_b, r.ts)) have_ts = true;
+                else { status = FG_EL_TS; err_pos = ts_part; }
             }
         }
     }
