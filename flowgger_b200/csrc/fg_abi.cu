@@ -67,6 +67,7 @@ struct ErrorTableInit {
         t[FG_EG_SEV_HIGH] = "Invalid severity level (too high)";                  // :85
         t[FG_EG_SD_TYPE] = "Invalid value type in structured data";               // :97
         t[FG_EG_MISSING_HOST] = "Missing hostname";                               // :110
+        t[FG_ES_INVALID_UTF8] = "Invalid UTF-8 input";                            // splitter/line_splitter.rs:23
     }
 } g_error_table_init;
 
@@ -95,6 +96,12 @@ struct fg_ctx {
     unsigned long long* d_tmp_val = nullptr;
     uint8_t* d_tmp_meta = nullptr;
     size_t tmp_cap = 0;
+    // split mode (fg_split_decode)
+    uint32_t* d_seg = nullptr;
+    int32_t* d_n_lines = nullptr;
+    uint8_t* d_invalid = nullptr;
+    int32_t* h_offsets = nullptr;
+    int32_t* h_n_lines = nullptr;
     size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
@@ -231,6 +238,8 @@ void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
     P.tmp_name = c->d_tmp_name;
     P.tmp_val = c->d_tmp_val;
     P.tmp_meta = c->d_tmp_meta;
+    P.line_invalid = nullptr;
+    P.strip_eol = 0;
     P.entry_counter = c->d_counter;
     P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
     P.ltsv = c->ltsv;
@@ -453,6 +462,11 @@ void fg_destroy(fg_ctx* c) {
     if (c->d_rows) cudaFree(c->d_rows);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_flush) cudaFree(c->d_flush);
+    if (c->d_seg) cudaFree(c->d_seg);
+    if (c->d_n_lines) cudaFree(c->d_n_lines);
+    if (c->d_invalid) cudaFree(c->d_invalid);
+    if (c->h_offsets) cudaFreeHost(c->h_offsets);
+    if (c->h_n_lines) cudaFreeHost(c->h_n_lines);
     if (c->d_tmp_name) cudaFree(c->d_tmp_name);
     if (c->d_tmp_val) cudaFree(c->d_tmp_val);
     if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
@@ -549,6 +563,74 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
         return FG_OK;
     }
     return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+}
+
+int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
+    if (!c || !out) return FG_E_ARG;
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if (nbytes < 0 || (nbytes > 0 && !stream)) return fail(c, FG_E_ARG, "null input");
+    if ((size_t)nbytes > c->max_bytes) return fail(c, FG_E_CAPACITY, "stream has more bytes than max_batch_bytes");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (!c->d_seg) {
+        FG_CUDA(c, cudaMalloc(&c->d_seg, sizeof(uint32_t) * ((size_t)fg::split_segments((long long)c->max_bytes) + 16)));
+        FG_CUDA(c, cudaMalloc(&c->d_n_lines, 256));
+        FG_CUDA(c, cudaMalloc(&c->d_invalid, (size_t)c->max_lines + 64));
+        FG_CUDA(c, cudaHostAlloc(&c->h_offsets, sizeof(int32_t) * ((size_t)c->max_lines + 1), cudaHostAllocDefault));
+        FG_CUDA(c, cudaHostAlloc(&c->h_n_lines, 64, cudaHostAllocDefault));
+    }
+    memset(out, 0, sizeof *out);
+    // 1. raw stream -> HBM (zero tail so that whole-vector loads past the end see no newline)
+    int bounce_ix = 0;
+    if (int rc = h2d(c, c->d_bytes, stream, (size_t)nbytes, nbytes > 0 && is_pinned(stream), bounce_ix)) return rc;
+    FG_CUDA(c, cudaMemsetAsync(c->d_bytes + nbytes, 0, 64, c->s_h2d));
+    FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_h2d));
+    FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_a, 0));
+    // 2. framing + UTF-8 validation on device
+    FG_CUDA(c, cudaMemsetAsync(c->d_invalid, 0, (size_t)c->max_lines, c->s_comp));
+    FG_CUDA(c, fg::launch_split(c->d_bytes, (long long)nbytes, c->d_seg, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, c->s_comp));
+    c->launches += 4;
+    FG_CUDA(c, cudaMemcpyAsync(c->h_n_lines, c->d_n_lines, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+    const int32_t n = *c->h_n_lines;
+    if (n < 0) return fail(c, FG_E_CAPACITY, "stream has more lines than max_batch_lines");
+    // 3. parse (terminators stripped and invalid lines skipped inside the kernel)
+    uint32_t total = 0;
+    float kms = 0.f;
+    const int tile = pick_tile(c, (size_t)nbytes, n);
+    for (int attempt = 0; attempt < 2 && n > 0; ++attempt) {
+        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        fg::ParseParams P;
+        fill_params(c, P, 0, n, tile);
+        P.line_invalid = c->d_invalid;
+        P.strip_eol = 1;
+        FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
+        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
+        ++c->launches;
+        FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
+        FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+        FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+        if ((size_t)total > c->entry_cap) {
+            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+            total = 0;
+            continue;
+        }
+        FG_CUDA(c, cudaEventElapsedTime(&kms, c->ev_a, c->ev_b));
+        break;
+    }
+    // 4. results + the line offsets back to the host
+    if (n > 0) {
+        if (int rc = copy_rows_d2h(c, fmt, 0, n, c->s_d2h)) return rc;
+        if (int rc = copy_entries_d2h(c, 0, total, c->s_d2h)) return rc;
+    }
+    FG_CUDA(c, cudaMemcpyAsync(c->h_offsets, c->d_offsets, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->s_d2h));
+    FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+    fill_out(c, fmt, n, total, out);
+    out->line_offsets = c->h_offsets;
+    out->kernel_ms = kms;
+    out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return FG_OK;
 }
 
 int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {

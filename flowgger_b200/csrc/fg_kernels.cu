@@ -179,11 +179,29 @@ __global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(cons
             parity ^= 1u;
         }
         const bool active = tid < r;
-        const int len = active ? o1 - o0 : 0;  // idle lanes run the lock-step phases on an empty line
+        int len = active ? o1 - o0 : 0;  // idle lanes run the lock-step phases on an empty line
+        bool bad_utf8 = false;
+        if (P.strip_eol && len > 0) {
+            // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
+            const uint8_t* lp = direct ? P.bytes + o0 : tile + (o0 - base);
+            if (lp[len - 1] == '\n') {
+                --len;
+                if (len > 0 && lp[len - 1] == '\r') --len;
+            }
+            if (P.line_invalid != nullptr && P.line_invalid[i]) {
+                bad_utf8 = true;
+                len = 0;
+            }
+        }
         LineResult res;
         const int lidx = P.line0 + i;  // index of the line inside the batch (unique scratch slot)
         if (!direct) Format<FMT>::parse(tile + (o0 - base), len, o0, lidx, active, true, fsh, res, tmp, P);
         else Format<FMT>::parse(P.bytes + o0, len, o0, lidx, active, false, fsh, res, tmp, P);
+        if (bad_utf8) {
+            res.status = FG_ES_INVALID_UTF8;
+            res.n_entries = 0;
+            res.full_o = 0;
+        }
         const uint32_t my_n = (active && res.status == FG_ST_OK) ? res.n_entries : 0u;
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);

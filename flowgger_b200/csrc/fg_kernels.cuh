@@ -41,6 +41,10 @@ struct ParseParams {
     int2* tmp_name;
     unsigned long long* tmp_val;
     uint8_t* tmp_meta;
+    // split mode (fg_split_decode): every line still carries its "\n" / "\r\n" terminator, and lines flagged invalid
+    // by the UTF-8 pass are not parsed
+    const uint8_t* line_invalid;  // [n] or nullptr
+    int32_t strip_eol;
     uint32_t* entry_counter;  // running total (atomic bump, one add per CTA round)
     uint32_t entry_cap;
     LtsvDeviceConfig ltsv;
@@ -52,5 +56,10 @@ constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (ti
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes);
 const char* kernel_build_info();
+
+// device-side line framing + UTF-8 validation (fg_split.cu)
+cudaError_t launch_split(const uint8_t* d_bytes, long long nbytes, uint32_t* d_seg, int32_t* d_offsets, int32_t* d_n_lines,
+                         int max_lines, uint8_t* d_invalid, cudaStream_t stream);
+int split_segments(long long nbytes);
 
 }  // namespace fg

@@ -51,5 +51,7 @@ enum FgStatus : uint32_t {
     FG_EG_SEV_HIGH = 73,
     FG_EG_SD_TYPE = 74,
     FG_EG_MISSING_HOST = 75,
-    FG_ST_COUNT = 76
+    // framing (splitter/line_splitter.rs:22-25): not a decoder error; the line is skipped with this stderr text
+    FG_ES_INVALID_UTF8 = 76,
+    FG_ST_COUNT = 77
 };

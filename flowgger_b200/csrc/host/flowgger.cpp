@@ -234,13 +234,33 @@ static std::string_view span_sv(const uint8_t* bytes, fg_span s) {
 
 DecodeResult CudaBatchDecoder::materialize(const fg_batch_out& out, const uint8_t* bytes, const int32_t* offsets,
                                            int32_t i, std::vector<std::string>* side_effects) const {
+    return materialize_line(out, bytes, offsets[i], offsets[i + 1], i, side_effects);
+}
+
+void CudaBatchDecoder::split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
+    const int rc = fg_split_decode(ctx_, fmt_, stream, nbytes, out);
+    if (rc != FG_OK) throw std::runtime_error(std::string("fg_split_decode: ") + fg_last_error(ctx_));
+}
+
+// extent of line i of a split-mode result without its "\n" / "\r\n" terminator (BufRead::lines)
+static void split_extent(const fg_batch_out& out, const uint8_t* stream, int32_t i, int32_t& lo, int32_t& hi) {
+    lo = out.line_offsets[i];
+    hi = out.line_offsets[i + 1];
+    if (hi > lo && stream[hi - 1] == '\n') {
+        --hi;
+        if (hi > lo && stream[hi - 1] == '\r') --hi;
+    }
+}
+
+DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t line_hi,
+                                                int32_t i, std::vector<std::string>* side_effects) const {
     DecodeResult r;
     const uint32_t meta = out.meta[i];
     const uint32_t status = FG_META_STATUS(meta), flags = FG_META_FLAGS(meta);
     if (side_effects && (flags & FG_FLAG_MISSING_VALUE)) {
         // println! at ltsv_decoder.rs:99 for every tab-separated part without ':' that the decode loop
         // reached: all parts when Ok / post-loop error, else the parts before the failing one.
-        const int32_t lo = offsets[i], hi = offsets[i + 1];
+        const int32_t lo = line_lo, hi = line_hi;
         const int32_t stop = status ? out.full_msg[i].off : hi + 1;
         int32_t a = lo;
         for (;;) {
@@ -652,6 +672,43 @@ double fgh_materialize_bench(void* d, const fg_batch_out* out, const uint8_t* by
     for (auto& x : th) x.join();
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
+}
+
+// fg_split_decode + canonical dumps of every line (split-mode twin of fgh_dump_out); also returns the line offsets
+int fgh_split_dump(void* d, const uint8_t* stream, int64_t nbytes, uint8_t** out_buf, int64_t** out_offsets, int32_t** out_line_offsets,
+                   int32_t* out_n, float* kernel_ms, char* errbuf, int errlen) {
+    auto* dec = (CudaBatchDecoder*)d;
+    try {
+        fg_batch_out out;
+        dec->split_decode(stream, nbytes, &out);
+        const int32_t n = out.n;
+        std::string all;
+        int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
+        int32_t* lo_out = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+        offs[0] = 0;
+        std::vector<std::string> fx;
+        for (int32_t i = 0; i < n; ++i) {
+            int32_t lo, hi;
+            split_extent(out, stream, i, lo, hi);
+            fx.clear();
+            DecodeResult r = dec->materialize_line(out, stream, lo, hi, i, &fx);
+            const bool now = r.ok() && (FG_META_FLAGS(out.meta[i]) & FG_FLAG_TS_MISSING);
+            dump_result(r, now, fx, all);
+            offs[i + 1] = (int64_t)all.size();
+        }
+        memcpy(lo_out, out.line_offsets, sizeof(int32_t) * ((size_t)n + 1));
+        uint8_t* buf = (uint8_t*)malloc(all.size() ? all.size() : 1);
+        memcpy(buf, all.data(), all.size());
+        *out_buf = buf;
+        *out_offsets = offs;
+        *out_line_offsets = lo_out;
+        *out_n = n;
+        if (kernel_ms) *kernel_ms = out.kernel_ms;
+        return 0;
+    } catch (const std::exception& e) {
+        if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());
+        return -1;
+    }
 }
 
 int fgh_is_valid_utf8(const uint8_t* p, int64_t n) { return is_valid_utf8(p, (size_t)n) ? 1 : 0; }

@@ -97,6 +97,11 @@ class CudaBatchDecoder {
     // `side_effects`, if given, receives the println! lines of ltsv_decoder.rs:99.
     DecodeResult materialize(const fg_batch_out& out, const uint8_t* bytes, const int32_t* offsets, int32_t i,
                              std::vector<std::string>* side_effects = nullptr) const;
+    // same, for a line whose extent [line_lo, line_hi) is given explicitly (split mode: terminator already removed)
+    DecodeResult materialize_line(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t line_hi, int32_t i,
+                                  std::vector<std::string>* side_effects = nullptr) const;
+    // framing + UTF-8 validation + decode of a raw byte stream on the device (fg_split_decode)
+    void split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
 
    private:
     fg_format fmt_;

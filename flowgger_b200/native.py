@@ -28,6 +28,7 @@ class FgBatchOut(C.Structure):
         ("msgid", C.POINTER(FgSpan)), ("msg", C.POINTER(FgSpan)), ("full_msg", C.POINTER(FgSpan)),
         ("sd", C.POINTER(FgSpan)),
         ("entry_name", C.POINTER(FgSpan)), ("entry_val", C.POINTER(C.c_uint64)), ("entry_meta", C.POINTER(C.c_uint8)),
+        ("line_offsets", C.POINTER(C.c_int32)),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float),
     ]
 
@@ -91,6 +92,8 @@ def load_host() -> C.CDLL:
         L.fgh_materialize_bench.restype = C.c_double
         L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
         L.fgh_is_valid_utf8.argtypes = [C.c_void_p, C.c_int64]
+        L.fgh_split_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_char_p, C.c_int]
         L.fgh_shard_by_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
         L.fgh_multi_decode_dump.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
@@ -274,6 +277,25 @@ class BatchDecoder:
             self.H.fgh_free(pb)
             self.H.fgh_free(po)
         return buf, offs
+
+    def split_dump(self, stream: np.ndarray) -> tuple[bytes, np.ndarray, np.ndarray, float]:
+        """fg_split_decode on a raw byte stream: (canonical dumps, dump offsets, line offsets int32[n+1], kernel ms)."""
+        assert stream.dtype == np.uint8
+        pb, po, pl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, ms = C.c_int32(), C.c_float()
+        err = C.create_string_buffer(512)
+        rc = self.H.fgh_split_dump(self._h, _ptr(stream), len(stream), C.byref(pb), C.byref(po), C.byref(pl), C.byref(n), C.byref(ms), err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        try:
+            offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+            lines = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_int32)), shape=(n.value + 1,)).copy()
+            buf = C.string_at(pb, int(offs[-1]))
+        finally:
+            self.H.fgh_free(pb)
+            self.H.fgh_free(po)
+            self.H.fgh_free(pl)
+        return buf, offs, lines, ms.value
 
     def materialize_seconds(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 1) -> float:
         return float(self.H.fgh_materialize_bench(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads))

@@ -98,6 +98,8 @@ typedef struct fg_batch_out {
     const fg_span* entry_name;  /* [n_entries] */
     const uint64_t* entry_val;  /* string: off | len<<32 ; bool/i64/u64/f64: the 8 value bytes ; header: #pairs */
     const uint8_t* entry_meta;  /* FG_EM_* */
+    const int32_t* line_offsets; /* fg_split_decode only: [n+1] line starts into the stream (each line still
+                                    carries its "\n" / "\r\n" terminator); NULL otherwise */
     /* timings of the call, milliseconds */
     float kernel_ms; /* sum of parse-kernel time (CUDA events on the launch stream) */
     float total_ms;  /* H2D + kernels + D2H wall time */
@@ -127,6 +129,13 @@ void fg_host_free(fg_ctx* ctx, void* p);
  * line terminator (what LineSplitter hands to decode, line_splitter.rs:17-50). */
 int fg_decode_batch(fg_ctx* ctx, fg_format fmt, const uint8_t* bytes, const int32_t* offsets, int32_t n,
                     fg_batch_out* out);
+
+/* Framing + decoding in one call: `stream` is a raw byte stream as LineSplitter::run reads it
+ * (splitter/line_splitter.rs:17-25).  The device finds the '\n' terminators (BufRead::lines: the '\n' and one
+ * preceding '\r' are dropped, an unterminated last line is still a line), validates every line as UTF-8 (an invalid
+ * line gets status fg_error_string() == "Invalid UTF-8 input" and is not decoded) and decodes the rest.
+ * Spans index `stream`; out->line_offsets locates the lines. */
+int fg_split_decode(fg_ctx* ctx, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
 
 /* Device-resident variant used for roofline measurement: fg_upload stages a
  * batch in HBM once; fg_parse_resident runs only the parse kernel(s) over it
