@@ -303,6 +303,7 @@ def main() -> None:
     ap.add_argument("--lines", type=int, default=0, help="lines per GPU (default: the BASELINE.json config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", action="store_true", help="also time fg_split_decode (device-side framing + UTF-8 validation, N1)")
     ap.add_argument("--ltsv-typed", action="store_true", help="LTSV with the 4-entry typed schema + suffixes (C4, second run)")
     args = ap.parse_args()
     if args.format == "mixed":
@@ -415,6 +416,31 @@ def main() -> None:
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_lines / (e2e_wall / args.e2e_steps)
 
+    # ---- optional: raw newline-terminated stream, framing + UTF-8 validation on the device (N1) -------
+    split = None
+    if args.split:
+        sdata, soffs = fb.generate(fmt, SEEDS[fmt_name], n, first_index=rank * n, mean_len=GEN_MEAN[fmt_name], bad_frac=0.005,
+                                   nthreads=min(os.cpu_count() or 8, 32), terminated=True)
+        sdec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=len(sdata) + (1 << 20), max_batch_lines=n + 64,
+                               **ltsv_kwargs(fmt_name, args.ltsv_typed))
+        hs = sdec.host_alloc(len(sdata))
+        hs[:] = sdata
+        del sdata
+        sdec.split_decode(hs)
+        barrier()
+        t0 = time.perf_counter()
+        sk = 0.0
+        for _ in range(args.e2e_steps):
+            r = sdec.split_decode(hs)
+            sk += sdec.last_split_ms()
+        barrier()
+        sw = max_over_ranks(time.perf_counter() - t0)
+        split = {"value": total_lines / (sw / args.e2e_steps), "unit": "lines/s", "stream_bytes_per_gpu": int(len(hs)),
+                 "split_kernels_ms": sk / args.e2e_steps,
+                 "split_kernels_gb_per_s": len(hs) / 1e9 / (sk / args.e2e_steps / 1e3),
+                 "api": "fg_split_decode (pinned raw stream in, columnar results + line offsets out; not yet chunk-pipelined)"}
+        sdec.close()
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -464,6 +490,8 @@ def main() -> None:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if split is not None:
+            line["split_e2e"] = split
         print(json.dumps(line), flush=True)
     dec.close()
     if dist is not None:

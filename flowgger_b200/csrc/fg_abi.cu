@@ -102,6 +102,8 @@ struct fg_ctx {
     uint8_t* d_invalid = nullptr;
     int32_t* h_offsets = nullptr;
     int32_t* h_n_lines = nullptr;
+    float last_split_ms = 0.f;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
     size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
@@ -467,6 +469,8 @@ void fg_destroy(fg_ctx* c) {
     if (c->d_invalid) cudaFree(c->d_invalid);
     if (c->h_offsets) cudaFreeHost(c->h_offsets);
     if (c->h_n_lines) cudaFreeHost(c->h_n_lines);
+    if (c->ev_s0) cudaEventDestroy(c->ev_s0);
+    if (c->ev_s1) cudaEventDestroy(c->ev_s1);
     if (c->d_tmp_name) cudaFree(c->d_tmp_name);
     if (c->d_tmp_val) cudaFree(c->d_tmp_val);
     if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
@@ -579,6 +583,8 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
         FG_CUDA(c, cudaMalloc(&c->d_invalid, (size_t)c->max_lines + 64));
         FG_CUDA(c, cudaHostAlloc(&c->h_offsets, sizeof(int32_t) * ((size_t)c->max_lines + 1), cudaHostAllocDefault));
         FG_CUDA(c, cudaHostAlloc(&c->h_n_lines, 64, cudaHostAllocDefault));
+        FG_CUDA(c, cudaEventCreate(&c->ev_s0));
+        FG_CUDA(c, cudaEventCreate(&c->ev_s1));
     }
     memset(out, 0, sizeof *out);
     // 1. raw stream -> HBM (zero tail so that whole-vector loads past the end see no newline)
@@ -589,10 +595,13 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
     FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_a, 0));
     // 2. framing + UTF-8 validation on device
     FG_CUDA(c, cudaMemsetAsync(c->d_invalid, 0, (size_t)c->max_lines, c->s_comp));
+    FG_CUDA(c, cudaEventRecord(c->ev_s0, c->s_comp));
     FG_CUDA(c, fg::launch_split(c->d_bytes, (long long)nbytes, c->d_seg, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, c->s_comp));
     c->launches += 4;
+    FG_CUDA(c, cudaEventRecord(c->ev_s1, c->s_comp));
     FG_CUDA(c, cudaMemcpyAsync(c->h_n_lines, c->d_n_lines, 4, cudaMemcpyDeviceToHost, c->s_comp));
     FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+    FG_CUDA(c, cudaEventElapsedTime(&c->last_split_ms, c->ev_s0, c->ev_s1));
     const int32_t n = *c->h_n_lines;
     if (n < 0) return fail(c, FG_E_CAPACITY, "stream has more lines than max_batch_lines");
     // 3. parse (terminators stripped and invalid lines skipped inside the kernel)
@@ -709,5 +718,6 @@ uint32_t fg_error_count(void) { return FG_ST_COUNT; }
 
 const char* fg_build_info(void) { return fg::kernel_build_info(); }
 int64_t fg_kernel_launches(const fg_ctx* c) { return c ? c->launches : 0; }
+float fg_last_split_ms(const fg_ctx* c) { return c ? c->last_split_ms : 0.f; }
 
 }  // extern "C"

@@ -399,6 +399,9 @@ extern "C" {
 void fgen_free(void* p) { free(p); }
 
 // kind 0 = RFC5424 (C2).  Returns malloc'd bytes + int32 offsets[n+1]; fails (-1) past 2 GiB.
+static int g_terminate = 0;  // 1: every line is followed by '\n' (raw stream for fg_split_decode); offsets then include it
+void fgen_set_terminator(int on) { g_terminate = on; }
+
 int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, double mean_len, double bad_frac,
                   int nthreads, uint8_t** out_bytes, int32_t** out_offsets, int64_t* out_total) {
     if (nthreads < 1) nthreads = 1;
@@ -417,6 +420,10 @@ int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, doubl
                     case 2: gen_gelf(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     case 1: gen_ltsv(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     default: gen_rfc5424(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
+                }
+                if (g_terminate) {
+                    for (size_t q = before; q < o.size(); ++q) if (o[q] == '\n') o[q] = ' ';  // a raw LF would be a line break
+                    o.push_back('\n');
                 }
                 lens[(size_t)t].push_back((int32_t)(o.size() - before));
             }

@@ -69,6 +69,9 @@ def load_cuda() -> C.CDLL:
         L.fg_flush_l2.argtypes = [C.c_void_p]
         L.fg_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.fg_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.fg_split_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(FgBatchOut)]
+        L.fg_last_split_ms.restype = C.c_float
+        L.fg_last_split_ms.argtypes = [C.c_void_p]
         L.fg_error_count.restype = C.c_uint32
         _cuda = L
     return _cuda
@@ -109,6 +112,7 @@ def load_gen() -> C.CDLL:
         L.fgen_generate.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int,
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.fgen_free.argtypes = [C.c_void_p]
+        L.fgen_set_terminator.argtypes = [C.c_int]
         _gen = L
     return _gen
 
@@ -123,12 +127,13 @@ def error_string(fmt: int, status: int) -> str | None:
 
 
 def generate(fmt: int, seed: int, n: int, *, first_index: int = 0, mean_len: float = 0.0, bad_frac: float = 0.005,
-             nthreads: int = 8) -> tuple[np.ndarray, np.ndarray]:
+             nthreads: int = 8, terminated: bool = False) -> tuple[np.ndarray, np.ndarray]:
     """Synthetic batch (SURVEY.md §8(d) shapes): returns (bytes uint8[total], offsets int32[n+1])."""
     L = load_gen()
     if mean_len <= 0:
         mean_len = {FMT_RFC5424: 180.0, FMT_GELF: 512.0, FMT_LTSV: 420.0}[fmt]
     pb, po, tot = C.c_void_p(), C.c_void_p(), C.c_int64()
+    L.fgen_set_terminator(1 if terminated else 0)  # terminated: every line ends in '\n' (raw stream for split_decode)
     rc = L.fgen_generate(fmt, seed, first_index, n, mean_len, bad_frac, nthreads, C.byref(pb), C.byref(po), C.byref(tot))
     if rc != 0:
         raise ValueError("generated batch exceeds the int32 offset range; generate fewer lines per batch")
@@ -245,6 +250,17 @@ class BatchDecoder:
         self._keep = (data, offsets)
         self._check(self.L.fg_decode_batch(self.ctx, self.fmt, _ptr(data), _ptr(offsets), n, C.byref(out)), "fg_decode_batch")
         return BatchResult(out, self.fmt)
+
+    def split_decode(self, stream: np.ndarray) -> BatchResult:
+        """Framing + UTF-8 validation + decode of a raw newline-terminated byte stream, all on the device."""
+        assert stream.dtype == np.uint8
+        out = FgBatchOut()
+        self._keep = (stream,)
+        self._check(self.L.fg_split_decode(self.ctx, self.fmt, _ptr(stream), len(stream), C.byref(out)), "fg_split_decode")
+        return BatchResult(out, self.fmt)
+
+    def last_split_ms(self) -> float:
+        return float(self.L.fg_last_split_ms(self.ctx))
 
     def upload(self, data: np.ndarray, offsets: np.ndarray) -> None:
         assert data.dtype == np.uint8 and offsets.dtype == np.int32

@@ -153,6 +153,7 @@ uint32_t fg_error_count(void);
 /* build/launch facts for tests and bench */
 const char* fg_build_info(void);          /* arch, compiler, kernel list */
 int64_t fg_kernel_launches(const fg_ctx* ctx); /* parse kernels launched by this ctx so far */
+float fg_last_split_ms(const fg_ctx* ctx);     /* device time of the framing + UTF-8 kernels of the last fg_split_decode */
 
 #ifdef __cplusplus
 }
