@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -209,8 +210,10 @@ int ensure_scratch(fg_ctx* c, int fmt) {
 
 // shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles
 // whatever does not fit in extra rounds
-int pick_tile(const fg_ctx* c, size_t total_bytes, int n) {
+int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt = 0) {
     double mean = n > 0 ? (double)total_bytes / n : 0.0;
+    // long-line formats: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
+    if (fmt != FG_FMT_RFC5424 && mean > 256.0 && getenv("FG_FORCE_STAGE") == nullptr) return 0;
     long t = (long)(mean * fg::kLinesPerCta * 1.10) + 1024;
     t = (t + 1023) & ~1023L;
     t = std::max(t, 8L * 1024);
@@ -521,7 +524,7 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
     const int C = c->chunk_lines;
     const int chunks = (n + C - 1) / C;
     if (int rc = ensure_events(c, chunks)) return rc;
-    const int tile = pick_tile(c, (size_t)(offsets[n] - offsets[0]), n);
+    const int tile = pick_tile(c, (size_t)(offsets[n] - offsets[0]), n, (int)fmt);
     for (int attempt = 0; attempt < 2; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
         int bounce_ix = 0;
@@ -607,7 +610,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
     // 3. parse (terminators stripped and invalid lines skipped inside the kernel)
     uint32_t total = 0;
     float kms = 0.f;
-    const int tile = pick_tile(c, (size_t)nbytes, n);
+    const int tile = pick_tile(c, (size_t)nbytes, n, (int)fmt);
     for (int attempt = 0; attempt < 2 && n > 0; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
         fg::ParseParams P;
@@ -667,7 +670,7 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
         fg::ParseParams P;
-        fill_params(c, P, 0, c->res_n, c->res_tile);
+        fill_params(c, P, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt));
         FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
         FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
         ++c->launches;

@@ -294,6 +294,22 @@ __device__ __noinline__ int key_iter_next(KeyIter& k) {  // -1 at the end
         default: return (int)x;  // '"' '\\' '/'
     }
 }
+// String Ord when neither key holds an escape: plain byte-wise compare of the raw spans (the common case)
+FG_DEV int raw_key_cmp(bytes_t p, int a0, int a1, int b0, int b1) {
+    const int la = a1 - a0, lb = b1 - b0, n = la < lb ? la : lb;
+    for (int k = 0; k < n; ++k) {
+        const int ca = p[a0 + k], cb = p[b0 + k];
+        if (ca != cb) return ca < cb ? -1 : 1;
+    }
+    return la == lb ? 0 : (la < lb ? -1 : 1);
+}
+FG_DEV bool raw_str_is(bytes_t p, int a0, int a1, const char* lit, int n) {
+    if (a1 - a0 != n) return false;
+    for (int k = 0; k < n; ++k)
+        if (p[a0 + k] != (uint8_t)lit[k]) return false;
+    return true;
+}
+
 // String Ord on the unescaped bytes
 __device__ __noinline__ int json_key_cmp(bytes_t p, int a0, int a1, int b0, int b1, bool mode2) {
     KeyIter x, y;
@@ -478,34 +494,40 @@ __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mod
     // reserved keys contain no '_' and differ in their first byte: skip the literal compares for ordinary `_extra` keys
     const uint32_t k0 = (ke > ks) ? p[ks] : 0u;
     const bool maybe = k0 == 't' || k0 == 'h' || k0 == 's' || k0 == 'f' || k0 == 'v' || k0 == 'l' || k0 == '\\';
-    if (maybe && json_str_is(p, ks, ke, mode2, "timestamp", 9)) {  // as_f64 :53
+    const bool kesc = (meta & 0x40u) != 0, vesc = (meta & 0x08u) != 0;
+    auto key_is = [&](const char* lit, int n) { return kesc ? json_str_is(p, ks, ke, mode2, lit, n) : raw_str_is(p, ks, ke, lit, n); };
+    auto val_is = [&](const char* lit, int n) { return vesc ? json_str_is(p, vs, vs + vl, mode2, lit, n) : raw_str_is(p, vs, vs + vl, lit, n); };
+    if (maybe && key_is("timestamp", 9)) {  // as_f64 :53
         if (tag == JT_F64) r.ts = __longlong_as_double((long long)val);
         else if (tag == JT_U64) r.ts = __ull2double_rn(val);
         else if (tag == JT_I64) r.ts = __ll2double_rn((long long)val);
         else g.status = FG_EG_TS;
         g.have_ts = true;
-    } else if (maybe && json_str_is(p, ks, ke, mode2, "host", 4)) {
+    } else if (maybe && key_is("host", 4)) {
         if (tag != JT_STRING) g.status = FG_EG_HOST;
         else { r.host_o = vs; r.host_l = vl; if (meta & 0x08u) g.flags |= 0x04u; }
-    } else if (maybe && json_str_is(p, ks, ke, mode2, "short_message", 13)) {
+    } else if (maybe && key_is("short_message", 13)) {
         if (tag != JT_STRING) g.status = FG_EG_SHORT;
         else { r.msg_o = vs; r.msg_l = vl; if (meta & 0x08u) g.flags |= 0x08u; }
-    } else if (maybe && json_str_is(p, ks, ke, mode2, "full_message", 12)) {
+    } else if (maybe && key_is("full_message", 12)) {
         if (tag != JT_STRING) g.status = FG_EG_FULL;
         else { r.full_o = vs; r.full_l = vl; if (meta & 0x08u) g.flags |= 0x10u; }
-    } else if (maybe && json_str_is(p, ks, ke, mode2, "version", 7)) {
+    } else if (maybe && key_is("version", 7)) {
         if (tag != JT_STRING) g.status = FG_EG_VERSION_T;
-        else if (!json_str_is(p, vs, vs + vl, mode2, "1.0", 3) && !json_str_is(p, vs, vs + vl, mode2, "1.1", 3)) g.status = FG_EG_VERSION;
-    } else if (maybe && json_str_is(p, ks, ke, mode2, "level", 5)) {  // as_u64 :83
+        else if (!val_is("1.0", 3) && !val_is("1.1", 3)) g.status = FG_EG_VERSION;
+    } else if (maybe && key_is("level", 5)) {  // as_u64 :83
         if (tag != JT_U64) g.status = FG_EG_SEV;
         else if (val > 7ull) g.status = FG_EG_SEV_HIGH;
         else r.severity = (uint32_t)val;
     } else {
         if (tag == JT_CONTAINER) g.status = FG_EG_SD_TYPE;  // :97
         else {
-            KeyIter it;
-            key_iter_init(it, p, ks, ke, mode2);
-            const bool under = key_iter_next(it) == '_';
+            bool under = k0 == '_';
+            if (kesc) {
+                KeyIter it;
+                key_iter_init(it, p, ks, ke, mode2);
+                under = key_iter_next(it) == '_';
+            }
             const uint32_t e = sbase + g.kept;
             sink.name[e] = name;
             sink.val[e] = val;
@@ -549,9 +571,13 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
             for (uint32_t a = 0; a < m; ++a) {
                 const int2 kn = M.name[a];
                 int b = (int)a - 1;
+                const bool kn_esc = (M.meta[a] & 0x40u) != 0;
                 while (b >= 0) {
                     const int2 on = M.name[ord[b]];
-                    if (json_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y, mode2) <= 0) break;
+                    const int cmp = (kn_esc || (M.meta[ord[b]] & 0x40u))
+                                        ? json_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y, mode2)
+                                        : raw_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y);
+                    if (cmp <= 0) break;
                     ord[b + 1] = ord[b];
                     --b;
                 }
@@ -562,9 +588,12 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                 uint32_t ge = gi + 1;  // group of equal keys [gi, ge): the last inserted value wins
                 const int2 gn = M.name[ord[gi]];
                 const int ks = gn.x - line_off, ke = ks + gn.y;
+                const bool g_esc = (M.meta[ord[gi]] & 0x40u) != 0;
                 while (ge < m) {
                     const int2 nn = M.name[ord[ge]];
-                    if (json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2) != 0) break;
+                    const int cmp = (g_esc || (M.meta[ord[ge]] & 0x40u)) ? json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2)
+                                                                        : raw_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y);
+                    if (cmp != 0) break;
                     ++ge;
                 }
                 const uint32_t w = ord[ge - 1];

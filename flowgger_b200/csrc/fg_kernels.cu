@@ -137,7 +137,10 @@ struct Format<2> {  // GELF
     }
 };
 
-template <int FMT>
+// STAGE = true : the CTA's byte span is bulk-copied into shared memory first (short lines: RFC5424).
+// STAGE = false: threads read their lines straight from global memory through L1 (long lines: at ~500 B/line the tile
+//                would cap an SM at 12 resident warps; without it the register file is the limit).
+template <int FMT, bool STAGE>
 __global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
@@ -162,10 +165,12 @@ __global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(cons
         const int o1 = __ldg(P.offsets + min(i + 1, last));
         const int ocur = __ldg(P.offsets + cur);
         const int base = ocur & ~15;
-        const bool fits = (i < last) && (o1 - base <= P.tile_bytes);
+        const bool fits = (i < last) && (!STAGE || o1 - base <= P.tile_bytes);
         int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
-        const bool direct = (r == 0);       // first pending line alone exceeds the tile
-        if (direct) {
+        const bool direct = !STAGE || (r == 0);  // r == 0: the first pending line alone exceeds the tile
+        if (!STAGE) {
+            // every pending line of the CTA is parsed from global memory in this single round
+        } else if (direct) {
             r = 1;
         } else {
             if (tid == 0) {
@@ -253,11 +258,11 @@ cudaError_t configure_kernels(int max_tile_bytes) {
         cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);
         if (e1 != cudaSuccess) return e1;
     }
-    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(parse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    e = cudaFuncSetAttribute(parse_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(parse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    e = cudaFuncSetAttribute(parse_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     return e;
 }
 
@@ -265,9 +270,15 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
     switch (fmt) {
-        case 0: parse_kernel<0><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
-        case 1: parse_kernel<1><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
-        case 2: parse_kernel<2><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        case 0: parse_kernel<0, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        case 1:
+            if (p.tile_bytes > 0) parse_kernel<1, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
+            else parse_kernel<1, false><<<grid, kLinesPerCta, 0, stream>>>(p);
+            break;
+        case 2:
+            if (p.tile_bytes > 0) parse_kernel<2, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
+            else parse_kernel<2, false><<<grid, kLinesPerCta, 0, stream>>>(p);
+            break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
