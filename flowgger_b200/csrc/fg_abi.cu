@@ -692,6 +692,35 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
 }
 
+// K back-to-back passes over the resident batch with ONE host synchronisation at the end (what bench.py times):
+// total_ms = CUDA-event time from before the first launch to after the last one.
+int fg_parse_resident_n(fg_ctx* c, fg_format fmt, int32_t k, float* total_ms) {
+    if (!c || k < 1) return FG_E_ARG;
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
+    // the side table must already be large enough (one fg_parse_resident warm-up regrows it): checked after the loop
+    fg::ParseParams P;
+    fill_params(c, P, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt));
+    FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
+    for (int32_t it = 0; it < k; ++it) {
+        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
+        ++c->launches;
+    }
+    FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
+    uint32_t total = 0;
+    FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+    if ((size_t)total > c->entry_cap) return fail(c, FG_E_CAPACITY, "side table too small: call fg_parse_resident once before fg_parse_resident_n");
+    float ms = 0.f;
+    FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+    if (total_ms) *total_ms = ms;
+    c->res_fmt = (int)fmt;
+    c->res_entries = total;
+    return FG_OK;
+}
+
 int fg_download(fg_ctx* c, fg_format fmt, fg_batch_out* out) {
     if (!c || !out) return FG_E_ARG;
     if (c->res_fmt != (int)fmt) return fail(c, FG_E_ARG, "no resident parse of this format to download");

@@ -66,6 +66,7 @@ def load_cuda() -> C.CDLL:
         L.fg_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.fg_parse_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.fg_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(FgBatchOut)]
+        L.fg_parse_resident_n.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(C.c_float)]
         L.fg_flush_l2.argtypes = [C.c_void_p]
         L.fg_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.fg_host_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -269,6 +270,12 @@ class BatchDecoder:
     def parse_resident(self) -> float:
         ms = C.c_float()
         self._check(self.L.fg_parse_resident(self.ctx, self.fmt, C.byref(ms)), "fg_parse_resident")
+        return ms.value
+
+    def parse_resident_many(self, k: int) -> float:
+        """k back-to-back passes over the resident batch, one host sync; returns the CUDA-event time of all k (ms)."""
+        ms = C.c_float()
+        self._check(self.L.fg_parse_resident_n(self.ctx, self.fmt, k, C.byref(ms)), "fg_parse_resident_n")
         return ms.value
 
     def download(self) -> BatchResult:

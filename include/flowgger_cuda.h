@@ -143,6 +143,7 @@ int fg_split_decode(fg_ctx* ctx, fg_format fmt, const uint8_t* stream, int64_t n
  * resident parse. */
 int fg_upload(fg_ctx* ctx, const uint8_t* bytes, const int32_t* offsets, int32_t n);
 int fg_parse_resident(fg_ctx* ctx, fg_format fmt, float* kernel_ms);
+int fg_parse_resident_n(fg_ctx* ctx, fg_format fmt, int32_t k, float* total_ms); /* k passes, one host sync */
 int fg_download(fg_ctx* ctx, fg_format fmt, fg_batch_out* out);
 int fg_flush_l2(fg_ctx* ctx); /* writes a >L2-sized scratch buffer */
 

@@ -125,3 +125,16 @@ def test_roundtrip_property_full_msg(dec, native):
     has = m[:, 0] >= 0
     assert (m[has, 0] + m[has, 1] <= fo[has] + fl[has]).all()
     assert np.isfinite(res.ts[ok]).all() and (res.ts[ok] > 1.4e9).all() and (res.ts[ok] < 2.1e9).all()
+
+
+def test_many_resident_passes_are_idempotent(dec, oracle, native):
+    """fg_parse_resident_n (what bench.py times): K back-to-back passes leave exactly the result of one pass."""
+    data, offs = native.generate(native.FMT_RFC5424, 13, 200_000)
+    dec.upload(data, offs)
+    dec.parse_resident()
+    ms = dec.parse_resident_many(7)
+    assert ms > 0
+    res = dec.download()
+    g, go = dec.dump(res, data, offs)
+    r, ro = oracle.decode_dump(0, data, offs)
+    assert g == r and np.array_equal(go, ro)
