@@ -386,7 +386,7 @@ def main() -> None:
     b_read = nbytes + 4 * (n + 1)  # algorithmic bytes per launch: every input byte + offset read once
 
     dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nbytes + (1 << 20), max_batch_lines=n,
-                          chunk_lines=1 << 18, **ltsv_kwargs(fmt_name, args.ltsv_typed))
+                          chunk_lines=env_int("FG_CHUNK_LINES", 1 << 18), **ltsv_kwargs(fmt_name, args.ltsv_typed))
     # pinned host arenas, as a batching splitter would fill them
     h_bytes = dec.host_alloc(nbytes)
     h_offs = dec.host_alloc(offs.nbytes, dtype=np.int32)

@@ -118,7 +118,7 @@ struct fg_ctx {
     int h_counts_cap = 0;
     uint8_t* h_bounce[2] = {nullptr, nullptr};
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_h2d, ev_k0, ev_k1;
+    std::vector<cudaEvent_t> ev_h2d, ev_k0, ev_k1, ev_cnt;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // resident batch
     int res_n = 0;
@@ -275,16 +275,31 @@ void fill_out(fg_ctx* c, int fmt, int n, uint32_t n_entries, fg_batch_out* out) 
 }
 
 int copy_rows_d2h(fg_ctx* c, int fmt, int line0, int n, cudaStream_t s) {
-    for (int col = 0; col < C_COUNT; ++col) {
-        if (!col_used(fmt, col)) continue;
+    static const bool skip = getenv("FG_DEBUG_SKIP_D2H") != nullptr;  // diagnostic only (profiles/r1_notes.md, e2e)
+    if (skip || n <= 0) return FG_OK;
+    // ts and meta: one copy each; the 8-byte span columns share one pitch (8 * max_lines), so every run of consecutive
+    // used span columns goes back as ONE 2-D copy (few large D2H operations disturb the concurrent H2D stream less)
+    for (int col = C_TS; col <= C_META; ++col) {
         const size_t o = col_off(c, col) + (size_t)line0 * kColW[col];
         FG_CUDA(c, cudaMemcpyAsync(c->h_rows + o, c->d_rows + o, (size_t)n * kColW[col], cudaMemcpyDeviceToHost, s));
+    }
+    const size_t pitch = (size_t)c->max_lines * 8;
+    int col = C_HOST;
+    while (col < C_COUNT) {
+        if (!col_used(fmt, col)) { ++col; continue; }
+        int end = col;
+        while (end + 1 < C_COUNT && col_used(fmt, end + 1)) ++end;
+        const size_t o = col_off(c, col) + (size_t)line0 * 8;
+        FG_CUDA(c, cudaMemcpy2DAsync(c->h_rows + o, pitch, c->d_rows + o, pitch, (size_t)n * 8, (size_t)(end - col + 1),
+                                     cudaMemcpyDeviceToHost, s));
+        col = end + 1;
     }
     return FG_OK;
 }
 
 int copy_entries_d2h(fg_ctx* c, size_t from, size_t to, cudaStream_t s) {
-    if (to <= from) return FG_OK;
+    static const bool skip = getenv("FG_DEBUG_SKIP_D2H") != nullptr;
+    if (to <= from || skip) return FG_OK;
     const size_t k = to - from;
     FG_CUDA(c, cudaMemcpyAsync(c->h_entry_name + from, c->d_entry_name + from, k * sizeof(int2), cudaMemcpyDeviceToHost, s));
     FG_CUDA(c, cudaMemcpyAsync(c->h_entry_val + from, c->d_entry_val + from, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -324,13 +339,15 @@ int h2d(fg_ctx* c, void* dst, const void* src, size_t bytes, bool pinned, int& b
 
 int ensure_events(fg_ctx* c, int chunks) {
     while ((int)c->ev_h2d.size() < chunks) {
-        cudaEvent_t a, b, d;
+        cudaEvent_t a, b, d, e;
         FG_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         FG_CUDA(c, cudaEventCreate(&b));
         FG_CUDA(c, cudaEventCreate(&d));
+        FG_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->ev_h2d.push_back(a);
         c->ev_k0.push_back(b);
         c->ev_k1.push_back(d);
+        c->ev_cnt.push_back(e);
     }
     if (c->h_counts_cap < chunks) {
         if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -487,6 +504,7 @@ void fg_destroy(fg_ctx* c) {
     for (auto e : c->ev_h2d) cudaEventDestroy(e);
     for (auto e : c->ev_k0) cudaEventDestroy(e);
     for (auto e : c->ev_k1) cudaEventDestroy(e);
+    for (auto e : c->ev_cnt) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -543,20 +561,33 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
             ++c->launches;
             FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));
             FG_CUDA(c, cudaMemcpyAsync(c->h_counts + k, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
-            FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
-            FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_a, 0));
+            FG_CUDA(c, cudaEventRecord(c->ev_cnt[k], c->s_comp));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_cnt[k], 0));
             if (int rc = copy_rows_d2h(c, fmt, l0, l1 - l0, c->s_d2h)) return rc;
         }
-        // side table: every chunk's rows are a contiguous range of the bump allocator
-        FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+        // side table: chunk k's rows are the contiguous range [count(k-1), count(k)) of the bump allocator; each range is
+        // copied back as soon as its chunk has been parsed, while later chunks are still in flight
+        uint32_t copied = 0;
+        bool overflow = false;
+        for (int k = 0; k < chunks; ++k) {
+            FG_CUDA(c, cudaEventSynchronize(c->ev_cnt[k]));
+            const uint32_t upto = c->h_counts[k];
+            if ((size_t)upto > c->entry_cap) {
+                overflow = true;
+                continue;  // keep draining the events; the batch is redone below
+            }
+            if (!overflow) {
+                if (int rc = copy_entries_d2h(c, copied, upto, c->s_d2h)) return rc;
+                copied = upto;
+            }
+        }
         const uint32_t total = c->h_counts[chunks - 1];
-        if ((size_t)total > c->entry_cap) {
+        if (overflow) {
             // the allocator kept counting past the capacity: grow once to the exact need and redo
             FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
             if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
             continue;
         }
-        if (int rc = copy_entries_d2h(c, 0, total, c->s_d2h)) return rc;
         FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
         float kms = 0.f;
         for (int k = 0; k < chunks; ++k) {

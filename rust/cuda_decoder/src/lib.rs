@@ -121,6 +121,31 @@ impl CudaDecoder {
     }
 }
 
+impl CudaDecoder {
+    /// Framing + UTF-8 validation + decode of a raw stream on the device (`fg_split_decode`): `f(i, line, result)` in
+    /// stream order; a line that is not UTF-8 arrives as `Err("Invalid UTF-8 input")` (line_splitter.rs:22-25).
+    pub fn split_decode<F: FnMut(usize, &[u8], Result<Record, &'static str>, &[String])>(&self, stream: &[u8], mut f: F) {
+        let ctx = self.ctx.lock().unwrap();
+        let mut out: fg_batch_out = unsafe { std::mem::zeroed() };
+        let rc = unsafe { fg_split_decode(ctx.raw, ctx.fmt, stream.as_ptr(), stream.len() as i64, &mut out) };
+        if rc != 0 {
+            let e = unsafe { CStr::from_ptr(fg_last_error(ctx.raw)) }.to_string_lossy().into_owned();
+            panic!("fg_split_decode: {}", e);
+        }
+        let offs = unsafe { std::slice::from_raw_parts(out.line_offsets, out.n as usize + 1) };
+        for i in 0..out.n as usize {
+            // BufRead::lines: drop the '\n' and one '\r' before it
+            let (lo, mut hi) = (offs[i] as usize, offs[i + 1] as usize);
+            if hi > lo && stream[hi - 1] == b'\n' { hi -= 1; if hi > lo && stream[hi - 1] == b'\r' { hi -= 1; } }
+            let ext = [lo as i32, hi as i32];
+            let mut side = Vec::new();
+            // `materialize` reads the extent of line i from offsets[i..i+2]: hand it the stripped extent
+            let r = materialize_ext(&ctx, &out, stream, ext[0], ext[1], i, &mut side);
+            f(i, &stream[lo..hi], r, &side);
+        }
+    }
+}
+
 fn span<'a>(bytes: &'a [u8], s: fg_span) -> &'a str {
     // spans delimit whole UTF-8 sequences of a line that was validated before the call
     unsafe { std::str::from_utf8_unchecked(&bytes[s.off as usize..(s.off + s.len) as usize]) }
@@ -177,13 +202,17 @@ fn json_unescape(v: &str, nl_retry: bool) -> String {
 }
 
 fn materialize(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], offsets: &[i32], i: usize, side: &mut Vec<String>) -> Result<Record, &'static str> {
+    materialize_ext(ctx, out, bytes, offsets[i], offsets[i + 1], i, side)
+}
+
+fn materialize_ext(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, line_hi: i32, i: usize, side: &mut Vec<String>) -> Result<Record, &'static str> {
     unsafe {
         let meta = *out.meta.add(i);
         let status = meta & 0xFF;
         let flags = (meta >> 24) & 0xFF;
         if flags & FG_FLAG_MISSING_VALUE != 0 {
             // println! at ltsv_decoder.rs:99 for every part without ':' that the decode loop reached
-            let (lo, hi) = (offsets[i] as usize, offsets[i + 1] as usize);
+            let (lo, hi) = (line_lo as usize, line_hi as usize);
             let stop = if status != 0 { (*out.full_msg.add(i)).off as usize } else { hi + 1 };
             let mut a = lo;
             for part in span(bytes, fg_span { off: lo as i32, len: (hi - lo) as i32 }).split('\t') {
