@@ -70,8 +70,8 @@ typedef enum fg_ltsv_type { FG_LTSV_STRING = 0, FG_LTSV_BOOL = 1, FG_LTSV_F64 = 
 
 typedef struct fg_config {
     int32_t device;           /* CUDA device ordinal */
-    int64_t max_batch_bytes;  /* capacity of one fg_decode_batch call (<= 2^31-64) ; 0 = default 1 GiB */
-    int32_t max_batch_lines;  /* 0 = default 8 Mi */
+    int64_t max_batch_bytes;  /* capacity of one fg_decode_batch call (<= 2^31-64) ; 0 = default 256 MiB */
+    int32_t max_batch_lines;  /* 0 = default 2 Mi (rounded up to a multiple of 64) */
     int32_t chunk_lines;      /* host<->device pipeline granularity; 0 = default 256 Ki */
     /* input.ltsv_schema / input.ltsv_suffixes (ltsv_decoder.rs:25-81); ignored by other formats */
     int32_t ltsv_has_schema;
