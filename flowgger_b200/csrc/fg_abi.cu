@@ -105,6 +105,10 @@ struct fg_ctx {
     int32_t* h_n_lines = nullptr;
     float last_split_ms = 0.f;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+    cudaStream_t s_parse = nullptr;
+    std::vector<cudaEvent_t> ev_split;
+    int32_t* d_cum = nullptr;
+    int32_t* h_cum = nullptr;
     size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
@@ -489,6 +493,10 @@ void fg_destroy(fg_ctx* c) {
     if (c->d_invalid) cudaFree(c->d_invalid);
     if (c->h_offsets) cudaFreeHost(c->h_offsets);
     if (c->h_n_lines) cudaFreeHost(c->h_n_lines);
+    if (c->s_parse) cudaStreamDestroy(c->s_parse);
+    for (auto e : c->ev_split) cudaEventDestroy(e);
+    if (c->d_cum) cudaFree(c->d_cum);
+    if (c->h_cum) cudaFreeHost(c->h_cum);
     if (c->ev_s0) cudaEventDestroy(c->ev_s0);
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
     if (c->d_tmp_name) cudaFree(c->d_tmp_name);
@@ -611,6 +619,8 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_scratch(c, (int)fmt)) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
+    constexpr long long kChunk = 64ll << 20;  // pipeline granularity in bytes (a multiple of the 8 KB framing segment)
+    const int chunks = nbytes > 0 ? (int)((nbytes + kChunk - 1) / kChunk) : 1;
     if (!c->d_seg) {
         FG_CUDA(c, cudaMalloc(&c->d_seg, sizeof(uint32_t) * ((size_t)fg::split_segments((long long)c->max_bytes) + 16)));
         FG_CUDA(c, cudaMalloc(&c->d_n_lines, 256));
@@ -619,61 +629,124 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
         FG_CUDA(c, cudaHostAlloc(&c->h_n_lines, 64, cudaHostAllocDefault));
         FG_CUDA(c, cudaEventCreate(&c->ev_s0));
         FG_CUDA(c, cudaEventCreate(&c->ev_s1));
+        FG_CUDA(c, cudaStreamCreateWithFlags(&c->s_parse, cudaStreamNonBlocking));
     }
+    if ((int)c->ev_split.size() < chunks + 1) {
+        const size_t want = (size_t)chunks + 1;
+        while (c->ev_split.size() < want) {
+            cudaEvent_t e;
+            FG_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_split.push_back(e);
+        }
+        if (c->d_cum) cudaFree(c->d_cum);
+        if (c->h_cum) cudaFreeHost(c->h_cum);
+        FG_CUDA(c, cudaMalloc(&c->d_cum, sizeof(int32_t) * want));
+        FG_CUDA(c, cudaHostAlloc(&c->h_cum, sizeof(int32_t) * want, cudaHostAllocDefault));
+    }
+    if (int rc = ensure_events(c, chunks + 1)) return rc;
     memset(out, 0, sizeof *out);
-    // 1. raw stream -> HBM (zero tail so that whole-vector loads past the end see no newline)
-    int bounce_ix = 0;
-    if (int rc = h2d(c, c->d_bytes, stream, (size_t)nbytes, nbytes > 0 && is_pinned(stream), bounce_ix)) return rc;
-    FG_CUDA(c, cudaMemsetAsync(c->d_bytes + nbytes, 0, 64, c->s_h2d));
-    FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_h2d));
-    FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_a, 0));
-    // 2. framing + UTF-8 validation on device
-    FG_CUDA(c, cudaMemsetAsync(c->d_invalid, 0, (size_t)c->max_lines, c->s_comp));
-    FG_CUDA(c, cudaEventRecord(c->ev_s0, c->s_comp));
-    FG_CUDA(c, fg::launch_split(c->d_bytes, (long long)nbytes, c->d_seg, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, c->s_comp));
-    c->launches += 4;
-    FG_CUDA(c, cudaEventRecord(c->ev_s1, c->s_comp));
-    FG_CUDA(c, cudaMemcpyAsync(c->h_n_lines, c->d_n_lines, 4, cudaMemcpyDeviceToHost, c->s_comp));
-    FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
-    FG_CUDA(c, cudaEventElapsedTime(&c->last_split_ms, c->ev_s0, c->ev_s1));
-    const int32_t n = *c->h_n_lines;
-    if (n < 0) return fail(c, FG_E_CAPACITY, "stream has more lines than max_batch_lines");
-    // 3. parse (terminators stripped and invalid lines skipped inside the kernel)
-    uint32_t total = 0;
-    float kms = 0.f;
-    const int tile = pick_tile(c, (size_t)nbytes, n, (int)fmt);
-    for (int attempt = 0; attempt < 2 && n > 0; ++attempt) {
+    const bool pinned = nbytes > 0 && is_pinned(stream);
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // ---- enqueue, chunk by chunk: raw bytes -> HBM, then framing + UTF-8 validation of that chunk (no host dependency)
+        FG_CUDA(c, cudaMemsetAsync(c->d_n_lines + 8, 0, 4, c->s_comp));  // running newline count (uint32 at d_n_lines[8])
+        FG_CUDA(c, cudaMemsetAsync(c->d_invalid, 0, (size_t)c->max_lines, c->s_comp));
         FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
-        fg::ParseParams P;
-        fill_params(c, P, 0, n, tile);
-        P.line_invalid = c->d_invalid;
-        P.strip_eol = 1;
-        FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
-        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
-        ++c->launches;
-        FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
-        FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
-        FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
-        if ((size_t)total > c->entry_cap) {
+        FG_CUDA(c, cudaEventRecord(c->ev_s0, c->s_comp));
+        int bounce_ix = 0;
+        for (int k = 0; k < chunks; ++k) {
+            const long long c0 = (long long)k * kChunk, c1 = std::min<long long>(nbytes, c0 + kChunk);
+            const bool last = k == chunks - 1;
+            if (int rc = h2d(c, c->d_bytes + c0, stream + c0, (size_t)(c1 - c0), pinned, bounce_ix)) return rc;
+            if (last) FG_CUDA(c, cudaMemsetAsync(c->d_bytes + nbytes, 0, 64, c->s_h2d));  // whole-vector loads past the end see no '\n'
+            FG_CUDA(c, cudaEventRecord(c->ev_h2d[k], c->s_h2d));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[k], 0));
+            FG_CUDA(c, fg::launch_split_chunk(c->d_bytes, (long long)nbytes, c0, c1, last ? 1 : 0, c->d_seg, (uint32_t*)(c->d_n_lines + 8),
+                                              c->d_cum + k, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, c->s_comp));
+            c->launches += 4;
+            FG_CUDA(c, cudaMemcpyAsync(c->h_cum + k, c->d_cum + k, 4, cudaMemcpyDeviceToHost, c->s_comp));
+            if (last) {
+                FG_CUDA(c, cudaMemcpyAsync(c->h_n_lines, c->d_n_lines, 4, cudaMemcpyDeviceToHost, c->s_comp));
+                FG_CUDA(c, cudaEventRecord(c->ev_s1, c->s_comp));
+            }
+            FG_CUDA(c, cudaEventRecord(c->ev_split[k], c->s_comp));
+        }
+        // ---- parse the lines that END in chunk k once chunk k+1 has been validated too (a sequence that starts in the
+        //      last 16 bytes of a chunk is checked with the next one); rows go back while later chunks are still in flight
+        int32_t done_lines = 0;
+        int32_t n = 0;
+        int nparse = 0;
+        bool over = false;
+        const int tile = pick_tile(c, (size_t)nbytes, std::max<int32_t>(1, (int32_t)(nbytes / 180)), (int)fmt);  // refined per launch below
+        (void)tile;
+        for (int k = 0; k < chunks; ++k) {
+            const int dep = std::min(k + 1, chunks - 1);
+            FG_CUDA(c, cudaEventSynchronize(c->ev_split[dep]));
+            int32_t upto = c->h_cum[k];
+            if (upto < 0) { over = true; break; }
+            if (k == chunks - 1) {
+                n = *c->h_n_lines;
+                if (n < 0) { over = true; break; }
+                upto = n;  // includes an unterminated last line
+            }
+            const int32_t cnt = upto - done_lines;
+            if (cnt > 0) {
+                fg::ParseParams P;
+                const size_t span_bytes = (size_t)std::min<long long>(nbytes, (long long)(k + 1) * kChunk) - (size_t)((long long)k * kChunk);
+                fill_params(c, P, done_lines, cnt, pick_tile(c, std::max<size_t>(span_bytes, 1), cnt, (int)fmt));
+                P.line_invalid = c->d_invalid + done_lines;
+                P.strip_eol = 1;
+                FG_CUDA(c, cudaStreamWaitEvent(c->s_parse, c->ev_split[dep], 0));
+                FG_CUDA(c, cudaEventRecord(c->ev_k0[nparse], c->s_parse));
+                FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_parse));
+                ++c->launches;
+                FG_CUDA(c, cudaEventRecord(c->ev_k1[nparse], c->s_parse));
+                FG_CUDA(c, cudaMemcpyAsync(c->h_counts + nparse, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_parse));
+                FG_CUDA(c, cudaEventRecord(c->ev_cnt[nparse], c->s_parse));
+                FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_cnt[nparse], 0));
+                if (int rc = copy_rows_d2h(c, fmt, done_lines, cnt, c->s_d2h)) return rc;
+                ++nparse;
+                done_lines = upto;
+            }
+        }
+        if (over) {
+            FG_CUDA(c, cudaDeviceSynchronize());
+            return fail(c, FG_E_CAPACITY, "stream has more lines than max_batch_lines");
+        }
+        // ---- side table ranges, line offsets
+        uint32_t copied = 0, total = 0;
+        bool overflow = false;
+        for (int j = 0; j < nparse; ++j) {
+            FG_CUDA(c, cudaEventSynchronize(c->ev_cnt[j]));
+            total = c->h_counts[j];
+            if ((size_t)total > c->entry_cap) { overflow = true; continue; }
+            if (!overflow) {
+                if (int rc = copy_entries_d2h(c, copied, total, c->s_d2h)) return rc;
+                copied = total;
+            }
+        }
+        if (overflow) {
+            FG_CUDA(c, cudaDeviceSynchronize());
             if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
-            total = 0;
             continue;
         }
-        FG_CUDA(c, cudaEventElapsedTime(&kms, c->ev_a, c->ev_b));
-        break;
+        FG_CUDA(c, cudaStreamSynchronize(c->s_parse));
+        FG_CUDA(c, cudaMemcpyAsync(c->h_offsets, c->d_offsets, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->s_d2h));
+        FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+        float kms = 0.f;
+        for (int j = 0; j < nparse; ++j) {
+            float ms = 0.f;
+            FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_k0[j], c->ev_k1[j]));
+            kms += ms;
+        }
+        FG_CUDA(c, cudaEventElapsedTime(&c->last_split_ms, c->ev_s0, c->ev_s1));  // includes waiting for the H2D chunks
+        fill_out(c, fmt, n, total, out);
+        out->line_offsets = c->h_offsets;
+        out->kernel_ms = kms;
+        out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        return FG_OK;
     }
-    // 4. results + the line offsets back to the host
-    if (n > 0) {
-        if (int rc = copy_rows_d2h(c, fmt, 0, n, c->s_d2h)) return rc;
-        if (int rc = copy_entries_d2h(c, 0, total, c->s_d2h)) return rc;
-    }
-    FG_CUDA(c, cudaMemcpyAsync(c->h_offsets, c->d_offsets, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->s_d2h));
-    FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
-    fill_out(c, fmt, n, total, out);
-    out->line_offsets = c->h_offsets;
-    out->kernel_ms = kms;
-    out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    return FG_OK;
+    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
 }
 
 int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {

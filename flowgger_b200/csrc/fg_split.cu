@@ -25,8 +25,8 @@ __device__ __forceinline__ uint32_t nl_flags(uint32_t w) {  // 0x80 in every byt
 
 // bytes beyond nbytes are zero (the host clears a tail), so whole 16-byte loads are safe up to the padded end
 __global__ void __launch_bounds__(kWarpsPerCta * 32) count_newlines_kernel(const uint8_t* __restrict__ bytes, long long nbytes,
-                                                                            uint32_t* __restrict__ seg_counts, int nseg) {
-    const int seg = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+                                                                            uint32_t* __restrict__ seg_counts, int seg0, int nseg) {
+    const int seg = seg0 + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (seg >= nseg) return;
     const uint32_t lane = threadIdx.x & 31u;
     const long long base = (long long)seg * kSegBytes;
@@ -43,14 +43,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) count_newlines_kernel(const
     if (lane == 0) seg_counts[seg] = cnt;
 }
 
-// single CTA: exclusive scan of the segment counts; also the line count and the two end offsets
-__global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restrict__ seg_counts, int nseg, const uint8_t* __restrict__ bytes,
+// single CTA: exclusive scan of the counts of segments [seg0, seg1) on top of the running newline count `*run`
+// (chunk-pipelined framing: chunk k is scanned as soon as its bytes are resident).  Publishes the cumulative newline
+// count after this chunk; the last chunk also settles the line count and the end offset of an unterminated last line.
+__global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restrict__ seg_counts, int seg0, int seg1, uint32_t* __restrict__ run,
+                                                             int32_t* __restrict__ cum_out, int is_last, const uint8_t* __restrict__ bytes,
                                                              long long nbytes, int32_t* __restrict__ offsets, int32_t* __restrict__ n_lines,
                                                              int max_lines) {
     __shared__ uint32_t part[1024];
     const int t = threadIdx.x;
+    const int nseg = seg1 - seg0;
     const int per = (nseg + 1023) / 1024;
-    const int lo = t * per, hi = min(nseg, lo + per);
+    const int lo = seg0 + t * per, hi = min(seg1, lo + per);
     uint32_t s = 0;
     for (int k = lo; k < hi; ++k) s += seg_counts[k];
     part[t] = s;
@@ -61,27 +65,33 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restric
         part[t] += v;
         __syncthreads();
     }
-    uint32_t run = part[t] - s;  // exclusive prefix of this thread's range
+    const uint32_t before = *run;
+    uint32_t r = before + part[t] - s;  // exclusive prefix of this thread's range
     for (int k = lo; k < hi; ++k) {
         const uint32_t c = seg_counts[k];
-        seg_counts[k] = run;
-        run += c;
+        seg_counts[k] = r;
+        r += c;
     }
+    __syncthreads();
     if (t == 1023) {
-        const uint32_t newlines = part[1023];
-        const bool tail = nbytes > 0 && bytes[nbytes - 1] != '\n';  // BufRead::lines yields an unterminated last line
-        const long long n = (long long)newlines + (tail ? 1 : 0);
-        *n_lines = n > max_lines ? -1 : (int32_t)n;
-        offsets[0] = 0;
-        if (n <= max_lines && tail) offsets[n] = (int32_t)nbytes;
+        const unsigned long long newlines = (unsigned long long)before + part[1023];
+        *run = (uint32_t)newlines;
+        const bool over = newlines + 1ull > (unsigned long long)max_lines;
+        *cum_out = over ? -1 : (int32_t)newlines;
+        if (seg0 == 0) offsets[0] = 0;
+        if (is_last) {
+            const bool tail = nbytes > 0 && bytes[nbytes - 1] != '\n';  // BufRead::lines yields an unterminated last line
+            const long long n = (long long)newlines + (tail ? 1 : 0);
+            *n_lines = (over || n > max_lines) ? -1 : (int32_t)n;
+            if (!over && n <= max_lines && tail) offsets[n] = (int32_t)nbytes;
+        }
     }
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_offsets_kernel(const uint8_t* __restrict__ bytes, long long nbytes,
-                                                                          const uint32_t* __restrict__ seg_base, int nseg,
-                                                                          int32_t* __restrict__ offsets, const int32_t* __restrict__ n_lines) {
-    if (*n_lines < 0) return;  // more lines than the context can hold: the host reports FG_E_CAPACITY
-    const int seg = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+                                                                          const uint32_t* __restrict__ seg_base, int seg0, int nseg,
+                                                                          int32_t* __restrict__ offsets, int max_lines) {
+    const int seg = seg0 + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (seg >= nseg) return;
     const uint32_t lane = threadIdx.x & 31u;
     const long long base = (long long)seg * kSegBytes;
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_offsets_kernel(const u
             uint32_t f = z[wI];
             while (f) {
                 const int b = (__ffs((int)f) - 1) >> 3;
-                offsets[k + 1] = (int32_t)(pos + wI * 4 + b + 1);  // the next line starts after this '\n'
+                if (k + 1 <= (uint32_t)max_lines) offsets[k + 1] = (int32_t)(pos + wI * 4 + b + 1);  // the next line starts after this '\n'
                 ++k;
                 f &= f - 1;
             }
@@ -126,13 +136,17 @@ __device__ __forceinline__ int utf8_need(uint32_t c) {  // continuation bytes a 
     return -1;  // 0x80..0xC1 (continuation or overlong lead), 0xF5..0xFF
 }
 
-__global__ void __launch_bounds__(256) validate_utf8_kernel(const uint8_t* __restrict__ bytes, long long nbytes,
-                                                            const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_lines,
+// Validates the byte positions [v0, v1) (16-byte aligned bounds); everything it reads (up to 3 bytes past v1) must be
+// resident, so the chunk-pipelined caller lags the validated window 16 bytes behind the uploaded bytes.  `known` = number of
+// newlines found so far: lines 0 .. known (the last one possibly still open) have valid start offsets.
+__global__ void __launch_bounds__(256) validate_utf8_kernel(const uint8_t* __restrict__ bytes, long long nbytes, long long v0, long long v1,
+                                                            const int32_t* __restrict__ offsets, const int32_t* __restrict__ known,
                                                             uint8_t* __restrict__ invalid) {
-    const int n = *n_lines;
-    if (n <= 0) return;
-    const long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (pos >= nbytes) return;
+    const int kn = *known;
+    if (kn < 0) return;
+    const int n = kn + 1;
+    const long long pos = v0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (pos >= v1 || pos >= nbytes) return;
     const uint4 v = *reinterpret_cast<const uint4*>(bytes + pos);
     if (((v.x | v.y | v.z | v.w) & 0x80808080u) == 0u) return;  // ASCII only
     // an error flags the line that holds the offending byte (several lines may meet inside one chunk)
@@ -145,7 +159,8 @@ __global__ void __launch_bounds__(256) validate_utf8_kernel(const uint8_t* __res
         }
         invalid[lo] = 1;
     };
-    const long long end = pos + 16 < nbytes ? pos + 16 : nbytes;
+    long long end = pos + 16 < nbytes ? pos + 16 : nbytes;
+    if (end > v1) end = v1;
     for (long long q = pos; q < end; ++q) {
         const uint32_t c = bytes[q];
         if (c < 0x80u) continue;
@@ -180,16 +195,23 @@ __global__ void __launch_bounds__(256) validate_utf8_kernel(const uint8_t* __res
 
 }  // namespace
 
-cudaError_t launch_split(const uint8_t* d_bytes, long long nbytes, uint32_t* d_seg, int32_t* d_offsets, int32_t* d_n_lines,
-                         int max_lines, uint8_t* d_invalid, cudaStream_t stream) {
-    const int nseg = (int)((nbytes + kSegBytes - 1) / kSegBytes);
-    const int grid = (nseg + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (nseg > 0) count_newlines_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes, d_seg, nseg);
-    scan_segments_kernel<<<1, 1024, 0, stream>>>(d_seg, nseg, d_bytes, nbytes, d_offsets, d_n_lines, max_lines);
-    if (nseg > 0) {
-        fill_offsets_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes, d_seg, nseg, d_offsets, d_n_lines);
-        const long long chunks = (nbytes + 15) / 16;
-        validate_utf8_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(d_bytes, nbytes, d_offsets, d_n_lines, d_invalid);
+// Framing + validation of the bytes [c0, c1) (c0 a multiple of the segment size) of a stream of nbytes bytes whose bytes
+// [0, c1) are resident.  `d_run` carries the newline count across chunks, d_cum[k] receives the count after this chunk.
+cudaError_t launch_split_chunk(const uint8_t* d_bytes, long long nbytes, long long c0, long long c1, int is_last, uint32_t* d_seg,
+                               uint32_t* d_run, int32_t* d_cum_k, int32_t* d_offsets, int32_t* d_n_lines, int max_lines,
+                               uint8_t* d_invalid, cudaStream_t stream) {
+    const int seg0 = (int)(c0 / kSegBytes), seg1 = (int)((c1 + kSegBytes - 1) / kSegBytes);
+    const int grid = (seg1 - seg0 + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (seg1 > seg0) count_newlines_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1);
+    scan_segments_kernel<<<1, 1024, 0, stream>>>(d_seg, seg0, seg1, d_run, d_cum_k, is_last, d_bytes, nbytes, d_offsets, d_n_lines, max_lines);
+    if (seg1 > seg0) {
+        fill_offsets_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1, d_offsets, max_lines);
+        // validated window lags 16 bytes behind the resident bytes (sequences read up to 3 bytes ahead), except at the end
+        const long long v0 = c0 >= 16 ? c0 - 16 : 0, v1 = is_last ? ((nbytes + 15) & ~15LL) : c1 - 16;
+        if (v1 > v0) {
+            const long long chunks = (v1 - v0 + 15) / 16;
+            validate_utf8_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(d_bytes, nbytes, v0, v1, d_offsets, d_cum_k, d_invalid);
+        }
     }
     return cudaGetLastError();
 }

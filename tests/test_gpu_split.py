@@ -64,3 +64,45 @@ def test_generated_stream_all_formats(native, oracle):
             check(dec, oracle, fmt, stream)
         finally:
             dec.close()
+
+
+def test_multi_chunk_stream_and_chunk_boundaries(native, oracle):
+    """fg_split_decode pipelines the stream in 64 MiB chunks: lines, multi-byte characters and invalid sequences that
+    straddle a chunk boundary must come out exactly as in the single-chunk case."""
+    import pysplit
+    base = ("<13>1 2015-08-05T15:53:45Z h a p m - " + "x" * 24).encode()      # 61 bytes
+    assert len(base) == 61
+    line = base + b"ab\n"                                                         # 64 bytes incl. terminator
+    n_fill = (64 << 20) // 64
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=200 << 20, max_batch_lines=3 << 20)
+    try:
+        for shift, tail in [(0, "é"), (1, "é"), (2, "日"), (3, "\U0001F680"), (1, None), (2, b"\xe2\x82"), (3, b"\xf0\x9f")]:
+            first = b"<13>1 2015-08-05T15:53:45Z h a p m - " + b"y" * (26 + shift) + b"\n"   # shifts every later line
+            if tail is None:
+                special = base + b"\xc3\n"            # lead byte right before the '\n': invalid line
+            elif isinstance(tail, bytes):
+                special = base + tail + b"\n"         # truncated sequence: invalid line
+            else:
+                special = base + tail.encode() + b"\n"
+            # the special line sits so that its non-ASCII bytes fall around the 64 MiB boundary
+            k = n_fill - 2
+            stream = first + line * k + special + line * 5 + b"<13>1 2015-08-05T15:53:45Z h a p m - end"
+            stream = stream + line * (n_fill // 2)    # a third chunk and an unterminated... (ends with '\n' here)
+            arr = np.frombuffer(stream, dtype=np.uint8)
+            buf, bo, line_offs, _ = dec.split_dump(arr)
+            offs, lines, valid = pysplit.split_lines(stream)
+            assert np.array_equal(line_offs, offs)
+            idx = k + 1
+            assert lines[idx].startswith(base)
+            got = buf[bo[idx]:bo[idx + 1]]
+            if valid[idx]:
+                d, o = oracle.pack([lines[idx]])
+                ob, oo = oracle.decode_dump(0, d, o)
+                assert got == ob
+            else:
+                assert got == b"E:Invalid UTF-8 input;out=0"
+            # every other line is valid
+            bad = [j for j in range(len(lines)) if buf[bo[j]:bo[j] + 2] != b"R:"]
+            assert bad == ([] if valid[idx] else [idx])
+    finally:
+        dec.close()
