@@ -155,3 +155,15 @@ def test_rust_f64_grammar(oracle):
     for s in ["", "+", "-", ".", "e5", "1e", "1e+", "0x10", "1_0", " 1", "1 ", "infinit", "nane", "1.5.2", "--1"]:
         assert oracle.parse_f64(s.encode()) is None, s
     assert oracle.parse_f64(b"NaN") != oracle.parse_f64(b"NaN")
+
+
+def test_golden_fixture_file_matches_vectors_module():
+    """tests/golden/reference_vectors.json (the reference's own test inputs, with file:line) and tests/vectors.py agree."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "reference_vectors.json").read_text())
+    assert g["G1"]["line"] == V.G1_LINE and g["G2"]["line"] == V.G2_LINE and g["G3"]["line"] == V.G3_LINE
+    assert g["G9"]["line"] == V.G9_LINE and g["G11"]["line"] == V.G11_LINE and g["G14"]["line"] == V.G14_LINE
+    assert [c["err"] for c in g["G4-G8"]["cases"]] == [e for _, e in V.GELF_ERRORS]
+    assert f64_hex(g["G1"]["expect"]["ts"]) == g["G1"]["expect"]["ts_bits"]
+    assert f64_hex(g["G11"]["expect"]["ts"]) == g["G11"]["expect"]["ts_bits"]
