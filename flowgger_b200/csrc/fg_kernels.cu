@@ -270,7 +270,10 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
     switch (fmt) {
-        case 0: parse_kernel<0, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p); break;
+        case 0:
+            if (p.tile_bytes > 0) parse_kernel<0, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
+            else parse_kernel<0, false><<<grid, kLinesPerCta, 0, stream>>>(p);  // experiment switch FG_FORCE_UNSTAGED
+            break;
         case 1:
             if (p.tile_bytes > 0) parse_kernel<1, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
             else parse_kernel<1, false><<<grid, kLinesPerCta, 0, stream>>>(p);
