@@ -120,6 +120,32 @@ __device__ __noinline__ bool ltsv_needs_suffix(bytes_t p, int a, int n, int type
     return false;
 }
 
+
+// typed value of a schema key (:138-195): returns FG_ST_OK and the 8 value bytes, or the reference's type error
+__device__ __noinline__ uint32_t ltsv_parse_typed(bytes_t p, int va, int vb, int type, unsigned long long& val) {
+    if (type == 1) {  // bool::from_str: exactly "true" / "false"
+        if (key_is(p, va, vb - va, "true", 4)) { val = 1; return FG_ST_OK; }
+        if (key_is(p, va, vb - va, "false", 5)) { val = 0; return FG_ST_OK; }
+        return FG_EL_BOOL;
+    }
+    if (type == 2) {
+        double f;
+        if (!parse_f64_rust(p, va, vb, f)) return FG_EL_F64;
+        val = (unsigned long long)__double_as_longlong(f);
+        return FG_ST_OK;
+    }
+    if (type == 3) {
+        int64_t v;
+        if (!parse_i64(p, va, vb, v)) return FG_EL_I64;
+        val = (unsigned long long)v;
+        return FG_ST_OK;
+    }
+    uint64_t v;
+    if (!parse_u64(p, va, vb, v)) return FG_EL_U64;
+    val = v;
+    return FG_ST_OK;
+}
+
 // All 32 lanes of a warp must call this (idle lanes with len = 0, active_line = false).
 FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bool active_line,
                             const LtsvDeviceConfig& cfg, LineResult& r, const EntrySink& sink) {
@@ -142,6 +168,9 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     // a second `time`, or any error found later in the line, first settles the pending one.
     int ts_a = -1, ts_b = -1, ts_part = 0;
     bool err_set = false;
+    uint32_t np = 0;  // parked typed values
+    int t_va0 = 0, t_va1 = 0, t_va2 = 0, t_va3 = 0, t_pt0 = 0, t_pt1 = 0, t_pt2 = 0, t_pt3 = 0;
+    uint32_t t_pk0 = 0, t_pk1 = 0, t_pk2 = 0, t_pk3 = 0;
     while (__any_sync(kFullMask, active)) {  // line.split('\t') :94
         // scan the part 4 bytes per step: first ':' (splitn(2, ':') :95), then the terminating TAB
         int i = part;
@@ -212,46 +241,35 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                 } else {  // :122-199
                     const int type = cfg.has_schema ? ltsv_schema_type(p, ka, kn, cfg) : 0;
                     unsigned long long val = (unsigned long long)(uint32_t)(line_off + va) | ((unsigned long long)(uint32_t)(vb - va) << 32);
-                    uint32_t meta = 0;  // FG_TAG_STRING
-                    if (type == 1) {  // bool::from_str: exactly "true" / "false"
-                        if (key_is(p, va, vb - va, "true", 4)) val = 1;
-                        else if (key_is(p, va, vb - va, "false", 5)) val = 0;
-                        else status = FG_EL_BOOL;
-                        meta = 1;
-                    } else if (type == 2) {
-                        double f;
-                        if (!parse_f64_rust(p, va, vb, f)) status = FG_EL_F64;
-                        else val = (unsigned long long)__double_as_longlong(f);
-                        meta = 2;
-                    } else if (type == 3) {
-                        int64_t v;
-                        if (!parse_i64(p, va, vb, v)) status = FG_EL_I64;
-                        else val = (unsigned long long)v;
-                        meta = 3;
-                    } else if (type == 4) {
-                        uint64_t v;
-                        if (!parse_u64(p, va, vb, v)) status = FG_EL_U64;
-                        else val = v;
-                        meta = 4;
+                    uint32_t meta = (uint32_t)type;  // FG_TAG_* == fg_ltsv_type
+                    if (type != 0 && ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
+                    const uint32_t e = sbase + n;
+                    bool deferred = false;
+                    if (type != 0) {
+                        // typed values sit at different field positions in every line: parsing them here would run one lane at a
+                        // time, so up to 4 per line are parked in registers and parsed in lock step after the part loop
+                        if (np < 4u && (vb - va) < (1 << 20) && n < 256u) {
+                            const uint32_t packed = (uint32_t)(vb - va) | ((uint32_t)type << 20) | (n << 24);
+                            if (np == 0u) { t_va0 = va; t_pk0 = packed; t_pt0 = part; }
+                            else if (np == 1u) { t_va1 = va; t_pk1 = packed; t_pt1 = part; }
+                            else if (np == 2u) { t_va2 = va; t_pk2 = packed; t_pt2 = part; }
+                            else { t_va3 = va; t_pk3 = packed; t_pt3 = part; }
+                            ++np;
+                            deferred = true;
+                        } else {
+                            status = ltsv_parse_typed(p, va, vb, type, val);
+                        }
                     }
                     if (status == FG_ST_OK) {
-                        if (type != 0 && ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
-                        const uint32_t e = sbase + n;
                         sink.name[e] = make_int2(line_off + ka, kn);
-                        sink.val[e] = val;
+                        if (!deferred) sink.val[e] = val;
                         sink.meta[e] = (uint8_t)meta;
                         ++n;
                     }
                 }
             }
             if (status != FG_ST_OK) {
-                if (!err_set) err_pos = part;  // the error belongs to the current part
-                if (ts_a >= 0) {
-                    // an error in a LATER part: the pending `time` (earlier in the line) is evaluated first
-                    double t;
-                    if (!ltsv_parse_ts(p, ts_a, ts_b, t)) { status = FG_EL_TS; err_pos = ts_part; }
-                    ts_a = -1;
-                }
+                if (!err_set) err_pos = part;  // the error belongs to the current part (unless an earlier `time` already failed)
                 active = false;
             } else if (part_end >= len) {
                 active = false;
@@ -260,13 +278,30 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
             }
         }
     }
-    // the pending `time` of every lane, in lock step
+    // Deferred work, in lock step.  All of it is pure, so it is evaluated even when a later part already failed; the
+    // reference returns at the FIRST failing part, i.e. the candidate error with the smallest part position wins.
     {
-        const bool pend = active_line && status == FG_ST_OK && ts_a >= 0;
+        const bool pend = active_line && ts_a >= 0 && (status == FG_ST_OK || ts_part < err_pos);
         if (__any_sync(kFullMask, pend)) {
             if (pend) {
-                if (ltsv_parse_ts(p, ts_a, ts_b, r.ts)) have_ts = true;
+                double t;
+                if (ltsv_parse_ts(p, ts_a, ts_b, t)) { r.ts = t; have_ts = true; }
                 else { status = FG_EL_TS; err_pos = ts_part; }
+            }
+        }
+    }
+#pragma unroll
+    for (uint32_t sl = 0; sl < 4u; ++sl) {
+        const int va = sl == 0u ? t_va0 : (sl == 1u ? t_va1 : (sl == 2u ? t_va2 : t_va3));
+        const uint32_t pk = sl == 0u ? t_pk0 : (sl == 1u ? t_pk1 : (sl == 2u ? t_pk2 : t_pk3));
+        const int pt = sl == 0u ? t_pt0 : (sl == 1u ? t_pt1 : (sl == 2u ? t_pt2 : t_pt3));
+        const bool has = active_line && sl < np && (status == FG_ST_OK || pt < err_pos);
+        if (__any_sync(kFullMask, has)) {
+            if (has) {
+                unsigned long long val = 0;
+                const uint32_t st = ltsv_parse_typed(p, va, va + (int)(pk & 0xFFFFFu), (int)((pk >> 20) & 7u), val);
+                if (st == FG_ST_OK) sink.val[sbase + (pk >> 24)] = val;
+                else { status = st; err_pos = pt; }
             }
         }
     }
