@@ -161,8 +161,8 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     int err_pos = 0;
     int part = 0;  // start of the current part
     bool active = active_line;
-    const uint32_t a0 = (uint32_t)(size_t)p & 3u;
-    const uint32_t* wp = (const uint32_t*)(p - a0);
+    const uint32_t b0 = (uint32_t)(size_t)p & 15u;
+    const uint4* qp = (const uint4*)(p - b0);
     // The `time` value is parsed AFTER the part loop, in lock step for the whole warp (its position among the 20
     // fields differs per line, so parsing it inline would run one lane at a time).  Evaluation order is preserved:
     // a second `time`, or any error found later in the line, first settles the pending one.
@@ -172,18 +172,16 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     int t_va0 = 0, t_va1 = 0, t_va2 = 0, t_va3 = 0, t_pt0 = 0, t_pt1 = 0, t_pt2 = 0, t_pt3 = 0;
     uint32_t t_pk0 = 0, t_pk1 = 0, t_pk2 = 0, t_pk3 = 0;
     while (__any_sync(kFullMask, active)) {  // line.split('\t') :94
-        // scan the part 4 bytes per step: first ':' (splitn(2, ':') :95), then the terminating TAB
+        // scan the part 16 bytes per step: first ':' (splitn(2, ':') :95), then the terminating TAB
         int i = part;
         {
             const int lim = active ? len : i;
             for (;;) {
                 bool more = false;
                 if (i < lim) {
-                    uint32_t sh;
-                    const uint32_t w = scan_word(wp, a0, i, sh);
-                    const uint32_t z = swar_zero(w ^ 0x09090909u) | swar_zero(w ^ 0x3A3A3A3Au);
-                    if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
-                    else { i += 4 - (int)(sh >> 3); more = true; }
+                    bool hit;
+                    i = scan_block16<true>(qp, b0, i, 0x09090909u, 0x3A3A3A3Au, hit);
+                    more = !hit;
                 }
                 if (!__any_sync(kFullMask, more)) break;
             }
@@ -196,10 +194,9 @@ FG_DEV void ltsv_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
             for (;;) {
                 bool more = false;
                 if (i < lim) {
-                    uint32_t sh;
-                    const uint32_t z = swar_zero(scan_word(wp, a0, i, sh) ^ 0x09090909u);
-                    if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
-                    else { i += 4 - (int)(sh >> 3); more = true; }
+                    bool hit;
+                    i = scan_block16<false>(qp, b0, i, 0x09090909u, 0u, hit);
+                    more = !hit;
                 }
                 if (!__any_sync(kFullMask, more)) break;
             }

@@ -54,6 +54,41 @@ FG_DEV uint32_t scan_word(const uint32_t* wp, uint32_t a0, int i, uint32_t& sh) 
     return (wp[o >> 2] & keep) | (0x41414141u & ~keep);
 }
 
+// 16 bytes per step, for formats whose tokens are long (LTSV values, JSON strings): one 16-byte aligned load, an
+// EXACT per-byte equality mask (0x80 where byte == pattern byte; no borrow artefacts, so hits below the cursor can
+// simply be masked off), first hit at or after byte i.  Returns the new cursor: the hit position (`hit` = true) or
+// the start of the next 16-byte block.  The block holding byte i is qp[(b0 + i) >> 4], b0 = address of p & 15.
+FG_DEV uint32_t swar_eq(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+template <bool TWO>
+FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint32_t pat2, bool& hit) {
+    const uint32_t o = b0 + (uint32_t)i;
+    const uint4 v = qp[o >> 4];
+    const uint32_t sh = o & 15u;
+    uint32_t z0 = swar_eq(v.x, pat1), z1 = swar_eq(v.y, pat1), z2 = swar_eq(v.z, pat1), z3 = swar_eq(v.w, pat1);
+    if (TWO) {
+        z0 |= swar_eq(v.x, pat2);
+        z1 |= swar_eq(v.y, pat2);
+        z2 |= swar_eq(v.z, pat2);
+        z3 |= swar_eq(v.w, pat2);
+    }
+    unsigned long long lo = (unsigned long long)z0 | ((unsigned long long)z1 << 32);
+    unsigned long long hi = (unsigned long long)z2 | ((unsigned long long)z3 << 32);
+    if (sh < 8u) {
+        lo &= ~0ull << (sh * 8u);
+    } else {
+        lo = 0ull;
+        hi &= ~0ull << ((sh - 8u) * 8u);
+    }
+    hit = (lo | hi) != 0ull;
+    int adv = 16;
+    if (lo) adv = (__ffsll((long long)lo) - 1) >> 3;
+    else if (hi) adv = 8 + ((__ffsll((long long)hi) - 1) >> 3);
+    return i + adv - (int)sh;
+}
+
 
 // --- side-table staging for RFC5424 ------------------------------------------------------------------------
 // After phase 1 the bytes [0, sp5) of a line (PRI, timestamp, hostname ... msgid) are never read again: every
