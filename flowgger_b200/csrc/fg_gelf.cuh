@@ -59,20 +59,15 @@ FG_DEV bool json_hex4(Json& j, uint32_t& n) {
 __device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
     s = j.i;
     has_bs = false;
-    const uint32_t a0 = (uint32_t)(size_t)j.p & 3u;
-    const uint32_t* wp = (const uint32_t*)(j.p - a0);
+    const uint32_t b0 = (uint32_t)(size_t)j.p & 15u;
+    const uint4* qp = (const uint4*)(j.p - b0);
     for (;;) {
         if (j.i >= j.len) return JS_SYNTAX;  // EOFWhileParsingString
         {
-            // 4 bytes per step up to the next '"', '\\' or control byte (read.rs ESCAPE table)
-            uint32_t sh;
-            const uint32_t w = scan_word(wp, a0, j.i, sh);
-            const uint32_t z = swar_zero(w ^ 0x22222222u) | swar_zero(w ^ 0x5C5C5C5Cu) | ((w - 0x20202020u) & ~w & 0x80808080u);
-            if (!z) {
-                j.i += 4 - (int)(sh >> 3);
-                continue;
-            }
-            j.i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);
+            // 16 bytes per step up to the next '"', '\\' or control byte (read.rs ESCAPE table)
+            bool hit;
+            j.i = scan_block16_json(qp, b0, j.i, hit);
+            if (!hit) continue;
             if (j.i >= j.len) return JS_SYNTAX;  // the hit lies past the end of the line
         }
         const uint32_t c = j.p[j.i];

@@ -62,18 +62,7 @@ FG_DEV uint32_t swar_eq(uint32_t w, uint32_t pat) {
     const uint32_t x = w ^ pat;
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
-template <bool TWO>
-FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint32_t pat2, bool& hit) {
-    const uint32_t o = b0 + (uint32_t)i;
-    const uint4 v = qp[o >> 4];
-    const uint32_t sh = o & 15u;
-    uint32_t z0 = swar_eq(v.x, pat1), z1 = swar_eq(v.y, pat1), z2 = swar_eq(v.z, pat1), z3 = swar_eq(v.w, pat1);
-    if (TWO) {
-        z0 |= swar_eq(v.x, pat2);
-        z1 |= swar_eq(v.y, pat2);
-        z2 |= swar_eq(v.z, pat2);
-        z3 |= swar_eq(v.w, pat2);
-    }
+FG_DEV int first_hit16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3, uint32_t sh, int i, bool& hit) {
     unsigned long long lo = (unsigned long long)z0 | ((unsigned long long)z1 << 32);
     unsigned long long hi = (unsigned long long)z2 | ((unsigned long long)z3 << 32);
     if (sh < 8u) {
@@ -88,7 +77,26 @@ FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint
     else if (hi) adv = 8 + ((__ffsll((long long)hi) - 1) >> 3);
     return i + adv - (int)sh;
 }
-
+template <bool TWO>
+FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint32_t pat2, bool& hit) {
+    const uint32_t o = b0 + (uint32_t)i;
+    const uint4 v = qp[o >> 4];
+    uint32_t z0 = swar_eq(v.x, pat1), z1 = swar_eq(v.y, pat1), z2 = swar_eq(v.z, pat1), z3 = swar_eq(v.w, pat1);
+    if (TWO) {
+        z0 |= swar_eq(v.x, pat2);
+        z1 |= swar_eq(v.y, pat2);
+        z2 |= swar_eq(v.z, pat2);
+        z3 |= swar_eq(v.w, pat2);
+    }
+    return first_hit16(z0, z1, z2, z3, o & 15u, i, hit);
+}
+// JSON string body (serde_json read.rs ESCAPE table): '"', '\\' or a control byte (< 0x20)
+FG_DEV uint32_t swar_json_stop(uint32_t w) { return swar_eq(w, 0x22222222u) | swar_eq(w, 0x5C5C5C5Cu) | swar_eq(w & 0xE0E0E0E0u, 0u); }
+FG_DEV int scan_block16_json(const uint4* qp, uint32_t b0, int i, bool& hit) {
+    const uint32_t o = b0 + (uint32_t)i;
+    const uint4 v = qp[o >> 4];
+    return first_hit16(swar_json_stop(v.x), swar_json_stop(v.y), swar_json_stop(v.z), swar_json_stop(v.w), o & 15u, i, hit);
+}
 
 // --- side-table staging for RFC5424 ------------------------------------------------------------------------
 // After phase 1 the bytes [0, sp5) of a line (PRI, timestamp, hostname ... msgid) are never read again: every
