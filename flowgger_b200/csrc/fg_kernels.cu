@@ -140,8 +140,8 @@ struct Format<2> {  // GELF
 // STAGE = true : the CTA's byte span is bulk-copied into shared memory first (short lines: RFC5424).
 // STAGE = false: threads read their lines straight from global memory through L1 (long lines: at ~500 B/line the tile
 //                would cap an SM at 12 resident warps; without it the register file is the limit).
-template <int FMT, bool STAGE>
-__global__ void __launch_bounds__(kLinesPerCta, kMinCtasPerSm) parse_kernel(const __grid_constant__ ParseParams P) {
+template <int FMT, bool STAGE, int MINB = kMinCtasPerSm>
+__global__ void __launch_bounds__(kLinesPerCta, MINB) parse_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
@@ -269,6 +269,7 @@ cudaError_t configure_kernels(int max_tile_bytes) {
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
+    static const int minb = [] { const char* e = getenv("FG_MINB"); return e ? atoi(e) : 0; }();  // experiment switch (profiles/minb_sweep.sh)
     switch (fmt) {
         case 0:
             if (p.tile_bytes > 0) parse_kernel<0, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
@@ -280,7 +281,9 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
             break;
         case 2:
             if (p.tile_bytes > 0) parse_kernel<2, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
-            else parse_kernel<2, false><<<grid, kLinesPerCta, 0, stream>>>(p);
+            else if (minb == 7) parse_kernel<2, false, 7><<<grid, kLinesPerCta, 0, stream>>>(p);
+            else if (minb == 16) parse_kernel<2, false, 16><<<grid, kLinesPerCta, 0, stream>>>(p);
+            else parse_kernel<2, false, kGelfUnstagedCtasPerSm><<<grid, kLinesPerCta, 0, stream>>>(p);
             break;
         default: return cudaErrorInvalidValue;
     }

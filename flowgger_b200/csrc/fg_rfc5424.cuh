@@ -77,6 +77,8 @@ FG_DEV int first_hit16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3, uint3
     else if (hi) adv = 8 + ((__ffsll((long long)hi) - 1) >> 3);
     return i + adv - (int)sh;
 }
+// 0x80-per-byte flags of one word -> 4 bits (byte j -> bit j): the multiply moves bit 8j to bit 24+j, no carries
+FG_DEV uint32_t swar_nibble(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24; }
 template <bool TWO>
 FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint32_t pat2, bool& hit) {
     const uint32_t o = b0 + (uint32_t)i;
@@ -149,28 +151,29 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
     if (len >= 3 && p[0] == 0xEFu && p[1] == 0xBBu && p[2] == 0xBFu) b = 3;
     else if (!(len > 0 && p[0] == '<')) status = FG_E5_BOM;
 
-    // ---- splitn(7, ' ') :23 — first six spaces, scanned a 32-bit word at a time ----------------------
+    // ---- splitn(7, ' ') :23 — first six spaces, scanned a 16-byte block at a time -------------------
     int nsp = 0;
     {
         const uint8_t* q = p + b;
-        const uint32_t s0 = (uint32_t)(size_t)q & 3u;
-        const uint32_t* wq = (const uint32_t*)(q - s0);
-        const int nwords = (status == FG_ST_OK) ? (int)((s0 + (uint32_t)(len - b) + 3u) >> 2) : 0;
+        const uint32_t s0 = (uint32_t)(size_t)q & 15u;
+        const uint4* bq = (const uint4*)(q - s0);
+        const int nblocks = (status == FG_ST_OK) ? (int)((s0 + (uint32_t)(len - b) + 15u) >> 4) : 0;
         int k = 0;
-        bool active = nwords > 0;
+        bool active = nblocks > 0;
         while (__any_sync(kFullMask, active)) {
             if (active) {
-                const uint32_t x = wq[k] ^ 0x20202020u;
-                uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every byte == ' '
-                if (k == 0) z &= 0xFFFFFFFFu << (8u * s0);
-                while (z != 0 && nsp < 6) {
-                    const int j = (__ffs((int)z) - 1) >> 3;
-                    marks[nsp * 128] = b + 4 * k + j - (int)s0;
+                const uint4 v = bq[k];
+                // one bit per byte == ' ' (exact SWAR equality, then the 0x80 flags of a word gathered into a nibble)
+                uint32_t m = swar_nibble(swar_eq(v.x, 0x20202020u)) | (swar_nibble(swar_eq(v.y, 0x20202020u)) << 4) |
+                             (swar_nibble(swar_eq(v.z, 0x20202020u)) << 8) | (swar_nibble(swar_eq(v.w, 0x20202020u)) << 12);
+                if (k == 0) m &= 0xFFFFu << s0;
+                while (m != 0 && nsp < 6) {
+                    marks[nsp * 128] = b + 16 * k + (__ffs((int)m) - 1) - (int)s0;
                     ++nsp;
-                    z &= z - 1;
+                    m &= m - 1;
                 }
                 ++k;
-                active = (k < nwords) && (nsp < 6);
+                active = (k < nblocks) && (nsp < 6);
             }
         }
     }
@@ -237,6 +240,8 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
         uint32_t n = 1, pairs = 0, hdr = 0;
         const uint32_t a0 = (uint32_t)(size_t)p & 3u;
         const uint32_t* wp = (const uint32_t*)(p - a0);
+        const uint32_t b0 = (uint32_t)(size_t)p & 15u;
+        const uint4* qp = (const uint4*)(p - b0);
         int i = d + 1, elem_start = d + 1, id_end = 0;
         bool st_id = true;
         const uint32_t sbase = (uint32_t)line_off / 3u;
@@ -346,25 +351,17 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
                     else { ++i; do_val = true; }
                 }
             }
-            // (D) VAL: up to the first unescaped '"' (:216, :217, :231) — 4 bytes per step
+            // (D) VAL: up to the first unescaped '"' (:216, :217, :231) — 16 bytes per step
             uint32_t has_bs = 0;
             {
                 const int lim = do_val ? len : i;
                 for (;;) {
                     bool more = false;
                     if (i < lim) {
-                        uint32_t sh;
-                        const uint32_t w = scan_word(wp, a0, i, sh);
-                        const uint32_t zb = swar_zero(w ^ 0x5C5C5C5Cu);
-                        const uint32_t z = swar_zero(w ^ 0x22222222u) | zb;
-                        if (z) {
-                            const uint32_t bit = (uint32_t)__ffs((int)z) - 1u;  // 7, 15, 23 or 31: the first hit is exact
-                            i += (int)((bit - sh) >> 3);
-                            if ((zb >> bit) & 1u) { has_bs = 1u; i += 2; more = true; }  // escaped byte skipped
-                        } else {
-                            i += 4 - (int)(sh >> 3);
-                            more = true;
-                        }
+                        bool hit;
+                        i = scan_block16<true>(qp, b0, i, 0x22222222u, 0x5C5C5C5Cu, hit);
+                        more = !hit;
+                        if (hit && i < lim && p[i] == '\\') { has_bs = 1u; i += 2; more = true; }  // escaped byte skipped
                     }
                     if (!__any_sync(kFullMask, more)) break;
                 }
