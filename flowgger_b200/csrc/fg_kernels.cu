@@ -282,7 +282,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
         case 2:
             if (p.tile_bytes > 0) parse_kernel<2, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
             else if (minb == 7) parse_kernel<2, false, 7><<<grid, kLinesPerCta, 0, stream>>>(p);
-            else if (minb == 16) parse_kernel<2, false, 16><<<grid, kLinesPerCta, 0, stream>>>(p);
+            else if (minb == 12) parse_kernel<2, false, 12><<<grid, kLinesPerCta, 0, stream>>>(p);
             else parse_kernel<2, false, kGelfUnstagedCtasPerSm><<<grid, kLinesPerCta, 0, stream>>>(p);
             break;
         default: return cudaErrorInvalidValue;

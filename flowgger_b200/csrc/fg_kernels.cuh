@@ -52,9 +52,9 @@ struct ParseParams {
 
 constexpr int kLinesPerCta = 128;   // lines (= threads) per CTA (256 was measured slower: bigger barriers, same warps/SM)
 constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (tile ~26 KB at 180 B/line) allows 7 CTAs
-// GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 12 CTAs/SM at 40
-// registers beat 7 at 72 (12.3 -> 10.9 ms per 3.5 M lines); LTSV is the opposite (5.8 -> 8.8 ms: L1 working set)
-constexpr int kGelfUnstagedCtasPerSm = 12;
+// GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 16 CTAs/SM at 32
+// registers beat 12 at 40 and 7 at 72 (10.5 / 10.9 / 12.3 ms per 3.5 M lines); LTSV is the opposite (5.8 -> 8.8 ms: L1 working set)
+constexpr int kGelfUnstagedCtasPerSm = 16;
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes);

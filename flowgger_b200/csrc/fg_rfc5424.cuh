@@ -261,17 +261,16 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
         // Inner scans are written as `lim`-bounded loops whose only loop-carried value is the cursor:
         // a lane that is not scanning has lim == i and falls through; nothing else is updated inside.
         while (__any_sync(kFullMask, active)) {
-            // (A) sd_id: up to the first ' ' — 4 bytes per step (aligned word, bytes before the cursor masked off)
+            // (A) sd_id: up to the first ' ' — 16 bytes per step (aligned block, hits before the cursor masked off)
             {
                 const bool scan = active && st_id;
                 const int lim = scan ? len : i;
                 for (;;) {
                     bool more = false;
                     if (i < lim) {
-                        uint32_t sh;
-                        const uint32_t z = swar_zero(scan_word(wp, a0, i, sh) ^ 0x20202020u);
-                        if (z) i += (int)(((uint32_t)__ffs((int)z) - 1u - sh) >> 3);  // stop on the space (may lie past len: checked below)
-                        else { i += 4 - (int)(sh >> 3); more = true; }
+                        bool hit;
+                        i = scan_block16<false>(qp, b0, i, 0x20202020u, 0u, hit);  // stop on the space (may lie past len: checked below)
+                        more = !hit;
                     }
                     if (!__any_sync(kFullMask, more)) break;
                 }
