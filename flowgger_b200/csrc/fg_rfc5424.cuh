@@ -62,23 +62,18 @@ FG_DEV uint32_t swar_eq(uint32_t w, uint32_t pat) {
     const uint32_t x = w ^ pat;
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
+// 0x80-per-byte flags of one word -> 4 bits in the top nibble (byte j -> bit 28 + j): the multiply moves bit 8j + 7 to
+// bit 28 + j; every cross term lands on a distinct bit below 28, so nothing carries into the nibble
+FG_DEV uint32_t swar_top_nibble(uint32_t z) { return z * 0x00204081u; }
+// first flagged byte at or after the cursor (sh = cursor position inside the block), branch-free
 FG_DEV int first_hit16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3, uint32_t sh, int i, bool& hit) {
-    unsigned long long lo = (unsigned long long)z0 | ((unsigned long long)z1 << 32);
-    unsigned long long hi = (unsigned long long)z2 | ((unsigned long long)z3 << 32);
-    if (sh < 8u) {
-        lo &= ~0ull << (sh * 8u);
-    } else {
-        lo = 0ull;
-        hi &= ~0ull << ((sh - 8u) * 8u);
-    }
-    hit = (lo | hi) != 0ull;
-    int adv = 16;
-    if (lo) adv = (__ffsll((long long)lo) - 1) >> 3;
-    else if (hi) adv = 8 + ((__ffsll((long long)hi) - 1) >> 3);
-    return i + adv - (int)sh;
+    uint32_t m = (swar_top_nibble(z0) >> 28) | ((swar_top_nibble(z1) >> 24) & 0xF0u) | ((swar_top_nibble(z2) >> 20) & 0xF00u) |
+                 ((swar_top_nibble(z3) >> 16) & 0xF000u);
+    m &= 0xFFFFFFFFu << sh;
+    hit = m != 0u;
+    return i + (__ffs((int)(m | 0x10000u)) - 1) - (int)sh;  // no hit: the start of the next block
 }
-// 0x80-per-byte flags of one word -> 4 bits (byte j -> bit j): the multiply moves bit 8j to bit 24+j, no carries
-FG_DEV uint32_t swar_nibble(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24; }
+FG_DEV uint32_t swar_nibble(uint32_t z) { return swar_top_nibble(z) >> 28; }
 template <bool TWO>
 FG_DEV int scan_block16(const uint4* qp, uint32_t b0, int i, uint32_t pat1, uint32_t pat2, bool& hit) {
     const uint32_t o = b0 + (uint32_t)i;
