@@ -219,8 +219,9 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt = 0) {
     // long-line formats: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
     if (fmt != FG_FMT_RFC5424 && mean > 256.0 && getenv("FG_FORCE_STAGE") == nullptr) return 0;
     if (getenv("FG_FORCE_UNSTAGED") != nullptr) return 0;  // experiment: every format reads through L1
-    long t = (long)(mean * fg::kLinesPerCta * 1.10) + 1024;
-    t = (t + 1023) & ~1023L;
+    const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
+    long t = (long)(mean * lines * 1.10) + gran;
+    t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
     t = std::min(t, (long)c->max_tile);
     return (int)t;

@@ -140,8 +140,8 @@ struct Format<2> {  // GELF
 // STAGE = true : the CTA's byte span is bulk-copied into shared memory first (short lines: RFC5424).
 // STAGE = false: threads read their lines straight from global memory through L1 (long lines: at ~500 B/line the tile
 //                would cap an SM at 12 resident warps; without it the register file is the limit).
-template <int FMT, bool STAGE, int MINB = kMinCtasPerSm>
-__global__ void __launch_bounds__(kLinesPerCta, MINB) parse_kernel(const __grid_constant__ ParseParams P) {
+template <int FMT, bool STAGE, int MINB = kMinCtasPerSm, int LINES = kLinesPerCta>
+__global__ void __launch_bounds__(LINES, MINB) parse_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kLinesPerCta, MINB) parse_kernel(const __grid_
     __shared__ typename Format<FMT>::Shared fsh;
 
     const int tid = threadIdx.x;
-    const int first = blockIdx.x * kLinesPerCta;
-    const int last = min(P.n, first + kLinesPerCta);
+    const int first = blockIdx.x * LINES;
+    const int last = min(P.n, first + LINES);
     if (tid == 0) mbar_init(&mbar, 1);
     Format<FMT>::init_shared(fsh);
     __syncthreads();
@@ -258,7 +258,7 @@ cudaError_t configure_kernels(int max_tile_bytes) {
         cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);
         if (e1 != cudaSuccess) return e1;
     }
-    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0, true, kRfc5424CtasPerSm, kRfc5424LinesPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
@@ -268,12 +268,13 @@ cudaError_t configure_kernels(int max_tile_bytes) {
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    const int grid = (p.n + kLinesPerCta - 1) / kLinesPerCta;
+    const int lines = lines_per_cta(fmt);
+    const int grid = (p.n + lines - 1) / lines;
     static const int minb = [] { const char* e = getenv("FG_MINB"); return e ? atoi(e) : 0; }();  // experiment switch (profiles/minb_sweep.sh)
     switch (fmt) {
         case 0:
-            if (p.tile_bytes > 0) parse_kernel<0, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
-            else parse_kernel<0, false><<<grid, kLinesPerCta, 0, stream>>>(p);  // experiment switch FG_FORCE_UNSTAGED
+            if (p.tile_bytes > 0) parse_kernel<0, true, kRfc5424CtasPerSm, kRfc5424LinesPerCta><<<grid, kRfc5424LinesPerCta, p.tile_bytes, stream>>>(p);
+            else parse_kernel<0, false, kRfc5424CtasPerSm, kRfc5424LinesPerCta><<<grid, kRfc5424LinesPerCta, 0, stream>>>(p);  // experiment switch FG_FORCE_UNSTAGED
             break;
         case 1:
             if (p.tile_bytes > 0) parse_kernel<1, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);

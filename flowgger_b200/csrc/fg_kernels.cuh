@@ -55,6 +55,10 @@ constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (ti
 // GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 16 CTAs/SM at 32
 // registers beat 12 at 40 and 7 at 72 (10.5 / 10.9 / 12.3 ms per 3.5 M lines); LTSV is the opposite (5.8 -> 8.8 ms: L1 working set)
 constexpr int kGelfUnstagedCtasPerSm = 16;
+// RFC5424 (short lines, staged tile): 64-line CTAs at 14 per SM — same warps/SM, tile waits and barriers half as wide
+constexpr int kRfc5424LinesPerCta = 64;
+constexpr int kRfc5424CtasPerSm = 14;
+constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : kLinesPerCta; }
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes);

@@ -16,6 +16,7 @@
 // All 32 lanes of a warp MUST call rfc5424_parse_line (idle lanes with len = 0).
 #pragma once
 #include "fg_common.cuh"
+#include "fg_kernels.cuh"
 #include "fg_status.h"
 
 namespace fg {
@@ -123,11 +124,11 @@ FG_DEV void r5_unpack(unsigned long long v, int line_off, int2& name, unsigned l
 
 // Per-CTA scratch in shared memory used by the RFC5424 parser
 struct R5Shared {
-    int marks[6][128];  // [space index][thread]: positions of the first six spaces
+    int marks[6][kRfc5424LinesPerCta];  // [space index][thread]: positions of the first six spaces
 };
 
 // p: line bytes (shared memory, or global for oversized lines); len may be 0 for idle lanes.
-// marks: &sh.marks[0][threadIdx.x] (stride 128 ints between slots).
+// marks: &sh.marks[0][threadIdx.x] (stride kRfc5424LinesPerCta ints between slots).
 FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, bool in_smem, LineResult& r,
                                const EntrySink& sink) {
     r.ts = 0.0;
@@ -163,7 +164,7 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
                              (swar_nibble(swar_eq(v.z, 0x20202020u)) << 8) | (swar_nibble(swar_eq(v.w, 0x20202020u)) << 12);
                 if (k == 0) m &= 0xFFFFu << s0;
                 while (m != 0 && nsp < 6) {
-                    marks[nsp * 128] = b + 16 * k + (__ffs((int)m) - 1) - (int)s0;
+                    marks[nsp * kRfc5424LinesPerCta] = b + 16 * k + (__ffs((int)m) - 1) - (int)s0;
                     ++nsp;
                     m &= m - 1;
                 }
@@ -176,12 +177,12 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
     {
         // marks past the end of the line come from the bytes after it in the last word: drop them
         int v;
-        v = nsp > 0 ? marks[0 * 128] : len; sp0 = v < len ? v : len;
-        v = nsp > 1 ? marks[1 * 128] : len; sp1 = v < len ? v : len;
-        v = nsp > 2 ? marks[2 * 128] : len; sp2 = v < len ? v : len;
-        v = nsp > 3 ? marks[3 * 128] : len; sp3 = v < len ? v : len;
-        v = nsp > 4 ? marks[4 * 128] : len; sp4 = v < len ? v : len;
-        v = nsp > 5 ? marks[5 * 128] : len; sp5 = v < len ? v : len;
+        v = nsp > 0 ? marks[0 * kRfc5424LinesPerCta] : len; sp0 = v < len ? v : len;
+        v = nsp > 1 ? marks[1 * kRfc5424LinesPerCta] : len; sp1 = v < len ? v : len;
+        v = nsp > 2 ? marks[2 * kRfc5424LinesPerCta] : len; sp2 = v < len ? v : len;
+        v = nsp > 3 ? marks[3 * kRfc5424LinesPerCta] : len; sp3 = v < len ? v : len;
+        v = nsp > 4 ? marks[4 * kRfc5424LinesPerCta] : len; sp4 = v < len ? v : len;
+        v = nsp > 5 ? marks[5 * kRfc5424LinesPerCta] : len; sp5 = v < len ? v : len;
         nsp = (sp0 < len) + (sp1 < len) + (sp2 < len) + (sp3 < len) + (sp4 < len) + (sp5 < len);
     }
     __syncwarp();
