@@ -421,8 +421,12 @@ def main() -> None:
     res = dec.download()
     n_err = int((res.status != 0).sum())
     n_entries = res.n_entries
-    used_cols = 9 if fmt == 0 else 6
-    b_write = n * (12 + 8 * (used_cols - 2)) + n_entries * 17
+    if fmt == 0:
+        # compact results: 32-byte row per line + 8-byte side-table rows + the arena of unescaped values (+ rare wide rows)
+        n_entries = int(res.raw.n_entries8)
+        b_write = n * 32 + n_entries * 8 + int(res.raw.arena_bytes) + int(res.raw.n_wide) * 72 + int(res.n_entries) * 17
+    else:
+        b_write = n * (12 + 8 * 4) + n_entries * 17
     d2h_bytes = b_write
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------

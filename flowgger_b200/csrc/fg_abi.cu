@@ -75,6 +75,8 @@ struct ErrorTableInit {
 constexpr size_t kPad = 256;            // slack after the device byte buffer (16-byte bulk-copy granules)
 constexpr size_t kBounceBytes = 32u << 20;  // pinned bounce buffers for pageable caller memory
 constexpr size_t kL2FlushBytes = 256u << 20;
+constexpr int kCnt = 8;                 // u32 counters snapshotted per chunk (fg::K5_* + the bad-offsets flag)
+constexpr int kBadFlag = 6;             // d_k[kBadFlag]: set by check_offsets_kernel
 
 }  // namespace
 
@@ -84,19 +86,40 @@ struct fg_ctx {
     int max_lines = 0;
     int chunk_lines = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
-    // device
+    // device: input
     uint8_t* d_bytes = nullptr;
     int32_t* d_offsets = nullptr;
-    uint8_t* d_rows = nullptr;  // 9 columns, each sized for max_lines
+    uint32_t* d_k = nullptr;  // counter block (fg::K5_* ; [kBadFlag] = offsets check)
+    uint8_t* d_flush = nullptr;
+    // LTSV / GELF: columnar rows (9 columns sized for max_lines) + 17-byte side-table rows + scratch.
+    // The side-table arrays also hold the rows of the RFC5424 wide lines.
+    uint8_t* d_rows = nullptr;
+    uint8_t* h_rows = nullptr;
     int2* d_entry_name = nullptr;
     unsigned long long* d_entry_val = nullptr;
     uint8_t* d_entry_meta = nullptr;
-    uint32_t* d_counter = nullptr;
-    uint8_t* d_flush = nullptr;
+    fg_span* h_entry_name = nullptr;
+    uint64_t* h_entry_val = nullptr;
+    uint8_t* h_entry_meta = nullptr;
+    size_t entry_cap = 0;
     int2* d_tmp_name = nullptr;  // provisional side-table rows, indexed by byte offset / scratch_div
     unsigned long long* d_tmp_val = nullptr;
     uint8_t* d_tmp_meta = nullptr;
     size_t tmp_cap = 0;
+    // RFC5424: compact rows, 8-byte entries, work lists, arena, wide rows
+    uint4* d_rows5 = nullptr;
+    fg_row5424* h_rows5 = nullptr;
+    unsigned long long* d_e8 = nullptr;
+    uint64_t* h_e8 = nullptr;
+    size_t e8_cap = 0;
+    uint32_t* d_esc_list = nullptr;
+    uint32_t* d_wide_list = nullptr;
+    uint8_t* d_arena = nullptr;
+    uint8_t* h_arena = nullptr;
+    size_t arena_cap = 0;
+    fg::WideRow* d_wide = nullptr;
+    fg_wide_row* h_wide = nullptr;
+    size_t wide_cap = 0;
     // split mode (fg_split_decode)
     uint32_t* d_seg = nullptr;
     int32_t* d_n_lines = nullptr;
@@ -109,16 +132,11 @@ struct fg_ctx {
     std::vector<cudaEvent_t> ev_split;
     int32_t* d_cum = nullptr;
     int32_t* h_cum = nullptr;
-    size_t entry_cap = 0;
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
     fg::LtsvDeviceConfig ltsv{};
     // pinned host
-    uint8_t* h_rows = nullptr;
-    fg_span* h_entry_name = nullptr;
-    uint64_t* h_entry_val = nullptr;
-    uint8_t* h_entry_meta = nullptr;
-    uint32_t* h_counts = nullptr;  // per-chunk running entry totals
+    uint32_t* h_counts = nullptr;  // per-chunk snapshots of the counter block (kCnt words each)
     int h_counts_cap = 0;
     uint8_t* h_bounce[2] = {nullptr, nullptr};
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
@@ -127,26 +145,24 @@ struct fg_ctx {
     // resident batch
     int res_n = 0;
     size_t res_bytes = 0;
-    int res_tile = 0;
     int res_fmt = -1;
-    uint32_t res_entries = 0;
+    uint32_t res_tot[kCnt] = {};
     std::string last_error;
     int64_t launches = 0;
-    int max_tile = 0;
+    int max_tile = 0;   // LTSV / GELF staging tile limit
+    int max_tile5 = 0;  // RFC5424: tile + bitmap must fit the opt-in shared memory
 };
 
 namespace {
 
+constexpr int kColW[9] = {8, 4, 8, 8, 8, 8, 8, 8, 8};  // ts(8) meta(4) host app proc msgid msg full sd (8 each)
+enum { C_TS = 0, C_META, C_HOST, C_APP, C_PROC, C_MSGID, C_MSG, C_FULL, C_SD, C_COUNT };
 size_t col_off(const fg_ctx* c, int col) {
-    // ts(8) meta(4) host app proc msgid msg full sd (8 each)
     const size_t n = (size_t)c->max_lines;
-    static const int w[9] = {8, 4, 8, 8, 8, 8, 8, 8, 8};
     size_t o = 0;
-    for (int k = 0; k < col; ++k) o += (size_t)w[k] * n;
+    for (int k = 0; k < col; ++k) o += (size_t)kColW[k] * n;
     return o;
 }
-constexpr int kColW[9] = {8, 4, 8, 8, 8, 8, 8, 8, 8};
-enum { C_TS = 0, C_META, C_HOST, C_APP, C_PROC, C_MSGID, C_MSG, C_FULL, C_SD, C_COUNT };
 
 int fail(fg_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (c) {
@@ -165,23 +181,22 @@ int fail(fg_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
         if (_e != cudaSuccess) return fail(ctx, FG_E_CUDA, #call, _e); \
     } while (0)
 
-void free_entries(fg_ctx* c) {
-    if (c->d_entry_name) cudaFree(c->d_entry_name);
-    if (c->d_entry_val) cudaFree(c->d_entry_val);
-    if (c->d_entry_meta) cudaFree(c->d_entry_meta);
-    if (c->h_entry_name) cudaFreeHost(c->h_entry_name);
-    if (c->h_entry_val) cudaFreeHost(c->h_entry_val);
-    if (c->h_entry_meta) cudaFreeHost(c->h_entry_meta);
-    c->d_entry_name = nullptr;
-    c->d_entry_val = nullptr;
-    c->d_entry_meta = nullptr;
-    c->h_entry_name = nullptr;
-    c->h_entry_val = nullptr;
-    c->h_entry_meta = nullptr;
+template <class T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+template <class T>
+void hfree(T*& p) {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
 }
 
+// 17-byte side-table rows (LTSV / GELF, RFC5424 wide lines)
 int alloc_entries(fg_ctx* c, size_t cap) {
-    free_entries(c);
+    dfree(c->d_entry_name); dfree(c->d_entry_val); dfree(c->d_entry_meta);
+    hfree(c->h_entry_name); hfree(c->h_entry_val); hfree(c->h_entry_meta);
+    c->entry_cap = 0;
     cap = (cap + 255) & ~(size_t)255;
     FG_CUDA(c, cudaMalloc(&c->d_entry_name, cap * sizeof(int2)));
     FG_CUDA(c, cudaMalloc(&c->d_entry_val, cap * sizeof(unsigned long long)));
@@ -192,42 +207,142 @@ int alloc_entries(fg_ctx* c, size_t cap) {
     c->entry_cap = cap;
     return FG_OK;
 }
-
-// Scratch table for provisional side-table rows, indexed by byte offset (see Format<>::scratch_index):
-// a row needs >= 3 input bytes in RFC5424 / GELF, >= 1 byte + its TAB in LTSV.  Allocated on first use of a format.
-int ensure_scratch(fg_ctx* c, int fmt) {
-    const size_t need = (fmt == FG_FMT_LTSV ? c->max_bytes / 2 + (size_t)c->max_lines : c->max_bytes / 3) + 64;
-    if (c->tmp_cap >= need) return FG_OK;
-    if (c->d_tmp_name) cudaFree(c->d_tmp_name);
-    if (c->d_tmp_val) cudaFree(c->d_tmp_val);
-    if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
-    c->d_tmp_name = nullptr;
-    c->d_tmp_val = nullptr;
-    c->d_tmp_meta = nullptr;
-    c->tmp_cap = 0;
-    FG_CUDA(c, cudaMalloc(&c->d_tmp_name, need * sizeof(int2)));
-    FG_CUDA(c, cudaMalloc(&c->d_tmp_val, need * sizeof(unsigned long long)));
-    FG_CUDA(c, cudaMalloc(&c->d_tmp_meta, need));
-    c->tmp_cap = need;
+int alloc_e8(fg_ctx* c, size_t cap) {
+    dfree(c->d_e8); hfree(c->h_e8);
+    c->e8_cap = 0;
+    cap = (cap + 255) & ~(size_t)255;
+    FG_CUDA(c, cudaMalloc(&c->d_e8, cap * 8));
+    FG_CUDA(c, cudaHostAlloc(&c->h_e8, cap * 8, cudaHostAllocDefault));
+    c->e8_cap = cap;
+    return FG_OK;
+}
+int alloc_arena(fg_ctx* c, size_t cap) {
+    dfree(c->d_arena); hfree(c->h_arena);
+    c->arena_cap = 0;
+    cap = (cap + 255) & ~(size_t)255;
+    FG_CUDA(c, cudaMalloc(&c->d_arena, cap));
+    FG_CUDA(c, cudaHostAlloc(&c->h_arena, cap, cudaHostAllocDefault));
+    c->arena_cap = cap;
+    return FG_OK;
+}
+int alloc_wide(fg_ctx* c, size_t cap) {
+    dfree(c->d_wide); hfree(c->h_wide);
+    c->wide_cap = 0;
+    FG_CUDA(c, cudaMalloc(&c->d_wide, cap * sizeof(fg::WideRow)));
+    FG_CUDA(c, cudaHostAlloc(&c->h_wide, cap * sizeof(fg_wide_row), cudaHostAllocDefault));
+    c->wide_cap = cap;
     return FG_OK;
 }
 
-// shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles
-// whatever does not fit in extra rounds
-int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt = 0) {
-    double mean = n > 0 ? (double)total_bytes / n : 0.0;
+// Format-specific buffers are allocated on first use of the format.
+int ensure_format(fg_ctx* c, int fmt) {
+    if (fmt == FG_FMT_RFC5424) {
+        if (!c->d_rows5) {
+            FG_CUDA(c, cudaMalloc(&c->d_rows5, (size_t)c->max_lines * 32));
+            FG_CUDA(c, cudaHostAlloc(&c->h_rows5, (size_t)c->max_lines * 32, cudaHostAllocDefault));
+            FG_CUDA(c, cudaMalloc(&c->d_esc_list, (size_t)c->max_lines * 4));
+            FG_CUDA(c, cudaMalloc(&c->d_wide_list, (size_t)c->max_lines * 4));
+        }
+        if (!c->e8_cap)
+            if (int rc = alloc_e8(c, std::max<size_t>(c->max_bytes / 24, 4096))) return rc;
+        if (!c->arena_cap)
+            if (int rc = alloc_arena(c, std::max<size_t>(c->max_bytes / 64, 64 << 10))) return rc;
+        if (!c->wide_cap)
+            if (int rc = alloc_wide(c, 1024)) return rc;
+        if (!c->entry_cap)
+            if (int rc = alloc_entries(c, 4096)) return rc;
+        return FG_OK;
+    }
+    if (!c->d_rows) {
+        const size_t rows_bytes = col_off(c, C_COUNT);
+        FG_CUDA(c, cudaMalloc(&c->d_rows, rows_bytes));
+        FG_CUDA(c, cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
+    }
+    const size_t want = std::max<size_t>(c->max_bytes / 24, 4096);
+    if (c->entry_cap < want)
+        if (int rc = alloc_entries(c, want)) return rc;
+    // Scratch table for provisional side-table rows, indexed by byte offset (see Format<>::scratch_index):
+    // a row needs >= 3 input bytes in GELF, >= 1 byte + its TAB in LTSV.
+    const size_t need = (fmt == FG_FMT_LTSV ? c->max_bytes / 2 + (size_t)c->max_lines : c->max_bytes / 3) + 64;
+    if (c->tmp_cap < need) {
+        dfree(c->d_tmp_name); dfree(c->d_tmp_val); dfree(c->d_tmp_meta);
+        c->tmp_cap = 0;
+        FG_CUDA(c, cudaMalloc(&c->d_tmp_name, need * sizeof(int2)));
+        FG_CUDA(c, cudaMalloc(&c->d_tmp_val, need * sizeof(unsigned long long)));
+        FG_CUDA(c, cudaMalloc(&c->d_tmp_meta, need));
+        c->tmp_cap = need;
+    }
+    return FG_OK;
+}
+
+// shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles whatever does not fit in extra rounds
+int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
+    const double mean = n > 0 ? (double)total_bytes / n : 0.0;
     // long-line formats: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
-    if (fmt != FG_FMT_RFC5424 && mean > 256.0 && getenv("FG_FORCE_STAGE") == nullptr) return 0;
-    if (getenv("FG_FORCE_UNSTAGED") != nullptr) return 0;  // experiment: every format reads through L1
+    if (fmt != FG_FMT_RFC5424 && mean > 256.0) return 0;
     const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
     long t = (long)(mean * lines * 1.10) + gran;
     t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
-    t = std::min(t, (long)c->max_tile);
+    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : c->max_tile));
     return (int)t;
 }
 
-void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
+// tables whose fill level the kernels report in the counter block
+bool tables_overflow(const fg_ctx* c, int fmt, const uint32_t* t) {
+    if (fmt == FG_FMT_RFC5424)
+        return t[fg::K5_ENTRIES] > c->e8_cap || t[fg::K5_ARENA] > c->arena_cap || t[fg::K5_WIDE_ROWS] > c->wide_cap ||
+               t[fg::K5_WIDE_ENTRIES] > c->entry_cap;
+    return t[fg::K5_ENTRIES] > c->entry_cap;
+}
+int regrow_tables(fg_ctx* c, int fmt, const uint32_t* t) {
+    auto grown = [](size_t need) { return need + need / 8 + 1024; };
+    if (fmt == FG_FMT_RFC5424) {
+        if (t[fg::K5_ENTRIES] > c->e8_cap)
+            if (int rc = alloc_e8(c, grown(t[fg::K5_ENTRIES]))) return rc;
+        if (t[fg::K5_ARENA] > c->arena_cap)
+            if (int rc = alloc_arena(c, grown(t[fg::K5_ARENA]))) return rc;
+        if (t[fg::K5_WIDE_ROWS] > c->wide_cap)
+            if (int rc = alloc_wide(c, grown(t[fg::K5_WIDE_ROWS]))) return rc;
+        if (t[fg::K5_WIDE_ENTRIES] > c->entry_cap)
+            if (int rc = alloc_entries(c, grown(t[fg::K5_WIDE_ENTRIES]))) return rc;
+        return FG_OK;
+    }
+    return alloc_entries(c, grown(t[fg::K5_ENTRIES]));
+}
+
+// One parse launch over lines [line0, line0 + n) of the resident offsets (for RFC5424: parse + unescape + wide kernels)
+int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* invalid, int strip_eol, cudaStream_t s) {
+    if (fmt == FG_FMT_RFC5424) {
+        fg::Parse5424Params P;
+        P.bytes = c->d_bytes;
+        P.offsets = c->d_offsets + line0;
+        P.n = n;
+        P.tile_bytes = tile;
+        P.rows = c->d_rows5 + 2 * (size_t)line0;
+        P.entries = c->d_e8;
+        P.entry_cap = (uint32_t)std::min<size_t>(c->e8_cap, 0xFFFFFFFFu);
+        P.counters = c->d_k;
+        P.esc_list = c->d_esc_list;
+        P.wide_list = c->d_wide_list;
+        P.arena = c->d_arena;
+        P.arena_cap = (uint32_t)std::min<size_t>(c->arena_cap, 0xFFFFFFFFu);
+        P.wide_rows = c->d_wide;
+        P.wide_cap = (uint32_t)c->wide_cap;
+        P.wentry_name = c->d_entry_name;
+        P.wentry_val = c->d_entry_val;
+        P.wentry_meta = c->d_entry_meta;
+        P.wentry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
+        P.line0 = line0;
+        P.bad_offsets = c->d_k + kBadFlag;
+        P.line_invalid = invalid;
+        P.strip_eol = strip_eol;
+        FG_CUDA(c, cudaMemsetAsync(c->d_k + fg::K5_ESC_LIST, 0, 8, s));  // the two work lists are per launch
+        FG_CUDA(c, fg::launch_parse5424(P, s));
+        c->launches += 3;
+        return FG_OK;
+    }
+    fg::ParseParams P;
     P.bytes = c->d_bytes;
     P.offsets = c->d_offsets + line0;
     P.n = n;
@@ -249,40 +364,51 @@ void fill_params(fg_ctx* c, fg::ParseParams& P, int line0, int n, int tile) {
     P.tmp_name = c->d_tmp_name;
     P.tmp_val = c->d_tmp_val;
     P.tmp_meta = c->d_tmp_meta;
-    P.line_invalid = nullptr;
-    P.strip_eol = 0;
-    P.entry_counter = c->d_counter;
+    P.line_invalid = invalid;
+    P.strip_eol = strip_eol;
+    P.entry_counter = c->d_k + fg::K5_ENTRIES;
     P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
+    P.bad_offsets = c->d_k + kBadFlag;
     P.ltsv = c->ltsv;
+    FG_CUDA(c, fg::launch_parse(fmt, P, s));
+    ++c->launches;
+    return FG_OK;
 }
 
-bool col_used(int fmt, int col) {
-    if (fmt == FG_FMT_RFC5424) return true;
-    return !(col == C_APP || col == C_PROC || col == C_MSGID);
-}
+bool col_used(int col) { return !(col == C_APP || col == C_PROC || col == C_MSGID); }  // LTSV / GELF have no such fields
 
-void fill_out(fg_ctx* c, int fmt, int n, uint32_t n_entries, fg_batch_out* out) {
-    uint8_t* r = c->h_rows;
+void fill_out(fg_ctx* c, int fmt, int n, const uint32_t* tot, fg_batch_out* out) {
     out->n = n;
-    out->n_entries = (int32_t)n_entries;
-    out->ts = (const double*)(r + col_off(c, C_TS));
-    out->meta = (const uint32_t*)(r + col_off(c, C_META));
-    out->hostname = (const fg_span*)(r + col_off(c, C_HOST));
-    const bool r5 = fmt == FG_FMT_RFC5424;
-    out->appname = r5 ? (const fg_span*)(r + col_off(c, C_APP)) : nullptr;
-    out->procid = r5 ? (const fg_span*)(r + col_off(c, C_PROC)) : nullptr;
-    out->msgid = r5 ? (const fg_span*)(r + col_off(c, C_MSGID)) : nullptr;
-    out->msg = (const fg_span*)(r + col_off(c, C_MSG));
-    out->full_msg = (const fg_span*)(r + col_off(c, C_FULL));
-    out->sd = (const fg_span*)(r + col_off(c, C_SD));
     out->entry_name = c->h_entry_name;
     out->entry_val = c->h_entry_val;
     out->entry_meta = c->h_entry_meta;
+    if (fmt == FG_FMT_RFC5424) {
+        out->n_entries = (int32_t)tot[fg::K5_WIDE_ENTRIES];
+        out->rows5424 = c->h_rows5;
+        out->entries8 = c->h_e8;
+        out->n_entries8 = (int32_t)tot[fg::K5_ENTRIES];
+        out->n_wide = (int32_t)tot[fg::K5_WIDE_ROWS];
+        out->wide_rows = c->h_wide;
+        out->arena = c->h_arena;
+        out->arena_bytes = (int64_t)tot[fg::K5_ARENA];
+        return;
+    }
+    uint8_t* r = c->h_rows;
+    out->n_entries = (int32_t)tot[fg::K5_ENTRIES];
+    out->ts = (const double*)(r + col_off(c, C_TS));
+    out->meta = (const uint32_t*)(r + col_off(c, C_META));
+    out->hostname = (const fg_span*)(r + col_off(c, C_HOST));
+    out->msg = (const fg_span*)(r + col_off(c, C_MSG));
+    out->full_msg = (const fg_span*)(r + col_off(c, C_FULL));
+    out->sd = (const fg_span*)(r + col_off(c, C_SD));
 }
 
 int copy_rows_d2h(fg_ctx* c, int fmt, int line0, int n, cudaStream_t s) {
-    static const bool skip = getenv("FG_DEBUG_SKIP_D2H") != nullptr;  // diagnostic only (profiles/r1_notes.md, e2e)
-    if (skip || n <= 0) return FG_OK;
+    if (n <= 0) return FG_OK;
+    if (fmt == FG_FMT_RFC5424) {
+        FG_CUDA(c, cudaMemcpyAsync(c->h_rows5 + line0, c->d_rows5 + 2 * (size_t)line0, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+        return FG_OK;
+    }
     // ts and meta: one copy each; the 8-byte span columns share one pitch (8 * max_lines), so every run of consecutive
     // used span columns goes back as ONE 2-D copy (few large D2H operations disturb the concurrent H2D stream less)
     for (int col = C_TS; col <= C_META; ++col) {
@@ -292,9 +418,9 @@ int copy_rows_d2h(fg_ctx* c, int fmt, int line0, int n, cudaStream_t s) {
     const size_t pitch = (size_t)c->max_lines * 8;
     int col = C_HOST;
     while (col < C_COUNT) {
-        if (!col_used(fmt, col)) { ++col; continue; }
+        if (!col_used(col)) { ++col; continue; }
         int end = col;
-        while (end + 1 < C_COUNT && col_used(fmt, end + 1)) ++end;
+        while (end + 1 < C_COUNT && col_used(end + 1)) ++end;
         const size_t o = col_off(c, col) + (size_t)line0 * 8;
         FG_CUDA(c, cudaMemcpy2DAsync(c->h_rows + o, pitch, c->d_rows + o, pitch, (size_t)n * 8, (size_t)(end - col + 1),
                                      cudaMemcpyDeviceToHost, s));
@@ -303,14 +429,28 @@ int copy_rows_d2h(fg_ctx* c, int fmt, int line0, int n, cudaStream_t s) {
     return FG_OK;
 }
 
-int copy_entries_d2h(fg_ctx* c, size_t from, size_t to, cudaStream_t s) {
-    static const bool skip = getenv("FG_DEBUG_SKIP_D2H") != nullptr;
-    if (to <= from || skip) return FG_OK;
+int copy_entries_range(fg_ctx* c, size_t from, size_t to, cudaStream_t s) {
+    if (to <= from) return FG_OK;
     const size_t k = to - from;
     FG_CUDA(c, cudaMemcpyAsync(c->h_entry_name + from, c->d_entry_name + from, k * sizeof(int2), cudaMemcpyDeviceToHost, s));
     FG_CUDA(c, cudaMemcpyAsync(c->h_entry_val + from, c->d_entry_val + from, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     FG_CUDA(c, cudaMemcpyAsync(c->h_entry_meta + from, c->d_entry_meta + from, k, cudaMemcpyDeviceToHost, s));
     return FG_OK;
+}
+
+// side tables: the rows a chunk produced are the contiguous range [prev, cur) of each bump allocator
+int copy_tables_d2h(fg_ctx* c, int fmt, const uint32_t* prev, const uint32_t* cur, cudaStream_t s) {
+    if (fmt != FG_FMT_RFC5424) return copy_entries_range(c, prev[fg::K5_ENTRIES], cur[fg::K5_ENTRIES], s);
+    if (cur[fg::K5_ENTRIES] > prev[fg::K5_ENTRIES])
+        FG_CUDA(c, cudaMemcpyAsync(c->h_e8 + prev[fg::K5_ENTRIES], c->d_e8 + prev[fg::K5_ENTRIES],
+                                   (size_t)(cur[fg::K5_ENTRIES] - prev[fg::K5_ENTRIES]) * 8, cudaMemcpyDeviceToHost, s));
+    if (cur[fg::K5_ARENA] > prev[fg::K5_ARENA])
+        FG_CUDA(c, cudaMemcpyAsync(c->h_arena + prev[fg::K5_ARENA], c->d_arena + prev[fg::K5_ARENA],
+                                   (size_t)(cur[fg::K5_ARENA] - prev[fg::K5_ARENA]), cudaMemcpyDeviceToHost, s));
+    if (cur[fg::K5_WIDE_ROWS] > prev[fg::K5_WIDE_ROWS])
+        FG_CUDA(c, cudaMemcpyAsync(c->h_wide + prev[fg::K5_WIDE_ROWS], c->d_wide + prev[fg::K5_WIDE_ROWS],
+                                   (size_t)(cur[fg::K5_WIDE_ROWS] - prev[fg::K5_WIDE_ROWS]) * sizeof(fg_wide_row), cudaMemcpyDeviceToHost, s));
+    return copy_entries_range(c, prev[fg::K5_WIDE_ENTRIES], cur[fg::K5_WIDE_ENTRIES], s);
 }
 
 bool is_pinned(const void* p) {
@@ -356,19 +496,21 @@ int ensure_events(fg_ctx* c, int chunks) {
         c->ev_cnt.push_back(e);
     }
     if (c->h_counts_cap < chunks) {
-        if (c->h_counts) cudaFreeHost(c->h_counts);
-        FG_CUDA(c, cudaHostAlloc(&c->h_counts, sizeof(uint32_t) * (size_t)chunks, cudaHostAllocDefault));
+        hfree(c->h_counts);
+        FG_CUDA(c, cudaHostAlloc(&c->h_counts, sizeof(uint32_t) * kCnt * (size_t)chunks, cudaHostAllocDefault));
         c->h_counts_cap = chunks;
     }
     return FG_OK;
 }
 
+// Cheap host-side checks; the interior of the offsets array is checked on the device (check_offsets_kernel) next to
+// the parse, so a non-monotone or out-of-range offset fails the call with FG_E_ARG instead of reaching a kernel.
 int check_batch(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {
     if (!c) return FG_E_ARG;
     if (n < 0 || (n > 0 && (!bytes || !offsets))) return fail(c, FG_E_ARG, "null input");
     if (n > c->max_lines) return fail(c, FG_E_CAPACITY, "batch has more lines than max_batch_lines");
     if (n > 0) {
-        if (offsets[0] < 0 || offsets[n] < offsets[0]) return fail(c, FG_E_ARG, "offsets must be non-negative and monotone");
+        if (offsets[0] < 0 || offsets[n] < offsets[0]) return fail(c, FG_E_ARG, "offsets must be non-negative and non-decreasing");
         if ((size_t)offsets[n] > c->max_bytes) return fail(c, FG_E_CAPACITY, "batch has more bytes than max_batch_bytes");
     }
     return FG_OK;
@@ -412,7 +554,8 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->device));
     c->max_tile = (int)std::min<size_t>(prop.sharedMemPerBlockOptin - 1024, 200 * 1024);
     c->max_tile &= ~1023;
-    FG_CREATE_CUDA(fg::configure_kernels(c->max_tile));
+    c->max_tile5 = (int)(((size_t)c->max_tile - 1024) * 8 / 9) & ~1023;  // tile + tile/8 bitmap + static shared memory
+    FG_CREATE_CUDA(fg::configure_kernels(c->max_tile, c->max_tile5));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
@@ -421,19 +564,11 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaMalloc(&c->d_bytes, c->max_bytes + kPad));
     FG_CREATE_CUDA(cudaMemset(c->d_bytes + c->max_bytes, 0, kPad));
     FG_CREATE_CUDA(cudaMalloc(&c->d_offsets, sizeof(int32_t) * ((size_t)c->max_lines + 1)));
-    const size_t rows_bytes = col_off(c, C_COUNT);
-    FG_CREATE_CUDA(cudaMalloc(&c->d_rows, rows_bytes));
-    FG_CREATE_CUDA(cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
-    FG_CREATE_CUDA(cudaMalloc(&c->d_counter, 256));
-    FG_CREATE_CUDA(cudaMemset(c->d_counter, 0, 256));
+    FG_CREATE_CUDA(cudaMalloc(&c->d_k, 256));
+    FG_CREATE_CUDA(cudaMemset(c->d_k, 0, 256));
     for (int b = 0; b < 2; ++b) {
         FG_CREATE_CUDA(cudaHostAlloc(&c->h_bounce[b], kBounceBytes, cudaHostAllocDefault));
         FG_CREATE_CUDA(cudaEventCreateWithFlags(&c->bounce_ev[b], cudaEventDisableTiming));
-    }
-    if (alloc_entries(c, std::max<size_t>(c->max_bytes / 24, 4096)) != FG_OK) {
-        fprintf(stderr, "flowgger_cuda: %s\n", c->last_error.c_str());
-        fg_destroy(c);
-        return FG_E_CUDA;
     }
     // LTSV schema / suffixes -> one device blob
     {
@@ -484,31 +619,23 @@ void fg_destroy(fg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    free_entries(c);
-    if (c->d_bytes) cudaFree(c->d_bytes);
-    if (c->d_offsets) cudaFree(c->d_offsets);
-    if (c->d_rows) cudaFree(c->d_rows);
-    if (c->d_counter) cudaFree(c->d_counter);
-    if (c->d_flush) cudaFree(c->d_flush);
-    if (c->d_seg) cudaFree(c->d_seg);
-    if (c->d_n_lines) cudaFree(c->d_n_lines);
-    if (c->d_invalid) cudaFree(c->d_invalid);
-    if (c->h_offsets) cudaFreeHost(c->h_offsets);
-    if (c->h_n_lines) cudaFreeHost(c->h_n_lines);
+    dfree(c->d_entry_name); dfree(c->d_entry_val); dfree(c->d_entry_meta);
+    hfree(c->h_entry_name); hfree(c->h_entry_val); hfree(c->h_entry_meta);
+    dfree(c->d_bytes); dfree(c->d_offsets); dfree(c->d_rows); dfree(c->d_k); dfree(c->d_flush);
+    dfree(c->d_rows5); hfree(c->h_rows5); dfree(c->d_e8); hfree(c->h_e8); dfree(c->d_esc_list); dfree(c->d_wide_list);
+    dfree(c->d_arena); hfree(c->h_arena); dfree(c->d_wide); hfree(c->h_wide);
+    dfree(c->d_seg); dfree(c->d_n_lines); dfree(c->d_invalid);
+    hfree(c->h_offsets); hfree(c->h_n_lines);
     if (c->s_parse) cudaStreamDestroy(c->s_parse);
     for (auto e : c->ev_split) cudaEventDestroy(e);
-    if (c->d_cum) cudaFree(c->d_cum);
-    if (c->h_cum) cudaFreeHost(c->h_cum);
+    dfree(c->d_cum); hfree(c->h_cum);
     if (c->ev_s0) cudaEventDestroy(c->ev_s0);
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
-    if (c->d_tmp_name) cudaFree(c->d_tmp_name);
-    if (c->d_tmp_val) cudaFree(c->d_tmp_val);
-    if (c->d_tmp_meta) cudaFree(c->d_tmp_meta);
-    if (c->d_ltsv_blob) cudaFree(c->d_ltsv_blob);
-    if (c->h_rows) cudaFreeHost(c->h_rows);
-    if (c->h_counts) cudaFreeHost(c->h_counts);
+    dfree(c->d_tmp_name); dfree(c->d_tmp_val); dfree(c->d_tmp_meta);
+    dfree(c->d_ltsv_blob);
+    hfree(c->h_rows); hfree(c->h_counts);
     for (int b = 0; b < 2; ++b) {
-        if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
+        hfree(c->h_bounce[b]);
         if (c->bounce_ev[b]) cudaEventDestroy(c->bounce_ev[b]);
     }
     for (auto e : c->ev_h2d) cudaEventDestroy(e);
@@ -541,10 +668,11 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
     if (int rc = check_batch(c, bytes, offsets, n)) return rc;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
-    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
+    if (int rc = ensure_format(c, (int)fmt)) return rc;
     memset(out, 0, sizeof *out);
+    const uint32_t zero[kCnt] = {};
     if (n == 0) {
-        fill_out(c, fmt, 0, 0, out);
+        fill_out(c, fmt, 0, zero, out);
         return FG_OK;
     }
     const auto t_begin = std::chrono::steady_clock::now();
@@ -554,51 +682,54 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
     if (int rc = ensure_events(c, chunks)) return rc;
     const int tile = pick_tile(c, (size_t)(offsets[n] - offsets[0]), n, (int)fmt);
     for (int attempt = 0; attempt < 2; ++attempt) {
-        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kCnt, c->s_comp));
         int bounce_ix = 0;
         for (int k = 0; k < chunks; ++k) {
             const int l0 = k * C, l1 = std::min(n, l0 + C);
             const size_t b0 = (size_t)offsets[l0], b1 = (size_t)offsets[l1];
+            if (b1 < b0 || b1 > c->max_bytes) {
+                cudaDeviceSynchronize();
+                return fail(c, FG_E_ARG, "offsets must be non-decreasing and within max_batch_bytes");
+            }
             if (int rc = h2d(c, c->d_bytes + b0, bytes + b0, b1 - b0, pin_b, bounce_ix)) return rc;
             if (int rc = h2d(c, c->d_offsets + l0, offsets + l0, sizeof(int32_t) * (size_t)(l1 - l0 + 1), pin_o, bounce_ix))
                 return rc;
             FG_CUDA(c, cudaEventRecord(c->ev_h2d[k], c->s_h2d));
             FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[k], 0));
-            fg::ParseParams P;
-            fill_params(c, P, l0, l1 - l0, tile);
+            FG_CUDA(c, fg::launch_check_offsets(c->d_offsets + l0, l1 - l0, (long long)c->max_bytes, c->d_k + kBadFlag, c->s_comp));
             FG_CUDA(c, cudaEventRecord(c->ev_k0[k], c->s_comp));
-            FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
-            ++c->launches;
+            if (int rc = launch_lines(c, (int)fmt, l0, l1 - l0, tile, nullptr, 0, c->s_comp)) return rc;
             FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));
-            FG_CUDA(c, cudaMemcpyAsync(c->h_counts + k, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_counts + (size_t)k * kCnt, c->d_k, sizeof(uint32_t) * kCnt, cudaMemcpyDeviceToHost, c->s_comp));
             FG_CUDA(c, cudaEventRecord(c->ev_cnt[k], c->s_comp));
             FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_cnt[k], 0));
             if (int rc = copy_rows_d2h(c, fmt, l0, l1 - l0, c->s_d2h)) return rc;
         }
-        // side table: chunk k's rows are the contiguous range [count(k-1), count(k)) of the bump allocator; each range is
+        // side tables: chunk k's rows are the contiguous range [count(k-1), count(k)) of each bump allocator; a range is
         // copied back as soon as its chunk has been parsed, while later chunks are still in flight
-        uint32_t copied = 0;
+        uint32_t prev[kCnt] = {};
         bool overflow = false;
         for (int k = 0; k < chunks; ++k) {
             FG_CUDA(c, cudaEventSynchronize(c->ev_cnt[k]));
-            const uint32_t upto = c->h_counts[k];
-            if ((size_t)upto > c->entry_cap) {
+            const uint32_t* cur = c->h_counts + (size_t)k * kCnt;
+            if (tables_overflow(c, (int)fmt, cur)) {
                 overflow = true;
                 continue;  // keep draining the events; the batch is redone below
             }
             if (!overflow) {
-                if (int rc = copy_entries_d2h(c, copied, upto, c->s_d2h)) return rc;
-                copied = upto;
+                if (int rc = copy_tables_d2h(c, (int)fmt, prev, cur, c->s_d2h)) return rc;
+                memcpy(prev, cur, sizeof prev);
             }
         }
-        const uint32_t total = c->h_counts[chunks - 1];
+        uint32_t total[kCnt];
+        memcpy(total, c->h_counts + (size_t)(chunks - 1) * kCnt, sizeof total);
+        FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+        if (total[kBadFlag]) return fail(c, FG_E_ARG, "offsets must be non-decreasing and within max_batch_bytes");
         if (overflow) {
-            // the allocator kept counting past the capacity: grow once to the exact need and redo
-            FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
-            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+            // the allocators kept counting past the capacity: grow once to the exact need and redo
+            if (int rc = regrow_tables(c, (int)fmt, total)) return rc;
             continue;
         }
-        FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
         float kms = 0.f;
         for (int k = 0; k < chunks; ++k) {
             float ms = 0.f;
@@ -610,7 +741,7 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
         out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         return FG_OK;
     }
-    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+    return fail(c, FG_E_CAPACITY, "side table overflow after regrow");
 }
 
 int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
@@ -619,7 +750,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
     if (nbytes < 0 || (nbytes > 0 && !stream)) return fail(c, FG_E_ARG, "null input");
     if ((size_t)nbytes > c->max_bytes) return fail(c, FG_E_CAPACITY, "stream has more bytes than max_batch_bytes");
     FG_CUDA(c, cudaSetDevice(c->device));
-    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
+    if (int rc = ensure_format(c, (int)fmt)) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
     constexpr long long kChunk = 64ll << 20;  // pipeline granularity in bytes (a multiple of the 8 KB framing segment)
     const int chunks = nbytes > 0 ? (int)((nbytes + kChunk - 1) / kChunk) : 1;
@@ -640,8 +771,8 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
             FG_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c->ev_split.push_back(e);
         }
-        if (c->d_cum) cudaFree(c->d_cum);
-        if (c->h_cum) cudaFreeHost(c->h_cum);
+        dfree(c->d_cum);
+        hfree(c->h_cum);
         FG_CUDA(c, cudaMalloc(&c->d_cum, sizeof(int32_t) * want));
         FG_CUDA(c, cudaHostAlloc(&c->h_cum, sizeof(int32_t) * want, cudaHostAllocDefault));
     }
@@ -653,7 +784,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
         // ---- enqueue, chunk by chunk: raw bytes -> HBM, then framing + UTF-8 validation of that chunk (no host dependency)
         FG_CUDA(c, cudaMemsetAsync(c->d_n_lines + 8, 0, 4, c->s_comp));  // running newline count (uint32 at d_n_lines[8])
         FG_CUDA(c, cudaMemsetAsync(c->d_invalid, 0, (size_t)c->max_lines, c->s_comp));
-        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
+        FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kCnt, c->s_comp));
         FG_CUDA(c, cudaEventRecord(c->ev_s0, c->s_comp));
         int bounce_ix = 0;
         for (int k = 0; k < chunks; ++k) {
@@ -679,8 +810,6 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
         int32_t n = 0;
         int nparse = 0;
         bool over = false;
-        const int tile = pick_tile(c, (size_t)nbytes, std::max<int32_t>(1, (int32_t)(nbytes / 180)), (int)fmt);  // refined per launch below
-        (void)tile;
         for (int k = 0; k < chunks; ++k) {
             const int dep = std::min(k + 1, chunks - 1);
             FG_CUDA(c, cudaEventSynchronize(c->ev_split[dep]));
@@ -693,17 +822,13 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
             }
             const int32_t cnt = upto - done_lines;
             if (cnt > 0) {
-                fg::ParseParams P;
                 const size_t span_bytes = (size_t)std::min<long long>(nbytes, (long long)(k + 1) * kChunk) - (size_t)((long long)k * kChunk);
-                fill_params(c, P, done_lines, cnt, pick_tile(c, std::max<size_t>(span_bytes, 1), cnt, (int)fmt));
-                P.line_invalid = c->d_invalid + done_lines;
-                P.strip_eol = 1;
+                const int tile = pick_tile(c, std::max<size_t>(span_bytes, 1), cnt, (int)fmt);
                 FG_CUDA(c, cudaStreamWaitEvent(c->s_parse, c->ev_split[dep], 0));
                 FG_CUDA(c, cudaEventRecord(c->ev_k0[nparse], c->s_parse));
-                FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_parse));
-                ++c->launches;
+                if (int rc = launch_lines(c, (int)fmt, done_lines, cnt, tile, c->d_invalid + done_lines, 1, c->s_parse)) return rc;
                 FG_CUDA(c, cudaEventRecord(c->ev_k1[nparse], c->s_parse));
-                FG_CUDA(c, cudaMemcpyAsync(c->h_counts + nparse, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_parse));
+                FG_CUDA(c, cudaMemcpyAsync(c->h_counts + (size_t)nparse * kCnt, c->d_k, sizeof(uint32_t) * kCnt, cudaMemcpyDeviceToHost, c->s_parse));
                 FG_CUDA(c, cudaEventRecord(c->ev_cnt[nparse], c->s_parse));
                 FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_cnt[nparse], 0));
                 if (int rc = copy_rows_d2h(c, fmt, done_lines, cnt, c->s_d2h)) return rc;
@@ -716,20 +841,21 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
             return fail(c, FG_E_CAPACITY, "stream has more lines than max_batch_lines");
         }
         // ---- side table ranges, line offsets
-        uint32_t copied = 0, total = 0;
+        uint32_t prev[kCnt] = {}, total[kCnt] = {};
         bool overflow = false;
         for (int j = 0; j < nparse; ++j) {
             FG_CUDA(c, cudaEventSynchronize(c->ev_cnt[j]));
-            total = c->h_counts[j];
-            if ((size_t)total > c->entry_cap) { overflow = true; continue; }
+            const uint32_t* cur = c->h_counts + (size_t)j * kCnt;
+            memcpy(total, cur, sizeof total);
+            if (tables_overflow(c, (int)fmt, cur)) { overflow = true; continue; }
             if (!overflow) {
-                if (int rc = copy_entries_d2h(c, copied, total, c->s_d2h)) return rc;
-                copied = total;
+                if (int rc = copy_tables_d2h(c, (int)fmt, prev, cur, c->s_d2h)) return rc;
+                memcpy(prev, cur, sizeof prev);
             }
         }
         if (overflow) {
             FG_CUDA(c, cudaDeviceSynchronize());
-            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+            if (int rc = regrow_tables(c, (int)fmt, total)) return rc;
             continue;
         }
         FG_CUDA(c, cudaStreamSynchronize(c->s_parse));
@@ -748,7 +874,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
         out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         return FG_OK;
     }
-    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+    return fail(c, FG_E_CAPACITY, "side table overflow after regrow");
 }
 
 int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n) {
@@ -762,8 +888,13 @@ int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n
     } else {
         c->res_bytes = 0;
     }
+    FG_CUDA(c, cudaMemset(c->d_k, 0, sizeof(uint32_t) * kCnt));
+    FG_CUDA(c, fg::launch_check_offsets(c->d_offsets, n, (long long)c->max_bytes, c->d_k + kBadFlag, c->s_comp));
+    uint32_t bad = 0;
+    FG_CUDA(c, cudaMemcpyAsync(&bad, c->d_k + kBadFlag, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
+    if (bad) return fail(c, FG_E_ARG, "offsets must be non-decreasing and within max_batch_bytes");
     c->res_n = n;
-    c->res_tile = pick_tile(c, c->res_bytes, n);
     c->res_fmt = -1;
     return FG_OK;
 }
@@ -772,30 +903,27 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     if (!c) return FG_E_ARG;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
-    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
+    if (int rc = ensure_format(c, (int)fmt)) return rc;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
-        fg::ParseParams P;
-        fill_params(c, P, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt));
+        FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kBadFlag, c->s_comp));
         FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
-        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
-        ++c->launches;
+        if (int rc = launch_lines(c, (int)fmt, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt), nullptr, 0, c->s_comp)) return rc;
         FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
-        uint32_t total = 0;
-        FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+        uint32_t total[kCnt] = {};
+        FG_CUDA(c, cudaMemcpyAsync(total, c->d_k, sizeof total, cudaMemcpyDeviceToHost, c->s_comp));
         FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
-        if ((size_t)total > c->entry_cap) {
-            if (int rc = alloc_entries(c, (size_t)total + (size_t)total / 8 + 1024)) return rc;
+        if (tables_overflow(c, (int)fmt, total)) {
+            if (int rc = regrow_tables(c, (int)fmt, total)) return rc;
             continue;
         }
         float ms = 0.f;
         FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
         if (kernel_ms) *kernel_ms = ms;
         c->res_fmt = (int)fmt;
-        c->res_entries = total;
+        memcpy(c->res_tot, total, sizeof total);
         return FG_OK;
     }
-    return fail(c, FG_E_CAPACITY, "structured-data table overflow after regrow");
+    return fail(c, FG_E_CAPACITY, "side table overflow after regrow");
 }
 
 // K back-to-back passes over the resident batch with ONE host synchronisation at the end (what bench.py times):
@@ -804,26 +932,25 @@ int fg_parse_resident_n(fg_ctx* c, fg_format fmt, int32_t k, float* total_ms) {
     if (!c || k < 1) return FG_E_ARG;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
-    if (int rc = ensure_scratch(c, (int)fmt)) return rc;
-    // the side table must already be large enough (one fg_parse_resident warm-up regrows it): checked after the loop
-    fg::ParseParams P;
-    fill_params(c, P, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt));
+    if (int rc = ensure_format(c, (int)fmt)) return rc;
+    // the side tables must already be large enough (one fg_parse_resident warm-up regrows them): checked after the loop
+    const int tile = pick_tile(c, c->res_bytes, c->res_n, (int)fmt);
     FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
     for (int32_t it = 0; it < k; ++it) {
-        FG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, 4, c->s_comp));
-        FG_CUDA(c, fg::launch_parse((int)fmt, P, c->s_comp));
-        ++c->launches;
+        FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kBadFlag, c->s_comp));
+        if (int rc = launch_lines(c, (int)fmt, 0, c->res_n, tile, nullptr, 0, c->s_comp)) return rc;
     }
     FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
-    uint32_t total = 0;
-    FG_CUDA(c, cudaMemcpyAsync(&total, c->d_counter, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    uint32_t total[kCnt] = {};
+    FG_CUDA(c, cudaMemcpyAsync(total, c->d_k, sizeof total, cudaMemcpyDeviceToHost, c->s_comp));
     FG_CUDA(c, cudaStreamSynchronize(c->s_comp));
-    if ((size_t)total > c->entry_cap) return fail(c, FG_E_CAPACITY, "side table too small: call fg_parse_resident once before fg_parse_resident_n");
+    if (tables_overflow(c, (int)fmt, total))
+        return fail(c, FG_E_CAPACITY, "side table too small: call fg_parse_resident once before fg_parse_resident_n");
     float ms = 0.f;
     FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
     if (total_ms) *total_ms = ms;
     c->res_fmt = (int)fmt;
-    c->res_entries = total;
+    memcpy(c->res_tot, total, sizeof total);
     return FG_OK;
 }
 
@@ -832,10 +959,11 @@ int fg_download(fg_ctx* c, fg_format fmt, fg_batch_out* out) {
     if (c->res_fmt != (int)fmt) return fail(c, FG_E_ARG, "no resident parse of this format to download");
     FG_CUDA(c, cudaSetDevice(c->device));
     memset(out, 0, sizeof *out);
+    const uint32_t zero[kCnt] = {};
     if (int rc = copy_rows_d2h(c, fmt, 0, c->res_n, c->s_d2h)) return rc;
-    if (int rc = copy_entries_d2h(c, 0, c->res_entries, c->s_d2h)) return rc;
+    if (int rc = copy_tables_d2h(c, (int)fmt, zero, c->res_tot, c->s_d2h)) return rc;
     FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
-    fill_out(c, fmt, c->res_n, c->res_entries, out);
+    fill_out(c, fmt, c->res_n, c->res_tot, out);
     return FG_OK;
 }
 

@@ -4,10 +4,9 @@
 // timestamp recipe (utils/mod.rs:24-28).  Never compile this with
 // --use_fast_math: the f64 conversion and division must be round-to-nearest.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
 
-#define FG_DEV __device__ __forceinline__
+#include "fg_simt.cuh"
 
 namespace fg {
 
@@ -305,6 +304,7 @@ FG_DEV bool parse_rfc3339(bytes_t p, int a, int b, double& ts) {
     return finish_datetime(t, leap, ts);
 }
 
+#ifndef FG_HOST_EMU
 // ---------------------------------------------------------------------------
 // small CTA-wide exclusive scan (blockDim.x <= 1024) used to place each line's
 // structured-data entries in the side table
@@ -336,5 +336,6 @@ FG_DEV uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [32] sme
     uint32_t r = warp_sums[wid] + x - v;
     return r;
 }
+#endif  // FG_HOST_EMU
 
 }  // namespace fg

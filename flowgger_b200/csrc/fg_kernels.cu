@@ -16,6 +16,7 @@
 #include "fg_kernels.cuh"
 
 #include "fg_common.cuh"
+#include "fg_tma.cuh"
 #include "fg_rfc5424.cuh"
 #include "fg_ltsv.cuh"
 #include "fg_gelf.cuh"
@@ -25,36 +26,6 @@
 #include <cstdlib>
 
 namespace fg {
-
-FG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-FG_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-FG_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-FG_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// global -> shared bulk copy through the TMA unit (1-D, 16-byte granules)
-FG_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-FG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // scratch table -> side table (loads first, then stores: independent L2 round trips in flight)
 FG_DEV void copy_rows(uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
@@ -77,33 +48,6 @@ FG_DEV void copy_rows(uint32_t src, uint32_t dst, uint32_t n, const EntrySink& s
 
 template <int FMT>
 struct Format;
-
-template <>
-struct Format<0> {  // RFC5424
-    typedef R5Shared Shared;
-    static FG_DEV void init_shared(Shared&) {}
-    static FG_DEV void parse(bytes_t p, int len, int line_off, int /*line_idx*/, bool /*active*/, bool in_smem, Shared& sh,
-                             LineResult& r, const EntrySink& tmp, const ParseParams&) {
-        rfc5424_parse_line(p, len, line_off, &sh.marks[0][threadIdx.x], in_smem, r, tmp);
-    }
-    // rows [0, stage_cap) were staged compactly in shared memory, the rest in the scratch table
-    static FG_DEV void expand(const LineResult& r, int line_off, uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink,
-                              const EntrySink& tmp) {
-        const uint32_t ns = n < r.stage_cap ? n : r.stage_cap;
-        for (uint32_t k = 0; k < ns; ++k) {
-            int2 nm;
-            unsigned long long v;
-            uint8_t m;
-            r5_unpack(r.stage[k], line_off, nm, v, m);
-            sink.name[dst + k] = nm;
-            sink.val[dst + k] = v;
-            sink.meta[dst + k] = m;
-        }
-        copy_rows(src + ns, dst + ns, n - ns, sink, tmp);
-    }
-    // an SD header needs >= 3 input bytes and a pair >= 4: rows of different lines never overlap
-    static FG_DEV uint32_t scratch_index(int line_off, int) { return (uint32_t)line_off / 3u; }
-};
 
 struct NoShared {};
 
@@ -151,6 +95,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse_kernel(const __grid_constan
     const int tid = threadIdx.x;
     const int first = blockIdx.x * LINES;
     const int last = min(P.n, first + LINES);
+    if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     Format<FMT>::init_shared(fsh);
     __syncthreads();
@@ -227,7 +172,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse_kernel(const __grid_constan
             P.ts[i] = res.ts;
             P.meta[i] = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);
             P.host[i] = make_int2(res.host_o >= 0 ? o0 + res.host_o : -1, res.host_l);
-            if (FMT == 0) {
+            if (false) {
                 P.app[i] = make_int2(res.app_o >= 0 ? o0 + res.app_o : -1, res.app_l);
                 P.proc[i] = make_int2(res.proc_o >= 0 ? o0 + res.proc_o : -1, res.proc_l);
                 P.msgid[i] = make_int2(res.mid_o >= 0 ? o0 + res.mid_o : -1, res.mid_l);
@@ -245,7 +190,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse_kernel(const __grid_constan
 
 static int g_max_tile = 48 * 1024;
 
-cudaError_t configure_kernels(int max_tile_bytes) {
+cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424) {
     g_max_tile = max_tile_bytes;
 
     {
@@ -258,7 +203,7 @@ cudaError_t configure_kernels(int max_tile_bytes) {
         cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);
         if (e1 != cudaSuccess) return e1;
     }
-    cudaError_t e = cudaFuncSetAttribute(parse_kernel<0, true, kRfc5424CtasPerSm, kRfc5424LinesPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    cudaError_t e = configure_parse5424(max_tile5424);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
@@ -266,24 +211,33 @@ cudaError_t configure_kernels(int max_tile_bytes) {
     return e;
 }
 
+__global__ void __launch_bounds__(256) check_offsets_kernel(const int32_t* __restrict__ offsets, int n, long long max_bytes,
+                                                           uint32_t* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const int a = offsets[i];
+    bool bad = a < 0 || (long long)a > max_bytes;
+    if (i < n) bad = bad || offsets[i + 1] < a;
+    if (bad) atomicOr(flag, 1u);
+}
+
+cudaError_t launch_check_offsets(const int32_t* d_offsets, int n, long long max_bytes, uint32_t* d_flag, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    check_offsets_kernel<<<(n + 1 + 255) / 256, 256, 0, stream>>>(d_offsets, n, max_bytes, d_flag);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int lines = lines_per_cta(fmt);
     const int grid = (p.n + lines - 1) / lines;
-    static const int minb = [] { const char* e = getenv("FG_MINB"); return e ? atoi(e) : 0; }();  // experiment switch (profiles/minb_sweep.sh)
     switch (fmt) {
-        case 0:
-            if (p.tile_bytes > 0) parse_kernel<0, true, kRfc5424CtasPerSm, kRfc5424LinesPerCta><<<grid, kRfc5424LinesPerCta, p.tile_bytes, stream>>>(p);
-            else parse_kernel<0, false, kRfc5424CtasPerSm, kRfc5424LinesPerCta><<<grid, kRfc5424LinesPerCta, 0, stream>>>(p);  // experiment switch FG_FORCE_UNSTAGED
-            break;
         case 1:
             if (p.tile_bytes > 0) parse_kernel<1, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
             else parse_kernel<1, false><<<grid, kLinesPerCta, 0, stream>>>(p);
             break;
         case 2:
             if (p.tile_bytes > 0) parse_kernel<2, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
-            else if (minb == 7) parse_kernel<2, false, 7><<<grid, kLinesPerCta, 0, stream>>>(p);
-            else if (minb == 12) parse_kernel<2, false, 12><<<grid, kLinesPerCta, 0, stream>>>(p);
             else parse_kernel<2, false, kGelfUnstagedCtasPerSm><<<grid, kLinesPerCta, 0, stream>>>(p);
             break;
         default: return cudaErrorInvalidValue;
@@ -292,8 +246,8 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
 }
 
 const char* kernel_build_info() {
-    return "flowgger_b200 parse kernels: sm_100a, thread-per-line over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse_kernel<rfc5424>, parse_kernel<ltsv>, parse_kernel<gelf>]";
+    return "flowgger_b200 parse kernels: sm_100a, RFC5424: structural bitmap + bit-walk over TMA-bulk-staged CTA tiles, "
+           "kernels=[parse5424_kernel, unescape5424_kernel, wide5424_kernel, parse_kernel<ltsv>, parse_kernel<gelf>]";
 }
 
 }  // namespace fg

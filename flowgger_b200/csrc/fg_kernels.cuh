@@ -1,7 +1,11 @@
 // fg_kernels.cuh — launch parameters shared by fg_kernels.cu and fg_abi.cu
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef FG_HOST_EMU
+#include "../../tests/emu/cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
 
 namespace fg {
 
@@ -47,8 +51,60 @@ struct ParseParams {
     int32_t strip_eol;
     uint32_t* entry_counter;  // running total (atomic bump, one add per CTA round)
     uint32_t entry_cap;
+    const uint32_t* bad_offsets;  // set by check_offsets_kernel when the offsets array is not monotone / in range: kernels do nothing
     LtsvDeviceConfig ltsv;
 };
+
+// ---- RFC5424 fast path (fg_parse5424.cu) ------------------------------------------------------------------------
+// compact row, 32 bytes per line (include/flowgger_cuda.h: fg_row5424)
+struct Row5424 {
+    double ts;
+    uint32_t meta;      // status | facility << 8 | severity << 16 | flags << 24
+    uint32_t sd_first;  // first 8-byte entry of this line (FG_FLAG_WIDE: index into the wide rows instead)
+    uint16_t sd_count;  // entries of this line (headers + pairs + extension rows)
+    uint16_t sp[5];     // spaces 2..6 relative to the line start
+    uint16_t msg_off, msg_len;
+};
+static_assert(sizeof(Row5424) == 32, "Row5424 must be 32 bytes");
+// wide row (fg_wide_row): absolute spans like the LTSV / GELF columns
+struct WideRow {
+    int32_t line;
+    uint32_t meta;
+    double ts;
+    int2 host, app, proc, msgid, msg, full, sd;  // sd = {first wide entry, count}
+};
+static_assert(sizeof(WideRow) == 72, "WideRow must be 72 bytes");
+
+enum { K5_ENTRIES = 0, K5_ARENA = 1, K5_WIDE_ROWS = 2, K5_WIDE_ENTRIES = 3, K5_ESC_LIST = 4, K5_WIDE_LIST = 5, K5_COUNT = 8 };
+
+struct Parse5424Params {
+    const uint8_t* bytes;
+    const int32_t* offsets;  // [n+1], element 0 = first line of this launch
+    int32_t n;
+    int32_t tile_bytes;      // staging tile (multiple of 512); the bitmap (tile_bytes / 8 + 16 bytes) follows it
+    uint4* rows;             // 2 x uint4 per line, element 0 = first line of this launch
+    unsigned long long* entries;
+    uint32_t entry_cap;
+    uint32_t* counters;      // K5_*: ENTRIES / ARENA / WIDE_* run over the whole batch, the two LIST lengths are per launch
+    uint32_t* esc_list;      // launch-relative line numbers with escaped values
+    uint32_t* wide_list;     // launch-relative line numbers for the wide kernel
+    uint8_t* arena;
+    uint32_t arena_cap;
+    WideRow* wide_rows;
+    uint32_t wide_cap;
+    int2* wentry_name;
+    unsigned long long* wentry_val;
+    uint8_t* wentry_meta;
+    uint32_t wentry_cap;
+    int32_t line0;           // batch index of the first line of this launch (WideRow.line)
+    const uint32_t* bad_offsets;  // see ParseParams
+    const uint8_t* line_invalid;  // split mode, or nullptr
+    int32_t strip_eol;
+};
+
+cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream);  // parse + unescape + wide kernels
+cudaError_t configure_parse5424(int max_tile_bytes);
+int parse5424_smem_bytes(int tile_bytes);
 
 constexpr int kLinesPerCta = 128;   // lines (= threads) per CTA (256 was measured slower: bigger barriers, same warps/SM)
 constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (tile ~26 KB at 180 B/line) allows 7 CTAs
@@ -62,7 +118,9 @@ constexpr int kRfc5424CtasPerSm = 14;
 constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : kLinesPerCta; }
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
-cudaError_t configure_kernels(int max_tile_bytes);
+// offsets[0 .. n] must be non-decreasing and within [0, max_bytes]; otherwise *flag |= 1 (the parse kernels then return at once)
+cudaError_t launch_check_offsets(const int32_t* d_offsets, int n, long long max_bytes, uint32_t* d_flag, cudaStream_t stream);
+cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424);
 const char* kernel_build_info();
 
 // device-side line framing + UTF-8 validation (fg_split.cu)

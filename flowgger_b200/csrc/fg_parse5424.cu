@@ -1,0 +1,323 @@
+// fg_parse5424.cu — the RFC5424 hot path on sm_100a: bytes -> compact 32-byte rows + 8-byte side-table entries.
+//
+//   parse5424_kernel     one CTA = LINES consecutive lines.  (1) thread 0 issues ONE TMA bulk copy (cp.async.bulk, SASS
+//                        UBLKCP) of the CTA's contiguous byte span into the shared-memory tile; (2) all threads sweep the tile
+//                        16 bytes per step and write the structural bitmap (fg_r5fast.cuh stage 1: coalesced, conflict-free,
+//                        32 of 32 lanes busy); (3) one thread per line walks its line hop by hop over the bitmap (stage 2,
+//                        lock step) and stages its side-table rows inside its own consumed bytes; (4) a CTA scan + ONE global
+//                        atomic place the rows, which are copied out with the 32-byte row of every line.
+//   unescape5424_kernel  the few lines (≈8 % at C2) whose SD values hold a backslash: unescape_sd_value
+//                        (rfc5424_decoder.rs:105-125) into the batch arena, one thread per listed line.
+//   wide5424_kernel      the lines the fast path cannot represent (>= 64 KiB, longer than the tile, rows that do not fit
+//                        behind the cursor): the round-1 scanner of fg_rfc5424.cuh straight from global memory.
+// The last two run over device-side work lists, so a batch needs no host round trip between the three launches.
+#include "fg_kernels.cuh"
+
+#include "fg_common.cuh"
+#include "fg_r5fast.cuh"
+#include "fg_rfc5424.cuh"
+#include "fg_status.h"
+#include "fg_tma.cuh"
+
+namespace fg {
+
+namespace {
+
+constexpr int kFastLines = kRfc5424LinesPerCta;  // lines (= threads) per CTA
+constexpr int kFastCtasPerSm = kRfc5424CtasPerSm;
+
+template <int LINES, int MINB>
+__global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_constant__ Parse5424Params P) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t scan_ws[33];
+    __shared__ uint32_t s_base[3];  // side-table base, escape-list base, wide-list base of this round
+    __shared__ uint32_t s_cnt[2];   // lines of this round on the escape list / wide list
+
+    const int tid = threadIdx.x;
+    const uint32_t lane = (uint32_t)tid & 31u;
+    const int first = blockIdx.x * LINES;
+    const int last = min(P.n, first + LINES);
+    uint32_t* bm = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
+    uint16_t* bm16 = reinterpret_cast<uint16_t*>(bm);
+    if (*P.bad_offsets) return;  // CTA-uniform
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+
+    uint32_t parity = 0;
+    int cur = first;
+    while (cur < last) {
+        const int i = cur + tid;
+        const int o0 = __ldg(P.offsets + min(i, last));
+        const int o1 = __ldg(P.offsets + min(i + 1, last));
+        const int ocur = __ldg(P.offsets + cur);
+        const int base = ocur & ~15;
+        const bool fits = (i < last) && (o1 - base <= P.tile_bytes);
+        const int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
+        if (r == 0) {
+            // the first pending line alone exceeds the tile: the wide kernel takes it
+            if (tid == 0) P.wide_list[atomicAdd(P.counters + K5_WIDE_LIST, 1u)] = (uint32_t)cur;
+            cur += 1;
+            continue;
+        }
+        const int oend = __ldg(P.offsets + cur + r);
+        const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
+        if (tid == 0) {
+            fence_proxy_async();  // generic-proxy accesses of the previous round happen-before this async write
+            mbar_expect_tx(&mbar, nbytes);
+            bulk_g2s(tile, P.bytes + base, nbytes, &mbar);
+            s_cnt[0] = 0;
+            s_cnt[1] = 0;
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+
+        // ---- stage 1: structural bitmap of the whole tile, 16 bytes per thread per step -------------------------
+        const int ngran = (int)(nbytes >> 4);
+        for (int g = tid; g < ngran; g += LINES) {
+            const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
+            bm16[g] = (uint16_t)r5_classify16(v.x, v.y, v.z, v.w);
+        }
+        if (tid < 6) bm16[ngran + tid] = 0;  // r5_window reads one word past the last granule
+        __syncthreads();
+
+        // ---- stage 2: one thread per line ------------------------------------------------------------------------
+        const bool active = tid < r;
+        int ls = active ? o0 - base : 0;
+        int le = active ? o1 - base : 0;
+        bool bad_utf8 = false;
+        if (P.strip_eol && le > ls) {
+            // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
+            if (tile[le - 1] == '\n') {
+                --le;
+                if (le > ls && tile[le - 1] == '\r') --le;
+            }
+            if (P.line_invalid != nullptr && P.line_invalid[i]) bad_utf8 = true;
+        }
+        const bool too_long = le - ls > 65535;
+        R5Fast res;
+        r5_walk(tile, bm, ls, (too_long || bad_utf8) ? ls : le, res);
+        if (too_long) res.wide = true;
+        if (bad_utf8) {
+            res.status = FG_ES_INVALID_UTF8;
+            res.n_entries = 0;
+            res.wide = false;
+        }
+        const bool wide = active && res.wide;
+        const uint32_t my_n = (active && !wide && res.status == FG_ST_OK) ? res.n_entries : 0u;
+        const bool esc = my_n != 0u && res.esc;
+
+        // work lists: warp-aggregated shared-memory counters, resolved by the barriers of the scan below
+        const uint32_t be = __ballot_sync(0xFFFFFFFFu, esc), bw = __ballot_sync(0xFFFFFFFFu, wide);
+        uint32_t esc_at = 0, wide_at = 0;
+        if (be) {
+            if (lane == 0) esc_at = atomicAdd(&s_cnt[0], (uint32_t)__popc(be));
+            esc_at = __shfl_sync(0xFFFFFFFFu, esc_at, 0) + (uint32_t)__popc(be & ((1u << lane) - 1u));
+        }
+        if (bw) {
+            if (lane == 0) wide_at = atomicAdd(&s_cnt[1], (uint32_t)__popc(bw));
+            wide_at = __shfl_sync(0xFFFFFFFFu, wide_at, 0) + (uint32_t)__popc(bw & ((1u << lane) - 1u));
+        }
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
+        const uint32_t n_esc = s_cnt[0], n_wide = s_cnt[1];
+        if (total | n_esc | n_wide) {  // CTA-uniform
+            if (tid == 0) {
+                if (total) s_base[0] = atomicAdd(P.counters + K5_ENTRIES, total);
+                if (n_esc) s_base[1] = atomicAdd(P.counters + K5_ESC_LIST, n_esc);
+                if (n_wide) s_base[2] = atomicAdd(P.counters + K5_WIDE_LIST, n_wide);
+            }
+            __syncthreads();
+        }
+        uint32_t my_begin = 0;
+        if (my_n) {
+            my_begin = s_base[0] + excl;
+            if ((unsigned long long)my_begin + my_n <= (unsigned long long)P.entry_cap) {
+                unsigned long long* dst = P.entries + my_begin;
+                for (uint32_t k = 0; k < my_n; ++k) dst[k] = res.stage[k];
+            }
+        }
+        if (esc) P.esc_list[s_base[1] + esc_at] = (uint32_t)i;
+        if (wide) P.wide_list[s_base[2] + wide_at] = (uint32_t)i;
+        if (active && !wide) {
+            const bool ok = res.status == FG_ST_OK;
+            const uint32_t meta = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);
+            uint4 lo4, hi4;
+            lo4.x = (uint32_t)__double2loint(res.ts);
+            lo4.y = (uint32_t)__double2hiint(res.ts);
+            lo4.z = meta;
+            lo4.w = my_begin;
+            hi4.x = my_n | ((uint32_t)res.sp1 << 16);
+            hi4.y = (uint32_t)res.sp2 | ((uint32_t)res.sp3 << 16);
+            hi4.z = (uint32_t)res.sp4 | ((uint32_t)res.sp5 << 16);
+            hi4.w = (uint32_t)res.msg_o | ((uint32_t)res.msg_l << 16);
+            if (!ok) {
+                lo4.x = lo4.y = 0u;
+                hi4 = make_uint4(0u, 0u, 0u, 0u);
+            }
+            P.rows[2 * (size_t)i] = lo4;
+            P.rows[2 * (size_t)i + 1] = hi4;
+        }
+        __syncthreads();  // tile, bitmap and scan scratch are reused by the next round
+        cur += r;
+    }
+}
+
+// One thread per listed line: pass 1 sums the unescaped lengths, one warp-aggregated atomic reserves the arena bytes,
+// pass 2 writes them and the extension row (arena offset | length << 32) behind every escaped pair.
+__global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant__ Parse5424Params P) {
+    if (*P.bad_offsets) return;
+    const uint32_t cnt = P.counters[K5_ESC_LIST];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); j0 < cnt; j0 += stride) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < cnt;
+        uint32_t first = 0, count = 0;
+        int o0 = 0;
+        if (valid) {
+            const uint32_t line = P.esc_list[j];
+            const uint4 lo4 = P.rows[2 * (size_t)line], hi4 = P.rows[2 * (size_t)line + 1];
+            first = lo4.w;
+            count = hi4.x & 0xFFFFu;
+            o0 = P.offsets[line];
+            if ((unsigned long long)first + count > (unsigned long long)P.entry_cap) count = 0;  // side table overflowed: the batch is redone
+        }
+        uint32_t tot = 0;
+        for (uint32_t e = 0; e < count; ++e) {
+            const unsigned long long v = P.entries[first + e];
+            if (v & kE8Header) continue;
+            if (v & kE8Esc) {
+                const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
+                tot += (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), nullptr);
+                ++e;  // its extension row
+            }
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        uint32_t abase = 0;
+        if (lane == 0 && warp_total) abase = atomicAdd(P.counters + K5_ARENA, warp_total);
+        abase = __shfl_sync(0xFFFFFFFFu, abase, 0);
+        if ((unsigned long long)abase + warp_total > (unsigned long long)P.arena_cap) continue;  // arena overflowed: the batch is redone
+        uint32_t at = abase + inc - tot;
+        for (uint32_t e = 0; e < count; ++e) {
+            const unsigned long long v = P.entries[first + e];
+            if (v & kE8Header) continue;
+            if (v & kE8Esc) {
+                const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
+                const uint32_t l = (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at);
+                P.entries[first + e + 1] = (unsigned long long)at | ((unsigned long long)l << 32);
+                at += l;
+                ++e;
+            }
+        }
+    }
+}
+
+// The round-1 scanner over the listed lines, one thread per line straight from global memory: a counting pass, one
+// atomic per line for its side-table rows, an emitting pass, then the unescape of its values and the wide row.
+__global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Parse5424Params P) {
+    __shared__ int marks[6][32];
+    if (*P.bad_offsets) return;
+    const uint32_t cnt = P.counters[K5_WIDE_LIST];
+    const uint32_t lane = threadIdx.x;
+    const EntrySink sink = {P.wentry_name, P.wentry_val, P.wentry_meta};
+    for (uint32_t j0 = blockIdx.x * 32u; j0 < cnt; j0 += gridDim.x * 32u) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < cnt;
+        uint32_t line = 0;
+        int o0 = 0, len = 0;
+        bool bad_utf8 = false;
+        if (valid) {
+            line = P.wide_list[j];
+            o0 = P.offsets[line];
+            len = P.offsets[line + 1] - o0;
+            if (P.strip_eol && len > 0) {
+                if (P.bytes[o0 + len - 1] == '\n') {
+                    --len;
+                    if (len > 0 && P.bytes[o0 + len - 1] == '\r') --len;
+                }
+                if (P.line_invalid != nullptr && P.line_invalid[line]) bad_utf8 = true;
+            }
+            if (bad_utf8) len = 0;
+        }
+        LineResult res;
+        rfc5424_parse_line<32>(P.bytes + o0, len, o0, &marks[0][lane], res, sink, 0u, false);
+        uint32_t n = (valid && !bad_utf8 && res.status == FG_ST_OK) ? res.n_entries : 0u;
+        uint32_t wbase = 0;
+        if (n) {
+            wbase = atomicAdd(P.counters + K5_WIDE_ENTRIES, n);
+            if ((unsigned long long)wbase + n > (unsigned long long)P.wentry_cap) n = 0;  // table overflowed: the batch is redone
+        }
+        {
+            LineResult again;  // same fields as `res`; only the rows matter (lanes without rows run an empty line)
+            rfc5424_parse_line<32>(P.bytes + o0, n ? len : 0, o0, &marks[0][lane], again, sink, wbase, true);
+        }
+        if (!valid) continue;
+        // unescape_sd_value (:105-125) of the flagged values into the arena
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t e = wbase + k;
+            const uint8_t m = sink.meta[e];
+            if ((m & 0x07u) == 0u && (m & 0x08u)) {
+                const unsigned long long v = sink.val[e];
+                const uint32_t off = (uint32_t)v, l = (uint32_t)(v >> 32);
+                const uint32_t ul = (uint32_t)r5_unescape(P.bytes + off, (int)l, nullptr);
+                const uint32_t at = atomicAdd(P.counters + K5_ARENA, ul);
+                if ((unsigned long long)at + ul <= (unsigned long long)P.arena_cap) r5_unescape(P.bytes + off, (int)l, P.arena + at);
+                sink.val[e] = (unsigned long long)at | ((unsigned long long)ul << 32);
+                sink.meta[e] = (uint8_t)0x80u;  // FG_TAG_STRING | FG_EM_ARENA
+            }
+        }
+        if (bad_utf8) {
+            res.status = FG_ES_INVALID_UTF8;
+            res.flags = 0;
+            res.facility = res.severity = 0xFFu;
+        }
+        const bool ok = res.status == FG_ST_OK;
+        const uint32_t widx = atomicAdd(P.counters + K5_WIDE_ROWS, 1u);
+        const uint32_t meta = res.status | (res.facility << 8) | (res.severity << 16) | ((res.flags | kFlagWide) << 24);
+        if (widx < P.wide_cap) {
+            WideRow w;
+            w.line = P.line0 + (int32_t)line;
+            w.meta = meta;
+            w.ts = res.ts;
+            w.host = make_int2(ok ? o0 + res.host_o : -1, res.host_l);
+            w.app = make_int2(ok ? o0 + res.app_o : -1, res.app_l);
+            w.proc = make_int2(ok ? o0 + res.proc_o : -1, res.proc_l);
+            w.msgid = make_int2(ok ? o0 + res.mid_o : -1, res.mid_l);
+            w.msg = make_int2(ok && res.msg_o >= 0 ? o0 + res.msg_o : -1, res.msg_l);
+            w.full = make_int2(ok && res.full_o >= 0 ? o0 + res.full_o : -1, res.full_l);
+            w.sd = make_int2((int)wbase, (int)(ok ? n : 0u));
+            P.wide_rows[widx] = w;
+        }
+        P.rows[2 * (size_t)line] = make_uint4((uint32_t)__double2loint(res.ts), (uint32_t)__double2hiint(res.ts), meta, widx);
+        P.rows[2 * (size_t)line + 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+}  // namespace
+
+int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 32; }
+
+cudaError_t configure_parse5424(int max_tile_bytes) {
+    return cudaFuncSetAttribute(parse5424_kernel<kFastLines, kFastCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                parse5424_smem_bytes(max_tile_bytes));
+}
+
+cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int grid = (p.n + kFastLines - 1) / kFastLines;
+    parse5424_kernel<kFastLines, kFastCtasPerSm><<<grid, kFastLines, parse5424_smem_bytes(p.tile_bytes), stream>>>(p);
+    // the work lists are usually short: a fixed small grid strides over them
+    const int lgrid = (int)min((long long)(p.n + 127) / 128, 148LL * 8);
+    unescape5424_kernel<<<lgrid, 128, 0, stream>>>(p);
+    wide5424_kernel<<<(int)min((long long)(p.n + 31) / 32, 148LL * 4), 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace fg

@@ -1,14 +1,19 @@
-// fg_rfc5424.cuh — one RFC5424 line -> Record fields, on device.
+// fg_rfc5424.cuh — one RFC5424 line -> Record fields, on device: the WIDE path (round-1 scanner).
+//
+// Since round 2 the hot path is fg_r5fast.cuh (structural bitmap + bit-walk over the shared-memory tile).  This file
+// keeps the self-contained SWAR scanner that reads a line straight from global memory; wide5424_kernel
+// (fg_parse5424.cu) runs it for the rare lines the fast path hands over: lines of 64 KiB or more (the compact rows
+// hold u16 positions), lines longer than the staging tile, and lines whose side-table rows do not fit behind the
+// cursor.  The block-scan primitives at the top are shared with the LTSV / GELF parsers.
 //
 // B200-native replacement for RFC5424Decoder::decode
 // (/root/reference/src/flowgger/decoder/rfc5424_decoder.rs:18-49) and its helpers
 // BOM::parse :63-71, parse_pri_version :74-92, rfc3339_to_unix :94-99,
 // parse_data :127-161, parse_msg :163-172, parse_sd_data :174-242.
-// The unescape of SD values (:105-125) is deferred to Record materialisation:
-// the table carries the raw value span plus FG_EM_UNESCAPE.
+// The table rows carry the raw value span plus FG_EM_UNESCAPE; wide5424_kernel then rewrites
+// those values (:105-125) into the batch arena.
 //
-// One thread owns one line whose bytes are already staged in shared memory by
-// the CTA-wide bulk copy (fg_kernels.cu).  SIMT discipline: the 32 lines of a
+// One thread owns one line.  SIMT discipline: the 32 lines of a
 // warp advance in LOCK STEP through the same phases; every data-dependent loop
 // is a warp-uniform `while (__any_sync(..))` whose body is predicated per lane,
 // so lanes never skew into different code (the first version of this kernel
@@ -29,13 +34,11 @@ struct LineResult {
     uint32_t facility, severity, flags;
     // spans relative to the line start; off < 0 => None
     int host_o, host_l, app_o, app_l, proc_o, proc_l, mid_o, mid_l, msg_o, msg_l, full_o, full_l;
-    uint32_t n_entries;  // SD headers + pairs staged for this line
-    unsigned long long* stage;  // RFC5424: compact rows staged in the line's own (already consumed) header bytes
-    uint32_t stage_cap;         // rows [0, stage_cap) are in `stage`, the rest in the scratch table
+    uint32_t n_entries;  // SD headers + pairs of this line
 };
 
-// provisional side-table rows of one line live at scratch index line_off/3 + k
-// (an SD header needs >= 3 input bytes, a pair >= 4, so ranges of different lines never overlap)
+// side-table columns (LTSV / GELF: provisional rows live in a scratch table indexed by the line's byte offset,
+// see Format<>::scratch_index; RFC5424 wide path: final rows)
 struct EntrySink {
     int2* name;
     unsigned long long* val;
@@ -96,41 +99,13 @@ FG_DEV int scan_block16_json(const uint4* qp, uint32_t b0, int i, bool& hit) {
     return first_hit16(swar_json_stop(v.x), swar_json_stop(v.y), swar_json_stop(v.z), swar_json_stop(v.w), o & 15u, i, hit);
 }
 
-// --- side-table staging for RFC5424 ------------------------------------------------------------------------
-// After phase 1 the bytes [0, sp5) of a line (PRI, timestamp, hostname ... msgid) are never read again: every
-// Record field that points there is a span.  A thread therefore stages the compact (u16 positions) rows of its
-// structured data in its OWN header bytes of the shared-memory tile; rows that do not fit (or lines >= 64 KiB,
-// or lines parsed straight from global memory) go to the scratch table.  This removes the L2/DRAM round trip of
-// the provisional rows for ~97 % of C2 lines (profiles/r1_notes.md).
-FG_DEV unsigned long long r5_pack_pair(int ns, int ne, int ve, uint32_t esc) {
-    return (unsigned long long)(uint32_t)ns | ((unsigned long long)(uint32_t)ne << 16) | ((unsigned long long)(uint32_t)ve << 32) |
-           ((unsigned long long)(esc ? 1u : 0u) << 48);
-}
-FG_DEV unsigned long long r5_pack_header(int es, int id_end, uint32_t pairs) {
-    return (unsigned long long)(uint32_t)es | ((unsigned long long)(uint32_t)id_end << 16) | ((unsigned long long)pairs << 32) | (0x8000ull << 48);
-}
-FG_DEV void r5_unpack(unsigned long long v, int line_off, int2& name, unsigned long long& val, uint8_t& meta) {
-    const int a = (int)(v & 0xFFFFu), b = (int)((v >> 16) & 0xFFFFu), c = (int)((v >> 32) & 0xFFFFu);
-    if ((v >> 63) & 1ull) {  // SD element header: name = sd_id, val = #pairs
-        name = make_int2(line_off + a, b - a);
-        val = (unsigned long long)c;
-        meta = 7u;
-    } else {
-        name = make_int2(line_off + a, b - a);
-        val = (unsigned long long)(uint32_t)(line_off + b + 2) | ((unsigned long long)(uint32_t)(c - (b + 2)) << 32);
-        meta = (uint8_t)(((v >> 48) & 1ull) ? 0x08u : 0u);
-    }
-}
-
-// Per-CTA scratch in shared memory used by the RFC5424 parser
-struct R5Shared {
-    int marks[6][kRfc5424LinesPerCta];  // [space index][thread]: positions of the first six spaces
-};
-
-// p: line bytes (shared memory, or global for oversized lines); len may be 0 for idle lanes.
-// marks: &sh.marks[0][threadIdx.x] (stride kRfc5424LinesPerCta ints between slots).
-FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, bool in_smem, LineResult& r,
-                               const EntrySink& sink) {
+// p: line bytes (global memory); len may be 0 for idle lanes.
+// marks: this thread's column of a [6][stride] int array in shared memory (positions of the first six spaces).
+// Side-table rows go to sink[sbase + k] when `emit` (the caller first runs a counting pass with emit = false, reserves
+// r.n_entries rows and runs the line again).
+template <int STRIDE>
+FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, LineResult& r, const EntrySink& sink, uint32_t sbase,
+                               bool emit) {
     r.ts = 0.0;
     r.facility = 0xFFu;
     r.severity = 0xFFu;
@@ -138,8 +113,6 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
     r.host_o = r.app_o = r.proc_o = r.mid_o = r.msg_o = r.full_o = -1;
     r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
     r.n_entries = 0;
-    r.stage = nullptr;
-    r.stage_cap = 0;
     uint32_t status = FG_ST_OK;
 
     // ---- BOM::parse :63-71 ---------------------------------------------------------------------
@@ -164,7 +137,7 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
                              (swar_nibble(swar_eq(v.z, 0x20202020u)) << 8) | (swar_nibble(swar_eq(v.w, 0x20202020u)) << 12);
                 if (k == 0) m &= 0xFFFFu << s0;
                 while (m != 0 && nsp < 6) {
-                    marks[nsp * kRfc5424LinesPerCta] = b + 16 * k + (__ffs((int)m) - 1) - (int)s0;
+                    marks[nsp * STRIDE] = b + 16 * k + (__ffs((int)m) - 1) - (int)s0;
                     ++nsp;
                     m &= m - 1;
                 }
@@ -177,12 +150,12 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
     {
         // marks past the end of the line come from the bytes after it in the last word: drop them
         int v;
-        v = nsp > 0 ? marks[0 * kRfc5424LinesPerCta] : len; sp0 = v < len ? v : len;
-        v = nsp > 1 ? marks[1 * kRfc5424LinesPerCta] : len; sp1 = v < len ? v : len;
-        v = nsp > 2 ? marks[2 * kRfc5424LinesPerCta] : len; sp2 = v < len ? v : len;
-        v = nsp > 3 ? marks[3 * kRfc5424LinesPerCta] : len; sp3 = v < len ? v : len;
-        v = nsp > 4 ? marks[4 * kRfc5424LinesPerCta] : len; sp4 = v < len ? v : len;
-        v = nsp > 5 ? marks[5 * kRfc5424LinesPerCta] : len; sp5 = v < len ? v : len;
+        v = nsp > 0 ? marks[0 * STRIDE] : len; sp0 = v < len ? v : len;
+        v = nsp > 1 ? marks[1 * STRIDE] : len; sp1 = v < len ? v : len;
+        v = nsp > 2 ? marks[2 * STRIDE] : len; sp2 = v < len ? v : len;
+        v = nsp > 3 ? marks[3 * STRIDE] : len; sp3 = v < len ? v : len;
+        v = nsp > 4 ? marks[4 * STRIDE] : len; sp4 = v < len ? v : len;
+        v = nsp > 5 ? marks[5 * STRIDE] : len; sp5 = v < len ? v : len;
         nsp = (sp0 < len) + (sp1 < len) + (sp2 < len) + (sp3 < len) + (sp4 < len) + (sp5 < len);
     }
     __syncwarp();
@@ -240,19 +213,6 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
         const uint4* qp = (const uint4*)(p - b0);
         int i = d + 1, elem_start = d + 1, id_end = 0;
         bool st_id = true;
-        const uint32_t sbase = (uint32_t)line_off / 3u;
-        // staging area: the 8-byte aligned part of this line's header bytes [0, sp5)
-        unsigned long long* stg = nullptr;
-        uint32_t cap = 0;
-        if (walk && in_smem && len < 65536) {
-            const uint32_t pad = (8u - ((uint32_t)(size_t)p & 7u)) & 7u;
-            if ((uint32_t)sp5 > pad + 8u) {
-                stg = (unsigned long long*)(const_cast<uint8_t*>(p) + pad);
-                cap = ((uint32_t)sp5 - pad) >> 3;
-            }
-        }
-        r.stage = stg;
-        r.stage_cap = cap;
         bool active = walk;
         // Inner scans are written as `lim`-bounded loops whose only loop-carried value is the cursor:
         // a lane that is not scanning has lim == i and falls through; nothing else is updated inside.
@@ -293,9 +253,7 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
             if (active) {
                 const uint32_t c = p[i];
                 if (c == ']') {  // :197 end of this element, then :145-155
-                    if (hdr < cap) {
-                        stg[hdr] = r5_pack_header(elem_start, id_end, pairs);
-                    } else {
+                    if (emit) {
                         const uint32_t e = sbase + hdr;
                         sink.name[e] = make_int2(line_off + elem_start, id_end - elem_start);
                         sink.val[e] = pairs;
@@ -364,9 +322,7 @@ FG_DEV void rfc5424_parse_line(bytes_t p, int len, int line_off, int* marks, boo
             if (do_val) {
                 if (i >= len) { active = false; status = FG_E5_SD_NO_END; }
                 else {
-                    if (n < cap) {
-                        stg[n] = r5_pack_pair(name_start, name_end, i, has_bs);
-                    } else {
+                    if (emit) {
                         const uint32_t e = sbase + n;
                         sink.name[e] = make_int2(line_off + name_start, name_end - name_start);
                         sink.val[e] = (unsigned long long)(uint32_t)(line_off + name_end + 2) |

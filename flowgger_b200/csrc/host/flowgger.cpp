@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <istream>
+#include <mutex>
 #include <ostream>
 #include <sstream>
 #include <stdexcept>
@@ -94,24 +95,6 @@ bool is_valid_utf8(const uint8_t* p, size_t n) {
         i += need + 1;
     }
     return true;
-}
-
-// rfc5424_decoder.rs:105-125 (deferred from the kernel: the table carries the raw span + FG_EM_UNESCAPE)
-static std::string unescape_sd_value(std::string_view v) {
-    std::string res;
-    res.reserve(v.size());
-    bool esc = false;
-    for (const char c : v) {
-        if (!esc) {
-            if (c == '\\') esc = true;
-            else res.push_back(c);
-        } else {
-            if (c != '"' && c != '\\' && c != ']') res.push_back('\\');
-            res.push_back(c);
-            esc = false;
-        }
-    }
-    return res;
 }
 
 static void push_utf8(std::string& s, uint32_t cp) {
@@ -252,8 +235,115 @@ static void split_extent(const fg_batch_out& out, const uint8_t* stream, int32_t
     }
 }
 
-DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t line_hi,
-                                                int32_t i, std::vector<std::string>* side_effects) const {
+uint32_t row_meta(const fg_batch_out& out, int32_t i) { return out.rows5424 ? out.rows5424[i].meta : out.meta[i]; }
+
+// Structured data of one line from 17-byte side-table rows [first, first + count) (LTSV / GELF, RFC5424 wide lines)
+static void sd_from_table(fg_format fmt, const std::string* suffix, const fg_batch_out& out, const uint8_t* bytes, int32_t first,
+                          int32_t count, bool nl_retry, Record& rec) {
+    std::vector<StructuredData> vec;
+    const bool r5 = fmt == FG_FMT_RFC5424;
+    if (!r5) vec.emplace_back();  // one element with sd_id None (ltsv_decoder.rs:88, gelf_decoder.rs:35)
+    for (int32_t e = first; e < first + count; ++e) {
+        const uint8_t em = out.entry_meta[e];
+        const uint32_t tag = em & FG_EM_TAG_MASK;
+        const fg_span nm = out.entry_name[e];
+        if (tag == FG_TAG_SD_HEADER) {
+            vec.emplace_back();
+            if (nm.off >= 0) vec.back().sd_id = std::string(span_sv(bytes, nm));
+            vec.back().pairs.reserve((size_t)out.entry_val[e]);
+            continue;
+        }
+        std::string name;
+        std::string_view raw = span_sv(bytes, nm);
+        if (!(em & FG_EM_NO_PREFIX)) name.push_back('_');
+        if (em & FG_EM_NAME_ESC) name += json_unescape(raw, nl_retry);
+        else name.append(raw);
+        if ((em & FG_EM_SUFFIX) && tag >= 1 && tag <= 4) name += suffix[tag];
+        SDValue v;
+        v.kind = (SDValue::Kind)tag;
+        const uint64_t val = out.entry_val[e];
+        switch (tag) {
+            case FG_TAG_STRING: {
+                const uint8_t* base = (em & FG_EM_ARENA) ? out.arena : bytes;  // arena: unescaped on the device
+                std::string_view sv((const char*)base + (uint32_t)(val & 0xFFFFFFFFu), (size_t)(val >> 32));
+                if (em & FG_EM_UNESCAPE) v.s = json_unescape(sv, nl_retry);
+                else v.s = std::string(sv);
+                break;
+            }
+            case FG_TAG_BOOL: v.b = val != 0; break;
+            case FG_TAG_F64: memcpy(&v.f, &val, 8); break;
+            case FG_TAG_I64: v.i = (int64_t)val; break;
+            case FG_TAG_U64: v.u = val; break;
+            default: break;
+        }
+        vec.back().pairs.emplace_back(std::move(name), std::move(v));
+    }
+    rec.sd = std::move(vec);
+}
+
+// RFC5424: compact 32-byte row + 8-byte entries (include/flowgger_cuda.h: fg_row5424); wide rows carry absolute spans
+static DecodeResult materialize_5424(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t i) {
+    DecodeResult r;
+    const fg_row5424& row = out.rows5424[i];
+    const uint32_t meta = row.meta;
+    const uint32_t status = FG_META_STATUS(meta);
+    if (status) {
+        r.err = fg_error_string(FG_FMT_RFC5424, status);
+        return r;
+    }
+    Record& rec = r.record;
+    rec.facility = (uint8_t)FG_META_FACILITY(meta);
+    rec.severity = (uint8_t)FG_META_SEVERITY(meta);
+    if (FG_META_FLAGS(meta) & FG_FLAG_WIDE) {
+        const fg_wide_row& w = out.wide_rows[row.sd_first];
+        rec.ts = w.ts;
+        rec.hostname = std::string(span_sv(bytes, w.hostname));
+        rec.appname = std::string(span_sv(bytes, w.appname));
+        rec.procid = std::string(span_sv(bytes, w.procid));
+        rec.msgid = std::string(span_sv(bytes, w.msgid));
+        if (w.msg.off >= 0) rec.msg = std::string(span_sv(bytes, w.msg));
+        if (w.full_msg.off >= 0) rec.full_msg = std::string(span_sv(bytes, w.full_msg));
+        if (w.sd.len > 0) sd_from_table(FG_FMT_RFC5424, nullptr, out, bytes, w.sd.off, w.sd.len, false, rec);
+        return r;
+    }
+    rec.ts = row.ts;
+    rec.hostname = std::string(span_sv(bytes, fg_row5424_field(&row, line_lo, 0)));
+    rec.appname = std::string(span_sv(bytes, fg_row5424_field(&row, line_lo, 1)));
+    rec.procid = std::string(span_sv(bytes, fg_row5424_field(&row, line_lo, 2)));
+    rec.msgid = std::string(span_sv(bytes, fg_row5424_field(&row, line_lo, 3)));
+    if (row.msg_len) rec.msg = std::string(span_sv(bytes, fg_row5424_msg(&row, line_lo)));
+    rec.full_msg = std::string(span_sv(bytes, fg_row5424_full(&row, line_lo)));
+    if (row.sd_count) {
+        std::vector<StructuredData> vec;
+        const uint8_t* line = bytes + line_lo;
+        for (uint32_t e = row.sd_first; e < row.sd_first + row.sd_count; ++e) {
+            const uint64_t v = out.entries8[e];
+            if (v & FG_E8_HEADER) {
+                vec.emplace_back();
+                vec.back().sd_id = std::string((const char*)line + FG_E8_A(v), FG_E8_B(v) - FG_E8_A(v));
+                vec.back().pairs.reserve(FG_E8_C(v));
+                continue;
+            }
+            std::string name(1, '_');  // rfc5424_decoder.rs:221
+            name.append((const char*)line + FG_E8_A(v), FG_E8_B(v) - FG_E8_A(v));
+            SDValue val;
+            val.kind = SDValue::String;
+            if (v & FG_E8_ESC) {
+                const uint64_t ext = out.entries8[++e];  // value unescaped on the device (rfc5424_decoder.rs:105-125)
+                val.s.assign((const char*)out.arena + (uint32_t)ext, (size_t)(ext >> 32));
+            } else {
+                val.s.assign((const char*)line + FG_E8_B(v) + 2, FG_E8_C(v) - (FG_E8_B(v) + 2));
+            }
+            vec.back().pairs.emplace_back(std::move(name), std::move(val));
+        }
+        rec.sd = std::move(vec);
+    }
+    return r;
+}
+
+DecodeResult materialize_record(fg_format fmt, const std::string* suffix, const fg_batch_out& out, const uint8_t* bytes,
+                                int32_t line_lo, int32_t line_hi, int32_t i, std::vector<std::string>* side_effects) {
+    if (fmt == FG_FMT_RFC5424) return materialize_5424(out, bytes, line_lo, i);
     DecodeResult r;
     const uint32_t meta = out.meta[i];
     const uint32_t status = FG_META_STATUS(meta), flags = FG_META_FLAGS(meta);
@@ -275,7 +365,7 @@ DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const u
         }
     }
     if (status) {
-        r.err = fg_error_string(fmt_, status);
+        r.err = fg_error_string(fmt, status);
         return r;
     }
     const bool nl_retry = (flags & FG_FLAG_NL_RETRY) != 0;
@@ -287,9 +377,6 @@ DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const u
     }
     if (FG_META_FACILITY(meta) != 0xFF) rec.facility = (uint8_t)FG_META_FACILITY(meta);
     if (FG_META_SEVERITY(meta) != 0xFF) rec.severity = (uint8_t)FG_META_SEVERITY(meta);
-    if (out.appname && out.appname[i].off >= 0) rec.appname = std::string(span_sv(bytes, out.appname[i]));
-    if (out.procid && out.procid[i].off >= 0) rec.procid = std::string(span_sv(bytes, out.procid[i]));
-    if (out.msgid && out.msgid[i].off >= 0) rec.msgid = std::string(span_sv(bytes, out.msgid[i]));
     if (out.msg[i].off >= 0) {
         std::string_view m = span_sv(bytes, out.msg[i]);
         rec.msg = (flags & FG_FLAG_MSG_ESC) ? json_unescape(m, nl_retry) : std::string(m);
@@ -299,47 +386,13 @@ DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const u
         rec.full_msg = (flags & FG_FLAG_FULL_ESC) ? json_unescape(m, nl_retry) : std::string(m);
     }
     const fg_span sd = out.sd[i];
-    if (sd.len > 0) {
-        std::vector<StructuredData> vec;
-        const bool r5 = fmt_ == FG_FMT_RFC5424;
-        if (!r5) vec.emplace_back();  // one element with sd_id None (ltsv_decoder.rs:88, gelf_decoder.rs:35)
-        for (int32_t e = sd.off; e < sd.off + sd.len; ++e) {
-            const uint8_t em = out.entry_meta[e];
-            const uint32_t tag = em & FG_EM_TAG_MASK;
-            const fg_span nm = out.entry_name[e];
-            if (tag == FG_TAG_SD_HEADER) {
-                vec.emplace_back();
-                if (nm.off >= 0) vec.back().sd_id = std::string(span_sv(bytes, nm));
-                vec.back().pairs.reserve((size_t)out.entry_val[e]);
-                continue;
-            }
-            std::string name;
-            std::string_view raw = span_sv(bytes, nm);
-            if (!(em & FG_EM_NO_PREFIX)) name.push_back('_');
-            if (em & FG_EM_NAME_ESC) name += json_unescape(raw, nl_retry);
-            else name.append(raw);
-            if ((em & FG_EM_SUFFIX) && tag >= 1 && tag <= 4) name += suffix_[tag];
-            SDValue v;
-            v.kind = (SDValue::Kind)tag;
-            const uint64_t val = out.entry_val[e];
-            switch (tag) {
-                case FG_TAG_STRING: {
-                    std::string_view sv((const char*)bytes + (uint32_t)(val & 0xFFFFFFFFu), (size_t)(val >> 32));
-                    if (em & FG_EM_UNESCAPE) v.s = r5 ? unescape_sd_value(sv) : json_unescape(sv, nl_retry);
-                    else v.s = std::string(sv);
-                    break;
-                }
-                case FG_TAG_BOOL: v.b = val != 0; break;
-                case FG_TAG_F64: memcpy(&v.f, &val, 8); break;
-                case FG_TAG_I64: v.i = (int64_t)val; break;
-                case FG_TAG_U64: v.u = val; break;
-                default: break;
-            }
-            vec.back().pairs.emplace_back(std::move(name), std::move(v));
-        }
-        rec.sd = std::move(vec);
-    }
+    if (sd.len > 0) sd_from_table(fmt, suffix, out, bytes, sd.off, sd.len, nl_retry, rec);
     return r;
+}
+
+DecodeResult CudaBatchDecoder::materialize_line(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t line_hi,
+                                                int32_t i, std::vector<std::string>* side_effects) const {
+    return materialize_record(fmt_, suffix_, out, bytes, line_lo, line_hi, i, side_effects);
 }
 
 // ---------------------------------------------------------------------------
@@ -353,11 +406,14 @@ DecodeResult CudaDecoder::decode(std::string_view line) const {
     fg_batch_out out;
     const uint8_t dummy = 0;
     const uint8_t* bytes = line.empty() ? &dummy : (const uint8_t*)line.data();
+    // a context is single-caller and its result arrays live until the next call: clones made by clone_boxed() share it,
+    // so concurrent decode() calls (one decoder clone per input thread in the reference) are serialised here
+    std::lock_guard<std::mutex> guard(impl_->mutex());
     impl_->decode_batch(bytes, offsets, 1, &out);
     std::vector<std::string> fx;
     DecodeResult r = impl_->materialize(out, bytes, offsets, 0, &fx);
     for (const auto& s : fx) fprintf(stdout, "%s\n", s.c_str());
-    if (r.ok() && (FG_META_FLAGS(out.meta[0]) & FG_FLAG_TS_MISSING)) {
+    if (r.ok() && (FG_META_FLAGS(row_meta(out, 0)) & FG_FLAG_TS_MISSING)) {
         // gelf_decoder.rs:109 -> utils/mod.rs:16-21
         timespec tsn;
         clock_gettime(CLOCK_REALTIME, &tsn);
@@ -388,6 +444,7 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
         fg_batch_out out;
         const uint8_t dummy = 0;
         const uint8_t* bytes = arena.empty() ? &dummy : arena.data();
+        std::lock_guard<std::mutex> guard(gpu->mutex());  // held until every Record of the batch has been materialised
         gpu->decode_batch(bytes, offsets.data(), n, &out);
         for (int32_t i = 0; i < n; ++i) {
             for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
@@ -396,7 +453,7 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
             for (const auto& s : fx) std_out << s << "\n";
             const char* e = r.err;
             if (!e) {
-                if (FG_META_FLAGS(out.meta[i]) & FG_FLAG_TS_MISSING) {
+                if (FG_META_FLAGS(row_meta(out, i)) & FG_FLAG_TS_MISSING) {
                     timespec tsn;
                     clock_gettime(CLOCK_REALTIME, &tsn);
                     r.record.ts = (double)tsn.tv_sec + (double)tsn.tv_nsec / 1e9;
@@ -602,18 +659,19 @@ void fgh_decoder_free(void* d) { delete (CudaBatchDecoder*)d; }
 fg_ctx* fgh_decoder_ctx(void* d) { return ((CudaBatchDecoder*)d)->ctx(); }
 void fgh_free(void* p) { free(p); }
 
-// materialise + canonical dump of every line of a decoded batch (multi-threaded over line shards)
-int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, int nthreads,
-                 uint8_t** out_buf, int64_t** out_offsets) {
+// materialise + canonical dump of lines [lo, hi) of a decoded batch (multi-threaded over line shards); offsets of the
+// dumps are relative to the first dumped line
+int fgh_dump_range(void* d, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, int64_t lo_line, int64_t hi_line,
+                   int nthreads, uint8_t** out_buf, int64_t** out_offsets) {
     auto* dec = (CudaBatchDecoder*)d;
-    const int64_t n = out->n;
+    const int64_t n = hi_line - lo_line;
     if (nthreads < 1) nthreads = 1;
     std::vector<std::string> parts((size_t)nthreads);
     std::vector<std::vector<int64_t>> lens((size_t)nthreads);
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) {
         th.emplace_back([&, t] {
-            const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            const int64_t lo = lo_line + n * t / nthreads, hi = lo_line + n * (t + 1) / nthreads;
             std::string& o = parts[(size_t)t];
             lens[(size_t)t].reserve((size_t)(hi - lo));
             std::vector<std::string> fx;
@@ -621,7 +679,7 @@ int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const i
                 const size_t before = o.size();
                 fx.clear();
                 DecodeResult r = dec->materialize(*out, bytes, offsets, (int32_t)i, &fx);
-                const bool now = r.ok() && (FG_META_FLAGS(out->meta[i]) & FG_FLAG_TS_MISSING);
+                const bool now = r.ok() && (FG_META_FLAGS(row_meta(*out, (int32_t)i)) & FG_FLAG_TS_MISSING);
                 dump_result(r, now, fx, o);
                 lens[(size_t)t].push_back((int64_t)(o.size() - before));
             }
@@ -643,6 +701,34 @@ int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const i
         }
         pos += parts[(size_t)t].size();
     }
+    *out_buf = buf;
+    *out_offsets = offs;
+    return 0;
+}
+int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, int nthreads,
+                 uint8_t** out_buf, int64_t** out_offsets) {
+    return fgh_dump_range(d, out, bytes, offsets, 0, out->n, nthreads, out_buf, out_offsets);
+}
+
+// same dump from bare result arrays (no context, no device): lets the CPU test-suite run the product's materialiser
+// over rows produced by the device-logic emulation (tests/emu)
+int fgh_dump_records(int fmt, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, uint8_t** out_buf,
+                     int64_t** out_offsets) {
+    const int64_t n = out->n;
+    std::string all;
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    offs[0] = 0;
+    const std::string suffix[5];
+    std::vector<std::string> fx;
+    for (int64_t i = 0; i < n; ++i) {
+        fx.clear();
+        DecodeResult r = materialize_record((fg_format)fmt, suffix, *out, bytes, offsets[i], offsets[i + 1], (int32_t)i, &fx);
+        const bool now = r.ok() && (FG_META_FLAGS(row_meta(*out, (int32_t)i)) & FG_FLAG_TS_MISSING);
+        dump_result(r, now, fx, all);
+        offs[i + 1] = (int64_t)all.size();
+    }
+    uint8_t* buf = (uint8_t*)malloc(all.size() ? all.size() : 1);
+    memcpy(buf, all.data(), all.size());
     *out_buf = buf;
     *out_offsets = offs;
     return 0;
@@ -692,7 +778,7 @@ int fgh_split_dump(void* d, const uint8_t* stream, int64_t nbytes, uint8_t** out
             split_extent(out, stream, i, lo, hi);
             fx.clear();
             DecodeResult r = dec->materialize_line(out, stream, lo, hi, i, &fx);
-            const bool now = r.ok() && (FG_META_FLAGS(out.meta[i]) & FG_FLAG_TS_MISSING);
+            const bool now = r.ok() && (FG_META_FLAGS(row_meta(out, i)) & FG_FLAG_TS_MISSING);
             dump_result(r, now, fx, all);
             offs[i + 1] = (int64_t)all.size();
         }

@@ -17,6 +17,7 @@
 #include <iosfwd>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <string>
 #include <string_view>
@@ -81,7 +82,7 @@ struct DeviceOptions {
     int32_t chunk_lines = 0;
 };
 
-// One GPU decoding context of a fixed format.  Single caller at a time.
+// One GPU decoding context of a fixed format.  Single caller at a time (see mutex()).
 class CudaBatchDecoder {
    public:
     CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv = {}, const DeviceOptions& opt = {});
@@ -91,6 +92,8 @@ class CudaBatchDecoder {
 
     fg_format format() const { return fmt_; }
     fg_ctx* ctx() const { return ctx_; }
+    // serialises the callers that share this context (decoder clones): hold it from decode_batch until the last materialize
+    std::mutex& mutex() { return mu_; }
     // packs nothing: bytes/offsets as in fg_decode_batch.  Throws std::runtime_error on a CUDA/argument failure.
     void decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_batch_out* out);
     // Owned Record (or the reference's error string) of line i of a decoded batch.
@@ -106,6 +109,7 @@ class CudaBatchDecoder {
    private:
     fg_format fmt_;
     fg_ctx* ctx_ = nullptr;
+    std::mutex mu_;
     std::string suffix_[5];
     bool has_suffix_[5] = {false, false, false, false, false};
 };
@@ -194,6 +198,12 @@ class MultiGpuBatchDecoder {
     std::vector<std::unique_ptr<CudaBatchDecoder>> dec_;
     std::vector<Shard> shards_;
 };
+
+// Owned Record (or the reference's error string) of line i = bytes[line_lo, line_hi) of a decoded batch; `suffix` = the
+// five LTSV type suffixes (may be null for other formats).  Pure function of the result arrays: no device, no context.
+DecodeResult materialize_record(fg_format fmt, const std::string* suffix, const fg_batch_out& out, const uint8_t* bytes,
+                                int32_t line_lo, int32_t line_hi, int32_t i, std::vector<std::string>* side_effects);
+uint32_t row_meta(const fg_batch_out& out, int32_t i);
 
 // helpers shared with tests
 bool is_valid_utf8(const uint8_t* p, size_t n);

@@ -29,8 +29,19 @@ class FgBatchOut(C.Structure):
         ("sd", C.POINTER(FgSpan)),
         ("entry_name", C.POINTER(FgSpan)), ("entry_val", C.POINTER(C.c_uint64)), ("entry_meta", C.POINTER(C.c_uint8)),
         ("line_offsets", C.POINTER(C.c_int32)),
+        ("rows5424", C.c_void_p), ("entries8", C.POINTER(C.c_uint64)), ("n_entries8", C.c_int32), ("n_wide", C.c_int32),
+        ("wide_rows", C.c_void_p), ("arena", C.POINTER(C.c_uint8)), ("arena_bytes", C.c_int64),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float),
     ]
+
+
+# include/flowgger_cuda.h: fg_row5424 (32 bytes) and fg_wide_row (72 bytes)
+ROW5424 = np.dtype([("ts", "<f8"), ("meta", "<u4"), ("sd_first", "<u4"), ("sd_count", "<u2"), ("sp", "<u2", (5,)),
+                    ("msg_off", "<u2"), ("msg_len", "<u2")])
+WIDE_ROW = np.dtype([("line", "<i4"), ("meta", "<u4"), ("ts", "<f8"), ("hostname", "<i4", (2,)), ("appname", "<i4", (2,)),
+                     ("procid", "<i4", (2,)), ("msgid", "<i4", (2,)), ("msg", "<i4", (2,)), ("full_msg", "<i4", (2,)),
+                     ("sd", "<i4", (2,))])
+assert ROW5424.itemsize == 32 and WIDE_ROW.itemsize == 72
 
 
 _cuda = None
@@ -93,6 +104,10 @@ def load_host() -> C.CDLL:
         L.fgh_free.argtypes = [C.c_void_p]
         L.fgh_dump_out.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.fgh_dump_range.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.fgh_dump_records.argtypes = [C.c_int, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p)]
         L.fgh_materialize_bench.restype = C.c_double
         L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
         L.fgh_is_valid_utf8.argtypes = [C.c_void_p, C.c_int64]
@@ -166,10 +181,26 @@ class BatchResult:
         def arr(p, dtype, count, cols=None):
             if not p or count == 0:
                 return np.zeros((0,) if cols is None else (0, cols), dtype=dtype)
+            if isinstance(p, int):
+                p = C.c_void_p(p)
             a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize * (cols or 1),))
             a = a.view(dtype)
             return a if cols is None else a.reshape(count, cols)
 
+        # RFC5424: compact rows (the columns below are derived views / empty)
+        self.rows5424 = arr(out.rows5424, ROW5424, n)
+        self.entries8 = arr(out.entries8, np.uint64, out.n_entries8)
+        self.wide_rows = arr(out.wide_rows, WIDE_ROW, out.n_wide)
+        self.arena = arr(out.arena, np.uint8, out.arena_bytes)
+        if fmt == FMT_RFC5424:
+            self.ts = self.rows5424["ts"] if n else np.zeros(0)
+            self.meta = self.rows5424["meta"] if n else np.zeros(0, np.uint32)
+            for name in ("hostname", "appname", "procid", "msgid", "msg", "full_msg", "sd"):
+                setattr(self, name, np.zeros((0, 2), np.int32))
+            self.entry_name = arr(out.entry_name, np.int32, ne, 2)
+            self.entry_val = arr(out.entry_val, np.uint64, ne)
+            self.entry_meta = arr(out.entry_meta, np.uint8, ne)
+            return
         self.ts = arr(out.ts, np.float64, n)
         self.meta = arr(out.meta, np.uint32, n)
         self.hostname = arr(out.hostname, np.int32, n, 2)
@@ -186,6 +217,24 @@ class BatchResult:
     @property
     def status(self) -> np.ndarray:
         return self.meta & 0xFF
+
+    def spans5424(self, offsets: np.ndarray) -> dict[str, np.ndarray]:
+        """RFC5424 compact rows -> absolute (off, len) spans like the fg_row5424_* helpers of the C header (rows that are
+        errors or FG_FLAG_WIDE get off = -1)."""
+        r = self.rows5424
+        lo = offsets[:-1].astype(np.int64)
+        flags = r["meta"] >> 24
+        good = ((r["meta"] & 0xFF) == 0) & ((flags & 0x80) == 0)
+        sp = r["sp"].astype(np.int64)
+        out = {}
+        for k, name in enumerate(("hostname", "appname", "procid", "msgid")):
+            out[name] = np.stack([np.where(good, lo + sp[:, k] + 1, -1), np.where(good, sp[:, k + 1] - sp[:, k] - 1, 0)], axis=1)
+        mo, ml = r["msg_off"].astype(np.int64), r["msg_len"].astype(np.int64)
+        out["msg"] = np.stack([np.where(good & (ml > 0), lo + mo, -1), np.where(good, ml, 0)], axis=1)
+        bom = np.where((flags & 0x40) != 0, 3, 0)
+        out["full_msg"] = np.stack([np.where(good, lo + bom, -1), np.where(good, mo + ml - bom, 0)], axis=1)
+        out["sd"] = np.stack([r["sd_first"].astype(np.int64), np.where(good, r["sd_count"].astype(np.int64), 0)], axis=1)
+        return out
 
 
 class BatchDecoder:
@@ -289,12 +338,14 @@ class BatchDecoder:
     def kernel_launches(self) -> int:
         return int(self.L.fg_kernel_launches(self.ctx))
 
-    def dump(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 8) -> tuple[bytes, np.ndarray]:
-        """Materialise every Record of a decoded batch and render the canonical parity dump."""
+    def dump(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 8, lo: int = 0,
+             hi: int | None = None) -> tuple[bytes, np.ndarray]:
+        """Materialise the Records of lines [lo, hi) of a decoded batch and render the canonical parity dump."""
+        hi = res.n if hi is None else hi
         pb, po = C.c_void_p(), C.c_void_p()
-        self.H.fgh_dump_out(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads, C.byref(pb), C.byref(po))
+        self.H.fgh_dump_range(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), lo, hi, nthreads, C.byref(pb), C.byref(po))
         try:
-            offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(res.n + 1,)).copy()
+            offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(hi - lo + 1,)).copy()
             buf = C.string_at(pb, int(offs[-1]))
         finally:
             self.H.fgh_free(pb)
@@ -322,6 +373,20 @@ class BatchDecoder:
 
     def materialize_seconds(self, res: BatchResult, data: np.ndarray, offsets: np.ndarray, nthreads: int = 1) -> float:
         return float(self.H.fgh_materialize_bench(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads))
+
+
+def dump_records(fmt: int, out: FgBatchOut, data: np.ndarray, offsets: np.ndarray) -> tuple[bytes, np.ndarray]:
+    """The product's Record materialiser + canonical dump over bare result arrays (no device, no context)."""
+    H = load_host()
+    pb, po = C.c_void_p(), C.c_void_p()
+    H.fgh_dump_records(fmt, C.byref(out), _ptr(data), _ptr(offsets), C.byref(pb), C.byref(po))
+    try:
+        offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(out.n + 1,)).copy()
+        buf = C.string_at(pb, int(offs[-1]))
+    finally:
+        H.fgh_free(pb)
+        H.fgh_free(po)
+    return buf, offs
 
 
 def shard_by_bytes(offsets: np.ndarray, G: int) -> np.ndarray:

@@ -11,7 +11,8 @@
  * The batched form is: N lines packed into one contiguous byte buffer plus an
  * int32 offsets array -> one fg_decode_batch() call -> N columnar results
  * (status code == the reference's Err(&'static str), or the Record fields as
- * zero-copy spans into the caller's byte buffer plus normalised scalars).
+ * zero-copy spans into the caller's byte buffer plus normalised scalars; escaped
+ * RFC5424 SD values are unescaped on the device into a small arena).
  *
  * Plain C: pointers and sizes only.  No CPU fallback exists behind this ABI:
  * every entry point that parses runs the sm_100a CUDA kernels or fails.
@@ -46,6 +47,7 @@ typedef enum fg_tag {
 #define FG_EM_NO_PREFIX 0x10u /* GELF: name already starts with '_' (gelf_decoder.rs:99-103); else host prepends "_" */
 #define FG_EM_SUFFIX 0x20u    /* LTSV: append the configured type suffix (ltsv_decoder.rs:131-136) */
 #define FG_EM_NAME_ESC 0x40u  /* GELF: name span holds JSON escapes */
+#define FG_EM_ARENA 0x80u     /* string value: off indexes fg_batch_out.arena (already unescaped), not `bytes` */
 
 /* row meta word: status | facility<<8 | severity<<16 | flags<<24 */
 #define FG_META_STATUS(m) ((uint32_t)(m)&0xFFu)
@@ -58,12 +60,72 @@ typedef enum fg_tag {
 #define FG_FLAG_MSG_ESC 0x08u      /* GELF: short_message span holds JSON escapes */
 #define FG_FLAG_FULL_ESC 0x10u     /* GELF: full_message span holds JSON escapes */
 #define FG_FLAG_NL_RETRY 0x20u     /* GELF: parsed through the raw-newline retry (gelf_decoder.rs:44-46) */
+#define FG_FLAG_BOM 0x40u          /* RFC5424: the line starts with a UTF-8 BOM, full_msg starts 3 bytes in (rfc5424_decoder.rs:65) */
+#define FG_FLAG_WIDE 0x80u         /* RFC5424: the row lives in fg_batch_out.wide_rows[row.sd_first] (line >= 64 KiB, ...) */
 
 /* (offset,len) into the `bytes` buffer given to the call; off < 0 => None */
 typedef struct fg_span {
     int32_t off;
     int32_t len;
 } fg_span;
+
+/* ---- RFC5424 results are COMPACT: 32 bytes per line + 8 bytes per structured-data row -------------------------
+ * All positions are u16 byte offsets relative to the start of the line (lines of 64 KiB or more, and a few other
+ * rare shapes, are flagged FG_FLAG_WIDE and delivered as fg_wide_row instead).  The header fields of RFC5424 are
+ * consecutive (rfc5424_decoder.rs:23-30), so five space positions give hostname / appname / procid / msgid:
+ *     hostname = [sp[0]+1, sp[1])   appname = [sp[1]+1, sp[2])   procid = [sp[2]+1, sp[3])   msgid = [sp[3]+1, sp[4])
+ *     msg      = msg_len ? [msg_off, msg_off+msg_len) : None
+ *     full_msg = [bom, end)  with bom = FG_FLAG_BOM ? 3 : 0 and end = msg_len ? msg_off+msg_len : msg_off
+ * Error rows (status != 0) carry only `meta`.  fg_row5424_* below decode a row into spans of the caller's buffer. */
+typedef struct fg_row5424 {
+    double ts;          /* Record.ts, bit-exact */
+    uint32_t meta;      /* FG_META_* */
+    uint32_t sd_first;  /* first row of this line in entries8 (FG_FLAG_WIDE: index into wide_rows) */
+    uint16_t sd_count;  /* rows of this line in entries8; 0 => Record.sd = None */
+    uint16_t sp[5];     /* positions of the 2nd .. 6th space */
+    uint16_t msg_off;
+    uint16_t msg_len;
+} fg_row5424;
+
+/* entries8 rows (uint64), positions relative to the line start:
+ *   header : sd_id start | sd_id end << 16 | #pairs << 32 | FG_E8_HEADER          opens a StructuredData element
+ *   pair   : name start | name end << 16 | value end << 32 | flags                 value starts at name end + 2
+ *   ext    : arena offset | length << 32    the row right after a pair with FG_E8_ESC: its value, already unescaped
+ *            (rfc5424_decoder.rs:105-125) on the device, lives in fg_batch_out.arena */
+#define FG_E8_ESC (1ull << 48)
+#define FG_E8_HEADER (0x8000ull << 48)
+#define FG_E8_A(e) ((uint32_t)((e)&0xFFFFu))
+#define FG_E8_B(e) ((uint32_t)(((e) >> 16) & 0xFFFFu))
+#define FG_E8_C(e) ((uint32_t)(((e) >> 32) & 0xFFFFu))
+
+/* a line the compact row cannot hold: absolute spans like the LTSV / GELF columns; its structured data are rows
+ * [sd.off, sd.off+sd.len) of entry_name / entry_val / entry_meta */
+typedef struct fg_wide_row {
+    int32_t line;
+    uint32_t meta;
+    double ts;
+    fg_span hostname, appname, procid, msgid, msg, full_msg, sd;
+} fg_wide_row;
+
+static inline fg_span fg_row5424_field(const fg_row5424* r, int32_t line_off, int k /* 0 host, 1 app, 2 procid, 3 msgid */) {
+    fg_span s;
+    s.off = line_off + (int32_t)r->sp[k] + 1;
+    s.len = (int32_t)r->sp[k + 1] - (int32_t)r->sp[k] - 1;
+    return s;
+}
+static inline fg_span fg_row5424_msg(const fg_row5424* r, int32_t line_off) {
+    fg_span s;
+    s.off = r->msg_len ? line_off + (int32_t)r->msg_off : -1;
+    s.len = (int32_t)r->msg_len;
+    return s;
+}
+static inline fg_span fg_row5424_full(const fg_row5424* r, int32_t line_off) {
+    const int32_t bom = (FG_META_FLAGS(r->meta) & FG_FLAG_BOM) ? 3 : 0;
+    fg_span s;
+    s.off = line_off + bom;
+    s.len = (int32_t)r->msg_off + (int32_t)r->msg_len - bom;
+    return s;
+}
 
 /* LTSV schema value types (ltsv_decoder.rs:36-43) */
 typedef enum fg_ltsv_type { FG_LTSV_STRING = 0, FG_LTSV_BOOL = 1, FG_LTSV_F64 = 2, FG_LTSV_I64 = 3, FG_LTSV_U64 = 4 } fg_ltsv_type;
@@ -95,11 +157,20 @@ typedef struct fg_batch_out {
     const fg_span* msg;
     const fg_span* full_msg; /* on error rows of LTSV: off = byte offset of the failing part */
     const fg_span* sd;       /* {first entry, entry count} ; count 0 => Record.sd = None */
+    /* side table of LTSV / GELF, and of the RFC5424 wide rows */
     const fg_span* entry_name;  /* [n_entries] */
     const uint64_t* entry_val;  /* string: off | len<<32 ; bool/i64/u64/f64: the 8 value bytes ; header: #pairs */
     const uint8_t* entry_meta;  /* FG_EM_* */
     const int32_t* line_offsets; /* fg_split_decode only: [n+1] line starts into the stream (each line still
                                     carries its "\n" / "\r\n" terminator); NULL otherwise */
+    /* RFC5424 (the columns ts .. sd above are NULL for this format) */
+    const fg_row5424* rows5424; /* [n] */
+    const uint64_t* entries8;   /* [n_entries8] */
+    int32_t n_entries8;
+    int32_t n_wide;             /* rows flagged FG_FLAG_WIDE */
+    const fg_wide_row* wide_rows;
+    const uint8_t* arena;       /* unescaped SD values (FG_E8_ESC extension rows, FG_EM_ARENA) */
+    int64_t arena_bytes;
     /* timings of the call, milliseconds */
     float kernel_ms; /* sum of parse-kernel time (CUDA events on the launch stream) */
     float total_ms;  /* H2D + kernels + D2H wall time */

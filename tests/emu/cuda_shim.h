@@ -1,0 +1,40 @@
+// cuda_shim.h — just enough of the CUDA device vocabulary to compile the line-walker sources
+// (flowgger_b200/csrc/fg_r5fast.cuh, fg_common.cuh, ...) with g++ for the CPU test-suite.
+// TEST INFRASTRUCTURE: the emulation build (tests/emu/libfg_emu.so) runs the DEVICE LOGIC one lane at a time so that
+// `pytest -m "not gpu"` can compare it with the oracle; nothing in the product libraries includes or links this.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define FG_DEV static inline
+
+struct uint4 { uint32_t x, y, z, w; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
+// IEEE round-to-nearest-even is the host default; these are exact stand-ins for the device intrinsics
+static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t bits = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d;
+    std::memcpy(&d, &bits, 8);
+    return d;
+}
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+}
+
+// host stand-ins for the types fg_kernels.cuh mentions and the warp intrinsics the round-1 scanner calls directly
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline void __syncwarp() {}
+static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
+#define __grid_constant__
