@@ -8,8 +8,10 @@
 //                        atomic place the rows, which are copied out with the 32-byte row of every line.
 //   unescape5424_kernel  the few lines (≈8 % at C2) whose SD values hold a backslash: unescape_sd_value
 //                        (rfc5424_decoder.rs:105-125) into the batch arena, one thread per listed line.
-//   wide5424_kernel      the lines the fast path cannot represent (>= 64 KiB, longer than the tile, rows that do not fit
-//                        behind the cursor): the round-1 scanner of fg_rfc5424.cuh straight from global memory.
+//   wide5424_kernel      the SLOW path: every line the fast walker does not recognise as regular (malformed lines and
+//                        their error strings, legal-but-unusual shapes, lines >= 64 KiB or longer than the tile, rows that
+//                        do not fit behind the cursor) goes through the exact scanner of fg_rfc5424.cuh straight from
+//                        global memory (≈0.6 % of the lines at C2).
 // The last two run over device-side work lists, so a batch needs no host round trip between the three launches.
 #include "fg_kernels.cuh"
 
@@ -38,8 +40,12 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     const uint32_t lane = (uint32_t)tid & 31u;
     const int first = blockIdx.x * LINES;
     const int last = min(P.n, first + LINES);
-    uint32_t* bm = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    uint16_t* bm16 = reinterpret_cast<uint16_t*>(bm);
+    // two bitmaps behind the tile: I ("may end a token") and V ('"' / '\\'), each tile_bytes / 8 + 16 bytes
+    const int bm_bytes = P.tile_bytes / 8 + 16;
+    uint32_t* bmI = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
+    uint32_t* bmV = reinterpret_cast<uint32_t*>(tile + P.tile_bytes + bm_bytes);
+    uint16_t* bmI16 = reinterpret_cast<uint16_t*>(bmI);
+    uint16_t* bmV16 = reinterpret_cast<uint16_t*>(bmV);
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -72,13 +78,17 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- stage 1: structural bitmap of the whole tile, 16 bytes per thread per step -------------------------
+        // ---- stage 1: structural bitmaps of the whole tile, 16 bytes per thread per step ------------------------
         const int ngran = (int)(nbytes >> 4);
         for (int g = tid; g < ngran; g += LINES) {
             const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
-            bm16[g] = (uint16_t)r5_classify16(v.x, v.y, v.z, v.w);
+            bmI16[g] = (uint16_t)r5_classify16(v.x, v.y, v.z, v.w);
+            bmV16[g] = (uint16_t)r5_classify16_v(v.x, v.y, v.z, v.w);
         }
-        if (tid < 6) bm16[ngran + tid] = 0;  // r5_window reads one word past the last granule
+        if (tid < 6) {  // r5_window reads up to two words past the last granule
+            bmI16[ngran + tid] = 0;
+            bmV16[ngran + tid] = 0;
+        }
         __syncthreads();
 
         // ---- stage 2: one thread per line ------------------------------------------------------------------------
@@ -96,14 +106,13 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         }
         const bool too_long = le - ls > 65535;
         R5Fast res;
-        r5_walk(tile, bm, ls, (too_long || bad_utf8) ? ls : le, res);
-        if (too_long) res.wide = true;
+        const bool regular = r5_regular(tile, bmI, bmV, ls, (too_long || bad_utf8 || !active) ? ls : le, res);
         if (bad_utf8) {
             res.status = FG_ES_INVALID_UTF8;
             res.n_entries = 0;
-            res.wide = false;
         }
-        const bool wide = active && res.wide;
+        // anything that is not a regular line (malformed, unusual but legal, 64 KiB or longer) is redone by the slow kernel
+        const bool wide = active && !regular && !bad_utf8;
         const uint32_t my_n = (active && !wide && res.status == FG_ST_OK) ? res.n_entries : 0u;
         const bool esc = my_n != 0u && res.esc;
 
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         if (wide) P.wide_list[s_base[2] + wide_at] = (uint32_t)i;
         if (active && !wide) {
             const bool ok = res.status == FG_ST_OK;
-            const uint32_t meta = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);
+            const uint32_t meta = ok ? (res.facility << 8) | (res.severity << 16) | (res.flags << 24) : res.status | 0x00FFFF00u;
             uint4 lo4, hi4;
             lo4.x = (uint32_t)__double2loint(res.ts);
             lo4.y = (uint32_t)__double2hiint(res.ts);
@@ -183,14 +192,13 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
             o0 = P.offsets[line];
             if ((unsigned long long)first + count > (unsigned long long)P.entry_cap) count = 0;  // side table overflowed: the batch is redone
         }
+        // arena records are [u16 length][bytes], 2-byte aligned
         uint32_t tot = 0;
         for (uint32_t e = 0; e < count; ++e) {
             const unsigned long long v = P.entries[first + e];
-            if (v & kE8Header) continue;
-            if (v & kE8Esc) {
+            if (!(v & kE8Header) && (v & kE8Esc)) {
                 const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
-                tot += (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), nullptr);
-                ++e;  // its extension row
+                tot += (2u + (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), nullptr) + 1u) & ~1u;
             }
         }
         uint32_t inc = tot;
@@ -207,13 +215,12 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
         uint32_t at = abase + inc - tot;
         for (uint32_t e = 0; e < count; ++e) {
             const unsigned long long v = P.entries[first + e];
-            if (v & kE8Header) continue;
-            if (v & kE8Esc) {
+            if (!(v & kE8Header) && (v & kE8Esc)) {
                 const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
-                const uint32_t l = (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at);
-                P.entries[first + e + 1] = (unsigned long long)at | ((unsigned long long)l << 32);
-                at += l;
-                ++e;
+                const uint32_t l = (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at + 2);
+                *reinterpret_cast<uint16_t*>(P.arena + at) = (uint16_t)l;
+                P.entries[first + e] = (v & 0xFFFFFFFFull) | ((unsigned long long)(at >> 1) << 32) | kE8Arena;
+                at += (2u + l + 1u) & ~1u;
             }
         }
     }
@@ -279,6 +286,11 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
             res.facility = res.severity = 0xFFu;
         }
         const bool ok = res.status == FG_ST_OK;
+        if (!ok) {  // an error row is its status, nothing else
+            P.rows[2 * (size_t)line] = make_uint4(0u, 0u, res.status | 0x00FFFF00u, 0u);
+            P.rows[2 * (size_t)line + 1] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         const uint32_t widx = atomicAdd(P.counters + K5_WIDE_ROWS, 1u);
         const uint32_t meta = res.status | (res.facility << 8) | (res.severity << 16) | ((res.flags | kFlagWide) << 24);
         if (widx < P.wide_cap) {
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
 
 }  // namespace
 
-int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 32; }
+int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + 2 * (tile_bytes / 8 + 16); }
 
 cudaError_t configure_parse5424(int max_tile_bytes) {
     return cudaFuncSetAttribute(parse5424_kernel<kFastLines, kFastCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -316,7 +328,7 @@ cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream) {
     // the work lists are usually short: a fixed small grid strides over them
     const int lgrid = (int)min((long long)(p.n + 127) / 128, 148LL * 8);
     unescape5424_kernel<<<lgrid, 128, 0, stream>>>(p);
-    wide5424_kernel<<<(int)min((long long)(p.n + 31) / 32, 148LL * 4), 32, 0, stream>>>(p);
+    wide5424_kernel<<<(int)min((long long)(p.n + 31) / 32, 148LL * 24), 32, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

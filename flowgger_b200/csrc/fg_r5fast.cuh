@@ -1,31 +1,35 @@
-// fg_r5fast.cuh — RFC5424 fast path: structural bitmap + bit-walk over a shared-memory tile.
+// fg_r5fast.cuh — RFC5424 fast path: structural bitmaps + one-pair-per-step walk over a shared-memory tile.
 //
 // B200-native replacement for RFC5424Decoder::decode
 // (/root/reference/src/flowgger/decoder/rfc5424_decoder.rs:18-49) and its helpers BOM::parse :63-71,
 // parse_pri_version :74-92, rfc3339_to_unix :94-99, parse_data :127-161, parse_msg :163-172,
-// parse_sd_data :174-242.  Two stages per CTA tile (a contiguous span of lines staged by one TMA bulk copy):
+// parse_sd_data :174-242 — for REGULAR lines, i.e. lines of the shape every syslog sender emits:
+//     <PRI>1 TS HOST APP PROCID MSGID (-|[id name="value" name="value"][id ...]) MSG
+// The walker proves regularity as it goes; the first byte that does not fit (a BOM, a header field holding a
+// delimiter-class byte, a lower-case 't', a stray quote, two spaces between params, any malformed line ...) hands the
+// line to the exact scanner of the slow kernel (fg_rfc5424.cuh), which restates the reference's state machine arm by
+// arm and produces every error string.  Regular lines therefore never carry an error status.
 //
 //   stage 1  r5_classify16: every thread takes 16-byte granules of the flat tile (LDS.128, conflict-free, all 32 lanes
-//            busy) and writes one bit per byte into a bitmap: I = "this byte may end a token".  I is a cheap SUPERSET of
-//            the bytes the grammar cares about (7 SWAR ops per 4 bytes, exact per byte, no cross-byte carries):
-//                b <= 0x22            control bytes, ' ', '!', '"'
-//                (b & 0x1E) == 0x1C   0x1C 0x1D '<' '=' '\\' ']' '|' '}'
-//                b >= 0x7F            DEL and every non-ASCII byte
-//            so every byte that is NOT flagged is a legal SD-NAME character and can never end a header field, an sd_id,
-//            a name or a value; the flagged bytes that turn out to be ordinary ('!', '<', '|', '}', ...) cost the walker
-//            one extra step.
-//   stage 2  r5_walk: one thread per line hops from flagged byte to flagged byte (two bitmap words, a funnel shift and
-//            a find-first-set per hop), peeks at the byte and drives the reference's state machine token by token.  The
-//            32 lines of a warp advance in lock step (every loop is a warp-uniform `while (any)`), so a warp pays the
-//            maximum number of TOKENS over its lanes, not of bytes.
+//            busy) and writes two bits per byte into two bitmaps (exact per byte, no cross-byte carries):
+//              I  "may end a token", a cheap SUPERSET of the delimiters (7 SWAR ops per 4 bytes):
+//                   b <= 0x22            control bytes, ' ', '!', '"'
+//                   (b & 0x1E) == 0x1C   0x1C 0x1D '<' '=' '\\' ']' '|' '}'
+//                   b >= 0x7F            DEL and every non-ASCII byte
+//                 every byte that is NOT flagged is a legal SD-NAME character (:188-192) and is neither a space, a
+//                 quote, '=', ']' nor a backslash;
+//              V  exactly '"' and '\\' (what can end or escape inside an SD value).
+//   stage 2  r5_regular: one thread per line.  Header: the first six flagged bytes must be the six spaces of
+//            splitn(7, ' ') (:23).  PRI and the RFC3339 stamp are parsed at fixed offsets.  Structured data: ONE
+//            name="value" pair per loop iteration — a find-first-set on I gives the '=' that ends the name, a
+//            find-first-set on V the closing quote — and the 32 lines of a warp advance in lock step, so a warp pays
+//            the maximum number of PAIRS over its lanes.
 //
 // Structured-data rows are staged as 8-byte packed entries (u16 positions relative to the line start) in the line's OWN
-// already-consumed bytes of the tile: slot k may be written once the cursor has passed its last byte, so no scratch table
-// exists on this path.  A line whose rows do not fit behind the cursor (dozens of 4-byte pairs) or that is 64 KiB or
-// longer is handed to the wide kernel (fg_rfc5424.cuh, the round-1 scanner reading global memory).
+// already-consumed bytes of the tile: slot k may be written once the cursor has passed its last byte.
 //
 // The unescape of SD values (:105-125) is done by unescape5424_kernel (fg_parse5424.cu) into the batch's arena; this
-// walker only reserves the extension slot behind every pair whose value holds a backslash.
+// walker only marks the pairs whose value holds a backslash.
 #pragma once
 #include "fg_common.cuh"
 #include "fg_status.h"
@@ -44,10 +48,22 @@ FG_DEV uint32_t r5_flags(uint32_t w) {
 }
 // the four 0x80 flags of a word -> bits 28..31 (byte j -> bit 28 + j); bits 24..27 of the product are always 0
 FG_DEV uint32_t r5_nibble_top(uint32_t f) { return f * 0x00204081u; }
-FG_DEV uint32_t r5_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    const uint32_t n0 = r5_nibble_top(r5_flags(w0)), n1 = r5_nibble_top(r5_flags(w1));
-    const uint32_t n2 = r5_nibble_top(r5_flags(w2)), n3 = r5_nibble_top(r5_flags(w3));
+FG_DEV uint32_t r5_gather16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    const uint32_t n0 = r5_nibble_top(f0), n1 = r5_nibble_top(f1), n2 = r5_nibble_top(f2), n3 = r5_nibble_top(f3);
     return (n0 >> 28) | ((n1 >> 24) & 0xF0u) | ((n2 >> 20) & 0xF00u) | ((n3 >> 16) & 0xF000u);
+}
+FG_DEV uint32_t r5_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return r5_gather16(r5_flags(w0), r5_flags(w1), r5_flags(w2), r5_flags(w3));
+}
+// 0x80 in every byte of w that is '"' (0x22) or '\\' (0x5C); exact per byte
+FG_DEV uint32_t r5_vflags(uint32_t w) {
+    const uint32_t x = w ^ 0x22222222u, y = w ^ 0x5C5C5C5Cu;
+    const uint32_t tx = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 set: byte != '"'
+    const uint32_t ty = ((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y;  // bit 7 set: byte != '\\'
+    return ~(tx & ty) & 0x80808080u;
+}
+FG_DEV uint32_t r5_classify16_v(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return r5_gather16(r5_vflags(w0), r5_vflags(w1), r5_vflags(w2), r5_vflags(w3));
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------------------------
@@ -57,18 +73,22 @@ FG_DEV uint32_t r5_window(const uint32_t* bm, int t) {
     return fg_funnel_r(bm[k], bm[k + 1], (uint32_t)t & 31u);
 }
 
-// packed 8-byte side-table rows (positions relative to the line start, < 65536)
-//   pair  : name_start | name_end << 16 | value_end << 32 | flags << 48   (value starts at name_end + 2)
-//   header: sd_id start | sd_id end << 16 | #pairs << 32 | 0x8000 << 48
-//   ext   : the row after a pair with FG_E8_ESC: arena offset | unescaped length << 32 (written by unescape5424_kernel)
+// packed 8-byte side-table rows (positions relative to the line start, < 65536); bits 63..62 select the kind
+//   10 header: sd_id start | sd_id end << 16 | #pairs << 32
+//   00 pair  : name_start | name_end << 16 | value_end << 32 | flags << 48   (value starts at name_end + 2)
+//              flag bit 48 (kE8Esc) = the value holds a backslash; such rows only exist between parse5424_kernel and
+//              unescape5424_kernel, which rewrites them as
+//   01 arena pair: name_start | name_end << 16 | (arena offset / 2) << 32; the arena record is [u16 length][bytes],
+//              2-byte aligned: the value with unescape_sd_value (:105-125) already applied
 constexpr unsigned long long kE8Esc = 1ull << 48;
-constexpr unsigned long long kE8Header = 0x8000ull << 48;
+constexpr unsigned long long kE8Header = 1ull << 63;
+constexpr unsigned long long kE8Arena = 1ull << 62;
 FG_DEV unsigned long long r5_pack_pair8(int ns, int ne, int ve, bool esc) {
     return (unsigned long long)(uint32_t)ns | ((unsigned long long)(uint32_t)ne << 16) | ((unsigned long long)(uint32_t)ve << 32) |
            (esc ? kE8Esc : 0ull);
 }
 FG_DEV unsigned long long r5_pack_header8(int es, int id_end, uint32_t pairs) {
-    return (unsigned long long)(uint32_t)es | ((unsigned long long)(uint32_t)id_end << 16) | ((unsigned long long)pairs << 32) | kE8Header;
+    return (unsigned long long)(uint32_t)es | ((unsigned long long)(uint32_t)id_end << 16) | ((unsigned long long)(pairs & 0xFFFFu) << 32) | kE8Header;
 }
 
 struct R5Fast {
@@ -78,7 +98,6 @@ struct R5Fast {
     int msg_o, msg_l;             // msg span; msg_l == 0 => msg None and msg_o = end of full_msg
     uint32_t n_entries;           // 8-byte rows staged at stage[0 .. n_entries)
     unsigned long long* stage;
-    bool wide;  // not representable / not stageable here: the wide kernel redoes this line
     bool esc;   // some value holds a backslash (the line goes on the unescape work list)
 };
 
@@ -108,13 +127,21 @@ FG_DEV int r5_unescape(const uint8_t* v, int len, uint8_t* out) {
     return o;
 }
 
-constexpr uint32_t kFlagBom = 0x40u;   // FG_FLAG_BOM
 constexpr uint32_t kFlagWide = 0x80u;  // FG_FLAG_WIDE
 
-// T: tile bytes (shared memory), bm: its bitmap; the line is T[ls, le).  Idle lanes pass ls == le.
-// ALL lanes of a warp must call this together.
-FG_DEV void r5_walk(uint8_t* T, const uint32_t* bm, int ls, int le, R5Fast& r) {
+// Days from 1970-01-01 of a date already known to be valid, and the calendar checks of the fast stamp parser
+FG_DEV uint32_t r5_digit(const uint8_t* T, int at, uint32_t& bad) {
+    const uint32_t d = (uint32_t)T[at] - (uint32_t)'0';
+    bad |= d > 9u ? 1u : 0u;
+    return d;
+}
+
+// T: tile bytes (shared memory), bmI / bmV: its bitmaps; the line is T[ls, le).  Idle lanes pass ls == le.
+// Returns true when the line is regular and `r` holds its Record fields (status is always Ok); false hands the line to
+// the slow kernel.  ALL lanes of a warp must call this together.
+FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, const uint32_t* bmV, int ls, int le, R5Fast& r) {
     r.ts = 0.0;
+    r.status = FG_ST_OK;
     r.facility = 0xFFu;
     r.severity = 0xFFu;
     r.flags = 0;
@@ -122,237 +149,166 @@ FG_DEV void r5_walk(uint8_t* T, const uint32_t* bm, int ls, int le, R5Fast& r) {
     r.msg_o = r.msg_l = 0;
     r.n_entries = 0;
     r.stage = nullptr;
-    r.wide = false;
     r.esc = false;
-    uint32_t status = FG_ST_OK;
+    bool ok = le - ls >= 32;  // "<1>1 2015-08-05T15:53:45Z h a p m -" is 35 bytes: nothing shorter is a complete line
 
-    // ---- BOM::parse :63-71 ---------------------------------------------------------------------
-    int b = ls;
-    if (le - ls >= 3 && T[ls] == 0xEFu && T[ls + 1] == 0xBBu && T[ls + 2] == 0xBFu) {
-        b = ls + 3;
-        r.flags |= kFlagBom;
-    } else if (!(le > ls && T[ls] == '<')) {
-        status = FG_E5_BOM;
-    }
-
-    // ---- splitn(7, ' ') :23 — the first six spaces, one bitmap hop each --------------------------
+    // ---- splitn(7, ' ') :23 — the first six flagged bytes after the leading '<' must be the six spaces -------------
     int sp[6];
     {
-        int t = b;
-        bool act = status == FG_ST_OK;
+        int t = ls + 1;  // the '<' that opens PRI is itself a flagged byte
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            bool s = act;
-            for (;;) {
-                if (s) {
-                    const uint32_t W = r5_window(bm, t);
-                    t += W ? fg_ffs(W) - 1 : 32;
-                    if (t >= le) {
-                        s = false;
-                        act = false;
-                    } else if (W) {
-                        if (T[t] == ' ') s = false;
-                        else ++t;
-                    }
-                }
-                if (!fg_any(s)) break;
+            uint32_t W = r5_window(bmI, t);
+            if (W == 0u) {  // a field longer than 31 bytes (a stamp with nanoseconds and an offset is 35): look once more
+                t += 32;
+                W = r5_window(bmI, t);
             }
-            sp[k] = act ? t : le;
-            if (act) ++t;
+            t += fg_ffs(W) - 1;  // W == 0: t - 1, caught by the check below
+            ok = ok && W != 0u && t < le && T[t] == ' ';
+            sp[k] = t;
+            t = ok ? t + 1 : ls;
         }
     }
-    const int nsp = (sp[0] < le) + (sp[1] < le) + (sp[2] < le) + (sp[3] < le) + (sp[4] < le) + (sp[5] < le);
-
-    // ---- parse_pri_version :74-92 on part0 = [b, sp0) --------------------------------------------
-    if (status == FG_ST_OK) {
-        const int e0 = sp[0];
-        if (!(b < e0 && T[b] == '<')) {
-            status = FG_E5_PRI_BRACKETS;
-        } else {
-            int gt = b + 1;
-            while (gt < e0 && T[gt] != '>') ++gt;
-            uint32_t pri = 0;
-            if (!parse_u8(T, b + 1, gt, pri)) status = FG_E5_INVALID_PRI;
-            else if (gt >= e0) status = FG_E5_MISSING_VERSION;
-            else if (!(e0 - gt == 2 && T[gt + 1] == '1')) status = FG_E5_UNSUPPORTED_VERSION;
-            else {
-                r.facility = pri >> 3;
-                r.severity = pri & 7u;
-            }
-        }
+    // ---- parse_pri_version :74-92: '<' 1..3 digits '>' '1' -----------------------------------------------------
+    uint32_t bad = 0;
+    {
+        const int l0 = sp[0] - ls;  // 4..6
+        ok = ok && T[ls] == '<' && l0 >= 4 && l0 <= 6;
+        const int gt = ok ? sp[0] - 2 : ls;
+        ok = ok && T[gt] == '>' && T[gt + 1] == '1';
+        uint32_t pri = 0;
+        for (int q = ls + 1; q < gt; ++q) pri = pri * 10u + r5_digit(T, q, bad);  // 1..3 iterations
+        ok = ok && pri <= 255u;
+        r.facility = pri >> 3;
+        r.severity = pri & 7u;
     }
-    fg_syncwarp();
-    // ---- timestamp :25, :94-103 ---------------------------------------------------------------
-    if (status == FG_ST_OK) {
-        if (nsp < 1) status = FG_E5_MISSING_TS;
-        else if (!parse_rfc3339(T, sp[0] + 1, sp[1], r.ts)) status = FG_E5_BAD_TS;
-        else if (nsp < 6) status = FG_E5_MISSING_HOST + (uint32_t)(nsp - 1);  // :26-30 in order
+    // ---- rfc3339_to_unix :94-99 at fixed offsets: YYYY-MM-DDTHH:MM:SS[.f{1,9}](Z|+HH:MM|-HH:MM) ---------------------
+    {
+        const int a = ok ? sp[0] + 1 : ls, e = ok ? sp[1] : ls;
+        const int L = e - a;
+        ok = ok && L >= 20;
+        const int z = ok ? e - 1 : ls;         // 'Z', or the last digit of the offset
+        const bool zulu = T[z] == 'Z';
+        const int zone = zulu ? z : z - 5;     // where the zone designator starts
+        DateTime t;
+        t.year = (int)(r5_digit(T, a, bad) * 1000u + r5_digit(T, a + 1, bad) * 100u + r5_digit(T, a + 2, bad) * 10u + r5_digit(T, a + 3, bad));
+        t.month = (int)(r5_digit(T, a + 5, bad) * 10u + r5_digit(T, a + 6, bad));
+        t.day = (int)(r5_digit(T, a + 8, bad) * 10u + r5_digit(T, a + 9, bad));
+        t.hour = (int)(r5_digit(T, a + 11, bad) * 10u + r5_digit(T, a + 12, bad));
+        t.minute = (int)(r5_digit(T, a + 14, bad) * 10u + r5_digit(T, a + 15, bad));
+        t.second = (int)(r5_digit(T, a + 17, bad) * 10u + r5_digit(T, a + 18, bad));
+        ok = ok && T[a + 4] == '-' && T[a + 7] == '-' && T[a + 10] == 'T' && T[a + 13] == ':' && T[a + 16] == ':';
+        // fraction: [a + 19, zone) is empty or '.' + 1..9 digits
+        const int fl = zone - (a + 19);
+        ok = ok && (fl == 0 || (fl >= 2 && fl <= 10 && T[a + 19] == '.'));
+        uint32_t nanos = 0, mult = 100000000u;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k + 1 < fl) nanos += r5_digit(T, a + 20 + k, bad) * mult;
+            mult /= 10u;
+        }
+        t.nanos = nanos;
+        int off = 0;
+        if (!zulu) {
+            const uint32_t sg = T[zone];
+            const int oh = (int)(r5_digit(T, zone + 1, bad) * 10u + r5_digit(T, zone + 2, bad));
+            const int om = (int)(r5_digit(T, zone + 4, bad) * 10u + r5_digit(T, zone + 5, bad));
+            ok = ok && (sg == '+' || sg == '-') && T[zone + 3] == ':' && oh <= 23 && om <= 59 && zone >= a + 19;
+            off = oh * 3600 + om * 60;
+            if (sg == '-') off = -off;
+        }
+        t.offset_seconds = off;
+        ok = ok && bad == 0u && t.second <= 59;  // :60 (leap second stand-in) is the slow path's business
+        if (!ok) { t.year = 2000; t.month = 1; t.day = 1; t.hour = t.minute = t.second = 0; t.nanos = 0; t.offset_seconds = 0; }
+        double ts = 0.0;
+        ok = finish_datetime(t, false, ts) && ok;
+        r.ts = ts;
     }
     fg_syncwarp();
 
     // ---- parse_data :127-161 on part6 = [sp5+1, le) ------------------------------------------------
-    const int d = sp[5] + 1;
+    const int d = ok ? sp[5] + 1 : ls;
     int msg_from = le;
     bool walk = false;
-    if (status == FG_ST_OK) {
-        if (d >= le) status = FG_E5_MISSING_MSG;  // :129
-        else {
-            const uint32_t c0 = T[d];
-            if (c0 == '-') msg_from = d + 1;
-            else if (c0 == '[') walk = true;
-            else status = FG_E5_MALFORMED;  // :159
-        }
+    ok = ok && d < le;
+    if (ok) {
+        const uint32_t c0 = T[d];
+        if (c0 == '-') msg_from = d + 1;
+        else if (c0 == '[') walk = true;
+        else ok = false;
     }
     {
-        // Structured data, token-nested and in lock step: one outer iteration handles (per lane) either an sd_id or one
-        // name="value" pair.  st_id: at the first byte of an sd_id (:175-177); !st_id: between params (!in_name, name None,
-        // !in_value).  Rows are staged behind the cursor in the line's own bytes (slot k ends at sbase + 8 (k + 1)).
+        // Structured data: one name="value" pair per iteration and lane (plus the sd_id before the first pair of an element
+        // and the "]" / "][" after the last).  Rows are staged behind the cursor in the line's own bytes: slot k ends at
+        // sbase + 8 (k + 1) and may be written once the cursor has passed that byte.
         const int sbase = (ls + 7) & ~7;
         unsigned long long* stg = (unsigned long long*)(T + sbase);
-        uint32_t n = 1, pairs = 0, hdr = 0;
-        int i = d + 1, elem_start = d + 1, id_end = 0;
-        bool st_id = true, active = walk, wide = false, any_esc = false;
+        uint32_t n = 0, pairs = 0, hdr = 0;
+        int i = d + 1, elem_start = 0, id_end = 0;
+        bool st_id = true, active = walk, any_esc = false;
         while (fg_any(active)) {
-            // (A) sd_id: up to the first ' ' (unvalidated, may contain ']')
-            {
-                const bool scan = active && st_id;
-                bool s = scan;
-                for (;;) {
-                    if (s) {
-                        const uint32_t W = r5_window(bm, i);
-                        i += W ? fg_ffs(W) - 1 : 32;
-                        if (i >= le) s = false;
-                        else if (W) {
-                            if (T[i] == ' ') s = false;
-                            else ++i;
-                        }
-                    }
-                    if (!fg_any(s)) break;
-                }
-                if (scan) {
-                    if (i >= le) { active = false; status = FG_E5_MISSING_SD; }  // :177
-                    else { id_end = i; ++i; st_id = false; }
-                }
+            if (active && st_id) {  // sd_id: up to the first ' ' (:175-177); any other flagged byte inside it -> slow path
+                const uint32_t W = r5_window(bmI, i);
+                const int s1 = i + fg_ffs(W) - 1;
+                if (W == 0u || s1 >= le || T[s1] != ' ') { ok = false; active = false; }
+                else { elem_start = i; id_end = s1; i = s1 + 1; st_id = false; hdr = n++; pairs = 0; }
             }
-            // (B) between params: skip ' ' and stray '"' (:194, :232)
+            // name: unflagged bytes (all legal name characters, :188-192) up to '=' (:208), then '"' (:212)
+            int e = i;
+            if (active) {
+                const uint32_t W = r5_window(bmI, i);
+                e = i + fg_ffs(W) - 1;
+                if (W == 0u || (W & 1u) || e + 2 >= le || T[e] != '=' || T[e + 1] != '"') { ok = false; active = false; }
+            }
+            // value: up to the first unescaped '"' (:216, :217, :231) — hops over the exact '"' / '\\' bitmap
+            int c = e + 2;
+            bool has_bs = false;
             {
                 bool s = active;
                 for (;;) {
-                    bool more = false;
                     if (s) {
-                        if (i >= le) s = false;
-                        else {
-                            const uint32_t c = T[i];
-                            more = (c == ' ') || (c == '"');
-                            if (more) ++i;
-                            else s = false;
+                        const uint32_t W = r5_window(bmV, c);
+                        c += W ? fg_ffs(W) - 1 : 32;
+                        if (c >= le) s = false;
+                        else if (W) {
+                            if (T[c] == '"') s = false;
+                            else { has_bs = true; c += 2; }  // the escaped byte is skipped
                         }
                     }
-                    if (!fg_any(more)) break;
+                    if (!fg_any(s)) break;
                 }
-                if (active && i >= le) { active = false; status = FG_E5_SD_NO_END; }  // :239
             }
-            // classify the byte that ended (B)
-            bool do_name = false;
-            int name_start = 0, name_end = 0;
             if (active) {
-                const uint32_t c = T[i];
-                if (c == ']') {  // :197 end of this element, then :145-155
-                    if (sbase + 8 * (int)n > i + 1) { wide = true; active = false; }
-                    else {
+                if (c + 1 >= le || sbase + 8 * ((int)n + 1) > c + 1) { ok = false; active = false; }  // :239 / :148 / no room: slow path
+                else {
+                    stg[n++] = r5_pack_pair8(i - ls, e - ls, c - ls, has_bs);
+                    any_esc |= has_bs;
+                    ++pairs;
+                    const uint32_t nx = T[c + 1];
+                    if (nx == ' ') {
+                        i = c + 2;
+                        if (i >= le) { ok = false; active = false; }
+                    } else if (nx == ']') {  // :197 end of this element, then :145-155
                         stg[hdr] = r5_pack_header8(elem_start - ls, id_end - ls, pairs);
-                        if (i + 1 >= le) { active = false; status = FG_E5_MISSING_MSG; }  // :148
-                        else {
-                            const uint32_t c2 = T[i + 1];
-                            if (c2 == '[') { elem_start = i + 2; i += 2; hdr = n++; pairs = 0; st_id = true; }
-                            else if (c2 == ' ') { msg_from = i + 1; active = false; }
-                            else { active = false; status = FG_E5_MALFORMED; }  // :154
-                        }
-                    }
-                } else if (c >= 33u && c <= 126u && c != '=') {  // is_sd_name :188-192 ('"' and ']' excluded above)
-                    do_name = true;
-                    name_start = i;
-                    ++i;
-                } else {
-                    active = false;
-                    status = FG_E5_SD_FORMAT;  // :235
-                }
-            }
-            // (C) name: hop to the next flagged byte; the flagged bytes that are legal name characters are stepped over
-            {
-                bool s = do_name;
-                for (;;) {
-                    if (s) {
-                        const uint32_t W = r5_window(bm, i);
-                        i += W ? fg_ffs(W) - 1 : 32;
-                        if (i >= le) s = false;
-                        else if (W) {
-                            const uint32_t c = T[i];
-                            if (c == '!' || c == '<' || c == '\\' || c == '|' || c == '}') ++i;
-                            else s = false;
-                        }
-                    }
-                    if (!fg_any(s)) break;
-                }
-            }
-            bool do_val = false;
-            if (do_name) {
-                if (i >= le) { active = false; status = FG_E5_SD_NO_END; }
-                else if (T[i] != '=') { active = false; status = FG_E5_SD_FORMAT; }
-                else {
-                    name_end = i;
-                    ++i;
-                    if (i >= le) { active = false; status = FG_E5_SD_NO_END; }
-                    else if (T[i] != '"') { active = false; status = FG_E5_SD_FORMAT; }  // :212 is the only arm
-                    else { ++i; do_val = true; }
-                }
-            }
-            // (D) value: up to the first unescaped '"' (:216, :217, :231)
-            bool has_bs = false;
-            {
-                bool s = do_val;
-                for (;;) {
-                    if (s) {
-                        const uint32_t W = r5_window(bm, i);
-                        i += W ? fg_ffs(W) - 1 : 32;
-                        if (i >= le) s = false;
-                        else if (W) {
-                            const uint32_t c = T[i];
-                            if (c == '"') s = false;
-                            else if (c == '\\') { has_bs = true; i += 2; }  // the escaped byte is skipped
-                            else ++i;
-                        }
-                    }
-                    if (!fg_any(s)) break;
-                }
-            }
-            if (do_val) {
-                if (i >= le) { active = false; status = FG_E5_SD_NO_END; }
-                else {
-                    const int need = has_bs ? 2 : 1;
-                    if (sbase + 8 * ((int)n + need) > i + 1) { wide = true; active = false; }
-                    else {
-                        stg[n] = r5_pack_pair8(name_start - ls, name_end - ls, i - ls, has_bs);
-                        n += (uint32_t)need;
-                        any_esc |= has_bs;
-                        ++pairs;
-                        ++i;
-                    }
+                        const uint32_t n2 = c + 2 < le ? T[c + 2] : 0u;
+                        if (n2 == ' ') { msg_from = c + 2; active = false; }
+                        else if (n2 == '[') { i = c + 3; st_id = true; }
+                        else { ok = false; active = false; }
+                    } else { ok = false; active = false; }
                 }
             }
         }
-        if (walk && status == FG_ST_OK && !wide) {
+        if (walk && ok) {
             r.n_entries = n;
             r.stage = stg;
             r.esc = any_esc;
         }
-        r.wide = wide;
     }
 
     // ---- parse_msg :163-172, Record assembly :32-47 ------------------------------------------------
-    if (status == FG_ST_OK) {
-        // msg = line[msg_from..].trim(); full_msg = line.trim_end() of the BOM-stripped line (:46).  The byte before
-        // msg_from is '-' or ']', so when the rest is all whitespace full_msg ends at msg_from.
+    if (ok) {
+        // msg = line[msg_from..].trim(); full_msg = line.trim_end() (:46).  The byte before msg_from is '-' or ']', so when
+        // the rest is all whitespace full_msg ends at msg_from.
         const int hi = trim_end(T, msg_from, le);
         const int lo = trim_start(T, msg_from, hi);
         if (hi > lo) {
@@ -368,8 +324,8 @@ FG_DEV void r5_walk(uint8_t* T, const uint32_t* bm, int ls, int le, R5Fast& r) {
         r.sp4 = sp[4] - ls;
         r.sp5 = sp[5] - ls;
     }
-    r.status = status;
     fg_syncwarp();
+    return ok;
 }
 
 }  // namespace fg

@@ -328,9 +328,11 @@ static DecodeResult materialize_5424(const fg_batch_out& out, const uint8_t* byt
             name.append((const char*)line + FG_E8_A(v), FG_E8_B(v) - FG_E8_A(v));
             SDValue val;
             val.kind = SDValue::String;
-            if (v & FG_E8_ESC) {
-                const uint64_t ext = out.entries8[++e];  // value unescaped on the device (rfc5424_decoder.rs:105-125)
-                val.s.assign((const char*)out.arena + (uint32_t)ext, (size_t)(ext >> 32));
+            if (v & FG_E8_ARENA) {  // value unescaped on the device (rfc5424_decoder.rs:105-125): [u16 length][bytes]
+                const uint8_t* rec = out.arena + FG_E8_ARENA_OFF(v);
+                uint16_t l;
+                memcpy(&l, rec, 2);
+                val.s.assign((const char*)rec + 2, (size_t)l);
             } else {
                 val.s.assign((const char*)line + FG_E8_B(v) + 2, FG_E8_C(v) - (FG_E8_B(v) + 2));
             }

@@ -231,8 +231,7 @@ class BatchResult:
             out[name] = np.stack([np.where(good, lo + sp[:, k] + 1, -1), np.where(good, sp[:, k + 1] - sp[:, k] - 1, 0)], axis=1)
         mo, ml = r["msg_off"].astype(np.int64), r["msg_len"].astype(np.int64)
         out["msg"] = np.stack([np.where(good & (ml > 0), lo + mo, -1), np.where(good, ml, 0)], axis=1)
-        bom = np.where((flags & 0x40) != 0, 3, 0)
-        out["full_msg"] = np.stack([np.where(good, lo + bom, -1), np.where(good, mo + ml - bom, 0)], axis=1)
+        out["full_msg"] = np.stack([np.where(good, lo, -1), np.where(good, mo + ml, 0)], axis=1)
         out["sd"] = np.stack([r["sd_first"].astype(np.int64), np.where(good, r["sd_count"].astype(np.int64), 0)], axis=1)
         return out
 

@@ -60,8 +60,7 @@ typedef enum fg_tag {
 #define FG_FLAG_MSG_ESC 0x08u      /* GELF: short_message span holds JSON escapes */
 #define FG_FLAG_FULL_ESC 0x10u     /* GELF: full_message span holds JSON escapes */
 #define FG_FLAG_NL_RETRY 0x20u     /* GELF: parsed through the raw-newline retry (gelf_decoder.rs:44-46) */
-#define FG_FLAG_BOM 0x40u          /* RFC5424: the line starts with a UTF-8 BOM, full_msg starts 3 bytes in (rfc5424_decoder.rs:65) */
-#define FG_FLAG_WIDE 0x80u         /* RFC5424: the row lives in fg_batch_out.wide_rows[row.sd_first] (line >= 64 KiB, ...) */
+#define FG_FLAG_WIDE 0x80u         /* RFC5424: the row lives in fg_batch_out.wide_rows[row.sd_first] (unusual shape, line >= 64 KiB, ...) */
 
 /* (offset,len) into the `bytes` buffer given to the call; off < 0 => None */
 typedef struct fg_span {
@@ -70,12 +69,14 @@ typedef struct fg_span {
 } fg_span;
 
 /* ---- RFC5424 results are COMPACT: 32 bytes per line + 8 bytes per structured-data row -------------------------
- * All positions are u16 byte offsets relative to the start of the line (lines of 64 KiB or more, and a few other
- * rare shapes, are flagged FG_FLAG_WIDE and delivered as fg_wide_row instead).  The header fields of RFC5424 are
+ * All positions are u16 byte offsets relative to the start of the line.  Lines that are valid but not of the regular
+ * shape `<PRI>1 TS HOST APP PROCID MSGID (-|[id name="value" ...]...) MSG` (a BOM, a delimiter-class byte inside a
+ * header field, stray quotes ...) or are 64 KiB or longer are flagged FG_FLAG_WIDE and delivered as fg_wide_row
+ * instead; they are decoded by the slow, exact kernel.  The header fields of RFC5424 are
  * consecutive (rfc5424_decoder.rs:23-30), so five space positions give hostname / appname / procid / msgid:
  *     hostname = [sp[0]+1, sp[1])   appname = [sp[1]+1, sp[2])   procid = [sp[2]+1, sp[3])   msgid = [sp[3]+1, sp[4])
  *     msg      = msg_len ? [msg_off, msg_off+msg_len) : None
- *     full_msg = [bom, end)  with bom = FG_FLAG_BOM ? 3 : 0 and end = msg_len ? msg_off+msg_len : msg_off
+ *     full_msg = [0, end)  with end = msg_len ? msg_off+msg_len : msg_off
  * Error rows (status != 0) carry only `meta`.  fg_row5424_* below decode a row into spans of the caller's buffer. */
 typedef struct fg_row5424 {
     double ts;          /* Record.ts, bit-exact */
@@ -87,13 +88,15 @@ typedef struct fg_row5424 {
     uint16_t msg_len;
 } fg_row5424;
 
-/* entries8 rows (uint64), positions relative to the line start:
- *   header : sd_id start | sd_id end << 16 | #pairs << 32 | FG_E8_HEADER          opens a StructuredData element
- *   pair   : name start | name end << 16 | value end << 32 | flags                 value starts at name end + 2
- *   ext    : arena offset | length << 32    the row right after a pair with FG_E8_ESC: its value, already unescaped
- *            (rfc5424_decoder.rs:105-125) on the device, lives in fg_batch_out.arena */
-#define FG_E8_ESC (1ull << 48)
-#define FG_E8_HEADER (0x8000ull << 48)
+/* entries8 rows (uint64), positions relative to the line start; bits 63..62 select the kind:
+ *   FG_E8_HEADER : sd_id start | sd_id end << 16 | #pairs << 32        opens a StructuredData element
+ *   (neither)    : name start | name end << 16 | value end << 32      value = [name end + 2, value end), no escapes
+ *   FG_E8_ARENA  : name start | name end << 16 | (arena offset / 2) << 32
+ *                  the value held escapes and was unescaped on the device (rfc5424_decoder.rs:105-125): the record at
+ *                  that offset of fg_batch_out.arena is [uint16 length][bytes] */
+#define FG_E8_HEADER (1ull << 63)
+#define FG_E8_ARENA (1ull << 62)
+#define FG_E8_ARENA_OFF(e) ((uint32_t)(((e) >> 32) & 0x3FFFFFFFu) << 1)
 #define FG_E8_A(e) ((uint32_t)((e)&0xFFFFu))
 #define FG_E8_B(e) ((uint32_t)(((e) >> 16) & 0xFFFFu))
 #define FG_E8_C(e) ((uint32_t)(((e) >> 32) & 0xFFFFu))
@@ -120,10 +123,9 @@ static inline fg_span fg_row5424_msg(const fg_row5424* r, int32_t line_off) {
     return s;
 }
 static inline fg_span fg_row5424_full(const fg_row5424* r, int32_t line_off) {
-    const int32_t bom = (FG_META_FLAGS(r->meta) & FG_FLAG_BOM) ? 3 : 0;
     fg_span s;
-    s.off = line_off + bom;
-    s.len = (int32_t)r->msg_off + (int32_t)r->msg_len - bom;
+    s.off = line_off;
+    s.len = (int32_t)r->msg_off + (int32_t)r->msg_len;
     return s;
 }
 
@@ -169,7 +171,7 @@ typedef struct fg_batch_out {
     int32_t n_entries8;
     int32_t n_wide;             /* rows flagged FG_FLAG_WIDE */
     const fg_wide_row* wide_rows;
-    const uint8_t* arena;       /* unescaped SD values (FG_E8_ESC extension rows, FG_EM_ARENA) */
+    const uint8_t* arena;       /* unescaped SD values (FG_E8_ARENA records, FG_EM_ARENA spans) */
     int64_t arena_bytes;
     /* timings of the call, milliseconds */
     float kernel_ms; /* sum of parse-kernel time (CUDA events on the launch stream) */

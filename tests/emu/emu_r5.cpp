@@ -33,7 +33,7 @@ struct Tables {
 void put_row(Tables& t, int i, const fg::R5Fast& r, uint32_t first, uint32_t n) {
     fg_row5424 row;
     memset(&row, 0, sizeof row);
-    row.meta = r.status | (r.facility << 8) | (r.severity << 16) | (r.flags << 24);
+    row.meta = r.status == FG_ST_OK ? (r.facility << 8) | (r.severity << 16) | (r.flags << 24) : r.status | 0x00FFFF00u;
     row.sd_first = first;
     if (r.status == FG_ST_OK) {
         row.ts = r.ts;
@@ -55,6 +55,11 @@ uint32_t emu5424_classify16(const uint8_t* p) {
     memcpy(w, p, 16);
     return fg::r5_classify16(w[0], w[1], w[2], w[3]);
 }
+uint32_t emu5424_classify16_v(const uint8_t* p) {
+    uint32_t w[4];
+    memcpy(w, p, 16);
+    return fg::r5_classify16_v(w[0], w[1], w[2], w[3]);
+}
 
 int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int32_t tile_bytes, int32_t strip_eol,
                    const uint8_t* invalid, fg_batch_out* out) {
@@ -62,7 +67,7 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
     T->rows.resize((size_t)std::max(n, 1));
     const int64_t total_bytes = n > 0 ? offsets[n] : 0;
     std::vector<uint8_t> tile((size_t)tile_bytes + 64);
-    std::vector<uint32_t> bm((size_t)tile_bytes / 32 + 8);
+    std::vector<uint32_t> bmI((size_t)tile_bytes / 32 + 8), bmV((size_t)tile_bytes / 32 + 8);
     for (int first = 0; first < n; first += kLines) {
         const int last = std::min(n, first + kLines);
         int cur = first;
@@ -78,10 +83,14 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
             const int oend = offsets[cur + r];
             const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
             for (uint32_t k = 0; k < nbytes; ++k) tile[k] = (int64_t)base + k < total_bytes ? bytes[base + k] : 0;  // the bulk copy
-            uint16_t* bm16 = (uint16_t*)bm.data();
+            uint16_t* bmI16 = (uint16_t*)bmI.data();
+            uint16_t* bmV16 = (uint16_t*)bmV.data();
             const int ngran = (int)(nbytes >> 4);
-            for (int g = 0; g < ngran; ++g) bm16[g] = (uint16_t)emu5424_classify16(tile.data() + 16 * g);
-            for (int k = 0; k < 6; ++k) bm16[ngran + k] = 0;
+            for (int g = 0; g < ngran; ++g) {
+                bmI16[g] = (uint16_t)emu5424_classify16(tile.data() + 16 * g);
+                bmV16[g] = (uint16_t)emu5424_classify16_v(tile.data() + 16 * g);
+            }
+            for (int k = 0; k < 6; ++k) bmI16[ngran + k] = bmV16[ngran + k] = 0;
             for (int tid = 0; tid < r; ++tid) {
                 const int i = cur + tid;
                 const int ls = offsets[i] - base;
@@ -96,14 +105,12 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
                 }
                 const bool too_long = le - ls > 65535;
                 fg::R5Fast res;
-                fg::r5_walk(tile.data(), bm.data(), ls, (too_long || bad) ? ls : le, res);
-                if (too_long) res.wide = true;
+                const bool regular = fg::r5_regular(tile.data(), bmI.data(), bmV.data(), ls, (too_long || bad) ? ls : le, res);
                 if (bad) {
                     res.status = FG_ES_INVALID_UTF8;
                     res.n_entries = 0;
-                    res.wide = false;
                 }
-                if (res.wide) {
+                if (!regular && !bad) {
                     T->wide_list.push_back((uint32_t)i);
                     continue;
                 }
@@ -116,22 +123,22 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
             cur += r;
         }
     }
-    // unescape5424_kernel
+    // unescape5424_kernel: arena records are [u16 length][bytes], 2-byte aligned
     for (uint32_t line : T->esc_list) {
         const fg_row5424& row = T->rows[line];
         const int o0 = offsets[line];
         for (uint32_t e = row.sd_first; e < row.sd_first + row.sd_count; ++e) {
             const uint64_t v = T->e8[e];
-            if (v & fg::kE8Header) continue;
-            if (v & fg::kE8Esc) {
+            if (!(v & fg::kE8Header) && (v & fg::kE8Esc)) {
                 const int ne = (int)FG_E8_B(v), ve = (int)FG_E8_C(v);
                 const int l = fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), nullptr);
                 const size_t at = T->arena.size();
-                T->arena.resize(at + (size_t)l + 1);
-                fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at);
-                T->arena.resize(at + (size_t)l);
-                T->e8[e + 1] = (uint64_t)at | ((uint64_t)l << 32);
-                ++e;
+                T->arena.resize(at + ((2 + (size_t)l + 1) & ~(size_t)1) + 2);
+                fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at + 2);
+                const uint16_t l16 = (uint16_t)l;
+                memcpy(T->arena.data() + at, &l16, 2);
+                T->arena.resize(at + ((2 + (size_t)l + 1) & ~(size_t)1));
+                T->e8[e] = (v & 0xFFFFFFFFull) | ((uint64_t)(at >> 1) << 32) | fg::kE8Arena;
             }
         }
     }
@@ -180,6 +187,13 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
             res.facility = res.severity = 0xFFu;
         }
         const bool ok = res.status == FG_ST_OK;
+        if (!ok) {
+            fg_row5424 row;
+            memset(&row, 0, sizeof row);
+            row.meta = res.status | 0x00FFFF00u;
+            T->rows[line] = row;
+            continue;
+        }
         fg_wide_row w;
         memset(&w, 0, sizeof w);
         w.line = (int32_t)line;

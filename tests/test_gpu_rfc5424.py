@@ -26,9 +26,17 @@ def test_golden_g1_g2(dec, oracle, native):
     sp = res.spans5424(offs)  # the compact 32-byte rows decoded like the fg_row5424_* helpers of the C header
     assert span(sp["hostname"], 0) == b"testhostname" and span(sp["appname"], 0) == b"appname"
     assert span(sp["procid"], 0) == b"69" and span(sp["msgid"], 0) == b"42" and span(sp["msg"], 1) == b"test message"
-    # header + 2 pairs + 1 extension row (software="te\st sc\"ript" is unescaped on the device) ; 2 headers + 4 pairs + 1
-    assert sp["sd"][:, 1].tolist() == [4, 7]
-    assert bytes(res.arena[:int(res.raw.arena_bytes)]) == b'te\\st sc"ript' * 2
+    assert sp["sd"][:, 1].tolist() == [3, 6]  # header + 2 pairs ; 2 headers + 4 pairs
+    # software="te\\st sc\\"ript" was unescaped on the device (rfc5424_decoder.rs:105-125): arena records are [u16 length][bytes]
+    arena = bytes(res.arena[:int(res.raw.arena_bytes)])
+    recs, at = [], 0
+    while at < len(arena):
+        l = int.from_bytes(arena[at:at + 2], "little")
+        recs.append(arena[at + 2:at + 2 + l])
+        at += (2 + l + 1) & ~1
+    assert recs == [b'te\\st sc"ript'] * 2
+    esc = [int(e) for e in res.entries8 if (int(e) >> 62) & 1]
+    assert len(esc) == 2
 
 
 def test_appendix_vectors(dec, oracle, native):
