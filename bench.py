@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
         except Exception:
             self.proc = None
             return
@@ -81,8 +81,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 9]
+        # samples taken while the GPU was drawing load power (the sampler runs from before the warm-ups to after the
+        # timed regions; idle samples between phases would dilute the median)
+        def watts(r):
+            try:
+                return float(r[3])
+            except ValueError:
+                return 0.0
+        peak_w = max([watts(r) for r in rows], default=0.0)
+        loaded = [r for r in rows if watts(r) >= 0.6 * peak_w] or rows
+        sm = sorted(int(float(r[1])) for r in loaded if r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
             if len(r) < 9:
@@ -91,7 +101,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(rows), "power_w_max": peak_w,
+                "window": "from before the warm-ups to after the e2e region (50 ms period); median over samples at >= 60 % of the peak power"}
 
 
 
@@ -144,7 +155,7 @@ def run_reference(args) -> None:
     fmt_name = args.format
     fmt = FORMATS[fmt_name]
     cores = os.cpu_count() or 1
-    sample = min(args.lines, 2_000_000)
+    sample = args.lines  # the same lines the GPU arm parses (same generator, seed and count)
     data, offs = make_batch(fb, fmt_name, sample, 0)
     nbytes = int(offs[-1])
     ocfg = pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES) if (fmt_name == "ltsv" and args.ltsv_typed) else None
@@ -161,7 +172,7 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "gb_per_s": nbytes / (t / args.steps) / 1e9,
-        "config": {"workload": workload_name(fmt_name, args.lines), "sample_lines": sample,
+        "config": {"workload": workload_name(fmt_name, args.lines), "lines_per_gpu": sample, "bytes_per_gpu": nbytes,
                    "mean_line_bytes": round(nbytes / sample, 2)},
         "cpu_baseline": {"value": value, "unit": "lines/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} lines of the same generator/seed, all {cores} host threads over contiguous line shards; "
@@ -395,13 +406,15 @@ def main() -> None:
     del data
 
     # ---- device-resident: the kernel against the HBM roofline -------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # runs through warm-ups, the timed region and the e2e region (>= 5 samples even for a 20 ms region)
     dec.upload(h_bytes, h_offs)
     for _ in range(max(args.warmup, 3)):
         dec.parse_resident()
+    # keep the GPU under the same load for a moment so that the clock record covers it (untimed)
+    dec.parse_resident_many(max(args.steps, 20) * 4)
     launches0 = dec.kernel_launches()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     t0 = time.perf_counter()
     # K passes enqueued back to back on the launch stream, CUDA events around them, ONE host sync (per-step host syncs
@@ -409,7 +422,6 @@ def main() -> None:
     kernel_ms = [dec.parse_resident_many(args.steps) / args.steps]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     gpu_launches = dec.kernel_launches() - launches0
     wall = max_over_ranks(wall)
     k_avg_ms = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
@@ -440,6 +452,17 @@ def main() -> None:
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_lines / (e2e_wall / args.e2e_steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- bytes -> owned Records: fg_decode_batch + the host materialiser (what the reference's decode() returns) ------
+    barrier()
+    t0 = time.perf_counter()
+    r = dec.decode(h_bytes, h_offs)
+    mat_s = dec.materialize_seconds(r, h_bytes, h_offs, nthreads=max(1, (os.cpu_count() or 8) // max(world, 1)))
+    barrier()
+    rec_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_record = {"value": total_lines / rec_wall, "unit": "lines/s", "materialize_s": mat_s,
+                  "api": "fg_decode_batch + CudaBatchDecoder::materialize of every line (owned Record per line, host threads = cores / ranks)"}
 
     # ---- optional: raw newline-terminated stream, framing + UTF-8 validation on the device (N1) -------
     split = None
@@ -487,11 +510,15 @@ def main() -> None:
     if rank == 0:
         peak, peak_kind = hbm_peak()
         achieved = (b_read / 1e9) / (k_avg_ms / 1e3)
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu capture of
+        # THIS kernel build (profiles/traffic.json names the build it was taken from); scaled to this run's line count
         traffic = None
         tp = REPO / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get(fmt_name)
+                t = json.loads(tp.read_text()).get(fmt_name)
+                if t and t.get("build") == fb.build_info():
+                    traffic = int(t["dram_bytes_per_line"] * n)
             except Exception:
                 traffic = None
         line = {
@@ -510,6 +537,7 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": b_read, "d2h_bytes_per_step": d2h_bytes,
                     "steps": args.e2e_steps, "gb_per_s": total_bytes / (e2e_wall / args.e2e_steps) / 1e9,
                     "kernel_ms_per_step": e2e_kernel_ms / args.e2e_steps, "api": "fg_decode_batch (pinned host buffers)"},
+            "e2e_record": e2e_record,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }

@@ -13,7 +13,9 @@ from .native import (  # noqa: F401
     BatchResult,
     NativeLibraryMissing,
     build_info,
+    clone_decode_threads,
     cuda_lib_path,
+    dump_records,
     error_string,
     generate,
     load_cuda,

@@ -170,7 +170,10 @@ static std::string json_unescape(std::string_view v, bool nl_retry) {
 // ---------------------------------------------------------------------------
 // CudaBatchDecoder
 // ---------------------------------------------------------------------------
-CudaBatchDecoder::CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv, const DeviceOptions& opt) : fmt_(fmt) {
+CudaBatchDecoder::CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv, const DeviceOptions& opt)
+    : fmt_(fmt), ltsv_(ltsv), opt_(opt) {
+    if (opt_.max_batch_bytes <= 0) opt_.max_batch_bytes = (int64_t)256 << 20;  // the C ABI's defaults (fg_create)
+    if (opt_.max_batch_lines <= 0) opt_.max_batch_lines = 2 << 20;
     fg_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.device = opt.device;
@@ -205,6 +208,14 @@ CudaBatchDecoder::CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv, const 
     }
 }
 CudaBatchDecoder::~CudaBatchDecoder() { fg_destroy(ctx_); }
+
+std::unique_ptr<CudaBatchDecoder> CudaBatchDecoder::make_sized(int64_t max_batch_bytes, int32_t max_batch_lines) const {
+    DeviceOptions o = opt_;
+    o.max_batch_bytes = max_batch_bytes;
+    o.max_batch_lines = max_batch_lines;
+    o.chunk_lines = 0;
+    return std::unique_ptr<CudaBatchDecoder>(new CudaBatchDecoder(fmt_, ltsv_, o));
+}
 
 void CudaBatchDecoder::decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_batch_out* out) {
     const int rc = fg_decode_batch(ctx_, fmt_, bytes, offsets, n, out);
@@ -432,11 +443,14 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
                                const Decoder& decoder, const Encoder& encoder, std::ostream& err_out,
                                std::ostream& std_out) const {
     std::shared_ptr<CudaBatchDecoder> gpu = decoder.batch();
+    // a batch never exceeds what the context can take (Limits used to be independent of DeviceOptions)
+    const int64_t max_bytes = std::min<int64_t>(lim_.max_bytes, gpu->capacity_bytes());
+    const int32_t max_lines = std::min<int32_t>(lim_.max_lines, gpu->capacity_lines());
     std::vector<uint8_t> arena;
     std::vector<int32_t> offsets{0};
     std::vector<int32_t> invalid_before{0};  // "Invalid UTF-8 input" events, kept in stream order relative to the lines
-    arena.reserve((size_t)lim_.max_bytes);
-    auto flush = [&]() {
+    arena.reserve((size_t)max_bytes);
+    auto flush_on = [&](CudaBatchDecoder* gpu) {
         const int32_t n = (int32_t)offsets.size() - 1;
         if (n == 0) {
             for (int32_t k = 0; k < invalid_before[0]; ++k) err_out << "Invalid UTF-8 input\n";
@@ -474,6 +488,7 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
         offsets.assign(1, 0);
         invalid_before.assign(1, 0);
     };
+    auto flush = [&]() { flush_on(gpu.get()); };
     std::string line;
     while (std::getline(in, line)) {
         // BufRead::lines: the '\n' is gone; a '\r' is stripped only when it preceded a '\n'
@@ -482,7 +497,18 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
             ++invalid_before.back();  // printed in stream order when the batch is flushed
             continue;
         }
-        if ((int64_t)(arena.size() + line.size()) > lim_.max_bytes || (int32_t)offsets.size() - 1 >= lim_.max_lines)
+        if ((int64_t)line.size() > max_bytes) {
+            // One line larger than a whole batch: the reference's LineSplitter takes lines of any length, and there is no
+            // CPU decoder to fall back on, so the line gets a context of its own, sized for it (rare, slow, correct).
+            flush();
+            std::unique_ptr<CudaBatchDecoder> big = gpu->make_sized((int64_t)line.size() + 4096, 64);
+            arena.insert(arena.end(), line.begin(), line.end());
+            offsets.push_back((int32_t)arena.size());
+            invalid_before.push_back(0);
+            flush_on(big.get());
+            continue;
+        }
+        if ((int64_t)(arena.size() + line.size()) > max_bytes || (int32_t)offsets.size() - 1 >= max_lines)
             flush();
         arena.insert(arena.end(), line.begin(), line.end());
         offsets.push_back((int32_t)arena.size());
@@ -792,6 +818,56 @@ int fgh_split_dump(void* d, const uint8_t* stream, int64_t nbytes, uint8_t** out
         *out_line_offsets = lo_out;
         *out_n = n;
         if (kernel_ms) *kernel_ms = out.kernel_ms;
+        return 0;
+    } catch (const std::exception& e) {
+        if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());
+        return -1;
+    }
+}
+
+// Decoder::clone_boxed() drop-in check: `nthreads` clones of one CudaDecoder, each decoding its interleaved share of the
+// lines through Decoder::decode (a batch of one per call), as the reference's per-connection threads do; canonical dumps
+// come back in line order
+int fgh_clone_decode_threads(int fmt, int device, const uint8_t* bytes, const int32_t* offsets, int32_t n, int nthreads,
+                             uint8_t** out_buf, int64_t** out_offsets, char* errbuf, int errlen) {
+    try {
+        DeviceOptions opt;
+        opt.device = device;
+        opt.max_batch_bytes = 1 << 20;
+        opt.max_batch_lines = 1024;
+        CudaDecoder root((fg_format)fmt, {}, opt);
+        std::vector<std::unique_ptr<Decoder>> clones;
+        for (int t = 0; t < nthreads; ++t) clones.push_back(root.clone_boxed());
+        std::vector<std::string> dumps((size_t)n);
+        std::vector<std::thread> th;
+        std::vector<std::string> errs((size_t)nthreads);
+        for (int t = 0; t < nthreads; ++t) {
+            th.emplace_back([&, t] {
+                try {
+                    for (int32_t i = t; i < n; i += nthreads) {
+                        std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+                        DecodeResult r = clones[(size_t)t]->decode(line);
+                        dump_result(r, false, {}, dumps[(size_t)i]);
+                    }
+                } catch (const std::exception& e) {
+                    errs[(size_t)t] = e.what();
+                }
+            });
+        }
+        for (auto& x : th) x.join();
+        for (const auto& e : errs)
+            if (!e.empty()) throw std::runtime_error(e);
+        std::string all;
+        int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
+        offs[0] = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            all += dumps[(size_t)i];
+            offs[i + 1] = (int64_t)all.size();
+        }
+        uint8_t* buf = (uint8_t*)malloc(all.size() ? all.size() : 1);
+        memcpy(buf, all.data(), all.size());
+        *out_buf = buf;
+        *out_offsets = offs;
         return 0;
     } catch (const std::exception& e) {
         if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());

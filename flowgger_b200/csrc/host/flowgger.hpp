@@ -94,6 +94,10 @@ class CudaBatchDecoder {
     fg_ctx* ctx() const { return ctx_; }
     // serialises the callers that share this context (decoder clones): hold it from decode_batch until the last materialize
     std::mutex& mutex() { return mu_; }
+    int64_t capacity_bytes() const { return opt_.max_batch_bytes; }
+    int32_t capacity_lines() const { return opt_.max_batch_lines; }
+    // a second context of the same format / LTSV configuration with another capacity (a single line larger than a batch)
+    std::unique_ptr<CudaBatchDecoder> make_sized(int64_t max_batch_bytes, int32_t max_batch_lines) const;
     // packs nothing: bytes/offsets as in fg_decode_batch.  Throws std::runtime_error on a CUDA/argument failure.
     void decode_batch(const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_batch_out* out);
     // Owned Record (or the reference's error string) of line i of a decoded batch.
@@ -110,6 +114,8 @@ class CudaBatchDecoder {
     fg_format fmt_;
     fg_ctx* ctx_ = nullptr;
     std::mutex mu_;
+    LtsvConfig ltsv_;
+    DeviceOptions opt_;
     std::string suffix_[5];
     bool has_suffix_[5] = {false, false, false, false, false};
 };

@@ -116,6 +116,8 @@ def load_host() -> C.CDLL:
         L.fgh_shard_by_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
         L.fgh_multi_decode_dump.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.fgh_clone_decode_threads.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
         L.fgh_splitter_run.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 3
         _host = L
     return _host
@@ -414,6 +416,26 @@ def multi_gpu_decode_dump(fmt: int, devices: list[int], data: np.ndarray, offset
         H.fgh_free(pb)
         H.fgh_free(po)
     return buf, offs
+
+
+def clone_decode_threads(fmt: int, lines: list[bytes], nthreads: int = 2, device: int = 0) -> list[bytes]:
+    """Decoder::clone_boxed() + concurrent Decoder::decode(line) from `nthreads` host threads; canonical dump per line."""
+    H = load_host()
+    offs = np.zeros(len(lines) + 1, dtype=np.int32)
+    np.cumsum([len(x) for x in lines], out=offs[1:])
+    data = np.frombuffer(b"".join(lines) or b"\0", dtype=np.uint8).copy()
+    pb, po = C.c_void_p(), C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = H.fgh_clone_decode_threads(fmt, device, _ptr(data), _ptr(offs), len(lines), nthreads, C.byref(pb), C.byref(po), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    try:
+        o = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(len(lines) + 1,)).copy()
+        buf = C.string_at(pb, int(o[-1]))
+    finally:
+        H.fgh_free(pb)
+        H.fgh_free(po)
+    return [buf[o[i]:o[i + 1]] for i in range(len(lines))]
 
 
 def splitter_run(dec: "BatchDecoder", text: bytes, max_lines: int = 1 << 16, max_bytes: int = 16 << 20) -> tuple[bytes, bytes, bytes]:

@@ -170,4 +170,96 @@ char* fgo_g15(int which) {
     return r;
 }
 
+// decode + GelfEncoder::encode (line_splitter.rs:50-52) of n lines: JSON records concatenated into *out_buf with
+// *out_offsets[n+1]; a line the decoder rejects contributes an empty record.  extra = output.gelf_extra pairs.
+int fgo_decode_encode_gelf(int fmt, const void* cfg, const uint8_t* bytes, const int32_t* offsets, int64_t n, int nthreads,
+                           int n_extra, const char* const* extra_keys, const char* const* extra_vals, uint8_t** out_buf,
+                           int64_t** out_offsets) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::pair<std::string, std::string>> extra;
+    for (int k = 0; k < n_extra; ++k) extra.emplace_back(extra_keys[k], extra_vals[k]);
+    std::vector<std::string> parts((size_t)nthreads);
+    std::vector<std::vector<int64_t>> lens((size_t)nthreads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            std::string& o = parts[(size_t)t];
+            for (int64_t i = lo; i < hi; ++i) {
+                const size_t before = o.size();
+                Decoded d = decode_one(fmt, (const LtsvConfig*)cfg,
+                                       std::string_view((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i])));
+                if (!d.err) o += gelf_encode(d.rec, extra);
+                lens[(size_t)t].push_back((int64_t)(o.size() - before));
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    uint8_t* buf = (uint8_t*)malloc(total ? total : 1);
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    size_t pos = 0;
+    int64_t li = 0;
+    offs[0] = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        memcpy(buf + pos, parts[(size_t)t].data(), parts[(size_t)t].size());
+        for (const int64_t l : lens[(size_t)t]) {
+            offs[li + 1] = offs[li] + l;
+            ++li;
+        }
+        pos += parts[(size_t)t].size();
+    }
+    *out_buf = buf;
+    *out_offsets = offs;
+    return 0;
+}
+
+// the four Records of the reference's own encoder tests (gelf_encoder.rs:125-150, :152-173, :175-199, :215-250)
+char* fgo_gelf_encoder_test(int which) {
+    auto sval = [](const char* s) { SDValue v; v.tag = SDTag::String; v.s = s; return v; };
+    Record r;
+    r.ts = 1385053862.3072;
+    r.severity = 1;
+    r.msg = "A short message that helps you identify what is going on";
+    std::vector<std::pair<std::string, std::string>> extra;
+    if (which == 0 || which == 3) {
+        r.hostname = "example.org";
+        r.appname = "appname";
+        r.procid = "44";
+        r.full_msg = "Backtrace here\n\nmore stuff";
+        StructuredData sd;
+        sd.sd_id = "someid";
+        sd.pairs = {{"_some_info", sval("foo")}};
+        std::vector<StructuredData> v{sd};
+        if (which == 3) {
+            StructuredData sd2;
+            sd2.sd_id = "someid2";
+            SDValue f;
+            f.tag = SDTag::F64;
+            f.f = 123.456;
+            sd2.pairs = {{"info", f}};
+            v.push_back(sd2);
+        }
+        r.sd = v;
+        extra = {{"secret-token", "secret"}};
+    } else if (which == 2) {
+        StructuredData sd;
+        sd.pairs = {{"a_key", sval("foo")}};
+        r.sd = std::vector<StructuredData>{sd};
+        extra = {{"a_key", "bar"}};
+    }
+    const std::string s = gelf_encode(r, extra);
+    char* out = (char*)malloc(s.size() + 1);
+    memcpy(out, s.c_str(), s.size() + 1);
+    return out;
+}
+
+char* fgo_format_f64(double v) {
+    const std::string s = format_f64_json(v);
+    char* out = (char*)malloc(s.size() + 1);
+    memcpy(out, s.c_str(), s.size() + 1);
+    return out;
+}
+
 }  // extern "C"

@@ -74,6 +74,10 @@ Decoded rfc5424_decode(std::string_view line);                       // rfc5424_
 Decoded ltsv_decode(const LtsvConfig& cfg, std::string_view line);   // ltsv_decoder.rs:87-221
 Decoded gelf_decode(std::string_view line);                          // gelf_decoder.rs:34-125
 
+// GelfEncoder::encode (encoder/gelf_encoder.rs:59-115) with output.gelf_extra = `extra`; serde_json 0.8 + dtoa text
+std::string gelf_encode(const Record& record, const std::vector<std::pair<std::string, std::string>>& extra);
+std::string format_f64_json(double v);  // the f64 writer alone
+
 // Canonical, unambiguous text dump used by the parity tests (one line of
 // bytes per record; same format is produced independently by the product's
 // host materialiser in flowgger_b200/csrc/host/record.cpp).

@@ -16,7 +16,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     so = HERE / "liboracle.so"
-    srcs = [HERE / "oracle.cpp", HERE / "capi.cpp", HERE / "oracle.hpp"]
+    srcs = [HERE / "oracle.cpp", HERE / "capi.cpp", HERE / "encoder.cpp", HERE / "oracle.hpp"]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(HERE), "-s", "-B", "liboracle.so"], check=True)
     return so
@@ -42,6 +42,11 @@ def lib() -> C.CDLL:
         L.fgo_decode_debug.restype = C.c_void_p
         L.fgo_decode_debug.argtypes = [C.c_int, C.c_void_p, C.c_char_p, C.c_int64]
         L.fgo_g15.restype = C.c_void_p
+        L.fgo_gelf_encoder_test.restype = C.c_void_p
+        L.fgo_format_f64.restype = C.c_void_p
+        L.fgo_format_f64.argtypes = [C.c_double]
+        L.fgo_decode_encode_gelf.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.fgo_parse_f64.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
         L.fgo_rfc3339.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
         L.fgo_english.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_double)]
@@ -85,6 +90,41 @@ def g15(which: int) -> str:
     s = C.string_at(p).decode()
     lib().fgo_free(C.c_void_p(p))
     return s
+
+
+def gelf_encoder_test(which: int) -> str:
+    """JSON of the Record built by the reference's encoder test #which (gelf_encoder.rs:125,152,175,215)."""
+    p = lib().fgo_gelf_encoder_test(which)
+    s = C.string_at(p).decode()
+    lib().fgo_free(C.c_void_p(p))
+    return s
+
+
+def format_f64(v: float) -> str:
+    p = lib().fgo_format_f64(v)
+    s = C.string_at(p).decode()
+    lib().fgo_free(C.c_void_p(p))
+    return s
+
+
+def decode_encode_gelf(fmt: int, data: np.ndarray, offsets: np.ndarray, extra: dict[str, str] | None = None,
+                       cfg: "LtsvConfig | None" = None, nthreads: int = 8) -> tuple[bytes, np.ndarray]:
+    """decode + GelfEncoder::encode per line (line_splitter.rs:50-52): (concatenated JSON, int64 offsets[n+1]); lines the
+    decoder rejects contribute an empty record."""
+    n = len(offsets) - 1
+    ex = list((extra or {}).items())
+    keys = (C.c_char_p * max(len(ex), 1))(*[k.encode() for k, _ in ex])
+    vals = (C.c_char_p * max(len(ex), 1))(*[v.encode() for _, v in ex])
+    pb, po = C.c_void_p(), C.c_void_p()
+    lib().fgo_decode_encode_gelf(fmt, cfg.h if cfg else None, C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n,
+                                 nthreads, len(ex), keys, vals, C.byref(pb), C.byref(po))
+    try:
+        offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+        buf = C.string_at(pb, int(offs[-1]))
+    finally:
+        lib().fgo_free(pb)
+        lib().fgo_free(po)
+    return buf, offs
 
 
 def decode_dump(fmt: int, data: np.ndarray, offsets: np.ndarray, cfg: LtsvConfig | None = None,

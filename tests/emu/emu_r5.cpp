@@ -15,6 +15,7 @@
 #include "../../include/flowgger_cuda.h"
 #include "../../flowgger_b200/csrc/fg_r5fast.cuh"
 #include "../../flowgger_b200/csrc/fg_rfc5424.cuh"
+#include "../../flowgger_b200/csrc/fg_dtoa.cuh"
 
 namespace {
 constexpr int kLines = fg::kRfc5424LinesPerCta;
@@ -55,6 +56,9 @@ uint32_t emu5424_classify16(const uint8_t* p) {
     memcpy(w, p, 16);
     return fg::r5_classify16(w[0], w[1], w[2], w[3]);
 }
+// f64 -> text of the GELF encoder (fg_dtoa.cuh), for the CPU tests of the Grisu2 restatement
+int emu_json_f64(double v, uint8_t* out) { return fg::json_f64(v, out); }
+
 uint32_t emu5424_classify16_v(const uint8_t* p) {
     uint32_t w[4];
     memcpy(w, p, 16);

@@ -60,11 +60,9 @@ def test_single_line_decoder_trait(native, oracle):
 
 
 def test_multi_context_fanout(native, oracle):
-    """MultiGpuBatchDecoder: byte-balanced shards, one context + host thread per device, gathered in order.
-    Uses every visible GPU (falls back to two contexts on GPU 0 when only one is visible)."""
-    import torch
-    ndev = torch.cuda.device_count()
-    devices = list(range(ndev)) if ndev >= 2 else [0, 0]
+    """MultiGpuBatchDecoder host logic (sharding, per-context threads, ordered gather) with two contexts on GPU 0;
+    the same on two REAL devices is tests/test_gpu_fullsize.py::test_multi_device_fanout (gpurun --gpus 2)."""
+    devices = [0, 0]
     data, offs = native.generate(native.FMT_RFC5424, 77, 400_000)
     gbuf, goffs = native.multi_gpu_decode_dump(native.FMT_RFC5424, devices, data, offs)
     obuf, ooffs = oracle.decode_dump(0, data, offs)
@@ -103,3 +101,21 @@ def test_capacity_and_argument_errors(native, oracle):
         assert g == r
     finally:
         dec.close()
+
+
+def test_splitter_line_larger_than_a_batch(native, oracle):
+    """a single line longer than the decoder's max_batch_bytes must not abort the stream — the reference's
+    LineSplitter takes lines of any length.  It is decoded on a context of its own; order of records is kept."""
+    big = b"<13>1 " + V.TS.encode() + b" h a p m - " + b"y" * (3 << 20)
+    lines = [V.G1_LINE.encode(), big, V.G2_LINE.encode(), b"abc"]
+    text = b"\n".join(lines) + b"\n"
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=1 << 20, max_batch_lines=1024)
+    try:
+        records, err, out = native.splitter_run(dec, text, max_lines=1 << 16, max_bytes=64 << 20)
+    finally:
+        dec.close()
+    d, o = oracle.pack(lines)
+    buf, bo = oracle.decode_dump(0, d, o)
+    dumps = [buf[bo[i]:bo[i + 1]] for i in range(4)]
+    assert records.split(b"\n")[:-1] == [x[:x.rindex(b";out=")] + b";out=0" for x in dumps[:3]]
+    assert err == b"Unsupported BOM: [abc]\n"
