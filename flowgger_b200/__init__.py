@@ -24,6 +24,7 @@ from .native import (  # noqa: F401
     multi_gpu_decode_dump,
     shard_by_bytes,
     splitter_run,
+    splitter_run_gelf,
 )
 
 __all__ = [

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/flowgger_cuda.h"
@@ -120,6 +121,27 @@ struct fg_ctx {
     fg::WideRow* d_wide = nullptr;
     fg_wide_row* h_wide = nullptr;
     size_t wide_cap = 0;
+    // fused GELF encoder (fg_decode_encode_gelf)
+    uint32_t* d_enc_lens = nullptr;
+    uint32_t* d_enc_rel = nullptr;
+    unsigned long long* d_enc_base = nullptr;  // [chunks + 1] running output size
+    unsigned long long* h_enc_base = nullptr;
+    int enc_base_cap = 0;
+    uint8_t* d_enc_out = nullptr;
+    uint8_t* h_enc_out = nullptr;
+    size_t enc_out_cap = 0;
+    long long* d_enc_offsets = nullptr;
+    int64_t* h_enc_offsets = nullptr;
+    uint8_t* d_enc_status = nullptr;
+    uint8_t* h_enc_status = nullptr;
+    void* d_scan_temp = nullptr;
+    size_t scan_temp_bytes = 0;
+    uint8_t* d_static_blob = nullptr;  // fixed GELF keys + output.gelf_extra, sorted
+    int n_static = 0;
+    const int32_t* d_static_key_off = nullptr;
+    const int32_t* d_static_lit_off = nullptr;
+    const int32_t* d_static_kind = nullptr;
+    std::vector<std::pair<std::string, std::string>> gelf_extra;
     // split mode (fg_split_decode)
     uint32_t* d_seg = nullptr;
     int32_t* d_n_lines = nullptr;
@@ -516,6 +538,117 @@ int check_batch(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t
     return FG_OK;
 }
 
+// serde_json 0.8 escape_bytes, for the keys / values of output.gelf_extra rendered once on the host
+void json_escape_into(const std::string& v, std::string& o) {
+    o.push_back('"');
+    for (const char c : v) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\x08': o += "\\b"; break;
+            case '\x0c': o += "\\f"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            default: o.push_back(c);
+        }
+    }
+    o.push_back('"');
+}
+
+// The keys GelfEncoder::encode always or conditionally inserts (gelf_encoder.rs:60-100) merged with output.gelf_extra
+// (:110-112, inserted last: an extra replaces a fixed key of the same name), sorted by key like the BTreeMap iterates.
+int build_static_items(fg_ctx* c) {
+    struct Item { std::string key, lit; int kind; };
+    static const char* fixed[9] = {"application_name", "full_message", "host", "level", "process_id", "sd_id", "short_message",
+                                   "timestamp", "version"};
+    std::vector<Item> items;
+    for (int k = 0; k < 9; ++k) {
+        Item it;
+        it.key = fixed[k];
+        json_escape_into(it.key, it.lit);
+        it.lit.push_back(':');
+        it.kind = k;
+        items.push_back(it);
+    }
+    for (const auto& kv : c->gelf_extra) {
+        Item it;
+        it.key = kv.first;
+        json_escape_into(kv.first, it.lit);
+        it.lit.push_back(':');
+        json_escape_into(kv.second, it.lit);
+        it.kind = 100;
+        bool replaced = false;
+        for (auto& x : items)
+            if (x.key == it.key) { x = it; replaced = true; }
+        if (!replaced) items.push_back(it);
+    }
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });  // byte order (std::string compares as unsigned char)
+    std::vector<int32_t> key_off{0}, lit_off, kind;
+    std::string blob;
+    for (const auto& it : items) {
+        blob += it.key;
+        key_off.push_back((int32_t)blob.size());
+    }
+    lit_off.push_back((int32_t)blob.size());
+    for (const auto& it : items) {
+        blob += it.lit;
+        lit_off.push_back((int32_t)blob.size());
+        kind.push_back(it.kind);
+    }
+    const size_t n = items.size();
+    const size_t o_key = (blob.size() + 15) & ~(size_t)15, o_lit = o_key + (n + 1) * 4, o_kind = o_lit + (n + 1) * 4;
+    std::vector<uint8_t> buf(o_kind + n * 4 + 16, 0);
+    memcpy(buf.data(), blob.data(), blob.size());
+    memcpy(buf.data() + o_key, key_off.data(), (n + 1) * 4);
+    memcpy(buf.data() + o_lit, lit_off.data(), (n + 1) * 4);
+    memcpy(buf.data() + o_kind, kind.data(), n * 4);
+    dfree(c->d_static_blob);
+    FG_CUDA(c, cudaMalloc(&c->d_static_blob, buf.size()));
+    FG_CUDA(c, cudaMemcpy(c->d_static_blob, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    c->n_static = (int)n;
+    c->d_static_key_off = (const int32_t*)(c->d_static_blob + o_key);
+    c->d_static_lit_off = (const int32_t*)(c->d_static_blob + o_lit);
+    c->d_static_kind = (const int32_t*)(c->d_static_blob + o_kind);
+    return FG_OK;
+}
+
+int alloc_enc_out(fg_ctx* c, size_t cap) {
+    dfree(c->d_enc_out);
+    hfree(c->h_enc_out);
+    c->enc_out_cap = 0;
+    cap = (cap + 4095) & ~(size_t)4095;
+    FG_CUDA(c, cudaMalloc(&c->d_enc_out, cap + 16));
+    FG_CUDA(c, cudaHostAlloc(&c->h_enc_out, cap + 16, cudaHostAllocDefault));
+    c->enc_out_cap = cap;
+    return FG_OK;
+}
+
+int ensure_encoder(fg_ctx* c, int chunks) {
+    if (!c->d_enc_lens) {
+        FG_CUDA(c, cudaMalloc(&c->d_enc_lens, (size_t)c->max_lines * 4));
+        FG_CUDA(c, cudaMalloc(&c->d_enc_rel, (size_t)c->max_lines * 4));
+        FG_CUDA(c, cudaMalloc(&c->d_enc_offsets, ((size_t)c->max_lines + 1) * 8));
+        FG_CUDA(c, cudaHostAlloc(&c->h_enc_offsets, ((size_t)c->max_lines + 1) * 8, cudaHostAllocDefault));
+        FG_CUDA(c, cudaMalloc(&c->d_enc_status, (size_t)c->max_lines));
+        FG_CUDA(c, cudaHostAlloc(&c->h_enc_status, (size_t)c->max_lines, cudaHostAllocDefault));
+        c->scan_temp_bytes = fg::gelf_scan_temp_bytes(c->max_lines);
+        FG_CUDA(c, cudaMalloc(&c->d_scan_temp, c->scan_temp_bytes + 256));
+    }
+    if (!c->enc_out_cap)
+        if (int rc = alloc_enc_out(c, c->max_bytes * 2 + (size_t)c->max_lines * 200)) return rc;
+    if (c->enc_base_cap < chunks + 1) {
+        dfree(c->d_enc_base);
+        hfree(c->h_enc_base);
+        FG_CUDA(c, cudaMalloc(&c->d_enc_base, sizeof(unsigned long long) * ((size_t)chunks + 1)));
+        FG_CUDA(c, cudaHostAlloc(&c->h_enc_base, sizeof(unsigned long long) * ((size_t)chunks + 1), cudaHostAllocDefault));
+        c->enc_base_cap = chunks + 1;
+    }
+    if (!c->d_static_blob)
+        if (int rc = build_static_items(c)) return rc;
+    return FG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -624,6 +757,9 @@ void fg_destroy(fg_ctx* c) {
     dfree(c->d_bytes); dfree(c->d_offsets); dfree(c->d_rows); dfree(c->d_k); dfree(c->d_flush);
     dfree(c->d_rows5); hfree(c->h_rows5); dfree(c->d_e8); hfree(c->h_e8); dfree(c->d_esc_list); dfree(c->d_wide_list);
     dfree(c->d_arena); hfree(c->h_arena); dfree(c->d_wide); hfree(c->h_wide);
+    dfree(c->d_enc_lens); dfree(c->d_enc_rel); dfree(c->d_enc_base); hfree(c->h_enc_base); dfree(c->d_enc_out); hfree(c->h_enc_out);
+    dfree(c->d_enc_offsets); hfree(c->h_enc_offsets); dfree(c->d_enc_status); hfree(c->h_enc_status); dfree(c->d_scan_temp);
+    dfree(c->d_static_blob);
     dfree(c->d_seg); dfree(c->d_n_lines); dfree(c->d_invalid);
     hfree(c->h_offsets); hfree(c->h_n_lines);
     if (c->s_parse) cudaStreamDestroy(c->s_parse);
@@ -742,6 +878,134 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
         return FG_OK;
     }
     return fail(c, FG_E_CAPACITY, "side table overflow after regrow");
+}
+
+int fg_set_gelf_extra(fg_ctx* c, int32_t n, const char* const* keys, const char* const* values) {
+    if (!c || n < 0 || (n > 0 && (!keys || !values))) return FG_E_ARG;
+    FG_CUDA(c, cudaSetDevice(c->device));
+    c->gelf_extra.clear();
+    for (int32_t k = 0; k < n; ++k) {
+        if (!keys[k] || !values[k]) return fail(c, FG_E_ARG, "output.gelf_extra values must be strings");  // gelf_encoder.rs:41
+        c->gelf_extra.emplace_back(keys[k], values[k]);
+    }
+    FG_CUDA(c, cudaDeviceSynchronize());
+    return build_static_items(c);
+}
+
+// decode (RFC5424) + GelfEncoder::encode fused: H2D lines -> parse kernels -> size / scan / write kernels -> D2H of the
+// encoded records only, chunk by chunk; the decoder's rows and side tables never leave the device.
+int fg_decode_encode_gelf(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_t* offsets, int32_t n, fg_encoded_out* out) {
+    if (!c || !out) return FG_E_ARG;
+    if (int rc = check_batch(c, bytes, offsets, n)) return rc;
+    if (fmt != FG_FMT_RFC5424) return fail(c, FG_E_ARG, "the fused encoder takes input.format = rfc5424");
+    FG_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_format(c, (int)fmt)) return rc;
+    const int C = c->chunk_lines;
+    const int chunks = n > 0 ? (n + C - 1) / C : 1;
+    if (int rc = ensure_encoder(c, chunks)) return rc;
+    memset(out, 0, sizeof *out);
+    out->bytes = c->h_enc_out;
+    out->offsets = c->h_enc_offsets;
+    out->status = c->h_enc_status;
+    if (n == 0) {
+        c->h_enc_offsets[0] = 0;
+        return FG_OK;
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    const bool pin_b = is_pinned(bytes), pin_o = is_pinned(offsets);
+    if (int rc = ensure_events(c, chunks)) return rc;
+    const int tile = pick_tile(c, (size_t)(offsets[n] - offsets[0]), n, (int)fmt);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kCnt, c->s_comp));
+        FG_CUDA(c, cudaMemsetAsync(c->d_enc_base, 0, sizeof(unsigned long long), c->s_comp));
+        int bounce_ix = 0;
+        for (int k = 0; k < chunks; ++k) {
+            const int l0 = k * C, l1 = std::min(n, l0 + C);
+            const size_t b0 = (size_t)offsets[l0], b1 = (size_t)offsets[l1];
+            if (b1 < b0 || b1 > c->max_bytes) {
+                cudaDeviceSynchronize();
+                return fail(c, FG_E_ARG, "offsets must be non-decreasing and within max_batch_bytes");
+            }
+            if (int rc = h2d(c, c->d_bytes + b0, bytes + b0, b1 - b0, pin_b, bounce_ix)) return rc;
+            if (int rc = h2d(c, c->d_offsets + l0, offsets + l0, sizeof(int32_t) * (size_t)(l1 - l0 + 1), pin_o, bounce_ix)) return rc;
+            FG_CUDA(c, cudaEventRecord(c->ev_h2d[k], c->s_h2d));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[k], 0));
+            FG_CUDA(c, fg::launch_check_offsets(c->d_offsets + l0, l1 - l0, (long long)c->max_bytes, c->d_k + kBadFlag, c->s_comp));
+            FG_CUDA(c, cudaEventRecord(c->ev_k0[k], c->s_comp));
+            if (int rc = launch_lines(c, (int)fmt, l0, l1 - l0, tile, nullptr, 0, c->s_comp)) return rc;
+            fg::GelfEncodeParams E;
+            E.bytes = c->d_bytes;
+            E.offsets = c->d_offsets + l0;
+            E.n = l1 - l0;
+            E.rows = c->d_rows5 + 2 * (size_t)l0;
+            E.entries = c->d_e8;
+            E.arena = c->d_arena;
+            E.wide_rows = c->d_wide;
+            E.wentry_name = c->d_entry_name;
+            E.wentry_val = c->d_entry_val;
+            E.wentry_meta = c->d_entry_meta;
+            E.static_blob = c->d_static_blob;
+            E.n_static = c->n_static;
+            E.static_key_off = c->d_static_key_off;
+            E.static_lit_off = c->d_static_lit_off;
+            E.static_kind = c->d_static_kind;
+            E.lens = c->d_enc_lens + l0;
+            E.rel = c->d_enc_rel + l0;
+            E.base = c->d_enc_base + k;
+            E.out = c->d_enc_out;
+            E.out_cap = c->enc_out_cap;
+            E.out_offsets = c->d_enc_offsets + l0;
+            E.status = c->d_enc_status + l0;
+            E.bad_offsets = c->d_k + kBadFlag;
+            E.entry_cap = (uint32_t)std::min<size_t>(c->e8_cap, 0xFFFFFFFFu);
+            E.wide_cap = (uint32_t)c->wide_cap;
+            E.wentry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
+            FG_CUDA(c, fg::launch_gelf_encode(E, c->d_scan_temp, c->scan_temp_bytes, c->s_comp));
+            c->launches += 4;
+            FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_counts + (size_t)k * kCnt, c->d_k, sizeof(uint32_t) * kCnt, cudaMemcpyDeviceToHost, c->s_comp));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_enc_base + k + 1, c->d_enc_base + k + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_comp));
+            FG_CUDA(c, cudaEventRecord(c->ev_cnt[k], c->s_comp));
+            FG_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_cnt[k], 0));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_enc_status + l0, c->d_enc_status + l0, (size_t)(l1 - l0), cudaMemcpyDeviceToHost, c->s_d2h));
+            FG_CUDA(c, cudaMemcpyAsync(c->h_enc_offsets + l0, c->d_enc_offsets + l0, (size_t)(l1 - l0 + 1) * 8, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        // encoded bytes: chunk k's records are the contiguous range [base(k), base(k+1)) of the output
+        c->h_enc_base[0] = 0;
+        bool overflow = false;
+        for (int k = 0; k < chunks; ++k) {
+            FG_CUDA(c, cudaEventSynchronize(c->ev_cnt[k]));
+            const uint32_t* cur = c->h_counts + (size_t)k * kCnt;
+            const unsigned long long lo = c->h_enc_base[k], hi = c->h_enc_base[k + 1];
+            if (tables_overflow(c, (int)fmt, cur) || hi > c->enc_out_cap) overflow = true;
+            if (!overflow && hi > lo)
+                FG_CUDA(c, cudaMemcpyAsync(c->h_enc_out + lo, c->d_enc_out + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        uint32_t total[kCnt];
+        memcpy(total, c->h_counts + (size_t)(chunks - 1) * kCnt, sizeof total);
+        FG_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+        if (total[kBadFlag]) return fail(c, FG_E_ARG, "offsets must be non-decreasing and within max_batch_bytes");
+        if (overflow) {
+            if (tables_overflow(c, (int)fmt, total))
+                if (int rc = regrow_tables(c, (int)fmt, total)) return rc;
+            const unsigned long long need = c->h_enc_base[chunks];
+            if (need > c->enc_out_cap)
+                if (int rc = alloc_enc_out(c, (size_t)need + (size_t)need / 8 + 4096)) return rc;
+            out->bytes = c->h_enc_out;
+            continue;
+        }
+        float kms = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            float ms = 0.f;
+            FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_k0[k], c->ev_k1[k]));
+            kms += ms;
+        }
+        out->n = n;
+        out->kernel_ms = kms;
+        out->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        return FG_OK;
+    }
+    return fail(c, FG_E_CAPACITY, "output / side table overflow after regrow");
 }
 
 int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {

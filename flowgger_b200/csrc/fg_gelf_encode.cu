@@ -1,0 +1,347 @@
+// fg_gelf_encode.cu — the stage AFTER the decoder, fused on the device: Record -> GELF JSON bytes.
+//
+// B200-native replacement for GelfEncoder::encode (/root/reference/src/flowgger/encoder/gelf_encoder.rs:59-115), which
+// every splitter calls right after Decoder::decode (splitter/line_splitter.rs:50-52).  The JSON text is what
+// serde_json "~0.8" `to_vec` prints for the BTreeMap the reference builds: keys in byte order, a later insert replaces
+// an earlier one (SD pairs replace fixed fields, output.gelf_extra replaces everything), compact separators, strings
+// with `"` `\\` \b \f \n \r \t escaped, Record.ts through dtoa (fg_dtoa.cuh).
+//
+// Input = the decoder's device-resident results (compact rows + 8-byte entries + arena, or wide rows); nothing of them
+// travels to the host in this mode.  Three launches per chunk of lines:
+//   gelf_size_kernel   one thread per line: exact length of its record (0 for a line the decoder rejected)
+//   cub exclusive sum  record offsets inside the chunk
+//   gelf_write_kernel  one thread per line writes its record; output bytes are assembled four at a time and stored as
+//                      aligned 32-bit words, so a record costs a quarter of the store instructions / L2 requests of a
+//                      byte-wise copy
+// Both kernels run ONE emit routine over a counting or a writing sink, so the two passes cannot disagree.
+// All SD names start with '_' (rfc5424_decoder.rs:221), i.e. they sort before every fixed GELF key; the general merge
+// with the pre-sorted static items (fixed keys + extras, prepared on the host once) still compares full keys.
+#include <cub/device/device_scan.cuh>
+
+#include "fg_kernels.cuh"
+
+#include "fg_common.cuh"
+#include "fg_dtoa.cuh"
+#include "fg_r5fast.cuh"
+#include "fg_status.h"
+
+namespace fg {
+
+namespace {
+
+struct Span {
+    const uint8_t* p;
+    int len;
+};
+
+struct CountSink {
+    uint32_t n = 0;
+    __device__ __forceinline__ void put(uint32_t) { ++n; }
+    __device__ __forceinline__ void finish() {}
+};
+// bytes -> aligned 32-bit stores (byte stores only for the unaligned head and the tail of the record)
+struct WordSink {
+    uint8_t* p;
+    uint32_t acc = 0;
+    int nacc = 0;
+    __device__ __forceinline__ explicit WordSink(uint8_t* at) : p(at) {}
+    __device__ __forceinline__ void put(uint32_t b) {
+        if (((size_t)p & 3u) != 0u && nacc == 0) {  // head: up to three single bytes until the address is aligned
+            *p++ = (uint8_t)b;
+            return;
+        }
+        acc |= b << (8 * nacc);
+        if (++nacc == 4) {
+            *reinterpret_cast<uint32_t*>(p) = acc;
+            p += 4;
+            acc = 0;
+            nacc = 0;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        for (int k = 0; k < nacc; ++k) p[k] = (uint8_t)(acc >> (8 * k));
+    }
+};
+
+template <class Sink>
+__device__ __forceinline__ void put_lit(Sink& s, const uint8_t* lit, int len) {
+    for (int k = 0; k < len; ++k) s.put(lit[k]);
+}
+// serde_json 0.8 ser.rs escape_bytes: `"` `\\` \b \f \n \r \t get a backslash form, every other byte is copied
+template <class Sink>
+__device__ __forceinline__ void put_escaped(Sink& s, Span v) {
+    for (int k = 0; k < v.len; ++k) {
+        const uint32_t c = v.p[k];
+        uint32_t e = 0;
+        if (c == '"' || c == '\\') e = c;
+        else if (c < 0x20u) e = c == 8u ? 'b' : c == 9u ? 't' : c == 10u ? 'n' : c == 12u ? 'f' : c == 13u ? 'r' : 0u;
+        if (e) {
+            s.put('\\');
+            s.put(e);
+        } else {
+            s.put(c);
+        }
+    }
+}
+template <class Sink>
+__device__ __forceinline__ void put_string(Sink& s, Span v) {
+    s.put('"');
+    put_escaped(s, v);
+    s.put('"');
+}
+
+// byte-order comparison of ('_' + a) with b
+__device__ __forceinline__ int cmp_sd_key(Span a, Span b) {
+    if (b.len == 0) return 1;
+    if ((uint32_t)'_' != b.p[0]) return (uint32_t)'_' < b.p[0] ? -1 : 1;
+    const int n = min(a.len, b.len - 1);
+    for (int k = 0; k < n; ++k) {
+        const uint32_t x = a.p[k], y = b.p[k + 1];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return a.len == b.len - 1 ? 0 : (a.len < b.len - 1 ? -1 : 1);
+}
+__device__ __forceinline__ int cmp_names(Span a, Span b) {
+    const int n = min(a.len, b.len);
+    for (int k = 0; k < n; ++k) {
+        const uint32_t x = a.p[k], y = b.p[k];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return a.len == b.len ? 0 : (a.len < b.len ? -1 : 1);
+}
+
+// One decoded line, whichever table it lives in
+struct RecView {
+    bool ok;
+    bool wide;
+    double ts;
+    uint32_t severity;
+    Span host, app, proc, msg, full;  // msg.p == nullptr: None
+    Span sd_id;                        // id of the LAST element (gelf_encoder.rs:97-99 inserts "sd_id" per element)
+    bool has_sd;
+    uint32_t first, count;             // entries8 range, or wide-entry range
+    const uint8_t* line;
+};
+
+__device__ __forceinline__ void load_view(const GelfEncodeParams& P, int i, RecView& r) {
+    const uint4 lo4 = P.rows[2 * (size_t)i], hi4 = P.rows[2 * (size_t)i + 1];
+    const uint32_t meta = lo4.z;
+    r.ok = (meta & 0xFFu) == 0u;
+    r.wide = ((meta >> 24) & kFlagWide) != 0u;
+    r.has_sd = false;
+    r.sd_id = Span{nullptr, 0};
+    r.msg = Span{nullptr, 0};
+    r.first = r.count = 0;
+    if (!r.ok) return;
+    r.severity = (meta >> 16) & 0xFFu;
+    const int o0 = P.offsets[i];
+    r.line = P.bytes + o0;
+    if (r.wide) {
+        if (lo4.w >= P.wide_cap) { r.ok = false; return; }
+        const WideRow& w = P.wide_rows[lo4.w];
+        r.ts = w.ts;
+        r.host = Span{P.bytes + w.host.x, w.host.y};
+        r.app = Span{P.bytes + w.app.x, w.app.y};
+        r.proc = Span{P.bytes + w.proc.x, w.proc.y};
+        if (w.msg.x >= 0) r.msg = Span{P.bytes + w.msg.x, w.msg.y};
+        r.full = Span{P.bytes + max(w.full.x, 0), w.full.x >= 0 ? w.full.y : 0};
+        r.first = (uint32_t)w.sd.x;
+        r.count = (uint32_t)w.sd.y;
+        if ((unsigned long long)r.first + r.count > (unsigned long long)P.wentry_cap) { r.ok = false; return; }
+        for (uint32_t e = r.first; e < r.first + r.count; ++e)
+            if ((P.wentry_meta[e] & 0x07u) == 7u) {
+                r.has_sd = true;
+                r.sd_id = Span{P.bytes + P.wentry_name[e].x, P.wentry_name[e].y};
+            }
+        return;
+    }
+    r.ts = __hiloint2double((int)lo4.y, (int)lo4.x);
+    const int sp1 = (int)(hi4.x >> 16), sp2 = (int)(hi4.y & 0xFFFFu), sp3 = (int)(hi4.y >> 16), sp4 = (int)(hi4.z & 0xFFFFu);
+    const int msg_o = (int)(hi4.w & 0xFFFFu), msg_l = (int)(hi4.w >> 16);
+    r.host = Span{r.line + sp1 + 1, sp2 - sp1 - 1};
+    r.app = Span{r.line + sp2 + 1, sp3 - sp2 - 1};
+    r.proc = Span{r.line + sp3 + 1, sp4 - sp3 - 1};
+    if (msg_l) r.msg = Span{r.line + msg_o, msg_l};
+    r.full = Span{r.line, msg_o + msg_l};
+    r.first = lo4.w;
+    r.count = hi4.x & 0xFFFFu;
+    if ((unsigned long long)r.first + r.count > (unsigned long long)P.entry_cap) { r.ok = false; return; }
+    for (uint32_t e = r.first; e < r.first + r.count; ++e) {
+        const unsigned long long v = P.entries[e];
+        if (v & kE8Header) {
+            r.has_sd = true;
+            r.sd_id = Span{r.line + (int)(v & 0xFFFFu), (int)((v >> 16) & 0xFFFFu) - (int)(v & 0xFFFFu)};
+        }
+    }
+}
+
+// pair e of the line (false: the row is an element header)
+__device__ __forceinline__ bool load_pair(const GelfEncodeParams& P, const RecView& r, uint32_t e, Span& name, Span& val) {
+    if (r.wide) {
+        const uint8_t m = P.wentry_meta[e];
+        if ((m & 0x07u) == 7u) return false;
+        name = Span{P.bytes + P.wentry_name[e].x, P.wentry_name[e].y};
+        const unsigned long long v = P.wentry_val[e];
+        val = Span{((m & 0x80u) ? P.arena : P.bytes) + (uint32_t)v, (int)(v >> 32)};
+        return true;
+    }
+    const unsigned long long v = P.entries[e];
+    if (v & kE8Header) return false;
+    const int ns = (int)(v & 0xFFFFu), ne = (int)((v >> 16) & 0xFFFFu);
+    name = Span{r.line + ns, ne - ns};
+    if (v & kE8Arena) {
+        const uint8_t* rec = P.arena + ((uint32_t)((v >> 32) & 0x3FFFFFFFu) << 1);
+        val = Span{rec + 2, (int)*reinterpret_cast<const uint16_t*>(rec)};
+    } else {
+        val = Span{r.line + ne + 2, (int)((v >> 32) & 0xFFFFu) - (ne + 2)};
+    }
+    return true;
+}
+
+// static items (host-prepared, sorted by key, extras already override fixed keys of the same name)
+enum { GF_APP = 0, GF_FULL, GF_HOST, GF_LEVEL, GF_PROC, GF_SDID, GF_SHORT, GF_TS, GF_VERSION, GF_EXTRA = 100 };
+
+template <class Sink>
+__device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const RecView& r, Sink& s) {
+    s.put('{');
+    bool first = true;
+    int si = 0;
+    Span prev{nullptr, -1};  // last SD name emitted (or skipped)
+    bool have_prev = false;
+    for (;;) {
+        // next SD pair in key order: the smallest name greater than `prev`; of equal names the LAST one (a later
+        // BTreeMap insert replaces the earlier value, gelf_encoder.rs:109)
+        Span bn{nullptr, 0}, bv{nullptr, 0};
+        bool have = false;
+        for (uint32_t e = r.first; e < r.first + r.count; ++e) {
+            Span nm, vl;
+            if (!load_pair(P, r, e, nm, vl)) continue;
+            if (have_prev && cmp_names(nm, prev) <= 0) continue;
+            if (!have || cmp_names(nm, bn) <= 0) {
+                bn = nm;
+                bv = vl;
+                have = true;
+            }
+        }
+        if (!have && si >= P.n_static) break;
+        int take_static = 0;  // 0: SD pair, 1: static item, 2: static item and drop the SD pair of the same key
+        if (!have) take_static = 1;
+        else if (si < P.n_static) {
+            const Span key{P.static_blob + P.static_key_off[si], P.static_key_off[si + 1] - P.static_key_off[si]};
+            const int c = cmp_sd_key(bn, key);
+            if (c > 0) take_static = 1;
+            else if (c == 0) {
+                if (P.static_kind[si] == GF_EXTRA) take_static = 2;  // extras are inserted last (gelf_encoder.rs:110-112)
+                else { ++si; }                                       // an SD pair replaces a fixed field of the same key
+            }
+        }
+        if (take_static) {
+            const int kind = P.static_kind[si];
+            const uint8_t* lit = P.static_blob + P.static_lit_off[si];
+            const int lit_len = P.static_lit_off[si + 1] - P.static_lit_off[si];
+            ++si;
+            if (take_static == 2) { prev = bn; have_prev = true; }
+            bool present = true;
+            if (kind == GF_SDID) present = r.has_sd;
+            if (!present) continue;
+            if (!first) s.put(',');
+            first = false;
+            put_lit(s, lit, lit_len);  // `"key":` — for an extra the whole `"key":"value"`
+            switch (kind) {
+                case GF_APP: put_string(s, r.app); break;
+                case GF_FULL: put_string(s, r.full); break;
+                case GF_HOST:
+                    if (r.host.len == 0) { const uint8_t u[] = {'"', 'u', 'n', 'k', 'n', 'o', 'w', 'n', '"'}; put_lit(s, u, 9); }
+                    else put_string(s, r.host);
+                    break;
+                case GF_LEVEL: s.put('0' + r.severity); break;
+                case GF_PROC: put_string(s, r.proc); break;
+                case GF_SDID: put_string(s, r.sd_id); break;
+                case GF_SHORT:
+                    if (r.msg.p == nullptr) { s.put('"'); s.put('-'); s.put('"'); }
+                    else put_string(s, r.msg);
+                    break;
+                case GF_TS: {
+                    uint8_t num[32];
+                    const int k = json_f64(r.ts, num);
+                    put_lit(s, num, k);
+                    break;
+                }
+                case GF_VERSION: { const uint8_t v[] = {'"', '1', '.', '1', '"'}; put_lit(s, v, 5); break; }
+                default: break;  // GF_EXTRA: the literal was everything
+            }
+            continue;
+        }
+        if (!first) s.put(',');
+        first = false;
+        s.put('"');
+        s.put('_');
+        put_escaped(s, bn);
+        s.put('"');
+        s.put(':');
+        put_string(s, bv);
+        prev = bn;
+        have_prev = true;
+    }
+    s.put('}');
+    s.finish();
+}
+
+__global__ void __launch_bounds__(128) gelf_size_kernel(const __grid_constant__ GelfEncodeParams P) {
+    if (*P.bad_offsets) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    RecView r;
+    load_view(P, i, r);
+    uint32_t len = 0;
+    if (r.ok) {
+        CountSink s;
+        emit_record(P, r, s);
+        len = s.n;
+    }
+    P.lens[i] = len;
+    P.status[i] = (uint8_t)(P.rows[2 * (size_t)i].z & 0xFFu);
+}
+
+// chunk totals: base[k + 1] = base[k] + bytes of this chunk (one thread)
+__global__ void gelf_base_kernel(const __grid_constant__ GelfEncodeParams P) {
+    if (*P.bad_offsets) return;
+    const unsigned long long total = (unsigned long long)P.rel[P.n - 1] + P.lens[P.n - 1];
+    P.base[1] = P.base[0] + total;
+}
+
+__global__ void __launch_bounds__(128) gelf_write_kernel(const __grid_constant__ GelfEncodeParams P) {
+    if (*P.bad_offsets) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const unsigned long long at = P.base[0] + P.rel[i];
+    P.out_offsets[i] = (long long)at;
+    if (i == P.n - 1) P.out_offsets[P.n] = (long long)(at + P.lens[i]);
+    const uint32_t len = P.lens[i];
+    if (len == 0u || at + len > P.out_cap) return;  // rejected line, or the output buffer overflowed (the batch is redone)
+    RecView r;
+    load_view(P, i, r);
+    WordSink s(P.out + at);
+    emit_record(P, r, s);
+}
+
+}  // namespace
+
+size_t gelf_scan_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+    return bytes;
+}
+
+cudaError_t launch_gelf_encode(const GelfEncodeParams& p, void* d_scan_temp, size_t scan_temp_bytes, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int grid = (p.n + 127) / 128;
+    gelf_size_kernel<<<grid, 128, 0, stream>>>(p);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_temp, scan_temp_bytes, p.lens, p.rel, p.n, stream);
+    if (e != cudaSuccess) return e;
+    gelf_base_kernel<<<1, 1, 0, stream>>>(p);
+    gelf_write_kernel<<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace fg

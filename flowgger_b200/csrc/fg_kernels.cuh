@@ -106,6 +106,37 @@ cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream);  //
 cudaError_t configure_parse5424(int max_tile_bytes);
 int parse5424_smem_bytes(int tile_bytes);
 
+// ---- fused GELF encoder over the RFC5424 results (fg_gelf_encode.cu) ---------------------------------------------------
+struct GelfEncodeParams {
+    const uint8_t* bytes;
+    const int32_t* offsets;  // [n+1], element 0 = first line of this launch
+    int32_t n;
+    const uint4* rows;       // compact rows of these lines
+    const unsigned long long* entries;
+    const uint8_t* arena;
+    const WideRow* wide_rows;
+    const int2* wentry_name;
+    const unsigned long long* wentry_val;
+    const uint8_t* wentry_meta;
+    // fixed GELF keys + output.gelf_extra, sorted by key on the host (extras already replace fixed keys of the same name)
+    const uint8_t* static_blob;
+    int32_t n_static;
+    const int32_t* static_key_off;  // [n_static+1] raw key bytes (for ordering against the SD names)
+    const int32_t* static_lit_off;  // [n_static+1] text to emit: `"key":`, for an extra `"key":"value"`
+    const int32_t* static_kind;     // [n_static] GF_*
+    uint32_t* lens;                 // [n] record lengths (size pass)
+    uint32_t* rel;                  // [n] exclusive sum of lens inside this launch
+    unsigned long long* base;       // base[0] = output bytes before this launch, base[1] receives base[0] + this launch's bytes
+    uint8_t* out;
+    unsigned long long out_cap;
+    long long* out_offsets;         // [n+1] absolute record offsets, element 0 = first line of this launch
+    uint8_t* status;                // [n] decoder status per line (0 = a record was written)
+    const uint32_t* bad_offsets;
+    uint32_t entry_cap, wide_cap, wentry_cap;  // a table that overflowed is not read (the batch is redone after a regrow)
+};
+cudaError_t launch_gelf_encode(const GelfEncodeParams& p, void* d_scan_temp, size_t scan_temp_bytes, cudaStream_t stream);
+size_t gelf_scan_temp_bytes(int n);
+
 constexpr int kLinesPerCta = 128;   // lines (= threads) per CTA (256 was measured slower: bigger barriers, same warps/SM)
 constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (tile ~26 KB at 180 B/line) allows 7 CTAs
 // GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 16 CTAs/SM at 32

@@ -222,6 +222,23 @@ void CudaBatchDecoder::decode_batch(const uint8_t* bytes, const int32_t* offsets
     if (rc != FG_OK) throw std::runtime_error(std::string("fg_decode_batch: ") + fg_last_error(ctx_));
 }
 
+void CudaBatchDecoder::decode_encode_gelf(const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                                          const std::vector<std::pair<std::string, std::string>>& extra, fg_encoded_out* out) {
+    if (!extra_valid_ || extra != extra_set_) {
+        std::vector<const char*> k, v;
+        for (const auto& kv : extra) {
+            k.push_back(kv.first.c_str());
+            v.push_back(kv.second.c_str());
+        }
+        if (fg_set_gelf_extra(ctx_, (int32_t)extra.size(), k.data(), v.data()) != FG_OK)
+            throw std::runtime_error(std::string("fg_set_gelf_extra: ") + fg_last_error(ctx_));
+        extra_set_ = extra;
+        extra_valid_ = true;
+    }
+    const int rc = fg_decode_encode_gelf(ctx_, fmt_, bytes, offsets, n, out);
+    if (rc != FG_OK) throw std::runtime_error(std::string("fg_decode_encode_gelf: ") + fg_last_error(ctx_));
+}
+
 static std::string_view span_sv(const uint8_t* bytes, fg_span s) {
     return std::string_view((const char*)bytes + s.off, (size_t)s.len);
 }
@@ -443,6 +460,7 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
                                const Decoder& decoder, const Encoder& encoder, std::ostream& err_out,
                                std::ostream& std_out) const {
     std::shared_ptr<CudaBatchDecoder> gpu = decoder.batch();
+    const CudaGelfEncoder* fused = dynamic_cast<const CudaGelfEncoder*>(&encoder);
     // a batch never exceeds what the context can take (Limits used to be independent of DeviceOptions)
     const int64_t max_bytes = std::min<int64_t>(lim_.max_bytes, gpu->capacity_bytes());
     const int32_t max_lines = std::min<int32_t>(lim_.max_lines, gpu->capacity_lines());
@@ -461,6 +479,25 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
         const uint8_t dummy = 0;
         const uint8_t* bytes = arena.empty() ? &dummy : arena.data();
         std::lock_guard<std::mutex> guard(gpu->mutex());  // held until every Record of the batch has been materialised
+        if (fused != nullptr && gpu->format() == FG_FMT_RFC5424) {
+            // decode + encode on the device (line_splitter.rs:50-52 fused): only the encoded records come back
+            fg_encoded_out eo;
+            gpu->decode_encode_gelf(bytes, offsets.data(), n, fused->extra(), &eo);
+            for (int32_t i = 0; i < n; ++i) {
+                for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";
+                if (eo.status[i] == 0) {
+                    tx(std::vector<uint8_t>(eo.bytes + eo.offsets[i], eo.bytes + eo.offsets[i + 1]));
+                } else {
+                    std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+                    err_out << fg_error_string(gpu->format(), eo.status[i]) << ": [" << rust_trim(line) << "]\n";
+                }
+            }
+            for (int32_t k = 0; k < invalid_before[(size_t)n]; ++k) err_out << "Invalid UTF-8 input\n";
+            arena.clear();
+            offsets.assign(1, 0);
+            invalid_before.assign(1, 0);
+            return;
+        }
         gpu->decode_batch(bytes, offsets.data(), n, &out);
         for (int32_t i = 0; i < n; ++i) {
             for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
@@ -873,6 +910,43 @@ int fgh_clone_decode_threads(int fmt, int device, const uint8_t* bytes, const in
         if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", e.what());
         return -1;
     }
+}
+
+// BatchingLineSplitter with output.format = "gelf" (fused decode + encode): text in, one JSON record per line out
+int fgh_splitter_run_gelf(void* d, const uint8_t* text, int64_t len, int32_t max_lines, int64_t max_bytes, int n_extra,
+                          const char* const* keys, const char* const* vals, uint8_t** out_records, int64_t* out_records_len,
+                          uint8_t** out_stderr, int64_t* out_stderr_len) {
+    struct Shared : Decoder {
+        std::shared_ptr<CudaBatchDecoder> b;
+        DecodeResult decode(std::string_view) const override { return {}; }
+        std::unique_ptr<Decoder> clone_boxed() const override { return nullptr; }
+        std::shared_ptr<CudaBatchDecoder> batch() const override { return b; }
+    } dec;
+    dec.b = std::shared_ptr<CudaBatchDecoder>((CudaBatchDecoder*)d, [](CudaBatchDecoder*) {});
+    std::vector<std::pair<std::string, std::string>> extra;
+    for (int k = 0; k < n_extra; ++k) extra.emplace_back(keys[k], vals[k]);
+    CudaGelfEncoder enc(extra);
+    BatchingLineSplitter::Limits lim;
+    lim.max_lines = max_lines;
+    lim.max_bytes = max_bytes;
+    BatchingLineSplitter sp(lim);
+    std::string in((const char*)text, (size_t)len);
+    std::istringstream is(in);
+    std::ostringstream es, os;
+    std::string records;
+    try {
+        sp.run(is, [&](std::vector<uint8_t>&& v) { records.append(v.begin(), v.end()); records.push_back('\n'); }, dec, enc, es, os);
+    } catch (const std::exception&) {
+        return -1;
+    }
+    auto give = [](const std::string& s, uint8_t** p, int64_t* n) {
+        *p = (uint8_t*)malloc(s.size() ? s.size() : 1);
+        memcpy(*p, s.data(), s.size());
+        *n = (int64_t)s.size();
+    };
+    give(records, out_records, out_records_len);
+    give(es.str(), out_stderr, out_stderr_len);
+    return 0;
 }
 
 int fgh_is_valid_utf8(const uint8_t* p, int64_t n) { return is_valid_utf8(p, (size_t)n) ? 1 : 0; }

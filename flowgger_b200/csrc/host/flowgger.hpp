@@ -109,11 +109,16 @@ class CudaBatchDecoder {
                                   std::vector<std::string>* side_effects = nullptr) const;
     // framing + UTF-8 validation + decode of a raw byte stream on the device (fg_split_decode)
     void split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
+    // decode + GelfEncoder::encode fused on the device (fg_decode_encode_gelf); `extra` = output.gelf_extra
+    void decode_encode_gelf(const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                            const std::vector<std::pair<std::string, std::string>>& extra, fg_encoded_out* out);
 
    private:
     fg_format fmt_;
     fg_ctx* ctx_ = nullptr;
     std::mutex mu_;
+    std::vector<std::pair<std::string, std::string>> extra_set_;
+    bool extra_valid_ = false;
     LtsvConfig ltsv_;
     DeviceOptions opt_;
     std::string suffix_[5];
@@ -156,6 +161,22 @@ class Encoder {
    public:
     virtual ~Encoder() = default;
     virtual bool encode(Record&& record, std::vector<uint8_t>& out, const char** err) const = 0;
+};
+
+// encoder/gelf_encoder.rs:10-48: output.format = "gelf".  The encoder runs FUSED with the decoder on the GPU
+// (fg_decode_encode_gelf): BatchingLineSplitter recognises this type and never materialises Records for it.
+class CudaGelfEncoder : public Encoder {
+   public:
+    explicit CudaGelfEncoder(std::vector<std::pair<std::string, std::string>> extra = {}) : extra_(std::move(extra)) {}
+    // a lone host-side Record cannot be encoded: there is no CPU encoder behind this interface
+    bool encode(Record&&, std::vector<uint8_t>&, const char** err) const override {
+        if (err) *err = "GelfEncoder runs fused with the decoder on the GPU (use BatchingLineSplitter)";
+        return false;
+    }
+    const std::vector<std::pair<std::string, std::string>>& extra() const { return extra_; }
+
+   private:
+    std::vector<std::pair<std::string, std::string>> extra_;
 };
 
 // Batched twin of LineSplitter::run (splitter/line_splitter.rs:10-54): reads lines like

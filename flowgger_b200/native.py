@@ -44,6 +44,11 @@ WIDE_ROW = np.dtype([("line", "<i4"), ("meta", "<u4"), ("ts", "<f8"), ("hostname
 assert ROW5424.itemsize == 32 and WIDE_ROW.itemsize == 72
 
 
+class FgEncodedOut(C.Structure):
+    _fields_ = [("n", C.c_int32), ("bytes", C.POINTER(C.c_uint8)), ("offsets", C.POINTER(C.c_int64)), ("status", C.POINTER(C.c_uint8)),
+                ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
+
+
 _cuda = None
 _host = None
 _gen = None
@@ -85,6 +90,8 @@ def load_cuda() -> C.CDLL:
         L.fg_last_split_ms.restype = C.c_float
         L.fg_last_split_ms.argtypes = [C.c_void_p]
         L.fg_error_count.restype = C.c_uint32
+        L.fg_set_gelf_extra.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+        L.fg_decode_encode_gelf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FgEncodedOut)]
         _cuda = L
     return _cuda
 
@@ -118,6 +125,8 @@ def load_host() -> C.CDLL:
                                             C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
         L.fgh_clone_decode_threads.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.fgh_splitter_run_gelf.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64, C.c_int, C.POINTER(C.c_char_p),
+                                            C.POINTER(C.c_char_p)] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 2
         L.fgh_splitter_run.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 3
         _host = L
     return _host
@@ -302,6 +311,29 @@ class BatchDecoder:
         self._check(self.L.fg_decode_batch(self.ctx, self.fmt, _ptr(data), _ptr(offsets), n, C.byref(out)), "fg_decode_batch")
         return BatchResult(out, self.fmt)
 
+    def set_gelf_extra(self, extra: dict[str, str]) -> None:
+        """output.gelf_extra of GelfEncoder::new (gelf_encoder.rs:29-48)."""
+        ex = list(extra.items())
+        keys = (C.c_char_p * max(len(ex), 1))(*[k.encode() for k, _ in ex])
+        vals = (C.c_char_p * max(len(ex), 1))(*[v.encode() for _, v in ex])
+        self._check(self.L.fg_set_gelf_extra(self.ctx, len(ex), keys, vals), "fg_set_gelf_extra")
+
+    def decode_encode_gelf(self, data: np.ndarray, offsets: np.ndarray, copy: bool = True):
+        """decode + GelfEncoder::encode fused on the device: (JSON bytes, int64 offsets[n+1], status uint8[n], kernel ms).
+        With copy=False the arrays are views of the context's pinned buffers (valid until the next call)."""
+        assert data.dtype == np.uint8 and offsets.dtype == np.int32
+        out = FgEncodedOut()
+        n = len(offsets) - 1
+        self._keep = (data, offsets)
+        self._check(self.L.fg_decode_encode_gelf(self.ctx, self.fmt, _ptr(data), _ptr(offsets), n, C.byref(out)), "fg_decode_encode_gelf")
+        offs = np.ctypeslib.as_array(out.offsets, shape=(n + 1,))
+        total = int(offs[-1]) if n else 0
+        buf = np.ctypeslib.as_array(out.bytes, shape=(max(total, 1),))[:total]
+        status = np.ctypeslib.as_array(out.status, shape=(max(n, 1),))[:n]
+        if copy:
+            return buf.tobytes(), offs.copy(), status.copy(), out.kernel_ms
+        return buf, offs, status, out.kernel_ms
+
     def split_decode(self, stream: np.ndarray) -> BatchResult:
         """Framing + UTF-8 validation + decode of a raw newline-terminated byte stream, all on the device."""
         assert stream.dtype == np.uint8
@@ -436,6 +468,27 @@ def clone_decode_threads(fmt: int, lines: list[bytes], nthreads: int = 2, device
         H.fgh_free(pb)
         H.fgh_free(po)
     return [buf[o[i]:o[i + 1]] for i in range(len(lines))]
+
+
+def splitter_run_gelf(dec: "BatchDecoder", text: bytes, extra: dict[str, str] | None = None, max_lines: int = 1 << 16,
+                      max_bytes: int = 16 << 20) -> tuple[bytes, bytes]:
+    """BatchingLineSplitter with input.format = rfc5424 and output.format = gelf (decode + encode fused on the GPU):
+    returns (JSON records separated by newlines, stderr text)."""
+    H = load_host()
+    ex = list((extra or {}).items())
+    keys = (C.c_char_p * max(len(ex), 1))(*[k.encode() for k, _ in ex])
+    vals = (C.c_char_p * max(len(ex), 1))(*[v.encode() for _, v in ex])
+    ps = [C.c_void_p() for _ in range(2)]
+    ns = [C.c_int64() for _ in range(2)]
+    rc = H.fgh_splitter_run_gelf(dec._h, text, len(text), max_lines, max_bytes, len(ex), keys, vals, C.byref(ps[0]), C.byref(ns[0]),
+                                 C.byref(ps[1]), C.byref(ns[1]))
+    if rc != 0:
+        raise RuntimeError("splitter failed")
+    out = []
+    for p, n in zip(ps, ns):
+        out.append(C.string_at(p, n.value))
+        H.fgh_free(p)
+    return tuple(out)
 
 
 def splitter_run(dec: "BatchDecoder", text: bytes, max_lines: int = 1 << 16, max_bytes: int = 16 << 20) -> tuple[bytes, bytes, bytes]:

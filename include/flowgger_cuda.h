@@ -220,6 +220,27 @@ int fg_parse_resident_n(fg_ctx* ctx, fg_format fmt, int32_t k, float* total_ms);
 int fg_download(fg_ctx* ctx, fg_format fmt, fg_batch_out* out);
 int fg_flush_l2(fg_ctx* ctx); /* writes a >L2-sized scratch buffer */
 
+/* ---- decode + encode fused on the device ------------------------------------------------------
+ * The reference calls Encoder::encode right after Decoder::decode for every record (splitter/line_splitter.rs:50-52).
+ * For the default pair input.format = "rfc5424" / output.format = "gelf" both stages run on the GPU and only the
+ * encoded records come back:
+ *     GelfEncoder::new(&Config)   encoder/gelf_encoder.rs:29-48   -> fg_set_gelf_extra (output.gelf_extra)
+ *     Encoder::encode(Record)     encoder/gelf_encoder.rs:59-115, encoder/mod.rs:54-56 -> fg_decode_encode_gelf
+ * Record i is bytes[offsets[i], offsets[i+1]) — exactly the Vec<u8> the reference's encode returns (serde_json 0.8
+ * text: keys in byte order, later inserts replace earlier ones, no whitespace); a line the decoder rejects has
+ * status[i] != 0 (fg_error_string) and an empty record. */
+typedef struct fg_encoded_out {
+    int32_t n;
+    const uint8_t* bytes;     /* concatenated records */
+    const int64_t* offsets;   /* [n+1] */
+    const uint8_t* status;    /* [n] */
+    float kernel_ms;          /* parse + encode kernels */
+    float total_ms;
+} fg_encoded_out;
+int fg_set_gelf_extra(fg_ctx* ctx, int32_t n, const char* const* keys, const char* const* values);
+int fg_decode_encode_gelf(fg_ctx* ctx, fg_format fmt /* FG_FMT_RFC5424 */, const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                          fg_encoded_out* out);
+
 /* the reference's Err(&'static str) for a row status (0 -> NULL) */
 const char* fg_error_string(fg_format fmt, uint32_t status);
 uint32_t fg_error_count(void);
