@@ -1009,8 +1009,15 @@ int fg_decode_encode_gelf(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const 
 }
 
 int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
+    return fg_split_decode_framed(c, fmt, FG_FRAME_LINE, stream, nbytes, out);
+}
+
+int fg_split_decode_framed(fg_ctx* c, fg_format fmt, fg_framing framing, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
     if (!c || !out) return FG_E_ARG;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if (framing != FG_FRAME_LINE && framing != FG_FRAME_NUL) return fail(c, FG_E_ARG, "unknown framing");
+    const int delim = framing == FG_FRAME_NUL ? 0 : '\n';
+    const int strip = framing == FG_FRAME_NUL ? 2 : 1;
     if (nbytes < 0 || (nbytes > 0 && !stream)) return fail(c, FG_E_ARG, "null input");
     if ((size_t)nbytes > c->max_bytes) return fail(c, FG_E_CAPACITY, "stream has more bytes than max_batch_bytes");
     FG_CUDA(c, cudaSetDevice(c->device));
@@ -1055,11 +1062,11 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
             const long long c0 = (long long)k * kChunk, c1 = std::min<long long>(nbytes, c0 + kChunk);
             const bool last = k == chunks - 1;
             if (int rc = h2d(c, c->d_bytes + c0, stream + c0, (size_t)(c1 - c0), pinned, bounce_ix)) return rc;
-            if (last) FG_CUDA(c, cudaMemsetAsync(c->d_bytes + nbytes, 0, 64, c->s_h2d));  // whole-vector loads past the end see no '\n'
+            if (last) FG_CUDA(c, cudaMemsetAsync(c->d_bytes + nbytes, delim ? 0 : 0xFF, 64, c->s_h2d));  // whole-vector loads past the end see no delimiter
             FG_CUDA(c, cudaEventRecord(c->ev_h2d[k], c->s_h2d));
             FG_CUDA(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[k], 0));
             FG_CUDA(c, fg::launch_split_chunk(c->d_bytes, (long long)nbytes, c0, c1, last ? 1 : 0, c->d_seg, (uint32_t*)(c->d_n_lines + 8),
-                                              c->d_cum + k, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, c->s_comp));
+                                              c->d_cum + k, c->d_offsets, c->d_n_lines, c->max_lines, c->d_invalid, delim, c->s_comp));
             c->launches += 4;
             FG_CUDA(c, cudaMemcpyAsync(c->h_cum + k, c->d_cum + k, 4, cudaMemcpyDeviceToHost, c->s_comp));
             if (last) {
@@ -1090,7 +1097,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
                 const int tile = pick_tile(c, std::max<size_t>(span_bytes, 1), cnt, (int)fmt);
                 FG_CUDA(c, cudaStreamWaitEvent(c->s_parse, c->ev_split[dep], 0));
                 FG_CUDA(c, cudaEventRecord(c->ev_k0[nparse], c->s_parse));
-                if (int rc = launch_lines(c, (int)fmt, done_lines, cnt, tile, c->d_invalid + done_lines, 1, c->s_parse)) return rc;
+                if (int rc = launch_lines(c, (int)fmt, done_lines, cnt, tile, c->d_invalid + done_lines, strip, c->s_parse)) return rc;
                 FG_CUDA(c, cudaEventRecord(c->ev_k1[nparse], c->s_parse));
                 FG_CUDA(c, cudaMemcpyAsync(c->h_counts + (size_t)nparse * kCnt, c->d_k, sizeof(uint32_t) * kCnt, cudaMemcpyDeviceToHost, c->s_parse));
                 FG_CUDA(c, cudaEventRecord(c->ev_cnt[nparse], c->s_parse));

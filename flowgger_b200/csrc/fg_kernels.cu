@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(LINES, MINB) parse_kernel(const __grid_constan
         if (P.strip_eol && len > 0) {
             // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
             const uint8_t* lp = direct ? P.bytes + o0 : tile + (o0 - base);
-            if (lp[len - 1] == '\n') {
+            if (P.strip_eol == 2) {  // BufRead::split(0): only the NUL terminator goes (nul_splitter.rs:18)
+                if (lp[len - 1] == 0) --len;
+            } else if (lp[len - 1] == '\n') {
                 --len;
                 if (len > 0 && lp[len - 1] == '\r') --len;
             }

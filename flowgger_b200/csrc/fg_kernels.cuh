@@ -157,7 +157,7 @@ const char* kernel_build_info();
 // device-side line framing + UTF-8 validation (fg_split.cu)
 cudaError_t launch_split_chunk(const uint8_t* d_bytes, long long nbytes, long long c0, long long c1, int is_last, uint32_t* d_seg,
                                uint32_t* d_run, int32_t* d_cum_k, int32_t* d_offsets, int32_t* d_n_lines, int max_lines,
-                               uint8_t* d_invalid, cudaStream_t stream);
+                               uint8_t* d_invalid, int delim, cudaStream_t stream);
 int split_segments(long long nbytes);
 
 }  // namespace fg

@@ -40,12 +40,9 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     const uint32_t lane = (uint32_t)tid & 31u;
     const int first = blockIdx.x * LINES;
     const int last = min(P.n, first + LINES);
-    // two bitmaps behind the tile: I ("may end a token") and V ('"' / '\\'), each tile_bytes / 8 + 16 bytes
-    const int bm_bytes = P.tile_bytes / 8 + 16;
+    // the bitmap I ("may end a token") lives behind the tile: tile_bytes / 8 + 16 bytes
     uint32_t* bmI = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    uint32_t* bmV = reinterpret_cast<uint32_t*>(tile + P.tile_bytes + bm_bytes);
     uint16_t* bmI16 = reinterpret_cast<uint16_t*>(bmI);
-    uint16_t* bmV16 = reinterpret_cast<uint16_t*>(bmV);
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -78,17 +75,13 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- stage 1: structural bitmaps of the whole tile, 16 bytes per thread per step ------------------------
+        // ---- stage 1: structural bitmap of the whole tile, 16 bytes per thread per step ------------------------
         const int ngran = (int)(nbytes >> 4);
         for (int g = tid; g < ngran; g += LINES) {
             const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
             bmI16[g] = (uint16_t)r5_classify16(v.x, v.y, v.z, v.w);
-            bmV16[g] = (uint16_t)r5_classify16_v(v.x, v.y, v.z, v.w);
         }
-        if (tid < 6) {  // r5_window reads up to two words past the last granule
-            bmI16[ngran + tid] = 0;
-            bmV16[ngran + tid] = 0;
-        }
+        if (tid < 6) bmI16[ngran + tid] = 0;  // r5_window reads up to two words past the last granule
         __syncthreads();
 
         // ---- stage 2: one thread per line ------------------------------------------------------------------------
@@ -98,7 +91,9 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         bool bad_utf8 = false;
         if (P.strip_eol && le > ls) {
             // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
-            if (tile[le - 1] == '\n') {
+            if (P.strip_eol == 2) {  // BufRead::split(0): only the NUL terminator goes (nul_splitter.rs:18)
+                if (tile[le - 1] == 0) --le;
+            } else if (tile[le - 1] == '\n') {
                 --le;
                 if (le > ls && tile[le - 1] == '\r') --le;
             }
@@ -106,7 +101,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         }
         const bool too_long = le - ls > 65535;
         R5Fast res;
-        const bool regular = r5_regular(tile, bmI, bmV, ls, (too_long || bad_utf8 || !active) ? ls : le, res);
+        const bool regular = r5_regular(tile, bmI, ls, (too_long || bad_utf8 || !active) ? ls : le, res);
         if (bad_utf8) {
             res.status = FG_ES_INVALID_UTF8;
             res.n_entries = 0;
@@ -245,7 +240,9 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
             o0 = P.offsets[line];
             len = P.offsets[line + 1] - o0;
             if (P.strip_eol && len > 0) {
-                if (P.bytes[o0 + len - 1] == '\n') {
+                if (P.strip_eol == 2) {
+                    if (P.bytes[o0 + len - 1] == 0) --len;
+                } else if (P.bytes[o0 + len - 1] == '\n') {
                     --len;
                     if (len > 0 && P.bytes[o0 + len - 1] == '\r') --len;
                 }
@@ -274,7 +271,7 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
                 const unsigned long long v = sink.val[e];
                 const uint32_t off = (uint32_t)v, l = (uint32_t)(v >> 32);
                 const uint32_t ul = (uint32_t)r5_unescape(P.bytes + off, (int)l, nullptr);
-                const uint32_t at = atomicAdd(P.counters + K5_ARENA, ul);
+                const uint32_t at = atomicAdd(P.counters + K5_ARENA, (ul + 1u) & ~1u);  // keeps the arena 2-byte aligned for the [u16 length] records
                 if ((unsigned long long)at + ul <= (unsigned long long)P.arena_cap) r5_unescape(P.bytes + off, (int)l, P.arena + at);
                 sink.val[e] = (unsigned long long)at | ((unsigned long long)ul << 32);
                 sink.meta[e] = (uint8_t)0x80u;  // FG_TAG_STRING | FG_EM_ARENA
@@ -314,7 +311,7 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
 
 }  // namespace
 
-int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + 2 * (tile_bytes / 8 + 16); }
+int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 16; }
 
 cudaError_t configure_parse5424(int max_tile_bytes) {
     return cudaFuncSetAttribute(parse5424_kernel<kFastLines, kFastCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -11,19 +11,18 @@
 // arm and produces every error string.  Regular lines therefore never carry an error status.
 //
 //   stage 1  r5_classify16: every thread takes 16-byte granules of the flat tile (LDS.128, conflict-free, all 32 lanes
-//            busy) and writes two bits per byte into two bitmaps (exact per byte, no cross-byte carries):
+//            busy) and writes one bit per byte into a bitmap (exact per byte, no cross-byte carries):
 //              I  "may end a token", a cheap SUPERSET of the delimiters (7 SWAR ops per 4 bytes):
 //                   b <= 0x22            control bytes, ' ', '!', '"'
 //                   (b & 0x1E) == 0x1C   0x1C 0x1D '<' '=' '\\' ']' '|' '}'
 //                   b >= 0x7F            DEL and every non-ASCII byte
 //                 every byte that is NOT flagged is a legal SD-NAME character (:188-192) and is neither a space, a
-//                 quote, '=', ']' nor a backslash;
-//              V  exactly '"' and '\\' (what can end or escape inside an SD value).
+//                 quote, '=', ']' nor a backslash.
 //   stage 2  r5_regular: one thread per line.  Header: the first six flagged bytes must be the six spaces of
 //            splitn(7, ' ') (:23).  PRI and the RFC3339 stamp are parsed at fixed offsets.  Structured data: ONE
-//            name="value" pair per loop iteration — a find-first-set on I gives the '=' that ends the name, a
-//            find-first-set on V the closing quote — and the 32 lines of a warp advance in lock step, so a warp pays
-//            the maximum number of PAIRS over its lanes.
+//            name="value" pair per loop iteration — a find-first-set on I gives the '=' that ends the name, the flagged
+//            bytes after the opening quote lead to the closing one — and the 32 lines of a warp advance in lock step, so a
+//            warp pays the maximum number of PAIRS over its lanes.
 //
 // Structured-data rows are staged as 8-byte packed entries (u16 positions relative to the line start) in the line's OWN
 // already-consumed bytes of the tile: slot k may be written once the cursor has passed its last byte.
@@ -55,17 +54,6 @@ FG_DEV uint32_t r5_gather16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) 
 FG_DEV uint32_t r5_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     return r5_gather16(r5_flags(w0), r5_flags(w1), r5_flags(w2), r5_flags(w3));
 }
-// 0x80 in every byte of w that is '"' (0x22) or '\\' (0x5C); exact per byte
-FG_DEV uint32_t r5_vflags(uint32_t w) {
-    const uint32_t x = w ^ 0x22222222u, y = w ^ 0x5C5C5C5Cu;
-    const uint32_t tx = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 set: byte != '"'
-    const uint32_t ty = ((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y;  // bit 7 set: byte != '\\'
-    return ~(tx & ty) & 0x80808080u;
-}
-FG_DEV uint32_t r5_classify16_v(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    return r5_gather16(r5_vflags(w0), r5_vflags(w1), r5_vflags(w2), r5_vflags(w3));
-}
-
 // ---- stage 2 ----------------------------------------------------------------------------------------------------
 // 32 bitmap bits starting at tile position t (bit 0 = byte t).  bm needs one readable word past the last granule.
 FG_DEV uint32_t r5_window(const uint32_t* bm, int t) {
@@ -130,16 +118,16 @@ FG_DEV int r5_unescape(const uint8_t* v, int len, uint8_t* out) {
 constexpr uint32_t kFlagWide = 0x80u;  // FG_FLAG_WIDE
 
 // Days from 1970-01-01 of a date already known to be valid, and the calendar checks of the fast stamp parser
-FG_DEV uint32_t r5_digit(const uint8_t* T, int at, uint32_t& bad) {
+FG_DEV uint32_t r5_digit(const uint8_t* T, int at, uint32_t& worst) {
     const uint32_t d = (uint32_t)T[at] - (uint32_t)'0';
-    bad |= d > 9u ? 1u : 0u;
+    worst = max(worst, d);  // every "digit" was one iff the maximum is <= 9
     return d;
 }
 
-// T: tile bytes (shared memory), bmI / bmV: its bitmaps; the line is T[ls, le).  Idle lanes pass ls == le.
+// T: tile bytes (shared memory), bmI: its bitmap; the line is T[ls, le).  Idle lanes pass ls == le.
 // Returns true when the line is regular and `r` holds its Record fields (status is always Ok); false hands the line to
 // the slow kernel.  ALL lanes of a warp must call this together.
-FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, const uint32_t* bmV, int ls, int le, R5Fast& r) {
+FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, int ls, int le, R5Fast& r) {
     r.ts = 0.0;
     r.status = FG_ST_OK;
     r.facility = 0xFFu;
@@ -159,7 +147,7 @@ FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, const uint32_t* bmV, int
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             uint32_t W = r5_window(bmI, t);
-            if (W == 0u) {  // a field longer than 31 bytes (a stamp with nanoseconds and an offset is 35): look once more
+            if (k == 1 && W == 0u) {  // the stamp may be longer than 31 bytes (nanoseconds + offset: 35): look once more
                 t += 32;
                 W = r5_window(bmI, t);
             }
@@ -218,7 +206,7 @@ FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, const uint32_t* bmV, int
             if (sg == '-') off = -off;
         }
         t.offset_seconds = off;
-        ok = ok && bad == 0u && t.second <= 59;  // :60 (leap second stand-in) is the slow path's business
+        ok = ok && bad <= 9u && t.second <= 59;  // :60 (leap second stand-in) is the slow path's business
         if (!ok) { t.year = 2000; t.month = 1; t.day = 1; t.hour = t.minute = t.second = 0; t.nanos = 0; t.offset_seconds = 0; }
         double ts = 0.0;
         ok = finish_datetime(t, false, ts) && ok;
@@ -260,20 +248,32 @@ FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, const uint32_t* bmV, int
                 e = i + fg_ffs(W) - 1;
                 if (W == 0u || (W & 1u) || e + 2 >= le || T[e] != '=' || T[e + 1] != '"') { ok = false; active = false; }
             }
-            // value: up to the first unescaped '"' (:216, :217, :231) — hops over the exact '"' / '\\' bitmap
+            // value: up to the first unescaped '"' (:216, :217, :231).  Every '"' and '\\' is a flagged byte; the flagged
+            // bytes of a 32-byte window are walked inside the lane (spaces and the like are stepped over), the warp only
+            // loops for values longer than a window.
             int c = e + 2;
             bool has_bs = false;
             {
                 bool s = active;
                 for (;;) {
                     if (s) {
-                        const uint32_t W = r5_window(bmV, c);
-                        c += W ? fg_ffs(W) - 1 : 32;
-                        if (c >= le) s = false;
-                        else if (W) {
-                            if (T[c] == '"') s = false;
-                            else { has_bs = true; c += 2; }  // the escaped byte is skipped
+                        uint32_t W = r5_window(bmI, c);
+                        const int room = le - c;  // > 0
+                        if (room < 32) W &= (1u << room) - 1u;
+                        int adv = 32;
+                        while (W) {
+                            const int b = fg_ffs(W) - 1;
+                            const uint32_t ch = T[c + b];
+                            if (ch == '"') { adv = b; s = false; break; }
+                            W &= W - 1u;
+                            if (ch == '\\') {  // the escaped byte is skipped, whatever it is
+                                has_bs = true;
+                                W &= ~(2u << b);
+                                if (b == 31) adv = 33;
+                            }
                         }
+                        c += adv;
+                        if (s && c >= le) { c = le; s = false; }
                     }
                     if (!fg_any(s)) break;
                 }

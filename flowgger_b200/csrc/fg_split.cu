@@ -1,5 +1,7 @@
 // fg_split.cu — device-side line framing + UTF-8 validation.
 //
+// The same kernels frame NUL-delimited streams (NulSplitter, splitter/nul_splitter.rs:18-40: `BufRead::split(0)`, the
+// delimiter is dropped, nothing else) — the delimiter byte is a launch parameter.
 // Replaces the per-record work of LineSplitter::run (/root/reference/src/flowgger/splitter/line_splitter.rs:17-25):
 // `BufRead::lines` (split at '\n', drop it and one preceding '\r', a last line without '\n' is still yielded) and the
 // UTF-8 check of `String` (invalid line => "Invalid UTF-8 input", line skipped).  Input: a raw byte stream resident in
@@ -18,14 +20,15 @@ namespace {
 constexpr int kSegBytes = 8192;   // one warp owns one segment
 constexpr int kWarpsPerCta = 8;
 
-__device__ __forceinline__ uint32_t nl_flags(uint32_t w) {  // 0x80 in every byte == '\n' (exact for all bytes)
-    const uint32_t x = w ^ 0x0A0A0A0Au;
+// 0x80 in every byte == the record delimiter (exact for all bytes); pat = the delimiter in all four bytes
+__device__ __forceinline__ uint32_t nl_flags(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
 
-// bytes beyond nbytes are zero (the host clears a tail), so whole 16-byte loads are safe up to the padded end
+// bytes beyond nbytes never equal the delimiter (the host pads the tail), so whole 16-byte loads are safe up to the padded end
 __global__ void __launch_bounds__(kWarpsPerCta * 32) count_newlines_kernel(const uint8_t* __restrict__ bytes, long long nbytes,
-                                                                            uint32_t* __restrict__ seg_counts, int seg0, int nseg) {
+                                                                            uint32_t* __restrict__ seg_counts, int seg0, int nseg, uint32_t pat) {
     const int seg = seg0 + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (seg >= nseg) return;
     const uint32_t lane = threadIdx.x & 31u;
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) count_newlines_kernel(const
         const long long pos = base + row * 512 + lane * 16;
         if (pos < nbytes) {
             const uint4 v = *reinterpret_cast<const uint4*>(bytes + pos);
-            cnt += __popc(nl_flags(v.x)) + __popc(nl_flags(v.y)) + __popc(nl_flags(v.z)) + __popc(nl_flags(v.w));
+            cnt += __popc(nl_flags(v.x, pat)) + __popc(nl_flags(v.y, pat)) + __popc(nl_flags(v.z, pat)) + __popc(nl_flags(v.w, pat));
         }
     }
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) count_newlines_kernel(const
 __global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restrict__ seg_counts, int seg0, int seg1, uint32_t* __restrict__ run,
                                                              int32_t* __restrict__ cum_out, int is_last, const uint8_t* __restrict__ bytes,
                                                              long long nbytes, int32_t* __restrict__ offsets, int32_t* __restrict__ n_lines,
-                                                             int max_lines) {
+                                                             int max_lines, uint32_t delim) {
     __shared__ uint32_t part[1024];
     const int t = threadIdx.x;
     const int nseg = seg1 - seg0;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restric
         *cum_out = over ? -1 : (int32_t)newlines;
         if (seg0 == 0) offsets[0] = 0;
         if (is_last) {
-            const bool tail = nbytes > 0 && bytes[nbytes - 1] != '\n';  // BufRead::lines yields an unterminated last line
+            const bool tail = nbytes > 0 && bytes[nbytes - 1] != delim;  // BufRead::lines / split yield an unterminated last record
             const long long n = (long long)newlines + (tail ? 1 : 0);
             *n_lines = (over || n > max_lines) ? -1 : (int32_t)n;
             if (!over && n <= max_lines && tail) offsets[n] = (int32_t)nbytes;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint32_t* __restric
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_offsets_kernel(const uint8_t* __restrict__ bytes, long long nbytes,
                                                                           const uint32_t* __restrict__ seg_base, int seg0, int nseg,
-                                                                          int32_t* __restrict__ offsets, int max_lines) {
+                                                                          int32_t* __restrict__ offsets, int max_lines, uint32_t pat) {
     const int seg = seg0 + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (seg >= nseg) return;
     const uint32_t lane = threadIdx.x & 31u;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_offsets_kernel(const u
         uint32_t z[4] = {0u, 0u, 0u, 0u};
         if (pos < nbytes) {
             const uint4 v = *reinterpret_cast<const uint4*>(bytes + pos);
-            z[0] = nl_flags(v.x); z[1] = nl_flags(v.y); z[2] = nl_flags(v.z); z[3] = nl_flags(v.w);
+            z[0] = nl_flags(v.x, pat); z[1] = nl_flags(v.y, pat); z[2] = nl_flags(v.z, pat); z[3] = nl_flags(v.w, pat);
         }
         const uint32_t c = __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
         uint32_t inc = c;  // inclusive warp scan
@@ -199,13 +202,14 @@ __global__ void __launch_bounds__(256) validate_utf8_kernel(const uint8_t* __res
 // [0, c1) are resident.  `d_run` carries the newline count across chunks, d_cum[k] receives the count after this chunk.
 cudaError_t launch_split_chunk(const uint8_t* d_bytes, long long nbytes, long long c0, long long c1, int is_last, uint32_t* d_seg,
                                uint32_t* d_run, int32_t* d_cum_k, int32_t* d_offsets, int32_t* d_n_lines, int max_lines,
-                               uint8_t* d_invalid, cudaStream_t stream) {
+                               uint8_t* d_invalid, int delim, cudaStream_t stream) {
+    const uint32_t pat = (uint32_t)(delim & 0xFF) * 0x01010101u;
     const int seg0 = (int)(c0 / kSegBytes), seg1 = (int)((c1 + kSegBytes - 1) / kSegBytes);
     const int grid = (seg1 - seg0 + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (seg1 > seg0) count_newlines_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1);
-    scan_segments_kernel<<<1, 1024, 0, stream>>>(d_seg, seg0, seg1, d_run, d_cum_k, is_last, d_bytes, nbytes, d_offsets, d_n_lines, max_lines);
+    if (seg1 > seg0) count_newlines_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1, pat);
+    scan_segments_kernel<<<1, 1024, 0, stream>>>(d_seg, seg0, seg1, d_run, d_cum_k, is_last, d_bytes, nbytes, d_offsets, d_n_lines, max_lines, (uint32_t)(delim & 0xFF));
     if (seg1 > seg0) {
-        fill_offsets_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1, d_offsets, max_lines);
+        fill_offsets_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(d_bytes, nbytes < c1 ? nbytes : c1, d_seg, seg0, seg1, d_offsets, max_lines, pat);
         // validated window lags 16 bytes behind the resident bytes (sequences read up to 3 bytes ahead), except at the end
         const long long v0 = c0 >= 16 ? c0 - 16 : 0, v1 = is_last ? ((nbytes + 15) & ~15LL) : c1 - 16;
         if (v1 > v0) {

@@ -248,15 +248,19 @@ DecodeResult CudaBatchDecoder::materialize(const fg_batch_out& out, const uint8_
     return materialize_line(out, bytes, offsets[i], offsets[i + 1], i, side_effects);
 }
 
-void CudaBatchDecoder::split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
-    const int rc = fg_split_decode(ctx_, fmt_, stream, nbytes, out);
+void CudaBatchDecoder::split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out, fg_framing framing) {
+    const int rc = fg_split_decode_framed(ctx_, fmt_, framing, stream, nbytes, out);
     if (rc != FG_OK) throw std::runtime_error(std::string("fg_split_decode: ") + fg_last_error(ctx_));
 }
 
 // extent of line i of a split-mode result without its "\n" / "\r\n" terminator (BufRead::lines)
-static void split_extent(const fg_batch_out& out, const uint8_t* stream, int32_t i, int32_t& lo, int32_t& hi) {
+static void split_extent(const fg_batch_out& out, const uint8_t* stream, int32_t i, int32_t& lo, int32_t& hi, fg_framing framing) {
     lo = out.line_offsets[i];
     hi = out.line_offsets[i + 1];
+    if (framing == FG_FRAME_NUL) {  // BufRead::split(0): only the NUL goes
+        if (hi > lo && stream[hi - 1] == 0) --hi;
+        return;
+    }
     if (hi > lo && stream[hi - 1] == '\n') {
         --hi;
         if (hi > lo && stream[hi - 1] == '\r') --hi;
@@ -454,56 +458,55 @@ DecodeResult CudaDecoder::decode(std::string_view line) const {
 std::unique_ptr<Decoder> CudaDecoder::clone_boxed() const { return std::unique_ptr<Decoder>(new CudaDecoder(impl_)); }
 
 // ---------------------------------------------------------------------------
-// BatchingLineSplitter
+// RecordBatcher + the batching splitters
 // ---------------------------------------------------------------------------
-void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx,
-                               const Decoder& decoder, const Encoder& encoder, std::ostream& err_out,
-                               std::ostream& std_out) const {
-    std::shared_ptr<CudaBatchDecoder> gpu = decoder.batch();
-    const CudaGelfEncoder* fused = dynamic_cast<const CudaGelfEncoder*>(&encoder);
+RecordBatcher::RecordBatcher(const Decoder& decoder, const Encoder& encoder, std::function<void(std::vector<uint8_t>&&)> tx,
+                             std::ostream& err_out, std::ostream& std_out, Limits lim, bool quiet_blank)
+    : gpu_(decoder.batch()), encoder_(encoder), fused_(dynamic_cast<const CudaGelfEncoder*>(&encoder)), tx_(std::move(tx)),
+      err_(err_out), out_(std_out), quiet_blank_(quiet_blank) {
     // a batch never exceeds what the context can take (Limits used to be independent of DeviceOptions)
-    const int64_t max_bytes = std::min<int64_t>(lim_.max_bytes, gpu->capacity_bytes());
-    const int32_t max_lines = std::min<int32_t>(lim_.max_lines, gpu->capacity_lines());
-    std::vector<uint8_t> arena;
-    std::vector<int32_t> offsets{0};
-    std::vector<int32_t> invalid_before{0};  // "Invalid UTF-8 input" events, kept in stream order relative to the lines
-    arena.reserve((size_t)max_bytes);
-    auto flush_on = [&](CudaBatchDecoder* gpu) {
-        const int32_t n = (int32_t)offsets.size() - 1;
-        if (n == 0) {
-            for (int32_t k = 0; k < invalid_before[0]; ++k) err_out << "Invalid UTF-8 input\n";
-            invalid_before.assign(1, 0);
-            return;
-        }
-        fg_batch_out out;
-        const uint8_t dummy = 0;
-        const uint8_t* bytes = arena.empty() ? &dummy : arena.data();
-        std::lock_guard<std::mutex> guard(gpu->mutex());  // held until every Record of the batch has been materialised
-        if (fused != nullptr && gpu->format() == FG_FMT_RFC5424) {
-            // decode + encode on the device (line_splitter.rs:50-52 fused): only the encoded records come back
-            fg_encoded_out eo;
-            gpu->decode_encode_gelf(bytes, offsets.data(), n, fused->extra(), &eo);
-            for (int32_t i = 0; i < n; ++i) {
-                for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";
-                if (eo.status[i] == 0) {
-                    tx(std::vector<uint8_t>(eo.bytes + eo.offsets[i], eo.bytes + eo.offsets[i + 1]));
-                } else {
-                    std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
-                    err_out << fg_error_string(gpu->format(), eo.status[i]) << ": [" << rust_trim(line) << "]\n";
-                }
-            }
-            for (int32_t k = 0; k < invalid_before[(size_t)n]; ++k) err_out << "Invalid UTF-8 input\n";
-            arena.clear();
-            offsets.assign(1, 0);
-            invalid_before.assign(1, 0);
-            return;
-        }
-        gpu->decode_batch(bytes, offsets.data(), n, &out);
+    max_bytes_ = std::min<int64_t>(lim.max_bytes, gpu_->capacity_bytes());
+    max_lines_ = std::min<int32_t>(lim.max_lines, gpu_->capacity_lines());
+    arena_.reserve((size_t)max_bytes_);
+}
+
+void RecordBatcher::report(const char* e, std::string_view line) {
+    const std::string_view t = rust_trim(line);
+    if (quiet_blank_ && t.empty()) return;  // nul_splitter.rs:41-45
+    err_ << e << ": [" << t << "]\n";       // line_splitter.rs:37-39, nul_splitter.rs:43, syslen_splitter.rs:37
+}
+
+void RecordBatcher::flush_on(CudaBatchDecoder* gpu) {
+    const int32_t n = (int32_t)offsets_.size() - 1;
+    auto invalid = [&](int32_t i) {
+        for (int32_t k = 0; k < invalid_before_[(size_t)i]; ++k) err_ << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
+    };
+    if (n == 0) {
+        invalid(0);
+        invalid_before_.assign(1, 0);
+        return;
+    }
+    const uint8_t dummy = 0;
+    const uint8_t* bytes = arena_.empty() ? &dummy : arena_.data();
+    std::lock_guard<std::mutex> guard(gpu->mutex());  // held until every Record of the batch has been materialised
+    if (fused_ != nullptr && gpu->format() == FG_FMT_RFC5424) {
+        // decode + encode on the device (line_splitter.rs:50-52 fused): only the encoded records come back
+        fg_encoded_out eo;
+        gpu->decode_encode_gelf(bytes, offsets_.data(), n, fused_->extra(), &eo);
         for (int32_t i = 0; i < n; ++i) {
-            for (int32_t k = 0; k < invalid_before[(size_t)i]; ++k) err_out << "Invalid UTF-8 input\n";  // line_splitter.rs:22-25
+            invalid(i);
+            if (eo.status[i] == 0) tx_(std::vector<uint8_t>(eo.bytes + eo.offsets[i], eo.bytes + eo.offsets[i + 1]));
+            else report(fg_error_string(gpu->format(), eo.status[i]),
+                        std::string_view((const char*)bytes + offsets_[(size_t)i], (size_t)(offsets_[(size_t)i + 1] - offsets_[(size_t)i])));
+        }
+    } else {
+        fg_batch_out out;
+        gpu->decode_batch(bytes, offsets_.data(), n, &out);
+        for (int32_t i = 0; i < n; ++i) {
+            invalid(i);
             std::vector<std::string> fx;
-            DecodeResult r = gpu->materialize(out, bytes, offsets.data(), i, &fx);
-            for (const auto& s : fx) std_out << s << "\n";
+            DecodeResult r = gpu->materialize(out, bytes, offsets_.data(), i, &fx);
+            for (const auto& s : fx) out_ << s << "\n";
             const char* e = r.err;
             if (!e) {
                 if (FG_META_FLAGS(row_meta(out, i)) & FG_FLAG_TS_MISSING) {
@@ -512,46 +515,113 @@ void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::v
                     r.record.ts = (double)tsn.tv_sec + (double)tsn.tv_nsec / 1e9;
                 }
                 std::vector<uint8_t> enc;
-                if (encoder.encode(std::move(r.record), enc, &e)) {
-                    tx(std::move(enc));
+                if (encoder_.encode(std::move(r.record), enc, &e)) {
+                    tx_(std::move(enc));
                     continue;
                 }
             }
-            std::string_view line((const char*)bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
-            err_out << e << ": [" << rust_trim(line) << "]\n";  // line_splitter.rs:37-39
+            report(e, std::string_view((const char*)bytes + offsets_[(size_t)i], (size_t)(offsets_[(size_t)i + 1] - offsets_[(size_t)i])));
         }
-        for (int32_t k = 0; k < invalid_before[(size_t)n]; ++k) err_out << "Invalid UTF-8 input\n";
-        arena.clear();
-        offsets.assign(1, 0);
-        invalid_before.assign(1, 0);
-    };
-    auto flush = [&]() { flush_on(gpu.get()); };
+    }
+    invalid(n);
+    arena_.clear();
+    offsets_.assign(1, 0);
+    invalid_before_.assign(1, 0);
+}
+
+void RecordBatcher::push(std::string_view line) {
+    if ((int64_t)line.size() > max_bytes_) {
+        // One record larger than a whole batch: the reference's splitters take records of any length, and there is no CPU
+        // decoder to fall back on, so the record gets a context of its own, sized for it (rare, slow, correct).
+        flush();
+        std::unique_ptr<CudaBatchDecoder> big = gpu_->make_sized((int64_t)line.size() + 4096, 64);
+        arena_.insert(arena_.end(), line.begin(), line.end());
+        offsets_.push_back((int32_t)arena_.size());
+        invalid_before_.push_back(0);
+        flush_on(big.get());
+        return;
+    }
+    if ((int64_t)(arena_.size() + line.size()) > max_bytes_ || (int32_t)offsets_.size() - 1 >= max_lines_) flush();
+    arena_.insert(arena_.end(), line.begin(), line.end());
+    offsets_.push_back((int32_t)arena_.size());
+    invalid_before_.push_back(0);
+}
+
+void BatchingLineSplitter::run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx,
+                               const Decoder& decoder, const Encoder& encoder, std::ostream& err_out,
+                               std::ostream& std_out) const {
+    RecordBatcher batch(decoder, encoder, tx, err_out, std_out, RecordBatcher::Limits{lim_.max_lines, lim_.max_bytes});
     std::string line;
     while (std::getline(in, line)) {
         // BufRead::lines: the '\n' is gone; a '\r' is stripped only when it preceded a '\n'
         if (!in.eof() && !line.empty() && line.back() == '\r') line.pop_back();
-        if (!is_valid_utf8((const uint8_t*)line.data(), line.size())) {
-            ++invalid_before.back();  // printed in stream order when the batch is flushed
-            continue;
-        }
-        if ((int64_t)line.size() > max_bytes) {
-            // One line larger than a whole batch: the reference's LineSplitter takes lines of any length, and there is no
-            // CPU decoder to fall back on, so the line gets a context of its own, sized for it (rare, slow, correct).
-            flush();
-            std::unique_ptr<CudaBatchDecoder> big = gpu->make_sized((int64_t)line.size() + 4096, 64);
-            arena.insert(arena.end(), line.begin(), line.end());
-            offsets.push_back((int32_t)arena.size());
-            invalid_before.push_back(0);
-            flush_on(big.get());
-            continue;
-        }
-        if ((int64_t)(arena.size() + line.size()) > max_bytes || (int32_t)offsets.size() - 1 >= max_lines)
-            flush();
-        arena.insert(arena.end(), line.begin(), line.end());
-        offsets.push_back((int32_t)arena.size());
-        invalid_before.push_back(0);
+        if (!is_valid_utf8((const uint8_t*)line.data(), line.size())) batch.invalid_utf8();  // printed in stream order at the flush
+        else batch.push(line);
     }
-    flush();
+    batch.flush();
+}
+
+// splitter/nul_splitter.rs:18-47: records end at a NUL byte; the message for a rejected record is suppressed when the record is blank
+void BatchingNulSplitter::run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx, const Decoder& decoder,
+                              const Encoder& encoder, std::ostream& err_out, std::ostream& std_out) const {
+    RecordBatcher batch(decoder, encoder, tx, err_out, std_out, RecordBatcher::Limits{lim_.max_lines, lim_.max_bytes}, true);
+    std::string rec;
+    while (std::getline(in, rec, '\0')) {
+        if (!is_valid_utf8((const uint8_t*)rec.data(), rec.size())) batch.invalid_utf8();
+        else batch.push(rec);
+    }
+    batch.flush();
+}
+
+// splitter/syslen_splitter.rs:17-57: octet-counted framing "<len> <record>"; the chain of lengths is sequential by nature, so
+// the host walks it and the records of a batch are decoded together
+void BatchingSyslenSplitter::run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx, const Decoder& decoder,
+                                 const Encoder& encoder, std::ostream& err_out, std::ostream& std_out) const {
+    RecordBatcher batch(decoder, encoder, tx, err_out, std_out, RecordBatcher::Limits{lim_.max_lines, lim_.max_bytes});
+    std::string rec;
+    for (;;) {
+        // read_msglen :42-57: bytes up to and including the first ' '; fewer than two => "Connection closed"
+        std::string num;
+        int ch;
+        size_t got = 0;
+        while ((ch = in.get()) != std::char_traits<char>::eof()) {
+            ++got;
+            if (ch == ' ') break;
+            num.push_back((char)ch);
+        }
+        bool ok = got >= 2 && ch == ' ';
+        if (got >= 2 && ch != ' ') ok = true, num.pop_back();  // read_until at EOF: the last byte plays the delimiter's role (:49)
+        uint64_t len = 0;
+        if (ok) {
+            // usize::from_str: [+]digit+
+            size_t k = 0;
+            if (k < num.size() && num[k] == '+') ++k;
+            ok = k < num.size();
+            for (; ok && k < num.size(); ++k) {
+                if (num[k] < '0' || num[k] > '9' || len > (UINT64_MAX - 9) / 10) ok = false;
+                else len = len * 10 + (uint64_t)(num[k] - '0');
+            }
+        }
+        if (!ok) {
+            batch.flush();
+            err_out << "Can't read message's length\n";  // :23
+            return;
+        }
+        rec.resize((size_t)len);
+        in.read(rec.data(), (std::streamsize)len);
+        if ((uint64_t)in.gcount() != len) {
+            batch.flush();
+            err_out << "failed to fill whole buffer\n";  // read_exact's io::Error text (:27-30)
+            return;
+        }
+        if (!is_valid_utf8((const uint8_t*)rec.data(), rec.size())) {
+            // the reference unwraps String::from_utf8 here and panics (:32); the batching twin stops the stream the same way
+            batch.flush();
+            err_out << "Invalid UTF-8 input\n";
+            return;
+        }
+        batch.push(rec);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -826,12 +896,12 @@ double fgh_materialize_bench(void* d, const fg_batch_out* out, const uint8_t* by
 }
 
 // fg_split_decode + canonical dumps of every line (split-mode twin of fgh_dump_out); also returns the line offsets
-int fgh_split_dump(void* d, const uint8_t* stream, int64_t nbytes, uint8_t** out_buf, int64_t** out_offsets, int32_t** out_line_offsets,
+int fgh_split_dump(void* d, int framing, const uint8_t* stream, int64_t nbytes, uint8_t** out_buf, int64_t** out_offsets, int32_t** out_line_offsets,
                    int32_t* out_n, float* kernel_ms, char* errbuf, int errlen) {
     auto* dec = (CudaBatchDecoder*)d;
     try {
         fg_batch_out out;
-        dec->split_decode(stream, nbytes, &out);
+        dec->split_decode(stream, nbytes, &out, (fg_framing)framing);
         const int32_t n = out.n;
         std::string all;
         int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
@@ -840,7 +910,7 @@ int fgh_split_dump(void* d, const uint8_t* stream, int64_t nbytes, uint8_t** out
         std::vector<std::string> fx;
         for (int32_t i = 0; i < n; ++i) {
             int32_t lo, hi;
-            split_extent(out, stream, i, lo, hi);
+            split_extent(out, stream, i, lo, hi, (fg_framing)framing);
             fx.clear();
             DecodeResult r = dec->materialize_line(out, stream, lo, hi, i, &fx);
             const bool now = r.ok() && (FG_META_FLAGS(row_meta(out, i)) & FG_FLAG_TS_MISSING);
@@ -986,7 +1056,7 @@ int fgh_multi_decode_dump(int fmt, const int* devices, int ndev, int64_t max_byt
 
 // BatchingLineSplitter twin of LineSplitter::run for tests: text in, one canonical dump line per record out
 // (encoder = the parity dump), stderr/stdout text of the reference captured.
-int fgh_splitter_run(void* d, const uint8_t* text, int64_t len, int32_t max_lines, int64_t max_bytes, uint8_t** out_records,
+int fgh_splitter_run(void* d, int framing, const uint8_t* text, int64_t len, int32_t max_lines, int64_t max_bytes, uint8_t** out_records,
                      int64_t* out_records_len, uint8_t** out_stderr, int64_t* out_stderr_len, uint8_t** out_stdout,
                      int64_t* out_stdout_len) {
     struct DumpEncoder : Encoder {
@@ -1009,14 +1079,16 @@ int fgh_splitter_run(void* d, const uint8_t* text, int64_t len, int32_t max_line
     BatchingLineSplitter::Limits lim;
     lim.max_lines = max_lines;
     lim.max_bytes = max_bytes;
-    BatchingLineSplitter sp(lim);
     std::string in((const char*)text, (size_t)len);
     std::istringstream is(in);
     std::ostringstream es, os;
     std::string records;
     DumpEncoder enc;
     try {
-        sp.run(is, [&](std::vector<uint8_t>&& v) { records.append(v.begin(), v.end()); records.push_back('\n'); }, dec, enc, es, os);
+        auto tx = [&](std::vector<uint8_t>&& v) { records.append(v.begin(), v.end()); records.push_back('\n'); };
+        if (framing == 1) BatchingNulSplitter(lim).run(is, tx, dec, enc, es, os);        // input.framing = "nul"
+        else if (framing == 2) BatchingSyslenSplitter(lim).run(is, tx, dec, enc, es, os);  // input.framing = "syslen"
+        else BatchingLineSplitter(lim).run(is, tx, dec, enc, es, os);                      // input.framing = "line"
     } catch (const std::exception&) {
         return -1;
     }

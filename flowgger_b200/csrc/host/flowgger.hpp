@@ -108,7 +108,7 @@ class CudaBatchDecoder {
     DecodeResult materialize_line(const fg_batch_out& out, const uint8_t* bytes, int32_t line_lo, int32_t line_hi, int32_t i,
                                   std::vector<std::string>* side_effects = nullptr) const;
     // framing + UTF-8 validation + decode of a raw byte stream on the device (fg_split_decode)
-    void split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
+    void split_decode(const uint8_t* stream, int64_t nbytes, fg_batch_out* out, fg_framing framing = FG_FRAME_LINE);
     // decode + GelfEncoder::encode fused on the device (fg_decode_encode_gelf); `extra` = output.gelf_extra
     void decode_encode_gelf(const uint8_t* bytes, const int32_t* offsets, int32_t n,
                             const std::vector<std::pair<std::string, std::string>>& extra, fg_encoded_out* out);
@@ -179,10 +179,45 @@ class CudaGelfEncoder : public Encoder {
     std::vector<std::pair<std::string, std::string>> extra_;
 };
 
+// The batching twin of the reference's per-record call sites (`decode -> encode -> tx.send`, or print
+// "{err}: [{line.trim()}]" to stderr): line_splitter.rs:50, nul_splitter.rs:57, syslen_splitter.rs:65,
+// input/udp_input.rs:139, input/redis_input.rs:159, input/file/worker.rs:116.  A caller frames its records as the old
+// code did and push()es each one; the batcher accumulates up to Limits, decodes the batch on the GPU in one call and then,
+// in the original order, encodes + sends every Record or prints the identical stderr line.  With a CudaGelfEncoder and an
+// RFC5424 decoder the two stages run fused on the device (fg_decode_encode_gelf).
+class CudaGelfEncoder;
+class RecordBatcher {
+   public:
+    struct Limits {
+        int32_t max_lines = 1 << 16;
+        int64_t max_bytes = 16 << 20;
+    };
+    RecordBatcher(const Decoder& decoder, const Encoder& encoder, std::function<void(std::vector<uint8_t>&&)> tx,
+                  std::ostream& err_out, std::ostream& std_out, Limits lim, bool quiet_blank = false);
+    void push(std::string_view record);        // one framed record (valid UTF-8)
+    void invalid_utf8() { ++invalid_before_.back(); }  // a record that failed the UTF-8 check: reported in stream order
+    void flush() { flush_on(gpu_.get()); }     // call on max_lines / max_bytes (automatic), input-idle timeout and EOF
+
+   private:
+    void flush_on(CudaBatchDecoder* gpu);
+    void report(const char* err, std::string_view line);
+    std::shared_ptr<CudaBatchDecoder> gpu_;
+    const Encoder& encoder_;
+    const CudaGelfEncoder* fused_;
+    std::function<void(std::vector<uint8_t>&&)> tx_;
+    std::ostream& err_;
+    std::ostream& out_;
+    bool quiet_blank_;
+    int64_t max_bytes_;
+    int32_t max_lines_;
+    std::vector<uint8_t> arena_;
+    std::vector<int32_t> offsets_{0};
+    std::vector<int32_t> invalid_before_{0};  // "Invalid UTF-8 input" events, kept in stream order relative to the records
+};
+
 // Batched twin of LineSplitter::run (splitter/line_splitter.rs:10-54): reads lines like
 // BufRead::lines (strip "\n" and one "\r"; invalid UTF-8 => "Invalid UTF-8 input" on stderr,
-// line skipped), accumulates up to max_lines/max_bytes, decodes the batch on the GPU, then in
-// the original order encodes + sends each Record, or prints "{err}: [{line.trim()}]" to stderr.
+// line skipped) and feeds a RecordBatcher.
 class BatchingLineSplitter {
    public:
     struct Limits {
@@ -197,6 +232,27 @@ class BatchingLineSplitter {
 
    private:
     Limits lim_;
+};
+// Batched twins of NulSplitter::run (splitter/nul_splitter.rs:10-47) and SyslenSplitter::run (syslen_splitter.rs:10-57)
+class BatchingNulSplitter {
+   public:
+    BatchingNulSplitter() = default;
+    explicit BatchingNulSplitter(BatchingLineSplitter::Limits l) : lim_(l) {}
+    void run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx, const Decoder& decoder,
+             const Encoder& encoder, std::ostream& err_out, std::ostream& std_out) const;
+
+   private:
+    BatchingLineSplitter::Limits lim_;
+};
+class BatchingSyslenSplitter {
+   public:
+    BatchingSyslenSplitter() = default;
+    explicit BatchingSyslenSplitter(BatchingLineSplitter::Limits l) : lim_(l) {}
+    void run(std::istream& in, const std::function<void(std::vector<uint8_t>&&)>& tx, const Decoder& decoder,
+             const Encoder& encoder, std::ostream& err_out, std::ostream& std_out) const;
+
+   private:
+    BatchingLineSplitter::Limits lim_;
 };
 
 // §8(e): lines are independent, so a batch shards across GPUs by contiguous line ranges balanced by BYTES

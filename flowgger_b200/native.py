@@ -118,7 +118,7 @@ def load_host() -> C.CDLL:
         L.fgh_materialize_bench.restype = C.c_double
         L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
         L.fgh_is_valid_utf8.argtypes = [C.c_void_p, C.c_int64]
-        L.fgh_split_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+        L.fgh_split_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_char_p, C.c_int]
         L.fgh_shard_by_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
         L.fgh_multi_decode_dump.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
@@ -127,7 +127,7 @@ def load_host() -> C.CDLL:
                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
         L.fgh_splitter_run_gelf.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64, C.c_int, C.POINTER(C.c_char_p),
                                             C.POINTER(C.c_char_p)] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 2
-        L.fgh_splitter_run.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int64] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 3
+        L.fgh_splitter_run.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int64, C.c_int32, C.c_int64] + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)] * 3
         _host = L
     return _host
 
@@ -385,13 +385,14 @@ class BatchDecoder:
             self.H.fgh_free(po)
         return buf, offs
 
-    def split_dump(self, stream: np.ndarray) -> tuple[bytes, np.ndarray, np.ndarray, float]:
-        """fg_split_decode on a raw byte stream: (canonical dumps, dump offsets, line offsets int32[n+1], kernel ms)."""
+    def split_dump(self, stream: np.ndarray, framing: int = 0) -> tuple[bytes, np.ndarray, np.ndarray, float]:
+        """fg_split_decode_framed on a raw byte stream (framing 0 = "line", 1 = "nul"): (canonical dumps, dump offsets,
+        record offsets int32[n+1], kernel ms)."""
         assert stream.dtype == np.uint8
         pb, po, pl = C.c_void_p(), C.c_void_p(), C.c_void_p()
         n, ms = C.c_int32(), C.c_float()
         err = C.create_string_buffer(512)
-        rc = self.H.fgh_split_dump(self._h, _ptr(stream), len(stream), C.byref(pb), C.byref(po), C.byref(pl), C.byref(n), C.byref(ms), err, 512)
+        rc = self.H.fgh_split_dump(self._h, framing, _ptr(stream), len(stream), C.byref(pb), C.byref(po), C.byref(pl), C.byref(n), C.byref(ms), err, 512)
         if rc != 0:
             raise RuntimeError(err.value.decode())
         try:
@@ -491,15 +492,17 @@ def splitter_run_gelf(dec: "BatchDecoder", text: bytes, extra: dict[str, str] | 
     return tuple(out)
 
 
-def splitter_run(dec: "BatchDecoder", text: bytes, max_lines: int = 1 << 16, max_bytes: int = 16 << 20) -> tuple[bytes, bytes, bytes]:
-    """BatchingLineSplitter over `text` (the stdin of config #1): returns (records, stderr, stdout)."""
+def splitter_run(dec: "BatchDecoder", text: bytes, max_lines: int = 1 << 16, max_bytes: int = 16 << 20,
+                 framing: int = 0) -> tuple[bytes, bytes, bytes]:
+    """Batching splitter over `text` (the stdin of config #1); framing 0 = "line", 1 = "nul", 2 = "syslen" (input.framing):
+    returns (records, stderr, stdout)."""
     H = load_host()
     ps = [C.c_void_p() for _ in range(3)]
     ns = [C.c_int64() for _ in range(3)]
     args = []
     for p, n in zip(ps, ns):
         args += [C.byref(p), C.byref(n)]
-    rc = H.fgh_splitter_run(dec._h, text, len(text), max_lines, max_bytes, *args)
+    rc = H.fgh_splitter_run(dec._h, framing, text, len(text), max_lines, max_bytes, *args)
     if rc != 0:
         raise RuntimeError("splitter failed")
     out = []

@@ -209,6 +209,11 @@ int fg_decode_batch(fg_ctx* ctx, fg_format fmt, const uint8_t* bytes, const int3
  * line gets status fg_error_string() == "Invalid UTF-8 input" and is not decoded) and decodes the rest.
  * Spans index `stream`; out->line_offsets locates the lines. */
 int fg_split_decode(fg_ctx* ctx, fg_format fmt, const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
+/* The same with the framing of input.framing (mod.rs: "line" | "nul"): FG_FRAME_NUL is NulSplitter::run
+ * (splitter/nul_splitter.rs:18-40): records end at a NUL byte, which is dropped (`BufRead::split(0)`), nothing else is
+ * stripped, an unterminated last record is still a record, invalid UTF-8 => "Invalid UTF-8 input". */
+typedef enum fg_framing { FG_FRAME_LINE = 0, FG_FRAME_NUL = 1 } fg_framing;
+int fg_split_decode_framed(fg_ctx* ctx, fg_format fmt, fg_framing framing, const uint8_t* stream, int64_t nbytes, fg_batch_out* out);
 
 /* Device-resident variant used for roofline measurement: fg_upload stages a
  * batch in HBM once; fg_parse_resident runs only the parse kernel(s) over it

@@ -31,3 +31,29 @@ def split_lines(stream: bytes) -> tuple[np.ndarray, list[bytes], list[bool]]:
         except UnicodeDecodeError:
             valid.append(False)
     return offs, lines, valid
+
+
+def split_nul(stream: bytes) -> tuple[np.ndarray, list[bytes], list[bool]]:
+    """NulSplitter::run (/root/reference/src/flowgger/splitter/nul_splitter.rs:18-40): `BufRead::split(0)` — records end at
+    a NUL byte, which is dropped; nothing else is stripped; an unterminated last record is still yielded; invalid UTF-8 =>
+    "Invalid UTF-8 input" and the record is skipped.  Same return shape as split_lines."""
+    if len(stream) == 0:
+        return np.zeros(1, np.int32), [], []
+    a = np.frombuffer(stream, dtype=np.uint8)
+    z = np.flatnonzero(a == 0)
+    starts = [0] + [int(p) + 1 for p in z]
+    if stream[-1] != 0:
+        starts.append(len(stream))
+    offs = np.asarray(starts, dtype=np.int32)
+    lines, valid = [], []
+    for i in range(len(offs) - 1):
+        l = stream[offs[i]:offs[i + 1]]
+        if l.endswith(b"\0"):
+            l = l[:-1]
+        lines.append(l)
+        try:
+            l.decode("utf-8")
+            valid.append(True)
+        except UnicodeDecodeError:
+            valid.append(False)
+    return offs, lines, valid

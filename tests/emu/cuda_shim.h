@@ -38,3 +38,6 @@ static inline int __any_sync(unsigned, int p) { return p; }
 static inline void __syncwarp() {}
 static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
 #define __grid_constant__
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }

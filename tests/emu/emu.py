@@ -33,8 +33,6 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(build()))
         _lib.emu5424_classify16.restype = C.c_uint32
         _lib.emu5424_classify16.argtypes = [C.c_void_p]
-        _lib.emu5424_classify16_v.restype = C.c_uint32
-        _lib.emu5424_classify16_v.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -42,12 +40,6 @@ def classify16(block: bytes) -> int:
     assert len(block) == 16
     buf = C.create_string_buffer(block, 16)
     return int(lib().emu5424_classify16(buf))
-
-
-def classify16_v(block: bytes) -> int:
-    assert len(block) == 16
-    buf = C.create_string_buffer(block, 16)
-    return int(lib().emu5424_classify16_v(buf))
 
 
 def decode_dump(native, data: np.ndarray, offsets: np.ndarray, tile_bytes: int = 13312, strip_eol: bool = False,

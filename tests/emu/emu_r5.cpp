@@ -59,19 +59,13 @@ uint32_t emu5424_classify16(const uint8_t* p) {
 // f64 -> text of the GELF encoder (fg_dtoa.cuh), for the CPU tests of the Grisu2 restatement
 int emu_json_f64(double v, uint8_t* out) { return fg::json_f64(v, out); }
 
-uint32_t emu5424_classify16_v(const uint8_t* p) {
-    uint32_t w[4];
-    memcpy(w, p, 16);
-    return fg::r5_classify16_v(w[0], w[1], w[2], w[3]);
-}
-
 int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int32_t tile_bytes, int32_t strip_eol,
                    const uint8_t* invalid, fg_batch_out* out) {
     Tables* T = new Tables();
     T->rows.resize((size_t)std::max(n, 1));
     const int64_t total_bytes = n > 0 ? offsets[n] : 0;
     std::vector<uint8_t> tile((size_t)tile_bytes + 64);
-    std::vector<uint32_t> bmI((size_t)tile_bytes / 32 + 8), bmV((size_t)tile_bytes / 32 + 8);
+    std::vector<uint32_t> bmI((size_t)tile_bytes / 32 + 8);
     for (int first = 0; first < n; first += kLines) {
         const int last = std::min(n, first + kLines);
         int cur = first;
@@ -88,13 +82,9 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
             const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
             for (uint32_t k = 0; k < nbytes; ++k) tile[k] = (int64_t)base + k < total_bytes ? bytes[base + k] : 0;  // the bulk copy
             uint16_t* bmI16 = (uint16_t*)bmI.data();
-            uint16_t* bmV16 = (uint16_t*)bmV.data();
             const int ngran = (int)(nbytes >> 4);
-            for (int g = 0; g < ngran; ++g) {
-                bmI16[g] = (uint16_t)emu5424_classify16(tile.data() + 16 * g);
-                bmV16[g] = (uint16_t)emu5424_classify16_v(tile.data() + 16 * g);
-            }
-            for (int k = 0; k < 6; ++k) bmI16[ngran + k] = bmV16[ngran + k] = 0;
+            for (int g = 0; g < ngran; ++g) bmI16[g] = (uint16_t)emu5424_classify16(tile.data() + 16 * g);
+            for (int k = 0; k < 6; ++k) bmI16[ngran + k] = 0;
             for (int tid = 0; tid < r; ++tid) {
                 const int i = cur + tid;
                 const int ls = offsets[i] - base;
@@ -109,7 +99,7 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
                 }
                 const bool too_long = le - ls > 65535;
                 fg::R5Fast res;
-                const bool regular = fg::r5_regular(tile.data(), bmI.data(), bmV.data(), ls, (too_long || bad) ? ls : le, res);
+                const bool regular = fg::r5_regular(tile.data(), bmI.data(), ls, (too_long || bad) ? ls : le, res);
                 if (bad) {
                     res.status = FG_ES_INVALID_UTF8;
                     res.n_entries = 0;
@@ -178,9 +168,9 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
                 const uint32_t off = (uint32_t)v, l = (uint32_t)(v >> 32);
                 const uint32_t ul = (uint32_t)fg::r5_unescape(bytes + off, (int)l, nullptr);
                 const size_t at = T->arena.size();
-                T->arena.resize(at + ul + 1);
+                T->arena.resize(at + ul + 2);
                 fg::r5_unescape(bytes + off, (int)l, T->arena.data() + at);
-                T->arena.resize(at + ul);
+                T->arena.resize(at + ((ul + 1) & ~(size_t)1));
                 T->wval[e] = (uint64_t)at | ((uint64_t)ul << 32);
                 T->wmeta[e] = 0x80u;
             }

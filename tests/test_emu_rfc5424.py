@@ -48,12 +48,6 @@ def test_stage1_classification_per_byte(emu):
     for b in range(256):
         if not want(b):
             assert 33 <= b <= 126 and b not in b'"=]'
-    # V is exactly '"' and '\\'
-    for b in range(256):
-        for pos in (0, 3, 4, 9, 15):
-            blk = bytearray(b"0123456789abcdef")
-            blk[pos] = b
-            assert emu.classify16_v(bytes(blk)) == ((1 << pos) if b in (0x22, 0x5C) else 0), (b, pos)
 
 
 def test_goldens_and_appendix(emu, native, oracle):

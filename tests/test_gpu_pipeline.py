@@ -119,3 +119,44 @@ def test_splitter_line_larger_than_a_batch(native, oracle):
     dumps = [buf[bo[i]:bo[i + 1]] for i in range(4)]
     assert records.split(b"\n")[:-1] == [x[:x.rindex(b";out=")] + b";out=0" for x in dumps[:3]]
     assert err == b"Unsupported BOM: [abc]\n"
+
+
+def _expected(oracle, lines, quiet_blank=False):
+    d, o = oracle.pack(lines)
+    buf, bo = oracle.decode_dump(0, d, o)
+    recs, errs = [], []
+    for i, l in enumerate(lines):
+        dump = buf[bo[i]:bo[i + 1]]
+        if dump.startswith(b"E:"):
+            t = l.decode().strip().encode()
+            if not (quiet_blank and not t):
+                errs.append(dump[2:dump.index(b";out=")] + b": [" + t + b"]")
+        else:
+            recs.append(dump[:dump.rindex(b";out=")] + b";out=0")
+    return recs, errs
+
+
+def test_nul_and_syslen_batching_splitters(native, oracle):
+    """Batching twins of NulSplitter (nul_splitter.rs:10-47: NUL-terminated records, no message for a blank rejected
+    record) and SyslenSplitter (syslen_splitter.rs:10-57: "<len> <record>", stream ends with "Can't read message's
+    length")."""
+    data, offs = native.generate(native.FMT_RFC5424, 5, 3000, bad_frac=0.02)
+    lines = [bytes(data[offs[i]:offs[i + 1]]) for i in range(3000)]
+    lines[10] = b""            # blank record: rejected ("Unsupported BOM") but not reported by the NUL splitter
+    lines[11] = b"   "
+    lines[12] = lines[12] + b"\r\n"  # '\r' / '\n' are ordinary bytes under NUL and syslen framing
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=8 << 20, max_batch_lines=1 << 12)
+    try:
+        recs, errs = _expected(oracle, lines, quiet_blank=True)
+        records, err, _ = native.splitter_run(dec, b"\0".join(lines) + b"\0", max_lines=700, framing=1)
+        assert records.split(b"\n")[:-1] == recs and err.split(b"\n")[:-1] == errs
+        # syslen: the newline inside record 12 must survive (records are split on b";out=0\n" here)
+        recs, errs = _expected(oracle, lines)
+        text = b"".join(b"%d %s" % (len(l), l) for l in lines)
+        records, err, _ = native.splitter_run(dec, text + b"12 short", max_lines=700, framing=2)
+        assert records.split(b"\n")[:-1] == recs
+        assert err.split(b"\n")[:-1] == errs + [b"failed to fill whole buffer"]
+        records, err, _ = native.splitter_run(dec, text + b"x1 abc", max_lines=700, framing=2)
+        assert err.split(b"\n")[:-1] == errs + [b"Can't read message's length"]
+    finally:
+        dec.close()

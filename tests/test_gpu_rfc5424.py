@@ -125,14 +125,15 @@ def test_roundtrip_property_full_msg(dec, native):
     span lies inside its own line; holds at any batch size without the oracle."""
     data, offs = native.generate(native.FMT_RFC5424, 3, 3_000_000, bad_frac=0.005)
     res = dec.decode(data, offs)
-    ok = res.status == 0
+    ok = (res.status == 0) & ((res.meta >> 24) & 0x80 == 0)  # compact rows (the few FG_FLAG_WIDE rows carry absolute spans)
+    assert int(ok.sum()) > 2_950_000
     lo, hi = offs[:-1][ok], offs[1:][ok]
     sp = res.spans5424(offs)
     for col in (sp["hostname"], sp["appname"], sp["procid"], sp["msgid"], sp["full_msg"]):
         o, l = col[ok, 0], col[ok, 1]
         assert (o >= lo).all() and (l >= 0).all() and (o + l <= hi).all()
     fo, fl = sp["full_msg"][ok, 0], sp["full_msg"][ok, 1]
-    assert ((fo == lo) | (fo == lo + 3)).all()
+    assert (fo == lo).all()
     m = sp["msg"][ok]
     has = m[:, 0] >= 0
     assert (m[has, 0] + m[has, 1] <= fo[has] + fl[has]).all()

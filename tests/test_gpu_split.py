@@ -8,11 +8,11 @@ import vectors as V
 pytestmark = pytest.mark.gpu
 
 
-def check(dec, oracle, fmt, stream: bytes):
+def check(dec, oracle, fmt, stream: bytes, framing: int = 0):
     import pysplit
-    offs, lines, valid = pysplit.split_lines(stream)
+    offs, lines, valid = (pysplit.split_nul if framing else pysplit.split_lines)(stream)
     arr = np.frombuffer(stream or b"\0", dtype=np.uint8).copy()[: len(stream)]
-    buf, bo, line_offs, _ = dec.split_dump(arr if len(stream) else np.zeros(0, np.uint8))
+    buf, bo, line_offs, _ = dec.split_dump(arr if len(stream) else np.zeros(0, np.uint8), framing)
     assert np.array_equal(line_offs, offs), (line_offs[:10], offs[:10])
     good = [l for l, v in zip(lines, valid) if v]
     d, o = oracle.pack(good)
@@ -104,5 +104,21 @@ def test_multi_chunk_stream_and_chunk_boundaries(native, oracle):
             # every other line is valid
             bad = [j for j in range(len(lines)) if buf[bo[j]:bo[j] + 2] != b"R:"]
             assert bad == ([] if valid[idx] else [idx])
+    finally:
+        dec.close()
+
+
+def test_nul_framing(native, oracle):
+    """input.framing = "nul" (NulSplitter, nul_splitter.rs:18-40) on the device: records end at a NUL byte; '\\n' and
+    '\\r' are ordinary bytes of the record."""
+    dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=64 << 20, max_batch_lines=1 << 18)
+    try:
+        g = V.G1_LINE.encode()
+        for stream in [b"", b"\0", b"\0\0", g, g + b"\0", g + b"\r\n\0", g + b"\0" + g, g + b"\0\0" + g + b"\0", b"\xff\0" + g + b"\0",
+                       g + b"\0\xc3", g + b"\n" + g + b"\0", b"a" * 20000 + b"\0" + g + b"\0" + b"b" * 9000]:
+            check(dec, oracle, 0, stream, framing=1)
+        data, offs = native.generate(native.FMT_RFC5424, 23, 100_000)
+        stream = b"".join(bytes(data[offs[i]:offs[i + 1]]) + b"\0" for i in range(100_000))
+        check(dec, oracle, 0, stream, framing=1)
     finally:
         dec.close()
