@@ -336,6 +336,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split", action="store_true", help="also time fg_split_decode (device-side framing + UTF-8 validation, N1)")
     ap.add_argument("--ltsv-typed", action="store_true", help="LTSV with the 4-entry typed schema + suffixes (C4, second run)")
+    ap.add_argument("--encode", action="store_true", help="also time fg_decode_encode_gelf (decode + GELF encode fused on the device, N2)")
     args = ap.parse_args()
     if args.format == "mixed":
         if args.lines <= 0:
@@ -464,6 +465,24 @@ def main() -> None:
     e2e_record = {"value": total_lines / rec_wall, "unit": "lines/s", "materialize_s": mat_s,
                   "api": "fg_decode_batch + CudaBatchDecoder::materialize of every line (owned Record per line, host threads = cores / ranks)"}
 
+    # ---- optional: bytes in -> encoded GELF records out (decode + encode fused on the device, N2) ---------------------
+    encode = None
+    if args.encode and fmt == 0:
+        _, eo, es, ek = dec.decode_encode_gelf(h_bytes, h_offs, copy=False)  # warm-up (sizes the output buffer)
+        out_bytes = int(eo[-1])
+        barrier()
+        t0 = time.perf_counter()
+        ek = 0.0
+        for _ in range(args.e2e_steps):
+            _, eo, es, k1 = dec.decode_encode_gelf(h_bytes, h_offs, copy=False)
+            ek += k1
+        barrier()
+        ew = max_over_ranks(time.perf_counter() - t0)
+        encode = {"value": total_lines / (ew / args.e2e_steps), "unit": "lines/s", "h2d_bytes_per_step": b_read,
+                  "d2h_bytes_per_step": out_bytes + 9 * n + 8, "json_bytes_per_gpu": out_bytes,
+                  "kernel_ms_per_step": ek / args.e2e_steps, "records": int((np.asarray(es) == 0).sum()),
+                  "api": "fg_decode_encode_gelf (pinned host lines in, GELF JSON records + offsets + status out; the decoder's rows never leave the device)"}
+
     # ---- optional: raw newline-terminated stream, framing + UTF-8 validation on the device (N1) -------
     split = None
     if args.split:
@@ -545,6 +564,8 @@ def main() -> None:
             line["cpu_baseline"] = cpu
         if split is not None:
             line["split_e2e"] = split
+        if encode is not None:
+            line["encode_e2e"] = encode
         print(json.dumps(line), flush=True)
     dec.close()
     if dist is not None:

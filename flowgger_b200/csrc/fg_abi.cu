@@ -303,7 +303,10 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     // long-line formats: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
     if (fmt != FG_FMT_RFC5424 && mean > 256.0) return 0;
     const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
-    long t = (long)(mean * lines * 1.10) + gran;
+#ifndef FG_TILE_SLACK_PCT  // head room of the tile over the mean span of a CTA's lines (profiles/variants.sh tries others)
+#define FG_TILE_SLACK_PCT 110
+#endif
+    long t = (long)(mean * lines * (FG_TILE_SLACK_PCT / 100.0)) + gran;
     t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
     t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : c->max_tile));
@@ -361,7 +364,7 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
         P.strip_eol = strip_eol;
         FG_CUDA(c, cudaMemsetAsync(c->d_k + fg::K5_ESC_LIST, 0, 8, s));  // the two work lists are per launch
         FG_CUDA(c, fg::launch_parse5424(P, s));
-        c->launches += 3;
+        c->launches += 2;  // parse5424_kernel + post5424_kernel
         return FG_OK;
     }
     fg::ParseParams P;

@@ -249,7 +249,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
 
 const char* kernel_build_info() {
     return "flowgger_b200 parse kernels: sm_100a, RFC5424: structural bitmap + bit-walk over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse5424_kernel, unescape5424_kernel, wide5424_kernel, parse_kernel<ltsv>, parse_kernel<gelf>]";
+           "kernels=[parse5424_kernel, post5424_kernel, gelf_size_kernel, gelf_write_kernel, parse_kernel<ltsv>, parse_kernel<gelf>]";
 }
 
 }  // namespace fg

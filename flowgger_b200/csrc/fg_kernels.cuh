@@ -144,8 +144,14 @@ constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (ti
 constexpr int kGelfUnstagedCtasPerSm = 16;
 // RFC5424 (short lines, staged tile): 64-line CTAs at 14 per SM — same warps/SM, tile waits and barriers half as wide
 // (2.36 -> 2.31 ms per 10 M lines; 13 KB tile + 1.8 KB static + 1 KB reserved per CTA = 225 KB of the SM's 227 KB)
-constexpr int kRfc5424LinesPerCta = 64;
-constexpr int kRfc5424CtasPerSm = 14;
+#ifndef FG_R5_LINES  // profiles/variants.sh builds other shapes with -DFG_R5_LINES / -DFG_R5_MINB for A/B runs
+#define FG_R5_LINES 64
+#endif
+#ifndef FG_R5_MINB
+#define FG_R5_MINB 14
+#endif
+constexpr int kRfc5424LinesPerCta = FG_R5_LINES;
+constexpr int kRfc5424CtasPerSm = FG_R5_MINB;
 constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : kLinesPerCta; }
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);

@@ -6,13 +6,14 @@
 //                        32 of 32 lanes busy); (3) one thread per line walks its line hop by hop over the bitmap (stage 2,
 //                        lock step) and stages its side-table rows inside its own consumed bytes; (4) a CTA scan + ONE global
 //                        atomic place the rows, which are copied out with the 32-byte row of every line.
-//   unescape5424_kernel  the few lines (≈8 % at C2) whose SD values hold a backslash: unescape_sd_value
-//                        (rfc5424_decoder.rs:105-125) into the batch arena, one thread per listed line.
-//   wide5424_kernel      the SLOW path: every line the fast walker does not recognise as regular (malformed lines and
+//   post5424_kernel      one launch for the two device-side work lists:
+//     unescape_lines     the few lines (≈8 % at C2) whose SD values hold a backslash: unescape_sd_value
+//                        (rfc5424_decoder.rs:105-125) into the batch arena, one thread per listed line;
+//     wide_lines         the SLOW path: every line the fast walker does not recognise as regular (malformed lines and
 //                        their error strings, legal-but-unusual shapes, lines >= 64 KiB or longer than the tile, rows that
 //                        do not fit behind the cursor) goes through the exact scanner of fg_rfc5424.cuh straight from
 //                        global memory (≈0.6 % of the lines at C2).
-// The last two run over device-side work lists, so a batch needs no host round trip between the three launches.
+// The work lists live on the device, so a batch needs no host round trip between the two launches.
 #include "fg_kernels.cuh"
 
 #include "fg_common.cuh"
@@ -32,9 +33,8 @@ template <int LINES, int MINB>
 __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_constant__ Parse5424Params P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t scan_ws[33];
-    __shared__ uint32_t s_base[3];  // side-table base, escape-list base, wide-list base of this round
-    __shared__ uint32_t s_cnt[2];   // lines of this round on the escape list / wide list
+    __shared__ uint32_t scan_ws[2 * (LINES / 32)];  // per-warp totals of the two packed counters
+    __shared__ uint32_t s_base[3];                  // side-table base, escape-list base, wide-list base of this round
 
     const int tid = threadIdx.x;
     const uint32_t lane = (uint32_t)tid & 31u;
@@ -69,8 +69,6 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
             fence_proxy_async();  // generic-proxy accesses of the previous round happen-before this async write
             mbar_expect_tx(&mbar, nbytes);
             bulk_g2s(tile, P.bytes + base, nbytes, &mbar);
-            s_cnt[0] = 0;
-            s_cnt[1] = 0;
         }
         mbar_wait(&mbar, parity);
         parity ^= 1u;
@@ -111,28 +109,37 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         const uint32_t my_n = (active && !wide && res.status == FG_ST_OK) ? res.n_entries : 0u;
         const bool esc = my_n != 0u && res.esc;
 
-        // work lists: warp-aggregated shared-memory counters, resolved by the barriers of the scan below
-        const uint32_t be = __ballot_sync(0xFFFFFFFFu, esc), bw = __ballot_sync(0xFFFFFFFFu, wide);
-        uint32_t esc_at = 0, wide_at = 0;
-        if (be) {
-            if (lane == 0) esc_at = atomicAdd(&s_cnt[0], (uint32_t)__popc(be));
-            esc_at = __shfl_sync(0xFFFFFFFFu, esc_at, 0) + (uint32_t)__popc(be & ((1u << lane) - 1u));
+        // Placement of this round's output: ONE scan over two packed counters per line — side-table rows, and
+        // (escape-list | wide-list << 8) memberships — then one global atomic per non-empty counter, issued by three
+        // different threads so that their round trips overlap.
+        uint32_t xa = my_n, xb = (esc ? 1u : 0u) | (wide ? 0x100u : 0u);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ya = __shfl_up_sync(0xFFFFFFFFu, xa, d), yb = __shfl_up_sync(0xFFFFFFFFu, xb, d);
+            if (lane >= (uint32_t)d) { xa += ya; xb += yb; }
         }
-        if (bw) {
-            if (lane == 0) wide_at = atomicAdd(&s_cnt[1], (uint32_t)__popc(bw));
-            wide_at = __shfl_sync(0xFFFFFFFFu, wide_at, 0) + (uint32_t)__popc(bw & ((1u << lane) - 1u));
+        const int wid = tid >> 5;
+        constexpr int kWarps = LINES / 32;
+        if (lane == 31u) { scan_ws[wid] = xa; scan_ws[kWarps + wid] = xb; }
+        __syncthreads();
+        uint32_t before_a = 0, before_b = 0, total = 0, total_b = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t ta = scan_ws[w], tb = scan_ws[kWarps + w];
+            if (w < wid) { before_a += ta; before_b += tb; }
+            total += ta;
+            total_b += tb;
         }
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
-        const uint32_t n_esc = s_cnt[0], n_wide = s_cnt[1];
-        if (total | n_esc | n_wide) {  // CTA-uniform
-            if (tid == 0) {
-                if (total) s_base[0] = atomicAdd(P.counters + K5_ENTRIES, total);
-                if (n_esc) s_base[1] = atomicAdd(P.counters + K5_ESC_LIST, n_esc);
-                if (n_wide) s_base[2] = atomicAdd(P.counters + K5_WIDE_LIST, n_wide);
-            }
+        const uint32_t excl = before_a + xa - my_n;
+        const uint32_t pos_b = before_b + xb - ((esc ? 1u : 0u) | (wide ? 0x100u : 0u));  // exclusive: esc rank | wide rank << 8
+        const uint32_t n_esc = total_b & 0xFFu, n_wide = total_b >> 8;
+        if (total | total_b) {  // CTA-uniform
+            if (tid == 0 && total) s_base[0] = atomicAdd(P.counters + K5_ENTRIES, total);
+            if (tid == 32 % LINES && n_esc) s_base[1] = atomicAdd(P.counters + K5_ESC_LIST, n_esc);
+            if (tid == 33 % LINES && n_wide) s_base[2] = atomicAdd(P.counters + K5_WIDE_LIST, n_wide);
             __syncthreads();
         }
+        const uint32_t esc_at = pos_b & 0xFFu, wide_at = pos_b >> 8;
         uint32_t my_begin = 0;
         if (my_n) {
             my_begin = s_base[0] + excl;
@@ -167,14 +174,13 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     }
 }
 
-// One thread per listed line: pass 1 sums the unescaped lengths, one warp-aggregated atomic reserves the arena bytes,
-// pass 2 writes them and the extension row (arena offset | length << 32) behind every escaped pair.
-__global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant__ Parse5424Params P) {
-    if (*P.bad_offsets) return;
+// One thread per listed line, ONE pass: the arena bytes are reserved from the raw lengths (an unescaped value is never
+// longer than the raw one; a record is [u16 length][bytes], 2-byte aligned) with one warp-aggregated atomic, then every
+// escaped value is rewritten and its side-table row switched to the arena form.
+__device__ __forceinline__ void unescape_lines(const Parse5424Params& P, uint32_t first_item, uint32_t stride) {
     const uint32_t cnt = P.counters[K5_ESC_LIST];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); j0 < cnt; j0 += stride) {
+    for (uint32_t j0 = first_item; j0 < cnt; j0 += stride) {
         const uint32_t j = j0 + lane;
         const bool valid = j < cnt;
         uint32_t first = 0, count = 0;
@@ -182,21 +188,17 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
         if (valid) {
             const uint32_t line = P.esc_list[j];
             const uint4 lo4 = P.rows[2 * (size_t)line], hi4 = P.rows[2 * (size_t)line + 1];
+            o0 = P.offsets[line];
             first = lo4.w;
             count = hi4.x & 0xFFFFu;
-            o0 = P.offsets[line];
             if ((unsigned long long)first + count > (unsigned long long)P.entry_cap) count = 0;  // side table overflowed: the batch is redone
         }
-        // arena records are [u16 length][bytes], 2-byte aligned
-        uint32_t tot = 0;
+        uint32_t need = 0;
         for (uint32_t e = 0; e < count; ++e) {
             const unsigned long long v = P.entries[first + e];
-            if (!(v & kE8Header) && (v & kE8Esc)) {
-                const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
-                tot += (2u + (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), nullptr) + 1u) & ~1u;
-            }
+            if (!(v & kE8Header) && (v & kE8Esc)) need += (2u + (uint32_t)((v >> 32) & 0xFFFFu) - ((uint32_t)((v >> 16) & 0xFFFFu) + 2u) + 1u) & ~1u;
         }
-        uint32_t inc = tot;
+        uint32_t inc = need;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
         if (lane == 0 && warp_total) abase = atomicAdd(P.counters + K5_ARENA, warp_total);
         abase = __shfl_sync(0xFFFFFFFFu, abase, 0);
         if ((unsigned long long)abase + warp_total > (unsigned long long)P.arena_cap) continue;  // arena overflowed: the batch is redone
-        uint32_t at = abase + inc - tot;
+        uint32_t at = abase + inc - need;
         for (uint32_t e = 0; e < count; ++e) {
             const unsigned long long v = P.entries[first + e];
             if (!(v & kE8Header) && (v & kE8Esc)) {
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
                 const uint32_t l = (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at + 2);
                 *reinterpret_cast<uint16_t*>(P.arena + at) = (uint16_t)l;
                 P.entries[first + e] = (v & 0xFFFFFFFFull) | ((unsigned long long)(at >> 1) << 32) | kE8Arena;
-                at += (2u + l + 1u) & ~1u;
+                at += (2u + (uint32_t)(ve - (ne + 2)) + 1u) & ~1u;
             }
         }
     }
@@ -223,13 +225,11 @@ __global__ void __launch_bounds__(128) unescape5424_kernel(const __grid_constant
 
 // The round-1 scanner over the listed lines, one thread per line straight from global memory: a counting pass, one
 // atomic per line for its side-table rows, an emitting pass, then the unescape of its values and the wide row.
-__global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Parse5424Params P) {
-    __shared__ int marks[6][32];
-    if (*P.bad_offsets) return;
+__device__ __forceinline__ void wide_lines(const Parse5424Params& P, int (*marks)[32], uint32_t first_item, uint32_t stride) {
     const uint32_t cnt = P.counters[K5_WIDE_LIST];
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
     const EntrySink sink = {P.wentry_name, P.wentry_val, P.wentry_meta};
-    for (uint32_t j0 = blockIdx.x * 32u; j0 < cnt; j0 += gridDim.x * 32u) {
+    for (uint32_t j0 = first_item; j0 < cnt; j0 += stride) {
         const uint32_t j = j0 + lane;
         const bool valid = j < cnt;
         uint32_t line = 0;
@@ -309,6 +309,21 @@ __global__ void __launch_bounds__(32) wide5424_kernel(const __grid_constant__ Pa
     }
 }
 
+// ONE launch after the parse kernel for both device-side work lists: the first `esc_ctas` CTAs rewrite the escaped values
+// (unescape_lines), the remaining CTAs run the slow exact scanner over the irregular lines (wide_lines) — the two lists
+// are independent, so they share the machine instead of queueing behind each other.
+__global__ void __launch_bounds__(128) post5424_kernel(const __grid_constant__ Parse5424Params P, int esc_ctas) {
+    __shared__ int marks[4][6][32];
+    if (*P.bad_offsets) return;
+    const uint32_t warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < esc_ctas) {
+        unescape_lines(P, (blockIdx.x * 4u + warp) * 32u, (uint32_t)esc_ctas * 128u);
+    } else {
+        const uint32_t wctas = gridDim.x - (uint32_t)esc_ctas;
+        wide_lines(P, marks[warp], ((blockIdx.x - (uint32_t)esc_ctas) * 4u + warp) * 32u, wctas * 128u);
+    }
+}
+
 }  // namespace
 
 int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 16; }
@@ -322,10 +337,10 @@ cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int grid = (p.n + kFastLines - 1) / kFastLines;
     parse5424_kernel<kFastLines, kFastCtasPerSm><<<grid, kFastLines, parse5424_smem_bytes(p.tile_bytes), stream>>>(p);
-    // the work lists are usually short: a fixed small grid strides over them
-    const int lgrid = (int)min((long long)(p.n + 127) / 128, 148LL * 8);
-    unescape5424_kernel<<<lgrid, 128, 0, stream>>>(p);
-    wide5424_kernel<<<(int)min((long long)(p.n + 31) / 32, 148LL * 24), 32, 0, stream>>>(p);
+    // the work lists live on the device (no host round trip): a fixed grid strides over them
+    const int esc_ctas = (int)min((long long)(p.n + 127) / 128, 148LL * 12);
+    const int wide_ctas = (int)min((long long)(p.n + 127) / 128, 148LL * 4);
+    post5424_kernel<<<esc_ctas + wide_ctas, 128, 0, stream>>>(p, esc_ctas);
     return cudaGetLastError();
 }
 

@@ -306,11 +306,31 @@ FG_DEV bool r5_regular(uint8_t* T, const uint32_t* bmI, int ls, int le, R5Fast& 
     }
 
     // ---- parse_msg :163-172, Record assembly :32-47 ------------------------------------------------
+    // msg = line[msg_from..].trim(); full_msg = line.trim_end() (:46).  The byte before msg_from is '-' or ']', so when the
+    // rest is all whitespace full_msg ends at msg_from.  Common case: the line ends in a plain character and the message
+    // starts one space after SD — then no trim loop runs (the votes are warp-wide: every lane gets here).
+    int hi = le, lo = msg_from;
+    {
+        bool plain_end = true, plain_start = true;
+        if (ok) {
+            const uint32_t cl = T[le - 1];
+            plain_end = cl > 0x20u && cl < 0x80u;
+            plain_start = false;
+            if (msg_from + 1 < le) {
+                const uint32_t c0 = T[msg_from], c1 = T[msg_from + 1];
+                plain_start = c0 == ' ' && c1 > 0x20u && c1 < 0x80u;
+            }
+        }
+        if (fg_any(!plain_end)) {
+            if (ok && !plain_end) hi = trim_end(T, msg_from, le);
+        }
+        if (fg_any(!plain_start)) {
+            if (ok) lo = plain_start ? msg_from + 1 : trim_start(T, msg_from, hi);
+        } else {
+            lo = msg_from + 1;
+        }
+    }
     if (ok) {
-        // msg = line[msg_from..].trim(); full_msg = line.trim_end() (:46).  The byte before msg_from is '-' or ']', so when
-        // the rest is all whitespace full_msg ends at msg_from.
-        const int hi = trim_end(T, msg_from, le);
-        const int lo = trim_start(T, msg_from, hi);
         if (hi > lo) {
             r.msg_o = lo - ls;
             r.msg_l = hi - lo;

@@ -125,13 +125,10 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
             const uint64_t v = T->e8[e];
             if (!(v & fg::kE8Header) && (v & fg::kE8Esc)) {
                 const int ne = (int)FG_E8_B(v), ve = (int)FG_E8_C(v);
-                const int l = fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), nullptr);
                 const size_t at = T->arena.size();
-                T->arena.resize(at + ((2 + (size_t)l + 1) & ~(size_t)1) + 2);
-                fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at + 2);
-                const uint16_t l16 = (uint16_t)l;
+                T->arena.resize(at + ((2 + (size_t)(ve - (ne + 2)) + 1) & ~(size_t)1));  // reserved from the raw length
+                const uint16_t l16 = (uint16_t)fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at + 2);
                 memcpy(T->arena.data() + at, &l16, 2);
-                T->arena.resize(at + ((2 + (size_t)l + 1) & ~(size_t)1));
                 T->e8[e] = (v & 0xFFFFFFFFull) | ((uint64_t)(at >> 1) << 32) | fg::kE8Arena;
             }
         }
