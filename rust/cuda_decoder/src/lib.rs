@@ -5,7 +5,9 @@
 //!   * `Decoder::decode(&self, line: &str) -> Result<Record, &'static str>`  (src/flowgger/decoder/mod.rs:44-46)
 //!   * `CloneBoxedDecoder` via `#[derive(Clone)]`                            (decoder/mod.rs:23-42)
 //!   * `Splitter<T>::run`                                                    (src/flowgger/splitter/mod.rs:18-26)
-//! All parsing happens on the GPU; this crate packs lines, calls `fg_decode_batch` and materialises Records.
+//! All parsing happens on the GPU — including line framing, the UTF-8 check and the unescape of RFC5424 SD values; this
+//! crate hands raw blocks to `fg_split_decode` (or packed lines to `fg_decode_batch`) and materialises Records, or, for
+//! the rfc5424 -> gelf pair, forwards the records the device already encoded (`fg_decode_encode_gelf`).
 #![allow(non_camel_case_types, non_upper_case_globals, dead_code)]
 
 use flowgger::flowgger::config::Config;
@@ -151,21 +153,6 @@ fn span<'a>(bytes: &'a [u8], s: fg_span) -> &'a str {
     unsafe { std::str::from_utf8_unchecked(&bytes[s.off as usize..(s.off + s.len) as usize]) }
 }
 
-/// rfc5424_decoder.rs:105-125, deferred from the kernel (FG_EM_UNESCAPE)
-fn unescape_sd_value(value: &str) -> String {
-    let mut res = String::with_capacity(value.len());
-    let mut esc = false;
-    for c in value.chars() {
-        match (c, esc) {
-            ('\\', false) => esc = true,
-            (_, false) => res.push(c),
-            ('"', true) | ('\\', true) | (']', true) => { res.push(c); esc = false; }
-            (_, true) => { res.push('\\'); res.push(c); esc = false; }
-        }
-    }
-    res
-}
-
 /// JSON string body already validated on the device -> String; `nl_retry` = gelf_decoder.rs:44-46 semantics.
 fn json_unescape(v: &str, nl_retry: bool) -> String {
     let b = v.as_bytes();
@@ -205,8 +192,80 @@ fn materialize(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], offsets: &[i32], i: 
     materialize_ext(ctx, out, bytes, offsets[i], offsets[i + 1], i, side)
 }
 
+/// RFC5424: compact 32-byte row (`fg_row5424`) + 8-byte entries; escaped SD values were unescaped ON THE DEVICE
+/// (rfc5424_decoder.rs:105-125) and live in `out.arena`.  Rows flagged FG_FLAG_WIDE carry absolute spans instead.
+unsafe fn materialize_5424(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, i: usize) -> Result<Record, &'static str> {
+    let row = &*out.rows5424.add(i);
+    let status = row.meta & 0xFF;
+    if status != 0 {
+        let s = CStr::from_ptr(fg_error_string(ctx.fmt, status));
+        return Err(std::str::from_utf8_unchecked(std::slice::from_raw_parts(s.as_ptr() as *const u8, s.to_bytes().len())));
+    }
+    let (fac, sev, flags) = ((row.meta >> 8) & 0xFF, (row.meta >> 16) & 0xFF, row.meta >> 24);
+    let arena = |off: u32, len: usize| std::str::from_utf8_unchecked(std::slice::from_raw_parts(out.arena.add(off as usize), len)).to_owned();
+    if flags & FG_FLAG_WIDE != 0 {
+        let w = &*out.wide_rows.add(row.sd_first as usize);
+        let mut sd: Vec<StructuredData> = Vec::new();
+        for e in w.sd.off..w.sd.off + w.sd.len {
+            let e = e as usize;
+            let em = *out.entry_meta.add(e) as u32;
+            let nm = *out.entry_name.add(e);
+            if em & FG_EM_TAG_MASK == fg_tag_FG_TAG_SD_HEADER as u32 {
+                sd.push(StructuredData::new(Some(span(bytes, nm))));
+                continue;
+            }
+            let val = *out.entry_val.add(e);
+            let v = if em & FG_EM_ARENA != 0 { arena(val as u32, (val >> 32) as usize) }
+                    else { span(bytes, fg_span { off: (val & 0xFFFF_FFFF) as i32, len: (val >> 32) as i32 }).to_owned() };
+            sd.last_mut().unwrap().pairs.push((format!("_{}", span(bytes, nm)), SDValue::String(v)));
+        }
+        return Ok(Record {
+            ts: w.ts, hostname: span(bytes, w.hostname).to_owned(), facility: Some(fac as u8), severity: Some(sev as u8),
+            appname: Some(span(bytes, w.appname).to_owned()), procid: Some(span(bytes, w.procid).to_owned()),
+            msgid: Some(span(bytes, w.msgid).to_owned()),
+            msg: if w.msg.off >= 0 { Some(span(bytes, w.msg).to_owned()) } else { None },
+            full_msg: Some(span(bytes, w.full_msg).to_owned()),
+            sd: if sd.is_empty() { None } else { Some(sd) },
+        });
+    }
+    let line = &bytes[line_lo as usize..];
+    let rel = |a: usize, b: usize| std::str::from_utf8_unchecked(&line[a..b]).to_owned();
+    let sp: Vec<usize> = row.sp.iter().map(|&x| x as usize).collect();
+    let (mo, ml) = (row.msg_off as usize, row.msg_len as usize);
+    let mut sd: Vec<StructuredData> = Vec::new();
+    let mut e = row.sd_first as usize;
+    let end = e + row.sd_count as usize;
+    while e < end {
+        let v = *out.entries8.add(e);
+        let (a, b, c) = ((v & 0xFFFF) as usize, ((v >> 16) & 0xFFFF) as usize, ((v >> 32) & 0xFFFF) as usize);
+        if v & FG_E8_HEADER != 0 {
+            sd.push(StructuredData::new(Some(&rel(a, b))));
+        } else {
+            let value = if v & FG_E8_ARENA != 0 {
+                let off = (((v >> 32) & 0x3FFF_FFFF) as u32) << 1;   // record = [u16 length][bytes]
+                let len = u16::from_le_bytes([*out.arena.add(off as usize), *out.arena.add(off as usize + 1)]) as usize;
+                arena(off + 2, len)
+            } else {
+                rel(b + 2, c)
+            };
+            sd.last_mut().unwrap().pairs.push((format!("_{}", rel(a, b)), SDValue::String(value)));   // :221
+        }
+        e += 1;
+    }
+    Ok(Record {
+        ts: row.ts, hostname: rel(sp[0] + 1, sp[1]), facility: Some(fac as u8), severity: Some(sev as u8),
+        appname: Some(rel(sp[1] + 1, sp[2])), procid: Some(rel(sp[2] + 1, sp[3])), msgid: Some(rel(sp[3] + 1, sp[4])),
+        msg: if ml > 0 { Some(rel(mo, mo + ml)) } else { None },
+        full_msg: Some(rel(0, mo + ml)),
+        sd: if sd.is_empty() { None } else { Some(sd) },
+    })
+}
+
 fn materialize_ext(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, line_hi: i32, i: usize, side: &mut Vec<String>) -> Result<Record, &'static str> {
     unsafe {
+        if !out.rows5424.is_null() {
+            return materialize_5424(ctx, out, bytes, line_lo, i);
+        }
         let meta = *out.meta.add(i);
         let status = meta & 0xFF;
         let flags = (meta >> 24) & 0xFF;
@@ -233,8 +292,7 @@ fn materialize_ext(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, li
         let sd_span = *out.sd.add(i);
         let mut sd: Vec<StructuredData> = Vec::new();
         if sd_span.len > 0 {
-            let r5 = ctx.fmt == fg_format_FG_FMT_RFC5424;
-            if !r5 { sd.push(StructuredData::new(None)); }
+            sd.push(StructuredData::new(None));  // LTSV / GELF: one element without sd_id
             for e in sd_span.off..sd_span.off + sd_span.len {
                 let e = e as usize;
                 let em = *out.entry_meta.add(e) as u32;
@@ -252,7 +310,7 @@ fn materialize_ext(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, li
                 let v = match tag {
                     0 => {
                         let raw = span(bytes, fg_span { off: (val & 0xFFFF_FFFF) as i32, len: (val >> 32) as i32 });
-                        SDValue::String(if em & FG_EM_UNESCAPE == 0 { raw.to_owned() } else if r5 { unescape_sd_value(raw) } else { json_unescape(raw, nl) })
+                        SDValue::String(if em & FG_EM_UNESCAPE == 0 { raw.to_owned() } else { json_unescape(raw, nl) })
                     }
                     1 => SDValue::Bool(val != 0),
                     2 => SDValue::F64(f64::from_bits(val)),
@@ -297,59 +355,115 @@ impl Decoder for CudaDecoder {
 }
 
 /// Batched twin of `LineSplitter` (src/flowgger/splitter/line_splitter.rs:10-54): inserted between `input` and
-/// `decoder`; same line reading rules, same stderr text, Records sent in the original order.
+/// `decoder`.  It reads RAW BLOCKS (no per-line `String`), cuts each block after its last '\n' and hands the block to
+/// `fg_split_decode`: line framing (`BufRead::lines`: "\n", one "\r"), the UTF-8 check of `String` and the decode all run
+/// on the device; stderr text and record order are those of the reference.
 pub struct BatchingLineSplitter {
     pub gpu: CudaDecoder,
+    pub max_bytes: usize,
+}
+
+impl BatchingLineSplitter {
+    fn flush<F: FnMut(Vec<u8>)>(&self, block: &[u8], encoder: &Box<dyn Encoder>, send: &mut F) {
+        self.gpu.split_decode(block, |_, line, r, side| {
+            for s in side { println!("{}", s); }
+            match r.and_then(|rec| encoder.encode(rec)) {
+                Ok(bytes) => send(bytes),
+                Err("Invalid UTF-8 input") => { let _ = writeln!(stderr(), "Invalid UTF-8 input"); }   // line_splitter.rs:22-25
+                Err(e) => { let _ = writeln!(stderr(), "{}: [{}]", e, String::from_utf8_lossy(line).trim()); }  // :37-39
+            }
+        });
+    }
+}
+
+impl<T: Read> Splitter<T> for BatchingLineSplitter {
+    fn run(&self, mut buf_reader: BufReader<T>, tx: SyncSender<Vec<u8>>, _decoder: Box<dyn Decoder>, encoder: Box<dyn Encoder>) {
+        let mut block: Vec<u8> = Vec::with_capacity(self.max_bytes);
+        let mut send = |bytes: Vec<u8>| tx.send(bytes).unwrap();
+        loop {
+            let got = match buf_reader.fill_buf() {
+                Ok(b) => { let n = b.len(); block.extend_from_slice(b); n }
+                Err(e) => match e.kind() {
+                    ErrorKind::Interrupted => continue,
+                    ErrorKind::WouldBlock => {
+                        self.flush(&block, &encoder, &mut send);
+                        let _ = writeln!(stderr(), "Client hasn't sent any data for a while - Closing idle connection");
+                        return;
+                    }
+                    _ => { self.flush(&block, &encoder, &mut send); return; }
+                },
+            };
+            buf_reader.consume(got);
+            if got == 0 {                       // EOF: an unterminated last line is still a line
+                self.flush(&block, &encoder, &mut send);
+                return;
+            }
+            if block.len() >= self.max_bytes {
+                // decode every complete line of the block, keep the unterminated tail for the next one
+                let cut = block.iter().rposition(|&c| c == b'\n').map_or(0, |p| p + 1);
+                if cut > 0 {
+                    self.flush(&block[..cut], &encoder, &mut send);
+                    block.drain(..cut);
+                }
+            }
+        }
+    }
+}
+
+/// `output.format = "gelf"` with `input.format = "rfc5424"`: decode AND encode run on the device
+/// (`fg_decode_encode_gelf`, replaces Decoder::decode + GelfEncoder::encode of line_splitter.rs:50-52); only the encoded
+/// records come back.  Lines are framed on the host here (the fused entry point takes offsets).
+pub struct FusedGelfLineSplitter {
+    pub gpu: CudaDecoder,
+    pub extra: Vec<(String, String)>,   // output.gelf_extra (gelf_encoder.rs:29-48)
     pub max_lines: usize,
     pub max_bytes: usize,
 }
 
-impl<T: Read> Splitter<T> for BatchingLineSplitter {
-    fn run(&self, buf_reader: BufReader<T>, tx: SyncSender<Vec<u8>>, _decoder: Box<dyn Decoder>, encoder: Box<dyn Encoder>) {
+impl<T: Read> Splitter<T> for FusedGelfLineSplitter {
+    fn run(&self, buf_reader: BufReader<T>, tx: SyncSender<Vec<u8>>, _decoder: Box<dyn Decoder>, _encoder: Box<dyn Encoder>) {
+        let ctx = self.gpu.ctx.lock().unwrap();
+        let keys: Vec<CString> = self.extra.iter().map(|(k, _)| CString::new(k.as_str()).unwrap()).collect();
+        let vals: Vec<CString> = self.extra.iter().map(|(_, v)| CString::new(v.as_str()).unwrap()).collect();
+        let kp: Vec<*const c_char> = keys.iter().map(|s| s.as_ptr()).collect();
+        let vp: Vec<*const c_char> = vals.iter().map(|s| s.as_ptr()).collect();
+        assert_eq!(unsafe { fg_set_gelf_extra(ctx.raw, kp.len() as i32, kp.as_ptr(), vp.as_ptr()) }, 0);
         let mut arena: Vec<u8> = Vec::with_capacity(self.max_bytes);
         let mut offsets: Vec<i32> = vec![0];
-        let mut invalid_before: Vec<u32> = vec![0];
-        let mut flush = |arena: &mut Vec<u8>, offsets: &mut Vec<i32>, invalid_before: &mut Vec<u32>| {
+        let flush = |arena: &mut Vec<u8>, offsets: &mut Vec<i32>| {
             if offsets.len() > 1 {
-                let inv = invalid_before.clone();
-                self.gpu.decode_batch(arena, offsets, |i, r, side| {
-                    for _ in 0..inv[i] { let _ = writeln!(stderr(), "Invalid UTF-8 input"); }
-                    for s in side { println!("{}", s); }
-                    let line = unsafe { std::str::from_utf8_unchecked(&arena[offsets[i] as usize..offsets[i + 1] as usize]) };
-                    match r.and_then(|rec| encoder.encode(rec)) {
-                        Ok(bytes) => tx.send(bytes).unwrap(),
-                        Err(e) => { let _ = writeln!(stderr(), "{}: [{}]", e, line.trim()); }
+                let mut out: fg_encoded_out = unsafe { std::mem::zeroed() };
+                let rc = unsafe { fg_decode_encode_gelf(ctx.raw, ctx.fmt, arena.as_ptr(), offsets.as_ptr(), offsets.len() as i32 - 1, &mut out) };
+                assert_eq!(rc, 0);
+                for i in 0..out.n as usize {
+                    let (st, lo, hi) = unsafe { (*out.status.add(i), *out.offsets.add(i) as usize, *out.offsets.add(i + 1) as usize) };
+                    if st == 0 {
+                        tx.send(unsafe { std::slice::from_raw_parts(out.bytes.add(lo), hi - lo) }.to_vec()).unwrap();
+                    } else {
+                        let e = unsafe { CStr::from_ptr(fg_error_string(ctx.fmt, st as u32)) }.to_string_lossy();
+                        let line = String::from_utf8_lossy(&arena[offsets[i] as usize..offsets[i + 1] as usize]);
+                        let _ = writeln!(stderr(), "{}: [{}]", e, line.trim());
                     }
-                });
+                }
             }
-            for _ in 0..*invalid_before.last().unwrap() { let _ = writeln!(stderr(), "Invalid UTF-8 input"); }
             arena.clear();
             offsets.clear();
             offsets.push(0);
-            invalid_before.clear();
-            invalid_before.push(0);
         };
         for line in buf_reader.lines() {
-            let line = match line {
-                Ok(line) => line,
+            match line {
+                Ok(line) => {
+                    if arena.len() + line.len() > self.max_bytes || offsets.len() > self.max_lines { flush(&mut arena, &mut offsets); }
+                    arena.extend_from_slice(line.as_bytes());
+                    offsets.push(arena.len() as i32);
+                }
                 Err(e) => match e.kind() {
                     ErrorKind::Interrupted => continue,
-                    ErrorKind::InvalidInput | ErrorKind::InvalidData => { *invalid_before.last_mut().unwrap() += 1; continue; }
-                    ErrorKind::WouldBlock => {
-                        flush(&mut arena, &mut offsets, &mut invalid_before);
-                        let _ = writeln!(stderr(), "Client hasn't sent any data for a while - Closing idle connection");
-                        return;
-                    }
-                    _ => { flush(&mut arena, &mut offsets, &mut invalid_before); return; }
+                    ErrorKind::InvalidInput | ErrorKind::InvalidData => { flush(&mut arena, &mut offsets); let _ = writeln!(stderr(), "Invalid UTF-8 input"); }
+                    _ => break,
                 },
-            };
-            if arena.len() + line.len() > self.max_bytes || offsets.len() > self.max_lines {
-                flush(&mut arena, &mut offsets, &mut invalid_before);
             }
-            arena.extend_from_slice(line.as_bytes());
-            offsets.push(arena.len() as i32);
-            invalid_before.push(0);
         }
-        flush(&mut arena, &mut offsets, &mut invalid_before);
+        flush(&mut arena, &mut offsets);
     }
 }
