@@ -304,7 +304,7 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     if (fmt != FG_FMT_RFC5424 && mean > 256.0) return 0;
     const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
 #ifndef FG_TILE_SLACK_PCT  // head room of the tile over the mean span of a CTA's lines (profiles/variants.sh tries others)
-#define FG_TILE_SLACK_PCT 110
+#define FG_TILE_SLACK_PCT 102
 #endif
     long t = (long)(mean * lines * (FG_TILE_SLACK_PCT / 100.0)) + gran;
     t = (t + gran - 1) / gran * gran;

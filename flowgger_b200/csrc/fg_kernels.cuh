@@ -142,13 +142,12 @@ constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (ti
 // GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 16 CTAs/SM at 32
 // registers beat 12 at 40 and 7 at 72 (10.5 / 10.9 / 12.3 ms per 3.5 M lines); LTSV is the opposite (5.8 -> 8.8 ms: L1 working set)
 constexpr int kGelfUnstagedCtasPerSm = 16;
-// RFC5424 (short lines, staged tile): 64-line CTAs at 14 per SM — same warps/SM, tile waits and barriers half as wide
-// (2.36 -> 2.31 ms per 10 M lines; 13 KB tile + 1.8 KB static + 1 KB reserved per CTA = 225 KB of the SM's 227 KB)
+// RFC5424 (short lines, staged tile): 64-line CTAs — tile waits and barriers half as wide as with 128 lines
 #ifndef FG_R5_LINES  // profiles/variants.sh builds other shapes with -DFG_R5_LINES / -DFG_R5_MINB for A/B runs
 #define FG_R5_LINES 64
 #endif
-#ifndef FG_R5_MINB
-#define FG_R5_MINB 14
+#ifndef FG_R5_MINB  // 16 CTAs/SM (64 registers, tile slack 2 %) measured 2 % faster than 14 (71 registers, 10 %): profiles/r2_notes.md
+#define FG_R5_MINB 16
 #endif
 constexpr int kRfc5424LinesPerCta = FG_R5_LINES;
 constexpr int kRfc5424CtasPerSm = FG_R5_MINB;

@@ -42,7 +42,6 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     const int last = min(P.n, first + LINES);
     // the bitmap I ("may end a token") lives behind the tile: tile_bytes / 8 + 16 bytes
     uint32_t* bmI = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    uint16_t* bmI16 = reinterpret_cast<uint16_t*>(bmI);
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -73,13 +72,13 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- stage 1: structural bitmap of the whole tile, 16 bytes per thread per step ------------------------
-        const int ngran = (int)(nbytes >> 4);
-        for (int g = tid; g < ngran; g += LINES) {
-            const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
-            bmI16[g] = (uint16_t)r5_classify16(v.x, v.y, v.z, v.w);
+        // ---- stage 1: structural bitmap of the whole tile, 32 bytes (= one bitmap word) per thread per step -------
+        const int nword = (int)((nbytes + 31u) >> 5);  // the tile allocation is a multiple of 512 bytes: reading the odd granule is safe
+        for (int g = tid; g < nword; g += LINES) {
+            const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
+            bmI[g] = r5_classify16(v0.x, v0.y, v0.z, v0.w) | (r5_classify16(v1.x, v1.y, v1.z, v1.w) << 16);
         }
-        if (tid < 6) bmI16[ngran + tid] = 0;  // r5_window reads up to two words past the last granule
+        if (tid < 3) bmI[nword + tid] = 0;  // r5_window reads up to two words past the last one
         __syncthreads();
 
         // ---- stage 2: one thread per line ------------------------------------------------------------------------
@@ -214,7 +213,7 @@ __device__ __forceinline__ void unescape_lines(const Parse5424Params& P, uint32_
             const unsigned long long v = P.entries[first + e];
             if (!(v & kE8Header) && (v & kE8Esc)) {
                 const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
-                const uint32_t l = (uint32_t)r5_unescape(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at + 2);
+                const uint32_t l = (uint32_t)r5_unescape_to(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at + 2);
                 *reinterpret_cast<uint16_t*>(P.arena + at) = (uint16_t)l;
                 P.entries[first + e] = (v & 0xFFFFFFFFull) | ((unsigned long long)(at >> 1) << 32) | kE8Arena;
                 at += (2u + (uint32_t)(ve - (ne + 2)) + 1u) & ~1u;

@@ -115,6 +115,22 @@ FG_DEV int r5_unescape(const uint8_t* v, int len, uint8_t* out) {
     return o;
 }
 
+// the same rewrite, write-only and one decision per raw byte pair (the hot loop of unescape_lines)
+FG_DEV int r5_unescape_to(const uint8_t* v, int len, uint8_t* out) {
+    int o = 0;
+    for (int k = 0; k < len; ++k) {
+        const uint32_t c = v[k];
+        if (c != '\\') {
+            out[o++] = (uint8_t)c;
+        } else if (k + 1 < len) {  // a trailing lone backslash is dropped
+            const uint32_t d = v[++k];
+            if (d != '"' && d != '\\' && d != ']') out[o++] = '\\';
+            out[o++] = (uint8_t)d;
+        }
+    }
+    return o;
+}
+
 constexpr uint32_t kFlagWide = 0x80u;  // FG_FLAG_WIDE
 
 // Days from 1970-01-01 of a date already known to be valid, and the calendar checks of the fast stamp parser

@@ -127,7 +127,7 @@ int emu5424_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int3
                 const int ne = (int)FG_E8_B(v), ve = (int)FG_E8_C(v);
                 const size_t at = T->arena.size();
                 T->arena.resize(at + ((2 + (size_t)(ve - (ne + 2)) + 1) & ~(size_t)1));  // reserved from the raw length
-                const uint16_t l16 = (uint16_t)fg::r5_unescape(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at + 2);
+                const uint16_t l16 = (uint16_t)fg::r5_unescape_to(bytes + o0 + ne + 2, ve - (ne + 2), T->arena.data() + at + 2);
                 memcpy(T->arena.data() + at, &l16, 2);
                 T->e8[e] = (v & 0xFFFFFFFFull) | ((uint64_t)(at >> 1) << 32) | fg::kE8Arena;
             }
