@@ -963,6 +963,7 @@ int fg_decode_encode_gelf(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const 
             E.entry_cap = (uint32_t)std::min<size_t>(c->e8_cap, 0xFFFFFFFFu);
             E.wide_cap = (uint32_t)c->wide_cap;
             E.wentry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
+            E.tile_bytes = tile;
             FG_CUDA(c, fg::launch_gelf_encode(E, c->d_scan_temp, c->scan_temp_bytes, c->s_comp));
             c->launches += 4;
             FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));

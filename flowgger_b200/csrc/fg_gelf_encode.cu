@@ -7,8 +7,9 @@
 // with `"` `\\` \b \f \n \r \t escaped, Record.ts through dtoa (fg_dtoa.cuh).
 //
 // Input = the decoder's device-resident results (compact rows + 8-byte entries + arena, or wide rows); nothing of them
-// travels to the host in this mode.  Three launches per chunk of lines:
-//   gelf_size_kernel   one thread per line: exact length of its record (0 for a line the decoder rejected)
+// travels to the host in this mode.  Launches per chunk of lines:
+//   gelf_size_kernel   one thread per line: exact length of its record (0 for a line the decoder rejected); the bytes of
+//                      the CTA's 64 lines are staged in shared memory by one TMA bulk copy (both kernels)
 //   cub exclusive sum  record offsets inside the chunk
 //   gelf_write_kernel  one thread per line writes its record; output bytes are assembled four at a time and stored as
 //                      aligned 32-bit words, so a record costs a quarter of the store instructions / L2 requests of a
@@ -24,6 +25,7 @@
 #include "fg_dtoa.cuh"
 #include "fg_r5fast.cuh"
 #include "fg_status.h"
+#include "fg_tma.cuh"
 
 namespace fg {
 
@@ -123,7 +125,15 @@ struct RecView {
     const uint8_t* line;
 };
 
-__device__ __forceinline__ void load_view(const GelfEncodeParams& P, int i, RecView& r) {
+// `src` = where the bytes of the caller's buffer are read from: the staged tile (src[k] = byte base + k) or global memory
+// (base = 0).  Spans of the compact rows are relative to the line, wide rows carry absolute spans.
+struct ByteSource {
+    const uint8_t* p;  // p[abs - base] is byte `abs`
+    int base;
+    __device__ __forceinline__ const uint8_t* at(int abs) const { return p + (abs - base); }
+};
+
+__device__ __forceinline__ void load_view(const GelfEncodeParams& P, const ByteSource& B, int i, RecView& r) {
     const uint4 lo4 = P.rows[2 * (size_t)i], hi4 = P.rows[2 * (size_t)i + 1];
     const uint32_t meta = lo4.z;
     r.ok = (meta & 0xFFu) == 0u;
@@ -135,23 +145,23 @@ __device__ __forceinline__ void load_view(const GelfEncodeParams& P, int i, RecV
     if (!r.ok) return;
     r.severity = (meta >> 16) & 0xFFu;
     const int o0 = P.offsets[i];
-    r.line = P.bytes + o0;
+    r.line = B.at(o0);
     if (r.wide) {
         if (lo4.w >= P.wide_cap) { r.ok = false; return; }
         const WideRow& w = P.wide_rows[lo4.w];
         r.ts = w.ts;
-        r.host = Span{P.bytes + w.host.x, w.host.y};
-        r.app = Span{P.bytes + w.app.x, w.app.y};
-        r.proc = Span{P.bytes + w.proc.x, w.proc.y};
-        if (w.msg.x >= 0) r.msg = Span{P.bytes + w.msg.x, w.msg.y};
-        r.full = Span{P.bytes + max(w.full.x, 0), w.full.x >= 0 ? w.full.y : 0};
+        r.host = Span{B.at(w.host.x), w.host.y};
+        r.app = Span{B.at(w.app.x), w.app.y};
+        r.proc = Span{B.at(w.proc.x), w.proc.y};
+        if (w.msg.x >= 0) r.msg = Span{B.at(w.msg.x), w.msg.y};
+        r.full = Span{B.at(max(w.full.x, o0)), w.full.x >= 0 ? w.full.y : 0};
         r.first = (uint32_t)w.sd.x;
         r.count = (uint32_t)w.sd.y;
         if ((unsigned long long)r.first + r.count > (unsigned long long)P.wentry_cap) { r.ok = false; return; }
         for (uint32_t e = r.first; e < r.first + r.count; ++e)
             if ((P.wentry_meta[e] & 0x07u) == 7u) {
                 r.has_sd = true;
-                r.sd_id = Span{P.bytes + P.wentry_name[e].x, P.wentry_name[e].y};
+                r.sd_id = Span{B.at(P.wentry_name[e].x), P.wentry_name[e].y};
             }
         return;
     }
@@ -176,13 +186,14 @@ __device__ __forceinline__ void load_view(const GelfEncodeParams& P, int i, RecV
 }
 
 // pair e of the line (false: the row is an element header)
-__device__ __forceinline__ bool load_pair(const GelfEncodeParams& P, const RecView& r, uint32_t e, Span& name, Span& val) {
+__device__ __forceinline__ bool load_pair(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, uint32_t e, Span& name,
+                                          Span& val) {
     if (r.wide) {
         const uint8_t m = P.wentry_meta[e];
         if ((m & 0x07u) == 7u) return false;
-        name = Span{P.bytes + P.wentry_name[e].x, P.wentry_name[e].y};
+        name = Span{B.at(P.wentry_name[e].x), P.wentry_name[e].y};
         const unsigned long long v = P.wentry_val[e];
-        val = Span{((m & 0x80u) ? P.arena : P.bytes) + (uint32_t)v, (int)(v >> 32)};
+        val = Span{(m & 0x80u) ? P.arena + (uint32_t)v : B.at((int)(uint32_t)v), (int)(v >> 32)};
         return true;
     }
     const unsigned long long v = P.entries[e];
@@ -202,7 +213,7 @@ __device__ __forceinline__ bool load_pair(const GelfEncodeParams& P, const RecVi
 enum { GF_APP = 0, GF_FULL, GF_HOST, GF_LEVEL, GF_PROC, GF_SDID, GF_SHORT, GF_TS, GF_VERSION, GF_EXTRA = 100 };
 
 template <class Sink>
-__device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const RecView& r, Sink& s) {
+__device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, Sink& s) {
     s.put('{');
     bool first = true;
     int si = 0;
@@ -215,7 +226,7 @@ __device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const Rec
         bool have = false;
         for (uint32_t e = r.first; e < r.first + r.count; ++e) {
             Span nm, vl;
-            if (!load_pair(P, r, e, nm, vl)) continue;
+            if (!load_pair(P, B, r, e, nm, vl)) continue;
             if (have_prev && cmp_names(nm, prev) <= 0) continue;
             if (!have || cmp_names(nm, bn) <= 0) {
                 bn = nm;
@@ -287,16 +298,44 @@ __device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const Rec
     s.finish();
 }
 
-__global__ void __launch_bounds__(128) gelf_size_kernel(const __grid_constant__ GelfEncodeParams P) {
+// Both kernels stage the byte span of the CTA's 64 lines in shared memory with one TMA bulk copy, like the parse kernel:
+// a lane reading ITS line byte by byte from global memory would cost 32 L1 wavefronts per load instruction (32 lanes,
+// 32 different lines); from the tile it is one shared-memory access.  A span larger than the tile is read from global.
+constexpr int kEncLines = 64;
+
+__device__ __forceinline__ ByteSource stage_lines(const GelfEncodeParams& P, uint8_t* tile, uint64_t* mbar, int first, int last) {
+    const int o_first = P.offsets[first], o_last = P.offsets[last];
+    const int base = o_first & ~15;
+    const uint32_t nbytes = (uint32_t)((o_last - base) + 15) & ~15u;
+    const bool staged = nbytes <= (uint32_t)P.tile_bytes;  // CTA-uniform
+    if (staged) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            fence_proxy_async();
+            mbar_expect_tx(mbar, nbytes);
+            bulk_g2s(tile, P.bytes + base, nbytes, mbar);
+        }
+        __syncthreads();  // the barrier is initialised before anyone waits on it
+        mbar_wait(mbar, 0);
+        return ByteSource{tile, base};
+    }
+    return ByteSource{P.bytes, 0};
+}
+
+__global__ void __launch_bounds__(kEncLines) gelf_size_kernel(const __grid_constant__ GelfEncodeParams P) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
     if (*P.bad_offsets) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
+    const ByteSource B = stage_lines(P, tile, &mbar, first, last);
+    const int i = first + threadIdx.x;
+    if (i >= last) return;
     RecView r;
-    load_view(P, i, r);
+    load_view(P, B, i, r);
     uint32_t len = 0;
     if (r.ok) {
         CountSink s;
-        emit_record(P, r, s);
+        emit_record(P, B, r, s);
         len = s.n;
     }
     P.lens[i] = len;
@@ -310,22 +349,32 @@ __global__ void gelf_base_kernel(const __grid_constant__ GelfEncodeParams P) {
     P.base[1] = P.base[0] + total;
 }
 
-__global__ void __launch_bounds__(128) gelf_write_kernel(const __grid_constant__ GelfEncodeParams P) {
+__global__ void __launch_bounds__(kEncLines) gelf_write_kernel(const __grid_constant__ GelfEncodeParams P) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
     if (*P.bad_offsets) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
+    const ByteSource B = stage_lines(P, tile, &mbar, first, last);
+    const int i = first + threadIdx.x;
+    if (i >= last) return;
     const unsigned long long at = P.base[0] + P.rel[i];
     P.out_offsets[i] = (long long)at;
     if (i == P.n - 1) P.out_offsets[P.n] = (long long)(at + P.lens[i]);
     const uint32_t len = P.lens[i];
     if (len == 0u || at + len > P.out_cap) return;  // rejected line, or the output buffer overflowed (the batch is redone)
     RecView r;
-    load_view(P, i, r);
+    load_view(P, B, i, r);
     WordSink s(P.out + at);
-    emit_record(P, r, s);
+    emit_record(P, B, r, s);
 }
 
 }  // namespace
+
+cudaError_t configure_gelf_encode(int max_tile_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(gelf_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gelf_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+}
 
 size_t gelf_scan_temp_bytes(int n) {
     size_t bytes = 0;
@@ -335,12 +384,12 @@ size_t gelf_scan_temp_bytes(int n) {
 
 cudaError_t launch_gelf_encode(const GelfEncodeParams& p, void* d_scan_temp, size_t scan_temp_bytes, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    const int grid = (p.n + 127) / 128;
-    gelf_size_kernel<<<grid, 128, 0, stream>>>(p);
+    const int grid = (p.n + kEncLines - 1) / kEncLines;
+    gelf_size_kernel<<<grid, kEncLines, p.tile_bytes, stream>>>(p);
     cudaError_t e = cub::DeviceScan::ExclusiveSum(d_scan_temp, scan_temp_bytes, p.lens, p.rel, p.n, stream);
     if (e != cudaSuccess) return e;
     gelf_base_kernel<<<1, 1, 0, stream>>>(p);
-    gelf_write_kernel<<<grid, 128, 0, stream>>>(p);
+    gelf_write_kernel<<<grid, kEncLines, p.tile_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -207,6 +207,8 @@ cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424) {
     }
     cudaError_t e = configure_parse5424(max_tile5424);
     if (e != cudaSuccess) return e;
+    e = configure_gelf_encode(max_tile5424);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);

@@ -133,7 +133,9 @@ struct GelfEncodeParams {
     uint8_t* status;                // [n] decoder status per line (0 = a record was written)
     const uint32_t* bad_offsets;
     uint32_t entry_cap, wide_cap, wentry_cap;  // a table that overflowed is not read (the batch is redone after a regrow)
+    int32_t tile_bytes;                        // staging tile of the two kernels (dynamic shared memory)
 };
+cudaError_t configure_gelf_encode(int max_tile_bytes);
 cudaError_t launch_gelf_encode(const GelfEncodeParams& p, void* d_scan_temp, size_t scan_temp_bytes, cudaStream_t stream);
 size_t gelf_scan_temp_bytes(int n);
 
