@@ -164,6 +164,8 @@ struct fg_ctx {
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_h2d, ev_k0, ev_k1, ev_cnt;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_dom0 = nullptr, ev_dom1 = nullptr;  // bracket the dominant kernel of a resident step
+    float last_dom_ms = 0.f;
     // resident batch
     int res_n = 0;
     size_t res_bytes = 0;
@@ -337,7 +339,8 @@ int regrow_tables(fg_ctx* c, int fmt, const uint32_t* t) {
 }
 
 // One parse launch over lines [line0, line0 + n) of the resident offsets (for RFC5424: parse + unescape + wide kernels)
-int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* invalid, int strip_eol, cudaStream_t s) {
+int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* invalid, int strip_eol, cudaStream_t s,
+                 bool time_dominant = false) {
     if (fmt == FG_FMT_RFC5424) {
         fg::Parse5424Params P;
         P.bytes = c->d_bytes;
@@ -363,7 +366,7 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
         P.line_invalid = invalid;
         P.strip_eol = strip_eol;
         FG_CUDA(c, cudaMemsetAsync(c->d_k + fg::K5_ESC_LIST, 0, 8, s));  // the two work lists are per launch
-        FG_CUDA(c, fg::launch_parse5424(P, s));
+        FG_CUDA(c, fg::launch_parse5424(P, s, time_dominant ? c->ev_dom0 : nullptr, time_dominant ? c->ev_dom1 : nullptr));
         c->launches += 2;  // parse5424_kernel + post5424_kernel
         return FG_OK;
     }
@@ -395,7 +398,9 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
     P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
     P.bad_offsets = c->d_k + kBadFlag;
     P.ltsv = c->ltsv;
+    if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom0, s));
     FG_CUDA(c, fg::launch_parse(fmt, P, s));
+    if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom1, s));
     ++c->launches;
     return FG_OK;
 }
@@ -697,6 +702,8 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     FG_CREATE_CUDA(cudaEventCreate(&c->ev_a));
     FG_CREATE_CUDA(cudaEventCreate(&c->ev_b));
+    FG_CREATE_CUDA(cudaEventCreate(&c->ev_dom0));
+    FG_CREATE_CUDA(cudaEventCreate(&c->ev_dom1));
     FG_CREATE_CUDA(cudaMalloc(&c->d_bytes, c->max_bytes + kPad));
     FG_CREATE_CUDA(cudaMemset(c->d_bytes + c->max_bytes, 0, kPad));
     FG_CREATE_CUDA(cudaMalloc(&c->d_offsets, sizeof(int32_t) * ((size_t)c->max_lines + 1)));
@@ -783,6 +790,8 @@ void fg_destroy(fg_ctx* c) {
     for (auto e : c->ev_cnt) cudaEventDestroy(e);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_dom0) cudaEventDestroy(c->ev_dom0);
+    if (c->ev_dom1) cudaEventDestroy(c->ev_dom1);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1182,7 +1191,7 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kBadFlag, c->s_comp));
         FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
-        if (int rc = launch_lines(c, (int)fmt, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt), nullptr, 0, c->s_comp)) return rc;
+        if (int rc = launch_lines(c, (int)fmt, 0, c->res_n, pick_tile(c, c->res_bytes, c->res_n, (int)fmt), nullptr, 0, c->s_comp, true)) return rc;
         FG_CUDA(c, cudaEventRecord(c->ev_b, c->s_comp));
         uint32_t total[kCnt] = {};
         FG_CUDA(c, cudaMemcpyAsync(total, c->d_k, sizeof total, cudaMemcpyDeviceToHost, c->s_comp));
@@ -1194,6 +1203,7 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
         float ms = 0.f;
         FG_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
         if (kernel_ms) *kernel_ms = ms;
+        FG_CUDA(c, cudaEventElapsedTime(&c->last_dom_ms, c->ev_dom0, c->ev_dom1));
         c->res_fmt = (int)fmt;
         memcpy(c->res_tot, total, sizeof total);
         return FG_OK;
@@ -1260,5 +1270,6 @@ uint32_t fg_error_count(void) { return FG_ST_COUNT; }
 const char* fg_build_info(void) { return fg::kernel_build_info(); }
 int64_t fg_kernel_launches(const fg_ctx* c) { return c ? c->launches : 0; }
 float fg_last_split_ms(const fg_ctx* c) { return c ? c->last_split_ms : 0.f; }
+float fg_last_dominant_kernel_ms(const fg_ctx* c) { return c ? c->last_dom_ms : 0.f; }
 
 }  // extern "C"

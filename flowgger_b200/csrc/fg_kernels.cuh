@@ -102,7 +102,8 @@ struct Parse5424Params {
     int32_t strip_eol;
 };
 
-cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream);  // parse + unescape + wide kernels
+// parse5424_kernel + post5424_kernel; when given, the two events bracket the parse kernel alone (roofline measurement)
+cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream, cudaEvent_t dom0 = nullptr, cudaEvent_t dom1 = nullptr);
 cudaError_t configure_parse5424(int max_tile_bytes);
 int parse5424_smem_bytes(int tile_bytes);
 

@@ -332,10 +332,12 @@ cudaError_t configure_parse5424(int max_tile_bytes) {
                                 parse5424_smem_bytes(max_tile_bytes));
 }
 
-cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream) {
+cudaError_t launch_parse5424(const Parse5424Params& p, cudaStream_t stream, cudaEvent_t dom0, cudaEvent_t dom1) {
     if (p.n <= 0) return cudaSuccess;
     const int grid = (p.n + kFastLines - 1) / kFastLines;
+    if (dom0) cudaEventRecord(dom0, stream);
     parse5424_kernel<kFastLines, kFastCtasPerSm><<<grid, kFastLines, parse5424_smem_bytes(p.tile_bytes), stream>>>(p);
+    if (dom1) cudaEventRecord(dom1, stream);
     // the work lists live on the device (no host round trip): a fixed grid strides over them
     const int esc_ctas = (int)min((long long)(p.n + 127) / 128, 148LL * 12);
     const int wide_ctas = (int)min((long long)(p.n + 127) / 128, 148LL * 4);

@@ -94,6 +94,8 @@ def load_cuda() -> C.CDLL:
         L.fg_last_split_ms.restype = C.c_float
         L.fg_last_split_ms.argtypes = [C.c_void_p]
         L.fg_error_count.restype = C.c_uint32
+        L.fg_last_dominant_kernel_ms.restype = C.c_float
+        L.fg_last_dominant_kernel_ms.argtypes = [C.c_void_p]
         L.fg_set_gelf_extra.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
         L.fg_decode_encode_gelf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FgEncodedOut)]
         _cuda = L
@@ -357,6 +359,10 @@ class BatchDecoder:
         ms = C.c_float()
         self._check(self.L.fg_parse_resident(self.ctx, self.fmt, C.byref(ms)), "fg_parse_resident")
         return ms.value
+
+    def last_dominant_kernel_ms(self) -> float:
+        """CUDA-event time of the dominant kernel alone inside the last parse_resident() step."""
+        return float(self.L.fg_last_dominant_kernel_ms(self.ctx))
 
     def parse_resident_many(self, k: int) -> float:
         """k back-to-back passes over the resident batch, one host sync; returns the CUDA-event time of all k (ms)."""

@@ -254,6 +254,8 @@ uint32_t fg_error_count(void);
 const char* fg_build_info(void);          /* arch, compiler, kernel list */
 int64_t fg_kernel_launches(const fg_ctx* ctx); /* parse kernels launched by this ctx so far */
 float fg_last_split_ms(const fg_ctx* ctx);     /* device time of the framing + UTF-8 kernels of the last fg_split_decode */
+float fg_last_dominant_kernel_ms(const fg_ctx* ctx); /* CUDA-event time of the dominant kernel alone (RFC5424: parse5424_kernel)
+                                                        inside the last fg_parse_resident step */
 
 #ifdef __cplusplus
 }

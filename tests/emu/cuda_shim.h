@@ -34,6 +34,7 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
 // host stand-ins for the types fg_kernels.cuh mentions and the warp intrinsics the round-1 scanner calls directly
 typedef int cudaError_t;
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline void __syncwarp() {}
 static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
