@@ -695,7 +695,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->device));
     c->max_tile = (int)std::min<size_t>(prop.sharedMemPerBlockOptin - 1024, 200 * 1024);
     c->max_tile &= ~1023;
-    c->max_tile5 = (int)(((size_t)c->max_tile - 1024) * 8 / 9) & ~1023;  // tile + tile/8 bitmap + static shared memory
+    c->max_tile5 = (int)(((size_t)c->max_tile - 2048) * 32 / 37) & ~1023;  // tile + tile/8 bitmap + tile/32 counts + static shared memory
     FG_CREATE_CUDA(fg::configure_kernels(c->max_tile, c->max_tile5));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));

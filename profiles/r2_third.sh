@@ -4,6 +4,9 @@ mkdir -p gpurun_out
 cp flowgger_b200/lib/libflowgger_cuda.so gpurun_out/lib_used.so  # the exact build the profiles below belong to (tools/ncu_by_line.py)
 timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/r2c_pytest.log 2>&1; tail -6 gpurun_out/r2c_pytest.log
 timeout 600 python bench.py --steps 20 --warmup 3 --encode --split 2> gpurun_out/r2c_bench.err | tail -1 > gpurun_out/r2c_bench_rfc5424.json; cut -c1-600 gpurun_out/r2c_bench_rfc5424.json; tail -3 gpurun_out/r2c_bench.err
+for d in flowgger_b200/lib_v_*; do
+  echo "== $d"; FG_VARIANT_DIR=$d timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 | python -c "import json,sys; d=json.load(sys.stdin); print('step_ms', d['kernel_ms'], 'dominant_ms', d['roofline'].get('kernel_ms'), 'frac', d['roofline']['frac'])"
+done 2>&1 | tee gpurun_out/r2c_variants.txt
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r2c_bench_reference.json; cut -c1-300 gpurun_out/r2c_bench_reference.json
 timeout 600 python bench.py --format ltsv --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r2c_bench_ltsv.json
 timeout 600 python bench.py --format ltsv --ltsv-typed --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r2c_bench_ltsv_typed.json
