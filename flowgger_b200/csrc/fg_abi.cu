@@ -574,6 +574,7 @@ int build_static_items(fg_ctx* c) {
     for (int k = 0; k < 9; ++k) {
         Item it;
         it.key = fixed[k];
+        it.lit = ",";  // the device skips the comma for the first item of a record
         json_escape_into(it.key, it.lit);
         it.lit.push_back(':');
         it.kind = k;
@@ -582,6 +583,7 @@ int build_static_items(fg_ctx* c) {
     for (const auto& kv : c->gelf_extra) {
         Item it;
         it.key = kv.first;
+        it.lit = ",";
         json_escape_into(kv.first, it.lit);
         it.lit.push_back(':');
         json_escape_into(kv.second, it.lit);
@@ -695,7 +697,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     FG_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->device));
     c->max_tile = (int)std::min<size_t>(prop.sharedMemPerBlockOptin - 1024, 200 * 1024);
     c->max_tile &= ~1023;
-    c->max_tile5 = (int)(((size_t)c->max_tile - 2048) * 32 / 37) & ~1023;  // tile + tile/8 bitmap + tile/32 counts + static shared memory
+    c->max_tile5 = (int)(((size_t)c->max_tile - 1024) * 8 / 9) & ~1023;  // tile + tile/8 bitmap + static shared memory
     FG_CREATE_CUDA(fg::configure_kernels(c->max_tile, c->max_tile5));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     FG_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));

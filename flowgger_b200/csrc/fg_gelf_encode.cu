@@ -62,35 +62,9 @@ struct WordSink {
     }
     __device__ __forceinline__ void finish() {
         for (int k = 0; k < nacc; ++k) p[k] = (uint8_t)(acc >> (8 * k));
+        nacc = 0;
     }
 };
-
-template <class Sink>
-__device__ __forceinline__ void put_lit(Sink& s, const uint8_t* lit, int len) {
-    for (int k = 0; k < len; ++k) s.put(lit[k]);
-}
-// serde_json 0.8 ser.rs escape_bytes: `"` `\\` \b \f \n \r \t get a backslash form, every other byte is copied
-template <class Sink>
-__device__ __forceinline__ void put_escaped(Sink& s, Span v) {
-    for (int k = 0; k < v.len; ++k) {
-        const uint32_t c = v.p[k];
-        uint32_t e = 0;
-        if (c == '"' || c == '\\') e = c;
-        else if (c < 0x20u) e = c == 8u ? 'b' : c == 9u ? 't' : c == 10u ? 'n' : c == 12u ? 'f' : c == 13u ? 'r' : 0u;
-        if (e) {
-            s.put('\\');
-            s.put(e);
-        } else {
-            s.put(c);
-        }
-    }
-}
-template <class Sink>
-__device__ __forceinline__ void put_string(Sink& s, Span v) {
-    s.put('"');
-    put_escaped(s, v);
-    s.put('"');
-}
 
 // byte-order comparison of ('_' + a) with b
 __device__ __forceinline__ int cmp_sd_key(Span a, Span b) {
@@ -212,9 +186,47 @@ __device__ __forceinline__ bool load_pair(const GelfEncodeParams& P, const ByteS
 // static items (host-prepared, sorted by key, extras already override fixed keys of the same name)
 enum { GF_APP = 0, GF_FULL, GF_HOST, GF_LEVEL, GF_PROC, GF_SDID, GF_SHORT, GF_TS, GF_VERSION, GF_EXTRA = 100 };
 
-template <class Sink>
-__device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, Sink& s) {
-    s.put('{');
+// ---- a record = a short list of segments, then ONE byte loop -------------------------------------------------------
+// Emitting field by field with a byte loop per field made every lane of a warp sit in a different loop (4 of 32 lanes
+// active, 1100 warp-instructions per record, profiles/r2c_ncu_gelf_write.txt).  Now a lane first lists its record as
+// segments (pointer, length, copy / JSON-escape) — short, divergent — and then all 32 lanes run the SAME loop that
+// produces one output byte per iteration from the current segment.
+struct Seg {
+    const uint8_t* p;
+    int len;  // bit 31: JSON-escape the bytes
+};
+constexpr int kMaxSegs = 56;  // a record with more segments is emitted in several windows (rebuilt with `skip`)
+constexpr int kEscBit = (int)0x80000000u;
+__device__ const uint8_t kLit[] = "{}\",\"_\":\"\"unknown\"\"-\"\"1.1\"01234567";
+//                                 0 1 2 3..5 6..8 9..17      18..20 21..25 26..33
+enum { L_OPEN = 0, L_CLOSE = 1, L_QUOTE = 2, L_PAIR = 3 /* ,"_ */, L_MID = 6 /* ":" */, L_UNKNOWN = 9, L_DASH = 18, L_V11 = 21, L_DIGITS = 26 };
+
+struct SegList {
+    Seg s[kMaxSegs];
+    int n = 0;     // segments held: those with running index in [skip, skip + kMaxSegs)
+    int idx = 0;   // running index over the whole record
+    int skip = 0;
+    __device__ __forceinline__ void reset(int skip_) { n = 0; idx = 0; skip = skip_; }
+    __device__ __forceinline__ void push(const uint8_t* p, int len, bool esc) {
+        if (len <= 0) return;
+        if (idx >= skip && n < kMaxSegs) {
+            s[n].p = p;
+            s[n].len = len | (esc ? kEscBit : 0);
+            ++n;
+        }
+        ++idx;
+    }
+    __device__ __forceinline__ void lit(int at, int len) { push(kLit + at, len, false); }
+    __device__ __forceinline__ void str(Span v) {
+        lit(L_QUOTE, 1);
+        push(v.p, v.len, true);
+        lit(L_QUOTE, 1);
+    }
+};
+
+// `num` (>= 32 bytes, owned by the caller) receives the text of Record.ts and is referenced by a segment
+__device__ __forceinline__ void build_segments(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, uint8_t* num, SegList& L) {
+    L.lit(L_OPEN, 1);
     bool first = true;
     int si = 0;
     Span prev{nullptr, -1};  // last SD name emitted (or skipped)
@@ -248,54 +260,109 @@ __device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const Byt
         }
         if (take_static) {
             const int kind = P.static_kind[si];
+            // the literal is `,"key":` (for an extra `,"key":"value"`): the comma is skipped for the first item
             const uint8_t* lit = P.static_blob + P.static_lit_off[si];
             const int lit_len = P.static_lit_off[si + 1] - P.static_lit_off[si];
             ++si;
             if (take_static == 2) { prev = bn; have_prev = true; }
-            bool present = true;
-            if (kind == GF_SDID) present = r.has_sd;
-            if (!present) continue;
-            if (!first) s.put(',');
+            if (kind == GF_SDID && !r.has_sd) continue;
+            L.push(lit + (first ? 1 : 0), lit_len - (first ? 1 : 0), false);
             first = false;
-            put_lit(s, lit, lit_len);  // `"key":` — for an extra the whole `"key":"value"`
             switch (kind) {
-                case GF_APP: put_string(s, r.app); break;
-                case GF_FULL: put_string(s, r.full); break;
+                case GF_APP: L.str(r.app); break;
+                case GF_FULL: L.str(r.full); break;
                 case GF_HOST:
-                    if (r.host.len == 0) { const uint8_t u[] = {'"', 'u', 'n', 'k', 'n', 'o', 'w', 'n', '"'}; put_lit(s, u, 9); }
-                    else put_string(s, r.host);
+                    if (r.host.len == 0) L.lit(L_UNKNOWN, 9);
+                    else L.str(r.host);
                     break;
-                case GF_LEVEL: s.put('0' + r.severity); break;
-                case GF_PROC: put_string(s, r.proc); break;
-                case GF_SDID: put_string(s, r.sd_id); break;
+                case GF_LEVEL: L.lit(L_DIGITS + (int)(r.severity & 7u), 1); break;
+                case GF_PROC: L.str(r.proc); break;
+                case GF_SDID: L.str(r.sd_id); break;
                 case GF_SHORT:
-                    if (r.msg.p == nullptr) { s.put('"'); s.put('-'); s.put('"'); }
-                    else put_string(s, r.msg);
+                    if (r.msg.p == nullptr) L.lit(L_DASH, 3);
+                    else L.str(r.msg);
                     break;
-                case GF_TS: {
-                    uint8_t num[32];
-                    const int k = json_f64(r.ts, num);
-                    put_lit(s, num, k);
-                    break;
-                }
-                case GF_VERSION: { const uint8_t v[] = {'"', '1', '.', '1', '"'}; put_lit(s, v, 5); break; }
+                case GF_TS: L.push(num, json_f64(r.ts, num), false); break;
+                case GF_VERSION: L.lit(L_V11, 5); break;
                 default: break;  // GF_EXTRA: the literal was everything
             }
             continue;
         }
-        if (!first) s.put(',');
+        L.lit(L_PAIR + (first ? 1 : 0), first ? 2 : 3);  // ,"_
         first = false;
-        s.put('"');
-        s.put('_');
-        put_escaped(s, bn);
-        s.put('"');
-        s.put(':');
-        put_string(s, bv);
+        L.push(bn.p, bn.len, true);
+        L.lit(L_MID, 3);  // ":"
+        L.push(bv.p, bv.len, true);
+        L.lit(L_QUOTE, 1);
         prev = bn;
         have_prev = true;
     }
-    s.put('}');
-    s.finish();
+    L.lit(L_CLOSE, 1);
+}
+
+// serde_json 0.8 ser.rs escape_bytes: `"` `\` \b \f \n \r \t get a backslash form (returns the second byte), else 0
+__device__ __forceinline__ uint32_t json_escape_of(uint32_t c) {
+    if (c == '"' || c == '\\') return c;
+    if (c >= 0x20u) return 0u;
+    return c == 8u ? 'b' : c == 9u ? 't' : c == 10u ? 'n' : c == 12u ? 'f' : c == 13u ? 'r' : 0u;
+}
+
+// The warp-uniform loop: one output byte per lane and iteration.  `live` = this lane has a record to emit.
+template <class Sink>
+__device__ __forceinline__ void run_segments(const SegList& L, bool live, Sink& s) {
+    int si = 0, k = 0, len = 0;
+    bool esc = false;
+    const uint8_t* p = nullptr;
+    uint32_t pending = 0;
+    bool more = live && L.n > 0;
+    if (more) {
+        p = L.s[0].p;
+        len = L.s[0].len & ~kEscBit;
+        esc = L.s[0].len < 0;
+    }
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        if (more) {
+            uint32_t out;
+            if (pending) {
+                out = pending;
+                pending = 0;
+            } else {
+                out = p[k++];
+                if (esc) {
+                    const uint32_t e = json_escape_of(out);
+                    if (e) { pending = e; out = '\\'; }
+                }
+            }
+            s.put(out);
+            if (k >= len && !pending) {  // next segment (none is empty)
+                ++si;
+                if (si < L.n) {
+                    p = L.s[si].p;
+                    len = L.s[si].len & ~kEscBit;
+                    esc = L.s[si].len < 0;
+                    k = 0;
+                } else {
+                    more = false;
+                }
+            }
+        }
+    }
+}
+
+// a record of any size: windows of kMaxSegs segments, every window through the warp-uniform loop
+template <class Sink>
+__device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, bool live, Sink& s) {
+    uint8_t num[32];
+    SegList L;
+    int skip = 0;
+    for (;;) {
+        L.reset(skip);
+        if (live) build_segments(P, B, r, num, L);
+        run_segments(L, live, s);
+        skip += kMaxSegs;
+        if (!__any_sync(0xFFFFFFFFu, live && L.idx > skip)) break;
+    }
+    if (live) s.finish();
 }
 
 // Both kernels stage the byte span of the CTA's 64 lines in shared memory with one TMA bulk copy, like the parse kernel:
@@ -329,16 +396,14 @@ __global__ void __launch_bounds__(kEncLines) gelf_size_kernel(const __grid_const
     const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
     const ByteSource B = stage_lines(P, tile, &mbar, first, last);
     const int i = first + threadIdx.x;
-    if (i >= last) return;
+    const bool valid = i < last;
     RecView r;
-    load_view(P, B, i, r);
-    uint32_t len = 0;
-    if (r.ok) {
-        CountSink s;
-        emit_record(P, B, r, s);
-        len = s.n;
-    }
-    P.lens[i] = len;
+    r.ok = false;
+    if (valid) load_view(P, B, i, r);
+    CountSink s;
+    emit_record(P, B, r, r.ok, s);
+    if (!valid) return;
+    P.lens[i] = r.ok ? s.n : 0u;
     P.status[i] = (uint8_t)(P.rows[2 * (size_t)i].z & 0xFFu);
 }
 
@@ -356,16 +421,22 @@ __global__ void __launch_bounds__(kEncLines) gelf_write_kernel(const __grid_cons
     const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
     const ByteSource B = stage_lines(P, tile, &mbar, first, last);
     const int i = first + threadIdx.x;
-    if (i >= last) return;
-    const unsigned long long at = P.base[0] + P.rel[i];
-    P.out_offsets[i] = (long long)at;
-    if (i == P.n - 1) P.out_offsets[P.n] = (long long)(at + P.lens[i]);
-    const uint32_t len = P.lens[i];
-    if (len == 0u || at + len > P.out_cap) return;  // rejected line, or the output buffer overflowed (the batch is redone)
+    const bool valid = i < last;
+    unsigned long long at = 0;
+    uint32_t len = 0;
+    if (valid) {
+        at = P.base[0] + P.rel[i];
+        len = P.lens[i];
+        P.out_offsets[i] = (long long)at;
+        if (i == P.n - 1) P.out_offsets[P.n] = (long long)(at + len);
+    }
+    // a rejected line has no record; an output buffer that overflowed is not written (the batch is redone)
+    const bool live = valid && len != 0u && at + len <= P.out_cap;
     RecView r;
-    load_view(P, B, i, r);
+    r.ok = false;
+    if (live) load_view(P, B, i, r);
     WordSink s(P.out + at);
-    emit_record(P, B, r, s);
+    emit_record(P, B, r, live && r.ok, s);
 }
 
 }  // namespace

@@ -35,16 +35,13 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[2 * (LINES / 32)];  // per-warp totals of the two packed counters
     __shared__ uint32_t s_base[3];                  // side-table base, escape-list base, wide-list base of this round
-    __shared__ uint32_t s_hist[16];                 // lines per sort key
-    __shared__ int s_perm[3][LINES];                // (ls, le, line) of the lines in sorted order
 
     const int tid = threadIdx.x;
     const uint32_t lane = (uint32_t)tid & 31u;
     const int first = blockIdx.x * LINES;
     const int last = min(P.n, first + LINES);
-    // the bitmap I ("may end a token") lives behind the tile (tile_bytes / 8 + 16 bytes), then one count byte per bitmap word
+    // the bitmap I ("may end a token") lives behind the tile: tile_bytes / 8 + 16 bytes
     uint32_t* bmI = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    uint8_t* cnt8 = tile + P.tile_bytes + P.tile_bytes / 8 + 16;
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -52,7 +49,7 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
     uint32_t parity = 0;
     int cur = first;
     while (cur < last) {
-        int i = cur + tid;
+        const int i = cur + tid;
         const int o0 = __ldg(P.offsets + min(i, last));
         const int o1 = __ldg(P.offsets + min(i + 1, last));
         const int ocur = __ldg(P.offsets + cur);
@@ -72,7 +69,6 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
             mbar_expect_tx(&mbar, nbytes);
             bulk_g2s(tile, P.bytes + base, nbytes, &mbar);
         }
-        if (tid < 16) s_hist[tid] = 0;
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
@@ -80,48 +76,18 @@ __global__ void __launch_bounds__(LINES, MINB) parse5424_kernel(const __grid_con
         const int nword = (int)((nbytes + 31u) >> 5);  // the tile allocation is a multiple of 512 bytes: reading the odd granule is safe
         for (int g = tid; g < nword; g += LINES) {
             const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
-            uint32_t k0, k1;
-            bmI[g] = r5_classify16_count(v0.x, v0.y, v0.z, v0.w, k0) | (r5_classify16_count(v1.x, v1.y, v1.z, v1.w, k1) << 16);
-            cnt8[g] = (uint8_t)(k0 + k1);
+            bmI[g] = r5_classify16(v0.x, v0.y, v0.z, v0.w) | (r5_classify16(v1.x, v1.y, v1.z, v1.w) << 16);
         }
         if (tid < 3) bmI[nword + tid] = 0;  // r5_window reads up to two words past the last one
         __syncthreads();
 
-        // ---- sort: lines with similar structured-data work share a warp -------------------------------------------
-        // The walk below costs a warp the MAXIMUM number of name="value" pairs over its 32 lines.  The number of '=' ']'
-        // '\\' bytes near the start of a line (counted for free in stage 1) tracks its pairs, so the CTA's lines are
-        // counting-sorted by that estimate (16 keys, descending) and lane t takes the t-th line of the sorted order.
-        bool active = tid < r;
+        // ---- stage 2: one thread per line ------------------------------------------------------------------------
+        // (Counting-sorting the CTA's lines by a work estimate so that a warp's 32 lines have similar pair counts was
+        //  measured: 1.56 vs 1.43 ms per step — the estimate, the two extra barriers and the scattered row stores cost
+        //  more than the shorter walks gain; profiles/r2_notes.md.)
+        const bool active = tid < r;
         int ls = active ? o0 - base : 0;
         int le = active ? o1 - base : 0;
-#ifndef FG_R5_NOSORT  // A/B switch of profiles/variants.sh
-        {
-            uint32_t key = 0;
-            if (active && le > ls) {
-                const int w0 = ls >> 5, w1 = min((le - 1) >> 5, w0 + 7);  // the first 256 bytes hold the structured data of ordinary lines
-                for (int w = w0; w <= w1; ++w) key += cnt8[w];
-                key = min(key, 15u);
-            }
-            const uint32_t within = atomicAdd(&s_hist[key], 1u);
-            __syncthreads();
-            uint32_t before = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < 16; ++k)
-                if (k > key) before += s_hist[k];
-            const uint32_t dest = before + within;
-            s_perm[0][dest] = ls;
-            s_perm[1][dest] = le;
-            s_perm[2][dest] = active ? i : -1;
-            __syncthreads();
-            ls = s_perm[0][tid];
-            le = s_perm[1][tid];
-            i = s_perm[2][tid];
-            active = i >= 0;
-            if (!active) { i = cur; ls = le = 0; }
-        }
-#endif
-
-        // ---- stage 2: one thread per line ------------------------------------------------------------------------
         bool bad_utf8 = false;
         if (P.strip_eol && le > ls) {
             // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
@@ -362,7 +328,7 @@ __global__ void __launch_bounds__(128) post5424_kernel(const __grid_constant__ P
 
 }  // namespace
 
-int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 16 + tile_bytes / 32 + 16; }
+int parse5424_smem_bytes(int tile_bytes) { return tile_bytes + tile_bytes / 8 + 16; }
 
 cudaError_t configure_parse5424(int max_tile_bytes) {
     return cudaFuncSetAttribute(parse5424_kernel<kFastLines, kFastCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -45,17 +45,6 @@ FG_DEV uint32_t r5_flags(uint32_t w) {
     const uint32_t a3 = x + 0x7F7F7F7Fu;                      // bit 7: x != 0        (x <= 0x1E: no carry)
     return (~a2 | a1 | w | ~a3) & 0x80808080u;
 }
-// the same flags plus, in `c2`, the 0x80 flags of the second class alone ('=' ']' '\\' and four rarer bytes): their count is
-// the sort key that groups lines with similar structured-data work into the same warp (fg_parse5424.cu)
-FG_DEV uint32_t r5_flags_c2(uint32_t w, uint32_t& c2) {
-    const uint32_t low = w & 0x7F7F7F7Fu;
-    const uint32_t a2 = low + 0x5D5D5D5Du;
-    const uint32_t a1 = low + 0x01010101u;
-    const uint32_t x = (w & 0x1E1E1E1Eu) ^ 0x1C1C1C1Cu;
-    const uint32_t a3 = x + 0x7F7F7F7Fu;
-    c2 = ~a3 & 0x80808080u;
-    return (~a2 | a1 | w | ~a3) & 0x80808080u;
-}
 // the four 0x80 flags of a word -> bits 28..31 (byte j -> bit 28 + j); bits 24..27 of the product are always 0
 FG_DEV uint32_t r5_nibble_top(uint32_t f) { return f * 0x00204081u; }
 FG_DEV uint32_t r5_gather16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
@@ -65,16 +54,6 @@ FG_DEV uint32_t r5_gather16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) 
 FG_DEV uint32_t r5_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     return r5_gather16(r5_flags(w0), r5_flags(w1), r5_flags(w2), r5_flags(w3));
 }
-#ifndef FG_HOST_EMU
-// bitmap bits of 16 bytes + the number of second-class bytes among them
-FG_DEV uint32_t r5_classify16_count(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t& count) {
-    uint32_t c0, c1, c2, c3;
-    const uint32_t f0 = r5_flags_c2(w0, c0), f1 = r5_flags_c2(w1, c1), f2 = r5_flags_c2(w2, c2), f3 = r5_flags_c2(w3, c3);
-    // the four flag sets sit on bit 7 of every byte: shifted onto disjoint bits they are counted by ONE popcount
-    count = (uint32_t)__popc(c0 | (c1 >> 1) | (c2 >> 2) | (c3 >> 3));
-    return r5_gather16(f0, f1, f2, f3);
-}
-#endif
 // ---- stage 2 ----------------------------------------------------------------------------------------------------
 // 32 bitmap bits starting at tile position t (bit 0 = byte t).  bm needs one readable word past the last granule.
 FG_DEV uint32_t r5_window(const uint32_t* bm, int t) {

@@ -3,7 +3,7 @@
 #   usage: bash profiles/variants.sh          -> flowgger_b200/lib_v_<lines>_<minb>/libflowgger_cuda.so
 set -e
 cd "$(dirname "$0")/.."
-for v in "64 16 102 -DFG_R5_NOSORT" "128 8 102 -DFG_R5_SORTED" "64 14 104 -DFG_R5_SORTED"; do
+for v in "64 14 104" "64 15 102"; do
   set -- $v
   d=flowgger_b200/lib_v_$1_$2${4:+_${4#-DFG_R5_}}
   mkdir -p $d

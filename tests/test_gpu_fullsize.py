@@ -119,11 +119,12 @@ def test_timestamp_bits_vs_python_mini_oracle(native):
     dec = native.BatchDecoder(native.FMT_RFC5424, max_batch_bytes=int(offs[-1]) + (1 << 20), max_batch_lines=n)
     try:
         res = dec.decode(data, offs)
+        status = np.array(res.status)               # the result arrays belong to the context: copy before closing it
+        got = np.array(res.ts).view(np.uint64)
     finally:
         dec.close()
-    assert (res.status == 0).all()
+    assert (status == 0).all()
     raw = data.tobytes()
-    got = res.ts.view(np.uint64)
     bad = 0
     for i in range(n):
         a = raw.index(b" ", int(offs[i])) + 1
