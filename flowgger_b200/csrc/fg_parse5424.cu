@@ -211,15 +211,41 @@ __device__ __forceinline__ void unescape_lines(const Parse5424Params& P, uint32_
         if (lane == 0 && warp_total) abase = atomicAdd(P.counters + K5_ARENA, warp_total);
         abase = __shfl_sync(0xFFFFFFFFu, abase, 0);
         if ((unsigned long long)abase + warp_total > (unsigned long long)P.arena_cap) continue;  // arena overflowed: the batch is redone
+        // The values are rewritten in lock step: round j handles every lane's j-th escaped value, and inside a round the
+        // 32 lanes consume one raw byte per iteration together (a lane per value with its own byte loop ran ~3 lanes wide).
         uint32_t at = abase + inc - need;
-        for (uint32_t e = 0; e < count; ++e) {
-            const unsigned long long v = P.entries[first + e];
-            if (!(v & kE8Header) && (v & kE8Esc)) {
-                const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
-                const uint32_t l = (uint32_t)r5_unescape_to(P.bytes + o0 + ne + 2, ve - (ne + 2), P.arena + at + 2);
-                *reinterpret_cast<uint16_t*>(P.arena + at) = (uint16_t)l;
+        uint32_t e = 0;
+        for (;;) {
+            // next escaped pair of this lane
+            unsigned long long v = 0;
+            bool have = false;
+            for (; e < count; ++e) {
+                v = P.entries[first + e];
+                if (!(v & kE8Header) && (v & kE8Esc)) { have = true; break; }
+            }
+            if (!__any_sync(0xFFFFFFFFu, have)) break;
+            const int ne = (int)((v >> 16) & 0xFFFFu), ve = (int)((v >> 32) & 0xFFFFu);
+            const int len = have ? ve - (ne + 2) : 0;
+            const uint8_t* src = P.bytes + o0 + ne + 2;
+            uint8_t* dst = P.arena + at + 2;
+            int k = 0, o = 0;
+            while (__any_sync(0xFFFFFFFFu, k < len)) {
+                if (k < len) {
+                    const uint32_t c = src[k++];
+                    if (c != '\\') {
+                        dst[o++] = (uint8_t)c;
+                    } else if (k < len) {  // a trailing lone backslash is dropped (rfc5424_decoder.rs:105-125)
+                        const uint32_t d = src[k++];
+                        if (d != '"' && d != '\\' && d != ']') dst[o++] = '\\';
+                        dst[o++] = (uint8_t)d;
+                    }
+                }
+            }
+            if (have) {
+                *reinterpret_cast<uint16_t*>(P.arena + at) = (uint16_t)o;
                 P.entries[first + e] = (v & 0xFFFFFFFFull) | ((unsigned long long)(at >> 1) << 32) | kE8Arena;
-                at += (2u + (uint32_t)(ve - (ne + 2)) + 1u) & ~1u;
+                at += (2u + (uint32_t)len + 1u) & ~1u;
+                ++e;
             }
         }
     }
