@@ -302,8 +302,8 @@ int ensure_format(fg_ctx* c, int fmt) {
 // shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles whatever does not fit in extra rounds
 int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     const double mean = n > 0 ? (double)total_bytes / n : 0.0;
-    // long-line formats: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
-    if (fmt != FG_FMT_RFC5424 && mean > 256.0) return 0;
+    // GELF with long lines: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
+    if (fmt == FG_FMT_GELF && mean > 256.0) return 0;
     const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
 #ifndef FG_TILE_SLACK_PCT  // head room of the tile over the mean span of a CTA's lines (profiles/variants.sh tries others)
 #define FG_TILE_SLACK_PCT 102
@@ -311,7 +311,7 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     long t = (long)(mean * lines * (FG_TILE_SLACK_PCT / 100.0)) + gran;
     t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
-    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : c->max_tile));
+    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : (fmt == FG_FMT_LTSV ? fg::kLtsvMaxTile : c->max_tile)));
     return (int)t;
 }
 
@@ -974,7 +974,7 @@ int fg_decode_encode_gelf(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const 
             E.entry_cap = (uint32_t)std::min<size_t>(c->e8_cap, 0xFFFFFFFFu);
             E.wide_cap = (uint32_t)c->wide_cap;
             E.wentry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
-            E.tile_bytes = tile;
+            E.tile_bytes = std::min(4 * tile, c->max_tile5);  // the encoder's CTAs take 256 lines (4 x the parse kernel's 64)
             FG_CUDA(c, fg::launch_gelf_encode(E, c->d_scan_temp, c->scan_temp_bytes, c->s_comp));
             c->launches += 4;
             FG_CUDA(c, cudaEventRecord(c->ev_k1[k], c->s_comp));

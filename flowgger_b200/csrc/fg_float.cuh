@@ -16,7 +16,7 @@
 namespace fg {
 
 // 10^0 .. 10^22 are exact doubles
-__device__ __constant__ double kPow10Exact[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+static __device__ __constant__ double kPow10Exact[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
 constexpr int kBigLimbs = 128;  // 4096 bits: enough for 768 digits * 10^310 and for the scaled division case
@@ -26,7 +26,7 @@ struct BigNum {
     int n;  // limbs in use
 };
 
-__device__ __noinline__ void big_mul_small_add(BigNum& b, uint32_t m, uint32_t add) {
+static __device__ __noinline__ void big_mul_small_add(BigNum& b, uint32_t m, uint32_t add) {
     uint64_t carry = add;
     for (int k = 0; k < b.n; ++k) {
         const uint64_t t = (uint64_t)b.v[k] * m + carry;
@@ -36,7 +36,7 @@ __device__ __noinline__ void big_mul_small_add(BigNum& b, uint32_t m, uint32_t a
     if (carry && b.n < kBigLimbs) b.v[b.n++] = (uint32_t)carry;
 }
 // b /= d ; returns remainder
-__device__ __noinline__ uint32_t big_div_small(BigNum& b, uint32_t d) {
+static __device__ __noinline__ uint32_t big_div_small(BigNum& b, uint32_t d) {
     uint64_t rem = 0;
     for (int k = b.n - 1; k >= 0; --k) {
         const uint64_t cur = (rem << 32) | b.v[k];
@@ -46,7 +46,7 @@ __device__ __noinline__ uint32_t big_div_small(BigNum& b, uint32_t d) {
     while (b.n > 0 && b.v[b.n - 1] == 0) --b.n;
     return (uint32_t)rem;
 }
-__device__ __noinline__ void big_shl(BigNum& b, int s) {
+static __device__ __noinline__ void big_shl(BigNum& b, int s) {
     if (b.n == 0 || s == 0) return;
     const int ws = s >> 5, bs = s & 31;
     int nn = b.n + ws + 1;
@@ -69,7 +69,7 @@ FG_DEV uint32_t big_bit(const BigNum& b, int i) {  // bit i (0 = LSB); 0 outside
     return (b.v[i >> 5] >> (i & 31)) & 1u;
 }
 // any bit set strictly below bit i ?
-__device__ __noinline__ bool big_any_below(const BigNum& b, int i) {
+static __device__ __noinline__ bool big_any_below(const BigNum& b, int i) {
     if (i <= 0) return false;
     const int w = i >> 5, r = i & 31;
     for (int k = 0; k < w && k < b.n; ++k)
@@ -86,7 +86,7 @@ FG_DEV uint64_t big_extract64(const BigNum& b, int i) {
 
 // Exact: value = (digits of [a,b) skipping '.', as an integer) * 10^q10, sign applied by the caller.
 // `p[a..b)` holds only digits and at most one '.'; leading zeros allowed.
-__device__ __noinline__ double big_decimal_to_f64(bytes_t p, int a, int b, int q10) {
+static __device__ __noinline__ double big_decimal_to_f64(bytes_t p, int a, int b, int q10) {
     BigNum N;
     N.n = 0;
     int nd = 0;           // significant digits accumulated
@@ -170,7 +170,7 @@ __device__ __noinline__ double big_decimal_to_f64(bytes_t p, int a, int b, int q
 struct Pow5 {
     unsigned long long hi, lo;
 };
-__device__ const Pow5 kPow5[651] = {
+static __device__ const Pow5 kPow5[651] = {
 #include "fg_pow5_table.inc"
 };
 
@@ -222,7 +222,7 @@ FG_DEV bool ieq3(bytes_t p, int i, char a, char b, char c) {
 }
 
 // Rust f64::from_str over [a,b).  Returns false on a grammar error.
-__device__ __noinline__ bool parse_f64_rust(bytes_t p, int a, int b, double& out) {
+static __device__ __noinline__ bool parse_f64_rust(bytes_t p, int a, int b, double& out) {
     if (a >= b) return false;
     int i = a;
     bool neg = false;
@@ -309,7 +309,7 @@ __device__ __noinline__ bool parse_f64_rust(bytes_t p, int a, int b, double& out
 struct Pow10Table {
     double v[309];
 };
-__device__ Pow10Table g_pow10;
+static __device__ Pow10Table g_pow10;  // one copy per translation unit; only fg_kernels.cu (GELF) reads and uploads its own
 
 // returns false for NumberOutOfRange
 FG_DEV bool serde_f64_from_parts(bool pos, uint64_t significand, int exponent, double& out) {

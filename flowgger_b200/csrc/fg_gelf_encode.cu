@@ -9,7 +9,8 @@
 // Input = the decoder's device-resident results (compact rows + 8-byte entries + arena, or wide rows); nothing of them
 // travels to the host in this mode.  Launches per chunk of lines:
 //   gelf_size_kernel   one thread per line: exact length of its record (0 for a line the decoder rejected); the bytes of
-//                      the CTA's 64 lines are staged in shared memory by one TMA bulk copy (both kernels)
+//                      the CTA's 256 lines are staged in shared memory by one TMA bulk copy and handed to the threads
+//                      in order of line length (both kernels)
 //   cub exclusive sum  record offsets inside the chunk
 //   gelf_write_kernel  one thread per line writes its record; output bytes are assembled four at a time and stored as
 //                      aligned 32-bit words, so a record costs a quarter of the store instructions / L2 requests of a
@@ -224,17 +225,66 @@ struct SegList {
     }
 };
 
-// `num` (>= 32 bytes, owned by the caller) receives the text of Record.ts and is referenced by a segment
-__device__ __forceinline__ void build_segments(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, uint8_t* num, SegList& L) {
-    L.lit(L_OPEN, 1);
-    bool first = true;
-    int si = 0;
-    Span prev{nullptr, -1};  // last SD name emitted (or skipped)
+// SD pairs in BTreeMap order.  The pairs of a line are gathered once as (4-byte big-endian name prefix, row) and
+// insertion-sorted by prefix (full byte compare only on equal prefixes; stable, so of equal names the LAST one — the one
+// a later insert leaves in the map, gelf_encoder.rs:109 — closes its run).  Lines with more pairs than the local array
+// holds fall back to selecting the next name by scanning all rows (O(pairs^2) full compares).
+constexpr int kLocalPairs = 24;
+struct PairRef {
+    uint32_t key;
+    uint32_t row;
+};
+__device__ __forceinline__ uint32_t name_prefix(Span n) {
+    uint32_t k = 0;
+    for (int j = 0; j < 4; ++j) k = (k << 8) | (j < n.len ? (uint32_t)n.p[j] : 0u);
+    return k;
+}
+
+struct PairCursor {
+    PairRef pr[kLocalPairs];
+    int np = 0, at = 0;
+    bool many = false;
+    Span prev{nullptr, -1};
     bool have_prev = false;
-    for (;;) {
-        // next SD pair in key order: the smallest name greater than `prev`; of equal names the LAST one (a later
-        // BTreeMap insert replaces the earlier value, gelf_encoder.rs:109)
-        Span bn{nullptr, 0}, bv{nullptr, 0};
+
+    __device__ __forceinline__ void init(const GelfEncodeParams& P, const ByteSource& B, const RecView& r) {
+        for (uint32_t e = r.first; e < r.first + r.count; ++e) {
+            Span nm, vl;
+            if (!load_pair(P, B, r, e, nm, vl)) continue;
+            if (np == kLocalPairs) { many = true; break; }
+            const uint32_t key = name_prefix(nm);
+            int j = np++;
+            while (j > 0) {  // stable insertion: move entries that sort strictly after the new one
+                const PairRef q = pr[j - 1];
+                bool after = q.key > key;
+                if (q.key == key) {
+                    Span qn, qv;
+                    load_pair(P, B, r, q.row, qn, qv);
+                    after = cmp_names(qn, nm) > 0;
+                }
+                if (!after) break;
+                pr[j] = q;
+                --j;
+            }
+            pr[j].key = key;
+            pr[j].row = e;
+        }
+    }
+    // next pair in key order with duplicates resolved; false when exhausted
+    __device__ __forceinline__ bool next(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, Span& bn, Span& bv) {
+        if (!many) {
+            while (at < np) {
+                load_pair(P, B, r, pr[at].row, bn, bv);
+                ++at;
+                if (at < np && pr[at].key == pr[at - 1].key) {  // a later pair with the same name replaces this one
+                    Span nn, nv;
+                    load_pair(P, B, r, pr[at].row, nn, nv);
+                    if (cmp_names(nn, bn) == 0) continue;
+                }
+                return true;
+            }
+            return false;
+        }
         bool have = false;
         for (uint32_t e = r.first; e < r.first + r.count; ++e) {
             Span nm, vl;
@@ -246,58 +296,88 @@ __device__ __forceinline__ void build_segments(const GelfEncodeParams& P, const 
                 have = true;
             }
         }
-        if (!have && si >= P.n_static) break;
-        int take_static = 0;  // 0: SD pair, 1: static item, 2: static item and drop the SD pair of the same key
-        if (!have) take_static = 1;
-        else if (si < P.n_static) {
-            const Span key{P.static_blob + P.static_key_off[si], P.static_key_off[si + 1] - P.static_key_off[si]};
-            const int c = cmp_sd_key(bn, key);
-            if (c > 0) take_static = 1;
-            else if (c == 0) {
-                if (P.static_kind[si] == GF_EXTRA) take_static = 2;  // extras are inserted last (gelf_encoder.rs:110-112)
-                else { ++si; }                                       // an SD pair replaces a fixed field of the same key
-            }
-        }
-        if (take_static) {
-            const int kind = P.static_kind[si];
-            // the literal is `,"key":` (for an extra `,"key":"value"`): the comma is skipped for the first item
-            const uint8_t* lit = P.static_blob + P.static_lit_off[si];
-            const int lit_len = P.static_lit_off[si + 1] - P.static_lit_off[si];
-            ++si;
-            if (take_static == 2) { prev = bn; have_prev = true; }
-            if (kind == GF_SDID && !r.has_sd) continue;
-            L.push(lit + (first ? 1 : 0), lit_len - (first ? 1 : 0), false);
-            first = false;
-            switch (kind) {
-                case GF_APP: L.str(r.app); break;
-                case GF_FULL: L.str(r.full); break;
-                case GF_HOST:
-                    if (r.host.len == 0) L.lit(L_UNKNOWN, 9);
-                    else L.str(r.host);
-                    break;
-                case GF_LEVEL: L.lit(L_DIGITS + (int)(r.severity & 7u), 1); break;
-                case GF_PROC: L.str(r.proc); break;
-                case GF_SDID: L.str(r.sd_id); break;
-                case GF_SHORT:
-                    if (r.msg.p == nullptr) L.lit(L_DASH, 3);
-                    else L.str(r.msg);
-                    break;
-                case GF_TS: L.push(num, json_f64(r.ts, num), false); break;
-                case GF_VERSION: L.lit(L_V11, 5); break;
-                default: break;  // GF_EXTRA: the literal was everything
-            }
-            continue;
-        }
-        L.lit(L_PAIR + (first ? 1 : 0), first ? 2 : 3);  // ,"_
-        first = false;
-        L.push(bn.p, bn.len, true);
-        L.lit(L_MID, 3);  // ":"
-        L.push(bv.p, bv.len, true);
-        L.lit(L_QUOTE, 1);
+        return have;
+    }
+    __device__ __forceinline__ void taken(Span bn) {
         prev = bn;
         have_prev = true;
     }
-    L.lit(L_CLOSE, 1);
+};
+
+// `num` (>= 32 bytes, owned by the caller) receives the text of Record.ts and is referenced by a segment.
+// Called by ALL 32 lanes (`live` = this lane has a record).  The loop runs over the STATIC items, which are the same for
+// every record, so the lanes of a warp stay on the same item (the first version merged pair by pair per lane: the lanes
+// drifted apart by their pair counts and every static item ran ~3 lanes wide, profiles/r2_notes.md); the SD pairs that
+// sort before the current item are emitted by an inner loop whose trip count is the warp's maximum.
+__device__ __forceinline__ void build_segments(const GelfEncodeParams& P, const ByteSource& B, const RecView& r, bool live, uint8_t* num,
+                                               SegList& L) {
+    if (live) L.lit(L_OPEN, 1);
+    bool first = true;
+    PairCursor pc;
+    if (live) pc.init(P, B, r);
+    Span bn{nullptr, 0}, bv{nullptr, 0};
+    bool have = live && pc.next(P, B, r, bn, bv);
+    for (int si = 0; si <= P.n_static; ++si) {  // warp-uniform; si == n_static: the pairs after the last static item
+        const bool tail = si == P.n_static;
+        Span key{nullptr, 0};
+        if (!tail) key = Span{P.static_blob + P.static_key_off[si], P.static_key_off[si + 1] - P.static_key_off[si]};
+        int c = 1;
+        for (;;) {
+            c = have ? (tail ? -1 : cmp_sd_key(bn, key)) : 1;
+            const bool emit = have && c < 0;
+            if (!__any_sync(0xFFFFFFFFu, emit)) break;
+            if (emit) {
+                L.lit(L_PAIR + (first ? 1 : 0), first ? 2 : 3);  // ,"_
+                first = false;
+                L.push(bn.p, bn.len, true);
+                L.lit(L_MID, 3);  // ":"
+                L.push(bv.p, bv.len, true);
+                L.lit(L_QUOTE, 1);
+                pc.taken(bn);
+                have = pc.next(P, B, r, bn, bv);
+            }
+        }
+        if (tail) break;
+        const int kind = P.static_kind[si];
+        if (live) {
+            bool take = true;
+            if (c == 0) {
+                if (kind == GF_EXTRA) {  // extras are inserted last (gelf_encoder.rs:110-112): the SD pair of this key is dropped
+                    pc.taken(bn);
+                    have = pc.next(P, B, r, bn, bv);
+                } else {
+                    take = false;  // an SD pair replaces a fixed field of the same key: the next round's pair loop emits it
+                }
+            }
+            if (kind == GF_SDID && !r.has_sd) take = false;
+            if (take) {
+                // the literal is `,"key":` (for an extra `,"key":"value"`): the comma is skipped for the first item
+                const uint8_t* lit = P.static_blob + P.static_lit_off[si];
+                const int lit_len = P.static_lit_off[si + 1] - P.static_lit_off[si];
+                L.push(lit + (first ? 1 : 0), lit_len - (first ? 1 : 0), false);
+                first = false;
+                switch (kind) {  // warp-uniform
+                    case GF_APP: L.str(r.app); break;
+                    case GF_FULL: L.str(r.full); break;
+                    case GF_HOST:
+                        if (r.host.len == 0) L.lit(L_UNKNOWN, 9);
+                        else L.str(r.host);
+                        break;
+                    case GF_LEVEL: L.lit(L_DIGITS + (int)(r.severity & 7u), 1); break;
+                    case GF_PROC: L.str(r.proc); break;
+                    case GF_SDID: L.str(r.sd_id); break;
+                    case GF_SHORT:
+                        if (r.msg.p == nullptr) L.lit(L_DASH, 3);
+                        else L.str(r.msg);
+                        break;
+                    case GF_TS: L.push(num, json_f64(r.ts, num), false); break;
+                    case GF_VERSION: L.lit(L_V11, 5); break;
+                    default: break;  // GF_EXTRA: the literal was everything
+                }
+            }
+        }
+    }
+    if (live) L.lit(L_CLOSE, 1);
 }
 
 // serde_json 0.8 ser.rs escape_bytes: `"` `\` \b \f \n \r \t get a backslash form (returns the second byte), else 0
@@ -357,7 +437,7 @@ __device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const Byt
     int skip = 0;
     for (;;) {
         L.reset(skip);
-        if (live) build_segments(P, B, r, num, L);
+        build_segments(P, B, r, live, num, L);
         run_segments(L, live, s);
         skip += kMaxSegs;
         if (!__any_sync(0xFFFFFFFFu, live && L.idx > skip)) break;
@@ -365,10 +445,22 @@ __device__ __forceinline__ void emit_record(const GelfEncodeParams& P, const Byt
     if (live) s.finish();
 }
 
-// Both kernels stage the byte span of the CTA's 64 lines in shared memory with one TMA bulk copy, like the parse kernel:
+// Both kernels stage the byte span of the CTA's lines in shared memory with one TMA bulk copy, like the parse kernel:
 // a lane reading ITS line byte by byte from global memory would cost 32 L1 wavefronts per load instruction (32 lanes,
 // 32 different lines); from the tile it is one shared-memory access.  A span larger than the tile is read from global.
-constexpr int kEncLines = 64;
+//
+// The byte loop of a warp runs as long as its LONGEST record, and record lengths follow the line lengths (full_message
+// is the line, short_message its tail): with lines in input order a warp ran ~4x longer than its mean record.  So a CTA
+// takes 256 lines and hands them to its threads in order of line length (counting sort over 16-byte classes): the 32
+// lines of a warp are neighbours in length.  Which thread emits which line changes nothing in the output.
+constexpr int kEncLines = 256;
+constexpr int kLenClasses = 64;
+
+struct EncShared {
+    uint64_t mbar;
+    uint32_t hist[kLenClasses];
+    uint16_t perm[kEncLines];
+};
 
 __device__ __forceinline__ ByteSource stage_lines(const GelfEncodeParams& P, uint8_t* tile, uint64_t* mbar, int first, int last) {
     const int o_first = P.offsets[first], o_last = P.offsets[last];
@@ -389,14 +481,43 @@ __device__ __forceinline__ ByteSource stage_lines(const GelfEncodeParams& P, uin
     return ByteSource{P.bytes, 0};
 }
 
+// line handled by this thread: the CTA's lines in order of length class (-1: none)
+__device__ __forceinline__ int sorted_line(const GelfEncodeParams& P, EncShared& sh, int first, int last) {
+    const int tid = threadIdx.x;
+    if (tid < kLenClasses) sh.hist[tid] = 0;
+    __syncthreads();
+    const int i = first + tid;
+    uint32_t cls = 0, rank = 0;
+    if (i < last) {
+        cls = min((uint32_t)(P.offsets[i + 1] - P.offsets[i]) >> 4, (uint32_t)kLenClasses - 1u);
+        rank = atomicAdd(&sh.hist[cls], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 class counts by one warp (two classes per lane)
+        const uint32_t a = sh.hist[2 * tid], b = sh.hist[2 * tid + 1];
+        uint32_t x = a + b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (tid >= d) x += y;
+        }
+        sh.hist[2 * tid] = x - a - b;
+        sh.hist[2 * tid + 1] = x - b;
+    }
+    __syncthreads();
+    if (i < last) sh.perm[sh.hist[cls] + rank] = (uint16_t)tid;
+    __syncthreads();
+    return tid < last - first ? first + (int)sh.perm[tid] : -1;
+}
+
 __global__ void __launch_bounds__(kEncLines) gelf_size_kernel(const __grid_constant__ GelfEncodeParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) EncShared sh;
     if (*P.bad_offsets) return;
     const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
-    const ByteSource B = stage_lines(P, tile, &mbar, first, last);
-    const int i = first + threadIdx.x;
-    const bool valid = i < last;
+    const ByteSource B = stage_lines(P, tile, &sh.mbar, first, last);
+    const int i = sorted_line(P, sh, first, last);
+    const bool valid = i >= 0;
     RecView r;
     r.ok = false;
     if (valid) load_view(P, B, i, r);
@@ -416,12 +537,12 @@ __global__ void gelf_base_kernel(const __grid_constant__ GelfEncodeParams P) {
 
 __global__ void __launch_bounds__(kEncLines) gelf_write_kernel(const __grid_constant__ GelfEncodeParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) EncShared sh;
     if (*P.bad_offsets) return;
     const int first = blockIdx.x * kEncLines, last = min(P.n, first + kEncLines);
-    const ByteSource B = stage_lines(P, tile, &mbar, first, last);
-    const int i = first + threadIdx.x;
-    const bool valid = i < last;
+    const ByteSource B = stage_lines(P, tile, &sh.mbar, first, last);
+    const int i = sorted_line(P, sh, first, last);
+    const bool valid = i >= 0;
     unsigned long long at = 0;
     uint32_t len = 0;
     if (valid) {

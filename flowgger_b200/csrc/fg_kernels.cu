@@ -18,7 +18,6 @@
 #include "fg_common.cuh"
 #include "fg_tma.cuh"
 #include "fg_rfc5424.cuh"
-#include "fg_ltsv.cuh"
 #include "fg_gelf.cuh"
 #include "fg_status.h"
 
@@ -50,21 +49,6 @@ template <int FMT>
 struct Format;
 
 struct NoShared {};
-
-template <>
-struct Format<1> {  // LTSV
-    typedef NoShared Shared;
-    static FG_DEV void init_shared(Shared&) {}
-    // a pair needs >= 1 input byte plus its tab: at most len/2 + 1 rows per line
-    static FG_DEV uint32_t scratch_index(int line_off, int line_idx) { return (uint32_t)line_off / 2u + (uint32_t)line_idx; }
-    static FG_DEV void parse(bytes_t p, int len, int line_off, int line_idx, bool active, bool /*in_smem*/, Shared&, LineResult& r,
-                             const EntrySink& tmp, const ParseParams& P) {
-        ltsv_parse_line(p, len, line_off, scratch_index(line_off, line_idx), active, P.ltsv, r, tmp);
-    }
-    static FG_DEV void expand(const LineResult&, int, uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
-        copy_rows(src, dst, n, sink, tmp);
-    }
-};
 
 template <>
 struct Format<2> {  // GELF
@@ -209,7 +193,7 @@ cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424) {
     if (e != cudaSuccess) return e;
     e = configure_gelf_encode(max_tile5424);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(parse_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
+    e = configure_parse_ltsv(kLtsvMaxTile);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(parse_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_tile_bytes);
     return e;
@@ -236,10 +220,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     const int lines = lines_per_cta(fmt);
     const int grid = (p.n + lines - 1) / lines;
     switch (fmt) {
-        case 1:
-            if (p.tile_bytes > 0) parse_kernel<1, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
-            else parse_kernel<1, false><<<grid, kLinesPerCta, 0, stream>>>(p);
-            break;
+        case 1: return launch_parse_ltsv(p, stream);
         case 2:
             if (p.tile_bytes > 0) parse_kernel<2, true><<<grid, kLinesPerCta, p.tile_bytes, stream>>>(p);
             else parse_kernel<2, false, kGelfUnstagedCtasPerSm><<<grid, kLinesPerCta, 0, stream>>>(p);
@@ -251,7 +232,7 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
 
 const char* kernel_build_info() {
     return "flowgger_b200 parse kernels: sm_100a, RFC5424: structural bitmap + bit-walk over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse5424_kernel, post5424_kernel, gelf_size_kernel, gelf_write_kernel, parse_kernel<ltsv>, parse_kernel<gelf>]";
+           "kernels=[parse5424_kernel, post5424_kernel, gelf_size_kernel, gelf_write_kernel, parse_ltsv_kernel, parse_kernel<gelf>]";
 }
 
 }  // namespace fg

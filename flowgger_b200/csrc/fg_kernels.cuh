@@ -154,9 +154,20 @@ constexpr int kGelfUnstagedCtasPerSm = 16;
 #endif
 constexpr int kRfc5424LinesPerCta = FG_R5_LINES;
 constexpr int kRfc5424CtasPerSm = FG_R5_MINB;
-constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : kLinesPerCta; }
+// LTSV (fg_parse_ltsv.cu): 64-line CTAs; the staging area holds kLtsvStageSlots side-table rows per CTA round
+#ifndef FG_LTSV_LINES
+#define FG_LTSV_LINES 64
+#endif
+constexpr int kLtsvLinesPerCta = FG_LTSV_LINES;
+constexpr int kLtsvStageSlots = kLtsvLinesPerCta * 24;
+constexpr int kLtsvMaxTile = 65024;  // tile positions are packed into 16 bits
+constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : kLinesPerCta); }
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
+// LTSV on the bitmap pipeline (fg_parse_ltsv.cu); launch_parse routes fmt 1 here
+cudaError_t launch_parse_ltsv(const ParseParams& p, cudaStream_t stream);
+cudaError_t configure_parse_ltsv(int max_tile_bytes);
+int parse_ltsv_smem_bytes(int tile_bytes, bool typed);
 // offsets[0 .. n] must be non-decreasing and within [0, max_bytes]; otherwise *flag |= 1 (the parse kernels then return at once)
 cudaError_t launch_check_offsets(const int32_t* d_offsets, int n, long long max_bytes, uint32_t* d_flag, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424);

@@ -19,7 +19,7 @@ namespace fg {
 
 // "[day padding:none]/[month repr:short]/[year]:[hour]:[minute]:[second](.[subsecond]) [offset_hour sign:mandatory][offset_minute]"
 // (ltsv_decoder.rs:239-247), `time` 0.3 format-description semantics.
-__device__ __noinline__ bool parse_english_time(bytes_t p, int a, int b, bool with_subsecond, double& ts) {
+static __device__ __noinline__ bool parse_english_time(bytes_t p, int a, int b, bool with_subsecond, double& ts) {
     int i = a;
     DateTime t;
     t.nanos = 0;
@@ -85,7 +85,7 @@ __device__ __noinline__ bool parse_english_time(bytes_t p, int a, int b, bool wi
 }
 
 // parse_ts :263-267: f64::from_str, then RFC3339, then the two English forms
-__device__ __noinline__ bool ltsv_parse_ts(bytes_t p, int a, int b, double& ts) {
+static __device__ __noinline__ bool ltsv_parse_ts(bytes_t p, int a, int b, double& ts) {
     if (parse_f64_rust(p, a, b, ts)) return true;
     if (parse_rfc3339(p, a, b, ts)) return true;
     if (parse_english_time(p, a, b, false, ts)) return true;
@@ -100,7 +100,7 @@ FG_DEV bool key_is(bytes_t p, int a, int n, const char* lit, int litn) {
 }
 
 // schema.get(name) :129 — linear scan of the (small) configured key set; returns the fg_ltsv_type or 0 (string)
-__device__ __noinline__ int ltsv_schema_type(bytes_t p, int a, int n, const LtsvDeviceConfig& cfg) {
+static __device__ __noinline__ int ltsv_schema_type(bytes_t p, int a, int n, const LtsvDeviceConfig& cfg) {
     for (int k = 0; k < cfg.n_schema; ++k) {
         const int o = cfg.name_off[k], l = cfg.name_off[k + 1] - o;
         if (l != n) continue;
@@ -111,7 +111,7 @@ __device__ __noinline__ int ltsv_schema_type(bytes_t p, int a, int n, const Ltsv
     return 0;
 }
 // !name.ends_with(suffix) :131 etc.
-__device__ __noinline__ bool ltsv_needs_suffix(bytes_t p, int a, int n, int type, const LtsvDeviceConfig& cfg) {
+static __device__ __noinline__ bool ltsv_needs_suffix(bytes_t p, int a, int n, int type, const LtsvDeviceConfig& cfg) {
     if (!((cfg.suffix_present >> type) & 1u)) return false;
     const int o = cfg.suffix_off[type], l = cfg.suffix_off[type + 1] - o;
     if (l > n) return true;
@@ -122,7 +122,7 @@ __device__ __noinline__ bool ltsv_needs_suffix(bytes_t p, int a, int n, int type
 
 
 // typed value of a schema key (:138-195): returns FG_ST_OK and the 8 value bytes, or the reference's type error
-__device__ __noinline__ uint32_t ltsv_parse_typed(bytes_t p, int va, int vb, int type, unsigned long long& val) {
+static __device__ __noinline__ uint32_t ltsv_parse_typed(bytes_t p, int va, int vb, int type, unsigned long long& val) {
     if (type == 1) {  // bool::from_str: exactly "true" / "false"
         if (key_is(p, va, vb - va, "true", 4)) { val = 1; return FG_ST_OK; }
         if (key_is(p, va, vb - va, "false", 5)) { val = 0; return FG_ST_OK; }

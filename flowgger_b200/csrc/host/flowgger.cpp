@@ -847,13 +847,15 @@ int fgh_dump_out(void* d, const fg_batch_out* out, const uint8_t* bytes, const i
 
 // same dump from bare result arrays (no context, no device): lets the CPU test-suite run the product's materialiser
 // over rows produced by the device-logic emulation (tests/emu)
-int fgh_dump_records(int fmt, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, uint8_t** out_buf,
-                     int64_t** out_offsets) {
+int fgh_dump_records(int fmt, const fg_batch_out* out, const uint8_t* bytes, const int32_t* offsets, const char* const* ltsv_suffix,
+                     uint8_t** out_buf, int64_t** out_offsets) {
     const int64_t n = out->n;
     std::string all;
     int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
     offs[0] = 0;
-    const std::string suffix[5];
+    std::string suffix[5];  // input.ltsv_suffixes by fg_ltsv_type (nullptr: none)
+    for (int t = 1; t < 5 && ltsv_suffix; ++t)
+        if (ltsv_suffix[t]) suffix[t] = ltsv_suffix[t];
     std::vector<std::string> fx;
     for (int64_t i = 0; i < n; ++i) {
         fx.clear();

@@ -119,7 +119,7 @@ def load_host() -> C.CDLL:
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.fgh_dump_range.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
-        L.fgh_dump_records.argtypes = [C.c_int, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+        L.fgh_dump_records.argtypes = [C.c_int, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p)]
         L.fgh_materialize_bench.restype = C.c_double
         L.fgh_materialize_bench.argtypes = [C.c_void_p, C.POINTER(FgBatchOut), C.c_void_p, C.c_void_p, C.c_int]
@@ -419,11 +419,16 @@ class BatchDecoder:
         return float(self.H.fgh_materialize_bench(self._h, C.byref(res.raw), _ptr(data), _ptr(offsets), nthreads))
 
 
-def dump_records(fmt: int, out: FgBatchOut, data: np.ndarray, offsets: np.ndarray) -> tuple[bytes, np.ndarray]:
-    """The product's Record materialiser + canonical dump over bare result arrays (no device, no context)."""
+def dump_records(fmt: int, out: FgBatchOut, data: np.ndarray, offsets: np.ndarray,
+                 ltsv_suffix: list | None = None) -> tuple[bytes, np.ndarray]:
+    """The product's Record materialiser + canonical dump over bare result arrays (no device, no context).
+    ltsv_suffix: 5 entries indexed by fg_ltsv_type (bytes or None)."""
     H = load_host()
     pb, po = C.c_void_p(), C.c_void_p()
-    H.fgh_dump_records(fmt, C.byref(out), _ptr(data), _ptr(offsets), C.byref(pb), C.byref(po))
+    suf = None
+    if ltsv_suffix is not None:
+        suf = (C.c_char_p * 5)(*[s if s is None else bytes(s) for s in ltsv_suffix])
+    H.fgh_dump_records(fmt, C.byref(out), _ptr(data), _ptr(offsets), suf, C.byref(pb), C.byref(po))
     try:
         offs = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_int64)), shape=(out.n + 1,)).copy()
         buf = C.string_at(pb, int(offs[-1]))

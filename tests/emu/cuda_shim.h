@@ -9,6 +9,8 @@
 
 #define __device__
 #define __host__
+#define __noinline__
+#define __constant__
 #define __forceinline__ inline
 #define FG_DEV static inline
 
@@ -42,3 +44,8 @@ static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; 
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+using std::isinf;

@@ -1,7 +1,8 @@
-"""Loader of tests/emu/libfg_emu.so — the CPU emulation of the RFC5424 device logic (TEST INFRASTRUCTURE).
+"""Loader of tests/emu/libfg_emu.so — the CPU emulation of the RFC5424 and LTSV device logic (TEST INFRASTRUCTURE).
 
-The library is the product's walker sources (flowgger_b200/csrc/fg_r5fast.cuh, fg_rfc5424.cuh) compiled with g++ plus a
-driver that replays the CTA rounds of parse5424_kernel one lane at a time.  Only tests import this module.
+The library is the product's walker sources (flowgger_b200/csrc/fg_r5fast.cuh, fg_rfc5424.cuh, fg_ltsvfast.cuh, fg_ltsv.cuh)
+compiled with g++ plus drivers that replay the CTA rounds of parse5424_kernel / parse_ltsv_kernel one lane at a time.
+Only tests import this module.
 """
 from __future__ import annotations
 
@@ -19,11 +20,11 @@ _lib = None
 def build(force: bool = False) -> Path:
     so = HERE / "libfg_emu.so"
     csrc = REPO / "flowgger_b200" / "csrc"
-    srcs = [HERE / "emu_r5.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h"] + sorted(csrc.glob("*.cuh")) + \
-        sorted(csrc.glob("*.h"))
+    srcs = [HERE / "emu_r5.cpp", HERE / "emu_ltsv.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h"] + \
+        sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h"))
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
-                        str(HERE / "emu_r5.cpp"), "-I", str(REPO / "include")], check=True)
+                        str(HERE / "emu_r5.cpp"), str(HERE / "emu_ltsv.cpp"), "-I", str(REPO / "include")], check=True)
     return so
 
 
@@ -33,6 +34,8 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(build()))
         _lib.emu5424_classify16.restype = C.c_uint32
         _lib.emu5424_classify16.argtypes = [C.c_void_p]
+        _lib.emu_ltsv_classify16.restype = C.c_uint32
+        _lib.emu_ltsv_classify16.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -57,3 +60,39 @@ def decode_dump(native, data: np.ndarray, offsets: np.ndarray, tile_bytes: int =
     finally:
         lib().emu5424_free(C.byref(out))
     return buf, offs, info
+
+
+LTSV_TYPES = {"string": 0, "bool": 1, "f64": 2, "i64": 3, "u64": 4}
+
+
+def ltsv_classify16(block: bytes) -> tuple[int, int]:
+    """(TAB mask, ':' mask) of a 16-byte granule."""
+    assert len(block) == 16
+    buf = C.create_string_buffer(block, 16)
+    v = int(lib().emu_ltsv_classify16(buf))
+    return v & 0xFFFF, v >> 16
+
+
+def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict | None = None, suffixes: dict | None = None,
+                     tile_bytes: int = 28160, strip_eol: int = 0, invalid: np.ndarray | None = None):
+    """Emulated LTSV decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser."""
+    from flowgger_b200.native import FgBatchOut, dump_records
+    out = FgBatchOut()
+    n = len(offsets) - 1
+    items = list((schema or {}).items())
+    names = (C.c_char_p * max(len(items), 1))(*[k.encode() for k, _ in items])
+    types = (C.c_int32 * max(len(items), 1))(*[LTSV_TYPES[v.lower()] for _, v in items])
+    suf = [None] * 5
+    for k, v in (suffixes or {}).items():
+        suf[LTSV_TYPES[k.lower()]] = v.encode()
+    csuf = (C.c_char_p * 5)(*suf)
+    info = (C.c_int32 * 2)()
+    lib().emu_ltsv_decode(C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n, tile_bytes, strip_eol,
+                          C.c_void_p(invalid.ctypes.data) if invalid is not None else None, 1 if schema is not None else 0,
+                          len(items), names, types, csuf, C.byref(out), info)
+    try:
+        buf, offs = dump_records(native.FMT_LTSV, out, data, offsets, ltsv_suffix=suf)
+        d = {"n_entries": out.n_entries, "rounds": int(info[0]), "direct": int(info[1])}
+    finally:
+        lib().emu_ltsv_free(C.byref(out))
+    return buf, offs, d
