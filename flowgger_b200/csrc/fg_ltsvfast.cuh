@@ -55,12 +55,71 @@ FG_DEV unsigned long long lt_pack_entry(int ka, int kn, int vl, uint32_t meta) {
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------------------------
+// the first 8 bytes at p (any alignment), little-endian; reads up to 11 bytes past p (tile + bitmaps are contiguous)
+FG_DEV unsigned long long lt_load8(const uint8_t* p) {
+#ifdef FG_HOST_EMU
+    unsigned long long v;
+    memcpy(&v, p, 8);
+    return v;
+#else
+    const uint32_t sh = ((uint32_t)(size_t)p & 3u) * 8u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p - ((size_t)p & 3u));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+#endif
+}
+
+// The schema (ltsv_decoder.rs:19-22) as the walker reads it: from shared memory when the kernel staged it (`names` etc.
+// then point into the CTA's copy), with two cheap filters in front of the byte compares — a key can only be a schema key
+// if its length and its first byte occur in the schema.
+struct LtsvSchemaView {
+    const uint8_t* names;
+    const int32_t* name_off;
+    const int32_t* types;
+    int n;
+    uint32_t len_mask;        // bit min(len, 31)
+    const uint32_t* first;    // [8] 256-bit set of first bytes (nullptr: no filter)
+};
+// the two filters of a schema (one thread)
+FG_DEV void lt_schema_filters(const uint8_t* names, const int32_t* name_off, int n, uint32_t& len_mask, uint32_t* first /* [8] */) {
+    len_mask = 0;
+    for (int k = 0; k < 8; ++k) first[k] = 0;
+    for (int k = 0; k < n; ++k) {
+        const int o = name_off[k], l = name_off[k + 1] - o;
+        len_mask |= 1u << (l < 31 ? l : 31);
+        if (l > 0) first[names[o] >> 5] |= 1u << (names[o] & 31u);
+    }
+}
+FG_DEV int lt_schema_type(bytes_t p, int a, int n, unsigned long long k8, const LtsvSchemaView& S) {
+    if (!((S.len_mask >> (n < 31 ? n : 31)) & 1u)) return 0;
+    if (S.first != nullptr && n > 0) {
+        const uint32_t c = (uint32_t)(k8 & 0xFFu);
+        if (!((S.first[c >> 5] >> (c & 31u)) & 1u)) return 0;
+    }
+    for (int k = 0; k < S.n; ++k) {
+        const int o = S.name_off[k], l = S.name_off[k + 1] - o;
+        if (l != n) continue;
+        bool eq = true;
+        for (int j = 0; j < n && eq; ++j) eq = S.names[o + j] == p[a + j];
+        if (eq) return S.types[k];
+    }
+    return 0;
+}
+
 // All 32 lanes of a warp must call this (idle lanes with active_line = false).  T = the tile, [ls, le) the line inside it
 // (le - ls < 65536).  `stage` / `stage_val` = this line's reserved slots (>= #tabs + 1).  Result spans are relative to ls,
 // exactly as ltsv_parse_line (fg_ltsv.cuh) reports them.
+//
+// The part loop holds NO per-key work that only a few lanes need: the four reserved keys are recognised branch-free from
+// the first 8 key bytes; `host` / `message` are two predicated moves; the values of `time`, `level` and of typed schema
+// keys are only PARKED (position, length, part) and parsed after the loop in lock step — one phase per kind, so all lanes
+// run the same parser.  (The first version parsed them where they stood: ~2 of 32 lanes active, 386 warp-instructions per
+// line, profiles/r2_notes.md.)  Evaluation order is preserved: the reference returns at the FIRST failing part, so a parked
+// item is evaluated iff no error was found at an earlier part, and an earlier failure replaces a later one.
 template <bool TYPED>
 FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC, int ls, int le, bool active_line,
-                      const LtsvDeviceConfig& cfg, LineResult& r, unsigned long long* stage, unsigned long long* stage_val) {
+                      const LtsvDeviceConfig& cfg, const LtsvSchemaView& S, LineResult& r, unsigned long long* stage,
+                      unsigned long long* stage_val) {
     r.ts = 0.0;
     r.facility = 0xFFu;
     r.severity = 0xFFu;
@@ -77,11 +136,13 @@ FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC
     // iterator over the TABs at or after `part`
     int tw = ls >> 5;
     uint32_t trem = active ? bmT[tw] & (0xFFFFFFFFu << (ls & 31)) : 0u;
-    // the `time` value and up to four typed values are parsed AFTER the part loop, in lock step (fg_ltsv.cuh explains why)
+    // parked values: `time`, `level`, and two typed values per schema type (slot = 2 * (type - 1) + {0, 1})
     int ts_a = -1, ts_b = -1, ts_part = 0;
-    uint32_t np = 0;
-    int t_va0 = 0, t_va1 = 0, t_va2 = 0, t_va3 = 0, t_pt0 = 0, t_pt1 = 0, t_pt2 = 0, t_pt3 = 0;
-    uint32_t t_pk0 = 0, t_pk1 = 0, t_pk2 = 0, t_pk3 = 0;
+    int lv_a = -1, lv_b = -1, lv_part = 0;
+    int pk_va[8], pk_pt[8];
+    uint32_t pk_info[8];  // value length | row << 16; 0xFFFFFFFF = empty
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { pk_va[q] = 0; pk_pt[q] = 0; pk_info[q] = 0xFFFFFFFFu; }
     const bytes_t p = T;
     while (fg_any(active)) {  // line.split('\t') :94
         // end of this part: the next TAB below le, else le
@@ -122,49 +183,51 @@ FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC
                 flags |= 0x02u;  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
             } else {
                 const int ka = part, kn = colon - part, va = colon + 1, vb = pe;
-                // the four reserved keys differ in (length, first byte): one cheap test rejects ordinary keys
-                const uint32_t k0 = kn > 0 ? p[ka] : 0u;
-                const bool maybe = (kn == 4 && (k0 == 't' || k0 == 'h')) || (kn == 7 && k0 == 'm') || (kn == 5 && k0 == 'l');
-                if (maybe && key_is(p, ka, kn, "time", 4)) {  // :104-111
-                    if (ts_a >= 0) {  // an earlier `time` is still pending: it is evaluated first (a failure returns there)
-                        if (ltsv_parse_ts(p, ts_a, ts_b, r.ts)) have_ts = true;
+                const unsigned long long k8 = lt_load8(p + ka);
+                const uint32_t k4 = (uint32_t)k8;
+                const bool is_time = kn == 4 && k4 == 0x656D6974u;                                       // "time"  :104
+                const bool is_host = kn == 4 && k4 == 0x74736F68u;                                       // "host"
+                const bool is_msg = kn == 7 && (k8 & 0x00FFFFFFFFFFFFFFull) == 0x006567617373656Dull;    // "message"
+                const bool is_level = kn == 5 && (k8 & 0x000000FFFFFFFFFFull) == 0x0000006C6576656Cull;  // "level"  :114
+                if (is_host) { r.host_o = va - ls; r.host_l = vb - va; }
+                if (is_msg) { r.msg_o = va - ls; r.msg_l = vb - va; }
+                if (is_time) {
+                    if (ts_a >= 0) {  // an earlier `time` is still parked: it is evaluated first (a failure returns there)
+                        int a = ts_a, b = ts_b;
+                        if (b - a >= 2 && p[a] == '[' && p[b - 1] == ']') { ++a; --b; }
+                        if (ltsv_parse_ts(p, a, b, r.ts)) have_ts = true;
                         else { status = FG_EL_TS; err_pos = ts_part; err_set = true; }
                     }
-                    if (status == FG_ST_OK) {
-                        ts_a = va;
-                        ts_b = vb;
-                        ts_part = part;
-                        if (ts_b - ts_a >= 2 && p[ts_a] == '[' && p[ts_b - 1] == ']') { ++ts_a; --ts_b; }
-                    } else {
-                        ts_a = -1;
+                    ts_a = status == FG_ST_OK ? va : -1;
+                    ts_b = vb;
+                    ts_part = part;
+                } else if (is_level) {
+                    if (lv_a >= 0) {  // same for an earlier `level` (:114-121)
+                        uint32_t sev;
+                        if (!parse_u8(p, lv_a, lv_b, sev)) { status = FG_EL_SEV; err_pos = lv_part; err_set = true; }
+                        else if (sev > 7u) { status = FG_EL_SEV_HIGH; err_pos = lv_part; err_set = true; }
+                        else r.severity = sev;
                     }
-                } else if (maybe && key_is(p, ka, kn, "host", 4)) {
-                    r.host_o = va - ls;
-                    r.host_l = vb - va;
-                } else if (maybe && key_is(p, ka, kn, "message", 7)) {
-                    r.msg_o = va - ls;
-                    r.msg_l = vb - va;
-                } else if (maybe && key_is(p, ka, kn, "level", 5)) {  // :114-121
-                    uint32_t sev;
-                    if (!parse_u8(p, va, vb, sev)) status = FG_EL_SEV;
-                    else if (sev > 7u) status = FG_EL_SEV_HIGH;
-                    else r.severity = sev;
-                } else {  // :122-199
+                    lv_a = status == FG_ST_OK ? va : -1;
+                    lv_b = vb;
+                    lv_part = part;
+                } else if (!is_host && !is_msg) {  // :122-199
                     uint32_t meta = 0;
                     bool deferred = false;
                     unsigned long long val = 0;
                     if (TYPED) {
-                        const int type = cfg.has_schema ? ltsv_schema_type(p, ka, kn, cfg) : 0;
-                        meta = (uint32_t)type;  // FG_TAG_* == fg_ltsv_type
-                        if (type != 0 && ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
+                        const int type = lt_schema_type(p, ka, kn, k8, S);
                         if (type != 0) {
-                            if (np < 4u && n < 256u) {
-                                const uint32_t packed = (uint32_t)(vb - va) | ((uint32_t)type << 20) | (n << 24);
-                                if (np == 0u) { t_va0 = va; t_pk0 = packed; t_pt0 = part; }
-                                else if (np == 1u) { t_va1 = va; t_pk1 = packed; t_pt1 = part; }
-                                else if (np == 2u) { t_va2 = va; t_pk2 = packed; t_pt2 = part; }
-                                else { t_va3 = va; t_pk3 = packed; t_pt3 = part; }
-                                ++np;
+                            meta = (uint32_t)type;  // FG_TAG_* == fg_ltsv_type
+                            if (ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
+                            int q = -1;  // first free slot of this type (static indices: the arrays stay in registers)
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (q < 0 && (u >> 1) == type - 1 && pk_info[u] == 0xFFFFFFFFu) q = u;
+                            if (q >= 0 && n < 65535u) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    if (u == q) { pk_va[u] = va; pk_pt[u] = part; pk_info[u] = (uint32_t)(vb - va) | (n << 16); }
                                 deferred = true;
                             } else {
                                 status = ltsv_parse_typed(p, va, vb, type, val);
@@ -179,7 +242,7 @@ FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC
                 }
             }
             if (status != FG_ST_OK) {
-                if (!err_set) err_pos = part;  // the error belongs to the current part (unless an earlier `time` already failed)
+                if (!err_set) err_pos = part;  // the error belongs to the current part (unless an earlier parked value failed)
                 active = false;
             } else if (pe >= le) {
                 active = false;
@@ -188,31 +251,41 @@ FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC
             }
         }
     }
-    // Deferred work, in lock step.  All of it is pure, so it is evaluated even when a later part already failed; the
-    // reference returns at the FIRST failing part, i.e. the candidate error with the smallest part position wins.
+    // Parked work, in lock step.  All of it is pure, so it is evaluated even when a later part already failed.
     {
         const bool pend = active_line && ts_a >= 0 && (status == FG_ST_OK || ts_part < err_pos);
         if (fg_any(pend)) {
             if (pend) {
+                int a = ts_a, b = ts_b;
+                if (b - a >= 2 && p[a] == '[' && p[b - 1] == ']') { ++a; --b; }  // :105-109
                 double t;
-                if (ltsv_parse_ts(p, ts_a, ts_b, t)) { r.ts = t; have_ts = true; }
+                if (ltsv_parse_ts(p, a, b, t)) { r.ts = t; have_ts = true; }
                 else { status = FG_EL_TS; err_pos = ts_part; }
+            }
+        }
+    }
+    {
+        const bool pend = active_line && lv_a >= 0 && (status == FG_ST_OK || lv_part < err_pos);
+        if (fg_any(pend)) {
+            if (pend) {
+                uint32_t sev;
+                if (!parse_u8(p, lv_a, lv_b, sev)) { status = FG_EL_SEV; err_pos = lv_part; }
+                else if (sev > 7u) { status = FG_EL_SEV_HIGH; err_pos = lv_part; }
+                else r.severity = sev;
             }
         }
     }
     if (TYPED) {
 #pragma unroll
-        for (uint32_t sl = 0; sl < 4u; ++sl) {
-            const int va = sl == 0u ? t_va0 : (sl == 1u ? t_va1 : (sl == 2u ? t_va2 : t_va3));
-            const uint32_t pk = sl == 0u ? t_pk0 : (sl == 1u ? t_pk1 : (sl == 2u ? t_pk2 : t_pk3));
-            const int pt = sl == 0u ? t_pt0 : (sl == 1u ? t_pt1 : (sl == 2u ? t_pt2 : t_pt3));
-            const bool has = active_line && sl < np && (status == FG_ST_OK || pt < err_pos);
+        for (int q = 0; q < 8; ++q) {  // slots 2t, 2t+1 hold values of schema type t + 1: one parser per phase
+            const uint32_t info = pk_info[q];
+            const bool has = active_line && info != 0xFFFFFFFFu && (status == FG_ST_OK || pk_pt[q] < err_pos);
             if (fg_any(has)) {
                 if (has) {
                     unsigned long long val = 0;
-                    const uint32_t st = ltsv_parse_typed(p, va, va + (int)(pk & 0xFFFFFu), (int)((pk >> 20) & 7u), val);
-                    if (st == FG_ST_OK) stage_val[pk >> 24] = val;
-                    else { status = st; err_pos = pt; }
+                    const uint32_t st = ltsv_parse_typed(p, pk_va[q], pk_va[q] + (int)(info & 0xFFFFu), q / 2 + 1, val);
+                    if (st == FG_ST_OK) stage_val[info >> 16] = val;
+                    else { status = st; err_pos = pk_pt[q]; }
                 }
             }
         }

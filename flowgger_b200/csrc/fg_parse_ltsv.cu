@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kLines = kLtsvLinesPerCta;
 constexpr int kStageSlots = kLtsvStageSlots;
+constexpr int kSchemaKeys = 64, kSchemaBlob = 1024, kSuffixBlob = 64;  // larger schemas are read from global memory
 
 // scratch table -> side table (the direct path only)
 __device__ __forceinline__ void copy_rows_direct(uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
@@ -51,6 +52,14 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
     __shared__ uint32_t s_ebase, s_slots;
     __shared__ uint32_t line_slot[LINES];   // first staging slot | rows << 16
     __shared__ uint32_t line_dense[LINES];  // exclusive sum of the rows of the lines before this one
+    // TYPED: the CTA's copy of the schema and the suffixes (a few hundred bytes) — the walker compares keys against
+    // shared memory instead of pulling the schema through L1 from every lane
+    __shared__ uint8_t s_names[TYPED ? kSchemaBlob : 4];
+    __shared__ int32_t s_name_off[TYPED ? kSchemaKeys + 1 : 1];
+    __shared__ int32_t s_types[TYPED ? kSchemaKeys : 1];
+    __shared__ uint8_t s_suffix[TYPED ? kSuffixBlob : 4];
+    __shared__ uint32_t s_first[8];
+    __shared__ uint32_t s_len_mask;
 
     const int tid = threadIdx.x;
     const int first = blockIdx.x * LINES;
@@ -64,6 +73,26 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
     uint8_t* slot_line = reinterpret_cast<uint8_t*>(stage + (TYPED ? 2 : 1) * kStageSlots);
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
+    LtsvDeviceConfig cfg = P.ltsv;
+    LtsvSchemaView S = {cfg.names, cfg.name_off, cfg.types, cfg.n_schema, 0xFFFFFFFFu, nullptr};
+    if (TYPED) {
+        const int nblob = cfg.n_schema > 0 ? cfg.name_off[cfg.n_schema] : 0, nsuf = cfg.suffix_off[5];
+        if (cfg.n_schema <= kSchemaKeys && nblob <= kSchemaBlob && nsuf <= kSuffixBlob) {  // CTA-uniform
+            for (int k = tid; k < nblob; k += LINES) s_names[k] = cfg.names[k];
+            for (int k = tid; k <= cfg.n_schema; k += LINES) s_name_off[k] = cfg.name_off[k];
+            for (int k = tid; k < cfg.n_schema; k += LINES) s_types[k] = cfg.types[k];
+            for (int k = tid; k < nsuf; k += LINES) s_suffix[k] = cfg.suffix[k];
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t lm;
+                lt_schema_filters(s_names, s_name_off, cfg.n_schema, lm, s_first);
+                s_len_mask = lm;
+            }
+            __syncthreads();
+            cfg.suffix = s_suffix;
+            S = LtsvSchemaView{s_names, s_name_off, s_types, cfg.n_schema, s_len_mask, s_first};
+        }
+    }
     __syncthreads();
 
     const EntrySink sink = {P.entry_name, P.entry_val, P.entry_meta};
@@ -183,7 +212,7 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
 
         // ---- stage 2: one thread per line ------------------------------------------------------------------------
         LineResult res;
-        ltsv_walk<TYPED>(tile, bmT, bmC, ls, walk2 ? le : ls, walk2, P.ltsv, res, stage + slot0, stage_val + slot0);
+        ltsv_walk<TYPED>(tile, bmT, bmC, ls, walk2 ? le : ls, walk2, cfg, S, res, stage + slot0, stage_val + slot0);
         if (bad_utf8) {
             res.status = FG_ES_INVALID_UTF8;
             res.n_entries = 0;

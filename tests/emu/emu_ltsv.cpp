@@ -82,6 +82,9 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
     cfg.types = tys.data();
     cfg.suffix = (const uint8_t*)suffix_blob.data();
     const bool typed = cfg.has_schema != 0;
+    uint32_t first[8], len_mask;
+    fg::lt_schema_filters(cfg.names, cfg.name_off, cfg.n_schema, len_mask, first);
+    const fg::LtsvSchemaView S = {cfg.names, cfg.name_off, cfg.types, cfg.n_schema, len_mask, first};
 
     const int64_t total_bytes = n > 0 ? offsets[n] : 0;
     std::vector<uint8_t> tile((size_t)tile_bytes + 64);
@@ -183,9 +186,9 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                 const int i = cur + tid;
                 fg::LineResult res;
                 const bool walk = !bad[tid];
-                if (typed) fg::ltsv_walk<true>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, res,
+                if (typed) fg::ltsv_walk<true>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, S, res,
                                                stage.data() + slot0[tid], stage_val.data() + slot0[tid]);
-                else fg::ltsv_walk<false>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, res,
+                else fg::ltsv_walk<false>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, S, res,
                                           stage.data() + slot0[tid], stage_val.data() + slot0[tid]);
                 if (bad[tid]) { res.status = FG_ES_INVALID_UTF8; res.n_entries = 0; res.full_o = 0; }
                 const uint32_t my_n = (walk && res.status == FG_ST_OK) ? res.n_entries : 0u;

@@ -155,3 +155,27 @@ def test_mutation_fuzz(typed, oracle, native):
         out.append(bytes(ln))
     d2, o2 = oracle.pack(out)
     assert_parity(typed, oracle, LT, d2, o2, oracle.LtsvConfig(SCHEMA))
+
+
+MANY_TYPED_SCHEMA = {"a": "u64", "b": "u64", "c": "u64", "d": "i64", "e": "f64", "f": "bool", "time": "u64"}
+MANY_TYPED_LINES = [
+    b"time:1\thost:h\ta:1\tb:2\tc:3\td:-4\te:5.5\tf:true",
+    b"a:1\ta:2\ta:3\ta:4\ttime:1\thost:h",                      # four values of one type: two parked, two parsed in place
+    b"a:1\tb:x\tc:y\ttime:1\thost:h",                            # the FIRST failing part wins (b)
+    b"a:1\tb:2\tc:y\ta:z\ttime:1\thost:h",                      # in-place failure (c) after two parked values
+    b"a:1\tb:2\tc:3\ta:z\ttime:bad\thost:h",                    # in-place failure (second a) before the parked time fails
+    b"time:bad\ta:1\tb:2\tc:3\ta:z\thost:h",                    # parked time at an earlier part than the in-place failure
+    b"level:9\ta:x\ttime:1\thost:h", b"a:x\tlevel:9\ttime:1\thost:h", b"level:3\tlevel:8\tlevel:2\ttime:1\thost:h",
+    b"time:1\ttime:bad\ttime:2\thost:h", b"time:bad\ttime:1\thost:h", b"level:x\tlevel:1\ttime:1\thost:h",
+    b"d:-9223372036854775808\te:1e400\tf:TRUE\ttime:1\thost:h", b"e:.\ttime:1\thost:h", b"f:false\tf:true\tf:no\ttime:1\thost:h",
+]
+
+
+def test_many_typed_values_and_parked_order(oracle, native):
+    """Several values of one schema type, failures at parked and in-place positions: the first failing PART decides."""
+    d = native.BatchDecoder(native.FMT_LTSV, ltsv_schema=MANY_TYPED_SCHEMA)
+    try:
+        data, offs = oracle.pack(MANY_TYPED_LINES * 40)
+        assert_parity(d, oracle, LT, data, offs, oracle.LtsvConfig(MANY_TYPED_SCHEMA))
+    finally:
+        d.close()

@@ -20,9 +20,14 @@ for f in sorted(os.listdir(tmp)):
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
     if kname not in dis:
         continue
-    cur, infn, out = ("?", 0), False, []
+    # every .text section whose name holds the substring is a candidate (template instantiations): the one whose
+    # instruction count matches the report wins
+    cur, infn, out, cands = ("?", 0), False, [], []
     for ln in dis.splitlines():
         if ln.startswith(".text.") and ln.rstrip().endswith(":"):
+            if out:
+                cands.append(out)
+            out = []
             infn = kname in ln
             continue
         if not infn:
@@ -33,8 +38,11 @@ for f in sorted(os.listdir(tmp)):
             continue
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
             out.append(cur)
-    if out and (lines is None or abs(len(out) - len(counts)) < abs(len(lines) - len(counts))):
-        lines = out
+    if out:
+        cands.append(out)
+    for out in cands:
+        if lines is None or abs(len(out) - len(counts)) < abs(len(lines) - len(counts)):
+            lines = out
 assert lines is not None, "kernel not found"
 if len(lines) != len(counts):
     print(f"warning: {len(lines)} disassembled instructions vs {len(counts)} in the report", file=sys.stderr)
