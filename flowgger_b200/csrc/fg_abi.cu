@@ -282,6 +282,7 @@ int ensure_format(fg_ctx* c, int fmt) {
         FG_CUDA(c, cudaMalloc(&c->d_rows, rows_bytes));
         FG_CUDA(c, cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
     }
+    if (fmt == FG_FMT_GELF && !c->d_wide_list) FG_CUDA(c, cudaMalloc(&c->d_wide_list, (size_t)c->max_lines * 4));  // slow list
     const size_t want = std::max<size_t>(c->max_bytes / 24, 4096);
     if (c->entry_cap < want)
         if (int rc = alloc_entries(c, want)) return rc;
@@ -302,8 +303,6 @@ int ensure_format(fg_ctx* c, int fmt) {
 // shared-memory tile: mean span of a CTA's lines plus slack; the kernel handles whatever does not fit in extra rounds
 int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     const double mean = n > 0 ? (double)total_bytes / n : 0.0;
-    // GELF with long lines: no staging tile (tile_bytes = 0 selects the read-through-L1 kernel variant)
-    if (fmt == FG_FMT_GELF && mean > 256.0) return 0;
     const long lines = fg::lines_per_cta(fmt), gran = 8 * lines;  // 1 KiB steps for 128-line CTAs, 512 B for 64
 #ifndef FG_TILE_SLACK_PCT  // head room of the tile over the mean span of a CTA's lines (profiles/variants.sh tries others)
 #define FG_TILE_SLACK_PCT 102
@@ -311,7 +310,7 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     long t = (long)(mean * lines * (FG_TILE_SLACK_PCT / 100.0)) + gran;
     t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
-    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : (fmt == FG_FMT_LTSV ? fg::kLtsvMaxTile : c->max_tile)));
+    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : (fmt == FG_FMT_LTSV ? fg::kLtsvMaxTile : fg::kGelfMaxTile)));
     return (int)t;
 }
 
@@ -397,6 +396,9 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
     P.entry_counter = c->d_k + fg::K5_ENTRIES;
     P.entry_cap = (uint32_t)std::min<size_t>(c->entry_cap, 0xFFFFFFFFu);
     P.bad_offsets = c->d_k + kBadFlag;
+    P.slow_list = c->d_wide_list;
+    P.slow_count = c->d_k + fg::K5_WIDE_LIST;
+    if (fmt == FG_FMT_GELF) FG_CUDA(c, cudaMemsetAsync(c->d_k + fg::K5_WIDE_LIST, 0, 4, s));  // the work list is per launch
     P.ltsv = c->ltsv;
     if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom0, s));
     FG_CUDA(c, fg::launch_parse(fmt, P, s));
@@ -682,7 +684,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     c->max_lines = cfg->max_batch_lines > 0 ? cfg->max_batch_lines : (2 << 20);
     c->max_lines = (c->max_lines + 63) & ~63;  // keeps every row column 256-byte aligned
     c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (256 << 10);
-    c->chunk_lines = (c->chunk_lines + fg::kLinesPerCta - 1) / fg::kLinesPerCta * fg::kLinesPerCta;
+    c->chunk_lines = (c->chunk_lines + 127) / 128 * 128;  // a multiple of every kernel's lines per CTA
 #define FG_CREATE_CUDA(call)                                  \
     do {                                                      \
         cudaError_t _e = (call);                              \

@@ -309,7 +309,7 @@ static __device__ __noinline__ bool parse_f64_rust(bytes_t p, int a, int b, doub
 struct Pow10Table {
     double v[309];
 };
-static __device__ Pow10Table g_pow10;  // one copy per translation unit; only fg_kernels.cu (GELF) reads and uploads its own
+static __device__ Pow10Table g_pow10;  // one copy per translation unit; only fg_parse_gelf.cu reads it and uploads its own (configure_parse_gelf)
 
 // returns false for NumberOutOfRange
 FG_DEV bool serde_f64_from_parts(bool pos, uint64_t significand, int exponent, double& out) {

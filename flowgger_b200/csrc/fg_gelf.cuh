@@ -56,7 +56,7 @@ FG_DEV bool json_hex4(Json& j, uint32_t& n) {
 }
 
 // read.rs parse_str_bytes; j.i is just past the opening quote.  On JS_OK: [s,e) is the raw body, j.i past the closing quote.
-__device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
+static __device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
     s = j.i;
     has_bs = false;
     const uint32_t b0 = (uint32_t)(size_t)j.p & 15u;
@@ -113,7 +113,7 @@ __device__ __noinline__ int json_string(Json& j, int& s, int& e, bool& has_bs) {
 }
 
 // de.rs number parsing.  j.i at the first byte after an optional '-'.  tag/bits receive the Value.
-__device__ __noinline__ bool json_number(Json& j, bool pos, uint32_t& tag, uint64_t& bits) {
+static __device__ __noinline__ bool json_number(Json& j, bool pos, uint32_t& tag, uint64_t& bits) {
     // parse_integer
     if (j.i >= j.len) return false;
     uint32_t c = j.p[j.i++];
@@ -241,7 +241,7 @@ struct KeyIter {
 FG_DEV void key_iter_init(KeyIter& k, bytes_t p, int a, int b, bool mode2) {
     k.p = p; k.i = a; k.end = b; k.mode2 = mode2; k.pend = 0; k.npend = 0;
 }
-__device__ __noinline__ int key_iter_next(KeyIter& k) {  // -1 at the end
+static __device__ __noinline__ int key_iter_next(KeyIter& k) {  // -1 at the end
     if (k.npend) {
         const int b = (int)(k.pend & 0xFFu);
         k.pend >>= 8;
@@ -306,7 +306,7 @@ FG_DEV bool raw_str_is(bytes_t p, int a0, int a1, const char* lit, int n) {
 }
 
 // String Ord on the unescaped bytes
-__device__ __noinline__ int json_key_cmp(bytes_t p, int a0, int a1, int b0, int b1, bool mode2) {
+static __device__ __noinline__ int json_key_cmp(bytes_t p, int a0, int a1, int b0, int b1, bool mode2) {
     KeyIter x, y;
     key_iter_init(x, p, a0, a1, mode2);
     key_iter_init(y, p, b0, b1, mode2);
@@ -316,7 +316,7 @@ __device__ __noinline__ int json_key_cmp(bytes_t p, int a0, int a1, int b0, int 
         if (cx < 0) return 0;
     }
 }
-__device__ __noinline__ bool json_str_is(bytes_t p, int a0, int a1, bool mode2, const char* lit, int n) {
+static __device__ __noinline__ bool json_str_is(bytes_t p, int a0, int a1, bool mode2, const char* lit, int n) {
     KeyIter x;
     key_iter_init(x, p, a0, a1, mode2);
     for (int k = 0; k < n; ++k)
@@ -358,7 +358,7 @@ FG_DEV void members_put(Members& M, const EntrySink& sink, uint32_t sbase, int2 
 
 // One full parse of the document in the given mode.  Returns JS_*; on JS_OK `is_object` tells whether the
 // top-level value is an object and `m` members were staged at sink[sbase ..) in document order.
-__device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off, uint32_t sbase, bool mode2,
+static __device__ __noinline__ int gelf_parse_document(bytes_t p, int len, int line_off, uint32_t sbase, bool mode2,
                                                 const EntrySink& sink, bool& is_object, Members& M) {
     Json j;
     j.p = p; j.len = len; j.i = 0; j.mode2 = mode2;
@@ -481,7 +481,7 @@ struct GelfAcc {
     uint32_t status, flags, kept;
     bool have_ts;
 };
-__device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta,
+static __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta,
                                                LineResult& r, GelfAcc& g, const EntrySink& sink, uint32_t sbase) {
     const int ks = name.x - line_off, ke = ks + name.y;
     const uint32_t tag = meta & 7u;
@@ -532,9 +532,7 @@ __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mod
     }
 }
 
-// All 32 lanes call this; idle lanes pass active_line = false.
-FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bool active_line, LineResult& r,
-                            const EntrySink& sink) {
+FG_DEV void gelf_result_init(LineResult& r) {
     r.ts = 0.0;
     r.facility = 0xFFu;
     r.severity = 0xFFu;
@@ -543,6 +541,64 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
     r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
     r.n_entries = 0;
     r.status = FG_EG_JSON;
+}
+
+// Phase 2 over members held in local memory: BTreeMap order = stable insertion sort of an index permutation by unescaped
+// key, the last duplicate wins, then the per-key rules in that order (rows go to sink[sbase ..)).
+FG_DEV void gelf_finish_local(bytes_t p, int line_off, bool mode2, const Members& M, LineResult& r, GelfAcc& g, const EntrySink& sink,
+                              uint32_t sbase) {
+    const uint32_t m = M.m;
+    uint8_t ord[kMaxLocalMembers];
+    for (uint32_t a = 0; a < m; ++a) {
+        const int2 kn = M.name[a];
+        int b = (int)a - 1;
+        const bool kn_esc = (M.meta[a] & 0x40u) != 0;
+        while (b >= 0) {
+            const int2 on = M.name[ord[b]];
+            const int cmp = (kn_esc || (M.meta[ord[b]] & 0x40u))
+                                ? json_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y, mode2)
+                                : raw_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y);
+            if (cmp <= 0) break;
+            ord[b + 1] = ord[b];
+            --b;
+        }
+        ord[b + 1] = (uint8_t)a;
+    }
+    uint32_t gi = 0;
+    while (gi < m && g.status == FG_ST_OK) {
+        uint32_t ge = gi + 1;  // group of equal keys [gi, ge): the last inserted value wins
+        const int2 gn = M.name[ord[gi]];
+        const int ks = gn.x - line_off, ke = ks + gn.y;
+        const bool g_esc = (M.meta[ord[gi]] & 0x40u) != 0;
+        while (ge < m) {
+            const int2 nn = M.name[ord[ge]];
+            const int cmp = (g_esc || (M.meta[ord[ge]] & 0x40u)) ? json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2)
+                                                                : raw_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y);
+            if (cmp != 0) break;
+            ++ge;
+        }
+        const uint32_t w = ord[ge - 1];
+        gelf_apply_member(p, line_off, mode2, M.name[w], M.val[w], M.meta[w], r, g, sink, sbase);
+        gi = ge;
+    }
+}
+
+// gelf_decoder.rs:109-110 and the shape of an error row
+FG_DEV void gelf_finalize(LineResult& r, GelfAcc& g) {
+    if (g.status == FG_ST_OK) {
+        if (r.host_o < 0) g.status = FG_EG_MISSING_HOST;  // :110
+        else if (!g.have_ts) g.flags |= 0x01u;            // FG_FLAG_TS_MISSING :109
+    }
+    if (g.status == FG_ST_OK) r.n_entries = g.kept;
+    else { r.host_o = r.msg_o = r.full_o = -1; r.severity = 0xFFu; r.ts = 0.0; }
+    r.flags = g.flags;
+    r.status = g.status;
+}
+
+// All 32 lanes call this; idle lanes pass active_line = false.
+FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bool active_line, LineResult& r,
+                            const EntrySink& sink) {
+    gelf_result_init(r);
     if (active_line) {
         GelfAcc g;
         g.status = FG_ST_OK;
@@ -561,40 +617,7 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
         else if (!is_object) g.status = FG_EG_EMPTY;   // :50
         const uint32_t m = M.m;
         if (g.status == FG_ST_OK && !M.spilled) {
-            // BTreeMap order: stable insertion sort of an index permutation by unescaped key (members stay in local memory)
-            uint8_t ord[kMaxLocalMembers];
-            for (uint32_t a = 0; a < m; ++a) {
-                const int2 kn = M.name[a];
-                int b = (int)a - 1;
-                const bool kn_esc = (M.meta[a] & 0x40u) != 0;
-                while (b >= 0) {
-                    const int2 on = M.name[ord[b]];
-                    const int cmp = (kn_esc || (M.meta[ord[b]] & 0x40u))
-                                        ? json_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y, mode2)
-                                        : raw_key_cmp(p, on.x - line_off, on.x - line_off + on.y, kn.x - line_off, kn.x - line_off + kn.y);
-                    if (cmp <= 0) break;
-                    ord[b + 1] = ord[b];
-                    --b;
-                }
-                ord[b + 1] = (uint8_t)a;
-            }
-            uint32_t gi = 0;
-            while (gi < m && g.status == FG_ST_OK) {
-                uint32_t ge = gi + 1;  // group of equal keys [gi, ge): the last inserted value wins
-                const int2 gn = M.name[ord[gi]];
-                const int ks = gn.x - line_off, ke = ks + gn.y;
-                const bool g_esc = (M.meta[ord[gi]] & 0x40u) != 0;
-                while (ge < m) {
-                    const int2 nn = M.name[ord[ge]];
-                    const int cmp = (g_esc || (M.meta[ord[ge]] & 0x40u)) ? json_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y, mode2)
-                                                                        : raw_key_cmp(p, ks, ke, nn.x - line_off, nn.x - line_off + nn.y);
-                    if (cmp != 0) break;
-                    ++ge;
-                }
-                const uint32_t w = ord[ge - 1];
-                gelf_apply_member(p, line_off, mode2, M.name[w], M.val[w], M.meta[w], r, g, sink, sbase);
-                gi = ge;
-            }
+            gelf_finish_local(p, line_off, mode2, M, r, g, sink, sbase);
         } else if (g.status == FG_ST_OK) {
             // > kMaxLocalMembers members: same algorithm in place on the scratch table
             for (uint32_t a = 1; a < m; ++a) {
@@ -632,14 +655,7 @@ FG_DEV void gelf_parse_line(bytes_t p, int len, int line_off, uint32_t sbase, bo
                 gi = ge;
             }
         }
-        if (g.status == FG_ST_OK) {
-            if (r.host_o < 0) g.status = FG_EG_MISSING_HOST;  // :110
-            else if (!g.have_ts) g.flags |= 0x01u;            // FG_FLAG_TS_MISSING :109
-        }
-        if (g.status == FG_ST_OK) r.n_entries = g.kept;
-        else { r.host_o = r.msg_o = r.full_o = -1; r.severity = 0xFFu; r.ts = 0.0; }
-        r.flags = g.flags;
-        r.status = g.status;
+        gelf_finalize(r, g);
     }
     __syncwarp();
 }

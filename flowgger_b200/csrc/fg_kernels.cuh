@@ -52,6 +52,9 @@ struct ParseParams {
     uint32_t* entry_counter;  // running total (atomic bump, one add per CTA round)
     uint32_t entry_cap;
     const uint32_t* bad_offsets;  // set by check_offsets_kernel when the offsets array is not monotone / in range: kernels do nothing
+    // GELF: launch-relative numbers of the lines the fast walker hands to the exact parser (post_gelf_kernel)
+    uint32_t* slow_list;
+    uint32_t* slow_count;
     LtsvDeviceConfig ltsv;
 };
 
@@ -140,11 +143,6 @@ cudaError_t configure_gelf_encode(int max_tile_bytes);
 cudaError_t launch_gelf_encode(const GelfEncodeParams& p, void* d_scan_temp, size_t scan_temp_bytes, cudaStream_t stream);
 size_t gelf_scan_temp_bytes(int n);
 
-constexpr int kLinesPerCta = 128;   // lines (= threads) per CTA (256 was measured slower: bigger barriers, same warps/SM)
-constexpr int kMinCtasPerSm = 7;    // <= 72 registers/thread; shared memory (tile ~26 KB at 180 B/line) allows 7 CTAs
-// GELF read straight from global memory is latency-bound (divergent tokenizer, ~7 active lanes): 16 CTAs/SM at 32
-// registers beat 12 at 40 and 7 at 72 (10.5 / 10.9 / 12.3 ms per 3.5 M lines); LTSV is the opposite (5.8 -> 8.8 ms: L1 working set)
-constexpr int kGelfUnstagedCtasPerSm = 16;
 // RFC5424 (short lines, staged tile): 64-line CTAs — tile waits and barriers half as wide as with 128 lines
 #ifndef FG_R5_LINES  // profiles/variants.sh builds other shapes with -DFG_R5_LINES / -DFG_R5_MINB for A/B runs
 #define FG_R5_LINES 64
@@ -161,13 +159,24 @@ constexpr int kRfc5424CtasPerSm = FG_R5_MINB;
 constexpr int kLtsvLinesPerCta = FG_LTSV_LINES;
 constexpr int kLtsvStageSlots = kLtsvLinesPerCta * 24;
 constexpr int kLtsvMaxTile = 65024;  // tile positions are packed into 16 bits
-constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : kLinesPerCta); }
+// GELF (fg_parse_gelf.cu): 64-line CTAs; the staging area holds kGelfStageSlots side-table rows per CTA round
+#ifndef FG_GELF_LINES
+#define FG_GELF_LINES 64
+#endif
+constexpr int kGelfLinesPerCta = FG_GELF_LINES;
+constexpr int kGelfStageSlots = kGelfLinesPerCta * 10;
+constexpr int kGelfMaxTile = 65024;
+constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : kGelfLinesPerCta); }
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 // LTSV on the bitmap pipeline (fg_parse_ltsv.cu); launch_parse routes fmt 1 here
 cudaError_t launch_parse_ltsv(const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_parse_ltsv(int max_tile_bytes);
 int parse_ltsv_smem_bytes(int tile_bytes, bool typed);
+// GELF on the bitmap pipeline + the exact parser over the slow list (fg_parse_gelf.cu); launch_parse routes fmt 2 here
+cudaError_t launch_parse_gelf(const ParseParams& p, cudaStream_t stream);
+cudaError_t configure_parse_gelf(int max_tile_bytes);
+int parse_gelf_smem_bytes(int tile_bytes);
 // offsets[0 .. n] must be non-decreasing and within [0, max_bytes]; otherwise *flag |= 1 (the parse kernels then return at once)
 cudaError_t launch_check_offsets(const int32_t* d_offsets, int n, long long max_bytes, uint32_t* d_flag, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424);

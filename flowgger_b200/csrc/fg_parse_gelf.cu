@@ -1,0 +1,265 @@
+// fg_parse_gelf.cu — the GELF decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline.
+//
+//   parse_gelf_kernel   one CTA = LINES consecutive lines.  (1) ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the CTA's
+//                       contiguous byte span into the shared-memory tile; (2) all threads sweep the tile 32 bytes per step
+//                       and write the string bitmap X (fg_gelffast.cuh stage 1); (3) one thread per line walks its members
+//                       over the bitmap (stage 2, lock step) into per-thread local memory; (4) slots for the side-table
+//                       rows are reserved by a CTA scan, phase 2 (sort by key, last duplicate wins, per-key rules) stages
+//                       the rows in shared memory; (5) a second scan + ONE global atomic place them and all threads copy
+//                       them out — consecutive threads write consecutive rows of the three side-table columns.
+//                       Lines the walker does not recognise as regular go on a device-side list.
+//   post_gelf_kernel    the SLOW path over that list: the exact parser of fg_gelf.cuh (the whole serde_json grammar, the
+//                       newline retry, every error string), one thread per listed line straight from global memory.
+#include "fg_kernels.cuh"
+
+#include "fg_common.cuh"
+#include "fg_gelffast.cuh"
+#include "fg_status.h"
+#include "fg_tma.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace fg {
+
+namespace {
+
+constexpr int kLines = kGelfLinesPerCta;
+constexpr int kSlots = kGelfStageSlots;
+
+__device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, const LineResult& res, uint32_t my_begin, uint32_t my_n) {
+    const bool ok = res.status == FG_ST_OK;
+    P.ts[i] = res.ts;
+    P.meta[i] = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);
+    P.host[i] = make_int2(res.host_o >= 0 ? o0 + res.host_o : -1, res.host_l);
+    P.msg[i] = make_int2(res.msg_o >= 0 ? o0 + res.msg_o : -1, res.msg_l);
+    P.full[i] = ok ? make_int2(res.full_o >= 0 ? o0 + res.full_o : -1, res.full_l) : make_int2(o0 + max(res.full_o, 0), 0);
+    P.sd[i] = make_int2((int)my_begin, (int)my_n);
+}
+
+template <int LINES>
+__global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant__ ParseParams P) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t scan_ws[33];
+    __shared__ uint32_t s_ebase, s_slots, s_slow_base;
+    __shared__ uint32_t line_slot[LINES];   // first staging slot | rows << 16
+    __shared__ uint32_t line_dense[LINES];  // exclusive sum of the rows of the lines before this one
+
+    const int tid = threadIdx.x;
+    const int first = blockIdx.x * LINES;
+    const int last = min(P.n, first + LINES);
+    // behind the tile: the bitmap (tile_bytes / 32 + 4 words), the staged rows (three columns), the slot -> line map
+    const int bm_words = P.tile_bytes / 32 + 4;
+    uint32_t* bmX = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
+    int2* st_name = reinterpret_cast<int2*>(bmX + bm_words);
+    unsigned long long* st_val = reinterpret_cast<unsigned long long*>(st_name + kSlots);
+    uint8_t* st_meta = reinterpret_cast<uint8_t*>(st_val + kSlots);
+    uint8_t* slot_line = st_meta + kSlots;
+    if (*P.bad_offsets) return;  // CTA-uniform
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+
+    const EntrySink sink = {P.entry_name, P.entry_val, P.entry_meta};
+    const EntrySink stage = {st_name, st_val, st_meta};
+    uint32_t parity = 0;
+    int cur = first;
+    while (cur < last) {
+        const int i = cur + tid;
+        const int o0 = __ldg(P.offsets + min(i, last));
+        const int o1 = __ldg(P.offsets + min(i + 1, last));
+        const int ocur = __ldg(P.offsets + cur);
+        const int base = ocur & ~15;
+        const bool fits = (i < last) && (o1 - base <= P.tile_bytes);
+        int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
+        if (r == 0) {
+            // the first pending line alone exceeds the tile: the slow kernel takes it
+            if (tid == 0) P.slow_list[atomicAdd(P.slow_count, 1u)] = (uint32_t)cur;
+            cur += 1;
+            continue;
+        }
+        const int oend = __ldg(P.offsets + cur + r);
+        const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
+        if (tid == 0) {
+            fence_proxy_async();  // generic-proxy accesses of the previous round happen-before this async write
+            mbar_expect_tx(&mbar, nbytes);
+            bulk_g2s(tile, P.bytes + base, nbytes, &mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+
+        // ---- stage 1: the string bitmap of the whole tile, 32 bytes (= one word) per thread per step -----------------
+        const int nword = (int)((nbytes + 31u) >> 5);
+        for (int g = tid; g < nword; g += LINES) {
+            const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
+            bmX[g] = gf_classify16(v0.x, v0.y, v0.z, v0.w) | (gf_classify16(v1.x, v1.y, v1.z, v1.w) << 16);
+        }
+        if (tid < 4) bmX[nword + tid] = 0;
+        __syncthreads();
+
+        // ---- stage 2: one thread per line ------------------------------------------------------------------------
+        bool active = tid < r;
+        const int ls = active ? o0 - base : 0;
+        int le = active ? o1 - base : 0;
+        bool bad_utf8 = false;
+        if (P.strip_eol && le > ls) {
+            // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
+            if (P.strip_eol == 2) {  // BufRead::split(0): only the NUL terminator goes (nul_splitter.rs:18)
+                if (tile[le - 1] == 0) --le;
+            } else if (tile[le - 1] == '\n') {
+                --le;
+                if (le > ls && tile[le - 1] == '\r') --le;
+            }
+            if (P.line_invalid != nullptr && P.line_invalid[i]) bad_utf8 = true;
+        }
+        const bool walk = active && !bad_utf8;
+        Members M;
+        uint32_t n_plain = 0;
+        const bool regular = gf_walk(tile, bmX, ls, walk ? le : ls, walk, o0, M, n_plain);
+        bool slow = walk && !regular;
+
+        // staging slots for the rows of the regular lines (upper bound: members that are not reserved keys)
+        const uint32_t nb = (walk && regular) ? n_plain : 0u;
+        uint32_t slots_total;
+        const uint32_t slot0 = block_exclusive_scan(nb, scan_ws, slots_total);
+        if (slots_total > (uint32_t)kSlots) {  // CTA-uniform, rare: keep the lines whose slots fit, redo the rest next round
+            r = __syncthreads_count(active && slot0 + nb <= (uint32_t)kSlots);  // >= 1: one line holds <= kMaxLocalMembers rows
+            active = tid < r;
+            slow = slow && active;
+        }
+        const bool fast = walk && regular && active;
+
+        // ---- phase 2: BTreeMap order, last duplicate wins, the per-key rules; rows staged at stage[slot0 ..) -----------
+        LineResult res;
+        gelf_result_init(res);
+        if (fast) {
+            GelfAcc g;
+            g.status = FG_ST_OK;
+            g.flags = 0;
+            g.kept = 0;
+            g.have_ts = false;
+            gelf_finish_local(tile + ls, o0, false, M, res, g, stage, slot0);
+            gelf_finalize(res, g);
+        }
+        __syncwarp();
+        if (bad_utf8) {
+            res.status = FG_ES_INVALID_UTF8;
+            res.n_entries = 0;
+            res.full_o = 0;
+        }
+        const uint32_t my_n = (fast && res.status == FG_ST_OK) ? res.n_entries : 0u;
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
+        uint32_t slow_total;
+        const uint32_t slow_at = block_exclusive_scan(slow ? 1u : 0u, scan_ws, slow_total);
+        line_slot[tid] = slot0 | (my_n << 16);
+        line_dense[tid] = excl;
+        if (fast)
+            for (uint32_t k = 0; k < nb; ++k) slot_line[slot0 + k] = (uint8_t)tid;
+        if (tid == r - 1) s_slots = slot0 + nb;
+        if (tid == 0 && total) s_ebase = atomicAdd(P.entry_counter, total);
+        if (tid == 32 % LINES && slow_total) s_slow_base = atomicAdd(P.slow_count, slow_total);
+        __syncthreads();
+        if (slow) P.slow_list[s_slow_base + slow_at] = (uint32_t)i;
+        uint32_t my_begin = 0;
+        if (total) {  // CTA-uniform
+            const uint32_t ebase = s_ebase;
+            const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
+            if (!ovf) {
+                if (my_n) my_begin = ebase + excl;
+                const uint32_t nslots = s_slots;
+                for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)LINES) {
+                    const uint32_t l = slot_line[s];
+                    const uint32_t ls_n = line_slot[l];
+                    const uint32_t k = s - (ls_n & 0xFFFFu);
+                    if (k < (ls_n >> 16)) {
+                        const uint32_t j = ebase + line_dense[l] + k;
+                        sink.name[j] = st_name[s];
+                        sink.val[j] = st_val[s];
+                        sink.meta[j] = st_meta[s];
+                    }
+                }
+            }
+        }
+        if (active && !slow) write_row(P, i, o0, res, my_begin, my_n);
+        __syncthreads();  // tile, bitmap, staging and scan scratch are reused by the next round
+        cur += r;
+    }
+}
+
+// the exact parser over the listed lines: one thread per line straight from global memory, rows through the scratch table
+__global__ void __launch_bounds__(128) post_gelf_kernel(const __grid_constant__ ParseParams P) {
+    if (*P.bad_offsets) return;
+    const uint32_t cnt = *P.slow_count;
+    const uint32_t lane = threadIdx.x & 31u;
+    const EntrySink sink = {P.entry_name, P.entry_val, P.entry_meta};
+    const EntrySink tmp = {P.tmp_name, P.tmp_val, P.tmp_meta};
+    const uint32_t stride = gridDim.x * 128u;
+    for (uint32_t j0 = (blockIdx.x * 4u + (threadIdx.x >> 5)) * 32u; j0 < cnt; j0 += stride) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < cnt;
+        int line = 0, o0 = 0, len = 0;
+        if (valid) {
+            line = (int)P.slow_list[j];
+            o0 = P.offsets[line];
+            len = P.offsets[line + 1] - o0;
+            if (P.strip_eol && len > 0) {
+                if (P.strip_eol == 2) {
+                    if (P.bytes[o0 + len - 1] == 0) --len;
+                } else if (P.bytes[o0 + len - 1] == '\n') {
+                    --len;
+                    if (len > 0 && P.bytes[o0 + len - 1] == '\r') --len;
+                }
+            }
+        }
+        LineResult res;
+        const uint32_t sidx = (uint32_t)o0 / 3u;  // a top-level member needs >= 5 input bytes (`"":0,`)
+        gelf_parse_line(P.bytes + o0, len, o0, sidx, valid, res, tmp);
+        if (!valid) continue;
+        const uint32_t my_n = res.status == FG_ST_OK ? res.n_entries : 0u;
+        uint32_t my_begin = 0;
+        if (my_n) {
+            const uint32_t eb = atomicAdd(P.entry_counter, my_n);
+            if ((unsigned long long)eb + my_n <= (unsigned long long)P.entry_cap) {
+                my_begin = eb;
+                for (uint32_t k = 0; k < my_n; ++k) {
+                    sink.name[eb + k] = tmp.name[sidx + k];
+                    sink.val[eb + k] = tmp.val[sidx + k];
+                    sink.meta[eb + k] = tmp.meta[sidx + k];
+                }
+            }
+        }
+        write_row(P, line, o0, res, my_begin, my_n);
+    }
+}
+
+}  // namespace
+
+int parse_gelf_smem_bytes(int tile_bytes) { return tile_bytes + (tile_bytes / 32 + 4) * 4 + kSlots * (8 + 8 + 1 + 1) + 16; }
+
+cudaError_t configure_parse_gelf(int max_tile_bytes) {
+    {   // serde_json's POW10 table (visit_f64_from_parts): correctly rounded decimal literals, like rustc's
+        static Pow10Table t;
+        for (int k = 0; k <= 308; ++k) {
+            char buf[16];
+            snprintf(buf, sizeof buf, "1e%d", k);
+            t.v[k] = strtod(buf, nullptr);
+        }
+        cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);  // this translation unit's copy: the one the GELF kernels read
+        if (e1 != cudaSuccess) return e1;
+    }
+    return cudaFuncSetAttribute(parse_gelf_kernel<kLines>, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_gelf_smem_bytes(max_tile_bytes));
+}
+
+cudaError_t launch_parse_gelf(const ParseParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    if (p.tile_bytes <= 0 || p.tile_bytes > kGelfMaxTile || (p.tile_bytes & 511)) return cudaErrorInvalidValue;
+    const int grid = (p.n + kLines - 1) / kLines;
+    parse_gelf_kernel<kLines><<<grid, kLines, parse_gelf_smem_bytes(p.tile_bytes), stream>>>(p);
+    // the work list lives on the device (no host round trip): a fixed grid strides over it
+    const int post = (int)min((long long)(p.n + 127) / 128, 148LL * 8);
+    post_gelf_kernel<<<post, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace fg

@@ -1,7 +1,8 @@
 """Loader of tests/emu/libfg_emu.so — the CPU emulation of the RFC5424 and LTSV device logic (TEST INFRASTRUCTURE).
 
 The library is the product's walker sources (flowgger_b200/csrc/fg_r5fast.cuh, fg_rfc5424.cuh, fg_ltsvfast.cuh, fg_ltsv.cuh)
-compiled with g++ plus drivers that replay the CTA rounds of parse5424_kernel / parse_ltsv_kernel one lane at a time.
+compiled with g++ plus drivers that replay the CTA rounds of parse5424_kernel / parse_ltsv_kernel / parse_gelf_kernel one
+lane at a time.
 Only tests import this module.
 """
 from __future__ import annotations
@@ -20,11 +21,11 @@ _lib = None
 def build(force: bool = False) -> Path:
     so = HERE / "libfg_emu.so"
     csrc = REPO / "flowgger_b200" / "csrc"
-    srcs = [HERE / "emu_r5.cpp", HERE / "emu_ltsv.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h"] + \
+    srcs = [HERE / "emu_r5.cpp", HERE / "emu_ltsv.cpp", HERE / "emu_gelf.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h"] + \
         sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h"))
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
-                        str(HERE / "emu_r5.cpp"), str(HERE / "emu_ltsv.cpp"), "-I", str(REPO / "include")], check=True)
+                        str(HERE / "emu_r5.cpp"), str(HERE / "emu_ltsv.cpp"), str(HERE / "emu_gelf.cpp"), "-I", str(REPO / "include")], check=True)
     return so
 
 
@@ -36,6 +37,8 @@ def lib() -> C.CDLL:
         _lib.emu5424_classify16.argtypes = [C.c_void_p]
         _lib.emu_ltsv_classify16.restype = C.c_uint32
         _lib.emu_ltsv_classify16.argtypes = [C.c_void_p]
+        _lib.emu_gelf_classify16.restype = C.c_uint32
+        _lib.emu_gelf_classify16.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -95,4 +98,27 @@ def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict
         d = {"n_entries": out.n_entries, "rounds": int(info[0]), "direct": int(info[1])}
     finally:
         lib().emu_ltsv_free(C.byref(out))
+    return buf, offs, d
+
+
+def gelf_classify16(block: bytes) -> int:
+    assert len(block) == 16
+    buf = C.create_string_buffer(block, 16)
+    return int(lib().emu_gelf_classify16(buf))
+
+
+def gelf_decode_dump(native, data: np.ndarray, offsets: np.ndarray, tile_bytes: int = 34304, strip_eol: int = 0,
+                     invalid: np.ndarray | None = None):
+    """Emulated GELF decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser."""
+    from flowgger_b200.native import FgBatchOut, dump_records
+    out = FgBatchOut()
+    n = len(offsets) - 1
+    info = (C.c_int32 * 3)()
+    lib().emu_gelf_decode(C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n, tile_bytes, strip_eol,
+                          C.c_void_p(invalid.ctypes.data) if invalid is not None else None, C.byref(out), info)
+    try:
+        buf, offs = dump_records(native.FMT_GELF, out, data, offsets)
+        d = {"n_entries": out.n_entries, "rounds": int(info[0]), "slow": int(info[1]), "bound_violations": int(info[2])}
+    finally:
+        lib().emu_gelf_free(C.byref(out))
     return buf, offs, d

@@ -68,3 +68,13 @@ for (f, l), (e, t, s) in sorted(agg.items(), key=lambda kv: (kv[0][0], kv[0][1])
     if e * 200 < tot and s * 200 < tots:
         continue
     print(f"{f + ':' + str(l):28s} {e:11d} {100 * e / tot:5.1f} {e / per if per else 0:6.2f} {t / max(e, 1):9.1f} {100 * s / max(tots, 1):8.1f}  {src(f, l)}")
+
+# totals per source file and per function-sized block of 25 lines: where the long tail of small lines sits
+by_file = collections.OrderedDict()
+for (f, l), (e, t, s_) in agg.items():
+    a = by_file.setdefault((f, l // 25 * 25), [0, 0])
+    a[0] += e; a[1] += t
+print("\nby 25-line block (>= 1 %):")
+for (f, l), (e, t) in sorted(by_file.items()):
+    if e * 100 >= tot:
+        print(f"{f + ':' + str(l) + '+':28s} {e:11d} {100 * e / tot:5.1f} {e / per if per else 0:6.2f} {t / max(e, 1):9.1f}")
