@@ -152,11 +152,15 @@ size_t gelf_scan_temp_bytes(int n);
 #endif
 constexpr int kRfc5424LinesPerCta = FG_R5_LINES;
 constexpr int kRfc5424CtasPerSm = FG_R5_MINB;
-// LTSV (fg_parse_ltsv.cu): 64-line CTAs; the staging area holds kLtsvStageSlots side-table rows per CTA round
+// LTSV (fg_parse_ltsv.cu): 64 lines and 256 threads per CTA; a CTA round has kLtsvStageSlots slots, one per tab-separated part
 #ifndef FG_LTSV_LINES
 #define FG_LTSV_LINES 64
 #endif
+#ifndef FG_LTSV_THREADS
+#define FG_LTSV_THREADS 256
+#endif
 constexpr int kLtsvLinesPerCta = FG_LTSV_LINES;
+constexpr int kLtsvThreadsPerCta = FG_LTSV_THREADS;
 constexpr int kLtsvStageSlots = kLtsvLinesPerCta * 24;
 constexpr int kLtsvMaxTile = 65024;  // tile positions are packed into 16 bits
 // GELF (fg_parse_gelf.cu): 64-line CTAs; the staging area holds kGelfStageSlots side-table rows per CTA round

@@ -1,18 +1,22 @@
-// fg_ltsvfast.cuh — LTSV on the bitmap pipeline: two structural bitmaps + one-part-per-step walk over a shared-memory tile.
+// fg_ltsvfast.cuh — LTSV on the bitmap pipeline, PART-parallel: the tab-separated parts of a line are independent of each
+// other, so the unit of work of the hot phase is a part, not a line.
 //
 // B200-native replacement for LTSVDecoder::decode (/root/reference/src/flowgger/decoder/ltsv_decoder.rs:87-221); the
 // value parsers (parse_ts :263-267, the typed schema values :138-195) are the ones of fg_ltsv.cuh, called on tile bytes.
 //
-//   stage 1  lt_classify16: every thread takes 32-byte granules of the flat tile (two LDS.128, all 32 lanes busy) and writes
-//            one word each of two bitmaps, exact per byte: T = TAB (line.split('\t') :94), C = ':' (splitn(2, ':') :95).
-//   stage 2  ltsv_walk: one thread per line, ONE tab-separated part per loop iteration for all 32 lines of a warp.  The end
-//            of the part is the next set bit of T (a per-lane iterator: word + remaining bits, no byte is read), the key
-//            ends at the first set bit of C inside the part (one funnel-shifted 32-bit window).  What the round-1 scanner
-//            found with 16-byte SWAR scans per lane and per part (645 warp-instructions per line, 3.5x read amplification
-//            from 32 lanes pulling 32 different lines through L1) costs a find-first-set here.
-//
-// Side-table rows are staged as 8-byte packed entries in shared memory — the line's slots are reserved from its TAB
-// count (#parts = #tabs + 1 >= #pairs), known from T before the walk — and leave the SM as coalesced column stores.
+//   stage 1  lt_tab16: every thread takes 32-byte granules of the flat tile (two LDS.128, all 32 lanes busy) and writes one
+//            word of the TAB bitmap T (line.split('\t') :94), exact per byte.
+//   tabs     one thread per line lists the positions of its TABs (find-first-set over T) into the line's slots: slot k of a
+//            line = its k-th part, ending at tabs[k] (the last one at the end of the line).  #slots = #tabs + 1.
+//   parts    lt_part: one thread per SLOT, for all slots of the CTA round, 256 threads wide: the key ends at the first ':'
+//            (splitn(2, ':') :95, a SWAR test on the first 8 key bytes), the four reserved keys are recognised from
+//            those 8 bytes, everything else becomes a packed side-table row in the slot.  No loop over a line, no lock step,
+//            no lane waits for a longer line (round 2 measured the thread-per-line walk at 315 warp-instructions per line
+//            with 8 warps per SM; profiles/r2_notes.md).
+//   lines    lt_finish_line: one thread per line parses the (last) `time` and `level` values, picks the first failing part
+//            and builds the row.
+// Lines that need the reference's sequential semantics beyond that — a repeated `time` or `level` key — and lines that do
+// not fit the tile or the slots go through the round-1 scanner (fg_ltsv.cuh), one at a time.
 #pragma once
 #include "fg_common.cuh"
 #include "fg_ltsv.cuh"
@@ -28,9 +32,8 @@ FG_DEV uint32_t lt_eq_flags(uint32_t w, uint32_t pat) {
     const uint32_t y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7: byte != 0
     return ~y & 0x80808080u;
 }
-FG_DEV void lt_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t& t16, uint32_t& c16) {
-    t16 = r5_gather16(lt_eq_flags(w0, 0x09090909u), lt_eq_flags(w1, 0x09090909u), lt_eq_flags(w2, 0x09090909u), lt_eq_flags(w3, 0x09090909u));
-    c16 = r5_gather16(lt_eq_flags(w0, 0x3A3A3A3Au), lt_eq_flags(w1, 0x3A3A3A3Au), lt_eq_flags(w2, 0x3A3A3A3Au), lt_eq_flags(w3, 0x3A3A3A3Au));
+FG_DEV uint32_t lt_tab16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return r5_gather16(lt_eq_flags(w0, 0x09090909u), lt_eq_flags(w1, 0x09090909u), lt_eq_flags(w2, 0x09090909u), lt_eq_flags(w3, 0x09090909u));
 }
 
 // TABs inside tile range [ls, le)
@@ -48,7 +51,9 @@ FG_DEV int lt_count_tabs(const uint32_t* bmT, int ls, int le) {
 }
 
 // staged side-table row: key start (tile-relative) | key length << 16 | value length << 32 | meta << 56; the value starts
-// one byte after the key (the colon).  meta = fg_ltsv_type | FG_EM_SUFFIX; typed values sit in the parallel `stage_val`.
+// one byte after the key (the colon).  meta = fg_ltsv_type | FG_EM_SUFFIX | kLtRow (the slot holds a row); typed values
+// sit in the parallel `stage_val`.  A slot without a row (reserved key, part without ':') is 0.
+constexpr uint32_t kLtRow = 0x80u;
 FG_DEV unsigned long long lt_pack_entry(int ka, int kn, int vl, uint32_t meta) {
     return (unsigned long long)(uint32_t)ka | ((unsigned long long)(uint32_t)kn << 16) | ((unsigned long long)(uint32_t)vl << 32) |
            ((unsigned long long)meta << 56);
@@ -106,205 +111,118 @@ FG_DEV int lt_schema_type(bytes_t p, int a, int n, unsigned long long k8, const 
     return 0;
 }
 
-// All 32 lanes of a warp must call this (idle lanes with active_line = false).  T = the tile, [ls, le) the line inside it
-// (le - ls < 65536).  `stage` / `stage_val` = this line's reserved slots (>= #tabs + 1).  Result spans are relative to ls,
-// exactly as ltsv_parse_line (fg_ltsv.cuh) reports them.
-//
-// The part loop holds NO per-key work that only a few lanes need: the four reserved keys are recognised branch-free from
-// the first 8 key bytes; `host` / `message` are two predicated moves; the values of `time`, `level` and of typed schema
-// keys are only PARKED (position, length, part) and parsed after the loop in lock step — one phase per kind, so all lanes
-// run the same parser.  (The first version parsed them where they stood: ~2 of 32 lanes active, 386 warp-instructions per
-// line, profiles/r2_notes.md.)  Evaluation order is preserved: the reference returns at the FIRST failing part, so a parked
-// item is evaluated iff no error was found at an earlier part, and an earlier failure replaces a later one.
+// positions of the TABs of [ls, le) into tabs[0 .. n - 1), tabs[n - 1] = le; n = #tabs + 1 (the caller reserved n slots)
+FG_DEV void lt_list_tabs(const uint32_t* bmT, int ls, int le, uint16_t* tabs) {
+    int k = 0;
+    if (le > ls) {
+        const int w0 = ls >> 5, w1 = (le - 1) >> 5;
+        for (int w = w0; w <= w1; ++w) {
+            uint32_t m = bmT[w];
+            if (w == w0) m &= 0xFFFFFFFFu << (ls & 31);
+            if (w == w1 && (le & 31)) m &= 0xFFFFFFFFu >> (32 - (le & 31));
+            while (m) {
+                tabs[k++] = (uint16_t)((w << 5) + fg_ffs(m) - 1);
+                m &= m - 1u;
+            }
+        }
+    }
+    tabs[k] = (uint16_t)le;
+}
+
+// 0x80 in every byte of the 8 that is ':'
+FG_DEV unsigned long long lt_colon_flags8(unsigned long long k8) {
+    const uint32_t lo = lt_eq_flags((uint32_t)k8, 0x3A3A3A3Au), hi = lt_eq_flags((uint32_t)(k8 >> 32), 0x3A3A3A3Au);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+FG_DEV int lt_first_flag8(unsigned long long z) {  // byte index of the lowest 0x80 flag (z != 0)
+    const uint32_t lo = (uint32_t)z;
+    return lo ? (fg_ffs(lo) - 1) >> 3 : 4 + ((fg_ffs((uint32_t)(z >> 32)) - 1) >> 3);
+}
+
+enum { LP_NONE = 0 /* no ':' */, LP_ROW, LP_HOST, LP_MSG, LP_TIME, LP_LEVEL };
+struct LtPart {
+    int kind;
+    int kn;                    // key length: key = [start, start + kn), value = [start + kn + 1, end)
+    unsigned long long row;    // LP_ROW: the packed side-table row (typed values: parsed later by lt_typed_value)
+};
+
+// One tab-separated part [start, end) of the tile (:95-199 without the value parsers).
 template <bool TYPED>
-FG_DEV void ltsv_walk(const uint8_t* T, const uint32_t* bmT, const uint32_t* bmC, int ls, int le, bool active_line,
-                      const LtsvDeviceConfig& cfg, const LtsvSchemaView& S, LineResult& r, unsigned long long* stage,
-                      unsigned long long* stage_val) {
-    r.ts = 0.0;
-    r.facility = 0xFFu;
-    r.severity = 0xFFu;
-    r.flags = 0;
-    r.host_o = r.app_o = r.proc_o = r.mid_o = r.msg_o = r.full_o = -1;
-    r.host_l = r.app_l = r.proc_l = r.mid_l = r.msg_l = r.full_l = 0;
-    r.n_entries = 0;
-    uint32_t status = FG_ST_OK, n = 0, flags = 0;
+FG_DEV LtPart lt_part(const uint8_t* T, int start, int end, const LtsvDeviceConfig& cfg, const LtsvSchemaView& S) {
+    LtPart r;
+    r.kind = LP_NONE;
+    r.kn = 0;
+    r.row = 0;
+    const int len = end - start;
+    const unsigned long long k8 = lt_load8(T + start);
+    int kn = -1;
+    {
+        const unsigned long long z = lt_colon_flags8(k8);
+        if (z) {
+            const int b = lt_first_flag8(z);
+            if (b < len) kn = b;
+        } else {
+            for (int i = 8; i < len && kn < 0; i += 8) {  // keys of 8 bytes and more
+                const unsigned long long z2 = lt_colon_flags8(lt_load8(T + start + i));
+                if (z2) {
+                    const int b = i + lt_first_flag8(z2);
+                    if (b < len) kn = b;
+                    break;
+                }
+            }
+        }
+    }
+    if (kn < 0) return r;  // println! "Missing value" :99
+    r.kn = kn;
+    const uint32_t k4 = (uint32_t)k8;
+    if (kn == 4 && k4 == 0x656D6974u) r.kind = LP_TIME;                                                     // "time"  :104
+    else if (kn == 4 && k4 == 0x74736F68u) r.kind = LP_HOST;                                                // "host"
+    else if (kn == 7 && (k8 & 0x00FFFFFFFFFFFFFFull) == 0x006567617373656Dull) r.kind = LP_MSG;             // "message"
+    else if (kn == 5 && (k8 & 0x000000FFFFFFFFFFull) == 0x0000006C6576656Cull) r.kind = LP_LEVEL;           // "level"  :114
+    else {
+        r.kind = LP_ROW;
+        uint32_t meta = kLtRow;
+        if (TYPED) {
+            const int type = lt_schema_type(T, start, kn, k8, S);
+            if (type != 0) {
+                meta |= (uint32_t)type;  // FG_TAG_* == fg_ltsv_type
+                if (ltsv_needs_suffix(T, start, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
+            }
+        }
+        r.row = lt_pack_entry(start, kn, len - kn - 1, meta);
+    }
+    return r;
+}
+
+// the reference's per-line rules once every part is classified (:104-121, :205-219).  time_* / level_* = the bounds of the
+// VALUE of the only `time` / `level` part (start < 0: none) and the index of that part; err_in = the smallest
+// (part index << 8 | status) among the typed values that failed (0xFFFFFFFF: none); part_start(k) is only needed for the
+// failing part.  Fills ts / severity / status; returns the index of the failing part (or -1).
+FG_DEV int lt_finish_line(const uint8_t* T, int t_a, int t_b, int t_k, int l_a, int l_b, int l_k, uint32_t err_in, bool have_host,
+                          LineResult& r) {
+    uint32_t err = err_in;
     bool have_ts = false;
-    int err_pos = 0;  // tile position of the failing part
-    bool err_set = false;
-    int part = ls;  // start of the current part
-    bool active = active_line;
-    // iterator over the TABs at or after `part`
-    int tw = ls >> 5;
-    uint32_t trem = active ? bmT[tw] & (0xFFFFFFFFu << (ls & 31)) : 0u;
-    // parked values: `time`, `level`, and two typed values per schema type (slot = 2 * (type - 1) + {0, 1})
-    int ts_a = -1, ts_b = -1, ts_part = 0;
-    int lv_a = -1, lv_b = -1, lv_part = 0;
-    int pk_va[8], pk_pt[8];
-    uint32_t pk_info[8];  // value length | row << 16; 0xFFFFFFFF = empty
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { pk_va[q] = 0; pk_pt[q] = 0; pk_info[q] = 0xFFFFFFFFu; }
-    const bytes_t p = T;
-    while (fg_any(active)) {  // line.split('\t') :94
-        // end of this part: the next TAB below le, else le
-        for (;;) {
-            const bool need = active && trem == 0u && ((tw + 1) << 5) < le;
-            if (!fg_any(need)) break;
-            if (need) {
-                ++tw;
-                trem = bmT[tw];
-            }
-        }
-        int pe = le;
-        if (active && trem) {
-            const int t = (tw << 5) + fg_ffs(trem) - 1;
-            if (t < le) {
-                pe = t;
-                trem &= trem - 1u;
-            }
-        }
-        // splitn(2, ':') :95 — the first ':' of the part
-        int cpos = part;
-        uint32_t wc = active ? r5_window(bmC, part) : 0u;
-        for (;;) {  // keys longer than 32 bytes, or long parts without a colon
-            const bool need = active && wc == 0u && cpos + 32 < pe;
-            if (!fg_any(need)) break;
-            if (need) {
-                cpos += 32;
-                wc = r5_window(bmC, cpos);
-            }
-        }
-        int colon = -1;
-        if (active && wc) {
-            const int c = cpos + fg_ffs(wc) - 1;
-            if (c < pe) colon = c;
-        }
-        if (active) {
-            if (colon < 0) {
-                flags |= 0x02u;  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
-            } else {
-                const int ka = part, kn = colon - part, va = colon + 1, vb = pe;
-                const unsigned long long k8 = lt_load8(p + ka);
-                const uint32_t k4 = (uint32_t)k8;
-                const bool is_time = kn == 4 && k4 == 0x656D6974u;                                       // "time"  :104
-                const bool is_host = kn == 4 && k4 == 0x74736F68u;                                       // "host"
-                const bool is_msg = kn == 7 && (k8 & 0x00FFFFFFFFFFFFFFull) == 0x006567617373656Dull;    // "message"
-                const bool is_level = kn == 5 && (k8 & 0x000000FFFFFFFFFFull) == 0x0000006C6576656Cull;  // "level"  :114
-                if (is_host) { r.host_o = va - ls; r.host_l = vb - va; }
-                if (is_msg) { r.msg_o = va - ls; r.msg_l = vb - va; }
-                if (is_time) {
-                    if (ts_a >= 0) {  // an earlier `time` is still parked: it is evaluated first (a failure returns there)
-                        int a = ts_a, b = ts_b;
-                        if (b - a >= 2 && p[a] == '[' && p[b - 1] == ']') { ++a; --b; }
-                        if (ltsv_parse_ts(p, a, b, r.ts)) have_ts = true;
-                        else { status = FG_EL_TS; err_pos = ts_part; err_set = true; }
-                    }
-                    ts_a = status == FG_ST_OK ? va : -1;
-                    ts_b = vb;
-                    ts_part = part;
-                } else if (is_level) {
-                    if (lv_a >= 0) {  // same for an earlier `level` (:114-121)
-                        uint32_t sev;
-                        if (!parse_u8(p, lv_a, lv_b, sev)) { status = FG_EL_SEV; err_pos = lv_part; err_set = true; }
-                        else if (sev > 7u) { status = FG_EL_SEV_HIGH; err_pos = lv_part; err_set = true; }
-                        else r.severity = sev;
-                    }
-                    lv_a = status == FG_ST_OK ? va : -1;
-                    lv_b = vb;
-                    lv_part = part;
-                } else if (!is_host && !is_msg) {  // :122-199
-                    uint32_t meta = 0;
-                    bool deferred = false;
-                    unsigned long long val = 0;
-                    if (TYPED) {
-                        const int type = lt_schema_type(p, ka, kn, k8, S);
-                        if (type != 0) {
-                            meta = (uint32_t)type;  // FG_TAG_* == fg_ltsv_type
-                            if (ltsv_needs_suffix(p, ka, kn, type, cfg)) meta |= 0x20u;  // FG_EM_SUFFIX
-                            int q = -1;  // first free slot of this type (static indices: the arrays stay in registers)
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (q < 0 && (u >> 1) == type - 1 && pk_info[u] == 0xFFFFFFFFu) q = u;
-                            if (q >= 0 && n < 65535u) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u)
-                                    if (u == q) { pk_va[u] = va; pk_pt[u] = part; pk_info[u] = (uint32_t)(vb - va) | (n << 16); }
-                                deferred = true;
-                            } else {
-                                status = ltsv_parse_typed(p, va, vb, type, val);
-                            }
-                        }
-                    }
-                    if (status == FG_ST_OK) {
-                        stage[n] = lt_pack_entry(ka, kn, vb - va, meta);
-                        if (TYPED && !deferred) stage_val[n] = val;
-                        ++n;
-                    }
-                }
-            }
-            if (status != FG_ST_OK) {
-                if (!err_set) err_pos = part;  // the error belongs to the current part (unless an earlier parked value failed)
-                active = false;
-            } else if (pe >= le) {
-                active = false;
-            } else {
-                part = pe + 1;
-            }
-        }
+    if (t_a >= 0 && (uint32_t)t_k < (err >> 8)) {
+        int a = t_a, b = t_b;
+        if (b - a >= 2 && T[a] == '[' && T[b - 1] == ']') { ++a; --b; }  // :105-109
+        double ts;
+        if (ltsv_parse_ts(T, a, b, ts)) { r.ts = ts; have_ts = true; }
+        else err = ((uint32_t)t_k << 8) | FG_EL_TS;
     }
-    // Parked work, in lock step.  All of it is pure, so it is evaluated even when a later part already failed.
-    {
-        const bool pend = active_line && ts_a >= 0 && (status == FG_ST_OK || ts_part < err_pos);
-        if (fg_any(pend)) {
-            if (pend) {
-                int a = ts_a, b = ts_b;
-                if (b - a >= 2 && p[a] == '[' && p[b - 1] == ']') { ++a; --b; }  // :105-109
-                double t;
-                if (ltsv_parse_ts(p, a, b, t)) { r.ts = t; have_ts = true; }
-                else { status = FG_EL_TS; err_pos = ts_part; }
-            }
-        }
+    if (l_a >= 0 && (uint32_t)l_k < (err >> 8)) {
+        uint32_t sev;
+        if (!parse_u8(T, l_a, l_b, sev)) err = ((uint32_t)l_k << 8) | FG_EL_SEV;
+        else if (sev > 7u) err = ((uint32_t)l_k << 8) | FG_EL_SEV_HIGH;
+        else r.severity = sev;
     }
-    {
-        const bool pend = active_line && lv_a >= 0 && (status == FG_ST_OK || lv_part < err_pos);
-        if (fg_any(pend)) {
-            if (pend) {
-                uint32_t sev;
-                if (!parse_u8(p, lv_a, lv_b, sev)) { status = FG_EL_SEV; err_pos = lv_part; }
-                else if (sev > 7u) { status = FG_EL_SEV_HIGH; err_pos = lv_part; }
-                else r.severity = sev;
-            }
-        }
+    if (err != 0xFFFFFFFFu) {
+        r.status = err & 0xFFu;
+        return (int)(err >> 8);
     }
-    if (TYPED) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {  // slots 2t, 2t+1 hold values of schema type t + 1: one parser per phase
-            const uint32_t info = pk_info[q];
-            const bool has = active_line && info != 0xFFFFFFFFu && (status == FG_ST_OK || pk_pt[q] < err_pos);
-            if (fg_any(has)) {
-                if (has) {
-                    unsigned long long val = 0;
-                    const uint32_t st = ltsv_parse_typed(p, pk_va[q], pk_va[q] + (int)(info & 0xFFFFu), q / 2 + 1, val);
-                    if (st == FG_ST_OK) stage_val[info >> 16] = val;
-                    else { status = st; err_pos = pk_pt[q]; }
-                }
-            }
-        }
-    }
-    int err_rel = err_pos - ls;
-    if (active_line && status == FG_ST_OK) {
-        if (!have_ts) { status = FG_EL_MISSING_TS; err_rel = (le - ls) + 1; }             // :205
-        else if (r.host_o < 0) { status = FG_EL_MISSING_HOST; err_rel = (le - ls) + 1; }  // :206
-    }
-    if (status == FG_ST_OK) {
-        r.full_o = 0;  // full_msg = the whole line, untrimmed :219
-        r.full_l = le - ls;
-        r.n_entries = n;
-    } else {
-        r.full_o = err_rel;
-    }
-    r.flags = flags;
-    r.status = status;
-    fg_syncwarp();
+    if (!have_ts) r.status = FG_EL_MISSING_TS;          // :205
+    else if (!have_host) r.status = FG_EL_MISSING_HOST;  // :206
+    else r.status = FG_ST_OK;
+    return -1;
 }
 
 }  // namespace fg

@@ -1,14 +1,19 @@
-// fg_parse_ltsv.cu — the LTSV decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline.
+// fg_parse_ltsv.cu — the LTSV decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline, part-parallel.
 //
-//   parse_ltsv_kernel   one CTA = LINES consecutive lines.  (1) thread 0 issues ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP)
-//                       of the CTA's contiguous byte span into the shared-memory tile — HBM is read once, coalesced, with no
-//                       per-thread global loads; (2) all threads sweep the tile 32 bytes per step and write the TAB and ':'
-//                       bitmaps (fg_ltsvfast.cuh stage 1); (3) each line's staging slots are reserved from its TAB count by a
-//                       CTA scan; (4) one thread per line walks its parts over the bitmaps (stage 2, lock step) and stages
-//                       8-byte packed rows; (5) a second CTA scan + ONE global atomic place the rows, which all threads copy
-//                       out slot by slot — consecutive threads write consecutive rows of the three side-table columns.
-//   A line that does not fit the tile (or whose TAB count exceeds the staging area) is parsed by the round-1 scanner
-//   (fg_ltsv.cuh) straight from global memory, through the scratch table.
+//   parse_ltsv_kernel   one CTA = 64 consecutive lines, 256 threads.  Per round:
+//     (1) thread 0 issues ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the lines' contiguous byte span into the
+//         shared-memory tile — HBM is read once, coalesced, with no per-thread global loads;
+//     (2) all threads sweep the tile 32 bytes per step into the TAB bitmap (fg_ltsvfast.cuh stage 1);
+//     (3) one thread per line counts its TABs; a CTA scan reserves one SLOT per part; the thread lists the TAB positions
+//         into its slots;
+//     (4) one thread per SLOT (all 256 threads, over all slots of the round) classifies its part: packed side-table row
+//         into the slot, or — for the reserved keys — the slot number into the line's record (shared-memory atomics);
+//     (5) one thread per typed row parses the schema value; one thread per line parses `time` / `level` and settles the
+//         line's status (the first failing part wins);
+//     (6) the rows of the lines that decoded are compacted by two ballot scans over the slots, placed by ONE global atomic
+//         and written as three coalesced columns; then the row columns of the lines.
+//   Lines with a repeated `time` / `level` key, lines that do not fit the tile and lines with more parts than the CTA has
+//   slots are parsed by the round-1 scanner (fg_ltsv.cuh) straight from global memory, through the scratch table.
 #include "fg_kernels.cuh"
 
 #include "fg_common.cuh"
@@ -21,17 +26,11 @@ namespace fg {
 namespace {
 
 constexpr int kLines = kLtsvLinesPerCta;
+constexpr int kThreads = kLtsvThreadsPerCta;
+constexpr int kWarps = kThreads / 32;
+constexpr int kLtsvCtasPerSm = 4;  // shared memory (tile ~28 KB + slots) allows 4 CTAs: 64 registers keep all of them resident
 constexpr int kStageSlots = kLtsvStageSlots;
 constexpr int kSchemaKeys = 64, kSchemaBlob = 1024, kSuffixBlob = 64;  // larger schemas are read from global memory
-
-// scratch table -> side table (the direct path only)
-__device__ __forceinline__ void copy_rows_direct(uint32_t src, uint32_t dst, uint32_t n, const EntrySink& sink, const EntrySink& tmp) {
-    for (uint32_t k = 0; k < n; ++k) {
-        sink.name[dst + k] = tmp.name[src + k];
-        sink.val[dst + k] = tmp.val[src + k];
-        sink.meta[dst + k] = tmp.meta[src + k];
-    }
-}
 
 __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, const LineResult& res, uint32_t my_begin, uint32_t my_n) {
     const bool ok = res.status == FG_ST_OK;
@@ -44,16 +43,72 @@ __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, c
     P.sd[i] = make_int2((int)my_begin, (int)my_n);
 }
 
-template <int LINES, bool TYPED>
-__global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant__ ParseParams P) {
+// one line through the round-1 scanner, straight from global memory (all threads call; thread 0 does the work)
+__device__ __forceinline__ void direct_line(const ParseParams& P, int line, const EntrySink& sink, const EntrySink& tmp) {
+    const bool act = threadIdx.x == 0;
+    const int d0 = __ldg(P.offsets + line);
+    int len = act ? __ldg(P.offsets + line + 1) - d0 : 0;
+    bool bad_utf8 = false;
+    if (act && P.strip_eol && len > 0) {
+        const uint8_t* lp = P.bytes + d0;
+        if (P.strip_eol == 2) {
+            if (lp[len - 1] == 0) --len;
+        } else if (lp[len - 1] == '\n') {
+            --len;
+            if (len > 0 && lp[len - 1] == '\r') --len;
+        }
+        if (P.line_invalid != nullptr && P.line_invalid[line]) {
+            bad_utf8 = true;
+            len = 0;
+        }
+    }
+    LineResult res;
+    const uint32_t sidx = (uint32_t)d0 / 2u + (uint32_t)(P.line0 + line);  // a row needs >= 1 input byte + its TAB
+    ltsv_parse_line(P.bytes + d0, len, d0, sidx, act, P.ltsv, res, tmp);
+    if (bad_utf8) {
+        res.status = FG_ES_INVALID_UTF8;
+        res.n_entries = 0;
+        res.full_o = 0;
+    }
+    if (act) {
+        const uint32_t my_n = res.status == FG_ST_OK ? res.n_entries : 0u;
+        uint32_t my_begin = 0;
+        if (my_n) {
+            const uint32_t eb = atomicAdd(P.entry_counter, my_n);
+            if ((unsigned long long)eb + my_n <= (unsigned long long)P.entry_cap) {
+                my_begin = eb;
+                for (uint32_t k = 0; k < my_n; ++k) {
+                    sink.name[eb + k] = tmp.name[sidx + k];
+                    sink.val[eb + k] = tmp.val[sidx + k];
+                    sink.meta[eb + k] = tmp.meta[sidx + k];
+                }
+            }
+        }
+        write_row(P, line, d0, res, my_begin, my_n);
+    }
+}
+
+// per-line record of a round (shared memory, one array per field)
+struct LineRecs {
+    int ls[kLines];
+    uint32_t slot0[kLines], nb[kLines];                                       // the line's slots
+    uint32_t host_s[kLines], msg_s[kLines], time_s[kLines], level_s[kLines];  // 1 + slot of the LAST such part (0: none)
+    uint32_t dups[kLines];       // #time | #level << 8
+    uint32_t flags[kLines];      // FG_FLAG_MISSING_VALUE
+    uint32_t err[kLines];        // min over failed typed values of (part index << 8 | status)
+    uint32_t dense0[kLines], dense1[kLines];  // the line's rows are [dense0, dense1) of the round
+    uint32_t state[kLines];      // 0: decoded, rows kept; 1: direct path; 2: not in this round; 3: decoded, no rows (error)
+};
+
+template <bool TYPED>
+__global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
-    __shared__ uint32_t s_ebase, s_slots;
-    __shared__ uint32_t line_slot[LINES];   // first staging slot | rows << 16
-    __shared__ uint32_t line_dense[LINES];  // exclusive sum of the rows of the lines before this one
-    // TYPED: the CTA's copy of the schema and the suffixes (a few hundred bytes) — the walker compares keys against
-    // shared memory instead of pulling the schema through L1 from every lane
+    __shared__ uint32_t s_ebase, s_slots, s_direct;
+    __shared__ uint32_t warp_cnt[kWarps];
+    __shared__ LineRecs L;
+    // TYPED: the CTA's copy of the schema and the suffixes (a few hundred bytes)
     __shared__ uint8_t s_names[TYPED ? kSchemaBlob : 4];
     __shared__ int32_t s_name_off[TYPED ? kSchemaKeys + 1 : 1];
     __shared__ int32_t s_types[TYPED ? kSchemaKeys : 1];
@@ -62,15 +117,16 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
     __shared__ uint32_t s_len_mask;
 
     const int tid = threadIdx.x;
-    const int first = blockIdx.x * LINES;
-    const int last = min(P.n, first + LINES);
-    // behind the tile: the two bitmaps (tile_bytes / 32 + 4 words each), the staged rows, the slot -> line map
+    const uint32_t lane = (uint32_t)tid & 31u, wid = (uint32_t)tid >> 5;
+    const int first = blockIdx.x * kLines;
+    const int last = min(P.n, first + kLines);
+    // behind the tile: the TAB bitmap (tile_bytes / 32 + 4 words), the slots (row | typed value | TAB position | line)
     const int bm_words = P.tile_bytes / 32 + 4;
     uint32_t* bmT = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    uint32_t* bmC = bmT + bm_words;
-    unsigned long long* stage = reinterpret_cast<unsigned long long*>(bmC + bm_words);
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(bmT + bm_words);
     unsigned long long* stage_val = stage + kStageSlots;  // TYPED only
-    uint8_t* slot_line = reinterpret_cast<uint8_t*>(stage + (TYPED ? 2 : 1) * kStageSlots);
+    uint16_t* tabs = reinterpret_cast<uint16_t*>(stage + (TYPED ? 2 : 1) * kStageSlots);
+    uint8_t* slot_line = reinterpret_cast<uint8_t*>(tabs + kStageSlots);
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     LtsvDeviceConfig cfg = P.ltsv;
@@ -78,10 +134,10 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
     if (TYPED) {
         const int nblob = cfg.n_schema > 0 ? cfg.name_off[cfg.n_schema] : 0, nsuf = cfg.suffix_off[5];
         if (cfg.n_schema <= kSchemaKeys && nblob <= kSchemaBlob && nsuf <= kSuffixBlob) {  // CTA-uniform
-            for (int k = tid; k < nblob; k += LINES) s_names[k] = cfg.names[k];
-            for (int k = tid; k <= cfg.n_schema; k += LINES) s_name_off[k] = cfg.name_off[k];
-            for (int k = tid; k < cfg.n_schema; k += LINES) s_types[k] = cfg.types[k];
-            for (int k = tid; k < nsuf; k += LINES) s_suffix[k] = cfg.suffix[k];
+            for (int k = tid; k < nblob; k += kThreads) s_names[k] = cfg.names[k];
+            for (int k = tid; k <= cfg.n_schema; k += kThreads) s_name_off[k] = cfg.name_off[k];
+            for (int k = tid; k < cfg.n_schema; k += kThreads) s_types[k] = cfg.types[k];
+            for (int k = tid; k < nsuf; k += kThreads) s_suffix[k] = cfg.suffix[k];
             __syncthreads();
             if (tid == 0) {
                 uint32_t lm;
@@ -99,56 +155,24 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
     const EntrySink tmp = {P.tmp_name, P.tmp_val, P.tmp_meta};
     uint32_t parity = 0;
     int cur = first;
-    bool direct_next = false;  // CTA-uniform: line `cur` must take the direct path (its TAB count exceeds the staging area)
+    bool direct_next = false;  // CTA-uniform: line `cur` must take the direct path (more parts than the CTA has slots)
     while (cur < last) {
+        // ---- the lines of this round ------------------------------------------------------------------------------
+        const bool lt = tid < kLines;  // line threads
         const int i = cur + tid;
-        const int o0 = __ldg(P.offsets + min(i, last));
-        const int o1 = __ldg(P.offsets + min(i + 1, last));
+        int o0 = 0, o1 = 0;
+        if (lt) {
+            o0 = __ldg(P.offsets + min(i, last));
+            o1 = __ldg(P.offsets + min(i + 1, last));
+        }
         const int ocur = __ldg(P.offsets + cur);
         const int base = ocur & ~15;
         // tile_bytes <= 65024 (launch_parse_ltsv): a line inside the tile is shorter than 64 KiB, positions fit 16 bits
-        const bool fits = !direct_next && (i < last) && (o1 - base <= P.tile_bytes);
+        const bool fits = lt && !direct_next && (i < last) && (o1 - base <= P.tile_bytes);
         int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
         if (r == 0) {
-            // ---- direct path: line `cur` alone, read from global memory by the round-1 scanner ----------------------
             direct_next = false;
-            const bool act = tid == 0;
-            const int d0 = ocur;
-            int len = act ? __ldg(P.offsets + cur + 1) - d0 : 0;
-            bool bad_utf8 = false;
-            if (P.strip_eol && len > 0) {
-                const uint8_t* lp = P.bytes + d0;
-                if (P.strip_eol == 2) {
-                    if (lp[len - 1] == 0) --len;
-                } else if (lp[len - 1] == '\n') {
-                    --len;
-                    if (len > 0 && lp[len - 1] == '\r') --len;
-                }
-                if (P.line_invalid != nullptr && P.line_invalid[cur]) {
-                    bad_utf8 = true;
-                    len = 0;
-                }
-            }
-            LineResult res;
-            const uint32_t sidx = (uint32_t)d0 / 2u + (uint32_t)(P.line0 + cur);  // Format<1>::scratch_index
-            ltsv_parse_line(P.bytes + d0, len, d0, sidx, act, P.ltsv, res, tmp);
-            if (bad_utf8) {
-                res.status = FG_ES_INVALID_UTF8;
-                res.n_entries = 0;
-                res.full_o = 0;
-            }
-            if (act) {
-                const uint32_t my_n = res.status == FG_ST_OK ? res.n_entries : 0u;
-                uint32_t my_begin = 0;
-                if (my_n) {
-                    const uint32_t eb = atomicAdd(P.entry_counter, my_n);
-                    if ((unsigned long long)eb + my_n <= (unsigned long long)P.entry_cap) {
-                        my_begin = eb;
-                        copy_rows_direct(sidx, eb, my_n, sink, tmp);
-                    }
-                }
-                write_row(P, cur, d0, res, my_begin, my_n);
-            }
+            direct_line(P, cur, sink, tmp);
             __syncthreads();
             cur += 1;
             continue;
@@ -163,28 +187,20 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- stage 1: TAB and ':' bitmaps of the whole tile, 32 bytes (= one word of each) per thread per step -------
+        // ---- (2) the TAB bitmap of the whole tile, 32 bytes (= one word) per thread per step --------------------------
         const int nword = (int)((nbytes + 31u) >> 5);  // the tile allocation is a multiple of 512 bytes: reading the odd granule is safe
-        for (int g = tid; g < nword; g += LINES) {
+        for (int g = tid; g < nword; g += kThreads) {
             const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
-            uint32_t t0, c0, t1, c1;
-            lt_classify16(v0.x, v0.y, v0.z, v0.w, t0, c0);
-            lt_classify16(v1.x, v1.y, v1.z, v1.w, t1, c1);
-            bmT[g] = t0 | (t1 << 16);
-            bmC[g] = c0 | (c1 << 16);
-        }
-        if (tid < 4) {  // the walker's windows read up to two words past the last one
-            bmT[nword + tid] = 0;
-            bmC[nword + tid] = 0;
+            bmT[g] = lt_tab16(v0.x, v0.y, v0.z, v0.w) | (lt_tab16(v1.x, v1.y, v1.z, v1.w) << 16);
         }
         __syncthreads();
 
-        // ---- the lines of this round; staging slots from the TAB counts -------------------------------------------
-        bool active = tid < r;
-        int ls = active ? o0 - base : 0;
+        // ---- (3) slots: one per part ----------------------------------------------------------------------------------
+        bool active = lt && tid < r;
+        const int ls = active ? o0 - base : 0;
         int le = active ? o1 - base : 0;
         bool bad_utf8 = false;
-        if (P.strip_eol && le > ls) {
+        if (active && P.strip_eol && le > ls) {
             // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
             if (P.strip_eol == 2) {  // BufRead::split(0): only the NUL terminator goes (nul_splitter.rs:18)
                 if (tile[le - 1] == 0) --le;
@@ -195,67 +211,193 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
             if (P.line_invalid != nullptr && P.line_invalid[i]) bad_utf8 = true;
         }
         const bool walk = active && !bad_utf8;
-        const uint32_t nb = walk ? (uint32_t)lt_count_tabs(bmT, ls, le) + 1u : 0u;  // #parts >= #pairs
+        const uint32_t nb = walk ? (uint32_t)lt_count_tabs(bmT, ls, le) + 1u : 0u;
         uint32_t slots_total;
         const uint32_t slot0 = block_exclusive_scan(nb, scan_ws, slots_total);
         if (slots_total > (uint32_t)kStageSlots) {  // CTA-uniform, rare: keep the lines whose slots fit, redo the rest next round
             const int r2 = __syncthreads_count(active && slot0 + nb <= (uint32_t)kStageSlots);
-            if (r2 == 0) {  // the first line alone has more parts than the staging area: direct path
+            if (r2 == 0) {  // the first line alone has more parts than there are slots: direct path
                 direct_next = true;
                 __syncthreads();
                 continue;
             }
             r = r2;
-            active = tid < r;
+            active = lt && tid < r;
         }
-        const bool walk2 = walk && active;
-
-        // ---- stage 2: one thread per line ------------------------------------------------------------------------
-        LineResult res;
-        ltsv_walk<TYPED>(tile, bmT, bmC, ls, walk2 ? le : ls, walk2, cfg, S, res, stage + slot0, stage_val + slot0);
-        if (bad_utf8) {
-            res.status = FG_ES_INVALID_UTF8;
-            res.n_entries = 0;
-            res.full_o = 0;
+        const bool mine = walk && active;
+        if (lt) {
+            L.ls[tid] = ls;
+            L.slot0[tid] = slot0;
+            L.nb[tid] = mine ? nb : 0u;
+            L.host_s[tid] = L.msg_s[tid] = L.time_s[tid] = L.level_s[tid] = 0u;
+            L.dups[tid] = 0u;
+            L.flags[tid] = 0u;
+            L.err[tid] = 0xFFFFFFFFu;
+            L.dense0[tid] = L.dense1[tid] = 0u;
+            L.state[tid] = active ? 0u : 2u;
+            if (tid == r - 1) s_slots = slot0 + (mine ? nb : 0u);
+            if (tid == 0) s_direct = 0u;
         }
-        const uint32_t my_n = (walk2 && res.status == FG_ST_OK) ? res.n_entries : 0u;
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
-        line_slot[tid] = slot0 | (my_n << 16);
-        line_dense[tid] = excl;
-        if (walk2)
+        if (mine) {
+            lt_list_tabs(bmT, ls, le, tabs + slot0);
             for (uint32_t k = 0; k < nb; ++k) slot_line[slot0 + k] = (uint8_t)tid;
-        if (tid == r - 1) s_slots = slot0 + nb;  // slots in use this round
-        if (tid == 0 && total) s_ebase = atomicAdd(P.entry_counter, total);
+        }
         __syncthreads();
-        uint32_t my_begin = 0;
-        if (total) {  // CTA-uniform
-            const uint32_t ebase = s_ebase;
-            const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
-            if (!ovf) {
-                if (my_n) my_begin = ebase + excl;
-                // every staged row -> the three side-table columns; slot s of line l is row (s - first slot of l)
-                const uint32_t nslots = s_slots;
-                for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)LINES) {
-                    const uint32_t l = slot_line[s];
-                    const uint32_t ls_n = line_slot[l];
-                    const uint32_t k = s - (ls_n & 0xFFFFu);
-                    if (k < (ls_n >> 16)) {
-                        const unsigned long long e = stage[s];
-                        const uint32_t j = ebase + line_dense[l] + k;
-                        const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
-                        const uint32_t meta = (uint32_t)(e >> 56);
-                        sink.name[j] = make_int2(ka, kn);
-                        unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
-                        if (TYPED && (meta & 0x07u) != 0u) v = stage_val[s];
-                        sink.val[j] = v;
-                        sink.meta[j] = (uint8_t)meta;
+        const uint32_t nslots = s_slots;
+
+        // ---- (4) one thread per part ----------------------------------------------------------------------------------
+        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
+            const uint32_t l = slot_line[s];
+            const uint32_t k = s - L.slot0[l];
+            const int start = k == 0u ? L.ls[l] : (int)tabs[s - 1] + 1;
+            const int end = (int)tabs[s];
+            const LtPart pt = lt_part<TYPED>(tile, start, end, cfg, S);
+            stage[s] = pt.row;
+            if (pt.kind != LP_ROW) {  // ~4 of 20 parts
+                if (pt.kind == LP_NONE) atomicOr(&L.flags[l], 0x02u);  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
+                else if (pt.kind == LP_HOST) atomicMax(&L.host_s[l], s + 1u);
+                else if (pt.kind == LP_MSG) atomicMax(&L.msg_s[l], s + 1u);
+                else if (pt.kind == LP_TIME) { atomicMax(&L.time_s[l], s + 1u); atomicAdd(&L.dups[l], 1u); }
+                else { atomicMax(&L.level_s[l], s + 1u); atomicAdd(&L.dups[l], 0x100u); }
+            }
+        }
+        __syncthreads();
+
+        // ---- (5) values: typed rows (one thread per row), then `time` / `level` and the status (one thread per line) ----
+        if (TYPED) {
+            for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
+                const unsigned long long e = stage[s];
+                const int type = (int)((e >> 56) & 0x07u);
+                if (type != 0) {
+                    const int va = (int)(e & 0xFFFFu) + (int)((e >> 16) & 0xFFFFu) + 1;
+                    unsigned long long val = 0;
+                    const uint32_t st = ltsv_parse_typed(tile, va, va + (int)((e >> 32) & 0xFFFFFFu), type, val);
+                    if (st == FG_ST_OK) stage_val[s] = val;
+                    else {
+                        const uint32_t l = slot_line[s];
+                        atomicMin(&L.err[l], ((s - L.slot0[l]) << 8) | st);
                     }
                 }
             }
+            __syncthreads();
         }
-        if (active) write_row(P, i, o0, res, my_begin, my_n);
-        __syncthreads();  // tile, bitmaps, staging and scan scratch are reused by the next round
+        LineResult res;
+        res.ts = 0.0;
+        res.facility = 0xFFu;
+        res.severity = 0xFFu;
+        res.flags = 0;
+        res.status = FG_ST_OK;
+        res.host_o = res.app_o = res.proc_o = res.mid_o = res.msg_o = res.full_o = -1;
+        res.host_l = res.app_l = res.proc_l = res.mid_l = res.msg_l = res.full_l = 0;
+        res.n_entries = 0;
+        bool direct = false;
+        if (mine) {
+            const uint32_t d = L.dups[tid];
+            if ((d & 0xFFu) > 1u || (d >> 8) > 1u) {
+                direct = true;  // a repeated `time` / `level`: every occurrence is evaluated in order (:104-121) — round-1 scanner
+            } else {
+                // value bounds of the special parts: slot s covers [start, tabs[s]), the value starts behind `key:`
+                auto value_of = [&](uint32_t s1, int key_len, int& a, int& b, int& k) {
+                    a = -1; b = 0; k = 0;
+                    if (s1 == 0u) return;
+                    const uint32_t s = s1 - 1u;
+                    k = (int)(s - slot0);
+                    const int start = k == 0 ? ls : (int)tabs[s - 1] + 1;
+                    a = start + key_len + 1;
+                    b = (int)tabs[s];
+                };
+                int t_a, t_b, t_k, l_a, l_b, l_k, h_a, h_b, h_k, m_a, m_b, m_k;
+                value_of(L.time_s[tid], 4, t_a, t_b, t_k);
+                value_of(L.level_s[tid], 5, l_a, l_b, l_k);
+                value_of(L.host_s[tid], 4, h_a, h_b, h_k);
+                value_of(L.msg_s[tid], 7, m_a, m_b, m_k);
+                const int bad_k = lt_finish_line(tile, t_a, t_b, t_k, l_a, l_b, l_k, L.err[tid], h_a >= 0, res);
+                res.flags = L.flags[tid];
+                if (res.status == FG_ST_OK) {
+                    if (h_a >= 0) { res.host_o = h_a - ls; res.host_l = h_b - h_a; }
+                    if (m_a >= 0) { res.msg_o = m_a - ls; res.msg_l = m_b - m_a; }
+                    res.full_o = 0;  // full_msg = the whole line, untrimmed :219
+                    res.full_l = le - ls;
+                } else {
+                    // the failing part (LTSV side effects on the host stop there); a missing timestamp / hostname: after the last part
+                    res.full_o = bad_k >= 0 ? (bad_k == 0 ? ls : (int)tabs[slot0 + (uint32_t)bad_k - 1u] + 1) - ls : (le - ls) + 1;
+                    res.severity = 0xFFu;
+                    res.ts = 0.0;
+                }
+            }
+            L.state[tid] = direct ? 1u : (res.status == FG_ST_OK ? 0u : 3u);
+            if (direct) atomicAdd(&s_direct, 1u);
+        }
+        if (bad_utf8) {
+            res.status = FG_ES_INVALID_UTF8;
+            res.full_o = 0;
+            if (active) L.state[tid] = 3u;
+        }
+        __syncthreads();
+
+        // ---- (6) rows of the decoded lines: count, place, write -------------------------------------------------------
+        // pass A: rows per thread -> total of the round
+        uint32_t mycnt = 0;
+        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads)
+            mycnt += (stage[s] != 0ull && L.state[slot_line[s]] == 0u) ? 1u : 0u;
+        uint32_t total;
+        (void)block_exclusive_scan(mycnt, scan_ws, total);
+        if (tid == 0 && total) s_ebase = atomicAdd(P.entry_counter, total);
+        __syncthreads();
+        const uint32_t ebase = total ? s_ebase : 0u;
+        const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
+        // pass B: slot order = row order; a ballot scan per chunk of 256 slots
+        uint32_t run = 0;
+        for (uint32_t cb = 0; cb < nslots; cb += (uint32_t)kThreads) {
+            const uint32_t s = cb + (uint32_t)tid;
+            unsigned long long e = 0;
+            uint32_t l = 0;
+            bool keep = false;
+            if (s < nslots) {
+                e = stage[s];
+                l = slot_line[s];
+                keep = e != 0ull && L.state[l] == 0u;
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) warp_cnt[wid] = (uint32_t)__popc(bal);
+            __syncthreads();
+            uint32_t before = run, chunk = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t c = warp_cnt[w];
+                if ((uint32_t)w < wid) before += c;
+                chunk += c;
+            }
+            const uint32_t idx = before + (uint32_t)__popc(bal & ((1u << lane) - 1u));  // rows of the round before this slot
+            if (s < nslots) {
+                const uint32_t k = s - L.slot0[l];
+                if (k == 0u) L.dense0[l] = idx;
+                if (k + 1u == L.nb[l]) L.dense1[l] = idx + (keep ? 1u : 0u);
+                if (keep && !ovf) {
+                    const uint32_t j = ebase + idx;
+                    const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
+                    const uint32_t meta = (uint32_t)(e >> 56) & 0x7Fu;  // without kLtRow
+                    sink.name[j] = make_int2(ka, kn);
+                    unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
+                    if (TYPED && (meta & 0x07u) != 0u) v = stage_val[s];
+                    sink.val[j] = v;
+                    sink.meta[j] = (uint8_t)meta;
+                }
+            }
+            run += chunk;
+            __syncthreads();  // warp_cnt is reused by the next chunk; dense0/1 are read below
+        }
+        if (active && !direct) {
+            const uint32_t my_n = (L.state[tid] == 0u && !ovf) ? L.dense1[tid] - L.dense0[tid] : 0u;
+            write_row(P, i, o0, res, my_n ? ebase + L.dense0[tid] : 0u, my_n);
+        }
+
+        // ---- lines of this round that need the sequential scanner (CTA-uniform loop, rare) -----------------------------
+        if (s_direct) {
+            for (int l = 0; l < r; ++l)
+                if (L.state[l] == 1u) direct_line(P, cur + l, sink, tmp);  // shared memory: the same for every thread
+        }
+        __syncthreads();  // tile, bitmap, slots and the line records are reused by the next round
         cur += r;
     }
 }
@@ -263,14 +405,14 @@ __global__ void __launch_bounds__(LINES) parse_ltsv_kernel(const __grid_constant
 }  // namespace
 
 int parse_ltsv_smem_bytes(int tile_bytes, bool typed) {
-    return tile_bytes + 2 * (tile_bytes / 32 + 4) * 4 + kStageSlots * 8 * (typed ? 2 : 1) + kStageSlots + 16;
+    return tile_bytes + (tile_bytes / 32 + 4) * 4 + kLtsvStageSlots * 8 * (typed ? 2 : 1) + kLtsvStageSlots * 2 + kLtsvStageSlots + 16;
 }
 
 cudaError_t configure_parse_ltsv(int max_tile_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(parse_ltsv_kernel<kLines, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(parse_ltsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          parse_ltsv_smem_bytes(max_tile_bytes, false));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(parse_ltsv_kernel<kLines, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(parse_ltsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 parse_ltsv_smem_bytes(max_tile_bytes, true));
 }
 
@@ -279,8 +421,8 @@ cudaError_t launch_parse_ltsv(const ParseParams& p, cudaStream_t stream) {
     if (p.tile_bytes <= 0 || p.tile_bytes > kLtsvMaxTile || (p.tile_bytes & 511)) return cudaErrorInvalidValue;
     const int grid = (p.n + kLines - 1) / kLines;
     const bool typed = p.ltsv.has_schema != 0;
-    if (typed) parse_ltsv_kernel<kLines, true><<<grid, kLines, parse_ltsv_smem_bytes(p.tile_bytes, true), stream>>>(p);
-    else parse_ltsv_kernel<kLines, false><<<grid, kLines, parse_ltsv_smem_bytes(p.tile_bytes, false), stream>>>(p);
+    if (typed) parse_ltsv_kernel<true><<<grid, kThreads, parse_ltsv_smem_bytes(p.tile_bytes, true), stream>>>(p);
+    else parse_ltsv_kernel<false><<<grid, kThreads, parse_ltsv_smem_bytes(p.tile_bytes, false), stream>>>(p);
     return cudaGetLastError();
 }
 

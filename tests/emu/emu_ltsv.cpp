@@ -1,8 +1,8 @@
 // emu_ltsv.cpp — CPU emulation of the LTSV device logic (TEST INFRASTRUCTURE, see cuda_shim.h).
 //
-// Compiles the product's walker sources (fg_ltsvfast.cuh: stage-1 TAB / ':' bitmaps, stage-2 part walk; fg_ltsv.cuh: the
+// Compiles the product's device sources (fg_ltsvfast.cuh: stage-1 TAB bitmap, lt_part, lt_finish_line; fg_ltsv.cuh: the
 // value parsers and the direct-path scanner) with g++ and replays what parse_ltsv_kernel does with them — CTA rounds over
-// a staging tile, slot reservation from the TAB counts, staged 8-byte rows, side-table placement — one lane at a time.
+// a staging tile, one slot per tab-separated part, the per-part and per-line phases, side-table placement — one thread at a time.
 // The result has the layout of fg_batch_out (columnar rows + side table), so the CPU test-suite can push it through the
 // product's materialiser and compare with the oracle without a GPU.
 #define FG_HOST_EMU 1
@@ -42,11 +42,20 @@ void put_row(Tables& t, int i, int o0, const fg::LineResult& res, uint32_t begin
 
 extern "C" {
 
-// the two 16-bit masks of stage 1 (TAB | ':' << 16), exposed so tests can pin the SWAR identity per byte
+// stage 1's TAB mask of a 16-byte granule | (the ':' mask of its first 8 bytes, lt_colon_flags8, << 16): exposed so tests
+// can pin the SWAR identities per byte
 uint32_t emu_ltsv_classify16(const uint8_t* p) {
     uint32_t w[4], t, c;
     memcpy(w, p, 16);
-    fg::lt_classify16(w[0], w[1], w[2], w[3], t, c);
+    t = fg::lt_tab16(w[0], w[1], w[2], w[3]);
+    unsigned long long k8;
+    memcpy(&k8, p, 8);
+    const unsigned long long z = fg::lt_colon_flags8(k8);
+    c = 0;
+    for (int b = 0; b < 8; ++b)
+        if ((z >> (8 * b + 7)) & 1ull) c |= 1u << b;
+    if (z && !((c >> fg::lt_first_flag8(z)) & 1u)) c = 0xFFFFu;  // the first-flag index must name a flagged byte
+    if (z && (c & ((1u << fg::lt_first_flag8(z)) - 1u))) c = 0xFFFFu;  // ... the lowest one
     return t | (c << 16);
 }
 
@@ -89,7 +98,7 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
     const int64_t total_bytes = n > 0 ? offsets[n] : 0;
     std::vector<uint8_t> tile((size_t)tile_bytes + 64);
     const int bm_words = tile_bytes / 32 + 4;
-    std::vector<uint32_t> bmT((size_t)bm_words + 4), bmC((size_t)bm_words + 4);
+    std::vector<uint32_t> bmT((size_t)bm_words + 4);
     std::vector<unsigned long long> stage((size_t)kSlots), stage_val((size_t)kSlots);
     // scratch table of the direct path
     std::vector<fg_span> tname;
@@ -147,13 +156,9 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
             const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
             for (uint32_t k = 0; k < nbytes; ++k) tile[k] = (int64_t)base + k < total_bytes ? bytes[base + k] : 0;  // the bulk copy
             const int nword = (int)((nbytes + 31u) >> 5);
-            for (int g = 0; g < nword; ++g) {
-                const uint32_t a = emu_ltsv_classify16(tile.data() + 32 * g), b = emu_ltsv_classify16(tile.data() + 32 * g + 16);
-                bmT[g] = (a & 0xFFFFu) | (b << 16);
-                bmC[g] = (a >> 16) | (b & 0xFFFF0000u);
-            }
-            for (int k = 0; k < 4; ++k) bmT[nword + k] = bmC[nword + k] = 0;
-            // slot reservation
+            for (int g = 0; g < nword; ++g)
+                bmT[g] = (emu_ltsv_classify16(tile.data() + 32 * g) & 0xFFFFu) | (emu_ltsv_classify16(tile.data() + 32 * g + 16) << 16);
+            // (3) slots: one per part
             std::vector<int> ls((size_t)r), le((size_t)r);
             std::vector<uint32_t> nb((size_t)r), slot0((size_t)r);
             std::vector<char> bad((size_t)r, 0);
@@ -182,28 +187,91 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                 continue;
             }
             r = r2;
+            std::vector<uint16_t> tabs((size_t)kSlots + 1);
+            for (int tid = 0; tid < r; ++tid)
+                if (!bad[tid]) fg::lt_list_tabs(bmT.data(), ls[tid], le[tid], tabs.data() + slot0[tid]);
             for (int tid = 0; tid < r; ++tid) {
                 const int i = cur + tid;
                 fg::LineResult res;
-                const bool walk = !bad[tid];
-                if (typed) fg::ltsv_walk<true>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, S, res,
-                                               stage.data() + slot0[tid], stage_val.data() + slot0[tid]);
-                else fg::ltsv_walk<false>(tile.data(), bmT.data(), bmC.data(), ls[tid], walk ? le[tid] : ls[tid], walk, cfg, S, res,
-                                          stage.data() + slot0[tid], stage_val.data() + slot0[tid]);
-                if (bad[tid]) { res.status = FG_ES_INVALID_UTF8; res.n_entries = 0; res.full_o = 0; }
-                const uint32_t my_n = (walk && res.status == FG_ST_OK) ? res.n_entries : 0u;
-                const uint32_t begin = my_n ? (uint32_t)T->ename.size() : 0u;
-                for (uint32_t k = 0; k < my_n; ++k) {  // the copy-out of parse_ltsv_kernel
-                    const unsigned long long e = stage[slot0[tid] + k];
-                    const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
-                    const uint32_t meta = (uint32_t)(e >> 56);
-                    unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
-                    if (typed && (meta & 0x07u) != 0u) v = stage_val[slot0[tid] + k];
-                    T->ename.push_back(fg_span{ka, kn});
-                    T->eval.push_back(v);
-                    T->emeta.push_back((uint8_t)meta);
+                res.ts = 0.0; res.facility = 0xFFu; res.severity = 0xFFu; res.flags = 0; res.status = FG_ST_OK;
+                res.host_o = res.app_o = res.proc_o = res.mid_o = res.msg_o = res.full_o = -1;
+                res.host_l = res.app_l = res.proc_l = res.mid_l = res.msg_l = res.full_l = 0;
+                res.n_entries = 0;
+                if (bad[tid]) {
+                    res.status = FG_ES_INVALID_UTF8;
+                    res.full_o = 0;
+                    put_row(*T, i, offsets[i], res, 0, 0);
+                    continue;
                 }
-                put_row(*T, i, offsets[i], res, begin, my_n);
+                // (4) parts, (5) typed values
+                uint32_t host_s = 0, msg_s = 0, time_s = 0, level_s = 0, ntime = 0, nlevel = 0, flags = 0, err = 0xFFFFFFFFu;
+                for (uint32_t k = 0; k < nb[tid]; ++k) {
+                    const uint32_t sl = slot0[tid] + k;
+                    const int start = k == 0 ? ls[tid] : (int)tabs[sl - 1] + 1, end = (int)tabs[sl];
+                    const fg::LtPart pt = typed ? fg::lt_part<true>(tile.data(), start, end, cfg, S) : fg::lt_part<false>(tile.data(), start, end, cfg, S);
+                    stage[sl] = pt.row;
+                    if (pt.kind == fg::LP_NONE) flags |= 0x02u;
+                    else if (pt.kind == fg::LP_HOST) host_s = sl + 1;
+                    else if (pt.kind == fg::LP_MSG) msg_s = sl + 1;
+                    else if (pt.kind == fg::LP_TIME) { time_s = sl + 1; ++ntime; }
+                    else if (pt.kind == fg::LP_LEVEL) { level_s = sl + 1; ++nlevel; }
+                    const int type = (int)((pt.row >> 56) & 0x07u);
+                    if (typed && type != 0) {
+                        const int va = start + pt.kn + 1;
+                        unsigned long long val = 0;
+                        const uint32_t st = fg::ltsv_parse_typed(tile.data(), va, end, type, val);
+                        if (st == FG_ST_OK) stage_val[sl] = val;
+                        else err = std::min(err, (k << 8) | st);
+                    }
+                }
+                if (ntime > 1 || nlevel > 1) {  // a repeated `time` / `level`: the round-1 scanner
+                    direct_line(i);
+                    continue;
+                }
+                auto value_of = [&](uint32_t s1, int key_len, int& a, int& b, int& k) {
+                    a = -1; b = 0; k = 0;
+                    if (s1 == 0u) return;
+                    const uint32_t sl = s1 - 1u;
+                    k = (int)(sl - slot0[tid]);
+                    const int start = k == 0 ? ls[tid] : (int)tabs[sl - 1] + 1;
+                    a = start + key_len + 1;
+                    b = (int)tabs[sl];
+                };
+                int t_a, t_b, t_k, l_a, l_b, l_k, h_a, h_b, h_k, m_a, m_b, m_k;
+                value_of(time_s, 4, t_a, t_b, t_k);
+                value_of(level_s, 5, l_a, l_b, l_k);
+                value_of(host_s, 4, h_a, h_b, h_k);
+                value_of(msg_s, 7, m_a, m_b, m_k);
+                const int bad_k = fg::lt_finish_line(tile.data(), t_a, t_b, t_k, l_a, l_b, l_k, err, h_a >= 0, res);
+                res.flags = flags;
+                if (res.status == FG_ST_OK) {
+                    if (h_a >= 0) { res.host_o = h_a - ls[tid]; res.host_l = h_b - h_a; }
+                    if (m_a >= 0) { res.msg_o = m_a - ls[tid]; res.msg_l = m_b - m_a; }
+                    res.full_o = 0;
+                    res.full_l = le[tid] - ls[tid];
+                } else {
+                    res.full_o = bad_k >= 0 ? (bad_k == 0 ? ls[tid] : (int)tabs[slot0[tid] + (uint32_t)bad_k - 1u] + 1) - ls[tid] : (le[tid] - ls[tid]) + 1;
+                    res.severity = 0xFFu;
+                    res.ts = 0.0;
+                }
+                // (6) the rows of the line, in slot order
+                uint32_t my_n = 0;
+                const uint32_t begin = (uint32_t)T->ename.size();
+                if (res.status == FG_ST_OK) {
+                    for (uint32_t k = 0; k < nb[tid]; ++k) {
+                        const unsigned long long e = stage[slot0[tid] + k];
+                        if (e == 0ull) continue;
+                        const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
+                        const uint32_t meta = (uint32_t)(e >> 56) & 0x7Fu;
+                        unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
+                        if (typed && (meta & 0x07u) != 0u) v = stage_val[slot0[tid] + k];
+                        T->ename.push_back(fg_span{ka, kn});
+                        T->eval.push_back(v);
+                        T->emeta.push_back((uint8_t)meta);
+                        ++my_n;
+                    }
+                }
+                put_row(*T, i, offsets[i], res, my_n ? begin : 0u, my_n);
             }
             cur += r;
         }
