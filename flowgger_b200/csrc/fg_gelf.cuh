@@ -481,43 +481,42 @@ struct GelfAcc {
     uint32_t status, flags, kept;
     bool have_ts;
 };
-static __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta,
-                                               LineResult& r, GelfAcc& g, const EntrySink& sink, uint32_t sbase) {
+enum { GKEY_OTHER = 0, GKEY_TIMESTAMP, GKEY_HOST, GKEY_SHORT, GKEY_FULL, GKEY_VERSION, GKEY_LEVEL };
+
+// the rule of one key class; `kind` = GKEY_* of the (unescaped) key
+FG_DEV void gelf_apply_kind(int kind, bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta, LineResult& r,
+                            GelfAcc& g, const EntrySink& sink, uint32_t sbase) {
     const int ks = name.x - line_off, ke = ks + name.y;
     const uint32_t tag = meta & 7u;
     const int vs = (int)(uint32_t)(val & 0xFFFFFFFFull) - line_off, vl = (int)(val >> 32);
-    // reserved keys contain no '_' and differ in their first byte: skip the literal compares for ordinary `_extra` keys
-    const uint32_t k0 = (ke > ks) ? p[ks] : 0u;
-    const bool maybe = k0 == 't' || k0 == 'h' || k0 == 's' || k0 == 'f' || k0 == 'v' || k0 == 'l' || k0 == '\\';
     const bool kesc = (meta & 0x40u) != 0, vesc = (meta & 0x08u) != 0;
-    auto key_is = [&](const char* lit, int n) { return kesc ? json_str_is(p, ks, ke, mode2, lit, n) : raw_str_is(p, ks, ke, lit, n); };
     auto val_is = [&](const char* lit, int n) { return vesc ? json_str_is(p, vs, vs + vl, mode2, lit, n) : raw_str_is(p, vs, vs + vl, lit, n); };
-    if (maybe && key_is("timestamp", 9)) {  // as_f64 :53
+    if (kind == GKEY_TIMESTAMP) {  // as_f64 :53
         if (tag == JT_F64) r.ts = __longlong_as_double((long long)val);
         else if (tag == JT_U64) r.ts = __ull2double_rn(val);
         else if (tag == JT_I64) r.ts = __ll2double_rn((long long)val);
         else g.status = FG_EG_TS;
         g.have_ts = true;
-    } else if (maybe && key_is("host", 4)) {
+    } else if (kind == GKEY_HOST) {
         if (tag != JT_STRING) g.status = FG_EG_HOST;
         else { r.host_o = vs; r.host_l = vl; if (meta & 0x08u) g.flags |= 0x04u; }
-    } else if (maybe && key_is("short_message", 13)) {
+    } else if (kind == GKEY_SHORT) {
         if (tag != JT_STRING) g.status = FG_EG_SHORT;
         else { r.msg_o = vs; r.msg_l = vl; if (meta & 0x08u) g.flags |= 0x08u; }
-    } else if (maybe && key_is("full_message", 12)) {
+    } else if (kind == GKEY_FULL) {
         if (tag != JT_STRING) g.status = FG_EG_FULL;
         else { r.full_o = vs; r.full_l = vl; if (meta & 0x08u) g.flags |= 0x10u; }
-    } else if (maybe && key_is("version", 7)) {
+    } else if (kind == GKEY_VERSION) {
         if (tag != JT_STRING) g.status = FG_EG_VERSION_T;
         else if (!val_is("1.0", 3) && !val_is("1.1", 3)) g.status = FG_EG_VERSION;
-    } else if (maybe && key_is("level", 5)) {  // as_u64 :83
+    } else if (kind == GKEY_LEVEL) {  // as_u64 :83
         if (tag != JT_U64) g.status = FG_EG_SEV;
         else if (val > 7ull) g.status = FG_EG_SEV_HIGH;
         else r.severity = (uint32_t)val;
     } else {
         if (tag == JT_CONTAINER) g.status = FG_EG_SD_TYPE;  // :97
         else {
-            bool under = k0 == '_';
+            bool under = (ke > ks) && p[ks] == '_';
             if (kesc) {
                 KeyIter it;
                 key_iter_init(it, p, ks, ke, mode2);
@@ -530,6 +529,26 @@ static __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, b
             ++g.kept;
         }
     }
+}
+
+static __device__ __noinline__ void gelf_apply_member(bytes_t p, int line_off, bool mode2, int2 name, unsigned long long val, uint32_t meta,
+                                                      LineResult& r, GelfAcc& g, const EntrySink& sink, uint32_t sbase) {
+    const int ks = name.x - line_off, ke = ks + name.y;
+    // reserved keys contain no '_' and differ in their first byte: skip the literal compares for ordinary `_extra` keys
+    const uint32_t k0 = (ke > ks) ? p[ks] : 0u;
+    const bool maybe = k0 == 't' || k0 == 'h' || k0 == 's' || k0 == 'f' || k0 == 'v' || k0 == 'l' || k0 == '\\';
+    const bool kesc = (meta & 0x40u) != 0;
+    auto key_is = [&](const char* lit, int n) { return kesc ? json_str_is(p, ks, ke, mode2, lit, n) : raw_str_is(p, ks, ke, lit, n); };
+    int kind = GKEY_OTHER;
+    if (maybe) {
+        if (key_is("timestamp", 9)) kind = GKEY_TIMESTAMP;
+        else if (key_is("host", 4)) kind = GKEY_HOST;
+        else if (key_is("short_message", 13)) kind = GKEY_SHORT;
+        else if (key_is("full_message", 12)) kind = GKEY_FULL;
+        else if (key_is("version", 7)) kind = GKEY_VERSION;
+        else if (key_is("level", 5)) kind = GKEY_LEVEL;
+    }
+    gelf_apply_kind(kind, p, line_off, mode2, name, val, meta, r, g, sink, sbase);
 }
 
 FG_DEV void gelf_result_init(LineResult& r) {

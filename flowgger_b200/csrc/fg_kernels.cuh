@@ -163,12 +163,17 @@ constexpr int kLtsvLinesPerCta = FG_LTSV_LINES;
 constexpr int kLtsvThreadsPerCta = FG_LTSV_THREADS;
 constexpr int kLtsvStageSlots = kLtsvLinesPerCta * 24;
 constexpr int kLtsvMaxTile = 65024;  // tile positions are packed into 16 bits
-// GELF (fg_parse_gelf.cu): 64-line CTAs; the staging area holds kGelfStageSlots side-table rows per CTA round
+// GELF (fg_parse_gelf.cu): 64 lines and 256 threads per CTA; a CTA round has kGelfStageSlots slots, one per top-level member
 #ifndef FG_GELF_LINES
 #define FG_GELF_LINES 64
 #endif
+#ifndef FG_GELF_THREADS
+#define FG_GELF_THREADS 256
+#endif
 constexpr int kGelfLinesPerCta = FG_GELF_LINES;
-constexpr int kGelfStageSlots = kGelfLinesPerCta * 10;
+constexpr int kGelfThreadsPerCta = FG_GELF_THREADS;
+constexpr int kGelfCtasPerSm = 3;  // tile (~34 KB at 520 B/line) + bitmap + slots: 3 CTAs = 24 warps per SM
+constexpr int kGelfStageSlots = kGelfLinesPerCta * 16;
 constexpr int kGelfMaxTile = 65024;
 constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : kGelfLinesPerCta); }
 

@@ -1,13 +1,16 @@
 // fg_parse_gelf.cu — the GELF decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline.
 //
-//   parse_gelf_kernel   one CTA = LINES consecutive lines.  (1) ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the CTA's
-//                       contiguous byte span into the shared-memory tile; (2) all threads sweep the tile 32 bytes per step
-//                       and write the string bitmap X (fg_gelffast.cuh stage 1); (3) one thread per line walks its members
-//                       over the bitmap (stage 2, lock step) into per-thread local memory; (4) slots for the side-table
-//                       rows are reserved by a CTA scan, phase 2 (sort by key, last duplicate wins, per-key rules) stages
-//                       the rows in shared memory; (5) a second scan + ONE global atomic place them and all threads copy
-//                       them out — consecutive threads write consecutive rows of the three side-table columns.
-//                       Lines the walker does not recognise as regular go on a device-side list.
+//   parse_gelf_kernel   one CTA = 64 consecutive lines, 256 threads.  Per round:
+//     (1) ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the lines' contiguous byte span into the shared-memory tile;
+//     (2) all threads sweep the tile 32 bytes per step into the string bitmap X (fg_gelffast.cuh stage 1);
+//     (3) one thread per line walks its members over the bitmap (lock step, one member per iteration) — only to find
+//         where keys and values are; a CTA scan gives every member a SLOT;
+//     (4) one thread per SLOT (all 256 threads) validates and converts its member: string escapes, numbers, literals;
+//     (5) one thread per line: BTreeMap order, last duplicate wins, the per-key rules (gelf_decoder.rs:51-110); the rows it
+//         keeps are written over the line's own slots;
+//     (6) a second scan + ONE global atomic place the rows and all threads copy them out — consecutive threads write
+//         consecutive rows of the three side-table columns.
+//     Lines that are not regular (fg_gelffast.cuh) go on a device-side list.
 //   post_gelf_kernel    the SLOW path over that list: the exact parser of fg_gelf.cuh (the whole serde_json grammar, the
 //                       newline retry, every error string), one thread per listed line straight from global memory.
 #include "fg_kernels.cuh"
@@ -25,6 +28,7 @@ namespace fg {
 namespace {
 
 constexpr int kLines = kGelfLinesPerCta;
+constexpr int kThreads = kGelfThreadsPerCta;
 constexpr int kSlots = kGelfStageSlots;
 
 __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, const LineResult& res, uint32_t my_begin, uint32_t my_n) {
@@ -37,19 +41,21 @@ __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, c
     P.sd[i] = make_int2((int)my_begin, (int)my_n);
 }
 
-template <int LINES>
-__global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant__ ParseParams P) {
+__global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
     __shared__ uint32_t s_ebase, s_slots, s_slow_base;
-    __shared__ uint32_t line_slot[LINES];   // first staging slot | rows << 16
-    __shared__ uint32_t line_dense[LINES];  // exclusive sum of the rows of the lines before this one
+    __shared__ int line_ls[kLines], line_o0[kLines];
+    __shared__ uint32_t line_slot[kLines];   // first slot | members (later: rows) << 16
+    __shared__ uint32_t line_dense[kLines];  // exclusive sum of the rows of the lines before this one
+    __shared__ uint32_t line_bad[kLines];    // a member was rejected: the line goes to the exact parser
 
     const int tid = threadIdx.x;
-    const int first = blockIdx.x * LINES;
-    const int last = min(P.n, first + LINES);
-    // behind the tile: the bitmap (tile_bytes / 32 + 4 words), the staged rows (three columns), the slot -> line map
+    const int first = blockIdx.x * kLines;
+    const int last = min(P.n, first + kLines);
+    // behind the tile: the bitmap (tile_bytes / 32 + 4 words) and the slots — first a member each (spans, then the member
+    // itself), in the end the side-table rows of the line: name/span column, value column, meta column, slot -> line map
     const int bm_words = P.tile_bytes / 32 + 4;
     uint32_t* bmX = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
     int2* st_name = reinterpret_cast<int2*>(bmX + bm_words);
@@ -65,12 +71,16 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
     uint32_t parity = 0;
     int cur = first;
     while (cur < last) {
+        const bool lt = tid < kLines;  // line threads
         const int i = cur + tid;
-        const int o0 = __ldg(P.offsets + min(i, last));
-        const int o1 = __ldg(P.offsets + min(i + 1, last));
+        int o0 = 0, o1 = 0;
+        if (lt) {
+            o0 = __ldg(P.offsets + min(i, last));
+            o1 = __ldg(P.offsets + min(i + 1, last));
+        }
         const int ocur = __ldg(P.offsets + cur);
         const int base = ocur & ~15;
-        const bool fits = (i < last) && (o1 - base <= P.tile_bytes);
+        const bool fits = lt && (i < last) && (o1 - base <= P.tile_bytes);
         int r = __syncthreads_count(fits);  // offsets are monotone: `fits` is a prefix property
         if (r == 0) {
             // the first pending line alone exceeds the tile: the slow kernel takes it
@@ -88,21 +98,21 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- stage 1: the string bitmap of the whole tile, 32 bytes (= one word) per thread per step -----------------
+        // ---- (2) the string bitmap of the whole tile, 32 bytes (= one word) per thread per step -----------------------
         const int nword = (int)((nbytes + 31u) >> 5);
-        for (int g = tid; g < nword; g += LINES) {
+        for (int g = tid; g < nword; g += kThreads) {
             const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
             bmX[g] = gf_classify16(v0.x, v0.y, v0.z, v0.w) | (gf_classify16(v1.x, v1.y, v1.z, v1.w) << 16);
         }
         if (tid < 4) bmX[nword + tid] = 0;
         __syncthreads();
 
-        // ---- stage 2: one thread per line ------------------------------------------------------------------------
-        bool active = tid < r;
+        // ---- (3) one thread per line: where are the members ------------------------------------------------------------
+        bool active = lt && tid < r;
         const int ls = active ? o0 - base : 0;
         int le = active ? o1 - base : 0;
         bool bad_utf8 = false;
-        if (P.strip_eol && le > ls) {
+        if (active && P.strip_eol && le > ls) {
             // BufRead::lines: drop the '\n' and one '\r' before it (line_splitter.rs:17); invalid UTF-8 lines are skipped (:22-25)
             if (P.strip_eol == 2) {  // BufRead::split(0): only the NUL terminator goes (nul_splitter.rs:18)
                 if (tile[le - 1] == 0) --le;
@@ -113,35 +123,76 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
             if (P.line_invalid != nullptr && P.line_invalid[i]) bad_utf8 = true;
         }
         const bool walk = active && !bad_utf8;
-        Members M;
-        uint32_t n_plain = 0;
-        const bool regular = gf_walk(tile, bmX, ls, walk ? le : ls, walk, o0, M, n_plain);
-        bool slow = walk && !regular;
-
-        // staging slots for the rows of the regular lines (upper bound: members that are not reserved keys)
-        const uint32_t nb = (walk && regular) ? n_plain : 0u;
-        uint32_t slots_total;
-        const uint32_t slot0 = block_exclusive_scan(nb, scan_ws, slots_total);
-        if (slots_total > (uint32_t)kSlots) {  // CTA-uniform, rare: keep the lines whose slots fit, redo the rest next round
-            r = __syncthreads_count(active && slot0 + nb <= (uint32_t)kSlots);  // >= 1: one line holds <= kMaxLocalMembers rows
-            active = tid < r;
-            slow = slow && active;
+        bool regular = false;
+        uint32_t nm = 0;
+        GfSpans G;
+        if (tid < 64 || kLines > 64) {  // warp-uniform: only the warps that hold line threads walk
+            regular = gf_walk(tile, bmX, ls, walk ? le : ls, walk, G);
+            nm = (walk && regular) ? G.m : 0u;
         }
-        const bool fast = walk && regular && active;
+        uint32_t slots_total;
+        const uint32_t slot0 = block_exclusive_scan(nm, scan_ws, slots_total);
+        if (slots_total > (uint32_t)kSlots) {  // CTA-uniform, rare: keep the lines whose slots fit, redo the rest next round
+            r = __syncthreads_count(active && slot0 + nm <= (uint32_t)kSlots);  // >= 1: one line holds <= kMaxLocalMembers members
+            active = lt && tid < r;
+        }
+        bool fast = walk && regular && active;
+        if (lt) {
+            line_ls[tid] = ls;
+            line_o0[tid] = o0;
+            line_slot[tid] = slot0 | ((fast ? nm : 0u) << 16);
+            line_bad[tid] = 0u;
+            if (tid == r - 1) s_slots = slot0 + (fast ? nm : 0u);
+        }
+        if (fast) {
+            for (uint32_t k = 0; k < nm; ++k) {
+                st_val[slot0 + k] = G.sp[k];
+                st_meta[slot0 + k] = G.kind[k];
+                slot_line[slot0 + k] = (uint8_t)tid;
+            }
+        }
+        __syncthreads();
+        const uint32_t nslots = s_slots;
 
-        // ---- phase 2: BTreeMap order, last duplicate wins, the per-key rules; rows staged at stage[slot0 ..) -----------
+        // ---- (4) one thread per member ---------------------------------------------------------------------------------
+        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
+            const uint32_t l = slot_line[s];
+            int2 name;
+            unsigned long long val = 0;
+            uint32_t meta = 0;
+            bool plain;
+            if (gf_member(tile, bmX, st_val[s], st_meta[s], line_o0[l], line_ls[l], name, val, meta, plain)) {
+                st_name[s] = name;
+                st_val[s] = val;
+                st_meta[s] = (uint8_t)meta;
+            } else {
+                line_bad[l] = 1u;
+            }
+        }
+        __syncthreads();
+
+        // ---- (5) one thread per line: BTreeMap order, last duplicate wins, the per-key rules; rows over the line's slots -
+        if (fast && line_bad[tid]) fast = false;
+        const bool slow = walk && active && !fast;
         LineResult res;
         gelf_result_init(res);
         if (fast) {
+            Members M;
+            M.m = nm;
+            M.spilled = false;
+            for (uint32_t k = 0; k < nm; ++k) {
+                M.name[k] = st_name[slot0 + k];
+                M.val[k] = st_val[slot0 + k];
+                M.meta[k] = st_meta[slot0 + k];
+            }
             GelfAcc g;
             g.status = FG_ST_OK;
             g.flags = 0;
             g.kept = 0;
             g.have_ts = false;
-            gelf_finish_local(tile + ls, o0, false, M, res, g, stage, slot0);
+            gf_finish(tile + ls, o0, M, res, g, stage, slot0);
             gelf_finalize(res, g);
         }
-        __syncwarp();
         if (bad_utf8) {
             res.status = FG_ES_INVALID_UTF8;
             res.n_entries = 0;
@@ -152,13 +203,12 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
         const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);
         uint32_t slow_total;
         const uint32_t slow_at = block_exclusive_scan(slow ? 1u : 0u, scan_ws, slow_total);
-        line_slot[tid] = slot0 | (my_n << 16);
-        line_dense[tid] = excl;
-        if (fast)
-            for (uint32_t k = 0; k < nb; ++k) slot_line[slot0 + k] = (uint8_t)tid;
-        if (tid == r - 1) s_slots = slot0 + nb;
+        if (lt) {
+            line_slot[tid] = slot0 | (my_n << 16);
+            line_dense[tid] = excl;
+        }
         if (tid == 0 && total) s_ebase = atomicAdd(P.entry_counter, total);
-        if (tid == 32 % LINES && slow_total) s_slow_base = atomicAdd(P.slow_count, slow_total);
+        if (tid == 32 && slow_total) s_slow_base = atomicAdd(P.slow_count, slow_total);
         __syncthreads();
         if (slow) P.slow_list[s_slow_base + slow_at] = (uint32_t)i;
         uint32_t my_begin = 0;
@@ -167,8 +217,7 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
             const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
             if (!ovf) {
                 if (my_n) my_begin = ebase + excl;
-                const uint32_t nslots = s_slots;
-                for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)LINES) {
+                for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
                     const uint32_t l = slot_line[s];
                     const uint32_t ls_n = line_slot[l];
                     const uint32_t k = s - (ls_n & 0xFFFFu);
@@ -182,7 +231,7 @@ __global__ void __launch_bounds__(LINES) parse_gelf_kernel(const __grid_constant
             }
         }
         if (active && !slow) write_row(P, i, o0, res, my_begin, my_n);
-        __syncthreads();  // tile, bitmap, staging and scan scratch are reused by the next round
+        __syncthreads();  // tile, bitmap, slots and scan scratch are reused by the next round
         cur += r;
     }
 }
@@ -235,7 +284,7 @@ __global__ void __launch_bounds__(128) post_gelf_kernel(const __grid_constant__ 
 
 }  // namespace
 
-int parse_gelf_smem_bytes(int tile_bytes) { return tile_bytes + (tile_bytes / 32 + 4) * 4 + kSlots * (8 + 8 + 1 + 1) + 16; }
+int parse_gelf_smem_bytes(int tile_bytes) { return tile_bytes + (tile_bytes / 32 + 4) * 4 + kGelfStageSlots * (8 + 8 + 1 + 1) + 16; }
 
 cudaError_t configure_parse_gelf(int max_tile_bytes) {
     {   // serde_json's POW10 table (visit_f64_from_parts): correctly rounded decimal literals, like rustc's
@@ -248,14 +297,14 @@ cudaError_t configure_parse_gelf(int max_tile_bytes) {
         cudaError_t e1 = cudaMemcpyToSymbol(g_pow10, &t, sizeof t);  // this translation unit's copy: the one the GELF kernels read
         if (e1 != cudaSuccess) return e1;
     }
-    return cudaFuncSetAttribute(parse_gelf_kernel<kLines>, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_gelf_smem_bytes(max_tile_bytes));
+    return cudaFuncSetAttribute(parse_gelf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_gelf_smem_bytes(max_tile_bytes));
 }
 
 cudaError_t launch_parse_gelf(const ParseParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     if (p.tile_bytes <= 0 || p.tile_bytes > kGelfMaxTile || (p.tile_bytes & 511)) return cudaErrorInvalidValue;
     const int grid = (p.n + kLines - 1) / kLines;
-    parse_gelf_kernel<kLines><<<grid, kLines, parse_gelf_smem_bytes(p.tile_bytes), stream>>>(p);
+    parse_gelf_kernel<<<grid, kThreads, parse_gelf_smem_bytes(p.tile_bytes), stream>>>(p);
     // the work list lives on the device (no host round trip): a fixed grid strides over it
     const int post = (int)min((long long)(p.n + 127) / 128, 148LL * 8);
     post_gelf_kernel<<<post, 128, 0, stream>>>(p);

@@ -110,15 +110,34 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                     }
                     if (invalid && invalid[i]) bad = true;
                 }
-                fg::Members M;
-                uint32_t n_plain = 0;
+                fg::GfSpans G;
                 const bool walk = !bad;
-                const bool regular = fg::gf_walk(tile.data(), bmX.data(), ls, walk ? le : ls, walk, o0, M, n_plain);
-                const uint32_t nb = (walk && regular) ? n_plain : 0u;
+                bool regular = fg::gf_walk(tile.data(), bmX.data(), ls, walk ? le : ls, walk, G);
+                const uint32_t nb = (walk && regular) ? G.m : 0u;
                 if (run + nb > (uint32_t)kSlots) break;  // the round is cut here; the rest is redone
                 const uint32_t slot0 = run;
                 run += nb;
                 ++done;
+                // (4) one member at a time: validation + conversion, in place in the slots
+                fg::Members M;
+                M.m = 0;
+                M.spilled = false;
+                uint32_t n_plain = 0;
+                for (uint32_t k = 0; k < nb && regular; ++k) {
+                    int2 name;
+                    unsigned long long val = 0;
+                    uint32_t meta = 0;
+                    bool plain = false;
+                    if (!fg::gf_member(tile.data(), bmX.data(), G.sp[k], G.kind[k], o0, ls, name, val, meta, plain)) {
+                        regular = false;
+                        break;
+                    }
+                    M.name[k] = name;
+                    M.val[k] = val;
+                    M.meta[k] = (uint8_t)meta;
+                    M.m = k + 1;
+                    if (plain) ++n_plain;
+                }
                 if (walk && !regular) {
                     slow_list.push_back((uint32_t)i);
                     continue;
@@ -129,8 +148,8 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                     fg::GelfAcc g;
                     g.status = FG_ST_OK; g.flags = 0; g.kept = 0; g.have_ts = false;
                     fg::EntrySink stage = {(int2*)st_name.data(), (unsigned long long*)st_val.data(), st_meta.data()};
-                    fg::gelf_finish_local(tile.data() + ls, o0, false, M, res, g, stage, slot0);
-                    if (g.kept > nb) ++T->bound_violations;
+                    fg::gf_finish(tile.data() + ls, o0, M, res, g, stage, slot0);
+                    if (g.kept > n_plain || g.kept > nb) ++T->bound_violations;
                     fg::gelf_finalize(res, g);
                 }
                 if (bad) { res.status = FG_ES_INVALID_UTF8; res.n_entries = 0; res.full_o = 0; }
