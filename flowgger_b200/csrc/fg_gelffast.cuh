@@ -1,27 +1,27 @@
-// fg_gelffast.cuh — GELF on the bitmap pipeline: one structural bitmap + one-member-per-step walk over a shared-memory tile,
-// for REGULAR lines; everything else goes to the exact parser of fg_gelf.cuh.
+// fg_gelffast.cuh — GELF on the bitmap pipeline, MEMBER-parallel, for REGULAR lines; everything else goes to the exact
+// parser of fg_gelf.cuh.
 //
 // B200-native replacement for GelfDecoder::decode (/root/reference/src/flowgger/decoder/gelf_decoder.rs:34-125).  A regular
 // line is what every GELF sender emits: ONE flat JSON object
 //     { "key" : value , "key" : value ... }        value = string | number | true | false | null
 // with nothing but spaces between the tokens, no escape inside a key, no raw control byte anywhere, at most
-// kMaxLocalMembers members.  The walker proves that shape as it goes — with serde_json's own rules for what it accepts
-// (string escapes incl. \uXXXX surrogate pairs: read.rs parse_escape; numbers: json_number of fg_gelf.cuh) — and the first
-// byte that does not fit (a nested container, a TAB or LF between tokens, a raw control byte inside a string, any syntax
-// error ...) hands the line to gelf_parse_line, which restates the whole grammar, the newline-retry of :44-46 and every
-// error string.  A line accepted here is parsed to exactly the members the full parser would collect.
+// kMaxLocalMembers members.  The shape is PROVEN here — with serde_json's own rules for what it accepts (string escapes
+// incl. \uXXXX surrogate pairs: read.rs parse_escape; numbers: json_number of fg_gelf.cuh) — and the first byte that does
+// not fit (a nested container, a TAB or LF between tokens, a raw control byte, any syntax error ...) hands the line to
+// gelf_parse_line, which restates the whole grammar, the newline retry of :44-46 and every error string.  A line accepted
+// here is parsed to exactly the members the full parser would collect.
 //
-//   stage 1  gf_classify16: every thread takes 32-byte granules of the flat tile and writes one word of the bitmap
-//            X = '"' | '\\' | byte < 0x20 (exact per byte): the only bytes that can end or alter a JSON string.
-//   stage 2  gf_walk: one thread per line, ONE member per loop iteration for all 32 lines of a warp — but only to find
-//            where the members are: key span, value span, string or not.  A string body is not read: its end is the next X
-//            bit that is a quote (a per-lane word iterator skips 32 bytes per step; a backslash hit skips its byte).  Bytes
-//            BETWEEN tokens are read directly (a handful per member).
-//   members  gf_member: one thread per MEMBER, for all members of the CTA round, 256 threads wide: the escapes of a string
-//            value are validated, a number goes through json_number, the reserved keys are recognised.  (Doing this inside
-//            the walk ran ~3 of 32 lanes wide: 1258 warp-instructions per line, profiles/r2_notes.md.)
-//   phase 2  (gelf_finish_local, shared with the exact parser) one thread per line sorts the members by key, keeps the last
-//            duplicate and applies the per-key rules of gelf_decoder.rs:51-107.
+//   stage 1  gf_bits16: every thread takes 32-byte granules of the flat tile and writes one word each of three bitmaps,
+//            exact per byte — Q '"', B '\\', P ',' — plus one bit per granule "holds a byte < 0x20".
+//   lines    gf_line_members: one thread per line runs over the line's bitmap WORDS (17 for 520 bytes, not over its bytes):
+//            backslash runs -> escaped quotes -> string interior by a prefix XOR (the simdjson recipe on 32-bit words);
+//            the commas outside strings end the members and are listed into the line's slots.
+//   members  gf_member: one thread per MEMBER, for all members of the CTA round, 256 threads wide: key, colon, value token,
+//            string escapes, literals; numbers are listed and go through json_number in a dense second pass.
+//   phase 2  gf_finish: one thread per line sorts the members by key (8-byte prefix first), keeps the last duplicate and
+//            applies the per-key rules of gelf_decoder.rs:51-107.
+// (Walking a line member by member in lock step — the first two versions — cost 1258 / 1392 warp-instructions per line
+//  and was slower than the round-1 tokenizer; profiles/r2_notes.md.)
 #pragma once
 #include "fg_common.cuh"
 #include "fg_gelf.cuh"
@@ -32,13 +32,12 @@
 namespace fg {
 
 // ---- stage 1 ----------------------------------------------------------------------------------------------------
-FG_DEV uint32_t gf_flags(uint32_t w) {
-    const uint32_t t = w & 0xE0E0E0E0u;                                             // 0 iff the byte is < 0x20
-    const uint32_t ctrl = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
-    return lt_eq_flags(w, 0x22222222u) | lt_eq_flags(w, 0x5C5C5C5Cu) | ctrl;
-}
-FG_DEV uint32_t gf_classify16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    return r5_gather16(gf_flags(w0), gf_flags(w1), gf_flags(w2), gf_flags(w3));
+// 16 bytes -> 16 bits of Q, B, P each; ctrl = nonzero iff one of the 16 bytes is < 0x20
+FG_DEV void gf_bits16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t& q, uint32_t& b, uint32_t& p, uint32_t& ctrl) {
+    q = r5_gather16(lt_eq_flags(w0, 0x22222222u), lt_eq_flags(w1, 0x22222222u), lt_eq_flags(w2, 0x22222222u), lt_eq_flags(w3, 0x22222222u));
+    b = r5_gather16(lt_eq_flags(w0, 0x5C5C5C5Cu), lt_eq_flags(w1, 0x5C5C5C5Cu), lt_eq_flags(w2, 0x5C5C5C5Cu), lt_eq_flags(w3, 0x5C5C5C5Cu));
+    p = r5_gather16(lt_eq_flags(w0, 0x2C2C2C2Cu), lt_eq_flags(w1, 0x2C2C2C2Cu), lt_eq_flags(w2, 0x2C2C2C2Cu), lt_eq_flags(w3, 0x2C2C2C2Cu));
+    ctrl = lt_eq_flags(w0 & 0xE0E0E0E0u, 0u) | lt_eq_flags(w1 & 0xE0E0E0E0u, 0u) | lt_eq_flags(w2 & 0xE0E0E0E0u, 0u) | lt_eq_flags(w3 & 0xE0E0E0E0u, 0u);
 }
 
 // ---- stage 2 ----------------------------------------------------------------------------------------------------
@@ -73,63 +72,6 @@ FG_DEV int gf_escape_end(const uint8_t* T, int h, int le) {
     return h + 6;
 }
 
-// A JSON string body starting at s (the byte after the opening quote).  All lanes call; lanes with act = true scan.  Returns
-// the position of the closing quote, or -1 (no closing quote inside the line, a raw control byte).  A backslash skips the
-// byte behind it, whatever it is: gf_member validates the escapes (a line with an invalid one is not regular, so the
-// shortcut cannot change what a regular line parses to).  has_bs = the body holds a backslash.
-FG_DEV int gf_string(const uint8_t* T, const uint32_t* bmX, int s, int le, bool act, bool& has_bs) {
-    int xw = s >> 5;
-    uint32_t xrem = act ? bmX[xw] & (0xFFFFFFFFu << (s & 31)) : 0u;
-    int end = -1;
-    bool more = act;
-    has_bs = false;
-    while (fg_any(more)) {
-        for (;;) {  // next X bit: 32 bytes of string body per step
-            const bool need = more && xrem == 0u && ((xw + 1) << 5) < le;
-            if (!fg_any(need)) break;
-            if (need) {
-                ++xw;
-                xrem = bmX[xw];
-            }
-        }
-        if (more) {
-            const int h = (xw << 5) + fg_ffs(xrem) - 1;
-            if (xrem == 0u || h >= le) {
-                more = false;  // EOFWhileParsingString
-            } else {
-                const uint32_t c = T[h];
-                if (c == '"') {
-                    end = h;
-                    more = false;
-                } else if (c == '\\') {
-                    has_bs = true;
-                    const int nx = h + 2;
-                    if (nx > le) {
-                        more = false;
-                    } else {  // the iterator continues behind the escaped byte (which may be an X byte itself: \" \\)
-                        if ((nx >> 5) != xw) {
-                            xw = nx >> 5;
-                            xrem = bmX[xw];
-                        }
-                        xrem &= 0xFFFFFFFFu << (nx & 31);
-                    }
-                } else {
-                    more = false;  // raw control byte: InvalidUnicodeCodePoint -> newline retry / error (exact parser)
-                }
-            }
-        }
-    }
-    return end;
-}
-
-FG_DEV void gf_skip_spaces(const uint8_t* T, int& pos, int le, bool act) {
-    for (;;) {
-        const bool more = act && pos < le && T[pos] == ' ';
-        if (!fg_any(more)) break;
-        if (more) ++pos;
-    }
-}
-
 // GKEY_* of a raw key (keys with escapes never get here): the six keys gelf_decoder.rs:51-96 consumes, else GKEY_OTHER
 FG_DEV int gf_key_kind(const uint8_t* k, int len) {
     const unsigned long long a = lt_load8(k), b = lt_load8(k + 8);
@@ -155,160 +97,198 @@ FG_DEV unsigned long long gf_key_prefix(const uint8_t* k, int len) {
 #endif
 }
 
-// where the members of a line are (tile positions, < 65536): key [ks, ke), value [vs, ve) — for a string the body
-constexpr uint32_t GK_TOKEN = 0, GK_STRING = 1, GK_STRING_BS = 2;
-struct GfSpans {
-    unsigned long long sp[kMaxLocalMembers];  // ks | ke << 16 | vs << 32 | ve << 48
-    uint8_t kind[kMaxLocalMembers];
-    uint32_t m;
-};
-
-// All 32 lanes call (idle lanes with active_line = false).  T = the tile, [ls, le) the line inside it.  Returns true when
-// the line has the regular SHAPE (its members are in G, in document order); gf_member still has to accept every member.
-FG_DEV bool gf_walk(const uint8_t* T, const uint32_t* bmX, int ls, int le, bool active_line, GfSpans& G) {
-    G.m = 0;
-    bool reg = active_line;
-    int pos = ls;
-    gf_skip_spaces(T, pos, le, reg);
-    if (reg) {
-        if (pos < le && T[pos] == '{') ++pos;
-        else reg = false;
+// ---- lines: member boundaries from the bitmap words ----------------------------------------------------------------
+// bits of w below position `lo` / at and above `hi` (positions inside the word's 32) cleared
+FG_DEV uint32_t gf_clip(uint32_t w, int word, int lo, int hi) {
+    const int base = word << 5;
+    if (lo > base) w &= 0xFFFFFFFFu << (lo - base);
+    if (hi < base + 32) w &= hi > base ? 0xFFFFFFFFu >> (base + 32 - hi) : 0u;
+    return w;
+}
+// The structural commas of the line [ls, le) — commas outside strings — as tile positions into cuts[0 .. n), n <= cap;
+// returns n, or -1 when the line is not regular on this level: a string that does not close, more commas than `cap`.
+// The recipe per 32-bit word (simdjson's, with the carries kept in two registers): backslashes that start an odd-length run
+// escape the byte behind the run; quotes that are not escaped toggle "inside a string"; a prefix XOR spreads that over the
+// word.
+FG_DEV int gf_line_commas(const uint32_t* bmQ, const uint32_t* bmB, const uint32_t* bmP, int ls, int le, uint16_t* cuts, int cap) {
+    if (le <= ls) return 0;
+    const int w0 = ls >> 5, w1 = (le - 1) >> 5;
+    uint32_t prev_escaped = 0u;    // bit 0: the first byte of this word is escaped by a run ending in the previous word
+    uint32_t prev_in_string = 0u;  // all ones: the previous word ended inside a string
+    int n = 0;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t bs = gf_clip(bmB[w], w, ls, le);
+        const uint32_t q = gf_clip(bmQ[w], w, ls, le), pc = gf_clip(bmP[w], w, ls, le);
+        // escaped bytes
+        bs &= ~prev_escaped;
+        const uint32_t follows = (bs << 1) | prev_escaped;
+        const uint32_t odd_starts = bs & ~0x55555555u & ~follows;
+        const uint32_t sum = odd_starts + bs;
+        const uint32_t carry = sum < odd_starts ? 1u : 0u;  // a run reaching the end of the word that started on an odd bit
+        const uint32_t invert = sum << 1;
+        const uint32_t escaped = (0x55555555u ^ invert) & follows;
+        prev_escaped = carry;
+        // string interior
+        uint32_t x = q & ~escaped;
+        x ^= x << 1;
+        x ^= x << 2;
+        x ^= x << 4;
+        x ^= x << 8;
+        x ^= x << 16;
+        x ^= prev_in_string;
+        prev_in_string = (uint32_t)((int32_t)x >> 31);
+        uint32_t c = pc & ~x;
+        while (c) {
+            if (n >= cap) return -1;
+            cuts[n++] = (uint16_t)((w << 5) + fg_ffs(c) - 1);
+            c &= c - 1u;
+        }
     }
-    gf_skip_spaces(T, pos, le, reg);
-    bool open = reg;  // inside the object: a key comes next
-    if (reg && pos < le && T[pos] == '}') {
-        ++pos;
-        open = false;
-    }
-    while (fg_any(reg && open)) {
-        const bool run = reg && open;
-        // "key": the next X byte behind the opening quote must be the closing one (no escapes in keys, <= 32 bytes)
-        int key_s = pos + 1, key_e = 0;
-        if (run) {
-            const bool k_ok = pos < le && T[pos] == '"';
-            const uint32_t W = k_ok ? r5_window(bmX, key_s) : 0u;
-            const int h = key_s + fg_ffs(W) - 1;
-            if (W == 0u || h >= le || T[h] != '"') reg = false;  // KeyMustBeAString, escapes / control bytes, long keys: exact parser
-            else { key_e = h; pos = h + 1; }
-        }
-        gf_skip_spaces(T, pos, le, run && reg);
-        if (run && reg) {
-            if (pos < le && T[pos] == ':') ++pos;
-            else reg = false;
-        }
-        gf_skip_spaces(T, pos, le, run && reg);
-        // value
-        if (run && reg && pos >= le) reg = false;
-        const uint32_t c = (run && reg) ? T[pos] : 0u;
-        const bool is_str = run && reg && c == '"';
-        const int vs = is_str ? pos + 1 : pos;
-        bool vbs = false;
-        int ve = gf_string(T, bmX, vs, le, is_str, vbs);
-        if (run && reg && is_str) {
-            if (ve < 0) reg = false;
-            else pos = ve + 1;
-        }
-        // any other token runs up to the next ',', '}' or space
-        const bool is_tok = run && reg && !is_str;
-        int te = pos;
-        for (;;) {
-            bool more = false;
-            if (is_tok && te < le) {
-                const uint32_t d = T[te];
-                more = !(d == ',' || d == '}' || d == ' ');
-            }
-            if (!fg_any(more)) break;
-            if (more) ++te;
-        }
-        if (is_tok) {
-            // number, true, false, null; a container as a member value or anything else: exact parser
-            if (te == pos || !(c == '-' || c - '0' <= 9u || c == 't' || c == 'f' || c == 'n')) reg = false;
-            ve = te;
-            pos = te;
-        }
-        if (run && reg) {
-            if (G.m >= (uint32_t)kMaxLocalMembers) {
-                reg = false;
-            } else {
-                G.sp[G.m] = (unsigned long long)(uint32_t)key_s | ((unsigned long long)(uint32_t)key_e << 16) |
-                            ((unsigned long long)(uint32_t)vs << 32) | ((unsigned long long)(uint32_t)ve << 48);
-                G.kind[G.m] = (uint8_t)(is_str ? (vbs ? GK_STRING_BS : GK_STRING) : GK_TOKEN);
-                ++G.m;
-            }
-        }
-        gf_skip_spaces(T, pos, le, run && reg);
-        if (run && reg) {
-            const uint32_t d = pos < le ? T[pos] : 0u;
-            if (d == ',') ++pos;
-            else if (d == '}') { ++pos; open = false; }
-            else reg = false;  // ExpectedObjectCommaOrEnd
-        }
-        gf_skip_spaces(T, pos, le, run && reg && open);
-    }
-    gf_skip_spaces(T, pos, le, reg);
-    if (reg && pos != le) reg = false;  // TrailingCharacters
-    return reg;
+    return prev_in_string ? -1 : n;
 }
 
-// One member (any thread): validates the value the way serde_json does and produces the member as the exact parser would
-// (name span absolute, value, tag | flags).  false: the line is not regular after all.  plain = not a reserved key.
-FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmX, unsigned long long sp, uint32_t kind, int line_off, int ls, int2& name,
-                      unsigned long long& val, uint32_t& meta, bool& plain) {
-    const int ks = (int)(sp & 0xFFFFu), ke = (int)((sp >> 16) & 0xFFFFu), vs = (int)((sp >> 32) & 0xFFFFu), ve = (int)(sp >> 48);
+// the line [ls, le) as member spans: returns the number of members m (their spans are [start_k, cuts[k]) with
+// start_0 = `open` + 1, start_k = cuts[k - 1] + 1, the last cut being the closing brace), or -1: not regular.
+FG_DEV int gf_line_members(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB, const uint32_t* bmP, int ls, int le, uint16_t* cuts,
+                           int cap, int& open) {
+    int a = ls, b = le;
+    while (a < b && T[a] == ' ') ++a;
+    while (b > a && T[b - 1] == ' ') --b;
+    if (b - a < 2 || T[a] != '{' || T[b - 1] != '}') return -1;
+    open = a;
+    const int n = gf_line_commas(bmQ, bmB, bmP, a + 1, b - 1, cuts, cap - 1);
+    if (n < 0) return -1;
+    if (n == 0) {  // `{}` or one member
+        int c = a + 1;
+        while (c < b - 1 && T[c] == ' ') ++c;
+        if (c == b - 1) return 0;
+    }
+    cuts[n] = (uint16_t)(b - 1);
+    return n + 1;
+}
+
+// does [ls, le) hold a byte < 0x20?  anyK has one bit per 32-byte granule ("some byte of the granule is < 0x20"); only the
+// flagged granules are looked at byte by byte (in split mode those are the two that hold line terminators)
+FG_DEV bool gf_has_ctrl(const uint8_t* T, const uint32_t* anyK, int ls, int le) {
+    if (le <= ls) return false;
+    const int g0 = ls >> 5, g1 = (le - 1) >> 5;
+    for (int g = g0; g <= g1; ++g) {
+        if (!((anyK[g >> 5] >> (g & 31)) & 1u)) continue;
+        const int a = g == g0 ? ls : g << 5, b = g == g1 ? le : (g << 5) + 32;
+        for (int i = a; i < b; ++i)
+            if (T[i] < 0x20u) return true;
+    }
+    return false;
+}
+
+// ---- members ---------------------------------------------------------------------------------------------------------
+// position of the first set bit of bm in [from, to), or -1
+FG_DEV int gf_next_bit(const uint32_t* bm, int from, int to) {
+    if (from >= to) return -1;
+    int w = from >> 5;
+    uint32_t m = bm[w] & (0xFFFFFFFFu << (from & 31));
+    while (m == 0u && ((w + 1) << 5) < to) m = bm[++w];
+    if (m == 0u) return -1;
+    const int h = (w << 5) + fg_ffs(m) - 1;
+    return h < to ? h : -1;
+}
+// is the byte at h escaped, i.e. preceded by an odd number of backslashes (inside [lo, h))
+FG_DEV bool gf_escaped(const uint32_t* bmB, int lo, int h) {
+    int run = 0;
+    for (int i = h - 1; i >= lo && ((bmB[i >> 5] >> (i & 31)) & 1u); --i) ++run;
+    return (run & 1) != 0;
+}
+
+constexpr uint32_t kGfNumber = 0xFFu;  // meta of a member whose number token still has to go through json_number
+
+// One member [a, b) of a regular-looking line (any thread): validates it the way serde_json does and produces the member
+// as the exact parser would (name span absolute, value, tag | flags | key class << 5).  A number is only located: its
+// token span is left in `val` with meta = kGfNumber (gf_member_number finishes it).  false: the line is not regular.
+FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB, int a, int b, int line_off, int ls, int2& name,
+                      unsigned long long& val, uint32_t& meta) {
+    while (a < b && T[a] == ' ') ++a;
+    while (b > a && T[b - 1] == ' ') --b;
+    if (b - a < 4 || T[a] != '"') return false;  // KeyMustBeAString; the shortest member is `"":0`
+    // "key": up to the next quote; a backslash in it (escapes in keys) goes to the exact parser
+    const int ks = a + 1;
+    const int ke = gf_next_bit(bmQ, ks, b);
+    if (ke < 0 || gf_next_bit(bmB, ks, ke) >= 0) return false;
+    int p = ke + 1;
+    while (p < b && T[p] == ' ') ++p;
+    if (p >= b || T[p] != ':') return false;
+    ++p;
+    while (p < b && T[p] == ' ') ++p;
+    if (p >= b) return false;
     name = make_int2(line_off + (ks - ls), ke - ks);
-    const int kk = gf_key_kind(T + ks, ke - ks);
-    plain = kk == GKEY_OTHER;
-    const uint32_t kbits = (uint32_t)kk << 5;  // bits 5..7 of the member's meta: the key class, for phase 2
-    if (kind != GK_TOKEN) {
-        if (kind == GK_STRING_BS) {  // every backslash of the body starts a valid escape (read.rs parse_escape)
-            int pos = vs;
-            for (;;) {
-                int xw = pos >> 5;
-                uint32_t xrem = bmX[xw] & (0xFFFFFFFFu << (pos & 31));
-                while (xrem == 0u && ((xw + 1) << 5) < ve) xrem = bmX[++xw];
-                const int h = (xw << 5) + fg_ffs(xrem) - 1;
-                if (xrem == 0u || h >= ve) break;
-                pos = gf_escape_end(T, h, ve);  // T[h] is a backslash: quotes inside the body are escaped, control bytes excluded
-                if (pos < 0) return false;
-            }
+    const uint32_t kbits = (uint32_t)gf_key_kind(T + ks, ke - ks) << 5;  // bits 5..7: the key class, for phase 2
+    const uint32_t c = T[p];
+    if (c == '"') {
+        // the value string must end exactly at b - 1: its closing quote is the first unescaped one
+        const int vs = p + 1;
+        int h = vs - 1;
+        for (;;) {
+            h = gf_next_bit(bmQ, h + 1, b);
+            if (h < 0) return false;
+            if (!gf_escaped(bmB, vs, h)) break;
+        }
+        if (h != b - 1) return false;  // something behind the string (or a quote inside the member: not one string)
+        const int ve = h;
+        bool has_bs = false;
+        for (int pos = vs;;) {  // every backslash of the body starts a valid escape (read.rs parse_escape)
+            const int x = gf_next_bit(bmB, pos, ve);
+            if (x < 0) break;
+            has_bs = true;
+            pos = gf_escape_end(T, x, ve);
+            if (pos < 0) return false;
         }
         val = (unsigned long long)(uint32_t)(line_off + (vs - ls)) | ((unsigned long long)(uint32_t)(ve - vs) << 32);
-        meta = JT_STRING | (kind == GK_STRING_BS ? 0x08u : 0u) | kbits;  // FG_EM_UNESCAPE
+        meta = JT_STRING | (has_bs ? 0x08u : 0u) | kbits;  // FG_EM_UNESCAPE
+        return true;
+    }
+    if (c == '-' || c - '0' <= 9u) {
+        val = (unsigned long long)(uint32_t)p | ((unsigned long long)(uint32_t)b << 32) | ((unsigned long long)kbits << 48);
+        meta = kGfNumber;
         return true;
     }
     Json j;
     j.p = T;
-    j.len = ve;
-    j.i = vs;
+    j.len = b;
+    j.i = p + 1;
     j.mode2 = false;
-    const uint32_t c = T[vs];
+    bool ok;
     uint32_t tag = JT_NULL;
     uint64_t bits = 0;
-    bool ok;
-    if (c == '-') {
-        ++j.i;
-        ok = json_number(j, false, tag, bits);
-    } else if (c - '0' <= 9u) {
-        ok = json_number(j, true, tag, bits);
-    } else if (c == 'n') {
-        ++j.i;
-        ok = json_lit(j, "ull", 3);
-    } else if (c == 't') {
-        ++j.i;
-        ok = json_lit(j, "rue", 3);
-        tag = JT_BOOL;
-        bits = 1;
-    } else {
-        ++j.i;
-        ok = json_lit(j, "alse", 4);
-        tag = JT_BOOL;
-    }
-    if (!ok || j.i != ve) return false;
+    if (c == 'n') ok = json_lit(j, "ull", 3);
+    else if (c == 't') { ok = json_lit(j, "rue", 3); tag = JT_BOOL; bits = 1; }
+    else if (c == 'f') { ok = json_lit(j, "alse", 4); tag = JT_BOOL; }
+    else ok = false;  // a container as a member value, or ExpectedSomeValue: exact parser
+    if (!ok || j.i != b) return false;
     val = bits;
     meta = tag | kbits;
     return true;
 }
-
+// the number token left by gf_member (start | end << 32 | key class bits << 48) -> value and tag
+FG_DEV bool gf_member_number(const uint8_t* T, unsigned long long span, unsigned long long& val, uint32_t& meta) {
+    const uint32_t kbits = (uint32_t)(span >> 48);
+    Json j;
+    j.p = T;
+    j.len = (int)((span >> 32) & 0xFFFFu);
+    j.i = (int)(uint32_t)(span & 0xFFFFu);
+    j.mode2 = false;
+    uint32_t tag = JT_NULL;
+    uint64_t bits = 0;
+    bool ok;
+    if (T[j.i] == '-') {
+        ++j.i;
+        ok = json_number(j, false, tag, bits);
+    } else {
+        ok = json_number(j, true, tag, bits);
+    }
+    if (!ok || j.i != j.len) return false;
+    val = bits;
+    meta = tag | kbits;
+    return true;
+}
 
 // Phase 2 for members produced by gf_member (raw keys, key class in bits 5..7 of meta): BTreeMap order = stable insertion
 // sort of an index permutation — by the 8-byte key prefix, the bytes only when two prefixes tie —, the last duplicate wins,

@@ -194,19 +194,31 @@ FG_DEV LtPart lt_part(const uint8_t* T, int start, int end, const LtsvDeviceConf
     return r;
 }
 
-// the reference's per-line rules once every part is classified (:104-121, :205-219).  time_* / level_* = the bounds of the
-// VALUE of the only `time` / `level` part (start < 0: none) and the index of that part; err_in = the smallest
-// (part index << 8 | status) among the typed values that failed (0xFFFFFFFF: none); part_start(k) is only needed for the
-// failing part.  Fills ts / severity / status; returns the index of the failing part (or -1).
-FG_DEV int lt_finish_line(const uint8_t* T, int t_a, int t_b, int t_k, int l_a, int l_b, int l_k, uint32_t err_in, bool have_host,
+// which of parse_ts's four attempts (:263-267) will most likely take the value [a, b): only a SCHEDULING hint — lanes with
+// the same class run ltsv_parse_ts side by side, the result never depends on it.  0 other, 1 decimal, 2 RFC3339, 3 English.
+FG_DEV int lt_time_class(const uint8_t* T, int a, int b) {
+    if (b - a >= 2 && T[a] == '[' && T[b - 1] == ']') { ++a; --b; }
+    if (b - a < 4) return (b > a && is_digit(T[a])) ? 1 : 0;
+    if (T[a + 1] == '/' || T[a + 2] == '/') return 3;
+    if (b - a > 10 && T[a + 4] == '-' && (T[a + 10] | 0x20u) == 't') return 2;
+    return is_digit(T[a]) || T[a] == '.' || T[a] == '-' || T[a] == '+' ? 1 : 0;
+}
+// `time` value [a, b) -> Record.ts (:104-111)
+FG_DEV bool lt_time_value(const uint8_t* T, int a, int b, double& ts) {
+    if (b - a >= 2 && T[a] == '[' && T[b - 1] == ']') { ++a; --b; }  // :105-109
+    return ltsv_parse_ts(T, a, b, ts);
+}
+
+// the reference's per-line rules once every part is classified (:104-121, :205-219).  t_k = index of the only `time` part
+// (t_k < 0: none), ts_ok / ts = what lt_time_value made of its value; l_a / l_b / l_k = the value of the only `level` part
+// (l_a < 0: none) and its index; err_in = the smallest (part index << 8 | status) among the typed values that failed
+// (0xFFFFFFFF: none).  Fills ts / severity / status; returns the index of the failing part (or -1).
+FG_DEV int lt_finish_line(const uint8_t* T, int t_k, bool ts_ok, double ts, int l_a, int l_b, int l_k, uint32_t err_in, bool have_host,
                           LineResult& r) {
     uint32_t err = err_in;
     bool have_ts = false;
-    if (t_a >= 0 && (uint32_t)t_k < (err >> 8)) {
-        int a = t_a, b = t_b;
-        if (b - a >= 2 && T[a] == '[' && T[b - 1] == ']') { ++a; --b; }  // :105-109
-        double ts;
-        if (ltsv_parse_ts(T, a, b, ts)) { r.ts = ts; have_ts = true; }
+    if (t_k >= 0 && (uint32_t)t_k < (err >> 8)) {
+        if (ts_ok) { r.ts = ts; have_ts = true; }
         else err = ((uint32_t)t_k << 8) | FG_EL_TS;
     }
     if (l_a >= 0 && (uint32_t)l_k < (err >> 8)) {
@@ -223,6 +235,20 @@ FG_DEV int lt_finish_line(const uint8_t* T, int t_a, int t_b, int t_k, int l_a, 
     else if (!have_host) r.status = FG_EL_MISSING_HOST;  // :206
     else r.status = FG_ST_OK;
     return -1;
+}
+
+// rows among the slots [lo, hi) of a round: mask word w holds the row bits of slots [32 w, 32 w + 32)
+FG_DEV uint32_t lt_rows_between(const uint32_t* mask, uint32_t lo, uint32_t hi) {
+    if (hi <= lo) return 0u;
+    const uint32_t w0 = lo >> 5, w1 = (hi - 1u) >> 5;
+    uint32_t n = 0;
+    for (uint32_t w = w0; w <= w1; ++w) {
+        uint32_t m = mask[w];
+        if (w == w0) m &= 0xFFFFFFFFu << (lo & 31u);
+        if (w == w1 && (hi & 31u)) m &= 0xFFFFFFFFu >> (32u - (hi & 31u));
+        n += (uint32_t)__popc(m);
+    }
+    return n;
 }
 
 }  // namespace fg

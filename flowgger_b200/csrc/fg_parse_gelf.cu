@@ -1,11 +1,13 @@
-// fg_parse_gelf.cu — the GELF decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline.
+// fg_parse_gelf.cu — the GELF decoder on sm_100a: bytes -> row columns + side table, on the bitmap pipeline, member-parallel.
 //
 //   parse_gelf_kernel   one CTA = 64 consecutive lines, 256 threads.  Per round:
 //     (1) ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the lines' contiguous byte span into the shared-memory tile;
-//     (2) all threads sweep the tile 32 bytes per step into the string bitmap X (fg_gelffast.cuh stage 1);
-//     (3) one thread per line walks its members over the bitmap (lock step, one member per iteration) — only to find
-//         where keys and values are; a CTA scan gives every member a SLOT;
-//     (4) one thread per SLOT (all 256 threads) validates and converts its member: string escapes, numbers, literals;
+//     (2) all threads sweep the tile 32 bytes per step into three bitmaps — quotes, backslashes, commas — and a
+//         control-byte flag per granule (fg_gelffast.cuh stage 1);
+//     (3) one thread per line runs over the line's bitmap WORDS: escaped quotes, string interior, the commas outside
+//         strings = member boundaries; a CTA scan gives every member a SLOT;
+//     (4) one thread per SLOT (all 256 threads) validates and converts its member: key, colon, string escapes, literals;
+//         number tokens are listed and parsed by a dense second pass (json_number on 32 busy lanes);
 //     (5) one thread per line: BTreeMap order, last duplicate wins, the per-key rules (gelf_decoder.rs:51-110); the rows it
 //         keeps are written over the line's own slots;
 //     (6) a second scan + ONE global atomic place the rows and all threads copy them out — consecutive threads write
@@ -30,6 +32,7 @@ namespace {
 constexpr int kLines = kGelfLinesPerCta;
 constexpr int kThreads = kGelfThreadsPerCta;
 constexpr int kSlots = kGelfStageSlots;
+constexpr int kCtrlWords = kGelfMaxTile / 32 / 32 + 8;  // one bit per 32-byte granule of the largest tile
 
 __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, const LineResult& res, uint32_t my_begin, uint32_t my_n) {
     const bool ok = res.status == FG_ST_OK;
@@ -45,8 +48,8 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
-    __shared__ uint32_t s_ebase, s_slots, s_slow_base;
-    __shared__ int line_ls[kLines], line_o0[kLines];
+    __shared__ uint32_t s_ebase, s_slots, s_slow_base, s_nnum;
+    __shared__ int line_ls[kLines], line_o0[kLines], line_open[kLines];
     __shared__ uint32_t line_slot[kLines];   // first slot | members (later: rows) << 16
     __shared__ uint32_t line_dense[kLines];  // exclusive sum of the rows of the lines before this one
     __shared__ uint32_t line_bad[kLines];    // a member was rejected: the line goes to the exact parser
@@ -54,14 +57,21 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
     const int tid = threadIdx.x;
     const int first = blockIdx.x * kLines;
     const int last = min(P.n, first + kLines);
-    // behind the tile: the bitmap (tile_bytes / 32 + 4 words) and the slots — first a member each (spans, then the member
-    // itself), in the end the side-table rows of the line: name/span column, value column, meta column, slot -> line map
+    // behind the tile: three bitmaps (tile_bytes / 32 + 4 words each), the control-byte flags (one bit per 32-byte granule)
+    // and the slots — first a member each, in the end the side-table rows of the line: name column, value column, meta
+    // column, member end ("cut"), slot -> line map, the list of number members
     const int bm_words = P.tile_bytes / 32 + 4;
-    uint32_t* bmX = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
-    int2* st_name = reinterpret_cast<int2*>(bmX + bm_words);
+    uint32_t* bmQ = reinterpret_cast<uint32_t*>(tile + P.tile_bytes);
+    uint32_t* bmB = bmQ + bm_words;
+    uint32_t* bmP = bmB + bm_words;
+    uint32_t* anyK = bmP + bm_words;  // kCtrlWords
+    int2* st_name = reinterpret_cast<int2*>(anyK + kCtrlWords);
     unsigned long long* st_val = reinterpret_cast<unsigned long long*>(st_name + kSlots);
-    uint8_t* st_meta = reinterpret_cast<uint8_t*>(st_val + kSlots);
+    uint16_t* cuts = reinterpret_cast<uint16_t*>(st_val + kSlots);
+    uint16_t* numlist = cuts + kSlots;
+    uint8_t* st_meta = reinterpret_cast<uint8_t*>(numlist + kSlots);
     uint8_t* slot_line = st_meta + kSlots;
+    const uint32_t lane = (uint32_t)tid & 31u, wid = (uint32_t)tid >> 5;
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -98,16 +108,30 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        // ---- (2) the string bitmap of the whole tile, 32 bytes (= one word) per thread per step -----------------------
+        // ---- (2) the three bitmaps of the whole tile, 32 bytes (= one word of each) per thread per step ----------------------
         const int nword = (int)((nbytes + 31u) >> 5);
-        for (int g = tid; g < nword; g += kThreads) {
-            const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
-            bmX[g] = gf_classify16(v0.x, v0.y, v0.z, v0.w) | (gf_classify16(v1.x, v1.y, v1.z, v1.w) << 16);
+        for (int gb = 0; gb < nword; gb += kThreads) {  // warp w takes the 32 granules [gb + 32 w, gb + 32 w + 32)
+            const int g = gb + tid;
+            uint32_t ctrl = 0;
+            if (g < nword) {
+                const uint4 v0 = reinterpret_cast<const uint4*>(tile)[2 * g], v1 = reinterpret_cast<const uint4*>(tile)[2 * g + 1];
+                uint32_t q0, b0, p0, c0, q1, b1, p1, c1;
+                gf_bits16(v0.x, v0.y, v0.z, v0.w, q0, b0, p0, c0);
+                gf_bits16(v1.x, v1.y, v1.z, v1.w, q1, b1, p1, c1);
+                if ((uint32_t)(32 * g + 16) >= nbytes) q1 = b1 = p1 = c1 = 0u;  // the odd granule: bytes of an earlier round
+                bmQ[g] = q0 | (q1 << 16);
+                bmB[g] = b0 | (b1 << 16);
+                bmP[g] = p0 | (p1 << 16);
+                ctrl = c0 | c1;
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ctrl != 0u);
+            if (lane == 0) anyK[(gb >> 5) + (int)wid] = bal;
         }
-        if (tid < 4) bmX[nword + tid] = 0;
+        if (tid < 4) bmQ[nword + tid] = bmB[nword + tid] = bmP[nword + tid] = 0;
+        if (tid == 0) s_nnum = 0u;
         __syncthreads();
 
-        // ---- (3) one thread per line: where are the members ------------------------------------------------------------
+        // ---- (3) one thread per line: the member boundaries, from the bitmap words -----------------------------------------
         bool active = lt && tid < r;
         const int ls = active ? o0 - base : 0;
         int le = active ? o1 - base : 0;
@@ -125,10 +149,13 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
         const bool walk = active && !bad_utf8;
         bool regular = false;
         uint32_t nm = 0;
-        GfSpans G;
-        if (tid < 64 || kLines > 64) {  // warp-uniform: only the warps that hold line threads walk
-            regular = gf_walk(tile, bmX, ls, walk ? le : ls, walk, G);
-            nm = (walk && regular) ? G.m : 0u;
+        int open = 0;
+        uint16_t my_cuts[kMaxLocalMembers];
+        if (walk && !gf_has_ctrl(tile, anyK, ls, le)) {
+            // (a raw control byte anywhere near the line sends it to the exact parser: newline retry / error)
+            const int m = gf_line_members(tile, bmQ, bmB, bmP, ls, le, my_cuts, kMaxLocalMembers, open);
+            regular = m >= 0;
+            nm = regular ? (uint32_t)m : 0u;
         }
         uint32_t slots_total;
         const uint32_t slot0 = block_exclusive_scan(nm, scan_ws, slots_total);
@@ -140,33 +167,48 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
         if (lt) {
             line_ls[tid] = ls;
             line_o0[tid] = o0;
+            line_open[tid] = open;
             line_slot[tid] = slot0 | ((fast ? nm : 0u) << 16);
             line_bad[tid] = 0u;
             if (tid == r - 1) s_slots = slot0 + (fast ? nm : 0u);
         }
         if (fast) {
             for (uint32_t k = 0; k < nm; ++k) {
-                st_val[slot0 + k] = G.sp[k];
-                st_meta[slot0 + k] = G.kind[k];
+                cuts[slot0 + k] = my_cuts[k];
                 slot_line[slot0 + k] = (uint8_t)tid;
             }
         }
         __syncthreads();
         const uint32_t nslots = s_slots;
 
-        // ---- (4) one thread per member ---------------------------------------------------------------------------------
+        // ---- (4) one thread per member; numbers are only listed ----------------------------------------------------------------
         for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
             const uint32_t l = slot_line[s];
-            int2 name;
+            const uint32_t k = s - (line_slot[l] & 0xFFFFu);
+            const int a = k == 0u ? line_open[l] + 1 : (int)cuts[s - 1] + 1;
+            int2 name = make_int2(0, 0);
             unsigned long long val = 0;
             uint32_t meta = 0;
-            bool plain;
-            if (gf_member(tile, bmX, st_val[s], st_meta[s], line_o0[l], line_ls[l], name, val, meta, plain)) {
+            if (gf_member(tile, bmQ, bmB, a, (int)cuts[s], line_o0[l], line_ls[l], name, val, meta)) {
                 st_name[s] = name;
                 st_val[s] = val;
                 st_meta[s] = (uint8_t)meta;
+                if (meta == kGfNumber) numlist[atomicAdd(&s_nnum, 1u)] = (uint16_t)s;
             } else {
                 line_bad[l] = 1u;
+            }
+        }
+        __syncthreads();
+        // ... and go through json_number side by side: every lane of these warps holds a number
+        for (uint32_t q = (uint32_t)tid; q < s_nnum; q += (uint32_t)kThreads) {
+            const uint32_t s = numlist[q];
+            unsigned long long val = 0;
+            uint32_t meta = 0;
+            if (gf_member_number(tile, st_val[s], val, meta)) {
+                st_val[s] = val;
+                st_meta[s] = (uint8_t)meta;
+            } else {
+                line_bad[slot_line[s]] = 1u;
             }
         }
         __syncthreads();
@@ -284,7 +326,9 @@ __global__ void __launch_bounds__(128) post_gelf_kernel(const __grid_constant__ 
 
 }  // namespace
 
-int parse_gelf_smem_bytes(int tile_bytes) { return tile_bytes + (tile_bytes / 32 + 4) * 4 + kGelfStageSlots * (8 + 8 + 1 + 1) + 16; }
+int parse_gelf_smem_bytes(int tile_bytes) {
+    return tile_bytes + 3 * (tile_bytes / 32 + 4) * 4 + kCtrlWords * 4 + kGelfStageSlots * (8 + 8 + 2 + 2 + 1 + 1) + 16;
+}
 
 cudaError_t configure_parse_gelf(int max_tile_bytes) {
     {   // serde_json's POW10 table (visit_f64_from_parts): correctly rounded decimal literals, like rustc's

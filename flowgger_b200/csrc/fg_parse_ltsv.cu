@@ -96,8 +96,15 @@ struct LineRecs {
     uint32_t dups[kLines];       // #time | #level << 8
     uint32_t flags[kLines];      // FG_FLAG_MISSING_VALUE
     uint32_t err[kLines];        // min over failed typed values of (part index << 8 | status)
-    uint32_t dense0[kLines], dense1[kLines];  // the line's rows are [dense0, dense1) of the round
+    uint32_t dense0[kLines];     // rows of the round before the line's first one
     uint32_t state[kLines];      // 0: decoded, rows kept; 1: direct path; 2: not in this round; 3: decoded, no rows (error)
+    int t_a[kLines], t_b[kLines];  // value of the `time` part
+    double ts[kLines];
+    uint32_t ts_ok[kLines];
+    uint32_t tlist[4][kLines];   // lines by lt_time_class
+    uint32_t tcount[4];
+    uint32_t rowmask[kLtsvStageSlots / 32];  // bit s: slot s holds a row
+    uint32_t ycount[5], ybase[5], ypos[5];   // TYPED: typed rows per fg_ltsv_type (counting sort of the slots by type)
 };
 
 template <bool TYPED>
@@ -106,7 +113,6 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
     __shared__ uint32_t s_ebase, s_slots, s_direct;
-    __shared__ uint32_t warp_cnt[kWarps];
     __shared__ LineRecs L;
     // TYPED: the CTA's copy of the schema and the suffixes (a few hundred bytes)
     __shared__ uint8_t s_names[TYPED ? kSchemaBlob : 4];
@@ -126,7 +132,8 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
     unsigned long long* stage = reinterpret_cast<unsigned long long*>(bmT + bm_words);
     unsigned long long* stage_val = stage + kStageSlots;  // TYPED only
     uint16_t* tabs = reinterpret_cast<uint16_t*>(stage + (TYPED ? 2 : 1) * kStageSlots);
-    uint8_t* slot_line = reinterpret_cast<uint8_t*>(tabs + kStageSlots);
+    uint16_t* ylist = tabs + kStageSlots;  // TYPED only: the typed rows' slots, grouped by type
+    uint8_t* slot_line = reinterpret_cast<uint8_t*>(ylist + (TYPED ? kStageSlots : 0));
     if (*P.bad_offsets) return;  // CTA-uniform
     if (tid == 0) mbar_init(&mbar, 1);
     LtsvDeviceConfig cfg = P.ltsv;
@@ -233,7 +240,12 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
             L.dups[tid] = 0u;
             L.flags[tid] = 0u;
             L.err[tid] = 0xFFFFFFFFu;
-            L.dense0[tid] = L.dense1[tid] = 0u;
+            L.dense0[tid] = 0u;
+            L.t_a[tid] = -1;
+            L.t_b[tid] = 0;
+            L.ts_ok[tid] = 0u;
+            if (tid < 4) L.tcount[tid] = 0u;
+            if (tid < 5) L.ycount[tid] = L.ypos[tid] = 0u;
             L.state[tid] = active ? 0u : 2u;
             if (tid == r - 1) s_slots = slot0 + (mine ? nb : 0u);
             if (tid == 0) s_direct = 0u;
@@ -246,41 +258,102 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
         const uint32_t nslots = s_slots;
 
         // ---- (4) one thread per part ----------------------------------------------------------------------------------
-        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
-            const uint32_t l = slot_line[s];
-            const uint32_t k = s - L.slot0[l];
-            const int start = k == 0u ? L.ls[l] : (int)tabs[s - 1] + 1;
-            const int end = (int)tabs[s];
-            const LtPart pt = lt_part<TYPED>(tile, start, end, cfg, S);
-            stage[s] = pt.row;
-            if (pt.kind != LP_ROW) {  // ~4 of 20 parts
-                if (pt.kind == LP_NONE) atomicOr(&L.flags[l], 0x02u);  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
-                else if (pt.kind == LP_HOST) atomicMax(&L.host_s[l], s + 1u);
-                else if (pt.kind == LP_MSG) atomicMax(&L.msg_s[l], s + 1u);
-                else if (pt.kind == LP_TIME) { atomicMax(&L.time_s[l], s + 1u); atomicAdd(&L.dups[l], 1u); }
-                else { atomicMax(&L.level_s[l], s + 1u); atomicAdd(&L.dups[l], 0x100u); }
+        for (uint32_t sb = 0; sb < nslots; sb += (uint32_t)kThreads) {  // warp w takes the 32 slots [sb + 32 w, sb + 32 w + 32)
+            const uint32_t s = sb + (uint32_t)tid;
+            bool is_row = false;
+            if (s < nslots) {
+                const uint32_t l = slot_line[s];
+                const uint32_t k = s - L.slot0[l];
+                const int start = k == 0u ? L.ls[l] : (int)tabs[s - 1] + 1;
+                const int end = (int)tabs[s];
+                const LtPart pt = lt_part<TYPED>(tile, start, end, cfg, S);
+                stage[s] = pt.row;
+                is_row = pt.kind == LP_ROW;
+                if (TYPED && ((pt.row >> 56) & 0x07u) != 0u) atomicAdd(&L.ycount[(pt.row >> 56) & 0x07u], 1u);
+                if (!is_row) {  // ~4 of 20 parts
+                    if (pt.kind == LP_NONE) atomicOr(&L.flags[l], 0x02u);  // FG_FLAG_MISSING_VALUE: println! at :99 is replayed by the host
+                    else if (pt.kind == LP_HOST) atomicMax(&L.host_s[l], s + 1u);
+                    else if (pt.kind == LP_MSG) atomicMax(&L.msg_s[l], s + 1u);
+                    else if (pt.kind == LP_TIME) { atomicMax(&L.time_s[l], s + 1u); atomicAdd(&L.dups[l], 1u); }
+                    else { atomicMax(&L.level_s[l], s + 1u); atomicAdd(&L.dups[l], 0x100u); }
+                }
             }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is_row);
+            if (lane == 0 && sb + 32u * wid < (uint32_t)kStageSlots) L.rowmask[(sb >> 5) + wid] = bal;
         }
         __syncthreads();
 
-        // ---- (5) values: typed rows (one thread per row), then `time` / `level` and the status (one thread per line) ----
+        // ---- (5) values.  a: one thread per typed row; one thread per line lists its `time` value by kind ------------------
         if (TYPED) {
-            for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
-                const unsigned long long e = stage[s];
-                const int type = (int)((e >> 56) & 0x07u);
-                if (type != 0) {
-                    const int va = (int)(e & 0xFFFFu) + (int)((e >> 16) & 0xFFFFu) + 1;
-                    unsigned long long val = 0;
-                    const uint32_t st = ltsv_parse_typed(tile, va, va + (int)((e >> 32) & 0xFFFFFFu), type, val);
-                    if (st == FG_ST_OK) stage_val[s] = val;
-                    else {
-                        const uint32_t l = slot_line[s];
-                        atomicMin(&L.err[l], ((s - L.slot0[l]) << 8) | st);
-                    }
-                }
+            // typed values differ wildly in cost (bool: a compare, f64: Rust's from_str): the typed rows are grouped by
+            // type (counting sort over the slots), so that the lanes of a warp run the SAME value parser
+            if (tid == 0) {
+                uint32_t acc = 0;
+                for (int t = 1; t < 5; ++t) { L.ybase[t] = acc; acc += L.ycount[t]; }
+                L.ybase[0] = acc;  // total
             }
             __syncthreads();
+            for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
+                const uint32_t type = (uint32_t)(stage[s] >> 56) & 0x07u;
+                if (type != 0u) ylist[L.ybase[type] + atomicAdd(&L.ypos[type], 1u)] = (uint16_t)s;
+            }
+            __syncthreads();
+            const uint32_t ntyped = L.ybase[0];
+            for (uint32_t q = (uint32_t)tid; q < ntyped; q += (uint32_t)kThreads) {
+                const uint32_t s = ylist[q];
+                const unsigned long long e = stage[s];
+                const int type = (int)((e >> 56) & 0x07u);
+                const int va = (int)(e & 0xFFFFu) + (int)((e >> 16) & 0xFFFFu) + 1;
+                unsigned long long val = 0;
+                const uint32_t st = ltsv_parse_typed(tile, va, va + (int)((e >> 32) & 0xFFFFFFu), type, val);
+                if (st == FG_ST_OK) stage_val[s] = val;
+                else {
+                    const uint32_t l = slot_line[s];
+                    atomicMin(&L.err[l], ((s - L.slot0[l]) << 8) | st);
+                }
+            }
         }
+        // value bounds of a special part: slot s covers [start, tabs[s]), the value starts behind `key:`
+        auto value_of = [&](uint32_t s1, int key_len, int& a, int& b, int& k) {
+            a = -1; b = 0; k = -1;
+            if (s1 == 0u) return;
+            const uint32_t s = s1 - 1u;
+            k = (int)(s - slot0);
+            const int start = k == 0 ? ls : (int)tabs[s - 1] + 1;
+            a = start + key_len + 1;
+            b = (int)tabs[s];
+        };
+        bool direct = false;
+        int t_a = -1, t_b = 0, t_k = -1;
+        if (mine) {
+            const uint32_t d = L.dups[tid];
+            // a repeated `time` / `level`: every occurrence is evaluated in order (:104-121) — round-1 scanner
+            direct = (d & 0xFFu) > 1u || (d >> 8) > 1u;
+            if (!direct) {
+                value_of(L.time_s[tid], 4, t_a, t_b, t_k);
+                if (t_a >= 0) {
+                    L.t_a[tid] = t_a;
+                    L.t_b[tid] = t_b;
+                    const int c = lt_time_class(tile, t_a, t_b);
+                    L.tlist[c][atomicAdd(&L.tcount[c], 1u)] = (uint32_t)tid;
+                }
+            }
+        }
+        __syncthreads();
+        // b: parse_ts — warps 2c and 2c + 1 take the lines of class c, so the four attempts of :263-267 run side by side on
+        // different warps instead of one after the other on the same lanes
+        {
+            const uint32_t c = wid >> 1, idx = ((wid & 1u) << 5) + lane;
+            if (c < 4u && idx < L.tcount[c]) {
+                const uint32_t l = L.tlist[c][idx];
+                double ts;
+                const bool ok = lt_time_value(tile, L.t_a[l], L.t_b[l], ts);
+                L.ts[l] = ts;
+                L.ts_ok[l] = ok ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        // c: one thread per line settles the status
         LineResult res;
         res.ts = 0.0;
         res.facility = 0xFFu;
@@ -290,34 +363,21 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
         res.host_o = res.app_o = res.proc_o = res.mid_o = res.msg_o = res.full_o = -1;
         res.host_l = res.app_l = res.proc_l = res.mid_l = res.msg_l = res.full_l = 0;
         res.n_entries = 0;
-        bool direct = false;
+        uint32_t my_n = 0;
         if (mine) {
-            const uint32_t d = L.dups[tid];
-            if ((d & 0xFFu) > 1u || (d >> 8) > 1u) {
-                direct = true;  // a repeated `time` / `level`: every occurrence is evaluated in order (:104-121) — round-1 scanner
-            } else {
-                // value bounds of the special parts: slot s covers [start, tabs[s]), the value starts behind `key:`
-                auto value_of = [&](uint32_t s1, int key_len, int& a, int& b, int& k) {
-                    a = -1; b = 0; k = 0;
-                    if (s1 == 0u) return;
-                    const uint32_t s = s1 - 1u;
-                    k = (int)(s - slot0);
-                    const int start = k == 0 ? ls : (int)tabs[s - 1] + 1;
-                    a = start + key_len + 1;
-                    b = (int)tabs[s];
-                };
-                int t_a, t_b, t_k, l_a, l_b, l_k, h_a, h_b, h_k, m_a, m_b, m_k;
-                value_of(L.time_s[tid], 4, t_a, t_b, t_k);
+            if (!direct) {
+                int l_a, l_b, l_k, h_a, h_b, h_k, m_a, m_b, m_k;
                 value_of(L.level_s[tid], 5, l_a, l_b, l_k);
                 value_of(L.host_s[tid], 4, h_a, h_b, h_k);
                 value_of(L.msg_s[tid], 7, m_a, m_b, m_k);
-                const int bad_k = lt_finish_line(tile, t_a, t_b, t_k, l_a, l_b, l_k, L.err[tid], h_a >= 0, res);
+                const int bad_k = lt_finish_line(tile, t_k, L.ts_ok[tid] != 0u, L.ts[tid], l_a, l_b, l_k, L.err[tid], h_a >= 0, res);
                 res.flags = L.flags[tid];
                 if (res.status == FG_ST_OK) {
                     if (h_a >= 0) { res.host_o = h_a - ls; res.host_l = h_b - h_a; }
                     if (m_a >= 0) { res.msg_o = m_a - ls; res.msg_l = m_b - m_a; }
                     res.full_o = 0;  // full_msg = the whole line, untrimmed :219
                     res.full_l = le - ls;
+                    my_n = lt_rows_between(L.rowmask, slot0, slot0 + nb);
                 } else {
                     // the failing part (LTSV side effects on the host stop there); a missing timestamp / hostname: after the last part
                     res.full_o = bad_k >= 0 ? (bad_k == 0 ? ls : (int)tabs[slot0 + (uint32_t)bad_k - 1u] + 1) - ls : (le - ls) + 1;
@@ -333,63 +393,35 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
             res.full_o = 0;
             if (active) L.state[tid] = 3u;
         }
-        __syncthreads();
 
-        // ---- (6) rows of the decoded lines: count, place, write -------------------------------------------------------
-        // pass A: rows per thread -> total of the round
-        uint32_t mycnt = 0;
-        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads)
-            mycnt += (stage[s] != 0ull && L.state[slot_line[s]] == 0u) ? 1u : 0u;
+        // ---- (6) rows of the decoded lines: place (scan over the lines + ONE global atomic), write --------------------------
         uint32_t total;
-        (void)block_exclusive_scan(mycnt, scan_ws, total);
+        const uint32_t excl = block_exclusive_scan(my_n, scan_ws, total);  // (its barriers also publish L.state)
+        if (lt) L.dense0[tid] = excl;
         if (tid == 0 && total) s_ebase = atomicAdd(P.entry_counter, total);
         __syncthreads();
         const uint32_t ebase = total ? s_ebase : 0u;
         const bool ovf = (unsigned long long)ebase + total > (unsigned long long)P.entry_cap;
-        // pass B: slot order = row order; a ballot scan per chunk of 256 slots
-        uint32_t run = 0;
-        for (uint32_t cb = 0; cb < nslots; cb += (uint32_t)kThreads) {
-            const uint32_t s = cb + (uint32_t)tid;
-            unsigned long long e = 0;
-            uint32_t l = 0;
-            bool keep = false;
-            if (s < nslots) {
-                e = stage[s];
-                l = slot_line[s];
-                keep = e != 0ull && L.state[l] == 0u;
+        if (total && !ovf) {
+            // one thread per slot; a row's place = rows of its line before it (popcount over the row mask)
+            for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
+                const unsigned long long e = stage[s];
+                if (e == 0ull) continue;
+                const uint32_t l = slot_line[s];
+                if (L.state[l] != 0u) continue;
+                const uint32_t j = ebase + L.dense0[l] + lt_rows_between(L.rowmask, L.slot0[l], s);
+                const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
+                const uint32_t meta = (uint32_t)(e >> 56) & 0x7Fu;  // without kLtRow
+                sink.name[j] = make_int2(ka, kn);
+                unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
+                if (TYPED && (meta & 0x07u) != 0u) v = stage_val[s];
+                sink.val[j] = v;
+                sink.meta[j] = (uint8_t)meta;
             }
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-            if (lane == 0) warp_cnt[wid] = (uint32_t)__popc(bal);
-            __syncthreads();
-            uint32_t before = run, chunk = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const uint32_t c = warp_cnt[w];
-                if ((uint32_t)w < wid) before += c;
-                chunk += c;
-            }
-            const uint32_t idx = before + (uint32_t)__popc(bal & ((1u << lane) - 1u));  // rows of the round before this slot
-            if (s < nslots) {
-                const uint32_t k = s - L.slot0[l];
-                if (k == 0u) L.dense0[l] = idx;
-                if (k + 1u == L.nb[l]) L.dense1[l] = idx + (keep ? 1u : 0u);
-                if (keep && !ovf) {
-                    const uint32_t j = ebase + idx;
-                    const int ka = base + (int)(e & 0xFFFFu), kn = (int)((e >> 16) & 0xFFFFu);
-                    const uint32_t meta = (uint32_t)(e >> 56) & 0x7Fu;  // without kLtRow
-                    sink.name[j] = make_int2(ka, kn);
-                    unsigned long long v = (unsigned long long)(uint32_t)(ka + kn + 1) | (((e >> 32) & 0xFFFFFFull) << 32);
-                    if (TYPED && (meta & 0x07u) != 0u) v = stage_val[s];
-                    sink.val[j] = v;
-                    sink.meta[j] = (uint8_t)meta;
-                }
-            }
-            run += chunk;
-            __syncthreads();  // warp_cnt is reused by the next chunk; dense0/1 are read below
         }
         if (active && !direct) {
-            const uint32_t my_n = (L.state[tid] == 0u && !ovf) ? L.dense1[tid] - L.dense0[tid] : 0u;
-            write_row(P, i, o0, res, my_n ? ebase + L.dense0[tid] : 0u, my_n);
+            const uint32_t n_out = ovf ? 0u : my_n;
+            write_row(P, i, o0, res, n_out ? ebase + excl : 0u, n_out);
         }
 
         // ---- lines of this round that need the sequential scanner (CTA-uniform loop, rare) -----------------------------
@@ -405,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
 }  // namespace
 
 int parse_ltsv_smem_bytes(int tile_bytes, bool typed) {
-    return tile_bytes + (tile_bytes / 32 + 4) * 4 + kLtsvStageSlots * 8 * (typed ? 2 : 1) + kLtsvStageSlots * 2 + kLtsvStageSlots + 16;
+    return tile_bytes + (tile_bytes / 32 + 4) * 4 + kLtsvStageSlots * 8 * (typed ? 2 : 1) + kLtsvStageSlots * 2 * (typed ? 2 : 1) + kLtsvStageSlots + 16;
 }
 
 cudaError_t configure_parse_ltsv(int max_tile_bytes) {

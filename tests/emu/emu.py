@@ -37,8 +37,7 @@ def lib() -> C.CDLL:
         _lib.emu5424_classify16.argtypes = [C.c_void_p]
         _lib.emu_ltsv_classify16.restype = C.c_uint32
         _lib.emu_ltsv_classify16.argtypes = [C.c_void_p]
-        _lib.emu_gelf_classify16.restype = C.c_uint32
-        _lib.emu_gelf_classify16.argtypes = [C.c_void_p]
+        _lib.emu_gelf_bits16.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -101,10 +100,13 @@ def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict
     return buf, offs, d
 
 
-def gelf_classify16(block: bytes) -> int:
+def gelf_bits16(block: bytes) -> tuple[int, int, int, int]:
+    """(quote mask, backslash mask, comma mask, control-byte flag) of a 16-byte granule."""
     assert len(block) == 16
     buf = C.create_string_buffer(block, 16)
-    return int(lib().emu_gelf_classify16(buf))
+    out = (C.c_uint32 * 4)()
+    lib().emu_gelf_bits16(buf, out)
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
 
 def gelf_decode_dump(native, data: np.ndarray, offsets: np.ndarray, tile_bytes: int = 34304, strip_eol: int = 0,

@@ -1,6 +1,6 @@
 // emu_gelf.cpp — CPU emulation of the GELF device logic (TEST INFRASTRUCTURE, see cuda_shim.h).
 //
-// Compiles the product's walker sources (fg_gelffast.cuh: stage-1 string bitmap, stage-2 member walk; fg_gelf.cuh: the
+// Compiles the product's device sources (fg_gelffast.cuh: stage-1 bitmaps, line pass, gf_member, gf_finish; fg_gelf.cuh: the
 // exact parser and phase 2) with g++ and replays what parse_gelf_kernel / post_gelf_kernel do with them — CTA rounds over
 // a staging tile, slot reservation, staged rows, the slow list — one lane at a time.  The result has the layout of
 // fg_batch_out (columnar rows + side table), so the CPU test-suite can push it through the product's materialiser and
@@ -53,10 +53,12 @@ void init_pow10() {
 
 extern "C" {
 
-uint32_t emu_gelf_classify16(const uint8_t* p) {
-    uint32_t w[4];
+// out[4]: the Q / B / P masks of a 16-byte granule and its control-byte flag (0 / 1)
+void emu_gelf_bits16(const uint8_t* p, uint32_t* out) {
+    uint32_t w[4], c;
     memcpy(w, p, 16);
-    return fg::gf_classify16(w[0], w[1], w[2], w[3]);
+    fg::gf_bits16(w[0], w[1], w[2], w[3], out[0], out[1], out[2], c);
+    out[3] = c != 0u;
 }
 
 int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int32_t tile_bytes, int32_t strip_eol,
@@ -68,7 +70,7 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
     T->none.assign(nn, fg_span{-1, 0});
     const int64_t total_bytes = n > 0 ? offsets[n] : 0;
     std::vector<uint8_t> tile((size_t)tile_bytes + 64);
-    std::vector<uint32_t> bmX((size_t)tile_bytes / 32 + 8);
+    std::vector<uint32_t> bmQ((size_t)tile_bytes / 32 + 8), bmB(bmQ.size()), bmP(bmQ.size()), anyK(bmQ.size() / 32 + 8);
     std::vector<fg_span> st_name((size_t)kSlots + fg::kMaxLocalMembers);
     std::vector<uint64_t> st_val(st_name.size());
     std::vector<uint8_t> st_meta(st_name.size());
@@ -91,9 +93,17 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
             const uint32_t nbytes = (uint32_t)((oend - base) + 15) & ~15u;
             for (uint32_t k = 0; k < nbytes; ++k) tile[k] = (int64_t)base + k < total_bytes ? bytes[base + k] : 0;  // the bulk copy
             const int nword = (int)((nbytes + 31u) >> 5);
-            for (int g = 0; g < nword; ++g)
-                bmX[g] = emu_gelf_classify16(tile.data() + 32 * g) | (emu_gelf_classify16(tile.data() + 32 * g + 16) << 16);
-            for (int k = 0; k < 4; ++k) bmX[nword + k] = 0;
+            std::fill(anyK.begin(), anyK.end(), 0u);
+            for (int g = 0; g < nword; ++g) {
+                uint32_t lo[4], hi[4] = {0, 0, 0, 0};
+                emu_gelf_bits16(tile.data() + 32 * g, lo);
+                if ((uint32_t)(32 * g + 16) < nbytes) emu_gelf_bits16(tile.data() + 32 * g + 16, hi);
+                bmQ[g] = lo[0] | (hi[0] << 16);
+                bmB[g] = lo[1] | (hi[1] << 16);
+                bmP[g] = lo[2] | (hi[2] << 16);
+                if (lo[3] | hi[3]) anyK[g >> 5] |= 1u << (g & 31);
+            }
+            for (int k = 0; k < 4; ++k) bmQ[nword + k] = bmB[nword + k] = bmP[nword + k] = 0;
             uint32_t run = 0;
             int done = 0;
             for (int tid = 0; tid < r; ++tid) {
@@ -110,25 +120,29 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                     }
                     if (invalid && invalid[i]) bad = true;
                 }
-                fg::GfSpans G;
                 const bool walk = !bad;
-                bool regular = fg::gf_walk(tile.data(), bmX.data(), ls, walk ? le : ls, walk, G);
-                const uint32_t nb = (walk && regular) ? G.m : 0u;
+                uint16_t cuts[fg::kMaxLocalMembers];
+                int open = 0, m = -1;
+                if (walk && !fg::gf_has_ctrl(tile.data(), anyK.data(), ls, le))
+                    m = fg::gf_line_members(tile.data(), bmQ.data(), bmB.data(), bmP.data(), ls, le, cuts, fg::kMaxLocalMembers, open);
+                bool regular = m >= 0;
+                const uint32_t nb = (walk && regular) ? (uint32_t)m : 0u;
                 if (run + nb > (uint32_t)kSlots) break;  // the round is cut here; the rest is redone
                 const uint32_t slot0 = run;
                 run += nb;
                 ++done;
-                // (4) one member at a time: validation + conversion, in place in the slots
+                // (4) one member at a time: validation + conversion; numbers in a second pass
                 fg::Members M;
                 M.m = 0;
                 M.spilled = false;
                 uint32_t n_plain = 0;
                 for (uint32_t k = 0; k < nb && regular; ++k) {
-                    int2 name;
+                    int2 name = make_int2(0, 0);
                     unsigned long long val = 0;
                     uint32_t meta = 0;
-                    bool plain = false;
-                    if (!fg::gf_member(tile.data(), bmX.data(), G.sp[k], G.kind[k], o0, ls, name, val, meta, plain)) {
+                    const int a = k == 0 ? open + 1 : (int)cuts[k - 1] + 1;
+                    if (!fg::gf_member(tile.data(), bmQ.data(), bmB.data(), a, (int)cuts[k], o0, ls, name, val, meta) ||
+                        (meta == fg::kGfNumber && !fg::gf_member_number(tile.data(), val, val, meta))) {
                         regular = false;
                         break;
                     }
@@ -136,7 +150,7 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                     M.val[k] = val;
                     M.meta[k] = (uint8_t)meta;
                     M.m = k + 1;
-                    if (plain) ++n_plain;
+                    if ((meta >> 5) == (uint32_t)fg::GKEY_OTHER) ++n_plain;
                 }
                 if (walk && !regular) {
                     slow_list.push_back((uint32_t)i);

@@ -242,7 +242,13 @@ int emu_ltsv_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                 value_of(level_s, 5, l_a, l_b, l_k);
                 value_of(host_s, 4, h_a, h_b, h_k);
                 value_of(msg_s, 7, m_a, m_b, m_k);
-                const int bad_k = fg::lt_finish_line(tile.data(), t_a, t_b, t_k, l_a, l_b, l_k, err, h_a >= 0, res);
+                double tsv = 0.0;
+                bool ts_ok = false;
+                if (t_a >= 0) {
+                    (void)fg::lt_time_class(tile.data(), t_a, t_b);  // a scheduling hint on the device: must not fault on any value
+                    ts_ok = fg::lt_time_value(tile.data(), t_a, t_b, tsv);
+                }
+                const int bad_k = fg::lt_finish_line(tile.data(), t_a >= 0 ? t_k : -1, ts_ok, tsv, l_a, l_b, l_k, err, h_a >= 0, res);
                 res.flags = flags;
                 if (res.status == FG_ST_OK) {
                     if (h_a >= 0) { res.host_o = h_a - ls[tid]; res.host_l = h_b - h_a; }

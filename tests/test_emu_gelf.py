@@ -33,18 +33,24 @@ def check(emu, native, oracle, data, offs, **kw):
     return info
 
 
-def test_stage1_bitmap_per_byte(emu):
-    """gf_classify16 flags exactly '"', '\\\\' and the bytes below 0x20 — for every byte value in every position."""
-    want = lambda b: b == 0x22 or b == 0x5C or b < 0x20
+def test_stage1_bitmaps_per_byte(emu):
+    """gf_bits16 flags exactly the quotes, the backslashes, the commas and "some byte below 0x20" — for every byte value in
+    every position."""
     rng = np.random.default_rng(7)
     for b in range(256):
         for pos in range(16):
             blk = bytearray(rng.integers(0x61, 0x7B, 16, dtype=np.uint8).tobytes())
             blk[pos] = b
-            assert emu.gelf_classify16(bytes(blk)) == ((1 << pos) if want(b) else 0), (b, pos)
+            q, bs, p, c = emu.gelf_bits16(bytes(blk))
+            bit = 1 << pos
+            assert (q, bs, p, c) == (bit if b == 0x22 else 0, bit if b == 0x5C else 0, bit if b == 0x2C else 0, 1 if b < 0x20 else 0), (b, pos)
     for _ in range(3000):
         blk = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
-        assert emu.gelf_classify16(blk) == sum(1 << k for k in range(16) if want(blk[k]))
+        q, bs, p, c = emu.gelf_bits16(blk)
+        assert q == sum(1 << k for k in range(16) if blk[k] == 0x22)
+        assert bs == sum(1 << k for k in range(16) if blk[k] == 0x5C)
+        assert p == sum(1 << k for k in range(16) if blk[k] == 0x2C)
+        assert c == int(any(x < 0x20 for x in blk))
 
 
 def test_goldens_and_appendix(emu, native, oracle):
