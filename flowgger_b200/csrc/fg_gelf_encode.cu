@@ -40,26 +40,41 @@ struct Span {
 struct CountSink {
     uint32_t n = 0;
     __device__ __forceinline__ void put(uint32_t) { ++n; }
+    __device__ __forceinline__ void put4(uint32_t) { n += 4u; }
     __device__ __forceinline__ void finish() {}
 };
 // bytes -> aligned 32-bit stores (byte stores only for the unaligned head and the tail of the record)
 struct WordSink {
     uint8_t* p;
-    uint32_t acc = 0;
-    int nacc = 0;
+    unsigned long long acc = 0;  // pending bytes, low byte first
+    int nacc = 0;                // 0..3 between calls
     __device__ __forceinline__ explicit WordSink(uint8_t* at) : p(at) {}
     __device__ __forceinline__ void put(uint32_t b) {
         if (((size_t)p & 3u) != 0u && nacc == 0) {  // head: up to three single bytes until the address is aligned
             *p++ = (uint8_t)b;
             return;
         }
-        acc |= b << (8 * nacc);
+        acc |= (unsigned long long)b << (8 * nacc);
         if (++nacc == 4) {
-            *reinterpret_cast<uint32_t*>(p) = acc;
+            *reinterpret_cast<uint32_t*>(p) = (uint32_t)acc;
             p += 4;
             acc = 0;
             nacc = 0;
         }
+    }
+    // four bytes at once (low byte first): one aligned store, whatever is already pending stays in front
+    __device__ __forceinline__ void put4(uint32_t w) {
+        if (((size_t)p & 3u) != 0u && nacc == 0) {  // still in the head: byte by byte (at most once per record)
+            put(w & 0xFFu);
+            put((w >> 8) & 0xFFu);
+            put((w >> 16) & 0xFFu);
+            put(w >> 24);
+            return;
+        }
+        acc |= (unsigned long long)w << (8 * nacc);
+        *reinterpret_cast<uint32_t*>(p) = (uint32_t)acc;
+        p += 4;
+        acc >>= 32;
     }
     __device__ __forceinline__ void finish() {
         for (int k = 0; k < nacc; ++k) p[k] = (uint8_t)(acc >> (8 * k));
@@ -387,7 +402,18 @@ __device__ __forceinline__ uint32_t json_escape_of(uint32_t c) {
     return c == 8u ? 'b' : c == 9u ? 't' : c == 10u ? 'n' : c == 12u ? 'f' : c == 13u ? 'r' : 0u;
 }
 
-// The warp-uniform loop: one output byte per lane and iteration.  `live` = this lane has a record to emit.
+// 0x80 in every byte of w that serde_json escapes: '"', '\\', or a byte below 0x20 (a superset of \b \f \n \r \t: the
+// other control bytes take the one-byte path and are copied there)
+__device__ __forceinline__ uint32_t json_escape_flags4(uint32_t w) {
+    const uint32_t x1 = w ^ 0x22222222u, x2 = w ^ 0x5C5C5C5Cu, t = w & 0xE0E0E0E0u;
+    const uint32_t n1 = ((x1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x1, n2 = ((x2 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x2,
+                   n3 = ((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t;  // bit 7: byte != 0
+    return ~(n1 & n2 & n3) & 0x80808080u;
+}
+
+// The warp-uniform loop: per lane and iteration FOUR output bytes when the segment has them and none needs an escape, else
+// one.  `live` = this lane has a record to emit.  (One byte per iteration cost ~65 instructions per byte: 1570
+// warp-instructions per record, profiles/r2_notes.md.)
 template <class Sink>
 __device__ __forceinline__ void run_segments(const SegList& L, bool live, Sink& s) {
     int si = 0, k = 0, len = 0;
@@ -402,18 +428,29 @@ __device__ __forceinline__ void run_segments(const SegList& L, bool live, Sink& 
     }
     while (__any_sync(0xFFFFFFFFu, more)) {
         if (more) {
-            uint32_t out;
-            if (pending) {
-                out = pending;
-                pending = 0;
-            } else {
-                out = p[k++];
-                if (esc) {
-                    const uint32_t e = json_escape_of(out);
-                    if (e) { pending = e; out = '\\'; }
+            bool four = false;
+            if (!pending && k + 4 <= len) {
+                const uint32_t w = (uint32_t)p[k] | ((uint32_t)p[k + 1] << 8) | ((uint32_t)p[k + 2] << 16) | ((uint32_t)p[k + 3] << 24);
+                if (!esc || json_escape_flags4(w) == 0u) {
+                    s.put4(w);
+                    k += 4;
+                    four = true;
                 }
             }
-            s.put(out);
+            if (!four) {
+                uint32_t out;
+                if (pending) {
+                    out = pending;
+                    pending = 0;
+                } else {
+                    out = p[k++];
+                    if (esc) {
+                        const uint32_t e = json_escape_of(out);
+                        if (e) { pending = e; out = '\\'; }
+                    }
+                }
+                s.put(out);
+            }
             if (k >= len && !pending) {  // next segment (none is empty)
                 ++si;
                 if (si < L.n) {

@@ -32,7 +32,7 @@ namespace {
 constexpr int kLines = kGelfLinesPerCta;
 constexpr int kThreads = kGelfThreadsPerCta;
 constexpr int kSlots = kGelfStageSlots;
-constexpr int kCtrlWords = kGelfMaxTile / 32 / 32 + 8;  // one bit per 32-byte granule of the largest tile
+constexpr int kCtrlWords = (kGelfMaxTile / 32 / 32 + 8 + 3) & ~3;  // one bit per 32-byte granule of the largest tile; keeps the slots 16-byte aligned
 
 __device__ __forceinline__ void write_row(const ParseParams& P, int i, int o0, const LineResult& res, uint32_t my_begin, uint32_t my_n) {
     const bool ok = res.status == FG_ST_OK;
