@@ -110,54 +110,71 @@ FG_DEV uint32_t gf_clip(uint32_t w, int word, int lo, int hi) {
 // The recipe per 32-bit word (simdjson's, with the carries kept in two registers): backslashes that start an odd-length run
 // escape the byte behind the run; quotes that are not escaped toggle "inside a string"; a prefix XOR spreads that over the
 // word.
-FG_DEV int gf_line_commas(const uint32_t* bmQ, const uint32_t* bmB, const uint32_t* bmP, int ls, int le, uint16_t* cuts, int cap) {
-    if (le <= ls) return 0;
-    const int w0 = ls >> 5, w1 = (le - 1) >> 5;
+FG_DEV int gf_line_commas(const uint32_t* bmQ, const uint32_t* bmB, const uint32_t* bmP, int ls, int le, uint16_t* cuts, int cap, bool act) {
+    // All lanes of the warp call (act = this lane has a line): the word loop and the comma loop run in lock step — written
+    // with plain loops and early returns the lanes of a warp drifted apart and ran one at a time (profiles/r2_notes.md).
+    const bool run = act && le > ls;
+    const int w0 = ls >> 5, w1 = run ? (le - 1) >> 5 : w0 - 1;
     uint32_t prev_escaped = 0u;    // bit 0: the first byte of this word is escaped by a run ending in the previous word
     uint32_t prev_in_string = 0u;  // all ones: the previous word ended inside a string
     int n = 0;
-    for (int w = w0; w <= w1; ++w) {
-        uint32_t bs = gf_clip(bmB[w], w, ls, le);
-        const uint32_t q = gf_clip(bmQ[w], w, ls, le), pc = gf_clip(bmP[w], w, ls, le);
-        // escaped bytes
-        bs &= ~prev_escaped;
-        const uint32_t follows = (bs << 1) | prev_escaped;
-        const uint32_t odd_starts = bs & ~0x55555555u & ~follows;
-        const uint32_t sum = odd_starts + bs;
-        const uint32_t carry = sum < odd_starts ? 1u : 0u;  // a run reaching the end of the word that started on an odd bit
-        const uint32_t invert = sum << 1;
-        const uint32_t escaped = (0x55555555u ^ invert) & follows;
-        prev_escaped = carry;
-        // string interior
-        uint32_t x = q & ~escaped;
-        x ^= x << 1;
-        x ^= x << 2;
-        x ^= x << 4;
-        x ^= x << 8;
-        x ^= x << 16;
-        x ^= prev_in_string;
-        prev_in_string = (uint32_t)((int32_t)x >> 31);
-        uint32_t c = pc & ~x;
-        while (c) {
-            if (n >= cap) return -1;
-            cuts[n++] = (uint16_t)((w << 5) + fg_ffs(c) - 1);
-            c &= c - 1u;
+    bool bad = false;
+    for (int w = w0; fg_any(w <= w1); ++w) {
+        uint32_t c = 0u;
+        if (w <= w1) {
+            uint32_t bs = gf_clip(bmB[w], w, ls, le);
+            const uint32_t q = gf_clip(bmQ[w], w, ls, le), pc = gf_clip(bmP[w], w, ls, le);
+            // escaped bytes
+            bs &= ~prev_escaped;
+            const uint32_t follows = (bs << 1) | prev_escaped;
+            const uint32_t odd_starts = bs & ~0x55555555u & ~follows;
+            const uint32_t sum = odd_starts + bs;
+            prev_escaped = sum < odd_starts ? 1u : 0u;  // a run reaching the end of the word that started on an odd bit
+            const uint32_t escaped = (0x55555555u ^ (sum << 1)) & follows;
+            // string interior
+            uint32_t x = q & ~escaped;
+            x ^= x << 1;
+            x ^= x << 2;
+            x ^= x << 4;
+            x ^= x << 8;
+            x ^= x << 16;
+            x ^= prev_in_string;
+            prev_in_string = (uint32_t)((int32_t)x >> 31);
+            c = pc & ~x;
+        }
+        for (;;) {
+            const bool more = c != 0u;
+            if (!fg_any(more)) break;
+            if (more) {
+                if (n < cap) cuts[n] = (uint16_t)((w << 5) + fg_ffs(c) - 1);
+                else bad = true;
+                ++n;
+                c &= c - 1u;
+            }
         }
     }
-    return prev_in_string ? -1 : n;
+    return (bad || prev_in_string) ? -1 : n;
 }
 
 // the line [ls, le) as member spans: returns the number of members m (their spans are [start_k, cuts[k]) with
 // start_0 = `open` + 1, start_k = cuts[k - 1] + 1, the last cut being the closing brace), or -1: not regular.
 FG_DEV int gf_line_members(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB, const uint32_t* bmP, int ls, int le, uint16_t* cuts,
-                           int cap, int& open) {
+                           int cap, int& open, bool act) {
     int a = ls, b = le;
-    while (a < b && T[a] == ' ') ++a;
-    while (b > a && T[b - 1] == ' ') --b;
-    if (b - a < 2 || T[a] != '{' || T[b - 1] != '}') return -1;
+    for (;;) {
+        const bool m = act && a < b && T[a] == ' ';
+        if (!fg_any(m)) break;
+        if (m) ++a;
+    }
+    for (;;) {
+        const bool m = act && b > a && T[b - 1] == ' ';
+        if (!fg_any(m)) break;
+        if (m) --b;
+    }
+    const bool shape = act && b - a >= 2 && T[a] == '{' && T[b - 1] == '}';
     open = a;
-    const int n = gf_line_commas(bmQ, bmB, bmP, a + 1, b - 1, cuts, cap - 1);
-    if (n < 0) return -1;
+    const int n = gf_line_commas(bmQ, bmB, bmP, a + 1, b - 1, cuts, cap - 1, shape);
+    if (!shape || n < 0) return -1;
     if (n == 0) {  // `{}` or one member
         int c = a + 1;
         while (c < b - 1 && T[c] == ' ') ++c;
@@ -182,90 +199,127 @@ FG_DEV bool gf_has_ctrl(const uint8_t* T, const uint32_t* anyK, int ls, int le) 
 }
 
 // ---- members ---------------------------------------------------------------------------------------------------------
+// Everything below is called by ALL lanes of a warp (act = this lane has work) and loops in lock step.
 // position of the first set bit of bm in [from, to), or -1
-FG_DEV int gf_next_bit(const uint32_t* bm, int from, int to) {
-    if (from >= to) return -1;
+FG_DEV int gf_next_bit(const uint32_t* bm, int from, int to, bool act) {
+    const bool run = act && from < to;
     int w = from >> 5;
-    uint32_t m = bm[w] & (0xFFFFFFFFu << (from & 31));
-    while (m == 0u && ((w + 1) << 5) < to) m = bm[++w];
+    uint32_t m = run ? bm[w] & (0xFFFFFFFFu << (from & 31)) : 0u;
+    for (;;) {
+        const bool more = run && m == 0u && ((w + 1) << 5) < to;
+        if (!fg_any(more)) break;
+        if (more) m = bm[++w];
+    }
     if (m == 0u) return -1;
     const int h = (w << 5) + fg_ffs(m) - 1;
     return h < to ? h : -1;
 }
-// is the byte at h escaped, i.e. preceded by an odd number of backslashes (inside [lo, h))
-FG_DEV bool gf_escaped(const uint32_t* bmB, int lo, int h) {
-    int run = 0;
-    for (int i = h - 1; i >= lo && ((bmB[i >> 5] >> (i & 31)) & 1u); --i) ++run;
+// is the byte at h escaped, i.e. preceded by an odd number of backslashes?  (the byte before the string body is its
+// opening quote, so the run cannot reach back past it)
+FG_DEV bool gf_escaped(const uint32_t* bmB, int h) {
+    const int s0 = h >= 32 ? h - 32 : 0, nb = h - s0;
+    if (nb == 0) return false;
+    const uint32_t W = r5_window(bmB, s0) << (32 - nb);  // bit 31 = the byte before h
+    int run = fg_clz(~W);
+    if (run >= nb && nb == 32) {  // 32 backslashes and more: count on
+        for (int i = s0 - 1; i >= 0 && ((bmB[i >> 5] >> (i & 31)) & 1u); --i) ++run;
+    }
     return (run & 1) != 0;
+}
+FG_DEV void gf_skip_spaces(const uint8_t* T, int& p, int b, bool act) {
+    for (;;) {
+        const bool m = act && p < b && T[p] == ' ';
+        if (!fg_any(m)) break;
+        if (m) ++p;
+    }
 }
 
 constexpr uint32_t kGfNumber = 0xFFu;  // meta of a member whose number token still has to go through json_number
 
-// One member [a, b) of a regular-looking line (any thread): validates it the way serde_json does and produces the member
-// as the exact parser would (name span absolute, value, tag | flags | key class << 5).  A number is only located: its
-// token span is left in `val` with meta = kGfNumber (gf_member_number finishes it).  false: the line is not regular.
-FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB, int a, int b, int line_off, int ls, int2& name,
+// One member [a, b) of a regular-looking line: validates it the way serde_json does and produces the member as the exact
+// parser would (name span absolute, value, tag | flags | key class << 5).  A number is only located: its token span is
+// left in `val` with meta = kGfNumber (gf_member_number finishes it).  false: the line is not regular.
+FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB, int a, int b, int line_off, int ls, bool act, int2& name,
                       unsigned long long& val, uint32_t& meta) {
-    while (a < b && T[a] == ' ') ++a;
-    while (b > a && T[b - 1] == ' ') --b;
-    if (b - a < 4 || T[a] != '"') return false;  // KeyMustBeAString; the shortest member is `"":0`
+    bool ok = act;
+    gf_skip_spaces(T, a, b, ok);
+    for (;;) {
+        const bool m = ok && b > a && T[b - 1] == ' ';
+        if (!fg_any(m)) break;
+        if (m) --b;
+    }
+    ok = ok && b - a >= 4 && T[a] == '"';  // KeyMustBeAString; the shortest member is `"":0`
     // "key": up to the next quote; a backslash in it (escapes in keys) goes to the exact parser
     const int ks = a + 1;
-    const int ke = gf_next_bit(bmQ, ks, b);
-    if (ke < 0 || gf_next_bit(bmB, ks, ke) >= 0) return false;
+    const int ke = gf_next_bit(bmQ, ks, b, ok);
+    ok = ok && ke >= 0;
+    ok = ok && gf_next_bit(bmB, ks, ke, ok) < 0;
     int p = ke + 1;
-    while (p < b && T[p] == ' ') ++p;
-    if (p >= b || T[p] != ':') return false;
+    gf_skip_spaces(T, p, b, ok);
+    ok = ok && p < b && T[p] == ':';
     ++p;
-    while (p < b && T[p] == ' ') ++p;
-    if (p >= b) return false;
+    gf_skip_spaces(T, p, b, ok);
+    ok = ok && p < b;
+    const uint32_t c = ok ? T[p] : 0u;
     name = make_int2(line_off + (ks - ls), ke - ks);
-    const uint32_t kbits = (uint32_t)gf_key_kind(T + ks, ke - ks) << 5;  // bits 5..7: the key class, for phase 2
-    const uint32_t c = T[p];
-    if (c == '"') {
-        // the value string must end exactly at b - 1: its closing quote is the first unescaped one
-        const int vs = p + 1;
-        int h = vs - 1;
+    const uint32_t kbits = ok ? (uint32_t)gf_key_kind(T + ks, ke - ks) << 5 : 0u;  // bits 5..7: the key class, for phase 2
+    const bool is_str = ok && c == '"', is_num = ok && (c == '-' || c - '0' <= 9u), is_lit = ok && !is_str && !is_num;
+    // string: its closing quote — the first unescaped one — must be the last byte of the member
+    const int vs = p + 1;
+    int h = vs - 1;
+    bool looking = is_str;
+    for (;;) {
+        if (!fg_any(looking)) break;
+        const int hh = gf_next_bit(bmQ, h + 1, b, looking);
+        if (looking) {
+            h = hh;
+            if (h < 0 || !gf_escaped(bmB, h)) looking = false;
+        }
+    }
+    const int ve = h;
+    bool str_ok = is_str && h == b - 1;
+    bool has_bs = false;
+    {   // every backslash of the body starts a valid escape (read.rs parse_escape)
+        int pos = vs;
+        bool scanning = str_ok;
         for (;;) {
-            h = gf_next_bit(bmQ, h + 1, b);
-            if (h < 0) return false;
-            if (!gf_escaped(bmB, vs, h)) break;
+            if (!fg_any(scanning)) break;
+            const int x = gf_next_bit(bmB, pos, ve, scanning);
+            if (scanning) {
+                if (x < 0) {
+                    scanning = false;
+                } else {
+                    has_bs = true;
+                    pos = gf_escape_end(T, x, ve);
+                    if (pos < 0) { scanning = false; str_ok = false; }
+                }
+            }
         }
-        if (h != b - 1) return false;  // something behind the string (or a quote inside the member: not one string)
-        const int ve = h;
-        bool has_bs = false;
-        for (int pos = vs;;) {  // every backslash of the body starts a valid escape (read.rs parse_escape)
-            const int x = gf_next_bit(bmB, pos, ve);
-            if (x < 0) break;
-            has_bs = true;
-            pos = gf_escape_end(T, x, ve);
-            if (pos < 0) return false;
-        }
+    }
+    // true / false / null: the whole token
+    bool lit_ok = false;
+    uint32_t lit_tag = JT_NULL;
+    uint64_t lit_bits = 0;
+    if (is_lit) {
+        const unsigned long long t8 = lt_load8(T + p);
+        const int tl = b - p;
+        if (tl == 4 && (uint32_t)t8 == 0x6C6C756Eu) lit_ok = true;                                           // null
+        else if (tl == 4 && (uint32_t)t8 == 0x65757274u) { lit_ok = true; lit_tag = JT_BOOL; lit_bits = 1; }  // true
+        else if (tl == 5 && (t8 & 0x000000FFFFFFFFFFull) == 0x00000065736C6166ull) { lit_ok = true; lit_tag = JT_BOOL; }  // false
+    }
+    if (is_str) {
         val = (unsigned long long)(uint32_t)(line_off + (vs - ls)) | ((unsigned long long)(uint32_t)(ve - vs) << 32);
         meta = JT_STRING | (has_bs ? 0x08u : 0u) | kbits;  // FG_EM_UNESCAPE
-        return true;
+        return str_ok;
     }
-    if (c == '-' || c - '0' <= 9u) {
+    if (is_num) {
         val = (unsigned long long)(uint32_t)p | ((unsigned long long)(uint32_t)b << 32) | ((unsigned long long)kbits << 48);
         meta = kGfNumber;
         return true;
     }
-    Json j;
-    j.p = T;
-    j.len = b;
-    j.i = p + 1;
-    j.mode2 = false;
-    bool ok;
-    uint32_t tag = JT_NULL;
-    uint64_t bits = 0;
-    if (c == 'n') ok = json_lit(j, "ull", 3);
-    else if (c == 't') { ok = json_lit(j, "rue", 3); tag = JT_BOOL; bits = 1; }
-    else if (c == 'f') { ok = json_lit(j, "alse", 4); tag = JT_BOOL; }
-    else ok = false;  // a container as a member value, or ExpectedSomeValue: exact parser
-    if (!ok || j.i != b) return false;
-    val = bits;
-    meta = tag | kbits;
-    return true;
+    val = lit_bits;
+    meta = lit_tag | kbits;
+    return lit_ok;  // a container as a member value, ExpectedSomeValue, ...: exact parser
 }
 // the number token left by gf_member (start | end << 32 | key class bits << 48) -> value and tag
 FG_DEV bool gf_member_number(const uint8_t* T, unsigned long long span, unsigned long long& val, uint32_t& meta) {

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t scan_ws[33];
-    __shared__ uint32_t s_ebase, s_slots, s_slow_base, s_nnum;
+    __shared__ uint32_t s_ebase, s_slots, s_slow_base, s_nnum, s_nlong;
     __shared__ int line_ls[kLines], line_o0[kLines], line_open[kLines];
     __shared__ uint32_t line_slot[kLines];   // first slot | members (later: rows) << 16
     __shared__ uint32_t line_dense[kLines];  // exclusive sum of the rows of the lines before this one
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
             if (lane == 0) anyK[(gb >> 5) + (int)wid] = bal;
         }
         if (tid < 4) bmQ[nword + tid] = bmB[nword + tid] = bmP[nword + tid] = 0;
-        if (tid == 0) s_nnum = 0u;
+        if (tid == 0) s_nnum = s_nlong = 0u;
         __syncthreads();
 
         // ---- (3) one thread per line: the member boundaries, from the bitmap words -----------------------------------------
@@ -151,10 +151,11 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
         uint32_t nm = 0;
         int open = 0;
         uint16_t my_cuts[kMaxLocalMembers];
-        if (walk && !gf_has_ctrl(tile, anyK, ls, le)) {
-            // (a raw control byte anywhere near the line sends it to the exact parser: newline retry / error)
-            const int m = gf_line_members(tile, bmQ, bmB, bmP, ls, le, my_cuts, kMaxLocalMembers, open);
-            regular = m >= 0;
+        if (tid < kLines) {  // warp-uniform: the warps that hold line threads run the line pass in lock step
+            // (a raw control byte anywhere in the line sends it to the exact parser: newline retry / error)
+            const bool cand = walk && !gf_has_ctrl(tile, anyK, ls, le);
+            const int m = gf_line_members(tile, bmQ, bmB, bmP, ls, le, my_cuts, kMaxLocalMembers, open, cand);
+            regular = cand && m >= 0;
             nm = regular ? (uint32_t)m : 0u;
         }
         uint32_t slots_total;
@@ -182,33 +183,52 @@ __global__ void __launch_bounds__(kThreads, kGelfCtasPerSm) parse_gelf_kernel(co
         const uint32_t nslots = s_slots;
 
         // ---- (4) one thread per member; numbers are only listed ----------------------------------------------------------------
-        for (uint32_t s = (uint32_t)tid; s < nslots; s += (uint32_t)kThreads) {
-            const uint32_t l = slot_line[s];
-            const uint32_t k = s - (line_slot[l] & 0xFFFFu);
-            const int a = k == 0u ? line_open[l] + 1 : (int)cuts[s - 1] + 1;
+        for (uint32_t sb = 0; sb < nslots; sb += (uint32_t)kThreads) {  // warp-uniform trip count: gf_member runs in lock step
+            const uint32_t s = sb + (uint32_t)tid;
+            const bool act = s < nslots;
+            uint32_t l = 0;
+            int a = 0, b = 0;
+            if (act) {
+                l = slot_line[s];
+                const uint32_t k = s - (line_slot[l] & 0xFFFFu);
+                a = k == 0u ? line_open[l] + 1 : (int)cuts[s - 1] + 1;
+                b = (int)cuts[s];
+            }
             int2 name = make_int2(0, 0);
             unsigned long long val = 0;
             uint32_t meta = 0;
-            if (gf_member(tile, bmQ, bmB, a, (int)cuts[s], line_o0[l], line_ls[l], name, val, meta)) {
-                st_name[s] = name;
-                st_val[s] = val;
-                st_meta[s] = (uint8_t)meta;
-                if (meta == kGfNumber) numlist[atomicAdd(&s_nnum, 1u)] = (uint16_t)s;
-            } else {
-                line_bad[l] = 1u;
+            const bool good = gf_member(tile, bmQ, bmB, a, b, line_o0[l], line_ls[l], act, name, val, meta);
+            if (act) {
+                if (good) {
+                    st_name[s] = name;
+                    st_val[s] = val;
+                    st_meta[s] = (uint8_t)meta;
+                    if (meta == kGfNumber) {
+                        // short tokens (levels, small integers) from the front of the list, long ones (timestamps, floats)
+                        // from its end: lanes that run json_number side by side then loop about equally long
+                        const bool lng = (int)((val >> 32) & 0xFFFFu) - (int)(val & 0xFFFFu) > 6;
+                        if (lng) numlist[kSlots - 1 - (int)atomicAdd(&s_nlong, 1u)] = (uint16_t)s;
+                        else numlist[atomicAdd(&s_nnum, 1u)] = (uint16_t)s;
+                    }
+                } else {
+                    line_bad[l] = 1u;
+                }
             }
         }
         __syncthreads();
         // ... and go through json_number side by side: every lane of these warps holds a number
-        for (uint32_t q = (uint32_t)tid; q < s_nnum; q += (uint32_t)kThreads) {
-            const uint32_t s = numlist[q];
-            unsigned long long val = 0;
-            uint32_t meta = 0;
-            if (gf_member_number(tile, st_val[s], val, meta)) {
-                st_val[s] = val;
-                st_meta[s] = (uint8_t)meta;
-            } else {
-                line_bad[slot_line[s]] = 1u;
+        {
+            const uint32_t nshort = s_nnum, nall = nshort + s_nlong;
+            for (uint32_t q = (uint32_t)tid; q < nall; q += (uint32_t)kThreads) {
+                const uint32_t s = q < nshort ? numlist[q] : numlist[kSlots - 1 - (int)(q - nshort)];
+                unsigned long long val = 0;
+                uint32_t meta = 0;
+                if (gf_member_number(tile, st_val[s], val, meta)) {
+                    st_val[s] = val;
+                    st_meta[s] = (uint8_t)meta;
+                } else {
+                    line_bad[slot_line[s]] = 1u;
+                }
             }
         }
         __syncthreads();

@@ -22,6 +22,7 @@ namespace fg {
 FG_DEV bool fg_any(bool p) { return p; }
 FG_DEV void fg_syncwarp() {}
 FG_DEV int fg_ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
+FG_DEV int fg_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 FG_DEV uint32_t fg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
     sh &= 31u;
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
@@ -30,6 +31,7 @@ FG_DEV uint32_t fg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 FG_DEV bool fg_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 FG_DEV void fg_syncwarp() { __syncwarp(); }
 FG_DEV int fg_ffs(uint32_t x) { return __ffs((int)x); }
+FG_DEV int fg_clz(uint32_t x) { return __clz((int)x); }
 FG_DEV uint32_t fg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 #endif
 

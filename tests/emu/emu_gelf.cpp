@@ -124,7 +124,7 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                 uint16_t cuts[fg::kMaxLocalMembers];
                 int open = 0, m = -1;
                 if (walk && !fg::gf_has_ctrl(tile.data(), anyK.data(), ls, le))
-                    m = fg::gf_line_members(tile.data(), bmQ.data(), bmB.data(), bmP.data(), ls, le, cuts, fg::kMaxLocalMembers, open);
+                    m = fg::gf_line_members(tile.data(), bmQ.data(), bmB.data(), bmP.data(), ls, le, cuts, fg::kMaxLocalMembers, open, true);
                 bool regular = m >= 0;
                 const uint32_t nb = (walk && regular) ? (uint32_t)m : 0u;
                 if (run + nb > (uint32_t)kSlots) break;  // the round is cut here; the rest is redone
@@ -141,7 +141,7 @@ int emu_gelf_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int
                     unsigned long long val = 0;
                     uint32_t meta = 0;
                     const int a = k == 0 ? open + 1 : (int)cuts[k - 1] + 1;
-                    if (!fg::gf_member(tile.data(), bmQ.data(), bmB.data(), a, (int)cuts[k], o0, ls, name, val, meta) ||
+                    if (!fg::gf_member(tile.data(), bmQ.data(), bmB.data(), a, (int)cuts[k], o0, ls, true, name, val, meta) ||
                         (meta == fg::kGfNumber && !fg::gf_member_number(tile.data(), val, val, meta))) {
                         regular = false;
                         break;
