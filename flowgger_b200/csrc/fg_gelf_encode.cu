@@ -39,42 +39,37 @@ struct Span {
 
 struct CountSink {
     uint32_t n = 0;
-    __device__ __forceinline__ void put(uint32_t) { ++n; }
-    __device__ __forceinline__ void put4(uint32_t) { n += 4u; }
+    __device__ __forceinline__ void push(uint32_t, int k) { n += (uint32_t)k; }
     __device__ __forceinline__ void finish() {}
 };
-// bytes -> aligned 32-bit stores (byte stores only for the unaligned head and the tail of the record)
+// bytes -> aligned 32-bit stores: a 64-bit shift register takes 1 or 4 bytes per push (the same instructions for both, so
+// lanes that push one byte and lanes that push four stay together) and gives up a word whenever it holds four; only the
+// up-to-three bytes in front of the first aligned address and the tail of the record are stored byte-wise
 struct WordSink {
     uint8_t* p;
     unsigned long long acc = 0;  // pending bytes, low byte first
     int nacc = 0;                // 0..3 between calls
-    __device__ __forceinline__ explicit WordSink(uint8_t* at) : p(at) {}
-    __device__ __forceinline__ void put(uint32_t b) {
-        if (((size_t)p & 3u) != 0u && nacc == 0) {  // head: up to three single bytes until the address is aligned
-            *p++ = (uint8_t)b;
-            return;
-        }
-        acc |= (unsigned long long)b << (8 * nacc);
-        if (++nacc == 4) {
-            *reinterpret_cast<uint32_t*>(p) = (uint32_t)acc;
-            p += 4;
-            acc = 0;
-            nacc = 0;
-        }
-    }
-    // four bytes at once (low byte first): one aligned store, whatever is already pending stays in front
-    __device__ __forceinline__ void put4(uint32_t w) {
-        if (((size_t)p & 3u) != 0u && nacc == 0) {  // still in the head: byte by byte (at most once per record)
-            put(w & 0xFFu);
-            put((w >> 8) & 0xFFu);
-            put((w >> 16) & 0xFFu);
-            put(w >> 24);
-            return;
+    int head;                    // bytes still to store singly before p is 4-byte aligned
+    __device__ __forceinline__ explicit WordSink(uint8_t* at) : p(at), head((int)((4u - ((uint32_t)(size_t)at & 3u)) & 3u)) {}
+    // k = 1 or 4 bytes of w, low byte first (unused high bytes of w are 0)
+    __device__ __forceinline__ void push(uint32_t w, int k) {
+        if (head) {  // the first one or two pushes of a record
+            while (head && k) {
+                *p++ = (uint8_t)w;
+                w >>= 8;
+                --head;
+                --k;
+            }
+            if (k == 0) return;
         }
         acc |= (unsigned long long)w << (8 * nacc);
-        *reinterpret_cast<uint32_t*>(p) = (uint32_t)acc;
-        p += 4;
-        acc >>= 32;
+        nacc += k;
+        if (nacc >= 4) {
+            *reinterpret_cast<uint32_t*>(p) = (uint32_t)acc;
+            p += 4;
+            acc >>= 32;
+            nacc -= 4;
+        }
     }
     __device__ __forceinline__ void finish() {
         for (int k = 0; k < nacc; ++k) p[k] = (uint8_t)(acc >> (8 * k));
@@ -428,29 +423,27 @@ __device__ __forceinline__ void run_segments(const SegList& L, bool live, Sink& 
     }
     while (__any_sync(0xFFFFFFFFu, more)) {
         if (more) {
-            bool four = false;
-            if (!pending && k + 4 <= len) {
-                const uint32_t w = (uint32_t)p[k] | ((uint32_t)p[k + 1] << 8) | ((uint32_t)p[k + 2] << 16) | ((uint32_t)p[k + 3] << 24);
-                if (!esc || json_escape_flags4(w) == 0u) {
-                    s.put4(w);
-                    k += 4;
-                    four = true;
-                }
-            }
-            if (!four) {
-                uint32_t out;
-                if (pending) {
-                    out = pending;
-                    pending = 0;
-                } else {
-                    out = p[k++];
-                    if (esc) {
-                        const uint32_t e = json_escape_of(out);
-                        if (e) { pending = e; out = '\\'; }
+            uint32_t w;
+            int n = 1;
+            if (pending) {
+                w = pending;
+                pending = 0;
+            } else {
+                w = p[k];
+                if (k + 4 <= len) {
+                    const uint32_t w4 = w | ((uint32_t)p[k + 1] << 8) | ((uint32_t)p[k + 2] << 16) | ((uint32_t)p[k + 3] << 24);
+                    if (!esc || json_escape_flags4(w4) == 0u) {
+                        w = w4;
+                        n = 4;
                     }
                 }
-                s.put(out);
+                k += n;
+                if (esc && n == 1) {
+                    const uint32_t e = json_escape_of(w);
+                    if (e) { pending = e; w = '\\'; }
+                }
             }
+            s.push(w, n);
             if (k >= len && !pending) {  // next segment (none is empty)
                 ++si;
                 if (si < L.n) {

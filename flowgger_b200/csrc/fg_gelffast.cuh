@@ -253,7 +253,8 @@ FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB
     const int ks = a + 1;
     const int ke = gf_next_bit(bmQ, ks, b, ok);
     ok = ok && ke >= 0;
-    ok = ok && gf_next_bit(bmB, ks, ke, ok) < 0;
+    const int kbs = gf_next_bit(bmB, ks, ke, ok);  // (every lane makes every call: the loops inside vote)
+    ok = ok && kbs < 0;
     int p = ke + 1;
     gf_skip_spaces(T, p, b, ok);
     ok = ok && p < b && T[p] == ':';
