@@ -249,12 +249,16 @@ FG_DEV bool gf_member(const uint8_t* T, const uint32_t* bmQ, const uint32_t* bmB
         if (m) --b;
     }
     ok = ok && b - a >= 4 && T[a] == '"';  // KeyMustBeAString; the shortest member is `"":0`
-    // "key": up to the next quote; a backslash in it (escapes in keys) goes to the exact parser
+    // "key": up to the next quote, within one 32-bit window of the bitmaps (no loop); a longer key, or a backslash in it
+    // (escapes in keys), goes to the exact parser
     const int ks = a + 1;
-    const int ke = gf_next_bit(bmQ, ks, b, ok);
+    int ke = -1;
+    if (ok) {
+        const uint32_t wq = r5_window(bmQ, ks);
+        const int d = fg_ffs(wq) - 1;  // distance of the closing quote
+        if (wq != 0u && ks + d < b && (r5_window(bmB, ks) & ((1u << d) - 1u)) == 0u) ke = ks + d;
+    }
     ok = ok && ke >= 0;
-    const int kbs = gf_next_bit(bmB, ks, ke, ok);  // (every lane makes every call: the loops inside vote)
-    ok = ok && kbs < 0;
     int p = ke + 1;
     gf_skip_spaces(T, p, b, ok);
     ok = ok && p < b && T[p] == ':';
