@@ -403,7 +403,7 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
     if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom0, s));
     FG_CUDA(c, fg::launch_parse(fmt, P, s));
     if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom1, s));
-    ++c->launches;
+    c->launches += fmt == FG_FMT_GELF ? 2 : 1;  // GELF: parse_gelf_kernel + post_gelf_kernel
     return FG_OK;
 }
 
