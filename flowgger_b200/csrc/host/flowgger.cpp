@@ -1034,15 +1034,19 @@ int fgh_multi_decode_dump(int fmt, const int* devices, int ndev, int64_t max_byt
         opt.max_batch_bytes = max_bytes;
         opt.max_batch_lines = max_lines;
         MultiGpuBatchDecoder dec((fg_format)fmt, std::vector<int>(devices, devices + ndev), {}, opt);
-        dec.decode_batch(bytes, offsets, n);
+        const auto& shards = dec.decode_batch(bytes, offsets, n);
         std::string all;
         int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
         offs[0] = 0;
         std::vector<std::string> fx;
+        size_t g = 0;
         for (int32_t i = 0; i < n; ++i) {
             fx.clear();
             DecodeResult r = dec.materialize(i, bytes, &fx);
-            dump_result(r, false, fx, all);
+            while (g + 1 < shards.size() && i >= shards[g].line0 + shards[g].n) ++g;  // the shard that holds line i
+            // GELF without a timestamp: the reference stamps the record with the wall clock (gelf_decoder.rs:109)
+            const bool now = r.ok() && (FG_META_FLAGS(row_meta(shards[g].out, i - shards[g].line0)) & FG_FLAG_TS_MISSING);
+            dump_result(r, now, fx, all);
             offs[i + 1] = (int64_t)all.size();
         }
         uint8_t* buf = (uint8_t*)malloc(all.size() ? all.size() : 1);
