@@ -230,7 +230,7 @@ def run_mixed(args) -> None:
         fmt = FORMATS[fmt_name]
         data, offs = fb.generate(fmt, SEEDS[fmt_name], n, first_index=first, mean_len=GEN_MEAN[fmt_name], bad_frac=0.005, nthreads=nthreads)
         nb = int(offs[-1])
-        dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nb + (1 << 20), max_batch_lines=n, chunk_lines=1 << 18)
+        dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nb + (1 << 20), max_batch_lines=n, chunk_lines=1 << 19)
         hb = dec.host_alloc(nb)
         ho = dec.host_alloc(offs.nbytes, dtype=np.int32)
         hb[:] = data
@@ -398,7 +398,7 @@ def main() -> None:
     b_read = nbytes + 4 * (n + 1)  # algorithmic bytes per launch: every input byte + offset read once
 
     dec = fb.BatchDecoder(fmt, device=local, max_batch_bytes=nbytes + (1 << 20), max_batch_lines=n,
-                          chunk_lines=env_int("FG_CHUNK_LINES", 1 << 18), **ltsv_kwargs(fmt_name, args.ltsv_typed))
+                          chunk_lines=env_int("FG_CHUNK_LINES", 1 << 19), **ltsv_kwargs(fmt_name, args.ltsv_typed))
     # pinned host arenas, as a batching splitter would fill them
     h_bytes = dec.host_alloc(nbytes)
     h_offs = dec.host_alloc(offs.nbytes, dtype=np.int32)

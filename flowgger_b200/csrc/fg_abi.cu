@@ -683,7 +683,7 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     if (c->max_bytes > 0x7FFFFFC0ull) c->max_bytes = 0x7FFFFFC0ull;  // int32 offsets
     c->max_lines = cfg->max_batch_lines > 0 ? cfg->max_batch_lines : (2 << 20);
     c->max_lines = (c->max_lines + 63) & ~63;  // keeps every row column 256-byte aligned
-    c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (256 << 10);
+    c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (512 << 10);  // measured: 246 / 258 / 258 M lines/s e2e at 128 Ki / 512 Ki / 1 Mi lines per chunk (profiles/r2_notes.md)
     c->chunk_lines = (c->chunk_lines + 127) / 128 * 128;  // a multiple of every kernel's lines per CTA
 #define FG_CREATE_CUDA(call)                                  \
     do {                                                      \

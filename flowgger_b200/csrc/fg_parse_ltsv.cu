@@ -28,6 +28,7 @@ namespace {
 constexpr int kLines = kLtsvLinesPerCta;
 constexpr int kThreads = kLtsvThreadsPerCta;
 constexpr int kWarps = kThreads / 32;
+static_assert(kThreads >= kLines && kWarps >= 2, "the line phases need one thread per line");
 constexpr int kLtsvCtasPerSm = 4;  // shared memory (tile ~28 KB + slots) allows 4 CTAs: 64 registers keep all of them resident
 constexpr int kStageSlots = kLtsvStageSlots;
 constexpr int kSchemaKeys = 64, kSchemaBlob = 1024, kSuffixBlob = 64;  // larger schemas are read from global memory
@@ -343,13 +344,15 @@ __global__ void __launch_bounds__(kThreads, kLtsvCtasPerSm) parse_ltsv_kernel(co
         // b: parse_ts — warps 2c and 2c + 1 take the lines of class c, so the four attempts of :263-267 run side by side on
         // different warps instead of one after the other on the same lanes
         {
-            const uint32_t c = wid >> 1, idx = ((wid & 1u) << 5) + lane;
-            if (c < 4u && idx < L.tcount[c]) {
-                const uint32_t l = L.tlist[c][idx];
-                double ts;
-                const bool ok = lt_time_value(tile, L.t_a[l], L.t_b[l], ts);
-                L.ts[l] = ts;
-                L.ts_ok[l] = ok ? 1u : 0u;
+            const uint32_t idx = ((wid & 1u) << 5) + lane;
+            for (uint32_t c = wid >> 1; c < 4u; c += (uint32_t)kWarps >> 1) {  // 8 warps: one pair per class
+                if (idx < L.tcount[c]) {
+                    const uint32_t l = L.tlist[c][idx];
+                    double ts;
+                    const bool ok = lt_time_value(tile, L.t_a[l], L.t_b[l], ts);
+                    L.ts[l] = ts;
+                    L.ts_ok[l] = ok ? 1u : 0u;
+                }
             }
         }
         __syncthreads();
