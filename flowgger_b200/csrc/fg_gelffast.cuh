@@ -356,6 +356,7 @@ FG_DEV void gf_finish(bytes_t p, int line_off, const Members& M, LineResult& r, 
     const uint32_t m = M.m;
     unsigned long long pre[kMaxLocalMembers];
     uint8_t ord[kMaxLocalMembers];
+    for (uint32_t a = 0; a < m; ++a) pre[a] = gf_key_prefix(p + (M.name[a].x - line_off), M.name[a].y);
     auto cmp = [&](uint32_t x, uint32_t y) {  // key x vs key y
         if (pre[x] != pre[y]) return pre[x] < pre[y] ? -1 : 1;
         const int2 a = M.name[x], b = M.name[y];
@@ -363,7 +364,6 @@ FG_DEV void gf_finish(bytes_t p, int line_off, const Members& M, LineResult& r, 
         return raw_key_cmp(p, a.x - line_off, a.x - line_off + a.y, b.x - line_off, b.x - line_off + b.y);
     };
     for (uint32_t a = 0; a < m; ++a) {
-        pre[a] = gf_key_prefix(p + (M.name[a].x - line_off), M.name[a].y);
         int b = (int)a - 1;
         while (b >= 0 && cmp(ord[b], a) > 0) {
             ord[b + 1] = ord[b];
