@@ -27,7 +27,7 @@
 // Structured-data rows are staged as 8-byte packed entries (u16 positions relative to the line start) in the line's OWN
 // already-consumed bytes of the tile: slot k may be written once the cursor has passed its last byte.
 //
-// The unescape of SD values (:105-125) is done by unescape5424_kernel (fg_parse5424.cu) into the batch's arena; this
+// The unescape of SD values (:105-125) is done by post5424_kernel (fg_parse5424.cu: unescape_lines) into the batch's arena; this
 // walker only marks the pairs whose value holds a backslash.
 #pragma once
 #include "fg_common.cuh"
@@ -65,7 +65,7 @@ FG_DEV uint32_t r5_window(const uint32_t* bm, int t) {
 //   10 header: sd_id start | sd_id end << 16 | #pairs << 32
 //   00 pair  : name_start | name_end << 16 | value_end << 32 | flags << 48   (value starts at name_end + 2)
 //              flag bit 48 (kE8Esc) = the value holds a backslash; such rows only exist between parse5424_kernel and
-//              unescape5424_kernel, which rewrites them as
+//              post5424_kernel (unescape_lines), which rewrites them as
 //   01 arena pair: name_start | name_end << 16 | (arena offset / 2) << 32; the arena record is [u16 length][bytes],
 //              2-byte aligned: the value with unescape_sd_value (:105-125) already applied
 constexpr unsigned long long kE8Esc = 1ull << 48;

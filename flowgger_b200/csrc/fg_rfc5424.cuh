@@ -1,7 +1,7 @@
 // fg_rfc5424.cuh — one RFC5424 line -> Record fields, on device: the WIDE path (round-1 scanner).
 //
 // Since round 2 the hot path is fg_r5fast.cuh (structural bitmap + bit-walk over the shared-memory tile).  This file
-// keeps the self-contained SWAR scanner that reads a line straight from global memory; wide5424_kernel
+// keeps the self-contained SWAR scanner that reads a line straight from global memory; post5424_kernel (wide_lines)
 // (fg_parse5424.cu) runs it for the rare lines the fast path hands over: lines of 64 KiB or more (the compact rows
 // hold u16 positions), lines longer than the staging tile, and lines whose side-table rows do not fit behind the
 // cursor.  The block-scan primitives at the top are shared with the LTSV / GELF parsers.
@@ -10,7 +10,7 @@
 // (/root/reference/src/flowgger/decoder/rfc5424_decoder.rs:18-49) and its helpers
 // BOM::parse :63-71, parse_pri_version :74-92, rfc3339_to_unix :94-99,
 // parse_data :127-161, parse_msg :163-172, parse_sd_data :174-242.
-// The table rows carry the raw value span plus FG_EM_UNESCAPE; wide5424_kernel then rewrites
+// The table rows carry the raw value span plus FG_EM_UNESCAPE; post5424_kernel (wide_lines) then rewrites
 // those values (:105-125) into the batch arena.
 //
 // One thread owns one line.  SIMT discipline: the 32 lines of a

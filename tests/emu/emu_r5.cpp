@@ -1,8 +1,8 @@
 // emu_r5.cpp — CPU emulation of the RFC5424 device logic (TEST INFRASTRUCTURE, see cuda_shim.h).
 //
 // Compiles the product's walker sources (fg_r5fast.cuh: stage-1 classification, stage-2 bit-walk, unescape;
-// fg_rfc5424.cuh: the wide-path scanner) with g++ and replays what parse5424_kernel / unescape5424_kernel /
-// wide5424_kernel do with them — CTA rounds over a staging tile, rows staged in the line's own bytes, side-table
+// fg_rfc5424.cuh: the wide-path scanner) with g++ and replays what parse5424_kernel and post5424_kernel (unescape_lines,
+// wide_lines) do with them — CTA rounds over a staging tile, rows staged in the line's own bytes, side-table
 // placement, work lists — one lane at a time.  The result has the exact layout of fg_batch_out, so the CPU test-suite
 // can push it through the product's materialiser and compare with the oracle without a GPU.  It is built into
 // tests/emu/libfg_emu.so by tests/emu/build.py and loaded by tests only.
