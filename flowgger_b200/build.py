@@ -89,7 +89,7 @@ def build_gen(force: bool = False) -> Path | None:
 def build_oracle(force: bool = False) -> Path:
     odir = REPO / "oracle"
     target = odir / "liboracle.so"
-    srcs = [odir / "oracle.cpp", odir / "capi.cpp", odir / "encoder.cpp", odir / "oracle.hpp"]
+    srcs = [odir / "oracle.cpp", odir / "capi.cpp", odir / "encoder.cpp", odir / "rfc3164.cpp", odir / "oracle.hpp"]
     if force or _newer(target, srcs):
         _run(["make", "-C", str(odir), "-B" if force else "-s", "liboracle.so"])
     return target

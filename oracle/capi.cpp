@@ -11,11 +11,14 @@
 
 using namespace fgo;
 
-enum { FMT_RFC5424 = 0, FMT_LTSV = 1, FMT_GELF = 2 };
+enum { FMT_RFC5424 = 0, FMT_LTSV = 1, FMT_GELF = 2, FMT_RFC3164 = 3 };
 
+// `cfg` is the configuration object of the format: LtsvConfig for LTSV, Rfc3164Config for RFC3164, unused otherwise
 static Decoded decode_one(int fmt, const LtsvConfig* cfg, std::string_view line) {
     static const LtsvConfig empty;
+    static const Rfc3164Config empty3164;
     switch (fmt) {
+        case FMT_RFC3164: return rfc3164_decode(cfg ? *(const Rfc3164Config*)(const void*)cfg : empty3164, line);
         case FMT_RFC5424: return rfc5424_decode(line);
         case FMT_LTSV: return ltsv_decode(cfg ? *cfg : empty, line);
         default: return gelf_decode(line);
@@ -41,6 +44,21 @@ void fgo_ltsv_config_set_suffix(void* c, int type, const char* suffix) {  // :68
         case 3: cfg->suffix_i64 = suffix; break;
         case 4: cfg->suffix_u64 = suffix; break;
     }
+}
+
+// RFC3164: current year + zone table (oracle.hpp: Rfc3164Config)
+void* fgo_rfc3164_config_new(int year) {
+    auto* c = new Rfc3164Config();
+    c->year = year;
+    return c;
+}
+void fgo_rfc3164_config_free(void* c) { delete (Rfc3164Config*)c; }
+// offs has n_trans + 1 entries
+void fgo_rfc3164_config_add_zone(void* c, const char* name, int n_trans, const int64_t* trans, const int32_t* offs) {
+    TzZone z;
+    z.trans.assign(trans, trans + n_trans);
+    z.offs.assign(offs, offs + n_trans + 1);
+    ((Rfc3164Config*)c)->zones[name] = std::move(z);
 }
 
 void fgo_free(void* p) { free(p); }

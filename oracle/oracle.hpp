@@ -70,7 +70,19 @@ struct LtsvConfig {
     std::optional<std::string> suffix_bool, suffix_f64, suffix_i64, suffix_u64;
 };
 
+// rfc3164_decoder.rs: the two inputs the reference takes from its environment, made explicit so a decode is reproducible:
+// `OffsetDateTime::now_utc().year()` (:175) and the zone database behind time_tz::timezones::get_by_name (:196).
+struct TzZone {
+    std::vector<int64_t> trans;  // UTC seconds of the transitions, ascending
+    std::vector<int32_t> offs;   // trans.size() + 1 UTC offsets in seconds: offs[k] is in force on [trans[k-1], trans[k])
+};
+struct Rfc3164Config {
+    int32_t year = 1970;
+    std::map<std::string, TzZone> zones;
+};
+
 Decoded rfc5424_decode(std::string_view line);                       // rfc5424_decoder.rs:18-49
+Decoded rfc3164_decode(const Rfc3164Config& cfg, std::string_view line);  // rfc3164_decoder.rs:31-48 (oracle/rfc3164.cpp)
 Decoded ltsv_decode(const LtsvConfig& cfg, std::string_view line);   // ltsv_decoder.rs:87-221
 Decoded gelf_decode(std::string_view line);                          // gelf_decoder.rs:34-125
 

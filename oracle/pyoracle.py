@@ -16,7 +16,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     so = HERE / "liboracle.so"
-    srcs = [HERE / "oracle.cpp", HERE / "capi.cpp", HERE / "encoder.cpp", HERE / "oracle.hpp"]
+    srcs = [HERE / "oracle.cpp", HERE / "capi.cpp", HERE / "encoder.cpp", HERE / "rfc3164.cpp", HERE / "oracle.hpp"]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(HERE), "-s", "-B", "liboracle.so"], check=True)
     return so
@@ -35,6 +35,10 @@ def lib() -> C.CDLL:
         L.fgo_ltsv_config_enable_schema.argtypes = [C.c_void_p]
         L.fgo_ltsv_config_set_suffix.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         L.fgo_free.argtypes = [C.c_void_p]
+        L.fgo_rfc3164_config_new.restype = C.c_void_p
+        L.fgo_rfc3164_config_new.argtypes = [C.c_int]
+        L.fgo_rfc3164_config_free.argtypes = [C.c_void_p]
+        L.fgo_rfc3164_config_add_zone.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
         L.fgo_decode_dump.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.fgo_decode_bench.restype = C.c_double
@@ -77,7 +81,36 @@ class LtsvConfig:
             pass
 
 
-def decode_debug(fmt: int, line: bytes | str, cfg: LtsvConfig | None = None) -> str:
+class Rfc3164Config:
+    """The two inputs RFC3164Decoder takes from its environment (rfc3164_decoder.rs:175 current year, :196 zone database).
+    `zones`: name -> (transitions, offsets) as oracle/tzread.py produces them; default = the system's TZif files."""
+
+    _system_zones = None
+
+    def __init__(self, year: int, zones: dict | None = None):
+        L = lib()
+        if zones is None:
+            if Rfc3164Config._system_zones is None:
+                import tzread
+                Rfc3164Config._system_zones = tzread.load_zones()
+            zones = Rfc3164Config._system_zones
+        self.year = year
+        self.zones = zones
+        self.h = C.c_void_p(L.fgo_rfc3164_config_new(year))
+        for name, (trans, offs) in zones.items():
+            t = np.asarray(trans, dtype=np.int64)
+            o = np.asarray(offs, dtype=np.int32)
+            assert len(o) == len(t) + 1
+            L.fgo_rfc3164_config_add_zone(self.h, name.encode(), len(t), C.c_void_p(t.ctypes.data), C.c_void_p(o.ctypes.data))
+
+    def __del__(self):
+        try:
+            lib().fgo_rfc3164_config_free(self.h)
+        except Exception:
+            pass
+
+
+def decode_debug(fmt: int, line: bytes | str, cfg: "LtsvConfig | Rfc3164Config | None" = None) -> str:
     b = line.encode() if isinstance(line, str) else line
     p = lib().fgo_decode_debug(fmt, cfg.h if cfg else None, b, len(b))
     s = C.string_at(p).decode()

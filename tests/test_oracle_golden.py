@@ -224,3 +224,83 @@ def test_f64_writer_roundtrips_and_matches_device_logic(oracle):
             v = rnd.uniform(-1e6, 1e6)
         a, b = oracle.format_f64(v), dev(v)
         assert a == b and float(a) == v, (v, a, b)
+
+
+# ---- RFC3164 ----------------------------------------------------------------------------------
+R3 = 3
+
+
+def _utc_seconds(y, mo, d, h, mi, s):
+    import calendar
+    return float(calendar.timegm((y, mo, d, h, mi, s)))
+
+
+@pytest.mark.parametrize("year", [2026, 2021, 2024])
+def test_g16_g26_rfc3164(oracle, year):  # rfc3164_decoder.rs:218-425, the reference's eleven tests
+    cfg = oracle.Rfc3164Config(year)
+    for name, ref, line, exp in V.RFC3164_GOLDEN:
+        s = oracle.decode_debug(R3, line, cfg)
+        if exp is None:
+            assert s.startswith("Err("), (name, s)
+            continue
+        y, mo, d, h, mi, sec = exp["date"]
+        ts = _utc_seconds(y if y is not None else year, mo, d, h, mi, sec)  # ts_from_date_time / ts_from_partial_date_time
+        fac = "None" if exp["fac"] is None else f"Some({exp['fac']})"
+        sev = "None" if exp["sev"] is None else f"Some({exp['sev']})"
+        assert s.startswith(f'Ok(Record {{ ts: {ts!r}, hostname: "{exp["host"]}", facility: {fac}, severity: {sev}, '
+                            "appname: None, procid: None, msgid: None, "), (name, s)
+        assert s.endswith("sd: None })"), (name, s)
+        data, offs = oracle.pack([line.encode()])
+        buf, _ = oracle.decode_dump(R3, data, offs, cfg)
+        if exp["msg"] is not None:
+            m = exp["msg"].encode()
+            assert b";msg=%d:%s;" % (len(m), m) in buf, (name, buf)
+        full = (exp["full"] if exp["full"] is not None else line).encode()
+        assert b";full=%d:%s;" % (len(full), full) in buf, (name, buf)
+        assert f"ts={f64_hex(ts)};".encode() in buf
+
+
+def test_rfc3164_derived_cases(oracle):
+    cfg = oracle.Rfc3164Config(2026)
+    for line, err in V.RFC3164_CASES:
+        s = oracle.decode_debug(R3, line, cfg)
+        if err is None:
+            assert s.startswith("Ok("), (line, s)
+        else:
+            assert s == f'Err("{err}")', (line, s)
+    # spot values: zone arithmetic and the re-joined message
+    def rec(line):
+        return oracle.decode_debug(R3, line, cfg)
+    assert 'ts: 1596726924.0, hostname: "h"' in rec("2020 Aug 6 11:15:24 America/New_York h m")      # EDT, UTC-4
+    assert 'ts: 1596730524.0, hostname: "h"' in rec("2020 Aug 6 11:15:24 Etc/GMT+5 h m")             # POSIX sign: UTC-5
+    assert 'ts: 1596712524.0, hostname: "utc"' in rec("2020 Aug 6 11:15:24 utc h m")
+    assert 'ts: 1615707000.0' in rec("2021 Mar 14 02:30:00 America/New_York h m")                    # 02:30 EST (UTC-5) = 07:30Z
+    assert 'ts: 1636263000.0' in rec("2021 Nov 7 01:30:00 America/New_York h m")                     # the first 01:30 (EDT) = 05:30Z
+    assert 'ts: 2540282400.0' in rec("2050 Jul 1 12:00:00 Europe/Paris h m")                         # CEST from the footer rule
+    assert 'msg: Some("m n o")' in rec("Aug\t6 11:15:24 h　m  n\r\no ")
+    assert 'msg: Some("a b")' in rec("Aug 6 11:15:24 h a  b")
+    assert 'hostname: "a b"' in rec("a b: 2020 Aug 6 11:15:24: m: n: o ") and 'msg: Some("m: n: o ")' in rec("a b: 2020 Aug 6 11:15:24: m: n: o ")
+    assert 'facility: Some(1), severity: Some(5)' in rec("<<13>Aug 6 11:15:24 h m")
+
+
+def test_tz_tables_match_zoneinfo(oracle):
+    """oracle/tzread.py (TZif reader + POSIX footer expansion + the local-time rule of oracle/rfc3164.cpp) against the
+    standard library's zoneinfo (fold=0) on random local times and around transitions, 1901-2400."""
+    import random
+    from datetime import datetime, timedelta
+    from zoneinfo import ZoneInfo
+    import tzread
+    zones = tzread.load_zones()
+    assert len(zones) > 300 and "UTC" in zones and "America/Sao_Paulo" in zones
+    rnd = random.Random(3)
+    lo, hi = -2208988800 + 86400 * 400, 13569465600
+    for name in rnd.sample(sorted(zones), 60) + ["America/New_York", "Europe/Dublin", "Australia/Lord_Howe", "Africa/Casablanca"]:
+        zi, z = ZoneInfo(name), zones[name]
+        probes = [rnd.randrange(lo, hi) for _ in range(60)]
+        tr, of = z
+        for k in rnd.sample(range(len(tr)), min(len(tr), 12)):
+            if lo < tr[k] < hi:
+                probes += [tr[k] + o + d for o in (of[k], of[k + 1]) for d in (-3601, -1, 0, 1, 1800, 3599, 3601)]
+        for local in probes:
+            want = (datetime(1970, 1, 1) + timedelta(seconds=local)).replace(tzinfo=zi).utcoffset().total_seconds()
+            assert tzread.offset_at_local(z, local) == want, (name, local)

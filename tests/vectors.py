@@ -231,3 +231,120 @@ GELF_CASES = [
     ('{"host":"h","timestamp":0,"a":' + "[" * 126 + "]" * 126 + "}", "Invalid value type in structured data"),
     ('{"host":"h","timestamp":0,"a":' + "[" * 127 + "]" * 127 + "}", "Invalid GELF input, unable to parse as a JSON object"),
 ]
+
+# ---- RFC3164 (decoder/rfc3164_decoder.rs) -------------------------------------------------------------------------
+# G16-G26: the reference's own eleven tests.  `partial` = the expected timestamp is built from the CURRENT year
+# (ts_from_partial_date_time, utils/test_utils.rs:8-18); the tests below run the decoders with an explicit year instead.
+_R3_TAIL = r'''testhostname appname 69 42 [origin@123 software="te\st sc\"ript" swVersion="0.0.1"] test message'''
+_R3_MSG = r'''appname 69 42 [origin@123 software="te\st sc\"ript" swVersion="0.0.1"] test message'''
+# (name, ref lines, line, expectation) ; expectation None = Err; else dict(fac, sev, date=(y|None, mon, d, h, m, s), host, msg|None, full|None)
+RFC3164_GOLDEN = [
+    ("G16", "rfc3164_decoder.rs:223-241", "Aug  6 11:15:24 " + _R3_TAIL,
+     dict(fac=None, sev=None, date=(None, 8, 6, 11, 15, 24), host="testhostname", msg=_R3_MSG, full=None)),
+    ("G17", "rfc3164_decoder.rs:243-262", "<13>Aug  6 11:15:24 " + _R3_TAIL,
+     dict(fac=1, sev=5, date=(None, 8, 6, 11, 15, 24), host="testhostname", msg=_R3_MSG, full=None)),
+    ("G18", "rfc3164_decoder.rs:264-283", "<13>2020 Aug  6 11:15:24 " + _R3_TAIL,
+     dict(fac=1, sev=5, date=(2020, 8, 6, 11, 15, 24), host="testhostname", msg=_R3_MSG, full=None)),
+    ("G19", "rfc3164_decoder.rs:285-304", "<13>2020 Aug 6 05:15:24 America/Sao_Paulo " + _R3_TAIL,
+     dict(fac=1, sev=5, date=(2020, 8, 6, 8, 15, 24), host="testhostname", msg=_R3_MSG, full=None)),
+    ("G20", "rfc3164_decoder.rs:306-325", "Aug  6 11:15:24 UTC " + _R3_TAIL,
+     dict(fac=None, sev=None, date=(None, 8, 6, 11, 15, 24), host="testhostname", msg=_R3_MSG, full=None)),
+    ("G21", "rfc3164_decoder.rs:327-335", "test message", None),
+    ("G22", "rfc3164_decoder.rs:337-345", "Aug  36 11:15:24 " + _R3_TAIL, None),
+    ("G23", "rfc3164_decoder.rs:347-369", "testhostname: 2020 Aug  6 11:15:24 UTC: appname 69 42 some test message",
+     dict(fac=None, sev=None, date=(2020, 8, 6, 11, 15, 24), host="testhostname", msg="appname 69 42 some test message", full=None)),
+    ("G24", "rfc3164_decoder.rs:371-390", "testhostname: 2019 Mar 27 12:09:39: appname: a test message",
+     dict(fac=None, sev=None, date=(2019, 3, 27, 12, 9, 39), host="testhostname", msg="appname: a test message", full=None)),
+    ("G25", "rfc3164_decoder.rs:392-411", "<13>testhostname: 2019 Mar 27 12:09:39 UTC: appname: test message",
+     dict(fac=1, sev=5, date=(2019, 3, 27, 12, 9, 39), host="testhostname", msg="appname: test message", full=None)),
+    ("G26", "rfc3164_decoder.rs:413-425", "<13>testhostname: 2019 Mar 27 12:09:39 UTC: appname: test message \n",
+     dict(fac=1, sev=5, date=(2019, 3, 27, 12, 9, 39), host="testhostname", msg=None,
+          full="<13>testhostname: 2019 Mar 27 12:09:39 UTC: appname: test message")),
+]
+
+R3_E_PRI_MALFORMED = "Malformed RFC3164 event: Invalid priority"            # :131
+R3_E_PRI = "Invalid priority"                                                # :137
+R3_E_CUSTOM = "Malformed RFC3164 event: Invalid timestamp or hostname"       # :120
+R3_E_TIME = "Invalid time format"                                            # :158
+R3_E_YEAR = "Unable to parse RFC3164 date with year"                         # :178
+R3_E_DATE = "Unable to parse the date in RFC3164 decoder"                    # :211
+R3_E_PANIC = "(the reference panics here: index out of bounds, rfc3164_decoder.rs:64)"
+
+# Derived behaviour vectors (read off rfc3164_decoder.rs; each: line, expected error or None for Ok).  Decoded with year 2026.
+RFC3164_CASES = [
+    ("", R3_E_CUSTOM),
+    ("<", R3_E_PRI_MALFORMED),
+    ("<13", R3_E_PRI_MALFORMED),
+    ("<>Aug 6 11:15:24 h m", R3_E_PRI),
+    ("<<13>Aug 6 11:15:24 h m", None),                 # trim_start_matches('<') drops every '<'
+    ("<+13>Aug 6 11:15:24 h m", None),                 # u8::from_str accepts a '+'
+    ("<013>Aug 6 11:15:24 h m", None),
+    ("<256>Aug 6 11:15:24 h m", R3_E_PRI),
+    ("<-1>Aug 6 11:15:24 h m", R3_E_PRI),
+    ("<1 3>Aug 6 11:15:24 h m", R3_E_PRI),
+    ("<13>", R3_E_CUSTOM),
+    (" <13>Aug 6 11:15:24 h m", R3_E_CUSTOM),          # no '<' at byte 0: "<13>Aug" is the month token
+    ("Aug 6 11:15:24 h", None),                        # 4 tokens, message = ""
+    ("Aug 6 11:15:24", R3_E_CUSTOM),                   # 3 tokens only
+    ("Aug 6 11:15:24 UTC", R3_E_PANIC),                # the zone eats the 4th token: `_log_tokens[0]` on an empty Vec
+    ("2020 Aug 6 11:15:24 UTC", R3_E_PANIC),
+    ("2020 Aug 6 11:15:24", R3_E_PANIC),               # the with-year form consumes all four tokens
+    ("2020 Aug 6 11:15:24 h", None),
+    ("2020 Aug 6 11:15:24 h m", None),
+    ("Aug 6 11:15:24 UTC h", None),
+    ("Aug 6 11:15:24 utc h m", None),                  # get_by_name is exact: "utc" is the hostname
+    ("Aug 6 11:15:24 Europe/Paris h m", None),
+    ("Aug 6 11:15:24 Europe/paris h m", None),
+    ("Aug 06 11:15:24 h m", None),                     # [day padding:none] still takes two digits
+    ("Aug 0 11:15:24 h m", R3_E_CUSTOM),
+    ("Aug 006 11:15:24 h m", R3_E_CUSTOM),
+    ("Aug 31 11:15:24 h m", None),
+    ("Sep 31 11:15:24 h m", R3_E_CUSTOM),
+    ("Feb 29 11:15:24 h m", R3_E_CUSTOM),              # 2026 is not a leap year
+    ("2024 Feb 29 11:15:24 h m", None),
+    ("aug 6 11:15:24 h m", R3_E_CUSTOM),               # month names are case-sensitive
+    ("AUG 6 11:15:24 h m", R3_E_CUSTOM),
+    ("August 6 11:15:24 h m", R3_E_CUSTOM),
+    ("Aug 6 24:00:00 h m", R3_E_CUSTOM),
+    ("Aug 6 23:59:60 h m", R3_E_CUSTOM),
+    ("Aug 6 23:59:59 h m", None),
+    ("Aug 6 1:15:24 h m", R3_E_CUSTOM),                # [hour] is exactly two digits
+    ("Aug 6 11:15:24.5 h m", R3_E_CUSTOM),
+    ("Aug 6 11:15 h m", R3_E_CUSTOM),
+    ("+2020 Aug 6 11:15:24 h m", None),                # [year] sign:automatic
+    ("-2020 Aug 6 11:15:24 h m", None),
+    ("-0000 Feb 29 11:15:24 h m", None),
+    ("02020 Aug 6 11:15:24 h m", R3_E_CUSTOM),
+    ("202 Aug 6 11:15:24 h m", R3_E_CUSTOM),
+    ("9999 Dec 31 23:59:59 h m", None),
+    ("0000 Jan 1 00:00:00 Asia/Tokyo h m", None),
+    ("Aug\t6 11:15:24 h　m  n\r\no ", None),      # split_whitespace is Unicode White_Space
+    ("Aug 6 11:15:24 h m\u200bn", None),               # U+200B is not White_Space
+    ("Aug 6 11:15:24 h été m", None),
+    ("Aug 6 11:15:24 h a  b", None),                   # the message is re-joined with single spaces
+    ("Aug 6 11:15:24 h a b   ", None),
+    ("   Aug 6 11:15:24 h a b", None),
+    ("h: 2020 Aug 6 11:15:24: m", None),
+    ("h: Aug 6 11:15:24: m", None),                    # the custom form without a year
+    ("h: 2020 Aug 6 11:15:24 UTC junk: m", None),      # tokens after the date / zone are ignored
+    ("h: 2020 Aug 6 11:15:24 junk: m", None),
+    ("h: Aug 6: m", R3_E_TIME),                        # two date tokens
+    ("h: Aug 6 x: m", R3_E_YEAR),                      # three: the without-year parse fails, the with-year one needs four
+    ("h: Aug 6 x y: m", R3_E_DATE),
+    ("h: Aug 6 11:15:24", R3_E_CUSTOM),                # only two ": " pieces
+    ("h: a: m", R3_E_TIME),
+    ("h: : m", R3_E_TIME),
+    (": 2020 Aug 6 11:15:24: ", None),                 # empty hostname, empty message
+    ("a b: 2020 Aug 6 11:15:24: m: n: o ", None),      # the hostname may hold spaces; the message keeps ": " and is not trimmed
+    ("h:  2020 Aug 6 11:15:24: m", None),
+    ("h: 2020 Aug 6 11:15:24:m: n", R3_E_DATE),        # "11:15:24:m" is the time token
+    ("<13>h: 2020 Aug 6 11:15:24 America/New_York: m", None),
+    ("2021 Mar 14 02:30:00 America/New_York h m", None),   # a local time the zone skips (parity unpinned: offset before the jump)
+    ("2021 Nov 7 01:30:00 America/New_York h m", None),    # a local time that occurs twice (parity unpinned: the first)
+    ("2050 Jul 1 12:00:00 Europe/Paris h m", None),        # past the explicit transitions: POSIX footer rule
+    ("1890 Jul 1 12:00:00 Europe/Paris h m", None),        # local mean time
+    ("2020 Aug 6 11:15:24 Etc/GMT+5 h m", None),
+    ("2020 Aug 6 11:15:24 EST5EDT h m", None),
+    ("2020 Aug 6 11:15:24 posixrules h m", None),          # not an IANA name: stays the hostname
+    ("Aug 6 11:15:24 America/Argentina/ComodRivadavia h m", None),
+]
