@@ -8,6 +8,7 @@ fallback: importing works anywhere, but constructing a decoder needs the built l
 from .native import (  # noqa: F401
     FMT_GELF,
     FMT_LTSV,
+    FMT_RFC3164,
     FMT_RFC5424,
     BatchDecoder,
     BatchResult,
@@ -25,9 +26,11 @@ from .native import (  # noqa: F401
     shard_by_bytes,
     splitter_run,
     splitter_run_gelf,
+    tz_count,
+    tz_lookup,
 )
 
 __all__ = [
-    "FMT_RFC5424", "FMT_LTSV", "FMT_GELF", "BatchDecoder", "BatchResult", "NativeLibraryMissing",
+    "FMT_RFC5424", "FMT_LTSV", "FMT_GELF", "FMT_RFC3164", "BatchDecoder", "BatchResult", "NativeLibraryMissing",
     "build_info", "cuda_lib_path", "error_string", "generate", "load_cuda", "load_gen", "load_host",
 ]

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
@@ -20,6 +22,8 @@
 #include "../../include/flowgger_cuda.h"
 #include "fg_kernels.cuh"
 #include "fg_status.h"
+#include "fg_rfc3164.cuh"
+#include "fg_tz.h"
 
 namespace {
 
@@ -70,6 +74,13 @@ struct ErrorTableInit {
         t[FG_EG_SD_TYPE] = "Invalid value type in structured data";               // :97
         t[FG_EG_MISSING_HOST] = "Missing hostname";                               // :110
         t[FG_ES_INVALID_UTF8] = "Invalid UTF-8 input";                            // splitter/line_splitter.rs:23
+        t[FG_E3_PRI_MALFORMED] = "Malformed RFC3164 event: Invalid priority";     // rfc3164_decoder.rs:131
+        t[FG_E3_PRI_INVALID] = "Invalid priority";                                // :137
+        t[FG_E3_CUSTOM] = "Malformed RFC3164 event: Invalid timestamp or hostname";  // :120
+        t[FG_E3_TIME_FORMAT] = "Invalid time format";                             // :158
+        t[FG_E3_WITH_YEAR] = "Unable to parse RFC3164 date with year";            // :178
+        t[FG_E3_DATE] = "Unable to parse the date in RFC3164 decoder";            // :211
+        t[FG_E3_PANIC] = "(the reference panics here: index out of bounds, rfc3164_decoder.rs:64)";
     }
 } g_error_table_init;
 
@@ -154,6 +165,13 @@ struct fg_ctx {
     std::vector<cudaEvent_t> ev_split;
     int32_t* d_cum = nullptr;
     int32_t* h_cum = nullptr;
+    // RFC3164: the year `now_utc().year()` stands for (0: read the clock at every call) and the zone database
+    int r3164_year = 0;
+    int call_year = 1970;  // the year of the call in progress (current_year())
+    std::string tzdir;
+    fg::TzHostTable tz_host;
+    uint8_t* d_tz_blob = nullptr;
+    fg::TzDeviceTable tz_dev{};
     // LTSV config blobs
     uint8_t* d_ltsv_blob = nullptr;
     fg::LtsvDeviceConfig ltsv{};
@@ -258,6 +276,53 @@ int alloc_wide(fg_ctx* c, size_t cap) {
     return FG_OK;
 }
 
+// packed zone table -> one device blob (fg::TzDeviceTable points into it)
+int upload_tz(fg_ctx* c) {
+    const fg::TzHostTable& H = c->tz_host;
+    dfree(c->d_tz_blob);
+    size_t o = 0;
+    auto place = [&](size_t bytes) {
+        const size_t at = o;
+        o += (bytes + 15) & ~(size_t)15;
+        return at;
+    };
+    const size_t o_hash = place(H.hash.size() * 8), o_key = place(H.key.size() * 8), o_zone = place(H.zone.size() * 4),
+                 o_noff = place(H.name_off.size() * 4), o_first = place(H.first.size() * 4), o_off = place(H.off.size() * 4),
+                 o_names = place(H.names.size());
+    std::vector<uint8_t> blob(o + 16, 0);
+    auto put = [&](size_t at, const void* src, size_t bytes) {
+        if (bytes) memcpy(blob.data() + at, src, bytes);
+    };
+    put(o_hash, H.hash.data(), H.hash.size() * 8);
+    put(o_key, H.key.data(), H.key.size() * 8);
+    put(o_zone, H.zone.data(), H.zone.size() * 4);
+    put(o_noff, H.name_off.data(), H.name_off.size() * 4);
+    put(o_first, H.first.data(), H.first.size() * 4);
+    put(o_off, H.off.data(), H.off.size() * 4);
+    put(o_names, H.names.data(), H.names.size());
+    FG_CUDA(c, cudaMalloc(&c->d_tz_blob, blob.size()));
+    FG_CUDA(c, cudaMemcpy(c->d_tz_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    fg::TzDeviceTable& T = c->tz_dev;
+    T = H.view();
+    T.hash = (const unsigned long long*)(c->d_tz_blob + o_hash);
+    T.key = (const long long*)(c->d_tz_blob + o_key);
+    T.zone = (const int32_t*)(c->d_tz_blob + o_zone);
+    T.name_off = (const int32_t*)(c->d_tz_blob + o_noff);
+    T.first = (const int32_t*)(c->d_tz_blob + o_first);
+    T.off = (const int32_t*)(c->d_tz_blob + o_off);
+    T.names = c->d_tz_blob + o_names;
+    return FG_OK;
+}
+
+// `OffsetDateTime::now_utc().year()` (rfc3164_decoder.rs:175): the configured year, else the clock's, once per call
+int current_year(const fg_ctx* c) {
+    if (c->r3164_year != 0) return c->r3164_year;
+    const time_t now = time(nullptr);
+    struct tm g;
+    gmtime_r(&now, &g);
+    return g.tm_year + 1900;
+}
+
 // Format-specific buffers are allocated on first use of the format.
 int ensure_format(fg_ctx* c, int fmt) {
     if (fmt == FG_FMT_RFC5424) {
@@ -281,6 +346,19 @@ int ensure_format(fg_ctx* c, int fmt) {
         const size_t rows_bytes = col_off(c, C_COUNT);
         FG_CUDA(c, cudaMalloc(&c->d_rows, rows_bytes));
         FG_CUDA(c, cudaHostAlloc(&c->h_rows, rows_bytes, cudaHostAllocDefault));
+    }
+    if (fmt == FG_FMT_RFC3164) {  // no side table; re-joined messages go to the arena; zone names need the database
+        if (!c->arena_cap)
+            if (int rc = alloc_arena(c, std::max<size_t>(c->max_bytes / 32, 64 << 10))) return rc;
+        if (!c->entry_cap)
+            if (int rc = alloc_entries(c, 256)) return rc;
+        if (!c->tz_host.loaded) {
+            std::string err;
+            if (!fg::tz_load_dir(c->tzdir.empty() ? nullptr : c->tzdir.c_str(), c->tz_host, err)) return fail(c, FG_E_ARG, err.c_str());
+        }
+        if (!c->d_tz_blob)
+            if (int rc = upload_tz(c)) return rc;
+        return FG_OK;
     }
     if (fmt == FG_FMT_GELF && !c->d_wide_list) FG_CUDA(c, cudaMalloc(&c->d_wide_list, (size_t)c->max_lines * 4));  // slow list
     const size_t want = std::max<size_t>(c->max_bytes / 24, 4096);
@@ -310,7 +388,7 @@ int pick_tile(const fg_ctx* c, size_t total_bytes, int n, int fmt) {
     long t = (long)(mean * lines * (FG_TILE_SLACK_PCT / 100.0)) + gran;
     t = (t + gran - 1) / gran * gran;
     t = std::max(t, 8L * 1024);
-    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : (fmt == FG_FMT_LTSV ? fg::kLtsvMaxTile : fg::kGelfMaxTile)));
+    t = std::min(t, (long)(fmt == FG_FMT_RFC5424 ? c->max_tile5 : (fmt == FG_FMT_LTSV ? fg::kLtsvMaxTile : (fmt == FG_FMT_GELF ? fg::kGelfMaxTile : fg::kR3164MaxTile))));
     return (int)t;
 }
 
@@ -319,6 +397,7 @@ bool tables_overflow(const fg_ctx* c, int fmt, const uint32_t* t) {
     if (fmt == FG_FMT_RFC5424)
         return t[fg::K5_ENTRIES] > c->e8_cap || t[fg::K5_ARENA] > c->arena_cap || t[fg::K5_WIDE_ROWS] > c->wide_cap ||
                t[fg::K5_WIDE_ENTRIES] > c->entry_cap;
+    if (fmt == FG_FMT_RFC3164) return t[fg::K5_ARENA] > c->arena_cap;
     return t[fg::K5_ENTRIES] > c->entry_cap;
 }
 int regrow_tables(fg_ctx* c, int fmt, const uint32_t* t) {
@@ -334,6 +413,7 @@ int regrow_tables(fg_ctx* c, int fmt, const uint32_t* t) {
             if (int rc = alloc_entries(c, grown(t[fg::K5_WIDE_ENTRIES]))) return rc;
         return FG_OK;
     }
+    if (fmt == FG_FMT_RFC3164) return alloc_arena(c, grown(t[fg::K5_ARENA]));
     return alloc_entries(c, grown(t[fg::K5_ENTRIES]));
 }
 
@@ -400,6 +480,11 @@ int launch_lines(fg_ctx* c, int fmt, int line0, int n, int tile, const uint8_t* 
     P.slow_count = c->d_k + fg::K5_WIDE_LIST;
     if (fmt == FG_FMT_GELF) FG_CUDA(c, cudaMemsetAsync(c->d_k + fg::K5_WIDE_LIST, 0, 4, s));  // the work list is per launch
     P.ltsv = c->ltsv;
+    P.r3164.year = c->call_year;
+    P.r3164.tz = c->tz_dev;
+    P.r3164.arena = c->d_arena;
+    P.r3164.arena_cap = (uint32_t)std::min<size_t>(c->arena_cap, 0xFFFFFFFFu);
+    P.r3164.arena_counter = c->d_k + fg::K5_ARENA;
     if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom0, s));
     FG_CUDA(c, fg::launch_parse(fmt, P, s));
     if (time_dominant) FG_CUDA(c, cudaEventRecord(c->ev_dom1, s));
@@ -427,6 +512,11 @@ void fill_out(fg_ctx* c, int fmt, int n, const uint32_t* tot, fg_batch_out* out)
     }
     uint8_t* r = c->h_rows;
     out->n_entries = (int32_t)tot[fg::K5_ENTRIES];
+    if (fmt == FG_FMT_RFC3164) {
+        out->n_entries = 0;
+        out->arena = c->h_arena;
+        out->arena_bytes = (int64_t)tot[fg::K5_ARENA];
+    }
     out->ts = (const double*)(r + col_off(c, C_TS));
     out->meta = (const uint32_t*)(r + col_off(c, C_META));
     out->hostname = (const fg_span*)(r + col_off(c, C_HOST));
@@ -472,6 +562,12 @@ int copy_entries_range(fg_ctx* c, size_t from, size_t to, cudaStream_t s) {
 
 // side tables: the rows a chunk produced are the contiguous range [prev, cur) of each bump allocator
 int copy_tables_d2h(fg_ctx* c, int fmt, const uint32_t* prev, const uint32_t* cur, cudaStream_t s) {
+    if (fmt == FG_FMT_RFC3164) {
+        if (cur[fg::K5_ARENA] > prev[fg::K5_ARENA])
+            FG_CUDA(c, cudaMemcpyAsync(c->h_arena + prev[fg::K5_ARENA], c->d_arena + prev[fg::K5_ARENA],
+                                       (size_t)(cur[fg::K5_ARENA] - prev[fg::K5_ARENA]), cudaMemcpyDeviceToHost, s));
+        return FG_OK;
+    }
     if (fmt != FG_FMT_RFC5424) return copy_entries_range(c, prev[fg::K5_ENTRIES], cur[fg::K5_ENTRIES], s);
     if (cur[fg::K5_ENTRIES] > prev[fg::K5_ENTRIES])
         FG_CUDA(c, cudaMemcpyAsync(c->h_e8 + prev[fg::K5_ENTRIES], c->d_e8 + prev[fg::K5_ENTRIES],
@@ -685,6 +781,8 @@ int fg_create(const fg_config* cfg, fg_ctx** out) {
     c->max_lines = (c->max_lines + 63) & ~63;  // keeps every row column 256-byte aligned
     c->chunk_lines = cfg->chunk_lines > 0 ? cfg->chunk_lines : (512 << 10);  // measured: 246 / 258 / 258 M lines/s e2e at 128 Ki / 512 Ki / 1 Mi lines per chunk (profiles/r2_notes.md)
     c->chunk_lines = (c->chunk_lines + 127) / 128 * 128;  // a multiple of every kernel's lines per CTA
+    c->r3164_year = cfg->rfc3164_year;
+    if (cfg->tzdir) c->tzdir = cfg->tzdir;
 #define FG_CREATE_CUDA(call)                                  \
     do {                                                      \
         cudaError_t _e = (call);                              \
@@ -783,6 +881,7 @@ void fg_destroy(fg_ctx* c) {
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
     dfree(c->d_tmp_name); dfree(c->d_tmp_val); dfree(c->d_tmp_meta);
     dfree(c->d_ltsv_blob);
+    dfree(c->d_tz_blob);
     hfree(c->h_rows); hfree(c->h_counts);
     for (int b = 0; b < 2; ++b) {
         hfree(c->h_bounce[b]);
@@ -818,9 +917,10 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
                     fg_batch_out* out) {
     if (!c || !out) return FG_E_ARG;
     if (int rc = check_batch(c, bytes, offsets, n)) return rc;
-    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if ((int)fmt < 0 || (int)fmt > 3) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_format(c, (int)fmt)) return rc;
+    c->call_year = current_year(c);
     memset(out, 0, sizeof *out);
     const uint32_t zero[kCnt] = {};
     if (n == 0) {
@@ -896,6 +996,73 @@ int fg_decode_batch(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const int32_
     return fail(c, FG_E_CAPACITY, "side table overflow after regrow");
 }
 
+int fg_set_rfc3164_year(fg_ctx* c, int32_t year) {
+    if (!c) return FG_E_ARG;
+    c->r3164_year = year;
+    return FG_OK;
+}
+
+int fg_set_tz_table(fg_ctx* c, int32_t n_zones, const char* const* names, const int32_t* first, const int64_t* span_start_utc,
+                    const int32_t* span_offset) {
+    if (!c || n_zones < 0 || (n_zones > 0 && (!names || !first || !span_start_utc || !span_offset))) return FG_E_ARG;
+    std::vector<std::string> nm;
+    std::vector<fg::TzZoneSpans> zones;
+    for (int32_t z = 0; z < n_zones; ++z) {
+        const int32_t a = first[z], b = first[z + 1];
+        if (!names[z] || b <= a) return fail(c, FG_E_ARG, "fg_set_tz_table: every zone needs a name and at least one span");
+        fg::TzZoneSpans sp;
+        for (int32_t j = a; j < b; ++j) {
+            if (j > a) {
+                if (j > a + 1 && span_start_utc[j] <= span_start_utc[j - 1]) return fail(c, FG_E_ARG, "fg_set_tz_table: span starts must ascend");
+                sp.trans.push_back((long long)span_start_utc[j]);
+            }
+            sp.offs.push_back(span_offset[j]);
+        }
+        nm.emplace_back(names[z]);
+        zones.push_back(std::move(sp));
+    }
+    FG_CUDA(c, cudaSetDevice(c->device));
+    FG_CUDA(c, cudaDeviceSynchronize());
+    fg::tz_build(nm, zones, c->tz_host);
+    return upload_tz(c);
+}
+
+// host-side queries of the zone database (no device involved), for callers that want to check what a context will load
+namespace {
+std::mutex g_tz_mu;
+std::string g_tz_dir;
+fg::TzHostTable g_tz_table;
+bool tz_query_table(const char* tzdir) {  // g_tz_mu held
+    const std::string dir = tzdir ? tzdir : "";
+    if (g_tz_table.loaded && dir == g_tz_dir) return true;
+    std::string err;
+    fg::TzHostTable t;
+    if (!fg::tz_load_dir(tzdir, t, err)) return false;
+    g_tz_table = std::move(t);
+    g_tz_dir = dir;
+    return true;
+}
+}  // namespace
+
+// what get_by_name + assume_timezone answer for `name` at the local second `local`:
+// 1 = found (offset stored), 0 = no such identifier, FG_E_ARG = the database could not be read
+int fg_tz_lookup(const char* tzdir, const char* name, int64_t local, int32_t* offset) {
+    if (!name) return FG_E_ARG;
+    std::lock_guard<std::mutex> guard(g_tz_mu);
+    if (!tz_query_table(tzdir)) return FG_E_ARG;
+    const fg::TzDeviceTable T = g_tz_table.view();
+    const int z = fg::tz_find(T, (const uint8_t*)name, 0, (int)strlen(name));
+    if (z < 0) return 0;
+    if (offset) *offset = fg::tz_offset_local(T, z, (long long)local);
+    return 1;
+}
+// identifiers in the database under `tzdir` (negative: unreadable)
+int32_t fg_tz_count(const char* tzdir) {
+    std::lock_guard<std::mutex> guard(g_tz_mu);
+    if (!tz_query_table(tzdir)) return FG_E_ARG;
+    return (int32_t)g_tz_table.n_names();
+}
+
 int fg_set_gelf_extra(fg_ctx* c, int32_t n, const char* const* keys, const char* const* values) {
     if (!c || n < 0 || (n > 0 && (!keys || !values))) return FG_E_ARG;
     FG_CUDA(c, cudaSetDevice(c->device));
@@ -916,6 +1083,7 @@ int fg_decode_encode_gelf(fg_ctx* c, fg_format fmt, const uint8_t* bytes, const 
     if (fmt != FG_FMT_RFC5424) return fail(c, FG_E_ARG, "the fused encoder takes input.format = rfc5424");
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_format(c, (int)fmt)) return rc;
+    c->call_year = current_year(c);
     const int C = c->chunk_lines;
     const int chunks = n > 0 ? (n + C - 1) / C : 1;
     if (int rc = ensure_encoder(c, chunks)) return rc;
@@ -1031,7 +1199,7 @@ int fg_split_decode(fg_ctx* c, fg_format fmt, const uint8_t* stream, int64_t nby
 
 int fg_split_decode_framed(fg_ctx* c, fg_format fmt, fg_framing framing, const uint8_t* stream, int64_t nbytes, fg_batch_out* out) {
     if (!c || !out) return FG_E_ARG;
-    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if ((int)fmt < 0 || (int)fmt > 3) return fail(c, FG_E_ARG, "unknown format");
     if (framing != FG_FRAME_LINE && framing != FG_FRAME_NUL) return fail(c, FG_E_ARG, "unknown framing");
     const int delim = framing == FG_FRAME_NUL ? 0 : '\n';
     const int strip = framing == FG_FRAME_NUL ? 2 : 1;
@@ -1039,6 +1207,7 @@ int fg_split_decode_framed(fg_ctx* c, fg_format fmt, fg_framing framing, const u
     if ((size_t)nbytes > c->max_bytes) return fail(c, FG_E_CAPACITY, "stream has more bytes than max_batch_bytes");
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_format(c, (int)fmt)) return rc;
+    c->call_year = current_year(c);
     const auto t_begin = std::chrono::steady_clock::now();
     constexpr long long kChunk = 64ll << 20;  // pipeline granularity in bytes (a multiple of the 8 KB framing segment)
     const int chunks = nbytes > 0 ? (int)((nbytes + kChunk - 1) / kChunk) : 1;
@@ -1189,9 +1358,10 @@ int fg_upload(fg_ctx* c, const uint8_t* bytes, const int32_t* offsets, int32_t n
 
 int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
     if (!c) return FG_E_ARG;
-    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if ((int)fmt < 0 || (int)fmt > 3) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_format(c, (int)fmt)) return rc;
+    c->call_year = current_year(c);
     for (int attempt = 0; attempt < 2; ++attempt) {
         FG_CUDA(c, cudaMemsetAsync(c->d_k, 0, sizeof(uint32_t) * kBadFlag, c->s_comp));
         FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));
@@ -1219,9 +1389,10 @@ int fg_parse_resident(fg_ctx* c, fg_format fmt, float* kernel_ms) {
 // total_ms = CUDA-event time from before the first launch to after the last one.
 int fg_parse_resident_n(fg_ctx* c, fg_format fmt, int32_t k, float* total_ms) {
     if (!c || k < 1) return FG_E_ARG;
-    if ((int)fmt < 0 || (int)fmt > 2) return fail(c, FG_E_ARG, "unknown format");
+    if ((int)fmt < 0 || (int)fmt > 3) return fail(c, FG_E_ARG, "unknown format");
     FG_CUDA(c, cudaSetDevice(c->device));
     if (int rc = ensure_format(c, (int)fmt)) return rc;
+    c->call_year = current_year(c);
     // the side tables must already be large enough (one fg_parse_resident warm-up regrows them): checked after the loop
     const int tile = pick_tile(c, c->res_bytes, c->res_n, (int)fmt);
     FG_CUDA(c, cudaEventRecord(c->ev_a, c->s_comp));

@@ -4,6 +4,7 @@
 //   RFC5424  fg_parse5424.cu   parse5424_kernel + post5424_kernel
 //   LTSV     fg_parse_ltsv.cu  parse_ltsv_kernel
 //   GELF     fg_parse_gelf.cu  parse_gelf_kernel + post_gelf_kernel
+//   RFC3164  fg_parse3164.cu   parse3164_kernel (tile + one thread per line, no bitmap stage)
 // one CTA = 64 consecutive lines whose contiguous byte span is staged in shared memory by ONE TMA bulk copy
 // (cp.async.bulk, SASS UBLKCP); all threads sweep the tile into structural bitmaps; one thread per line walks its tokens over
 // the bitmaps in lock step; side-table rows are staged in shared memory, placed by a CTA scan + one global atomic and
@@ -23,7 +24,9 @@ cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424) {
     if (e != cudaSuccess) return e;
     e = configure_parse_ltsv(kLtsvMaxTile);
     if (e != cudaSuccess) return e;
-    return configure_parse_gelf(kGelfMaxTile);
+    e = configure_parse_gelf(kGelfMaxTile);
+    if (e != cudaSuccess) return e;
+    return configure_parse3164(kR3164MaxTile);
 }
 
 __global__ void __launch_bounds__(256) check_offsets_kernel(const int32_t* __restrict__ offsets, int n, long long max_bytes,
@@ -46,13 +49,14 @@ cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream) {
     switch (fmt) {
         case 1: return launch_parse_ltsv(p, stream);
         case 2: return launch_parse_gelf(p, stream);
+        case 3: return launch_parse3164(p, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 const char* kernel_build_info() {
     return "flowgger_b200 parse kernels: sm_100a, structural bitmaps + bit-walk over TMA-bulk-staged CTA tiles, "
-           "kernels=[parse5424_kernel, post5424_kernel, gelf_size_kernel, gelf_write_kernel, parse_ltsv_kernel, parse_gelf_kernel, post_gelf_kernel]";
+           "kernels=[parse5424_kernel, post5424_kernel, gelf_size_kernel, gelf_write_kernel, parse_ltsv_kernel, parse_gelf_kernel, post_gelf_kernel, parse3164_kernel]";
 }
 
 }  // namespace fg

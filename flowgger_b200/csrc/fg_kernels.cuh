@@ -21,6 +21,29 @@ struct LtsvDeviceConfig {
     uint32_t suffix_present;    // bit t set if a suffix is configured for type t
 };
 
+// RFC3164: zone database behind time_tz::timezones::get_by_name (rfc3164_decoder.rs:196), packed by fg_tz.cu.
+// A zone is a run of spans; span j is in force from LOCAL second key[j] on (key of a zone's first span: INT64_MIN), see
+// fg_rfc3164.cuh: tz_offset_local.
+struct TzDeviceTable {
+    int32_t n_names;            // identifiers (0: no database: no token is a zone name)
+    int32_t min_len, max_len;   // of the identifiers
+    uint32_t first_mask[8];     // bit c: some identifier starts with byte c
+    const unsigned long long* hash;  // [n_names] FNV-1a 64 of the identifier, ascending
+    const int32_t* zone;        // [n_names] zone of the identifier (links share the zone of their target)
+    const int32_t* name_off;    // [n_names + 1] into names, in hash order
+    const uint8_t* names;
+    const int32_t* first;       // [zones + 1] span range of a zone
+    const long long* key;       // [spans]
+    const int32_t* off;         // [spans] UTC offset in seconds
+};
+struct R3164DeviceConfig {
+    int32_t year;               // OffsetDateTime::now_utc().year() (rfc3164_decoder.rs:175), fixed per call
+    TzDeviceTable tz;
+    uint8_t* arena;             // re-joined messages (rfc3164_decoder.rs:67: tokens joined by one space)
+    uint32_t arena_cap;
+    uint32_t* arena_counter;    // bump allocator; keeps counting past arena_cap (the host regrows and redoes the batch)
+};
+
 struct ParseParams {
     const uint8_t* bytes;     // device copy of the caller's byte buffer (base of all spans)
     const int32_t* offsets;   // [n+1] line offsets into bytes
@@ -56,6 +79,7 @@ struct ParseParams {
     uint32_t* slow_list;
     uint32_t* slow_count;
     LtsvDeviceConfig ltsv;
+    R3164DeviceConfig r3164;
 };
 
 // ---- RFC5424 fast path (fg_parse5424.cu) ------------------------------------------------------------------------
@@ -175,7 +199,13 @@ constexpr int kGelfThreadsPerCta = FG_GELF_THREADS;
 constexpr int kGelfCtasPerSm = 3;  // tile (~34 KB at 520 B/line) + bitmap + slots: 3 CTAs = 24 warps per SM
 constexpr int kGelfStageSlots = kGelfLinesPerCta * 16;
 constexpr int kGelfMaxTile = 65024;
-constexpr int lines_per_cta(int fmt) { return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : kGelfLinesPerCta); }
+// RFC3164 (fg_parse3164.cu): 64 lines and 64 threads per CTA, one thread per line over the staged tile
+constexpr int kR3164LinesPerCta = 64;
+constexpr int kR3164CtasPerSm = 16;
+constexpr int kR3164MaxTile = 65024;
+constexpr int lines_per_cta(int fmt) {
+    return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : (fmt == 2 ? kGelfLinesPerCta : kR3164LinesPerCta));
+}
 
 cudaError_t launch_parse(int fmt, const ParseParams& p, cudaStream_t stream);
 // LTSV on the bitmap pipeline (fg_parse_ltsv.cu); launch_parse routes fmt 1 here
@@ -186,6 +216,9 @@ int parse_ltsv_smem_bytes(int tile_bytes, bool typed);
 cudaError_t launch_parse_gelf(const ParseParams& p, cudaStream_t stream);
 cudaError_t configure_parse_gelf(int max_tile_bytes);
 int parse_gelf_smem_bytes(int tile_bytes);
+// RFC3164 (fg_parse3164.cu); launch_parse routes fmt 3 here
+cudaError_t launch_parse3164(const ParseParams& p, cudaStream_t stream);
+cudaError_t configure_parse3164(int max_tile_bytes);
 // offsets[0 .. n] must be non-decreasing and within [0, max_bytes]; otherwise *flag |= 1 (the parse kernels then return at once)
 cudaError_t launch_check_offsets(const int32_t* d_offsets, int n, long long max_bytes, uint32_t* d_flag, cudaStream_t stream);
 cudaError_t configure_kernels(int max_tile_bytes, int max_tile5424);

@@ -53,5 +53,13 @@ enum FgStatus : uint32_t {
     FG_EG_MISSING_HOST = 75,
     // framing (splitter/line_splitter.rs:22-25): not a decoder error; the line is skipped with this stderr text
     FG_ES_INVALID_UTF8 = 76,
-    FG_ST_COUNT = 77
+    // RFC3164 (decoder/rfc3164_decoder.rs); the error of the LAST form tried is the one returned (:40-47)
+    FG_E3_PRI_MALFORMED = 80,  // '<' without '>'
+    FG_E3_PRI_INVALID = 81,
+    FG_E3_CUSTOM = 82,         // fewer than three ": " pieces
+    FG_E3_TIME_FORMAT = 83,    // fewer than three date tokens
+    FG_E3_WITH_YEAR = 84,      // three date tokens that do not parse without a year
+    FG_E3_DATE = 85,
+    FG_E3_PANIC = 86,          // `_log_tokens[0]` on an empty Vec (:64): the reference thread panics
+    FG_ST_COUNT = 87
 };

@@ -392,6 +392,100 @@ void gen_gelf(uint64_t seed, uint64_t idx, double mean_len, double bad_frac, std
     if (bad_kind == 15) { o.resize(line_start); o += "[1,2,3]"; }  // not an object
 }
 
+
+
+// RFC3164 (BSD syslog, decoder/rfc3164_decoder.rs): `[<PRI>][YYYY ]Mon D HH:MM:SS [Zone ]host tag: text` and the custom
+// form `[<PRI>]host: [YYYY ]Mon D HH:MM:SS[ Zone]: text`; mean ~140 B.  Irregular spacing (double spaces, TABs, Unicode
+// White_Space), non-ASCII text and trailing blanks appear at a few per cent each so that the re-join path is exercised.
+void gen_rfc3164(uint64_t seed, uint64_t idx, double mean_len, double bad_frac, std::string& o) {
+    Rng r(seed ^ 0x3164ull, idx);
+    static const char* MON[12] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
+    static const char* ZONES[] = {"UTC", "Europe/Paris", "America/Sao_Paulo", "America/New_York", "Asia/Tokyo", "Etc/GMT+5",
+                                  "Australia/Lord_Howe", "GMT", "Africa/Casablanca", "America/Argentina/Buenos_Aires", "EST5EDT",
+                                  "Europe/Dublin", "Pacific/Chatham", "Asia/Kolkata"};
+    const bool bad = r.chance(bad_frac);
+    const int bad_kind = bad ? (int)r.below(12) : -1;
+    const bool custom = r.chance(0.08);
+    const bool with_year = custom ? r.chance(0.8) : r.chance(0.12);
+    const bool with_zone = r.chance(0.10);
+    if (r.chance(0.9)) {
+        o.push_back('<');
+        if (bad_kind == 0) o += "256";
+        else if (bad_kind == 1) o += "1x";
+        else o += std::to_string(r.below(192));
+        if (bad_kind != 2) o.push_back('>');
+    }
+    std::string host;
+    rand_chars(r, host, r.range(4, 20), kHostChars, 38);
+    if (host[0] == '.' || host[0] == '-') host[0] = 'h';
+    std::string date;
+    {
+        const int y = r.range(1971, 2099), m = r.range(1, 12);
+        int d = r.range(1, dim(with_year ? y : 2023, m));  // a day every year has (without a year the current one decides)
+        if (with_year) {
+            char b[8];
+            snprintf(b, sizeof b, "%04d", y);
+            date += b;
+            date.push_back(' ');
+        }
+        date += bad_kind == 3 ? "aug" : (bad_kind == 4 ? "Sept" : MON[m - 1]);
+        date.push_back(' ');
+        if (!custom && d < 10 && r.chance(0.7)) date.push_back(' ');  // the BSD form pads the day with a space
+        if (bad_kind == 5) d = r.chance(0.5) ? 0 : 32;
+        date += std::to_string(d);
+        date.push_back(' ');
+        put2(date, bad_kind == 6 ? 24 : r.range(0, 23));
+        date.push_back(':');
+        put2(date, r.range(0, 59));
+        if (bad_kind != 7) {
+            date.push_back(':');
+            put2(date, bad_kind == 8 ? 60 : r.range(0, 59));
+        }
+        if (with_zone) {
+            date.push_back(' ');
+            date += r.chance(0.06) ? "Mars/Phobos" : ZONES[r.below((uint32_t)(sizeof ZONES / sizeof ZONES[0]))];
+        }
+    }
+    const int target = std::max(8, (int)(mean_len - 62.0 + r.normal() * 30.0));
+    if (custom) {
+        o += host;
+        o += bad_kind == 9 ? ":" : ": ";
+        o += date;
+        o += bad_kind == 10 ? " " : ": ";
+    } else {
+        o += date;
+        if (bad_kind == 11) return;  // the date alone: too few tokens, or a zone that swallows the last one
+        o.push_back(' ');
+        o += host;
+        o.push_back(' ');
+    }
+    // tag[pid]: text
+    rand_chars(r, o, r.range(3, 12), kAlnum, 52);
+    if (r.chance(0.6)) {
+        o.push_back('[');
+        o += std::to_string(r.below(65536));
+        o.push_back(']');
+    }
+    o += ": ";
+    const bool utf8 = r.chance(0.04);
+    const size_t m0 = o.size();
+    message_text(r, o, target, utf8);
+    const int style = (int)r.below(100);
+    if (style < 6) {  // irregular spacing inside the text
+        static const char* WS[] = {"  ", "\t", " \t ", "\xC2\xA0", "\xE3\x80\x80", "   ", "\xE2\x80\xA8", " \xC2\x85"};
+        for (size_t q = m0; q < o.size(); ++q)
+            if (o[q] == ' ' && r.chance(0.3)) {
+                const char* w = WS[r.below(8)];
+                o.replace(q, 1, w);
+                q += strlen(w) - 1;
+            }
+    } else if (style < 10) {
+        o += r.chance(0.5) ? " " : "  \t";  // trailing blanks: trimmed off full_msg, dropped by the re-join
+    } else if (style < 12) {
+        o += " \x01\x1b[0m x";  // control bytes that are not White_Space
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -417,6 +511,7 @@ int fgen_generate(int kind, uint64_t seed, int64_t first_index, int64_t n, doubl
             for (int64_t i = lo; i < hi; ++i) {
                 const size_t before = o.size();
                 switch (kind) {
+                    case 3: gen_rfc3164(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     case 2: gen_gelf(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     case 1: gen_ltsv(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;
                     default: gen_rfc5424(seed, (uint64_t)(first_index + i), mean_len, bad_frac, o); break;

@@ -180,6 +180,8 @@ CudaBatchDecoder::CudaBatchDecoder(fg_format fmt, const LtsvConfig& ltsv, const 
     cfg.max_batch_bytes = opt.max_batch_bytes;
     cfg.max_batch_lines = opt.max_batch_lines;
     cfg.chunk_lines = opt.chunk_lines;
+    cfg.rfc3164_year = opt.rfc3164_year;
+    cfg.tzdir = opt.tzdir.empty() ? nullptr : opt.tzdir.c_str();
     std::vector<const char*> names;
     std::vector<int32_t> types;
     for (const auto& kv : ltsv.schema) {
@@ -412,8 +414,12 @@ DecodeResult materialize_record(fg_format fmt, const std::string* suffix, const 
     if (FG_META_FACILITY(meta) != 0xFF) rec.facility = (uint8_t)FG_META_FACILITY(meta);
     if (FG_META_SEVERITY(meta) != 0xFF) rec.severity = (uint8_t)FG_META_SEVERITY(meta);
     if (out.msg[i].off >= 0) {
-        std::string_view m = span_sv(bytes, out.msg[i]);
-        rec.msg = (flags & FG_FLAG_MSG_ESC) ? json_unescape(m, nl_retry) : std::string(m);
+        if (flags & FG_FLAG_MSG_ARENA) {  // RFC3164: the tokens re-joined by single spaces on the device (rfc3164_decoder.rs:67)
+            rec.msg = std::string((const char*)out.arena + out.msg[i].off, (size_t)out.msg[i].len);
+        } else {
+            std::string_view m = span_sv(bytes, out.msg[i]);
+            rec.msg = (flags & FG_FLAG_MSG_ESC) ? json_unescape(m, nl_retry) : std::string(m);
+        }
     }
     if (out.full_msg[i].off >= 0) {
         std::string_view m = span_sv(bytes, out.full_msg[i]);

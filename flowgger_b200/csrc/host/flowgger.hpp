@@ -6,8 +6,8 @@
 // shipped as source) is mirrored here 1:1 in C++ and is what the tests drive:
 //   Record / StructuredData / SDValue      <- src/flowgger/record.rs:4-82
 //   Decoder::decode / clone_boxed          <- src/flowgger/decoder/mod.rs:23-46
-//   RFC5424Decoder / LTSVDecoder / GelfDecoder::new(&Config)
-//                                          <- decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16
+//   RFC5424Decoder / LTSVDecoder / GelfDecoder / RFC3164Decoder::new(&Config)
+//                                          <- decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16, rfc3164_decoder.rs:14
 //   BatchingLineSplitter::run              <- splitter/line_splitter.rs:10-54 (batched)
 // All parsing happens in the CUDA kernels; this layer only packs lines, calls
 // fg_decode_batch and materialises owned Records from the columnar spans.
@@ -80,6 +80,10 @@ struct DeviceOptions {
     int64_t max_batch_bytes = 0;
     int32_t max_batch_lines = 0;
     int32_t chunk_lines = 0;
+    // input.format = "rfc3164": the year `OffsetDateTime::now_utc().year()` stands for (0 = follow the clock,
+    // rfc3164_decoder.rs:175) and the TZif directory behind time_tz::timezones::get_by_name ("" = $TZDIR / system)
+    int32_t rfc3164_year = 0;
+    std::string tzdir;
 };
 
 // One GPU decoding context of a fixed format.  Single caller at a time (see mutex()).
@@ -154,6 +158,10 @@ struct LTSVDecoder : CudaDecoder {
 };
 struct GelfDecoder : CudaDecoder {
     explicit GelfDecoder(const DeviceOptions& opt = {}) : CudaDecoder(FG_FMT_GELF, {}, opt) {}
+};
+// decoder/rfc3164_decoder.rs:10-17 (the Config is unused there as well)
+struct RFC3164Decoder : CudaDecoder {
+    explicit RFC3164Decoder(const DeviceOptions& opt = {}) : CudaDecoder(FG_FMT_RFC3164, {}, opt) {}
 };
 
 // encoder/mod.rs:54-56 (interface only: encoders are out of scope)

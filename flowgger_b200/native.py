@@ -9,8 +9,8 @@ import numpy as np
 
 LIB_DIR = Path(__file__).resolve().parent / "lib"
 
-FMT_RFC5424, FMT_LTSV, FMT_GELF = 0, 1, 2
-FMT_NAMES = {FMT_RFC5424: "rfc5424", FMT_LTSV: "ltsv", FMT_GELF: "gelf"}
+FMT_RFC5424, FMT_LTSV, FMT_GELF, FMT_RFC3164 = 0, 1, 2, 3
+FMT_NAMES = {FMT_RFC5424: "rfc5424", FMT_LTSV: "ltsv", FMT_GELF: "gelf", FMT_RFC3164: "rfc3164"}
 
 
 class NativeLibraryMissing(ImportError):
@@ -96,6 +96,11 @@ def load_cuda() -> C.CDLL:
         L.fg_error_count.restype = C.c_uint32
         L.fg_last_dominant_kernel_ms.restype = C.c_float
         L.fg_last_dominant_kernel_ms.argtypes = [C.c_void_p]
+        L.fg_set_rfc3164_year.argtypes = [C.c_void_p, C.c_int32]
+        L.fg_set_tz_table.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fg_tz_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int32)]
+        L.fg_tz_count.argtypes = [C.c_char_p]
+        L.fg_tz_count.restype = C.c_int32
         L.fg_set_gelf_extra.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
         L.fg_decode_encode_gelf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FgEncodedOut)]
         _cuda = L
@@ -164,7 +169,7 @@ def generate(fmt: int, seed: int, n: int, *, first_index: int = 0, mean_len: flo
     """Synthetic batch (SURVEY.md §8(d) shapes): returns (bytes uint8[total], offsets int32[n+1])."""
     L = load_gen()
     if mean_len <= 0:
-        mean_len = {FMT_RFC5424: 180.0, FMT_GELF: 512.0, FMT_LTSV: 420.0}[fmt]
+        mean_len = {FMT_RFC5424: 180.0, FMT_GELF: 512.0, FMT_LTSV: 420.0, FMT_RFC3164: 140.0}[fmt]
     pb, po, tot = C.c_void_p(), C.c_void_p(), C.c_int64()
     L.fgen_set_terminator(1 if terminated else 0)  # terminated: every line ends in '\n' (raw stream for split_decode)
     rc = L.fgen_generate(fmt, seed, first_index, n, mean_len, bad_frac, nthreads, C.byref(pb), C.byref(po), C.byref(tot))
@@ -258,7 +263,7 @@ class BatchDecoder:
 
     def __init__(self, fmt: int, *, device: int = 0, max_batch_bytes: int = 0, max_batch_lines: int = 0,
                  chunk_lines: int = 0, ltsv_schema: dict[str, str] | None = None,
-                 ltsv_suffixes: dict[str, str] | None = None):
+                 ltsv_suffixes: dict[str, str] | None = None, rfc3164_year: int = 0):
         self._h = None
         self.L = load_cuda()
         self.H = load_host()
@@ -282,6 +287,28 @@ class BatchDecoder:
         self._h = C.c_void_p(h)
         self.ctx = C.c_void_p(self.H.fgh_decoder_ctx(self._h))
         self._pinned: list[C.c_void_p] = []
+        if rfc3164_year:
+            self.set_rfc3164_year(rfc3164_year)
+
+    def set_rfc3164_year(self, year: int) -> None:
+        """The year a timestamp without one belongs to (`OffsetDateTime::now_utc().year()`, rfc3164_decoder.rs:175);
+        0 = the UTC year of the clock at each call."""
+        self._check(self.L.fg_set_rfc3164_year(self.ctx, year), "fg_set_rfc3164_year")
+
+    def set_tz_table(self, zones: dict[str, tuple[list[int], list[int]]]) -> None:
+        """Replace the zone database: name -> (UTC transition seconds, len + 1 UTC offsets), as oracle/tzread.py yields."""
+        names = sorted(zones)
+        first = np.zeros(len(names) + 1, dtype=np.int32)
+        starts, offs = [], []
+        for k, nm in enumerate(names):
+            tr, of = zones[nm]
+            starts += [0] + [int(t) for t in tr]
+            offs += [int(o) for o in of]
+            first[k + 1] = len(offs)
+        st = np.asarray(starts, dtype=np.int64)
+        of = np.asarray(offs, dtype=np.int32)
+        cn = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        self._check(self.L.fg_set_tz_table(self.ctx, len(names), cn, _ptr(first), _ptr(st), _ptr(of)), "fg_set_tz_table")
 
     def close(self) -> None:
         if self._h:
@@ -436,6 +463,20 @@ def dump_records(fmt: int, out: FgBatchOut, data: np.ndarray, offsets: np.ndarra
         H.fgh_free(pb)
         H.fgh_free(po)
     return buf, offs
+
+
+def tz_lookup(name: str, local: int, tzdir: str | None = None):
+    """Host-side query of the zone database a context loads (fg_tz_lookup): UTC offset of `name` at the local second, or None."""
+    L = load_cuda()
+    off = C.c_int32()
+    rc = L.fg_tz_lookup(tzdir.encode() if tzdir else None, name.encode(), local, C.byref(off))
+    if rc < 0:
+        raise RuntimeError("no zone database")
+    return int(off.value) if rc == 1 else None
+
+
+def tz_count(tzdir: str | None = None) -> int:
+    return int(load_cuda().fg_tz_count(tzdir.encode() if tzdir else None))
 
 
 def shard_by_bytes(offsets: np.ndarray, G: int) -> np.ndarray:

@@ -4,8 +4,8 @@
  * replaces is
  *     trait Decoder { fn decode(&self, line: &str) -> Result<Record, &'static str>; }
  *         (/root/reference/src/flowgger/decoder/mod.rs:44-46)
- * constructed by RFC5424Decoder::new / LTSVDecoder::new / GelfDecoder::new
- *         (decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16)
+ * constructed by RFC5424Decoder::new / LTSVDecoder::new / GelfDecoder::new / RFC3164Decoder::new
+ *         (decoder/rfc5424_decoder.rs:12, ltsv_decoder.rs:24, gelf_decoder.rs:16, rfc3164_decoder.rs:14)
  * and called once per record by the splitters
  *         (splitter/line_splitter.rs:50, nul_splitter.rs:57, syslen_splitter.rs:65).
  * The batched form is: N lines packed into one contiguous byte buffer plus an
@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 /* input.format (mod.rs:413-422) */
-typedef enum fg_format { FG_FMT_RFC5424 = 0, FG_FMT_LTSV = 1, FG_FMT_GELF = 2 } fg_format;
+typedef enum fg_format { FG_FMT_RFC5424 = 0, FG_FMT_LTSV = 1, FG_FMT_GELF = 2, FG_FMT_RFC3164 = 3 } fg_format;
 
 /* SDValue discriminant (record.rs:4-11) + table-internal marker */
 typedef enum fg_tag {
@@ -60,6 +60,9 @@ typedef enum fg_tag {
 #define FG_FLAG_MSG_ESC 0x08u      /* GELF: short_message span holds JSON escapes */
 #define FG_FLAG_FULL_ESC 0x10u     /* GELF: full_message span holds JSON escapes */
 #define FG_FLAG_NL_RETRY 0x20u     /* GELF: parsed through the raw-newline retry (gelf_decoder.rs:44-46) */
+#define FG_FLAG_MSG_ARENA 0x40u    /* RFC3164: msg.off indexes fg_batch_out.arena — the message tokens re-joined by single
+                                      spaces on the device (rfc3164_decoder.rs:67); without the flag the re-joined message is
+                                      a span of the input */
 #define FG_FLAG_WIDE 0x80u         /* RFC5424: the row lives in fg_batch_out.wide_rows[row.sd_first] (unusual shape, line >= 64 KiB, ...) */
 
 /* (offset,len) into the `bytes` buffer given to the call; off < 0 => None */
@@ -143,6 +146,13 @@ typedef struct fg_config {
     const char* const* ltsv_schema_names; /* NUL-terminated UTF-8 */
     const int32_t* ltsv_schema_types;     /* fg_ltsv_type */
     const char* ltsv_suffix[5];           /* indexed by fg_ltsv_type; NULL = none ([0] unused) */
+    /* input.format = "rfc3164": the two things RFC3164Decoder takes from its environment.
+     * rfc3164_year: the year a timestamp without one belongs to — `OffsetDateTime::now_utc().year()`,
+     *   rfc3164_decoder.rs:175.  0 = the UTC year of the clock at each fg_decode_batch / fg_split_decode call.
+     * tzdir: directory of TZif files (RFC 8536) behind `time_tz::timezones::get_by_name`, :196.  NULL = $TZDIR, else
+     *   /usr/share/zoneinfo.  Read on the first RFC3164 call; fg_set_tz_table replaces it with the caller's own table. */
+    int32_t rfc3164_year;
+    const char* tzdir;
 } fg_config;
 
 /* Columnar result of one batch.  All pointers are host pointers owned by the
@@ -158,7 +168,7 @@ typedef struct fg_batch_out {
     const fg_span* msgid;    /* RFC5424 only, else NULL */
     const fg_span* msg;
     const fg_span* full_msg; /* on error rows of LTSV: off = byte offset of the failing part */
-    const fg_span* sd;       /* {first entry, entry count} ; count 0 => Record.sd = None */
+    const fg_span* sd;       /* {first entry, entry count} ; count 0 => Record.sd = None (always for RFC3164) */
     /* side table of LTSV / GELF, and of the RFC5424 wide rows */
     const fg_span* entry_name;  /* [n_entries] */
     const uint64_t* entry_val;  /* string: off | len<<32 ; bool/i64/u64/f64: the 8 value bytes ; header: #pairs */
@@ -171,7 +181,7 @@ typedef struct fg_batch_out {
     int32_t n_entries8;
     int32_t n_wide;             /* rows flagged FG_FLAG_WIDE */
     const fg_wide_row* wide_rows;
-    const uint8_t* arena;       /* unescaped SD values (FG_E8_ARENA records, FG_EM_ARENA spans) */
+    const uint8_t* arena;       /* unescaped SD values (FG_E8_ARENA records, FG_EM_ARENA spans); RFC3164: re-joined messages (FG_FLAG_MSG_ARENA) */
     int64_t arena_bytes;
     /* timings of the call, milliseconds */
     float kernel_ms; /* sum of parse-kernel time (CUDA events on the launch stream) */
@@ -196,6 +206,19 @@ const char* fg_last_error(const fg_ctx* ctx); /* human-readable detail of the la
  * Any host pointer is accepted by fg_decode_batch; pinned ones go at PCIe rate. */
 int fg_host_alloc(fg_ctx* ctx, size_t bytes, void** out);
 void fg_host_free(fg_ctx* ctx, void* p);
+
+/* RFC3164 environment after construction: the year (0 = follow the clock) and an explicit zone table.
+ * Zone z is `names[z]` with spans [first[z], first[z+1]): span j holds UTC offset span_offset[j] (seconds east) from the UTC
+ * second span_start_utc[j] on; the start of a zone's first span is ignored (it reaches back for ever).  A local time is
+ * resolved as time-tz's assume_timezone does it (rfc3164_decoder.rs:202): the offset in force at that local time; a local
+ * time that occurs twice takes the earlier offset, one that a forward jump skips the offset before the jump. */
+int fg_set_rfc3164_year(fg_ctx* ctx, int32_t year);
+int fg_set_tz_table(fg_ctx* ctx, int32_t n_zones, const char* const* names, const int32_t* first, const int64_t* span_start_utc,
+                    const int32_t* span_offset);
+/* Host-side queries of the zone database a context would load from `tzdir` (NULL as in fg_config); no device involved.
+ * fg_tz_lookup: 1 = `name` is a zone (its UTC offset at local second `local` is stored), 0 = not a zone, <0 = no database. */
+int fg_tz_lookup(const char* tzdir, const char* name, int64_t local, int32_t* offset);
+int32_t fg_tz_count(const char* tzdir);
 
 /* Decoder::decode for n lines.  offsets has n+1 monotone entries, offsets[0] >= 0;
  * line i is bytes[offsets[i] .. offsets[i+1]) and must be valid UTF-8 without the

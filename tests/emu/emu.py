@@ -21,11 +21,13 @@ _lib = None
 def build(force: bool = False) -> Path:
     so = HERE / "libfg_emu.so"
     csrc = REPO / "flowgger_b200" / "csrc"
-    srcs = [HERE / "emu_r5.cpp", HERE / "emu_ltsv.cpp", HERE / "emu_gelf.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h"] + \
-        sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h"))
+    srcs = [HERE / "emu_r5.cpp", HERE / "emu_ltsv.cpp", HERE / "emu_gelf.cpp", HERE / "emu_r3164.cpp", HERE / "cuda_shim.h",
+            REPO / "include" / "flowgger_cuda.h", csrc / "fg_tz.cu"] + sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h"))
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
-                        str(HERE / "emu_r5.cpp"), str(HERE / "emu_ltsv.cpp"), str(HERE / "emu_gelf.cpp"), "-I", str(REPO / "include")], check=True)
+                        str(HERE / "emu_r5.cpp"), str(HERE / "emu_ltsv.cpp"), str(HERE / "emu_gelf.cpp"), str(HERE / "emu_r3164.cpp"),
+                        # fg_tz.cu is host-only C++ (the zone-table reader / packer): the same source the product builds with nvcc
+                        "-x", "c++", "-DFG_HOST_EMU=1", str(csrc / "fg_tz.cu"), "-I", str(REPO / "include")], check=True)
     return so
 
 
@@ -38,6 +40,8 @@ def lib() -> C.CDLL:
         _lib.emu_ltsv_classify16.restype = C.c_uint32
         _lib.emu_ltsv_classify16.argtypes = [C.c_void_p]
         _lib.emu_gelf_bits16.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.emu_r3164_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_char_p,
+                                          C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -98,6 +102,42 @@ def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict
     finally:
         lib().emu_ltsv_free(C.byref(out))
     return buf, offs, d
+
+
+def r3164_decode_dump(native, data: np.ndarray, offsets: np.ndarray, year: int, tile_bytes: int = 8192, strip_eol: int = 0,
+                      invalid: np.ndarray | None = None, arena_cap: int = 1 << 20, tzdir: str | None = None):
+    """Emulated RFC3164 decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser."""
+    from flowgger_b200.native import FgBatchOut, dump_records
+    L = lib()
+    out = FgBatchOut()
+    n = len(offsets) - 1
+    info = (C.c_int32 * 3)()
+    rc = L.emu_r3164_decode(C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n, tile_bytes, strip_eol,
+                            C.c_void_p(invalid.ctypes.data) if invalid is not None else None, year,
+                            tzdir.encode() if tzdir else None, arena_cap, C.byref(out), info)
+    assert rc == 0, "no zone database"
+    try:
+        buf, offs = dump_records(3, out, data, offsets)
+        d = {"from_tile": int(info[0]), "from_global": int(info[1]), "redo": int(info[2]), "arena_bytes": int(out.arena_bytes)}
+    finally:
+        L.emu_r3164_free(C.byref(out))
+    return buf, offs, d
+
+
+def tz_lookup(name: str, local: int, tzdir: str | None = None):
+    """The packed zone table as the kernel searches it: UTC offset of `name` at the local second, or None."""
+    L = lib()
+    L.emu_tz_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int32)]
+    off = C.c_int32()
+    rc = L.emu_tz_lookup(tzdir.encode() if tzdir else None, name.encode(), local, C.byref(off))
+    assert rc >= 0, "no zone database"
+    return int(off.value) if rc == 1 else None
+
+
+def tz_count(tzdir: str | None = None) -> int:
+    L = lib()
+    L.emu_tz_count.argtypes = [C.c_char_p]
+    return int(L.emu_tz_count(tzdir.encode() if tzdir else None))
 
 
 def gelf_bits16(block: bytes) -> tuple[int, int, int, int]:
