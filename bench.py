@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the Decoder hot path on B200: log lines/s and GB/s parsed, with roofline + CPU baseline.
 
-    python bench.py --gpus N --steps K --warmup W [--format rfc5424|ltsv|gelf] [--lines L] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--format rfc5424|ltsv|gelf|rfc3164|mixed] [--lines L] [--impl reference]
 
 A "step" is one pass of the parse kernel over one synthetic batch that is already resident in HBM
 (BASELINE.json configs[1]: 10 M RFC5424 lines, mean 180 B, per GPU).  `e2e` is the same metric through
@@ -24,12 +24,13 @@ from pathlib import Path
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
-FORMATS = {"rfc5424": 0, "ltsv": 1, "gelf": 2}
-SEEDS = {"rfc5424": 5424, "ltsv": 1757, "gelf": 0x6E1F}
+FORMATS = {"rfc5424": 0, "ltsv": 1, "gelf": 2, "rfc3164": 3}
+SEEDS = {"rfc5424": 5424, "ltsv": 1757, "gelf": 0x6E1F, "rfc3164": 3164}
+RFC3164_YEAR = 2026  # the year timestamps without one belong to: fixed, so that a run is reproducible
 # generator parameter that lands the ACTUAL mean line length on the BASELINE.json shape
-GEN_MEAN = {"rfc5424": 169.2, "ltsv": 420.0, "gelf": 466.0}
-TARGET_MEAN = {"rfc5424": 180, "ltsv": 420, "gelf": 512}
-DEFAULT_LINES = {"rfc5424": 10_000_000, "ltsv": 4_000_000, "gelf": 3_500_000}  # int32 offsets cap a batch at 2 GiB
+GEN_MEAN = {"rfc5424": 169.2, "ltsv": 420.0, "gelf": 466.0, "rfc3164": 140.0}
+TARGET_MEAN = {"rfc5424": 180, "ltsv": 420, "gelf": 512, "rfc3164": 127}
+DEFAULT_LINES = {"rfc5424": 10_000_000, "ltsv": 4_000_000, "gelf": 3_500_000, "rfc3164": 10_000_000}  # int32 offsets cap a batch at 2 GiB
 
 
 def env_int(name: str, default: int) -> int:
@@ -139,9 +140,20 @@ LTSV_SUFFIXES = {"u64": "_u64", "i64": "_i64", "f64": "_f64", "bool": "_bool"}
 
 
 def ltsv_kwargs(fmt_name: str, typed: bool = False) -> dict:
+    """format-specific decoder configuration"""
     if fmt_name == "ltsv" and typed:
         return {"ltsv_schema": LTSV_SCHEMA, "ltsv_suffixes": LTSV_SUFFIXES}
+    if fmt_name == "rfc3164":
+        return {"rfc3164_year": RFC3164_YEAR}
     return {}
+
+
+def oracle_config(pyoracle, fmt_name: str, typed: bool):
+    if fmt_name == "ltsv" and typed:
+        return pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES)
+    if fmt_name == "rfc3164":
+        return pyoracle.Rfc3164Config(RFC3164_YEAR)
+    return None
 
 
 def run_reference(args) -> None:
@@ -158,7 +170,7 @@ def run_reference(args) -> None:
     sample = args.lines  # the same lines the GPU arm parses (same generator, seed and count)
     data, offs = make_batch(fb, fmt_name, sample, 0)
     nbytes = int(offs[-1])
-    ocfg = pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES) if (fmt_name == "ltsv" and args.ltsv_typed) else None
+    ocfg = oracle_config(pyoracle, fmt_name, args.ltsv_typed)
     for _ in range(max(args.warmup, 1)):
         pyoracle.decode_bench(fmt, data, offs, ocfg, nthreads=cores)
     t = 0.0
@@ -318,6 +330,9 @@ def run_mixed(args) -> None:
 
 
 def workload_name(fmt_name: str, lines: int) -> str:
+    if fmt_name == "rfc3164":
+        return (f"RFC3164 batch: {lines} synthetic BSD-syslog lines per GPU, mean {TARGET_MEAN[fmt_name]} B (SURVEY.md 8(f) N3; not a "
+                "BASELINE.json config)")
     if fmt_name != "rfc5424":
         return (f"{fmt_name.upper()} batch: {lines}-line int32-offset sub-batch per GPU of the 10 M-line workload, mean "
                 f"{TARGET_MEAN[fmt_name]} B (BASELINE.json configs[{ {'gelf': 2, 'ltsv': 3}[fmt_name] }])")
@@ -445,7 +460,7 @@ def main() -> None:
         n_entries = int(res.raw.n_entries8)
         b_write = n * 32 + n_entries * 8 + int(res.raw.arena_bytes) + int(res.raw.n_wide) * 72 + int(res.n_entries) * 17
     else:
-        b_write = n * (12 + 8 * 4) + n_entries * 17
+        b_write = n * (12 + 8 * 4) + n_entries * 17 + (int(res.raw.arena_bytes) if fmt == 3 else 0)
     d2h_bytes = b_write
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
@@ -523,7 +538,7 @@ def main() -> None:
         sample = min(n, 2_000_000)
         so = np.ascontiguousarray(h_offs[: sample + 1])
         sb = h_bytes[: int(so[-1])]
-        ocfg = pyoracle.LtsvConfig(LTSV_SCHEMA, LTSV_SUFFIXES) if (fmt_name == "ltsv" and args.ltsv_typed) else None
+        ocfg = oracle_config(pyoracle, fmt_name, args.ltsv_typed)
         pyoracle.decode_bench(fmt, sb, so, ocfg, nthreads=cores)
         s_all, _ = pyoracle.decode_bench(fmt, sb, so, ocfg, nthreads=cores)
         s_one, _ = pyoracle.decode_bench(fmt, sb[: int(so[sample // 8])], np.ascontiguousarray(so[: sample // 8 + 1]), ocfg, nthreads=1)
@@ -558,7 +573,7 @@ def main() -> None:
             "kernel_ms": k_avg_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "of": peak_kind, "traffic": traffic,
-                         "kernel": {0: "parse5424_kernel", 1: "parse_ltsv_kernel", 2: "parse_gelf_kernel + post_gelf_kernel"}[fmt],
+                         "kernel": {0: "parse5424_kernel", 1: "parse_ltsv_kernel", 2: "parse_gelf_kernel + post_gelf_kernel", 3: "parse3164_kernel"}[fmt],
                          "kernel_ms": dom_ms, "step_ms": k_avg_ms, "step_frac": (b_read / 1e9) / (k_avg_ms / 1e3) / peak,
                          "note": "achieved = algorithmic bytes / CUDA-event time of the dominant kernel alone (single steps); "
                                  "step_* = the same over every kernel of a step (RFC5424: + post5424_kernel), which is what `value` counts",

@@ -200,8 +200,14 @@ constexpr int kGelfCtasPerSm = 3;  // tile (~34 KB at 520 B/line) + bitmap + slo
 constexpr int kGelfStageSlots = kGelfLinesPerCta * 16;
 constexpr int kGelfMaxTile = 65024;
 // RFC3164 (fg_parse3164.cu): 64 lines and 64 threads per CTA, one thread per line over the staged tile
-constexpr int kR3164LinesPerCta = 64;
-constexpr int kR3164CtasPerSm = 16;
+#ifndef FG_R3_LINES  // profiles/r2_rfc3164_variants.sh builds other shapes for A/B runs
+#define FG_R3_LINES 64
+#endif
+#ifndef FG_R3_MINB
+#define FG_R3_MINB 16
+#endif
+constexpr int kR3164LinesPerCta = FG_R3_LINES;
+constexpr int kR3164CtasPerSm = FG_R3_MINB;
 constexpr int kR3164MaxTile = 65024;
 constexpr int lines_per_cta(int fmt) {
     return fmt == 0 ? kRfc5424LinesPerCta : (fmt == 1 ? kLtsvLinesPerCta : (fmt == 2 ? kGelfLinesPerCta : kR3164LinesPerCta));
