@@ -206,6 +206,9 @@ constexpr int kGelfMaxTile = 65024;
 #ifndef FG_R3_MINB
 #define FG_R3_MINB 16
 #endif
+#ifndef FG_R3_LOCKSTEP  // 1: r3164_parse_lockstep (warp-wide phases), 0: r3164_parse_line (one thread on its own); fg_rfc3164.cuh
+#define FG_R3_LOCKSTEP 1
+#endif
 constexpr int kR3164LinesPerCta = FG_R3_LINES;
 constexpr int kR3164CtasPerSm = FG_R3_MINB;
 constexpr int kR3164MaxTile = 65024;

@@ -12,6 +12,7 @@
 #include "fg_kernels.cuh"
 
 #include "fg_common.cuh"
+#define FG_R3164_WALKERS 1
 #include "fg_rfc3164.cuh"
 #include "fg_status.h"
 #include "fg_tma.cuh"
@@ -21,6 +22,7 @@ namespace fg {
 namespace {
 
 constexpr int kLines = kR3164LinesPerCta;
+static_assert(kLines % 32 == 0, "r3164_parse_lockstep is called by whole warps");
 
 __global__ void __launch_bounds__(kLines, kR3164CtasPerSm) parse3164_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t tile[];
@@ -49,13 +51,11 @@ __global__ void __launch_bounds__(kLines, kR3164CtasPerSm) parse3164_kernel(cons
         }
         mbar_wait(&mbar, 0u);
     }
-    if (i >= last) return;
-
-    const uint8_t* tp = tile + (o0 - base);
-    const uint8_t* lp = fits ? tp : P.bytes + o0;
+    const bool have = i < last;
+    const uint8_t* lp = fits ? tile + (o0 - base) : P.bytes + o0;
     int len = o1 - o0;
     bool bad_utf8 = false;
-    if (P.strip_eol && len > 0) {
+    if (have && P.strip_eol && len > 0) {
         // BufRead::lines drops the '\n' and one '\r' before it (line_splitter.rs:17); BufRead::split(0) only the NUL
         // (nul_splitter.rs:18); a record that is not UTF-8 is reported and skipped (:22-25)
         if (P.strip_eol == 2) {
@@ -67,16 +67,24 @@ __global__ void __launch_bounds__(kLines, kR3164CtasPerSm) parse3164_kernel(cons
         bad_utf8 = P.line_invalid != nullptr && P.line_invalid[i] != 0;
     }
     R3Out res;
+#if FG_R3_LOCKSTEP
+    // every lane of the warp walks the same phases (lanes without a line idle): see fg_rfc3164.cuh
+    r3164_parse_lockstep(lp, len, have && !bad_utf8, P.r3164, res);
+    if (!have) return;
+    if (bad_utf8) res.status = FG_ES_INVALID_UTF8;
+#else
+    if (!have) return;
     if (bad_utf8) {
         res.status = FG_ES_INVALID_UTF8;
         res.facility = res.severity = 0xFFu;
         res.flags = 0u;
         res.ts = 0.0;
     } else if (fits) {
-        r3164_parse_line(tp, len, P.r3164, res);  // shared-memory loads (LDS) on the common path
+        r3164_parse_line(tile + (o0 - base), len, P.r3164, res);  // shared-memory loads (LDS) on the common path
     } else {
         r3164_parse_line(P.bytes + o0, len, P.r3164, res);
     }
+#endif
     const bool ok = res.status == FG_ST_OK;
     P.ts[i] = ok ? res.ts : 0.0;
     P.meta[i] = res.status | (res.facility << 8) | (res.severity << 16) | (res.flags << 24);

@@ -41,7 +41,7 @@ def lib() -> C.CDLL:
         _lib.emu_ltsv_classify16.argtypes = [C.c_void_p]
         _lib.emu_gelf_bits16.argtypes = [C.c_void_p, C.c_void_p]
         _lib.emu_r3164_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_char_p,
-                                          C.c_uint32, C.c_void_p, C.c_void_p]
+                                          C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -105,7 +105,7 @@ def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict
 
 
 def r3164_decode_dump(native, data: np.ndarray, offsets: np.ndarray, year: int, tile_bytes: int = 8192, strip_eol: int = 0,
-                      invalid: np.ndarray | None = None, arena_cap: int = 1 << 20, tzdir: str | None = None):
+                      invalid: np.ndarray | None = None, arena_cap: int = 1 << 20, tzdir: str | None = None, lockstep: bool = True):
     """Emulated RFC3164 decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser."""
     from flowgger_b200.native import FgBatchOut, dump_records
     L = lib()
@@ -114,7 +114,7 @@ def r3164_decode_dump(native, data: np.ndarray, offsets: np.ndarray, year: int, 
     info = (C.c_int32 * 3)()
     rc = L.emu_r3164_decode(C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n, tile_bytes, strip_eol,
                             C.c_void_p(invalid.ctypes.data) if invalid is not None else None, year,
-                            tzdir.encode() if tzdir else None, arena_cap, C.byref(out), info)
+                            tzdir.encode() if tzdir else None, arena_cap, 1 if lockstep else 0, C.byref(out), info)
     assert rc == 0, "no zone database"
     try:
         buf, offs = dump_records(3, out, data, offsets)

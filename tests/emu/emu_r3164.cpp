@@ -37,7 +37,8 @@ extern "C" {
 // `year`: what now_utc().year() stands for.  tzdir: NULL = the system database.  arena_cap: initial capacity (small values
 // exercise the regrow + redo path).  info: [3] lines parsed from the tile, from the input buffer, redo passes.
 int emu_r3164_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, int32_t tile_bytes, int32_t strip_eol,
-                     const uint8_t* invalid, int32_t year, const char* tzdir, uint32_t arena_cap, fg_batch_out* out, int32_t* info) {
+                     const uint8_t* invalid, int32_t year, const char* tzdir, uint32_t arena_cap, int32_t lockstep, fg_batch_out* out,
+                     int32_t* info) {
     const std::string dir = tzdir ? tzdir : "";
     if (!g_tz.loaded || dir != g_tz_dir) {
         std::string err;
@@ -88,7 +89,10 @@ int emu_r3164_decode(const uint8_t* bytes, const int32_t* offsets, int32_t n, in
                     bad = invalid != nullptr && invalid[i] != 0;
                 }
                 fg::R3Out res;
-                if (bad) {
+                if (lockstep) {  // the walker the kernel is built with (FG_R3_LOCKSTEP = 1), a warp being this one lane
+                    fg::r3164_parse_lockstep(lp, len, !bad, cfg, res);
+                    if (bad) res.status = FG_ES_INVALID_UTF8;
+                } else if (bad) {
                     res.status = FG_ES_INVALID_UTF8;
                     res.facility = res.severity = 0xFFu;
                     res.flags = 0u;

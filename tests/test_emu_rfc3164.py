@@ -23,12 +23,18 @@ def emu():
 
 
 def check(emu, native, oracle, data, offs, year=YEAR, **kw):
-    gbuf, goffs, info = emu.r3164_decode_dump(native, data, offs, year, **kw)
+    """both walkers of fg_rfc3164.cuh — r3164_parse_lockstep (what the kernel is built with) and r3164_parse_line — against
+    the oracle"""
     obuf, ooffs = oracle.decode_dump(R3, data, offs, oracle.Rfc3164Config(year), nthreads=8)
-    if not (gbuf == obuf and np.array_equal(goffs, ooffs)):
-        diffs = first_diff(gbuf, goffs, obuf, ooffs, data, offs)
-        msg = "\n".join(f"line {i}: {line!r}\n   emu: {g!r}\n   ref: {o!r}" for i, line, g, o in diffs)
-        raise AssertionError(f"{len(diffs)}+ lines differ from the oracle:\n{msg}")
+    info = None
+    for lockstep in (False, True):
+        gbuf, goffs, inf = emu.r3164_decode_dump(native, data, offs, year, lockstep=lockstep, **kw)
+        if not (gbuf == obuf and np.array_equal(goffs, ooffs)):
+            diffs = first_diff(gbuf, goffs, obuf, ooffs, data, offs)
+            msg = "\n".join(f"line {i}: {line!r}\n   emu: {g!r}\n   ref: {o!r}" for i, line, g, o in diffs)
+            raise AssertionError(f"lockstep={lockstep}: {len(diffs)}+ lines differ from the oracle:\n{msg}")
+        assert info is None or info == inf
+        info = inf
     return info
 
 
