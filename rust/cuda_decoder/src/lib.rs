@@ -57,8 +57,11 @@ fn ltsv_type(t: &str) -> Option<i32> {
 }
 
 impl CudaDecoder {
-    /// `RFC5424Decoder::new(&Config)` / `LTSVDecoder::new` / `GelfDecoder::new` replacement, selected in
-    /// `flowgger::start` (src/flowgger/mod.rs:413-422) by `input.format`.
+    /// `RFC5424Decoder::new(&Config)` / `LTSVDecoder::new` / `GelfDecoder::new` / `RFC3164Decoder::new` replacement,
+    /// selected in `flowgger::start` (src/flowgger/mod.rs:413-422) by `input.format`.
+    /// RFC3164 (`fg_format_FG_FMT_RFC3164`): the context follows the UTC clock for `now_utc().year()`
+    /// (rfc3164_decoder.rs:175, `rfc3164_year = 0`) and reads the zone database behind `timezones::get_by_name` (:196) from
+    /// the TZif files under `input.cuda_tzdir` / `$TZDIR` / /usr/share/zoneinfo.
     pub fn new(config: &Config, fmt: fg_format) -> CudaDecoder {
         let mut names: Vec<CString> = Vec::new();
         let mut types: Vec<i32> = Vec::new();
@@ -89,6 +92,9 @@ impl CudaDecoder {
         cfg.device = config.lookup("input.cuda_device").and_then(|v| v.as_integer()).unwrap_or(0) as i32;
         cfg.max_batch_bytes = config.lookup("input.cuda_max_batch_bytes").and_then(|v| v.as_integer()).unwrap_or(0);
         cfg.max_batch_lines = config.lookup("input.cuda_max_batch_lines").and_then(|v| v.as_integer()).unwrap_or(0) as i32;
+        let tzdir: Option<CString> = config.lookup("input.cuda_tzdir").and_then(|v| v.as_str()).map(|s| CString::new(s).unwrap());
+        cfg.rfc3164_year = 0;
+        cfg.tzdir = tzdir.as_ref().map_or(ptr::null(), |s| s.as_ptr());
         cfg.ltsv_has_schema = has_schema as i32;
         cfg.ltsv_schema_len = names.len() as i32;
         cfg.ltsv_schema_names = name_ptrs.as_ptr();
@@ -334,7 +340,13 @@ fn materialize_ext(ctx: &Ctx, out: &fg_batch_out, bytes: &[u8], line_lo: i32, li
             appname: opt(out.appname),
             procid: opt(out.procid),
             msgid: opt(out.msgid),
-            msg: esc(opt(out.msg), FG_FLAG_MSG_ESC),
+            msg: if flags & FG_FLAG_MSG_ARENA != 0 {
+                // RFC3164: the message tokens re-joined by single spaces on the device (rfc3164_decoder.rs:67)
+                let m = *out.msg.add(i);
+                Some(std::str::from_utf8_unchecked(std::slice::from_raw_parts(out.arena.add(m.off as usize), m.len as usize)).to_owned())
+            } else {
+                esc(opt(out.msg), FG_FLAG_MSG_ESC)
+            },
             full_msg: esc(opt(out.full_msg), FG_FLAG_FULL_ESC),
             sd: if sd.is_empty() { None } else { Some(sd) },
         })
