@@ -304,3 +304,27 @@ def test_tz_tables_match_zoneinfo(oracle):
         for local in probes:
             want = (datetime(1970, 1, 1) + timedelta(seconds=local)).replace(tzinfo=zi).utcoffset().total_seconds()
             assert tzread.offset_at_local(z, local) == want, (name, local)
+
+
+def test_rfc3164_three_way(oracle, native):
+    """C++ oracle (oracle/rfc3164.cpp + the TZif tables of tzread.py) against the independent Python restatement
+    (oracle/pyrfc3164.py: regular expressions, datetime, zoneinfo) on the vectors and on generated lines, dump for dump."""
+    import pyrfc3164
+    year = 2026
+    cfg = oracle.Rfc3164Config(year)
+    lines = [l.encode() for _, _, l, _ in V.RFC3164_GOLDEN] + [l.encode() for l, _ in V.RFC3164_CASES]
+    data, offs = native.generate(native.FMT_RFC3164, 2, 60_000, bad_frac=0.05)
+    lines += [bytes(data[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+    import tzread
+    for k, nm in enumerate(sorted(tzread.load_zones())):       # every zone, across its history and into the footer rules
+        lines.append(f"{1900 + (k * 7) % 300} {'Mar Apr Oct Nov'.split()[k % 4]} {1 + k % 28} 0{k % 10}:30:00 {nm} h m".encode())
+    d, o = oracle.pack(lines)
+    buf, bo = oracle.decode_dump(R3, d, o, cfg)
+    skipped = 0
+    for i, l in enumerate(lines):
+        r = pyrfc3164.decode(l.decode(), year)
+        if r is pyrfc3164.UNSUPPORTED:
+            skipped += 1
+            continue
+        assert pyrfc3164.dump(r) == buf[bo[i]:bo[i + 1]], (l, pyrfc3164.dump(r), buf[bo[i]:bo[i + 1]])
+    assert skipped <= 4                                         # the vectors with year 0000 / negative years
