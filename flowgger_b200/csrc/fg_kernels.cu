@@ -1,6 +1,6 @@
 // fg_kernels.cu — configuration and dispatch of the batched parse kernels (sm_100a).
 //
-// Every format runs on the same pipeline, each in its own file:
+// RFC5424, LTSV and GELF run on the same pipeline, each in its own file; RFC3164 shares the staging only:
 //   RFC5424  fg_parse5424.cu   parse5424_kernel + post5424_kernel
 //   LTSV     fg_parse_ltsv.cu  parse_ltsv_kernel
 //   GELF     fg_parse_gelf.cu  parse_gelf_kernel + post_gelf_kernel
