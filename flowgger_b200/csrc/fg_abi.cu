@@ -1007,9 +1007,10 @@ int fg_set_tz_table(fg_ctx* c, int32_t n_zones, const char* const* names, const 
     if (!c || n_zones < 0 || (n_zones > 0 && (!names || !first || !span_start_utc || !span_offset))) return FG_E_ARG;
     std::vector<std::string> nm;
     std::vector<fg::TzZoneSpans> zones;
+    if (n_zones > 0 && first[0] < 0) return fail(c, FG_E_ARG, "fg_set_tz_table: first[] must start at a non-negative index");
     for (int32_t z = 0; z < n_zones; ++z) {
         const int32_t a = first[z], b = first[z + 1];
-        if (!names[z] || b <= a) return fail(c, FG_E_ARG, "fg_set_tz_table: every zone needs a name and at least one span");
+        if (!names[z] || !names[z][0] || b <= a) return fail(c, FG_E_ARG, "fg_set_tz_table: every zone needs a name and at least one span");
         fg::TzZoneSpans sp;
         for (int32_t j = a; j < b; ++j) {
             if (j > a) {

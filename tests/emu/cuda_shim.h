@@ -50,4 +50,4 @@ static inline long long __double_as_longlong(double d) { long long v; std::memcp
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 using std::isinf;
 static inline double __ll2double_rn(long long v) { return (double)v; }
-static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p = old + v; return old; }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

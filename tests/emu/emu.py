@@ -31,6 +31,31 @@ def build(force: bool = False) -> Path:
     return so
 
 
+_lib_warp = None
+
+
+def build_warp(force: bool = False) -> Path:
+    """emu_r3164.cpp once more with FG_HOST_EMU_WARP: 32 host threads per warp, fg_any = a rendezvous of the lanes"""
+    so = HERE / "libfg_emu_warp.so"
+    csrc = REPO / "flowgger_b200" / "csrc"
+    srcs = [HERE / "emu_r3164.cpp", HERE / "cuda_shim.h", REPO / "include" / "flowgger_cuda.h", csrc / "fg_tz.cu"] + \
+        sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h"))
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DFG_HOST_EMU_WARP=1",
+                        "-o", str(so), str(HERE / "emu_r3164.cpp"), "-x", "c++", "-DFG_HOST_EMU=1", str(csrc / "fg_tz.cu"),
+                        "-I", str(REPO / "include")], check=True)
+    return so
+
+
+def lib_warp() -> C.CDLL:
+    global _lib_warp
+    if _lib_warp is None:
+        _lib_warp = C.CDLL(str(build_warp()))
+        _lib_warp.emu_r3164_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_char_p,
+                                               C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]
+    return _lib_warp
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
@@ -105,13 +130,15 @@ def ltsv_decode_dump(native, data: np.ndarray, offsets: np.ndarray, schema: dict
 
 
 def r3164_decode_dump(native, data: np.ndarray, offsets: np.ndarray, year: int, tile_bytes: int = 8192, strip_eol: int = 0,
-                      invalid: np.ndarray | None = None, arena_cap: int = 1 << 20, tzdir: str | None = None, lockstep: bool = True):
-    """Emulated RFC3164 decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser."""
+                      invalid: np.ndarray | None = None, arena_cap: int = 1 << 20, tzdir: str | None = None, lockstep: bool = True,
+                      warp: bool = False):
+    """Emulated RFC3164 decode -> (canonical dumps, dump offsets, info dict) through the product's host materialiser.
+    warp=True: the 32-threads-per-warp build (info gains the rendezvous counts)."""
     from flowgger_b200.native import FgBatchOut, dump_records
-    L = lib()
+    L = lib_warp() if warp else lib()
     out = FgBatchOut()
     n = len(offsets) - 1
-    info = (C.c_int32 * 3)()
+    info = (C.c_int32 * 5)()
     rc = L.emu_r3164_decode(C.c_void_p(data.ctypes.data), C.c_void_p(offsets.ctypes.data), n, tile_bytes, strip_eol,
                             C.c_void_p(invalid.ctypes.data) if invalid is not None else None, year,
                             tzdir.encode() if tzdir else None, arena_cap, 1 if lockstep else 0, C.byref(out), info)
@@ -119,9 +146,20 @@ def r3164_decode_dump(native, data: np.ndarray, offsets: np.ndarray, year: int, 
     try:
         buf, offs = dump_records(3, out, data, offsets)
         d = {"from_tile": int(info[0]), "from_global": int(info[1]), "redo": int(info[2]), "arena_bytes": int(out.arena_bytes)}
+        if warp:
+            d["vote_mismatches"], d["votes"] = int(info[3]), int(info[4])
     finally:
         L.emu_r3164_free(C.byref(out))
     return buf, offs, d
+
+
+def r3164_site_votes() -> dict[int, int]:
+    """warp build: rendezvous per source line of fg_rfc3164.cuh since the last call"""
+    L = lib_warp()
+    lines = (C.c_int32 * 256)()
+    counts = (C.c_int64 * 256)()
+    k = L.emu_r3164_site_votes(lines, counts, 256)
+    return {int(lines[i]): int(counts[i]) for i in range(k)}
 
 
 def tz_lookup(name: str, local: int, tzdir: str | None = None):

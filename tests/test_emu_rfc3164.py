@@ -137,6 +137,21 @@ def test_split_mode_terminators(emu, native, oracle):
     assert gbuf[goffs[1]:goffs[2]] == b"E:Invalid UTF-8 input;out=0" and gbuf[goffs[0]:goffs[1]] == want[0]
 
 
+def test_lockstep_convergence_in_a_32_lane_emulation(emu, native, oracle):
+    """r3164_parse_lockstep with a warp emulated as 32 concurrent host threads (tests/emu: libfg_emu_warp.so): fg_any is a
+    rendezvous of the lanes, and at every rendezvous all 32 lanes must be at the SAME vote (same source line), all must make
+    the same number of votes, and the results (arena allocation by concurrent atomics included) must equal the oracle's."""
+    lines = [l.encode() for _, _, l, _ in V.RFC3164_GOLDEN] + [l.encode() for l, _ in V.RFC3164_CASES]
+    data, offs = oracle.pack(lines)
+    d2, o2 = native.generate(native.FMT_RFC3164, 11, 1536, bad_frac=0.08)
+    for dat, off in ((data, offs), (d2, o2)):
+        gbuf, goffs, info = emu.r3164_decode_dump(native, dat, off, YEAR, warp=True)
+        obuf, ooffs = oracle.decode_dump(R3, dat, off, oracle.Rfc3164Config(YEAR))
+        assert info["vote_mismatches"] == 0 and info["votes"] > 500, info
+        assert gbuf == obuf and np.array_equal(goffs, ooffs)
+    assert sum(emu.r3164_site_votes().values()) > 10_000
+
+
 def test_zone_tables_three_way(emu, native):
     """The product's TZif reader + POSIX footer expansion + packed search (fg_tz.cu / fg_rfc3164.cuh), reached both through
     the emulation build and through the C ABI's host-side query (fg_tz_lookup in libflowgger_cuda.so), against the oracle's
