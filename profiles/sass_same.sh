@@ -9,7 +9,7 @@ cd "$(dirname "$0")/.."
 old=$(mktemp -d)
 git archive "$1" flowgger_b200/csrc include | tar -x -C "$old"
 flags="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false -cubin"
-for k in fg_parse5424 fg_parse_ltsv fg_parse_gelf fg_gelf_encode fg_split; do
+for k in fg_parse5424 fg_parse_ltsv fg_parse_gelf fg_gelf_encode fg_split $( [ -f "$old/flowgger_b200/csrc/fg_parse3164.cu" ] && echo fg_parse3164 ); do
   (cd "$old" && /usr/local/cuda/bin/nvcc $flags -o $k.old.cubin flowgger_b200/csrc/$k.cu -I include 2>/dev/null)
   /usr/local/cuda/bin/nvcc $flags -o "$old/$k.new.cubin" flowgger_b200/csrc/$k.cu -I include 2>/dev/null
   for f in old new; do
