@@ -175,3 +175,55 @@ def test_zone_tables_three_way(emu, native):
             assert native.tz_lookup(name, local) == tzread.offset_at_local(z, local), (name, local)
     for bogus in ("utc", "UTC ", "Europe", "Europe/", "Mars/Phobos", "posixrules", "localtime", "", "Z" * 40):
         assert emu.tz_lookup(bogus, 0) is None and native.tz_lookup(bogus, 0) is None, bogus
+
+
+def test_token_soup_three_way(emu, native, oracle):
+    """Lines assembled at random from the pieces the decoder distinguishes (PRI forms, years, months, days, times, zone
+    names and near misses, separators of every White_Space kind, ": " in odd places): device logic (both walkers) ==
+    C++ oracle == the independent Python restatement (oracle/pyrfc3164.py)."""
+    import random
+    import pyrfc3164
+    rnd = random.Random(31640)
+    pri = ["", "", "<13>", "<0>", "<191>", "<255>", "<256>", "<+7>", "<<5>", "<>", "<1 2>", "<13", "< 13>", "<013>"]
+    year = ["", "", "", "2020 ", "1999 ", "0001 ", "9999 ", "+2020 ", "20200 ", "202 ", "2024 ", "2023 "]
+    mon = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec", "jan", "Sept", "Au", "Aug:"]
+    day = ["1", "6", " 6", "06", "28", "29", "30", "31", "32", "0", "00", "7th", ""]
+    tm = ["11:15:24", "00:00:00", "23:59:59", "24:00:00", "23:60:00", "23:59:60", "1:15:24", "11:15", "11:15:24:", "11-15-24", "11:15:24.5"]
+    zone = ["", "", "", "UTC ", "GMT ", "Europe/Paris ", "America/New_York ", "America/Argentina/Buenos_Aires ", "utc ", "Europe/paris ",
+            "Etc/GMT-14 ", "Asia/Kolkata ", "EST5EDT ", "Zulu ", "Mars/Phobos ", "Australia/Lord_Howe ", "Europe/Paris: "]
+    host = ["host", "web-01.example.org", "h", "été", "UTC", "10.0.0.1", "host:", ""]
+    sep = [" ", " ", " ", "  ", "\t", " ", " ", "　", " \t ", "\r\n", "\x0b", "\x1f", "​"]
+    # most picks are well-formed (so that every later stage of the decoder is reached), the rest are the near misses
+    mon = mon[:12] * 5 + mon
+    day = ["1", "6", " 6", "06", "28"] * 4 + day
+    tm = ["11:15:24", "00:00:00", "23:59:59"] * 6 + tm
+    pri = ["", "<13>", "<0>", "<191>"] * 4 + pri
+    year = ["", "", "2020 ", "1999 ", "2024 "] * 3 + year
+    words = ["error", "GET", "/x", "200", "a:", ": ", "b", "naïve", "日本", "x y", "[1]", "tag[2]:", "", "\x01"]
+    lines = []
+    for _ in range(30_000):
+        kind = rnd.random()
+        date = rnd.choice(year) + rnd.choice(mon) + rnd.choice(sep) + rnd.choice(day) + rnd.choice(sep) + rnd.choice(tm)
+        msg = rnd.choice(sep if rnd.random() < 0.2 else [" "]).join(rnd.choice(words) for _ in range(rnd.randrange(0, 9)))
+        tail = rnd.choice(["", "", "", " ", "\n", " \t", " "])
+        if kind < 0.7:
+            l = rnd.choice(pri) + date + rnd.choice(sep) + rnd.choice(zone) + rnd.choice(host) + rnd.choice(sep) + msg + tail
+        elif kind < 0.95:
+            l = rnd.choice(pri) + rnd.choice(host) + rnd.choice([": ", ": ", ":", " : ", ":  "]) + date + rnd.choice(["", " "]) + rnd.choice(zone).strip() + \
+                rnd.choice([": ", ": ", ":", " :", ""]) + msg + tail
+        else:
+            l = rnd.choice(pri) + msg + tail
+        lines.append(l.encode())
+    data, offs = oracle.pack(lines)
+    check(emu, native, oracle, data, offs)
+    obuf, ooffs = oracle.decode_dump(R3, data, offs, oracle.Rfc3164Config(YEAR))
+    ok = 0
+    for i, l in enumerate(lines):
+        if b"9999" in l:
+            continue  # past the year 2400 the zone tables keep their last offset (fg_tz.h: kTzLastYear), zoneinfo keeps applying the rule
+        r = pyrfc3164.decode(l.decode(), YEAR)
+        if r is pyrfc3164.UNSUPPORTED:
+            continue
+        assert pyrfc3164.dump(r) == obuf[ooffs[i]:ooffs[i + 1]], (l, pyrfc3164.dump(r), obuf[ooffs[i]:ooffs[i + 1]])
+        ok += isinstance(r, dict)
+    assert ok > 5000  # a good share of the soup decodes
